@@ -1,0 +1,260 @@
+"""ORACLE (test infrastructure, NOT product code): ctypes binding of oracle/orb_port.cpp.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  See orb_port.cpp's header for the parity-pinning statement.
+"""
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_BUILD = _HERE / "_build"
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4")])
+assert KP_DTYPE.itemsize == 24
+
+
+def build(force=False):
+    """(Re)build liborbport.so with g++ when missing or older than its source."""
+    so = _BUILD / "liborbport.so"
+    src = _HERE / "orb_port.cpp"
+    stale = (not so.exists()) or so.stat().st_mtime < src.stat().st_mtime
+    if force or stale:
+        subprocess.check_call(["make", "-s", "-C", str(_HERE)] + (["-B"] if force else []))
+    return so
+
+
+_lib = None
+_lib_fma = None
+u8p = C.POINTER(C.c_uint8)
+
+
+def _sig(lib):
+    lib.port_create.restype = C.c_void_p
+    lib.port_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+    lib.port_destroy.argtypes = [C.c_void_p]
+    lib.port_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+    lib.port_extract.restype = C.c_int
+    lib.port_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p,
+                                 C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.port_level.restype = C.c_int
+    lib.port_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int),
+                               C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
+    lib.port_raw_count.restype = C.c_int
+    lib.port_raw_count.argtypes = [C.c_void_p, C.c_int]
+    lib.port_raw_keys.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.port_sel_count.restype = C.c_int
+    lib.port_sel_count.argtypes = [C.c_void_p, C.c_int]
+    lib.port_sel_keys.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.port_resize_linear.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_size_t]
+    lib.port_fast9.restype = C.c_int
+    lib.port_fast9.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_int]
+    lib.port_gaussian7.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t]
+    lib.port_fast_atan2.restype = C.c_float
+    lib.port_fast_atan2.argtypes = [C.c_float, C.c_float]
+    lib.port_fast_atan2_array.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib.port_cv_round.restype = C.c_int
+    lib.port_cv_round.argtypes = [C.c_float]
+    lib.port_distribute.restype = C.c_int
+    lib.port_distribute.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    lib.port_sort_nodes.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.port_ic_angle.restype = C.c_float
+    lib.port_ic_angle.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+    lib.port_descriptors.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
+    lib.port_hamming.restype = C.c_int
+    lib.port_hamming.argtypes = [C.c_void_p, C.c_void_p]
+    lib.port_knn2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int]
+    lib.port_best2_csr.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.port_stereo.restype = C.c_int
+    lib.port_stereo.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    return lib
+
+
+def lib(fma=False):
+    global _lib, _lib_fma
+    if fma:
+        if _lib_fma is None:
+            build()
+            _lib_fma = _sig(C.CDLL(str(_BUILD / "liborbport_fma.so")))
+        return _lib_fma
+    if _lib is None:
+        _lib = _sig(C.CDLL(str(build())))
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u8c(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a
+
+
+class PortExtractor:
+    """Mirror of ORB_SLAM3::ORBextractor (ORBextractor.h:43-109) on the C++ port."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, fma=False):
+        self._l = lib(fma)
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+        self._h = self._l.port_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        sc = [np.zeros(nlevels, np.float32) for _ in range(4)]
+        nf = np.zeros(nlevels, np.int32)
+        um = np.zeros(16, np.int32)
+        self._l.port_tables(self._h, _ptr(sc[0]), _ptr(sc[1]), _ptr(sc[2]), _ptr(sc[3]), _ptr(nf), _ptr(um))
+        self.scale_factors, self.inv_scale_factors, self.level_sigma2, self.inv_level_sigma2 = sc
+        self.features_per_level, self.umax = nf, um
+
+    def __del__(self):
+        try:
+            self._l.port_destroy(self._h)
+        except Exception:
+            pass
+
+    def extract(self, img, lapping=(0, 0)):
+        """-> (rc, keypoints[KP_DTYPE], descriptors[n,32] u8, mono_index); rc=-1 on an empty image."""
+        if img is None or img.size == 0:
+            return -1, np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8), 0
+        assert img.dtype == np.uint8 and img.ndim == 2 and img.strides[1] == 1
+        h, w = img.shape
+        cap = self.nfeatures + 8 * self.nlevels + 64
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n, mono = C.c_int(0), C.c_int(0)
+        rc = self._l.port_extract(self._h, _ptr(img), w, h, img.strides[0], int(lapping[0]), int(lapping[1]), _ptr(kps),
+                                  _ptr(desc), cap, C.byref(n), C.byref(mono))
+        return rc, kps[:n.value].copy(), desc[:n.value].copy(), mono.value
+
+    def level(self, level, blurred=False, bordered=False):
+        p, w, h, s = C.c_void_p(), C.c_int(), C.c_int(), C.c_size_t()
+        rc = self._l.port_level(self._h, level, int(blurred), int(bordered), C.byref(p), C.byref(w), C.byref(h), C.byref(s))
+        if rc:
+            return None
+        ww, hh = w.value, h.value
+        if bordered and not blurred:
+            ww, hh = ww + 38, hh + 38
+        buf = (C.c_uint8 * (s.value * hh)).from_address(p.value)
+        a = np.frombuffer(buf, np.uint8).reshape(hh, s.value)[:, :ww]
+        return a.copy()
+
+    def raw_keys(self, level):
+        n = self._l.port_raw_count(self._h, level)
+        a = np.zeros((n, 3), np.float32)
+        if n:
+            self._l.port_raw_keys(self._h, level, _ptr(a))
+        return a
+
+    def selected(self, level):
+        n = self._l.port_sel_count(self._h, level)
+        a = np.zeros(n, KP_DTYPE)
+        if n:
+            self._l.port_sel_keys(self._h, level, _ptr(a))
+        return a
+
+
+def resize_linear(src, dw, dh):
+    src = _u8c(src)
+    dst = np.zeros((dh, dw), np.uint8)
+    lib().port_resize_linear(_ptr(src), src.shape[1], src.shape[0], src.strides[0], _ptr(dst), dw, dh, dst.strides[0])
+    return dst
+
+
+def fast9(img, threshold):
+    img = _u8c(img)
+    cap = max(16, img.size // 2)
+    out = np.zeros((cap, 3), np.float32)
+    n = lib().port_fast9(_ptr(img), img.shape[1], img.shape[0], img.strides[0], threshold, _ptr(out), cap)
+    return out[:n].copy()
+
+
+def gaussian7(img):
+    img = _u8c(img)
+    dst = np.zeros_like(img)
+    lib().port_gaussian7(_ptr(img), img.shape[1], img.shape[0], img.strides[0], _ptr(dst), dst.strides[0])
+    return dst
+
+
+def fast_atan2(y, x):
+    y = np.ascontiguousarray(y, np.float32)
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros_like(y)
+    lib().port_fast_atan2_array(_ptr(y), _ptr(x), _ptr(out), y.size)
+    return out
+
+
+def distribute(xyr, min_x, max_x, min_y, max_y, n):
+    xyr = np.ascontiguousarray(xyr, np.float32).reshape(-1, 3)
+    cap = n + 64
+    out = np.zeros(cap, np.int32)
+    rc = lib().port_distribute(_ptr(xyr), len(xyr), min_x, max_x, min_y, max_y, n, _ptr(out), cap)
+    if rc < 0:
+        raise RuntimeError(f"port_distribute rc={rc}")
+    return out[:rc].copy()
+
+
+def sort_nodes(sizes, x0s):
+    sizes = np.ascontiguousarray(sizes, np.int32)
+    x0s = np.ascontiguousarray(x0s, np.int32)
+    perm = np.zeros(len(sizes), np.int32)
+    lib().port_sort_nodes(_ptr(sizes), _ptr(x0s), len(sizes), _ptr(perm))
+    return perm
+
+
+def ic_angle(img, x, y, umax):
+    img = _u8c(img)
+    um = np.ascontiguousarray(umax, np.int32)
+    return float(lib().port_ic_angle(_ptr(img), img.strides[0], int(x), int(y), _ptr(um)))
+
+
+def descriptors(blurred, xya, fma=False):
+    blurred = _u8c(blurred)
+    xya = np.ascontiguousarray(xya, np.float32).reshape(-1, 3)
+    d = np.zeros((len(xya), 32), np.uint8)
+    lib(fma).port_descriptors(_ptr(blurred), blurred.strides[0], _ptr(xya), len(xya), _ptr(d))
+    return d
+
+
+def hamming(a, b):
+    a = _u8c(a)
+    b = _u8c(b)
+    return lib().port_hamming(_ptr(a), _ptr(b))
+
+
+def knn2(q, db, nthreads=1):
+    q = _u8c(q)
+    db = _u8c(db)
+    idx = np.zeros((len(q), 2), np.int32)
+    dist = np.zeros((len(q), 2), np.int32)
+    lib().port_knn2(_ptr(q), len(q), _ptr(db), len(db), _ptr(idx), _ptr(dist), nthreads)
+    return idx, dist
+
+
+def best2_csr(q, train, cand, rowptr, init=256):
+    q = _u8c(q)
+    train = _u8c(train)
+    cand = np.ascontiguousarray(cand, np.int32)
+    rowptr = np.ascontiguousarray(rowptr, np.int32)
+    out = np.zeros((len(q), 4), np.int32)
+    lib().port_best2_csr(_ptr(q), len(q), _ptr(train), _ptr(cand), _ptr(rowptr), init, _ptr(out))
+    return out
+
+
+def stereo(ext_l, ext_r, kps_l, desc_l, kps_r, desc_r, bf, b):
+    """Frame::ComputeStereoMatches on the two port extractors' current pyramids.
+    -> (uRight[nL] f32, depth[nL] f32, bestR[nL] i32, sad[nL] i32, n_kept)"""
+    kl = np.ascontiguousarray(kps_l, KP_DTYPE)
+    kr = np.ascontiguousarray(kps_r, KP_DTYPE)
+    dl, dr = _u8c(desc_l), _u8c(desc_r)
+    n = len(kl)
+    ur = np.zeros(n, np.float32)
+    dp = np.zeros(n, np.float32)
+    br = np.zeros(n, np.int32)
+    sad = np.zeros(n, np.int32)
+    kept = lib().port_stereo(ext_l._h, ext_r._h, _ptr(kl), _ptr(dl), n, _ptr(kr), _ptr(dr), len(kr), bf, b, _ptr(ur),
+                             _ptr(dp), _ptr(br), _ptr(sad))
+    return ur, dp, br, sad, kept

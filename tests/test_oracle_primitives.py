@@ -1,0 +1,136 @@
+"""CPU: pin the OpenCV-free port (oracle/orb_port.cpp) against the real OpenCV primitives (python cv2) and
+the known-answer constants of SURVEY.md §8c.  These closed forms are the specification of the CUDA kernels."""
+import cv2
+import numpy as np
+import pytest
+
+from oracle import port
+from oracle import orb_ref
+from orb_slam3_ros_b200 import synth
+
+cv2.setNumThreads(1)
+
+
+def test_tables_match_survey():
+    e = port.PortExtractor(1000, 1.2, 8, 20, 7)
+    assert list(e.features_per_level) == [217, 181, 151, 126, 105, 87, 73, 60]
+    assert list(e.umax) == [15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3]
+    np.testing.assert_array_equal(
+        e.scale_factors,
+        np.array([1, 1.20000005, 1.44000006, 1.72800016, 2.07360029, 2.48832035, 2.98598456, 3.58318162], np.float32))
+    assert list(port.PortExtractor(2000, 1.2, 8, 20, 7).features_per_level) == [434, 362, 302, 251, 209, 175, 145, 122]
+    assert list(port.PortExtractor(5000, 1.2, 8, 20, 7).features_per_level) == [1086, 905, 754, 628, 524, 436, 364, 303]
+    assert list(port.PortExtractor(8000, 1.2, 12, 20, 7).features_per_level) == [1502, 1251, 1043, 869, 724, 604, 503, 419,
+                                                                                   349, 291, 243, 202]
+
+
+def test_cv_round_half_even():
+    got = [port.lib().port_cv_round(v) for v in (0.5, 1.5, 2.5, -0.5, -1.5)]
+    assert got == [0, 2, 2, 0, -2]
+
+
+@pytest.mark.parametrize("shape", [(480, 752), (376, 1241), (480, 640), (97, 131)])
+def test_resize_chain_matches_cv2(shape):
+    h, w = shape
+    img = synth.frame(h, w, 3)
+    e = port.PortExtractor(1000, 1.2, 8, 20, 7)
+    cur = img
+    for l in range(1, 8):
+        s = np.float32(e.inv_scale_factors[l])
+        lw = port.lib().port_cv_round(float(np.float32(w) * s))
+        lh = port.lib().port_cv_round(float(np.float32(h) * s))
+        want = cv2.resize(cur, (lw, lh), interpolation=cv2.INTER_LINEAR)
+        got = port.resize_linear(cur, lw, lh)
+        assert np.array_equal(want, got), f"level {l}"
+        cur = want
+
+
+def test_resize_random_sizes_matches_cv2():
+    rng = np.random.default_rng(5)
+    for _ in range(40):
+        sh, sw = int(rng.integers(8, 200)), int(rng.integers(8, 200))
+        dh, dw = int(rng.integers(4, 260)), int(rng.integers(4, 260))   # includes up-scaling (clamped taps)
+        src = rng.integers(0, 256, size=(sh, sw), dtype=np.uint8)
+        if sw == 2 * dw and sh == 2 * dh:
+            continue  # cv::resize silently switches INTER_LINEAR to INTER_AREA for exact 2x decimation
+        assert np.array_equal(cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR), port.resize_linear(src, dw, dh))
+
+
+def test_fast9_matches_cv2():
+    rng = np.random.default_rng(11)
+    for trial in range(60):
+        h, w = int(rng.integers(7, 60)), int(rng.integers(7, 60))
+        if trial % 3 == 0:
+            img = rng.integers(0, 256, size=(h, w), dtype=np.uint8)       # noise: dense, adjacent equal scores
+        elif trial % 3 == 1:
+            img = synth.frame(max(h, 16), max(w, 16), trial)[:h, :w].copy()
+        else:
+            img = (rng.integers(0, 4, size=(h, w)) * 60).astype(np.uint8)  # plateaus: ties kill each other
+        for th in (7, 20, 0, 100):
+            det = cv2.FastFeatureDetector_create(th, True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+            want = np.array([(k.pt[0], k.pt[1], k.response) for k in det.detect(img, None)], np.float32).reshape(-1, 3)
+            got = port.fast9(img, th)
+            assert np.array_equal(want, got), (trial, th, len(want), len(got))
+
+
+def test_fast9_known_corner():
+    img = np.full((7, 7), 100, np.uint8)
+    img[3, 3] = 200
+    got = port.fast9(img, 20)
+    assert got.tolist() == [[3.0, 3.0, 99.0]]          # M = 100 -> response = M - 1
+
+
+def test_gaussian7_matches_cv2():
+    rng = np.random.default_rng(2)
+    for trial in range(12):
+        h, w = int(rng.integers(8, 150)), int(rng.integers(8, 150))
+        img = rng.integers(0, 256, size=(h, w), dtype=np.uint8) if trial % 2 else synth.frame(h + 8, w + 8, trial)[:h, :w].copy()
+        want = cv2.GaussianBlur(img, (7, 7), 2, None, 2, cv2.BORDER_REFLECT_101)
+        assert np.array_equal(want, port.gaussian7(img))
+    imp = np.zeros((15, 15), np.uint8)
+    imp[7, 7] = 255
+    assert np.array_equal(cv2.GaussianBlur(imp, (7, 7), 2, None, 2, cv2.BORDER_REFLECT_101), port.gaussian7(imp))
+
+
+def test_fast_atan2_matches_cv2():
+    assert port.fast_atan2(np.float32([1]), np.float32([2]))[0] == np.float32(26.56710433959961)
+    assert port.fast_atan2(np.float32([0]), np.float32([0]))[0] == 0
+    rng = np.random.default_rng(4)
+    y = np.concatenate([rng.integers(-200000, 200000, 20000), [0, 0, 5, -5, 1, -1]]).astype(np.float32)
+    x = np.concatenate([rng.integers(-200000, 200000, 20000), [7, -7, 0, 0, 1, -1]]).astype(np.float32)
+    want = np.array([cv2.fastAtan2(float(a), float(b)) for a, b in zip(y, x)], np.float32)
+    assert np.array_equal(want, port.fast_atan2(y, x))
+
+
+def test_hamming_known_answers():
+    z = np.zeros(32, np.uint8)
+    f = np.full(32, 255, np.uint8)
+    assert port.hamming(z, f) == 256 and port.hamming(z, z) == 0
+    rng = np.random.default_rng(0)
+    a, b = rng.integers(0, 256, (2, 32), dtype=np.uint8)
+    assert port.hamming(a, b) == int(np.unpackbits(a ^ b).sum())
+
+
+def test_knn2_tie_rule_and_cv2():
+    # distances 3,1,1,2,1,1 -> (idx 1, idx 2): stable ascending = lowest train index first
+    q = np.zeros((1, 32), np.uint8)
+    tr = np.zeros((6, 32), np.uint8)
+    for i, d in enumerate([3, 1, 1, 2, 1, 1]):
+        tr[i, 0] = (1 << d) - 1
+    idx, dist = port.knn2(q, tr)
+    assert idx.tolist() == [[1, 2]] and dist.tolist() == [[1, 1]]
+    rng = np.random.default_rng(9)
+    db, qq = synth.descriptor_db(3000, 200, seed=3, dup_every=97)
+    i1, d1 = port.knn2(qq, db, nthreads=2)
+    i2, d2 = orb_ref.bf_knn2(qq, db)
+    assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
+    # fewer than two train rows -> shorter list
+    i3, d3 = port.knn2(qq[:4], db[:1])
+    i4, d4 = orb_ref.bf_knn2(qq[:4], db[:1])
+    assert np.array_equal(i3, i4) and np.array_equal(d3, d4) and (i3[:, 1] == -1).all()
+
+
+def test_matcher_constants():
+    # ORBmatcher.cc:35-37, Frame.cc:816
+    from orb_slam3_ros_b200 import constants as c
+    assert (c.TH_LOW, c.TH_HIGH, c.HISTO_LENGTH, (c.TH_HIGH + c.TH_LOW) // 2) == (50, 100, 30, 75)
