@@ -1,0 +1,176 @@
+/*
+ * orbb200.h -- C ABI of liborbb200.so: the B200 (sm_100a) ORB-SLAM3 front-end.
+ *
+ * This is the drop-in boundary for ONE hot path of giltchcity/orb_slam3_ros: ORB extraction
+ * (ORB_SLAM3::ORBextractor::operator()), rectified-stereo matching (Frame::ComputeStereoMatches) and the
+ * Hamming best / best-2 scans of ORBmatcher.  Plain C types only; no OpenCV, no torch.  The C++ adapter in
+ * orb_slam3_ros_b200/host/ (ORBextractor.h / ORBmatcher.h, namespace ORB_SLAM3) sits on top of it and keeps
+ * the reference's class interface so Frame.cc / Tracking.cc compile unchanged.
+ *
+ * Reference interfaces replaced (paths relative to the reference repository root):
+ *   orbb_create / orbb_destroy      ORBextractor::ORBextractor            orb_slam3/src/ORBextractor.cc:409-469
+ *   orbb_get_tables                 GetScaleFactors() & friends           orb_slam3/include/ORBextractor.h:61-82
+ *   orbb_extract                    ORBextractor::operator()              orb_slam3/src/ORBextractor.cc:1086-1168
+ *   orbb_pyramid_level              public member mvImagePyramid          orb_slam3/include/ORBextractor.h:84
+ *   orbb_extract_batch*             (same operator(), many frames per launch; no reference counterpart)
+ *   orbb_stereo_match               Frame::ComputeStereoMatches           orb_slam3/src/Frame.cc:811-981
+ *   orbb_hamming_distance           ORBmatcher::DescriptorDistance        orb_slam3/src/ORBmatcher.cc:2058-2074
+ *   orbb_best2_csr                  best / second-best candidate scans    orb_slam3/src/ORBmatcher.cc:77-120 (and :273-325,
+ *                                                                         :1743-1768 ...: same loop shape)
+ *   orbb_knn2 / orbb_knn2_partial   cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, 2)   orb_slam3/src/Frame.cc:1144
+ *   orbb_knn2_merge                 (top-2 merge of database shards after an all-gather; no reference counterpart)
+ *
+ * Threading: one thread per handle at a time; distinct handles are independent (own stream, own workspace).
+ * Errors: every function returns ORBB_OK (0) or a negative code; orbb_last_error() gives the text.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with ORBB_ERR_CUDA.
+ */
+#ifndef ORBB200_H
+#define ORBB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBB_OK 0
+#define ORBB_ERR_EMPTY (-1)       /* empty image: mirrors "return -1" at ORBextractor.cc:1090-1091 */
+#define ORBB_ERR_UNSUPPORTED (-2) /* geometry for which the reference itself has undefined behaviour */
+#define ORBB_ERR_CAPACITY (-3)    /* caller buffer too small */
+#define ORBB_ERR_ARG (-4)
+#define ORBB_ERR_CUDA (-5)
+#define ORBB_ERR_INTERNAL (-6)
+
+#define ORBB_MAX_LEVELS 16
+
+typedef struct orbb_extractor orbb_extractor;
+
+/* Same field order as cv::KeyPoint minus class_id (24 bytes). */
+typedef struct orbb_keypoint {
+    float x, y;     /* pt, in level-0 pixel units (already multiplied by the level's scale factor) */
+    float size;     /* (int)(31 * scale[octave])                      ORBextractor.cc:880 */
+    float angle;    /* degrees in [0,360), IC_Angle + fastAtan2        ORBextractor.cc:76-103 */
+    float response; /* FAST score (max arc minimum - 1)                 cv::FAST */
+    int32_t octave;
+} orbb_keypoint;
+
+typedef struct orbb_params {
+    int32_t nfeatures;    /* ORBextractor.nFeatures   */
+    float scale_factor;   /* ORBextractor.scaleFactor */
+    int32_t nlevels;      /* ORBextractor.nLevels  (<= ORBB_MAX_LEVELS) */
+    int32_t ini_th_fast;  /* ORBextractor.iniThFAST */
+    int32_t min_th_fast;  /* ORBextractor.minThFAST */
+    int32_t device;       /* CUDA device ordinal */
+    int32_t max_batch;    /* frames per batched launch the handle is sized for (>= 1) */
+} orbb_params;
+
+/* ---- life cycle ------------------------------------------------------------------------------------ */
+int orbb_create(const orbb_params* params, orbb_extractor** out);
+void orbb_destroy(orbb_extractor* h);
+const char* orbb_last_error(const orbb_extractor* h); /* h may be NULL: last error of a handle-less call */
+const char* orbb_version(void);
+
+/* scale / inv_scale / sigma2 / inv_sigma2: nlevels floats each; feats_per_level: nlevels ints; any may be NULL */
+int orbb_get_tables(const orbb_extractor* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                    int32_t* feats_per_level);
+/* upper bound of keypoints one frame can yield (sum over levels of N_l + slack) */
+int orbb_max_keypoints(const orbb_extractor* h);
+
+/* ---- single frame, host buffers (the call ORBextractor::operator() makes) ------------------------------------- */
+/* img: 8-bit gray, `stride` bytes per row.  kps/desc: caller buffers of `capacity` entries (desc = capacity*32 bytes).
+ * Keypoints with lap0 <= x <= lap1 are written from the back, the others from the front (ORBextractor.cc:1153-1162);
+ * *mono_index = number written at the front (the reference's return value).  Synchronous. */
+int orbb_extract(orbb_extractor* h, const uint8_t* img, int width, int height, size_t stride, int lap0, int lap1,
+                 orbb_keypoint* kps, uint8_t* desc, int capacity, int* n_out, int* mono_index);
+
+/* Pyramid level of the most recent frame (frame 0 of the most recent batch), copied to a host buffer owned by the
+ * handle (valid until the next extract call): *ptr points at the level's first pixel; the 19-pixel reflect-101 apron
+ * lies around it at negative offsets exactly like the parent buffer of the reference's mvImagePyramid[level]. */
+int orbb_pyramid_level(orbb_extractor* h, int level, const uint8_t** ptr, int* width, int* height, size_t* stride);
+
+/* ---- batched, device-resident input (throughput path) ------------------------------------------------------ */
+/* dev_imgs: device pointer; frame f, row y starts at dev_imgs + f*frame_stride + y*row_stride.  nframes <= max_batch.
+ * Asynchronous on the handle's stream; results stay on the device until fetched. */
+int orbb_extract_batch(orbb_extractor* h, const uint8_t* dev_imgs, int nframes, int width, int height, size_t row_stride,
+                       size_t frame_stride, int lap0, int lap1);
+/* Same, from HOST memory (pinned memory makes the copy asynchronous): H2D + kernels + D2H of the results into the
+ * caller's host arrays, synchronous on return.  kps: nframes*capacity entries, desc: nframes*capacity*32 bytes,
+ * counts: nframes*2 ints {n, mono_index}. */
+int orbb_extract_batch_host(orbb_extractor* h, const uint8_t* host_imgs, int nframes, int width, int height,
+                            size_t row_stride, size_t frame_stride, int lap0, int lap1, orbb_keypoint* kps, uint8_t* desc,
+                            int capacity, int32_t* counts);
+int orbb_sync(orbb_extractor* h);
+/* counts: nframes*2 ints {n, mono_index}; kps/desc laid out with `capacity` entries per frame.  Synchronises. */
+int orbb_batch_fetch(orbb_extractor* h, int nframes, orbb_keypoint* kps, uint8_t* desc, int capacity, int32_t* counts);
+/* device views of the last batch's results (per-frame stride = orbb_max_keypoints entries) */
+int orbb_batch_device_ptrs(orbb_extractor* h, const orbb_keypoint** kps, const uint8_t** desc, const int32_t** counts);
+/* number of kernels this handle launched since creation (bench.py's gpu_launches) */
+long long orbb_launch_count(const orbb_extractor* h);
+/* device milliseconds spent in each stage of the last batch (CUDA events on the handle's stream); stage names via
+ * orbb_stage_name(i); returns the number of stages written (<= cap) */
+int orbb_stage_times(orbb_extractor* h, float* ms, int cap);
+const char* orbb_stage_name(int i);
+int orbb_set_profiling(orbb_extractor* h, int enabled);
+
+/* ---- stage taps for parity tests (frame index within the last batch) ------------------------------------------- */
+/* pyramid (blurred=0) or blurred (blurred=1) level pixels -> dst[height*width] tightly packed; bordered=1 returns the
+ * (w+38)x(h+38) apron-included buffer of the un-blurred level */
+int orbb_debug_level(orbb_extractor* h, int frame, int level, int blurred, int bordered, uint8_t* dst, size_t dst_cap,
+                     int* width, int* height);
+/* vToDistributeKeys of a level (x, y relative to the 16-px border, response), in the reference's order */
+int orbb_debug_raw_keys(orbb_extractor* h, int frame, int level, float* xyr, int cap, int* n);
+/* allKeypoints[level] after DistributeOctTree, level coordinates */
+int orbb_debug_selected(orbb_extractor* h, int frame, int level, float* xyr, int cap, int* n);
+
+/* ---- stereo ---------------------------------------------------------------------------------------------------- */
+/* Frame::ComputeStereoMatches for frame `frame` of the last batches of hL (left) and hR (right), whose pyramids and
+ * keypoints/descriptors are still resident.  Outputs (host): u_right[nL], depth[nL] (-1 = no match).  bf = mbf,
+ * b = mb (Frame.cc:841-843).  Optional best_r / sad (host, may be NULL) expose the intermediate decisions. */
+int orbb_stereo_match(orbb_extractor* hL, orbb_extractor* hR, int frame, float bf, float b, float* u_right, float* depth,
+                      int32_t* best_r, int32_t* sad, int capacity, int* n_left);
+/* batched: all frames [0,nframes) of the last batch; results stay on the device (see orbb_stereo_fetch) */
+int orbb_stereo_match_batch(orbb_extractor* hL, orbb_extractor* hR, int nframes, float bf, float b);
+int orbb_stereo_fetch(orbb_extractor* hL, int nframes, float* u_right, float* depth, int capacity);
+
+/* ---- Hamming matching ----------------------------------------------------------------------------------------- */
+/* host-side 256-bit Hamming distance (a single pair never goes to the GPU) */
+int orbb_hamming_distance(const uint8_t* a, const uint8_t* b);
+
+typedef struct orbb_matcher orbb_matcher;
+int orbb_matcher_create(int device, orbb_matcher** out);
+void orbb_matcher_destroy(orbb_matcher* m);
+const char* orbb_matcher_last_error(const orbb_matcher* m);
+long long orbb_matcher_launch_count(const orbb_matcher* m);
+/* CUDA stream (cudaStream_t) the matcher launches on, for callers that time with their own events */
+void* orbb_matcher_stream(orbb_matcher* m);
+
+/* Brute-force 2-NN.  q: nq x 32 bytes, db: nd x 32 bytes.  idx2/dist2: nq x 2 (best, second); a missing neighbour is
+ * (-1, INT32_MAX).  Ties resolve to the lowest database index (cv::BFMatcher behaviour).  *_dev take device pointers
+ * and run asynchronously on the matcher's stream; the host variant copies in/out and synchronises.
+ * index_base is added to every returned index (shard offset). */
+int orbb_knn2(orbb_matcher* m, const uint8_t* q, int nq, const uint8_t* db, int64_t nd, int32_t* idx2, int32_t* dist2);
+int orbb_knn2_dev(orbb_matcher* m, const uint8_t* q_dev, int nq, const uint8_t* db_dev, int64_t nd, int32_t index_base,
+                  int32_t* idx2_dev, int32_t* dist2_dev);
+/* merge nshards per-shard results (layout [shard][nq][2], e.g. straight out of an all-gather) into the global top-2
+ * by lexicographic (distance, index); output nq x 2 */
+int orbb_knn2_merge_dev(orbb_matcher* m, const int32_t* idx_sh_dev, const int32_t* dist_sh_dev, int nshards, int nq,
+                        int32_t* idx2_dev, int32_t* dist2_dev);
+/* Lowe ratio test of Frame.cc:1151 on device results: keep[i] = (second exists) && dist0 < dist1 * ratio (double) */
+int orbb_ratio_test_dev(orbb_matcher* m, const int32_t* idx2_dev, const int32_t* dist2_dev, int nq, double ratio,
+                        uint8_t* keep_dev);
+
+/* best / second-best scan over per-query candidate lists (CSR): query i scans cand[rowptr[i]..rowptr[i+1]) (row
+ * indices into train), strict '<' in list order, both distances start at `init` (256 / TH_LOW / INT_MAX ...).
+ * out4[i] = {bestDist, bestIdx, secondDist, secondIdx} (idx -1 if none).  Host pointers; synchronous. */
+int orbb_best2_csr(orbb_matcher* m, const uint8_t* q, int nq, const uint8_t* train, int ntrain, const int32_t* cand,
+                   const int32_t* rowptr, int init, int32_t* out4);
+
+/* pinned host memory helpers (so callers without a CUDA runtime can stage asynchronously) */
+void* orbb_host_alloc(size_t bytes);
+void orbb_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBB200_H */

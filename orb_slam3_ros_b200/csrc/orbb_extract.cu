@@ -1,0 +1,1310 @@
+// liborbb200.so -- ORB extraction for B200 (sm_100a).  Hand-written CUDA; no CPU fallback.
+//
+// Replaces ORB_SLAM3::ORBextractor (reference orb_slam3/src/ORBextractor.cc) behind the C ABI of
+// include/orbb200.h.  Stages (one launch each per BATCH of frames, all on the handle's stream):
+//   k_pyr_level0 / k_pyr_resize   ComputePyramid            :1170-1195  (cv::resize fixed point + reflect-101 apron)
+//   k_fast                        per-cell cv::FAST + ini/min threshold fallback   :787-872
+//   k_octree                      DistributeOctTree         :555-779    (array-rebuild formulation, see
+//                                                                         tests/models/octree_array_model.cpp)
+//   k_blur                        cv::GaussianBlur 7x7 s=2  :1133       (8.8 fixed point)
+//   k_assemble                    output ordering / scaling / lapping split   :1105-1167
+//   k_orient_desc                 IC_Angle + fastAtan2 + computeOrbDescriptor :76-146
+//
+// Compiled with -fmad=false: the un-fused float32 result is the specification.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "introsort.cuh"
+#include "orbb_internal.cuh"
+
+namespace orbb {
+
+thread_local std::string g_lastError;
+
+int set_err(orbb_extractor* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    g_lastError = buf;
+    return code;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int p, int len) {
+    // cv::borderInterpolate(BORDER_REFLECT_101); |p| never exceeds len by more than the 19-px apron here
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p;
+    return p;
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: pyramid.  Each thread produces one aligned 4-byte word of a bordered row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pyr_level0(const Plan* __restrict__ P, Bufs B, const uint8_t* __restrict__ src,
+                                                    size_t rowStride, size_t frameStride) {
+    const LevelPlan& L = P->lv[0];
+    const int word = blockIdx.x * blockDim.x + threadIdx.x;
+    const int by = blockIdx.y;                      // bordered row 0 .. h+37
+    const int frame = blockIdx.z;
+    if (word * 4 >= L.pitch) return;
+    const int sy = reflect101(by - kEdge, L.h);
+    const uint8_t* s = src + (size_t)frame * frameStride + (size_t)sy * rowStride;
+    uint8_t out[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int ix = word * 4 + k - kRoiX;
+        out[k] = (ix >= -kEdge && ix < L.w + kEdge) ? __ldg(s + reflect101(ix, L.w)) : (uint8_t)0;
+    }
+    uint8_t* d = B.pyr + (size_t)frame * P->pyrStride + L.pyrOff + (size_t)by * L.pitch;
+    *reinterpret_cast<uchar4*>(d + word * 4) = make_uchar4(out[0], out[1], out[2], out[3]);
+}
+
+// cv::resize INTER_LINEAR 8UC1: tables hold (source index, packed int16 coefficient pair) per destination
+// column / row, computed on the host exactly as OpenCV does (build_plan).  The apron is produced in the same pass
+// by evaluating the reflected destination coordinate (copyMakeBorder BORDER_REFLECT_101 | BORDER_ISOLATED).
+__global__ void __launch_bounds__(256) k_pyr_resize(const Plan* __restrict__ P, Bufs B, int level) {
+    const LevelPlan& L = P->lv[level];
+    const LevelPlan& S = P->lv[level - 1];
+    const int word = blockIdx.x * blockDim.x + threadIdx.x;
+    const int by = blockIdx.y;
+    const int frame = blockIdx.z;
+    if (word * 4 >= L.pitch) return;
+    const uint8_t* slab = B.pyr + (size_t)frame * P->pyrStride;
+    const uint8_t* sroi = slab + S.roiOff;
+    const int2 ty = __ldg(B.tab + L.tabY + reflect101(by - kEdge, L.h));
+    const int sy0 = min(max(ty.x, 0), S.h - 1), sy1 = min(max(ty.x + 1, 0), S.h - 1);
+    const int b0 = (short)(ty.y & 0xffff), b1 = (short)(ty.y >> 16);
+    const uint8_t* r0 = sroi + (size_t)sy0 * S.pitch;
+    const uint8_t* r1 = sroi + (size_t)sy1 * S.pitch;
+    uint8_t out[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int ix = word * 4 + k - kRoiX;
+        int v = 0;
+        if (ix >= -kEdge && ix < L.w + kEdge) {
+            const int2 tx = __ldg(B.tab + L.tabX + reflect101(ix, L.w));
+            const int sx = tx.x, sx1 = min(sx + 1, S.w - 1);
+            const int a0 = (short)(tx.y & 0xffff), a1 = (short)(tx.y >> 16);
+            const int h0 = r0[sx] * a0 + r0[sx1] * a1;
+            const int h1 = r1[sx] * a0 + r1[sx1] * a1;
+            v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            v = min(max(v, 0), 255);
+        }
+        out[k] = (uint8_t)v;
+    }
+    uint8_t* d = B.pyr + (size_t)frame * P->pyrStride + L.pyrOff + (size_t)by * L.pitch;
+    *reinterpret_cast<uchar4*>(d + word * 4) = make_uchar4(out[0], out[1], out[2], out[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5a: GaussianBlur 7x7 sigma 2, OpenCV's 8.8 fixed-point path: taps {18,34,48,56,48,34,18}/256, horizontal pass
+// in 16 bit, vertical pass 32 bit, one rounding (acc + 2^15) >> 16; BORDER_REFLECT_101 at the IMAGE edge
+// (the reference blurs a clone of the level, so the pyramid apron is not used) (:1132-1133).
+// ------------------------------------------------------------------------------------------------
+constexpr int BLUR_TW = 64, BLUR_TH = 32;
+
+__global__ void __launch_bounds__(256) k_blur(const Plan* __restrict__ P, Bufs B) {
+    __shared__ uint8_t sIn[BLUR_TH + 6][BLUR_TW + 8];
+    __shared__ unsigned short sH[BLUR_TH + 6][BLUR_TW];
+    const int frame = blockIdx.y;
+    int level = 0;
+    while (level + 1 < P->nlevels && (int)blockIdx.x >= P->lv[level + 1].blurTileBase) level++;
+    const LevelPlan& L = P->lv[level];
+    if (B.selCount[frame * ORBB_MAX_LEVELS + level] == 0) return;     // :1128 levels without keypoints are skipped
+    const int t = blockIdx.x - L.blurTileBase;
+    const int tx0 = (t % L.blurTilesX) * BLUR_TW, ty0 = (t / L.blurTilesX) * BLUR_TH;
+    const uint8_t* roi = B.pyr + (size_t)frame * P->pyrStride + L.roiOff;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < (BLUR_TH + 6) * (BLUR_TW + 6); i += 256) {
+        const int r = i / (BLUR_TW + 6), c = i - r * (BLUR_TW + 6);
+        const int gy = reflect101(min(ty0 + r - 3, L.h + 2), L.h), gx = reflect101(min(tx0 + c - 3, L.w + 2), L.w);
+        sIn[r][c] = roi[(size_t)gy * L.pitch + gx];
+    }
+    __syncthreads();
+    for (int i = tid; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
+        const int r = i / BLUR_TW, c = i - r * BLUR_TW;
+        const uint8_t* p = &sIn[r][c];
+        sH[r][c] = (unsigned short)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+    }
+    __syncthreads();
+    uint8_t* out = B.blur + (size_t)frame * P->blurStride + L.blurOff;
+    for (int i = tid; i < BLUR_TH * BLUR_TW; i += 256) {
+        const int r = i / BLUR_TW, c = i - r * BLUR_TW;
+        const int gx = tx0 + c, gy = ty0 + r;
+        if (gx < L.w && gy < L.h) {
+            const unsigned acc = 18u * (sH[r][c] + sH[r + 6][c]) + 34u * (sH[r + 1][c] + sH[r + 5][c]) +
+                                 48u * (sH[r + 2][c] + sH[r + 4][c]) + 56u * sH[r + 3][c];
+            out[(size_t)gy * L.bpitch + gx] = (uint8_t)((acc + 32768u) >> 16);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: FAST-9/16 per 35-px cell with NMS and the iniTh -> minTh fallback (:805-872; cv::FAST == FAST_t<16>).
+// One CTA per cell.  Cell interiors tile the level exactly, NMS never looks across a cell border.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool has_arc9(unsigned m16) {
+    unsigned m = m16 | (m16 << 16);
+    unsigned t = m & (m >> 1);
+    t &= t >> 2;
+    t &= t >> 4;          // bit i: 8 consecutive ring pixels starting at i
+    t &= m >> 8;          // ... and the 9th
+    return (t & 0xffffu) != 0;
+}
+
+// returns max-arc-minimum - 1 (cv::FAST response) if the pixel is a corner at threshold th, else 0
+__device__ __forceinline__ int fast_score(const uint8_t* c, int th) {
+    constexpr int PS = kCellPix;
+    const int v = c[0];
+    int d[16];
+    d[0] = v - c[3 * PS];
+    d[8] = v - c[-3 * PS];
+    bool pos = (d[0] > th) | (d[8] > th), neg = (d[0] < -th) | (d[8] < -th);
+    if (!(pos | neg)) return 0;
+    d[4] = v - c[3];
+    d[12] = v - c[-3];
+    pos &= (d[4] > th) | (d[12] > th);
+    neg &= (d[4] < -th) | (d[12] < -th);
+    if (!(pos | neg)) return 0;
+    d[1] = v - c[3 * PS + 1];   d[2] = v - c[2 * PS + 2];   d[3] = v - c[PS + 3];
+    d[5] = v - c[-PS + 3];      d[6] = v - c[-2 * PS + 2];  d[7] = v - c[-3 * PS + 1];
+    d[9] = v - c[-3 * PS - 1];  d[10] = v - c[-2 * PS - 2]; d[11] = v - c[-PS - 3];
+    d[13] = v - c[PS - 3];      d[14] = v - c[2 * PS - 2];  d[15] = v - c[3 * PS - 1];
+    unsigned mp = 0, mn = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        mp |= (unsigned)(d[k] > th) << k;
+        mn |= (unsigned)(d[k] < -th) << k;
+    }
+    const bool cp = pos && has_arc9(mp), cn = neg && has_arc9(mn);
+    if (!(cp | cn)) return 0;
+    if (cn) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) d[k] = -d[k];
+    }
+    int a[16], b[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) a[k] = min(d[k], d[(k + 1) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; k++) b[k] = min(a[k], a[(k + 2) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; k++) a[k] = min(b[k], b[(k + 4) & 15]);
+    int M = -256;
+#pragma unroll
+    for (int k = 0; k < 16; k++) M = max(M, min(a[k], d[(k + 8) & 15]));
+    return M - 1;
+}
+
+__global__ void __launch_bounds__(256) k_fast(const Plan* __restrict__ P, Bufs B) {
+    __shared__ uint8_t sPix[kCellPix * kCellPix];
+    __shared__ uint8_t sScore[kCellPix * kCellPix];
+    __shared__ int sWarpCnt[8];
+    const int frame = blockIdx.y;
+    const int gcell = blockIdx.x;
+    int level = 0;
+    while (level + 1 < P->nlevels && gcell >= P->lv[level + 1].cellBase) level++;
+    const LevelPlan& L = P->lv[level];
+    const int c = gcell - L.cellBase;
+    const int ci = c / L.nCols, cj = c - ci * L.nCols;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int* cellCount = B.cellCount + (size_t)frame * P->cellsTotal + gcell;
+    const int iniX = kMinBorder + cj * L.wCell, iniY = kMinBorder + ci * L.hCell;
+    const int maxX = min(iniX + L.wCell + 6, L.maxBX), maxY = min(iniY + L.hCell + 6, L.maxBY);
+    const int rw = maxX - iniX, rh = maxY - iniY;
+    if (iniY >= L.maxBY - 3 || iniX >= L.maxBX - 6 || rw < 7 || rh < 7) {     // :810,:819 and FAST_t on a <7-px ROI
+        if (tid == 0) *cellCount = 0;
+        return;
+    }
+    const uint8_t* roi = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + (size_t)iniY * L.pitch + iniX;
+    for (int r = warp; r < rh; r += 8)
+        for (int x = lane; x < rw; x += 32) sPix[r * kCellPix + x] = roi[(size_t)r * L.pitch + x];
+    const int iw = rw - 6, ih = rh - 6, npix = iw * ih;
+    const unsigned mdiv = ((1u << 20) + iw - 1) / iw;        // p / iw == (p * mdiv) >> 20 for p < 8192
+    u64* out = B.cellKeys + (size_t)frame * P->cellKeyStride + L.cellKeyBase + (size_t)c * L.cellCap;
+    const int kx = cj * L.wCell, ky = ci * L.hCell;          // :865-866
+    int total = 0;
+    for (int pass = 0; pass < 2 && total == 0; pass++) {
+        const int th = min(max(pass == 0 ? P->iniTh : P->minTh, 0), 255);
+        __syncthreads();
+        for (int i = tid; i < rh * kCellPix; i += 256) sScore[i] = 0;
+        __syncthreads();
+        for (int p = tid; p < npix; p += 256) {
+            const int y = (int)(((unsigned)p * mdiv) >> 20), x = p - y * iw;
+            const int s = fast_score(&sPix[(y + 3) * kCellPix + x + 3], th);
+            sScore[(y + 3) * kCellPix + x + 3] = (uint8_t)s;
+        }
+        __syncthreads();
+        for (int base = 0; base < npix; base += 256) {
+            const int p = base + tid;
+            bool keep = false;
+            int x = 0, y = 0, s = 0;
+            if (p < npix) {
+                y = (int)(((unsigned)p * mdiv) >> 20);
+                x = p - y * iw + 3;
+                y += 3;
+                const uint8_t* q = &sScore[y * kCellPix + x];
+                s = q[0];
+                keep = s > 0 && s > q[-1] && s > q[1] && s > q[-kCellPix - 1] && s > q[-kCellPix] && s > q[-kCellPix + 1] &&
+                       s > q[kCellPix - 1] && s > q[kCellPix] && s > q[kCellPix + 1];
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) sWarpCnt[warp] = __popc(bal);
+            __syncthreads();
+            int woff = 0, tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                const int cnt = sWarpCnt[w];
+                woff += w < warp ? cnt : 0;
+                tot += cnt;
+            }
+            if (keep) {
+                const int pos = total + woff + __popc(bal & ((1u << lane) - 1));
+                out[pos] = (u64)(unsigned)(x + kx) | ((u64)(unsigned)(y + ky) << 16) | ((u64)(unsigned)s << 32);
+            }
+            total += tot;
+            __syncthreads();
+        }
+    }
+    if (tid == 0) *cellCount = total;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: DistributeOctTree, one CTA per (frame, level).
+// ------------------------------------------------------------------------------------------------
+constexpr int OT_THREADS = 256;
+constexpr int OT_WARPS = OT_THREADS / 32;
+constexpr int OT_SORT_SMEM = 2048;
+
+__device__ __forceinline__ int node_count(const QNode& n) { return n.cntbuf & 0x7fffffff; }
+__device__ __forceinline__ int node_buf(const QNode& n) { return (unsigned)n.cntbuf >> 31; }
+
+__device__ __forceinline__ int key_quadrant(u64 k, int mx, int my) {
+    const int x = (int)(k & 0xffff), y = (int)((k >> 16) & 0xffff);
+    return x < mx ? (y < my ? 0 : 2) : (y < my ? 1 : 3);          // :514-524
+}
+
+// ExtractorNode::DivideNode key assignment (:511-525) by one warp: stable 4-way partition of the node's key
+// segment into the other ping-pong buffer; child sizes -> *out.
+__device__ void split_node_warp(const QNode nd, u64* k0, u64* k1, int4* out, int lane) {
+    const int cnt = node_count(nd);
+    const u64* src = node_buf(nd) ? k1 : k0;
+    u64* dst = node_buf(nd) ? k0 : k1;
+    const int mx = nd.x0 + ((nd.x1 - nd.x0 + 1) >> 1);             // ceil(w/2) :482
+    const int my = nd.y0 + ((nd.y1 - nd.y0 + 1) >> 1);             // :483
+    const unsigned lt = (1u << lane) - 1;
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    if (cnt > 32) {
+        for (int base = 0; base < cnt; base += 32) {
+            const int i = base + lane;
+            const int q = i < cnt ? key_quadrant(src[nd.start + i], mx, my) : 4;
+            c0 += __popc(__ballot_sync(0xffffffffu, q == 0));
+            c1 += __popc(__ballot_sync(0xffffffffu, q == 1));
+            c2 += __popc(__ballot_sync(0xffffffffu, q == 2));
+            c3 += __popc(__ballot_sync(0xffffffffu, q == 3));
+        }
+    }
+    int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+    for (int base = 0; base < cnt; base += 32) {
+        const int i = base + lane;
+        const bool valid = i < cnt;
+        const u64 k = valid ? src[nd.start + i] : 0;
+        const int q = valid ? key_quadrant(k, mx, my) : 4;
+        const unsigned b0 = __ballot_sync(0xffffffffu, q == 0), b1 = __ballot_sync(0xffffffffu, q == 1);
+        const unsigned b2 = __ballot_sync(0xffffffffu, q == 2), b3 = __ballot_sync(0xffffffffu, q == 3);
+        if (cnt <= 32) { c0 = __popc(b0); c1 = __popc(b1); c2 = __popc(b2); c3 = __popc(b3); }
+        if (valid) {
+            const unsigned bm = q == 0 ? b0 : q == 1 ? b1 : q == 2 ? b2 : b3;
+            const int off = q == 0 ? r0 : q == 1 ? c0 + r1 : q == 2 ? c0 + c1 + r2 : c0 + c1 + c2 + r3;
+            dst[nd.start + off + __popc(bm & lt)] = k;
+        }
+        r0 += __popc(b0); r1 += __popc(b1); r2 += __popc(b2); r3 += __popc(b3);
+    }
+    if (lane == 0) *out = make_int4(c0, c1, c2, c3);
+}
+
+// child q (0..3 = n1..n4, :486-507) of parent p given the four child sizes
+__device__ __forceinline__ QNode make_child(const QNode& p, const int4 c, int q) {
+    const int mx = p.x0 + ((p.x1 - p.x0 + 1) >> 1), my = p.y0 + ((p.y1 - p.y0 + 1) >> 1);
+    QNode n;
+    n.x0 = (q & 1) ? (short)mx : p.x0;
+    n.x1 = (q & 1) ? p.x1 : (short)mx;
+    n.y0 = (q & 2) ? (short)my : p.y0;
+    n.y1 = (q & 2) ? p.y1 : (short)my;
+    const int cnt = q == 0 ? c.x : q == 1 ? c.y : q == 2 ? c.z : c.w;
+    n.start = p.start + (q > 0 ? c.x : 0) + (q > 1 ? c.y : 0) + (q > 2 ? c.z : 0);
+    n.cntbuf = cnt | ((node_buf(p) ^ 1) << 31);
+    return n;
+}
+
+// Emit the children of one split node into the next node array.  `firstCreate` = creation index of its first
+// non-empty child; creation index j lives at list position T-1-j (children are push_front'ed, :639-675);
+// children with >1 keys are appended to the pending list (vSizeAndPointerToNode) in creation order.
+__device__ __forceinline__ void emit_children(const QNode& p, const int4 c, int T, int firstCreate, int firstPend,
+                                              QNode* next, int* pendNext) {
+    int j = firstCreate, e = firstPend;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int cnt = q == 0 ? c.x : q == 1 ? c.y : q == 2 ? c.z : c.w;
+        if (cnt > 0) {
+            next[T - 1 - j] = make_child(p, c, q);
+            if (cnt > 1) pendNext[e++] = T - 1 - j;
+            j++;
+        }
+    }
+}
+
+__device__ __forceinline__ int nonempty4(const int4 c) { return (c.x > 0) + (c.y > 0) + (c.z > 0) + (c.w > 0); }
+__device__ __forceinline__ int multi4(const int4 c) { return (c.x > 1) + (c.y > 1) + (c.z > 1) + (c.w > 1); }
+
+__global__ void __launch_bounds__(OT_THREADS) k_octree(const Plan* __restrict__ P, Bufs B) {
+    const int level = blockIdx.x, frame = blockIdx.y;
+    const LevelPlan& L = P->lv[level];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = L.nFeat;
+
+    const int* cellCount = B.cellCount + (size_t)frame * P->cellsTotal + L.cellBase;
+    int* cellOff = B.cellOff + (size_t)frame * P->cellsTotal + L.cellBase;
+    const u64* cellKeys = B.cellKeys + (size_t)frame * P->cellKeyStride + L.cellKeyBase;
+    u64* k0 = B.keys + ((size_t)frame * 2 + 0) * P->rawStride + L.rawBase;
+    u64* k1 = B.keys + ((size_t)frame * 2 + 1) * P->rawStride + L.rawBase;
+    QNode* nodesAB[2] = {B.nodes + ((size_t)frame * 2 + 0) * P->nodeStride + L.nodeBase,
+                         B.nodes + ((size_t)frame * 2 + 1) * P->nodeStride + L.nodeBase};
+    int* pendAB[2] = {B.pend + ((size_t)frame * 2 + 0) * P->nodeStride + L.nodeBase,
+                      B.pend + ((size_t)frame * 2 + 1) * P->nodeStride + L.nodeBase};
+    u64* rec = B.rec + (size_t)frame * P->nodeStride + L.nodeBase;
+    int4* cnt4 = B.cnt4 + (size_t)frame * P->nodeStride + L.nodeBase;
+    int* elist = B.elist + (size_t)frame * P->nodeStride + L.nodeBase;
+    uint8_t* erased = B.erased + (size_t)frame * P->nodeStride + L.nodeBase;
+
+    __shared__ int sN, sNodes, sPend, sM, sFinish, sPhase2, sCur, sPcur;
+    __shared__ int sSlotCnt[kMaxIni], sSlotStart[kMaxIni];
+    __shared__ int sWarpSlot[OT_WARPS][kMaxIni];
+    __shared__ u64 sRec[OT_SORT_SMEM];
+
+    // ---- 1. gather vToDistributeKeys in the reference's order: cell-row-major, raster inside the cell ----
+    const int nCells = L.nCols * L.nRows;
+    if (warp == 0) {
+        int run = 0;
+        for (int base = 0; base < nCells; base += 32) {
+            const int c = base + lane;
+            const int v = c < nCells ? cellCount[c] : 0;
+            const int inc = warp_incl_scan(v, lane);
+            if (c < nCells) cellOff[c] = run + inc - v;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) sN = run;
+    }
+    if (tid < kMaxIni) sSlotCnt[tid] = 0;
+    __syncthreads();
+    const int n = sN;
+    for (int c = warp; c < nCells; c += OT_WARPS) {
+        const int cnt = cellCount[c], off = cellOff[c];
+        for (int i = lane; i < cnt; i += 32) k0[off + i] = cellKeys[(size_t)c * L.cellCap + i];
+    }
+    __syncthreads();
+
+    // ---- 2. root nodes (:559-601): keys bucketed by (int)(x / hX), stable ----
+    const int nIni = L.nIni;
+    const float hX = L.hX;
+    int rootBuf = 0;
+    if (nIni > 1) {
+        rootBuf = 1;
+        for (int i = tid; i < n; i += OT_THREADS) {
+            int s = __float2int_rz(__fdiv_rn((float)(int)(k0[i] & 0xffff), hX));
+            atomicAdd(&sSlotCnt[min(s, nIni - 1)], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int acc = 0;
+            for (int s = 0; s < nIni; s++) { sSlotStart[s] = acc; acc += sSlotCnt[s]; }
+        }
+        __syncthreads();
+        int runSlot[kMaxIni];
+#pragma unroll
+        for (int s = 0; s < kMaxIni; s++) runSlot[s] = 0;
+        for (int base = 0; base < n; base += OT_THREADS) {
+            const int i = base + tid;
+            const bool valid = i < n;
+            const u64 k = valid ? k0[i] : 0;
+            const int slot = valid ? min(__float2int_rz(__fdiv_rn((float)(int)(k & 0xffff), hX)), nIni - 1) : -1;
+            int myRank = 0;
+            for (int s = 0; s < nIni; s++) {
+                const unsigned bal = __ballot_sync(0xffffffffu, slot == s);
+                if (lane == 0) sWarpSlot[warp][s] = __popc(bal);
+                if (slot == s) myRank = __popc(bal & ((1u << lane) - 1));
+            }
+            __syncthreads();
+            if (valid) {
+                int woff = 0;
+                for (int w = 0; w < warp; w++) woff += sWarpSlot[w][slot];
+                k1[sSlotStart[slot] + runSlot[slot] + woff + myRank] = k;
+            }
+            for (int s = 0; s < nIni; s++) {
+                int tot = 0;
+                for (int w = 0; w < OT_WARPS; w++) tot += sWarpSlot[w][s];
+                runSlot[s] += tot;
+            }
+            __syncthreads();
+        }
+    } else if (tid == 0) {
+        sSlotCnt[0] = n;
+        sSlotStart[0] = 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int m = 0;
+        for (int s = 0; s < nIni; s++) {
+            if (sSlotCnt[s] == 0) continue;                               // :597-598 empty roots are erased
+            QNode r;
+            r.x0 = (short)__float2int_rz(__fmul_rn(hX, (float)s));        // :571
+            r.x1 = (short)__float2int_rz(__fmul_rn(hX, (float)(s + 1)));  // :572
+            r.y0 = 0;
+            r.y1 = (short)(L.maxBY - kMinBorder);                         // :573
+            r.start = sSlotStart[s];
+            r.cntbuf = sSlotCnt[s] | (rootBuf << 31);
+            nodesAB[0][m++] = r;
+        }
+        sNodes = m; sCur = 0; sPcur = 0; sPend = 0; sFinish = 0; sPhase2 = 0;
+    }
+    __syncthreads();
+
+    // ---- 3. main loop (:610-755) ----
+    while (true) {
+        if (sFinish) break;
+        const int cur = sCur, pcur = sPcur;
+        QNode* nodes = nodesAB[cur];
+        QNode* next = nodesAB[cur ^ 1];
+        int* pendCur = pendAB[pcur];
+        int* pendNext = pendAB[pcur ^ 1];
+        const int nNodes = sNodes;
+        const bool phase2 = sPhase2 != 0;
+        __syncthreads();           // everyone has read the shared state before warp 0 rewrites it
+
+        if (!phase2) {
+            // ---------- phase 1: split every node that holds more than one key, in list order (:622-681) ----------
+            if (warp == 0) {
+                int run = 0;
+                for (int base = 0; base < nNodes; base += 32) {
+                    const int i = base + lane;
+                    const bool ex = i < nNodes && node_count(nodes[i]) > 1;
+                    const unsigned bal = __ballot_sync(0xffffffffu, ex);
+                    if (ex) elist[run + __popc(bal & ((1u << lane) - 1))] = i;
+                    run += __popc(bal);
+                }
+                if (lane == 0) sM = run;
+            }
+            __syncthreads();
+            const int m = sM;
+            if (m == 0) break;                                      // size == prevSize (:685)
+            for (int e = warp; e < m; e += OT_WARPS) split_node_warp(nodes[elist[e]], k0, k1, &cnt4[elist[e]], lane);
+            __syncthreads();
+            if (warp == 0) {
+                int T = 0, X = 0;
+                for (int base = 0; base < m; base += 32) {
+                    const int e = base + lane;
+                    int4 c = make_int4(0, 0, 0, 0);
+                    if (e < m) c = cnt4[elist[e]];
+                    T += nonempty4(c);
+                    X += multi4(c);
+                }
+                T = warp_sum(T);
+                X = warp_sum(X);
+                int runC = 0, runE = 0;
+                for (int base = 0; base < m; base += 32) {
+                    const int e = base + lane;
+                    int4 c = make_int4(0, 0, 0, 0);
+                    int idx = 0;
+                    if (e < m) { idx = elist[e]; c = cnt4[idx]; }
+                    const int nc = nonempty4(c), ne = multi4(c);
+                    const int incC = warp_incl_scan(nc, lane), incE = warp_incl_scan(ne, lane);
+                    if (e < m) emit_children(nodes[idx], c, T, runC + incC - nc, runE + incE - ne, next, pendNext);
+                    runC += __shfl_sync(0xffffffffu, incC, 31);
+                    runE += __shfl_sync(0xffffffffu, incE, 31);
+                }
+                int runK = 0;                                       // single-key nodes keep their relative order
+                for (int base = 0; base < nNodes; base += 32) {
+                    const int i = base + lane;
+                    QNode nd;
+                    bool keep = false;
+                    if (i < nNodes) { nd = nodes[i]; keep = node_count(nd) == 1; }
+                    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                    if (keep) next[T + runK + __popc(bal & ((1u << lane) - 1))] = nd;
+                    runK += __popc(bal);
+                }
+                if (lane == 0) {
+                    const int newSize = T + (nNodes - m);
+                    sNodes = newSize; sPend = X; sCur = cur ^ 1; sPcur = pcur ^ 1;
+                    if (newSize >= N || newSize == nNodes) sFinish = 1;             // :685
+                    else if (newSize + X * 3 > N) sPhase2 = 1;                      // :689
+                }
+            }
+            __syncthreads();
+        } else {
+            // ---------- phase 2: sort the pending nodes, split from the back until N nodes exist (:692-753) ----------
+            const int len = sPend;
+            u64* srt = len <= OT_SORT_SMEM ? sRec : rec;
+            for (int i = tid; i < nNodes; i += OT_THREADS) erased[i] = 0;
+            for (int e = warp; e < len; e += OT_WARPS) {
+                const int idx = pendCur[e];
+                const QNode nd = nodes[idx];
+                split_node_warp(nd, k0, k1, &cnt4[idx], lane);
+                if (lane == 0)
+                    srt[e] = ((u64)(unsigned)node_count(nd) << 40) | ((u64)(unsigned short)nd.x0 << 24) | (u64)(unsigned)idx;
+            }
+            __syncthreads();
+            if (tid == 0) std_sort_emul(srt, len);                  // std::sort(..., compareNodes) :700
+            __syncthreads();
+            if (warp == 0) {
+                // processing order i = 0..len-1 is the sorted vector walked from the back (:701)
+                int kstar = len, run = 0;
+                for (int base = 0; base < len && kstar == len; base += 32) {
+                    const int i = base + lane;
+                    int g = 0;
+                    if (i < len) g = nonempty4(cnt4[(int)(srt[len - 1 - i] & 0xffffff)]) - 1;
+                    const int inc = warp_incl_scan(g, lane);
+                    const unsigned bal = __ballot_sync(0xffffffffu, i < len && nNodes + run + inc >= N);   // :746
+                    if (bal) kstar = base + __ffs(bal);             // number of nodes split before the break
+                    run += __shfl_sync(0xffffffffu, inc, 31);
+                }
+                int T = 0, X = 0;
+                for (int base = 0; base < kstar; base += 32) {
+                    const int i = base + lane;
+                    int4 c = make_int4(0, 0, 0, 0);
+                    if (i < kstar) c = cnt4[(int)(srt[len - 1 - i] & 0xffffff)];
+                    T += nonempty4(c);
+                    X += multi4(c);
+                }
+                T = warp_sum(T);
+                X = warp_sum(X);
+                int runC = 0, runE = 0;
+                for (int base = 0; base < kstar; base += 32) {
+                    const int i = base + lane;
+                    int4 c = make_int4(0, 0, 0, 0);
+                    int idx = 0;
+                    if (i < kstar) { idx = (int)(srt[len - 1 - i] & 0xffffff); c = cnt4[idx]; erased[idx] = 1; }
+                    const int nc = nonempty4(c), ne = multi4(c);
+                    const int incC = warp_incl_scan(nc, lane), incE = warp_incl_scan(ne, lane);
+                    if (i < kstar) emit_children(nodes[idx], c, T, runC + incC - nc, runE + incE - ne, next, pendNext);
+                    runC += __shfl_sync(0xffffffffu, incC, 31);
+                    runE += __shfl_sync(0xffffffffu, incE, 31);
+                }
+                __syncwarp();
+                int runK = 0;
+                for (int base = 0; base < nNodes; base += 32) {
+                    const int i = base + lane;
+                    QNode nd;
+                    bool keep = false;
+                    if (i < nNodes) { nd = nodes[i]; keep = !erased[i]; }
+                    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                    if (keep) next[T + runK + __popc(bal & ((1u << lane) - 1))] = nd;
+                    runK += __popc(bal);
+                }
+                if (lane == 0) {
+                    const int newSize = T + (nNodes - kstar);
+                    sNodes = newSize; sPend = X; sCur = cur ^ 1; sPcur = pcur ^ 1;
+                    if (newSize >= N || newSize == nNodes) sFinish = 1;             // :750
+                }
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+
+    // ---- 4. best key of every node, first maximum wins (:757-776); +16 border offset (:886-887) ----
+    const QNode* fin = nodesAB[sCur];
+    const int nOut = sNodes;
+    u64* sel = B.sel + (size_t)frame * P->selStride + L.selBase;
+    for (int i = tid; i < nOut && i < L.selCap; i += OT_THREADS) {
+        const QNode nd = fin[i];
+        const u64* src = (node_buf(nd) ? k1 : k0) + nd.start;
+        u64 best = src[0];
+        const int cnt = node_count(nd);
+        for (int k = 1; k < cnt; k++) {
+            const u64 v = src[k];
+            if ((unsigned)(v >> 32) > (unsigned)(best >> 32)) best = v;
+        }
+        sel[i] = best + (u64)kMinBorder + ((u64)kMinBorder << 16);
+    }
+    if (tid == 0) {
+        B.selCount[frame * ORBB_MAX_LEVELS + level] = min(nOut, L.selCap);
+        if (nOut > L.selCap) atomicOr(&B.status[frame], 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: output assembly (:1105-1167): level-major order, pt *= scale for level > 0, keypoints inside the lapping
+// area are written from the back, the others from the front.  One CTA per frame.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_assemble(const Plan* __restrict__ P, Bufs B, int lap0, int lap1) {
+    const int frame = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int sOff[ORBB_MAX_LEVELS + 1];
+    __shared__ int sWarp[8];
+    if (tid == 0) {
+        int acc = 0;
+        for (int l = 0; l < P->nlevels; l++) { sOff[l] = acc; acc += B.selCount[frame * ORBB_MAX_LEVELS + l]; }
+        sOff[P->nlevels] = acc;
+    }
+    __syncthreads();
+    const int n = min(sOff[P->nlevels], P->kpCap);
+    orbb_keypoint* kps = B.kps + (size_t)frame * P->kpCap;
+    WorkItem* work = B.work + (size_t)frame * P->kpCap;
+    const float fl0 = (float)lap0, fl1 = (float)lap1;
+    int stereoRun = 0;
+    for (int base = 0; base < n; base += 256) {
+        const int g = base + tid;
+        bool valid = g < n, st = false;
+        int level = 0, x = 0, y = 0;
+        float xs = 0, ys = 0, resp = 0;
+        if (valid) {
+            while (g >= sOff[level + 1]) level++;
+            const LevelPlan& L = P->lv[level];
+            const u64 k = B.sel[(size_t)frame * P->selStride + L.selBase + (g - sOff[level])];
+            x = (int)(k & 0xffff); y = (int)((k >> 16) & 0xffff); resp = (float)(int)(k >> 32);
+            xs = (float)x; ys = (float)y;
+            if (level != 0) { xs = __fmul_rn(xs, L.scale); ys = __fmul_rn(ys, L.scale); }     // :1149-1151
+            st = xs >= fl0 && xs <= fl1;                                                       // :1153
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, st);
+        if (lane == 0) sWarp[warp] = __popc(bal);
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { woff += w < warp ? sWarp[w] : 0; tot += sWarp[w]; }
+        if (valid) {
+            const int stBefore = stereoRun + woff + __popc(bal & ((1u << lane) - 1));
+            const int pos = st ? n - 1 - stBefore : g - stBefore;
+            orbb_keypoint kp;
+            kp.x = xs; kp.y = ys; kp.size = P->lv[level].kpSize; kp.angle = -1.f; kp.response = resp; kp.octave = level;
+            kps[pos] = kp;
+            work[g] = WorkItem{level, x, y, pos};
+        }
+        stereoRun += tot;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        B.outCount[frame * 2] = n;
+        B.outCount[frame * 2 + 1] = n - stereoRun;
+        if (sOff[P->nlevels] > P->kpCap) atomicOr(&B.status[frame], 2);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 + K5b: one warp per keypoint -- IC_Angle over the umax disc (:76-103), cv::fastAtan2 (un-fused float32),
+// then the 256 steered rBRIEF tests on the blurred level (:107-146).
+// ------------------------------------------------------------------------------------------------
+struct PatternT { signed char v[8][32][4]; };      // [test-in-byte][byte][x0,y0,x1,y1] -> conflict-free per lane
+__constant__ signed char cPattern[256][4] = {
+#include "orb_pattern.inc"
+};
+
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    // cv::fastAtan2 scalar path; p-coefficients are the float products OpenCV stores
+    const float sc = (float)(180.0 / 3.141592653589793238462643383279502884197);
+    const float p1 = 0.9997878412794807f * sc, p3 = -0.3258083974640975f * sc;
+    const float p5 = 0.1555786518463281f * sc, p7 = -0.04432655554792128f * sc;
+    const float eps = (float)2.2204460492503131e-16;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+__global__ void __launch_bounds__(256) k_orient_desc(const Plan* __restrict__ P, Bufs B) {
+    __shared__ signed char sPat[8][32][4];
+    const int frame = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {   // transpose the pattern so that lane i (descriptor byte i) reads test j at [j][i]
+        const int i = tid >> 3, j = tid & 7;       // byte i, test j  <- pattern row 8*i + j
+#pragma unroll
+        for (int k = 0; k < 4; k++) sPat[j][i][k] = cPattern[8 * i + j][k];
+    }
+    __syncthreads();
+    const int n = B.outCount[frame * 2];
+    const int g = blockIdx.x * 8 + warp;
+    if (g >= n) return;
+    const WorkItem wi = B.work[(size_t)frame * P->kpCap + g];
+    const LevelPlan& L = P->lv[wi.level];
+    // ---- IC_Angle: lane u-15 covers column u of every row of the disc ----
+    const uint8_t* center = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + (size_t)wi.y * L.pitch + wi.x;
+    const int u = lane - 15;
+    int m10 = 0, m01 = 0;
+#pragma unroll 1
+    for (int v = -15; v <= 15; v++) {
+        const int d = P->umax[v < 0 ? -v : v];
+        if (lane < 31 && u >= -d && u <= d) {
+            const int val = center[v * L.pitch + u];
+            m10 += u * val;
+            m01 += v * val;
+        }
+    }
+    m10 = warp_sum(m10);
+    m01 = warp_sum(m01);
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+    orbb_keypoint* kp = B.kps + (size_t)frame * P->kpCap + wi.pos;
+    if (lane == 0) kp->angle = angle;
+    // ---- steered BRIEF on the blurred level ----
+    const float factorPI = (float)(3.141592653589793238462643383279502884197 / 180.f);     // :106
+    const float rad = __fmul_rn(angle, factorPI);
+    const float a = (float)cos((double)rad), b = (float)sin((double)rad);                  // :112 (correctly rounded)
+    const uint8_t* bc = B.blur + (size_t)frame * P->blurStride + L.blurOff + (size_t)wi.y * L.bpitch + wi.x;
+    const int step = L.bpitch;
+    unsigned val = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const char4 pt = *reinterpret_cast<const char4*>(&sPat[j][lane][0]);
+        const float x0 = (float)pt.x, y0 = (float)pt.y, x1 = (float)pt.z, y1 = (float)pt.w;
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));      // :118
+        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));      // :119
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int t0 = bc[r0 * step + c0], t1 = bc[r1 * step + c1];
+        val |= (unsigned)(t0 < t1) << j;
+    }
+    B.desc[((size_t)frame * P->kpCap + wi.pos) * 32 + lane] = (uint8_t)val;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static inline int cv_round_f(float v) { return (int)lrintf(v); }
+static inline int cv_floor_f(float v) { int i = (int)v; return i - (i > v); }
+static inline int cv_ceil_f(float v) { int i = (int)v; return i + (i < v); }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ORBextractor::ORBextractor (:409-469): scale tables, features per level, umax
+static void build_tables(orbb_extractor* h) {
+    const int nl = h->prm.nlevels;
+    const double scaleFactor = (double)h->prm.scale_factor;      // the member is a double initialised from a float
+    h->scale.assign(nl, 1.f); h->sigma2.assign(nl, 1.f); h->invScale.assign(nl, 1.f); h->invSigma2.assign(nl, 1.f);
+    for (int i = 1; i < nl; i++) {
+        h->scale[i] = (float)(h->scale[i - 1] * scaleFactor);
+        h->sigma2[i] = h->scale[i] * h->scale[i];
+    }
+    for (int i = 0; i < nl; i++) { h->invScale[i] = 1.0f / h->scale[i]; h->invSigma2[i] = 1.0f / h->sigma2[i]; }
+    h->featPerLevel.assign(nl, 0);
+    float factor = (float)(1.0f / scaleFactor);
+    float nDesired = (float)(h->prm.nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nl)));
+    int sum = 0;
+    for (int l = 0; l < nl - 1; l++) {
+        h->featPerLevel[l] = cv_round_f(nDesired);
+        sum += h->featPerLevel[l];
+        nDesired *= factor;
+    }
+    h->featPerLevel[nl - 1] = std::max(h->prm.nfeatures - sum, 0);
+    const int HP = 15;
+    int v, v0, vmax = cv_floor_f(HP * sqrtf(2.f) / 2 + 1), vmin = cv_ceil_f(HP * sqrtf(2.f) / 2);
+    const double hp2 = HP * HP;
+    for (v = 0; v <= vmax; ++v) h->umax[v] = (int)lrint(sqrt(hp2 - v * v));
+    for (v = HP, v0 = 0; v >= vmin; --v) {
+        while (h->umax[v0] == h->umax[v0 + 1]) ++v0;
+        h->umax[v] = v0;
+        ++v0;
+    }
+}
+
+static void free_bufs(orbb_extractor* h) {
+    for (void* p : h->allocs) cudaFree(p);
+    h->allocs.clear();
+    memset(&h->b, 0, sizeof h->b);
+    h->capacity = 0;
+    h->planValid = false;
+}
+
+template <typename T>
+static int dev_alloc(orbb_extractor* h, T** p, size_t count) {
+    void* q = nullptr;
+    ORBB_CUDA(h, cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    h->allocs.push_back(q);
+    *p = (T*)q;
+    return ORBB_OK;
+}
+
+// Geometry of every level for a WxH input + the cv::resize coefficient tables (imgproc/resize.cpp).
+static int build_plan(orbb_extractor* h, int W, int H, int frames) {
+    free_bufs(h);
+    Plan& P = h->plan;
+    memset(&P, 0, sizeof P);
+    const int nl = h->prm.nlevels;
+    P.nlevels = nl; P.W = W; P.H = H;
+    P.iniTh = h->prm.ini_th_fast; P.minTh = h->prm.min_th_fast;
+    for (int i = 0; i < 16; i++) P.umax[i] = h->umax[i];
+    std::vector<int2> tab;
+    size_t pyrBytes = 0, blurBytes = 0;
+    unsigned cellKeys = 0, raw = 0, nodes = 0, sel = 0;
+    int cells = 0, tiles = 0, kpCap = 0;
+    for (int l = 0; l < nl; l++) {
+        LevelPlan& L = P.lv[l];
+        L.w = cv_round_f((float)W * h->invScale[l]);                 // :1175
+        L.h = cv_round_f((float)H * h->invScale[l]);
+        if (L.w > 32767 || L.h > 32767) return set_err(h, ORBB_ERR_UNSUPPORTED, "image too large (%dx%d)", W, H);
+        L.pitch = (int)align_up(kRoiX + L.w + kEdge, 128);
+        L.pyrOff = (unsigned)pyrBytes;
+        L.roiOff = L.pyrOff + kEdge * L.pitch + kRoiX;
+        pyrBytes += align_up((size_t)L.pitch * (L.h + 2 * kEdge), 256);
+        L.bpitch = (int)align_up(L.w, 128);
+        L.blurOff = (unsigned)blurBytes;
+        blurBytes += align_up((size_t)L.bpitch * L.h, 256);
+        // FAST cell grid (:789-803)
+        L.maxBX = L.w - kEdge + 3; L.maxBY = L.h - kEdge + 3;
+        const float width = (float)(L.maxBX - kMinBorder), height = (float)(L.maxBY - kMinBorder);
+        L.nCols = (int)(width / 35.f); L.nRows = (int)(height / 35.f);
+        if (L.nCols <= 0 || L.nRows <= 0)
+            return set_err(h, ORBB_ERR_UNSUPPORTED, "level %d (%dx%d) is smaller than one 35-px FAST cell: the reference divides by zero here", l, L.w, L.h);
+        L.wCell = (int)ceilf(width / L.nCols); L.hCell = (int)ceilf(height / L.nRows);
+        if (L.wCell + 6 > kCellPix || L.hCell + 6 > kCellPix) return set_err(h, ORBB_ERR_UNSUPPORTED, "cell %dx%d exceeds the kernel's tile", L.wCell, L.hCell);
+        L.cellBase = cells;
+        L.cellCap = ((L.wCell + 1) / 2) * ((L.hCell + 1) / 2);      // NMS survivors are never 8-adjacent
+        L.cellKeyBase = cellKeys;
+        cells += L.nCols * L.nRows;
+        cellKeys += (unsigned)(L.nCols * L.nRows * L.cellCap);
+        // quadtree (:559-561)
+        L.nFeat = h->featPerLevel[l];
+        L.nIni = (int)roundf((float)(L.maxBX - kMinBorder) / (L.maxBY - kMinBorder));
+        if (L.nIni <= 0 || L.nIni > kMaxIni)
+            return set_err(h, ORBB_ERR_UNSUPPORTED, "level %d aspect ratio gives %d root nodes (reference: undefined behaviour for 0)", l, L.nIni);
+        L.hX = (float)(L.maxBX - kMinBorder) / L.nIni;
+        L.rawBase = raw; L.rawCap = L.nCols * L.nRows * L.cellCap; raw += (unsigned)L.rawCap;
+        L.maxNodes = std::max(L.nFeat + 2, 4 * L.nIni) + 6;
+        L.nodeBase = nodes; nodes += (unsigned)L.maxNodes;
+        L.selBase = sel; L.selCap = L.maxNodes; sel += (unsigned)L.selCap;
+        kpCap += L.selCap;
+        L.scale = h->scale[l];
+        L.kpSize = (float)(int)(31 * h->scale[l]);                   // :880 (PATCH_SIZE*mvScaleFactor -> int)
+        L.blurTilesX = (L.w + BLUR_TW - 1) / BLUR_TW; L.blurTilesY = (L.h + BLUR_TH - 1) / BLUR_TH;
+        L.blurTileBase = tiles; tiles += L.blurTilesX * L.blurTilesY;
+        // cv::resize tables for level l from level l-1
+        if (l > 0) {
+            const LevelPlan& S = P.lv[l - 1];
+            const double inv_sx = (double)L.w / S.w, inv_sy = (double)L.h / S.h;
+            const double scale_x = 1. / inv_sx, scale_y = 1. / inv_sy;
+            L.tabX = (int)tab.size();
+            for (int dx = 0; dx < L.w; dx++) {
+                float fx = (float)((dx + 0.5) * scale_x - 0.5);
+                int sx = cv_floor_f(fx);
+                fx -= sx;
+                if (sx < 0) { fx = 0; sx = 0; }
+                if (sx >= S.w - 1) { fx = 0; sx = S.w - 1; }
+                const short a0 = (short)cv_round_f((1.f - fx) * 2048.f), a1 = (short)cv_round_f(fx * 2048.f);
+                tab.push_back(make_int2(sx, (int)((unsigned short)a0 | ((unsigned)(unsigned short)a1 << 16))));
+            }
+            L.tabY = (int)tab.size();
+            for (int dy = 0; dy < L.h; dy++) {
+                float fy = (float)((dy + 0.5) * scale_y - 0.5);
+                int sy = cv_floor_f(fy);
+                fy -= sy;
+                const short b0 = (short)cv_round_f((1.f - fy) * 2048.f), b1 = (short)cv_round_f(fy * 2048.f);
+                tab.push_back(make_int2(sy, (int)((unsigned short)b0 | ((unsigned)(unsigned short)b1 << 16))));
+            }
+        }
+    }
+    P.cellsTotal = cells; P.blurTilesTotal = tiles; P.kpCap = kpCap;
+    P.pyrStride = pyrBytes; P.blurStride = blurBytes;
+    P.cellKeyStride = cellKeys; P.rawStride = raw; P.nodeStride = nodes; P.selStride = sel;
+
+    Bufs& b = h->b;
+    const size_t F = (size_t)frames;
+    int rc;
+#define A(ptr, count) if ((rc = dev_alloc(h, &ptr, (count))) != ORBB_OK) return rc
+    A(b.pyr, F * pyrBytes);
+    A(b.blur, F * blurBytes);
+    A(b.tab, tab.size());
+    A(b.cellCount, F * cells);
+    A(b.cellOff, F * cells);
+    A(b.cellKeys, F * cellKeys);
+    A(b.keys, F * 2 * raw);
+    A(b.nodes, F * 2 * nodes);
+    A(b.rec, F * nodes);
+    A(b.cnt4, F * nodes);
+    A(b.pend, F * 2 * nodes);
+    A(b.elist, F * nodes);
+    A(b.erased, F * nodes);
+    A(b.sel, F * sel);
+    A(b.selCount, F * ORBB_MAX_LEVELS);
+    A(b.work, F * kpCap);
+    A(b.kps, F * kpCap);
+    A(b.desc, F * kpCap * 32);
+    A(b.outCount, F * 2);
+    A(b.status, F);
+    A(b.uRight, F * kpCap);
+    A(b.depth, F * kpCap);
+    A(b.bestR, F * kpCap);
+    A(b.sad, F * kpCap);
+    A(h->dPlan, 1);
+#undef A
+    if (!tab.empty()) ORBB_CUDA(h, cudaMemcpyAsync(b.tab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+    ORBB_CUDA(h, cudaMemcpyAsync(h->dPlan, &P, sizeof P, cudaMemcpyHostToDevice, h->stream));
+    ORBB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->capacity = frames;
+    h->planValid = true;
+    return ORBB_OK;
+}
+
+static int ensure_plan(orbb_extractor* h, int W, int H, int frames) {
+    if (W <= 0 || H <= 0) return set_err(h, ORBB_ERR_EMPTY, "empty image");
+    frames = std::max(frames, 1);
+    if (h->planValid && h->plan.W == W && h->plan.H == H && h->capacity >= frames) return ORBB_OK;
+    return build_plan(h, W, H, std::max(frames, h->prm.max_batch));
+}
+
+static void mark(orbb_extractor* h, int stage) {
+    if (h->profiling) cudaEventRecord(h->ev[stage], h->stream);
+}
+
+// the launch sequence for `nframes` device-resident frames
+static int run_batch(orbb_extractor* h, const uint8_t* dImgs, int nframes, size_t rowStride, size_t frameStride, int lap0, int lap1) {
+    const Plan& P = h->plan;
+    const Bufs& B = h->b;
+    cudaStream_t st = h->stream;
+    mark(h, ST_PYRAMID);
+    ORBB_CUDA(h, cudaMemsetAsync(B.status, 0, sizeof(int) * nframes, st));
+    for (int l = 0; l < P.nlevels; l++) {
+        const LevelPlan& L = P.lv[l];
+        dim3 grid((L.pitch / 4 + 255) / 256, L.h + 2 * kEdge, nframes);
+        if (l == 0) k_pyr_level0<<<grid, 256, 0, st>>>(h->dPlan, B, dImgs, rowStride, frameStride);
+        else k_pyr_resize<<<grid, 256, 0, st>>>(h->dPlan, B, l);
+        h->launches++;
+    }
+    mark(h, ST_FAST);
+    k_fast<<<dim3(P.cellsTotal, nframes), 256, 0, st>>>(h->dPlan, B);
+    mark(h, ST_OCTREE);
+    k_octree<<<dim3(P.nlevels, nframes), OT_THREADS, 0, st>>>(h->dPlan, B);
+    mark(h, ST_BLUR);
+    k_blur<<<dim3(P.blurTilesTotal, nframes), 256, 0, st>>>(h->dPlan, B);
+    mark(h, ST_ASSEMBLE);
+    k_assemble<<<nframes, 256, 0, st>>>(h->dPlan, B, lap0, lap1);
+    mark(h, ST_ORIENT_DESC);
+    k_orient_desc<<<dim3((P.kpCap + 7) / 8, nframes), 256, 0, st>>>(h->dPlan, B);
+    mark(h, ST_D2H);
+    h->launches += 5;
+    ORBB_CUDA(h, cudaGetLastError());
+    h->lastFrames = nframes;
+    h->hPyrFresh = false;
+    return ORBB_OK;
+}
+
+}  // namespace orbb
+
+using namespace orbb;
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* orbb_version(void) { return "orbb200 0.1 (sm_100a)"; }
+
+const char* orbb_last_error(const orbb_extractor* h) { return h ? h->err.c_str() : g_lastError.c_str(); }
+
+int orbb_create(const orbb_params* prm, orbb_extractor** out) {
+    if (!prm || !out) return set_err(nullptr, ORBB_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (prm->nlevels < 1 || prm->nlevels > ORBB_MAX_LEVELS || prm->nfeatures < 1 || !(prm->scale_factor > 1.0f))
+        return set_err(nullptr, ORBB_ERR_ARG, "bad parameters (nlevels 1..%d, nfeatures >= 1, scale_factor > 1)", ORBB_MAX_LEVELS);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_err(nullptr, ORBB_ERR_CUDA, "no CUDA device (%s): liborbb200 has no CPU fallback", cudaGetErrorString(e));
+    if (prm->device < 0 || prm->device >= ndev) return set_err(nullptr, ORBB_ERR_ARG, "device %d out of range", prm->device);
+    orbb_extractor* h = new orbb_extractor();
+    h->prm = *prm;
+    h->prm.max_batch = std::max(prm->max_batch, 1);
+    h->device = prm->device;
+    build_tables(h);
+    if (cudaSetDevice(h->device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_err(nullptr, ORBB_ERR_CUDA, "cannot create stream on device %d", h->device);
+        delete h;
+        return ORBB_ERR_CUDA;
+    }
+    for (int i = 0; i <= ST_COUNT; i++) cudaEventCreate(&h->ev[i]);
+    *out = h;
+    return ORBB_OK;
+}
+
+void orbb_destroy(orbb_extractor* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_bufs(h);
+    if (h->hImg) cudaFree(h->hImg);
+    if (h->hPyr) cudaFreeHost(h->hPyr);
+    if (h->hCounts) cudaFreeHost(h->hCounts);
+    for (int i = 0; i <= ST_COUNT; i++) cudaEventDestroy(h->ev[i]);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int orbb_get_tables(const orbb_extractor* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int32_t* feats) {
+    if (!h) return ORBB_ERR_ARG;
+    for (int i = 0; i < h->prm.nlevels; i++) {
+        if (scale) scale[i] = h->scale[i];
+        if (inv_scale) inv_scale[i] = h->invScale[i];
+        if (sigma2) sigma2[i] = h->sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = h->invSigma2[i];
+        if (feats) feats[i] = h->featPerLevel[i];
+    }
+    return ORBB_OK;
+}
+
+int orbb_max_keypoints(const orbb_extractor* h) {
+    if (!h) return ORBB_ERR_ARG;
+    if (h->planValid) return h->plan.kpCap;
+    int cap = 0;
+    for (int l = 0; l < h->prm.nlevels; l++) cap += std::max(h->featPerLevel[l] + 2, 4 * kMaxIni) + 6;
+    return cap;
+}
+
+long long orbb_launch_count(const orbb_extractor* h) { return h ? h->launches : 0; }
+
+int orbb_set_profiling(orbb_extractor* h, int enabled) {
+    if (!h) return ORBB_ERR_ARG;
+    h->profiling = enabled != 0;
+    return ORBB_OK;
+}
+
+const char* orbb_stage_name(int i) {
+    static const char* names[ST_COUNT] = {"h2d", "pyramid", "fast", "octree", "blur", "assemble", "orient_desc", "d2h"};
+    return (i >= 0 && i < ST_COUNT) ? names[i] : "";
+}
+
+int orbb_stage_times(orbb_extractor* h, float* ms, int cap) {
+    if (!h || !ms) return ORBB_ERR_ARG;
+    ORBB_CUDA(h, cudaSetDevice(h->device));
+    ORBB_CUDA(h, cudaStreamSynchronize(h->stream));
+    int n = std::min(cap, (int)ST_COUNT);
+    for (int i = 0; i < n; i++) {
+        ms[i] = 0.f;
+        if (i >= ST_PYRAMID && i < ST_D2H) cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]);
+    }
+    cudaGetLastError();
+    return n;
+}
+
+int orbb_extract_batch(orbb_extractor* h, const uint8_t* dev_imgs, int nframes, int width, int height, size_t row_stride,
+                       size_t frame_stride, int lap0, int lap1) {
+    if (!h) return ORBB_ERR_ARG;
+    if (!dev_imgs || nframes <= 0 || width <= 0 || height <= 0) return set_err(h, ORBB_ERR_EMPTY, "empty image");
+    ORBB_CUDA(h, cudaSetDevice(h->device));
+    int rc = ensure_plan(h, width, height, nframes);
+    if (rc) return rc;
+    return run_batch(h, dev_imgs, nframes, row_stride, frame_stride, lap0, lap1);
+}
+
+int orbb_sync(orbb_extractor* h) {
+    if (!h) return ORBB_ERR_ARG;
+    ORBB_CUDA(h, cudaSetDevice(h->device));
+    ORBB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return ORBB_OK;
+}
+
+static int ensure_counts(orbb_extractor* h, int nframes) {
+    if (h->hCountsCap >= nframes) return ORBB_OK;
+    if (h->hCounts) cudaFreeHost(h->hCounts);
+    h->hCounts = nullptr;
+    ORBB_CUDA(h, cudaMallocHost((void**)&h->hCounts, sizeof(int32_t) * 3 * nframes));
+    h->hCountsCap = nframes;
+    return ORBB_OK;
+}
+
+int orbb_batch_fetch(orbb_extractor* h, int nframes, orbb_keypoint* kps, uint8_t* desc, int capacity, int32_t* counts) {
+    if (!h || !counts) return ORBB_ERR_ARG;
+    if (nframes > h->lastFrames) return set_err(h, ORBB_ERR_ARG, "fetch of %d frames, last batch had %d", nframes, h->lastFrames);
+    ORBB_CUDA(h, cudaSetDevice(h->device));
+    int rc = ensure_counts(h, nframes);
+    if (rc) return rc;
+    const Plan& P = h->plan;
+    ORBB_CUDA(h, cudaMemcpyAsync(h->hCounts, h->b.outCount, sizeof(int) * 2 * nframes, cudaMemcpyDeviceToHost, h->stream));
+    ORBB_CUDA(h, cudaMemcpyAsync(h->hCounts + 2 * nframes, h->b.status, sizeof(int) * nframes, cudaMemcpyDeviceToHost, h->stream));
+    const int ncopy = std::min(capacity, P.kpCap);
+    if (kps && ncopy > 0)
+        ORBB_CUDA(h, cudaMemcpy2DAsync(kps, sizeof(orbb_keypoint) * capacity, h->b.kps, sizeof(orbb_keypoint) * P.kpCap,
+                                       sizeof(orbb_keypoint) * ncopy, nframes, cudaMemcpyDeviceToHost, h->stream));
+    if (desc && ncopy > 0)
+        ORBB_CUDA(h, cudaMemcpy2DAsync(desc, (size_t)32 * capacity, h->b.desc, (size_t)32 * P.kpCap, (size_t)32 * ncopy, nframes,
+                                       cudaMemcpyDeviceToHost, h->stream));
+    ORBB_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int f = 0; f < nframes; f++) {
+        counts[2 * f] = h->hCounts[2 * f];
+        counts[2 * f + 1] = h->hCounts[2 * f + 1];
+        if (h->hCounts[2 * nframes + f]) return set_err(h, ORBB_ERR_INTERNAL, "frame %d: device status 0x%x (capacity overflow)", f, h->hCounts[2 * nframes + f]);
+        if (counts[2 * f] > capacity && (kps || desc)) return set_err(h, ORBB_ERR_CAPACITY, "frame %d has %d keypoints, capacity %d", f, counts[2 * f], capacity);
+    }
+    return ORBB_OK;
+}
+
+int orbb_batch_device_ptrs(orbb_extractor* h, const orbb_keypoint** kps, const uint8_t** desc, const int32_t** counts) {
+    if (!h || !h->planValid) return ORBB_ERR_ARG;
+    if (kps) *kps = h->b.kps;
+    if (desc) *desc = h->b.desc;
+    if (counts) *counts = h->b.outCount;
+    return ORBB_OK;
+}
+
+int orbb_extract_batch_host(orbb_extractor* h, const uint8_t* host_imgs, int nframes, int width, int height, size_t row_stride,
+                            size_t frame_stride, int lap0, int lap1, orbb_keypoint* kps, uint8_t* desc, int capacity, int32_t* counts) {
+    if (!h) return ORBB_ERR_ARG;
+    if (!host_imgs || nframes <= 0 || width <= 0 || height <= 0) return set_err(h, ORBB_ERR_EMPTY, "empty image");
+    ORBB_CUDA(h, cudaSetDevice(h->device));
+    int rc = ensure_plan(h, width, height, nframes);
+    if (rc) return rc;
+    // device staging area for the raw frames: tightly packed WxH
+    const size_t need = (size_t)nframes * width * height;
+    if (h->hImgBytes < need) {
+        if (h->hImg) cudaFree(h->hImg);
+        h->hImg = nullptr; h->hImgBytes = 0;
+        ORBB_CUDA(h, cudaMalloc((void**)&h->hImg, need));
+        h->hImgBytes = need;
+    }
+    mark(h, ST_H2D);
+    if (frame_stride == (size_t)height * row_stride) {
+        ORBB_CUDA(h, cudaMemcpy2DAsync(h->hImg, width, host_imgs, row_stride, width, (size_t)height * nframes, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        for (int f = 0; f < nframes; f++)
+            ORBB_CUDA(h, cudaMemcpy2DAsync(h->hImg + (size_t)f * width * height, width, host_imgs + (size_t)f * frame_stride, row_stride, width,
+                                           height, cudaMemcpyHostToDevice, h->stream));
+    }
+    rc = run_batch(h, h->hImg, nframes, (size_t)width, (size_t)width * height, lap0, lap1);
+    if (rc) return rc;
+    return orbb_batch_fetch(h, nframes, kps, desc, capacity, counts);
+}
+
+int orbb_extract(orbb_extractor* h, const uint8_t* img, int width, int height, size_t stride, int lap0, int lap1,
+                 orbb_keypoint* kps, uint8_t* desc, int capacity, int* n_out, int* mono_index) {
+    if (!h) return ORBB_ERR_ARG;
+    if (n_out) *n_out = 0;
+    if (mono_index) *mono_index = 0;
+    if (!img || width <= 0 || height <= 0) return set_err(h, ORBB_ERR_EMPTY, "empty image");     // :1090-1091
+    int32_t counts[2] = {0, 0};
+    int rc = orbb_extract_batch_host(h, img, 1, width, height, stride, stride * (size_t)height, lap0, lap1, kps, desc, capacity, counts);
+    if (n_out) *n_out = counts[0];
+    if (mono_index) *mono_index = counts[1];
+    return rc;
+}
+
+int orbb_pyramid_level(orbb_extractor* h, int level, const uint8_t** ptr, int* width, int* height, size_t* stride) {
+    if (!h || !ptr) return ORBB_ERR_ARG;
+    if (!h->planValid || h->lastFrames == 0) return set_err(h, ORBB_ERR_ARG, "no frame has been extracted yet");
+    if (level < 0 || level >= h->plan.nlevels) return set_err(h, ORBB_ERR_ARG, "level %d out of range", level);
+    ORBB_CUDA(h, cudaSetDevice(h->device));
+    const Plan& P = h->plan;
+    if (!h->hPyrFresh) {      // lazy D2H of frame 0's whole pyramid slab
+        if (h->hPyrBytes < P.pyrStride) {
+            if (h->hPyr) cudaFreeHost(h->hPyr);
+            h->hPyr = nullptr; h->hPyrBytes = 0;
+            ORBB_CUDA(h, cudaMallocHost((void**)&h->hPyr, P.pyrStride));
+            h->hPyrBytes = P.pyrStride;
+        }
+        ORBB_CUDA(h, cudaMemcpyAsync(h->hPyr, h->b.pyr, P.pyrStride, cudaMemcpyDeviceToHost, h->stream));
+        ORBB_CUDA(h, cudaStreamSynchronize(h->stream));
+        h->hPyrFresh = true;
+    }
+    const LevelPlan& L = P.lv[level];
+    *ptr = h->hPyr + L.roiOff;
+    if (width) *width = L.w;
+    if (height) *height = L.h;
+    if (stride) *stride = (size_t)L.pitch;
+    return ORBB_OK;
+}
+
+// ---- stage taps ----------------------------------------------------------------------------------
+int orbb_debug_level(orbb_extractor* h, int frame, int level, int blurred, int bordered, uint8_t* dst, size_t dst_cap, int* width, int* height) {
+    if (!h || !h->planValid || frame < 0 || frame >= h->lastFrames || level < 0 || level >= h->plan.nlevels) return ORBB_ERR_ARG;
+    ORBB_CUDA(h, cudaSetDevice(h->device));
+    const Plan& P = h->plan;
+    const LevelPlan& L = P.lv[level];
+    int w = L.w, hh = L.h;
+    const uint8_t* src;
+    size_t pitch;
+    if (blurred) { src = h->b.blur + (size_t)frame * P.blurStride + L.blurOff; pitch = L.bpitch; }
+    else if (bordered) { src = h->b.pyr + (size_t)frame * P.pyrStride + L.pyrOff + (kRoiX - kEdge); pitch = L.pitch; w += 2 * kEdge; hh += 2 * kEdge; }
+    else { src = h->b.pyr + (size_t)frame * P.pyrStride + L.roiOff; pitch = L.pitch; }
+    if (width) *width = w;
+    if (height) *height = hh;
+    if (!dst) return ORBB_OK;
+    if (dst_cap < (size_t)w * hh) return set_err(h, ORBB_ERR_CAPACITY, "level buffer too small");
+    ORBB_CUDA(h, cudaMemcpy2DAsync(dst, w, src, pitch, w, hh, cudaMemcpyDeviceToHost, h->stream));
+    ORBB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return ORBB_OK;
+}
+
+int orbb_debug_raw_keys(orbb_extractor* h, int frame, int level, float* xyr, int cap, int* n) {
+    if (!h || !h->planValid || frame < 0 || frame >= h->lastFrames || level < 0 || level >= h->plan.nlevels || !n) return ORBB_ERR_ARG;
+    ORBB_CUDA(h, cudaSetDevice(h->device));
+    const Plan& P = h->plan;
+    const LevelPlan& L = P.lv[level];
+    const int nCells = L.nCols * L.nRows;
+    std::vector<int> cnt(nCells);
+    std::vector<u64> keys((size_t)nCells * L.cellCap);
+    ORBB_CUDA(h, cudaStreamSynchronize(h->stream));
+    ORBB_CUDA(h, cudaMemcpy(cnt.data(), h->b.cellCount + (size_t)frame * P.cellsTotal + L.cellBase, sizeof(int) * nCells, cudaMemcpyDeviceToHost));
+    ORBB_CUDA(h, cudaMemcpy(keys.data(), h->b.cellKeys + (size_t)frame * P.cellKeyStride + L.cellKeyBase, sizeof(u64) * keys.size(), cudaMemcpyDeviceToHost));
+    int m = 0;
+    for (int c = 0; c < nCells; c++)
+        for (int i = 0; i < cnt[c]; i++, m++) {
+            if (m < cap && xyr) {
+                const u64 k = keys[(size_t)c * L.cellCap + i];
+                xyr[3 * m] = (float)(k & 0xffff); xyr[3 * m + 1] = (float)((k >> 16) & 0xffff); xyr[3 * m + 2] = (float)(k >> 32);
+            }
+        }
+    *n = m;
+    return (xyr && m > cap) ? ORBB_ERR_CAPACITY : ORBB_OK;
+}
+
+int orbb_debug_selected(orbb_extractor* h, int frame, int level, float* xyr, int cap, int* n) {
+    if (!h || !h->planValid || frame < 0 || frame >= h->lastFrames || level < 0 || level >= h->plan.nlevels || !n) return ORBB_ERR_ARG;
+    ORBB_CUDA(h, cudaSetDevice(h->device));
+    const Plan& P = h->plan;
+    const LevelPlan& L = P.lv[level];
+    int cnt = 0;
+    ORBB_CUDA(h, cudaStreamSynchronize(h->stream));
+    ORBB_CUDA(h, cudaMemcpy(&cnt, h->b.selCount + frame * ORBB_MAX_LEVELS + level, sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<u64> keys(std::max(cnt, 1));
+    ORBB_CUDA(h, cudaMemcpy(keys.data(), h->b.sel + (size_t)frame * P.selStride + L.selBase, sizeof(u64) * cnt, cudaMemcpyDeviceToHost));
+    *n = cnt;
+    for (int i = 0; i < cnt && i < cap && xyr; i++) {
+        xyr[3 * i] = (float)(keys[i] & 0xffff); xyr[3 * i + 1] = (float)((keys[i] >> 16) & 0xffff); xyr[3 * i + 2] = (float)(keys[i] >> 32);
+    }
+    return (xyr && cnt > cap) ? ORBB_ERR_CAPACITY : ORBB_OK;
+}
+
+void* orbb_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void orbb_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

@@ -1,0 +1,131 @@
+// Internal declarations shared by the extractor and matcher translation units of liborbb200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/orbb200.h"
+
+namespace orbb {
+
+typedef unsigned long long u64;
+
+constexpr int kEdge = 19;          // EDGE_THRESHOLD        (reference ORBextractor.cc:73)
+constexpr int kRoiX = 32;          // column of the first image pixel inside a bordered row (>= kEdge, 16B aligned)
+constexpr int kMinBorder = 16;     // EDGE_THRESHOLD - 3    (:789)
+constexpr int kCellPix = 80;       // shared-memory pitch / max side of one FAST cell incl. its 6-px apron
+constexpr int kMaxIni = 16;        // max root nodes of the quadtree (image aspect ratio <= 16.5)
+
+// One pyramid level: geometry + where its data lives inside the per-frame slabs.
+struct LevelPlan {
+    int w, h, pitch;               // image size, bytes per bordered row
+    unsigned pyrOff, roiOff;       // byte offsets in the frame's pyramid slab: apron origin / first image pixel
+    int bpitch;
+    unsigned blurOff;              // blurred level (no apron)
+    int tabX, tabY;                // offsets (int2 units) of the resize tables of this level
+    int nCols, nRows, wCell, hCell, maxBX, maxBY;   // FAST cell grid (:789-803)
+    int cellBase, cellCap;         // first cell index; key capacity per cell
+    unsigned cellKeyBase;
+    int nFeat, nIni;               // mnFeaturesPerLevel[l]; root nodes (:559)
+    float hX;                      // :561
+    unsigned rawBase;              // quadtree key ping-pong buffers
+    int rawCap;
+    unsigned nodeBase;
+    int maxNodes;
+    unsigned selBase;
+    int selCap;
+    float scale, kpSize;
+    int blurTileBase, blurTilesX, blurTilesY;
+    int pad0;
+};
+
+struct Plan {
+    int nlevels, W, H;
+    int cellsTotal, blurTilesTotal;
+    int kpCap;
+    int iniTh, minTh;
+    u64 pyrStride, blurStride;                                  // bytes per frame
+    unsigned cellKeyStride, rawStride, nodeStride, selStride;   // entries per frame
+    int umax[16];
+    LevelPlan lv[ORBB_MAX_LEVELS];
+};
+
+struct QNode {                     // quadtree node: UL=(x0,y0) BR=(x1,y1); keys = segment of a ping-pong buffer
+    short x0, y0, x1, y1;
+    int start;
+    int cntbuf;                    // count | (buffer index << 31)
+};
+
+struct WorkItem { int level, x, y, pos; };
+
+// Device buffers of one extractor handle, sized for `capacity` frames.
+struct Bufs {
+    uint8_t* pyr;
+    uint8_t* blur;
+    int2* tab;                     // resize tables (shared by all frames)
+    int* cellCount;
+    int* cellOff;
+    u64* cellKeys;                 // key = x | y<<16 | score<<32 (x,y relative to the 16-px border)
+    u64* keys;                     // [frame][2][rawStride]
+    QNode* nodes;                  // [frame][2][nodeStride]
+    u64* rec;                      // [frame][nodeStride] sort records / scratch
+    int4* cnt4;                    // [frame][nodeStride]
+    int* pend;                     // [frame][2][nodeStride]
+    int* elist;                    // [frame][nodeStride]
+    uint8_t* erased;               // [frame][nodeStride]
+    u64* sel;                      // [frame][selStride] selected keys (level coordinates)
+    int* selCount;                 // [frame][ORBB_MAX_LEVELS]
+    WorkItem* work;                // [frame][kpCap]
+    orbb_keypoint* kps;            // [frame][kpCap]
+    uint8_t* desc;                 // [frame][kpCap][32]
+    int* outCount;                 // [frame][2] {n, monoIndex}
+    int* status;                   // [frame] error flags
+    float* uRight;                 // [frame][kpCap]   stereo outputs (left handle only)
+    float* depth;
+    int* bestR;
+    int* sad;
+};
+
+enum Stage { ST_H2D = 0, ST_PYRAMID, ST_FAST, ST_OCTREE, ST_BLUR, ST_ASSEMBLE, ST_ORIENT_DESC, ST_D2H, ST_COUNT };
+
+}  // namespace orbb
+
+struct orbb_extractor {
+    orbb_params prm;
+    std::vector<float> scale, invScale, sigma2, invSigma2;
+    std::vector<int> featPerLevel;
+    int umax[16];
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    // plan for the current image size
+    orbb::Plan plan;
+    orbb::Plan* dPlan = nullptr;
+    bool planValid = false;
+    int capacity = 0;              // frames the buffers are sized for
+    orbb::Bufs b{};
+    std::vector<void*> allocs;
+    int lastFrames = 0;
+    long long launches = 0;
+    bool profiling = false;
+    cudaEvent_t ev[orbb::ST_COUNT + 1]{};
+    bool evValid = false;
+    bool stageRan[orbb::ST_COUNT]{};
+    // staging: hImg is a DEVICE buffer for frames uploaded from the host; hPyr/hCounts are pinned host memory
+    uint8_t* hImg = nullptr; size_t hImgBytes = 0;
+    uint8_t* hPyr = nullptr; size_t hPyrBytes = 0; bool hPyrFresh = false;
+    int32_t* hCounts = nullptr; int hCountsCap = 0;
+    std::string err;
+};
+
+namespace orbb {
+int set_err(orbb_extractor* h, int code, const char* fmt, ...);
+extern thread_local std::string g_lastError;
+}
+
+#define ORBB_CUDA(h, call)                                                                               \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return orbb::set_err(h, ORBB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)

@@ -1,0 +1,641 @@
+// liborbb200.so -- Hamming matching and rectified-stereo matching for B200 (sm_100a).
+//
+//   k_knn2_partial / k_knn2_merge   cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, 2)   reference Frame.cc:1144
+//   k_ratio_test                    Lowe ratio                                       Frame.cc:1151
+//   k_best2_csr                     best / second-best candidate scans               ORBmatcher.cc:77-120 (and siblings)
+//   k_stereo_match / k_stereo_cut   Frame::ComputeStereoMatches                      Frame.cc:811-981
+//
+// The 2-NN kernel is integer work on the CUDA cores (8 x 32-bit XOR + POPC per pair, no tensor cores): queries live in
+// registers (4 per thread), database tiles are staged in shared memory with 1-D TMA bulk copies (cp.async.bulk +
+// mbarrier, 3 stages) and every thread of a warp reads the same database row (shared-memory broadcast).
+#include <limits.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "orbb_internal.cuh"
+
+struct orbb_matcher {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    std::string err;
+    // scratch
+    unsigned* partial = nullptr; size_t partialCap = 0;     // [chunk][nq][2] packed (dist<<22 | local index)
+    void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t scratchCap[4] = {0, 0, 0, 0};
+};
+
+namespace orbb {
+
+static int m_err(orbb_matcher* m, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (m) m->err = buf;
+    g_lastError = buf;
+    return code;
+}
+
+#define ORBM_CUDA(m, call)                                                                                   \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess) return orbb::m_err(m, ORBB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// mbarrier / TMA bulk-copy wrappers (PTX ISA 8.x, sm_90+; SASS: SYNCS.*, UBLKCP)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// brute-force Hamming 2-NN
+// ------------------------------------------------------------------------------------------------
+constexpr int KNN_THREADS = 256;
+constexpr int KNN_QPT = 4;                         // queries per thread
+constexpr int KNN_QTILE = KNN_THREADS * KNN_QPT;   // queries per CTA
+constexpr int KNN_ROWS = 256;                      // database rows per shared-memory tile (8 KB)
+constexpr int KNN_STAGES = 3;
+constexpr unsigned KNN_IDX_BITS = 22;              // packed key = dist << 22 | chunk-local index
+constexpr unsigned KNN_NONE = 0xffffffffu;
+
+__device__ __forceinline__ void top2_insert(unsigned& k1, unsigned& k2, unsigned k) {
+    const unsigned hi = max(k1, k);
+    k1 = min(k1, k);
+    k2 = min(k2, hi);
+}
+
+// grid (query tiles, database chunks).  A chunk is < 2^22 rows; packed keys make "lowest index wins ties" the
+// natural order of an unsigned min.
+__global__ void __launch_bounds__(KNN_THREADS) k_knn2_partial(const uint4* __restrict__ q, int nq, const uint4* __restrict__ db,
+                                                             long long nd, int chunkRows, unsigned* __restrict__ partial) {
+    __shared__ __align__(128) uint4 sDb[KNN_STAGES][KNN_ROWS * 2];
+    __shared__ __align__(8) unsigned long long sBar[KNN_STAGES];
+    const int tid = threadIdx.x;
+    const long long row0 = (long long)blockIdx.y * chunkRows;
+    const int rows = (int)min((long long)chunkRows, nd - row0);
+    const int ntiles = (rows + KNN_ROWS - 1) / KNN_ROWS;
+    if (tid == 0) {
+        for (int s = 0; s < KNN_STAGES; s++) mbar_init(&sBar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int t) {
+        const int s = t % KNN_STAGES;
+        const int r = min(KNN_ROWS, rows - t * KNN_ROWS);
+        mbar_expect_tx(&sBar[s], (unsigned)r * 32u);
+        tma_bulk_g2s(&sDb[s][0], db + (row0 + (long long)t * KNN_ROWS) * 2, (unsigned)r * 32u, &sBar[s]);
+    };
+    if (tid == 0)
+        for (int t = 0; t < KNN_STAGES && t < ntiles; t++) issue(t);
+
+    unsigned qa[KNN_QPT][8];
+#pragma unroll
+    for (int k = 0; k < KNN_QPT; k++) {
+        const int qi = min(blockIdx.x * KNN_QTILE + k * KNN_THREADS + tid, nq - 1);
+        const uint4 a = __ldg(q + (size_t)qi * 2), b = __ldg(q + (size_t)qi * 2 + 1);
+        qa[k][0] = a.x; qa[k][1] = a.y; qa[k][2] = a.z; qa[k][3] = a.w;
+        qa[k][4] = b.x; qa[k][5] = b.y; qa[k][6] = b.z; qa[k][7] = b.w;
+    }
+    unsigned k1[KNN_QPT], k2[KNN_QPT];
+#pragma unroll
+    for (int k = 0; k < KNN_QPT; k++) k1[k] = k2[k] = KNN_NONE;
+
+    for (int t = 0; t < ntiles; t++) {
+        const int s = t % KNN_STAGES;
+        mbar_wait(&sBar[s], (unsigned)(t / KNN_STAGES) & 1u);
+        const int r = min(KNN_ROWS, rows - t * KNN_ROWS);
+        const uint4* tile = &sDb[s][0];
+        const unsigned jbase = (unsigned)(t * KNN_ROWS);
+#pragma unroll 2
+        for (int j = 0; j < r; j++) {
+            const uint4 a = tile[2 * j], b = tile[2 * j + 1];
+#pragma unroll
+            for (int k = 0; k < KNN_QPT; k++) {
+                const int d = __popc(qa[k][0] ^ a.x) + __popc(qa[k][1] ^ a.y) + __popc(qa[k][2] ^ a.z) + __popc(qa[k][3] ^ a.w) +
+                              __popc(qa[k][4] ^ b.x) + __popc(qa[k][5] ^ b.y) + __popc(qa[k][6] ^ b.z) + __popc(qa[k][7] ^ b.w);
+                top2_insert(k1[k], k2[k], ((unsigned)d << KNN_IDX_BITS) + (jbase + (unsigned)j));
+            }
+        }
+        __syncthreads();                               // everyone is done with stage s
+        if (tid == 0 && t + KNN_STAGES < ntiles) issue(t + KNN_STAGES);
+    }
+#pragma unroll
+    for (int k = 0; k < KNN_QPT; k++) {
+        const int qi = blockIdx.x * KNN_QTILE + k * KNN_THREADS + tid;
+        if (qi < nq) {
+            unsigned* o = partial + ((size_t)blockIdx.y * nq + qi) * 2;
+            o[0] = k1[k];
+            o[1] = k2[k];
+        }
+    }
+}
+
+// merge per-chunk packed results into (idx, dist) pairs; chunks are visited in ascending database order so a strict
+// '<' keeps the lowest global index among equal distances.
+__global__ void k_knn2_merge_chunks(const unsigned* __restrict__ partial, int nchunks, int nq, int chunkRows, int indexBase,
+                                    int* __restrict__ idx2, int* __restrict__ dist2) {
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    int d1 = INT_MAX, d2 = INT_MAX, i1 = -1, i2 = -1;
+    for (int c = 0; c < nchunks; c++) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const unsigned p = partial[((size_t)c * nq + qi) * 2 + k];
+            if (p == KNN_NONE) continue;
+            const int d = (int)(p >> KNN_IDX_BITS);
+            const int i = indexBase + c * chunkRows + (int)(p & ((1u << KNN_IDX_BITS) - 1));
+            if (d < d1) { d2 = d1; i2 = i1; d1 = d; i1 = i; }
+            else if (d < d2) { d2 = d; i2 = i; }
+        }
+    }
+    idx2[2 * qi] = i1; idx2[2 * qi + 1] = i2;
+    dist2[2 * qi] = d1; dist2[2 * qi + 1] = d2;
+}
+
+// merge across database shards: input [shard][nq][2] (idx, dist), lexicographic (dist, idx) order
+__global__ void k_knn2_merge_shards(const int* __restrict__ idxSh, const int* __restrict__ distSh, int nshards, int nq,
+                                    int* __restrict__ idx2, int* __restrict__ dist2) {
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    int d1 = INT_MAX, d2 = INT_MAX, i1 = -1, i2 = -1;
+    for (int s = 0; s < nshards; s++) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int i = idxSh[((size_t)s * nq + qi) * 2 + k];
+            const int d = distSh[((size_t)s * nq + qi) * 2 + k];
+            if (i < 0) continue;
+            if (d < d1 || (d == d1 && i < i1)) { d2 = d1; i2 = i1; d1 = d; i1 = i; }
+            else if (d < d2 || (d == d2 && i < i2)) { d2 = d; i2 = i; }
+        }
+    }
+    idx2[2 * qi] = i1; idx2[2 * qi + 1] = i2;
+    dist2[2 * qi] = d1; dist2[2 * qi + 1] = d2;
+}
+
+__global__ void k_ratio_test(const int* __restrict__ idx2, const int* __restrict__ dist2, int nq, double ratio, uint8_t* __restrict__ keep) {
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    // (*it).size() >= 2 && (*it)[0].distance < (*it)[1].distance * 0.7   (DMatch::distance is a float)
+    const bool two = idx2[2 * qi] >= 0 && idx2[2 * qi + 1] >= 0;
+    keep[qi] = two && (double)(float)dist2[2 * qi] < (double)(float)dist2[2 * qi + 1] * ratio;
+}
+
+// ------------------------------------------------------------------------------------------------
+// best / second-best over candidate lists, one warp per query
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const uint4 b0, const uint4 b1) {
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) +
+           __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+__global__ void __launch_bounds__(256) k_best2_csr(const uint4* __restrict__ q, int nq, const uint4* __restrict__ train,
+                                                  const int* __restrict__ cand, const int* __restrict__ rowptr, int init,
+                                                  int* __restrict__ out4) {
+    const int qi = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (qi >= nq) return;
+    const uint4 a0 = __ldg(q + (size_t)qi * 2), a1 = __ldg(q + (size_t)qi * 2 + 1);
+    const int beg = rowptr[qi], end = rowptr[qi + 1];
+    unsigned long long k1 = ~0ull, k2 = ~0ull;            // dist << 32 | position in the list
+    for (int c = beg + lane; c < end; c += 32) {
+        const int t = cand[c];
+        const int d = hamming256(a0, a1, __ldg(train + (size_t)t * 2), __ldg(train + (size_t)t * 2 + 1));
+        if (d < init) {
+            const unsigned long long k = ((unsigned long long)(unsigned)d << 32) | (unsigned)(c - beg);
+            const unsigned long long hi = max(k1, k);
+            k1 = min(k1, k);
+            k2 = min(k2, hi);
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, k1, off), o2 = __shfl_xor_sync(0xffffffffu, k2, off);
+        const unsigned long long lo = min(k1, o1), hi = max(k1, o1);
+        k2 = min(min(k2, o2), hi);
+        k1 = lo;
+    }
+    if (lane == 0) {
+        int* o = out4 + (size_t)qi * 4;
+        o[0] = k1 == ~0ull ? init : (int)(k1 >> 32);
+        o[1] = k1 == ~0ull ? -1 : cand[beg + (int)(k1 & 0xffffffffu)];
+        o[2] = k2 == ~0ull ? init : (int)(k2 >> 32);
+        o[3] = k2 == ~0ull ? -1 : cand[beg + (int)(k2 & 0xffffffffu)];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Frame::ComputeStereoMatches (Frame.cc:811-981): one warp per left keypoint
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_stereo_match(const Plan* __restrict__ P, Bufs BL, Bufs BR, float mbf, float mb) {
+    const int frame = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int iL = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int nL = BL.outCount[frame * 2], nR = BR.outCount[frame * 2];
+    if (iL >= nL) return;
+    const size_t fo = (size_t)frame * P->kpCap;
+    float* uRightOut = BL.uRight + fo;
+    float* depthOut = BL.depth + fo;
+    int* bestROut = BL.bestR + fo;
+    int* sadOut = BL.sad + fo;
+    float resU = -1.f, resD = -1.f;
+    int resSad = -1, resR = -1;
+
+    const orbb_keypoint kpL = BL.kps[fo + iL];
+    const int levelL = kpL.octave;
+    const float vL = kpL.y, uL = kpL.x;
+    const float minZ = mb, minD = 0.f, maxD = __fdiv_rn(mbf, minZ);                       // :841-843
+    const float minU = __fsub_rn(uL, maxD), maxU = __fsub_rn(uL, minD);
+    const int rowL = (int)vL;                                                              // vRowIndices[vL] :856
+    const int nRows = P->lv[0].h;
+    bool alive = !(maxU < 0) && rowL >= 0 && rowL < nRows;                                 // :864
+
+    // ---- best Hamming candidate, ascending iR, strict '<', start at TH_HIGH (:867-894) ----
+    unsigned best = (100u << 16) | 0xffffu;          // dist << 16 | iR  (iR < 65535)
+    if (alive) {
+        const uint4* dl = reinterpret_cast<const uint4*>(BL.desc + (fo + iL) * 32);
+        const uint4 a0 = dl[0], a1 = dl[1];
+        const orbb_keypoint* kR = BR.kps + fo;
+        for (int base = 0; base < nR; base += 32) {
+            const int iR = base + lane;
+            if (iR < nR) {
+                const orbb_keypoint kp = kR[iR];
+                const float r = __fmul_rn(2.0f, P->lv[kp.octave].scale);                   // :832
+                const int maxr = (int)ceilf(__fadd_rn(kp.y, r)), minr = (int)floorf(__fsub_rn(kp.y, r));
+                if (rowL >= minr && rowL <= maxr && kp.octave >= levelL - 1 && kp.octave <= levelL + 1 && kp.x >= minU &&
+                    kp.x <= maxU) {
+                    const uint4* dr = reinterpret_cast<const uint4*>(BR.desc + (fo + iR) * 32);
+                    const int d = hamming256(a0, a1, dr[0], dr[1]);
+                    if (d < 100) best = min(best, ((unsigned)d << 16) | (unsigned)iR);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
+    const int bestDist = (int)(best >> 16);
+    const int bestIdxR = (int)(best & 0xffffu);
+
+    if (alive && bestDist < 75) {                                                          // thOrbDist :816,:897
+        resR = bestIdxR;
+        const float uR0 = BR.kps[fo + bestIdxR].x;
+        const LevelPlan& L = P->lv[levelL];
+        const float sf = 1.0f / L.scale;                                                   // mvInvScaleFactors
+        const float scaleduL = roundf(__fmul_rn(kpL.x, sf));
+        const float scaledvL = roundf(__fmul_rn(kpL.y, sf));
+        const float scaleduR0 = roundf(__fmul_rn(uR0, sf));
+        const int w = 5, LL = 5;
+        const float iniu = scaleduR0 + LL - w, endu = scaleduR0 + LL + w + 1;
+        if (!(iniu < 0 || endu >= (float)L.w)) {                                           // :918
+            const uint8_t* pl = BL.pyr + (size_t)frame * P->pyrStride + L.roiOff;
+            const uint8_t* pr = BR.pyr + (size_t)frame * P->pyrStride + L.roiOff;
+            const int y0 = (int)(scaledvL - w), xl0 = (int)(scaleduL - w), xr00 = (int)(scaleduR0 - w);
+            int lv[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int p = lane + 32 * k;
+                lv[k] = p < 121 ? pl[(size_t)(y0 + p / 11) * L.pitch + xl0 + p % 11] : 0;
+            }
+            int bestSad = INT_MAX, bestinc = 0;
+            float dists[11];
+#pragma unroll
+            for (int inc = -5; inc <= 5; inc++) {                                          // :921-933
+                int sad = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int p = lane + 32 * k;
+                    if (p < 121) sad += abs(lv[k] - (int)pr[(size_t)(y0 + p / 11) * L.pitch + xr00 + inc + p % 11]);
+                }
+                sad = warp_sum_i(sad);
+                const float dist = (float)sad;
+                if (dist < (float)bestSad) { bestSad = sad; bestinc = inc; }
+                dists[inc + 5] = dist;
+            }
+            if (!(bestinc == -LL || bestinc == LL)) {                                      // :935
+                float d1 = 0, d2 = 0, d3 = 0;
+#pragma unroll
+                for (int k = 1; k < 10; k++)
+                    if (k == bestinc + 5) { d1 = dists[k - 1]; d2 = dists[k]; d3 = dists[k + 1]; }
+                const float deltaR = __fdiv_rn(__fsub_rn(d1, d3), __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));   // :943
+                if (!(deltaR < -1 || deltaR > 1)) {
+                    float bestuR = __fmul_rn(L.scale, __fadd_rn(__fadd_rn(scaleduR0, (float)bestinc), deltaR));   // :949
+                    float disparity = __fsub_rn(uL, bestuR);
+                    if (disparity >= minD && disparity < maxD) {                           // :953
+                        if (disparity <= 0) {
+                            disparity = 0.01f;                                             // float(0.01)
+                            bestuR = (float)((double)uL - 0.01);
+                        }
+                        resD = __fdiv_rn(mbf, disparity);
+                        resU = bestuR;
+                        resSad = bestSad;
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        uRightOut[iL] = resU;
+        depthOut[iL] = resD;
+        bestROut[iL] = resR;
+        sadOut[iL] = resSad;
+    }
+}
+
+// median-based outlier cut (:967-980).  The sorted (SAD, iL) vector is only used for the value at index size/2 and
+// for "everything >= thDist from the back", i.e. an order statistic + a filter: two-pass radix select on the
+// 15-bit SAD.  One CTA per frame.
+__global__ void __launch_bounds__(256) k_stereo_cut(const Plan* __restrict__ P, Bufs BL) {
+    const int frame = blockIdx.x;
+    const int tid = threadIdx.x;
+    const size_t fo = (size_t)frame * P->kpCap;
+    const int nL = BL.outCount[frame * 2];
+    int* sad = BL.sad + fo;
+    __shared__ int hist[256];
+    __shared__ int sBin, sRank, sCount, sMedian;
+    hist[tid] = 0;
+    if (tid == 0) sCount = 0;
+    __syncthreads();
+    int local = 0;
+    for (int i = tid; i < nL; i += 256) {
+        const int s = sad[i];
+        if (s >= 0) { atomicAdd(&hist[min(s >> 7, 255)], 1); local++; }
+    }
+    atomicAdd(&sCount, local);
+    __syncthreads();
+    const int count = sCount;
+    if (count == 0) return;                      // the reference reads vDistIdx[0] of an empty vector here (UB)
+    const int kth = count / 2;
+    if (tid == 0) {
+        int acc = 0, b = 0;
+        for (; b < 256; b++) { if (acc + hist[b] > kth) break; acc += hist[b]; }
+        sBin = b; sRank = kth - acc;
+    }
+    __syncthreads();
+    const int bin = sBin;
+    __syncthreads();
+    hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < nL; i += 256) {
+        const int s = sad[i];
+        if (s >= 0 && min(s >> 7, 255) == bin) atomicAdd(&hist[s & 127], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0, b = 0;
+        for (; b < 128; b++) { if (acc + hist[b] > sRank) break; acc += hist[b]; }
+        sMedian = (bin << 7) | b;
+    }
+    __syncthreads();
+    const float median = (float)sMedian;
+    const float thDist = __fmul_rn(1.5f * 1.4f, median);                                   // :969
+    for (int i = tid; i < nL; i += 256) {
+        const int s = sad[i];
+        if (s >= 0 && !((float)s < thDist)) {                                              // :973-978
+            BL.uRight[fo + i] = -1.f;
+            BL.depth[fo + i] = -1.f;
+        }
+    }
+}
+
+static int ensure_scratch(orbb_matcher* m, int slot, size_t bytes) {
+    if (m->scratchCap[slot] >= bytes) return ORBB_OK;
+    if (m->scratch[slot]) cudaFree(m->scratch[slot]);
+    m->scratch[slot] = nullptr; m->scratchCap[slot] = 0;
+    ORBM_CUDA(m, cudaMalloc(&m->scratch[slot], bytes));
+    m->scratchCap[slot] = bytes;
+    return ORBB_OK;
+}
+
+}  // namespace orbb
+
+using namespace orbb;
+
+extern "C" {
+
+int orbb_hamming_distance(const uint8_t* a, const uint8_t* b) {
+    // ORBmatcher::DescriptorDistance (ORBmatcher.cc:2058-2074): a single 32-byte pair stays on the host
+    unsigned long long x[4], y[4];
+    memcpy(x, a, 32);
+    memcpy(y, b, 32);
+    return __builtin_popcountll(x[0] ^ y[0]) + __builtin_popcountll(x[1] ^ y[1]) + __builtin_popcountll(x[2] ^ y[2]) +
+           __builtin_popcountll(x[3] ^ y[3]);
+}
+
+int orbb_matcher_create(int device, orbb_matcher** out) {
+    if (!out) return m_err(nullptr, ORBB_ERR_ARG, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return m_err(nullptr, ORBB_ERR_CUDA, "no CUDA device (%s): liborbb200 has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return m_err(nullptr, ORBB_ERR_ARG, "device %d out of range", device);
+    orbb_matcher* m = new orbb_matcher();
+    m->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete m;
+        return m_err(nullptr, ORBB_ERR_CUDA, "cannot create stream on device %d", device);
+    }
+    *out = m;
+    return ORBB_OK;
+}
+
+void orbb_matcher_destroy(orbb_matcher* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaStreamSynchronize(m->stream);
+    if (m->partial) cudaFree(m->partial);
+    for (int i = 0; i < 4; i++) if (m->scratch[i]) cudaFree(m->scratch[i]);
+    cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+const char* orbb_matcher_last_error(const orbb_matcher* m) { return m ? m->err.c_str() : g_lastError.c_str(); }
+long long orbb_matcher_launch_count(const orbb_matcher* m) { return m ? m->launches : 0; }
+void* orbb_matcher_stream(orbb_matcher* m) { return m ? (void*)m->stream : nullptr; }
+
+int orbb_knn2_dev(orbb_matcher* m, const uint8_t* q_dev, int nq, const uint8_t* db_dev, int64_t nd, int32_t index_base,
+                  int32_t* idx2_dev, int32_t* dist2_dev) {
+    if (!m || !idx2_dev || !dist2_dev || nq < 0 || nd < 0) return m_err(m, ORBB_ERR_ARG, "bad argument");
+    if (nq == 0) return ORBB_OK;
+    if (((uintptr_t)q_dev | (uintptr_t)db_dev) & 15) return m_err(m, ORBB_ERR_ARG, "descriptor arrays must be 16-byte aligned");
+    if (nd + (int64_t)index_base > INT_MAX) return m_err(m, ORBB_ERR_ARG, "database too large for 32-bit indices");
+    ORBM_CUDA(m, cudaSetDevice(m->device));
+    const int qtiles = (nq + KNN_QTILE - 1) / KNN_QTILE;
+    // database chunks: enough CTAs to fill 148 SMs several times over, chunk a multiple of the tile, < 2^22 rows
+    int nchunks = 1;
+    if (nd > 0) {
+        const int want = std::max(1, (148 * 8 + qtiles - 1) / qtiles);
+        long long rowsPer = (nd + want - 1) / want;
+        rowsPer = std::max<long long>(KNN_ROWS * 4, (rowsPer + KNN_ROWS - 1) / KNN_ROWS * KNN_ROWS);
+        rowsPer = std::min<long long>(rowsPer, (1ll << KNN_IDX_BITS) - KNN_ROWS);
+        nchunks = (int)((nd + rowsPer - 1) / rowsPer);
+        const size_t need = (size_t)nchunks * nq * 2 * sizeof(unsigned);
+        if (m->partialCap < need) {
+            if (m->partial) cudaFree(m->partial);
+            m->partial = nullptr; m->partialCap = 0;
+            ORBM_CUDA(m, cudaMalloc((void**)&m->partial, need));
+            m->partialCap = need;
+        }
+        k_knn2_partial<<<dim3(qtiles, nchunks), KNN_THREADS, 0, m->stream>>>((const uint4*)q_dev, nq, (const uint4*)db_dev, nd, (int)rowsPer, m->partial);
+        m->launches++;
+        k_knn2_merge_chunks<<<(nq + 255) / 256, 256, 0, m->stream>>>(m->partial, nchunks, nq, (int)rowsPer, index_base, idx2_dev, dist2_dev);
+        m->launches++;
+    } else {
+        k_knn2_merge_chunks<<<(nq + 255) / 256, 256, 0, m->stream>>>(nullptr, 0, nq, 0, index_base, idx2_dev, dist2_dev);
+        m->launches++;
+    }
+    ORBM_CUDA(m, cudaGetLastError());
+    return ORBB_OK;
+}
+
+int orbb_knn2(orbb_matcher* m, const uint8_t* q, int nq, const uint8_t* db, int64_t nd, int32_t* idx2, int32_t* dist2) {
+    if (!m || !idx2 || !dist2 || nq < 0 || nd < 0) return m_err(m, ORBB_ERR_ARG, "bad argument");
+    if (nq == 0) return ORBB_OK;
+    ORBM_CUDA(m, cudaSetDevice(m->device));
+    int rc;
+    if ((rc = ensure_scratch(m, 0, (size_t)nq * 32)) || (rc = ensure_scratch(m, 1, std::max<size_t>((size_t)nd * 32, 32))) ||
+        (rc = ensure_scratch(m, 2, (size_t)nq * 2 * sizeof(int))) || (rc = ensure_scratch(m, 3, (size_t)nq * 2 * sizeof(int))))
+        return rc;
+    ORBM_CUDA(m, cudaMemcpyAsync(m->scratch[0], q, (size_t)nq * 32, cudaMemcpyHostToDevice, m->stream));
+    if (nd > 0) ORBM_CUDA(m, cudaMemcpyAsync(m->scratch[1], db, (size_t)nd * 32, cudaMemcpyHostToDevice, m->stream));
+    rc = orbb_knn2_dev(m, (const uint8_t*)m->scratch[0], nq, (const uint8_t*)m->scratch[1], nd, 0, (int32_t*)m->scratch[2], (int32_t*)m->scratch[3]);
+    if (rc) return rc;
+    ORBM_CUDA(m, cudaMemcpyAsync(idx2, m->scratch[2], (size_t)nq * 2 * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    ORBM_CUDA(m, cudaMemcpyAsync(dist2, m->scratch[3], (size_t)nq * 2 * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    ORBM_CUDA(m, cudaStreamSynchronize(m->stream));
+    return ORBB_OK;
+}
+
+int orbb_knn2_merge_dev(orbb_matcher* m, const int32_t* idx_sh_dev, const int32_t* dist_sh_dev, int nshards, int nq,
+                        int32_t* idx2_dev, int32_t* dist2_dev) {
+    if (!m || !idx_sh_dev || !dist_sh_dev || !idx2_dev || !dist2_dev || nshards < 1 || nq < 0) return m_err(m, ORBB_ERR_ARG, "bad argument");
+    if (nq == 0) return ORBB_OK;
+    ORBM_CUDA(m, cudaSetDevice(m->device));
+    k_knn2_merge_shards<<<(nq + 255) / 256, 256, 0, m->stream>>>(idx_sh_dev, dist_sh_dev, nshards, nq, idx2_dev, dist2_dev);
+    m->launches++;
+    ORBM_CUDA(m, cudaGetLastError());
+    return ORBB_OK;
+}
+
+int orbb_ratio_test_dev(orbb_matcher* m, const int32_t* idx2_dev, const int32_t* dist2_dev, int nq, double ratio, uint8_t* keep_dev) {
+    if (!m || !idx2_dev || !dist2_dev || !keep_dev || nq < 0) return m_err(m, ORBB_ERR_ARG, "bad argument");
+    if (nq == 0) return ORBB_OK;
+    ORBM_CUDA(m, cudaSetDevice(m->device));
+    k_ratio_test<<<(nq + 255) / 256, 256, 0, m->stream>>>(idx2_dev, dist2_dev, nq, ratio, keep_dev);
+    m->launches++;
+    ORBM_CUDA(m, cudaGetLastError());
+    return ORBB_OK;
+}
+
+int orbb_best2_csr(orbb_matcher* m, const uint8_t* q, int nq, const uint8_t* train, int ntrain, const int32_t* cand,
+                   const int32_t* rowptr, int init, int32_t* out4) {
+    if (!m || !rowptr || !out4 || nq < 0 || ntrain < 0) return m_err(m, ORBB_ERR_ARG, "bad argument");
+    if (nq == 0) return ORBB_OK;
+    ORBM_CUDA(m, cudaSetDevice(m->device));
+    const int ncand = rowptr[nq];
+    const size_t bq = (size_t)nq * 32, bt = std::max<size_t>((size_t)ntrain * 32, 32), bc = std::max<size_t>((size_t)ncand * 4, 4);
+    const size_t br = (size_t)(nq + 1) * 4, bo = (size_t)nq * 16;
+    int rc;
+    if ((rc = ensure_scratch(m, 0, bq + 256)) || (rc = ensure_scratch(m, 1, bt)) || (rc = ensure_scratch(m, 2, bc + br + 512)) ||
+        (rc = ensure_scratch(m, 3, bo)))
+        return rc;
+    int* dCand = (int*)m->scratch[2];
+    int* dRow = (int*)((char*)m->scratch[2] + (bc + 255) / 256 * 256);
+    ORBM_CUDA(m, cudaMemcpyAsync(m->scratch[0], q, bq, cudaMemcpyHostToDevice, m->stream));
+    if (ntrain > 0) ORBM_CUDA(m, cudaMemcpyAsync(m->scratch[1], train, (size_t)ntrain * 32, cudaMemcpyHostToDevice, m->stream));
+    if (ncand > 0) ORBM_CUDA(m, cudaMemcpyAsync(dCand, cand, (size_t)ncand * 4, cudaMemcpyHostToDevice, m->stream));
+    ORBM_CUDA(m, cudaMemcpyAsync(dRow, rowptr, br, cudaMemcpyHostToDevice, m->stream));
+    k_best2_csr<<<(nq + 7) / 8, 256, 0, m->stream>>>((const uint4*)m->scratch[0], nq, (const uint4*)m->scratch[1], dCand, dRow, init, (int*)m->scratch[3]);
+    m->launches++;
+    ORBM_CUDA(m, cudaGetLastError());
+    ORBM_CUDA(m, cudaMemcpyAsync(out4, m->scratch[3], bo, cudaMemcpyDeviceToHost, m->stream));
+    ORBM_CUDA(m, cudaStreamSynchronize(m->stream));
+    return ORBB_OK;
+}
+
+// ---- stereo ----------------------------------------------------------------------------------------
+int orbb_stereo_match_batch(orbb_extractor* hL, orbb_extractor* hR, int nframes, float bf, float b) {
+    if (!hL || !hR) return ORBB_ERR_ARG;
+    if (!hL->planValid || !hR->planValid || nframes < 1 || nframes > hL->lastFrames || nframes > hR->lastFrames)
+        return set_err(hL, ORBB_ERR_ARG, "stereo: both extractors must hold a batch of >= %d frames", nframes);
+    const Plan &A = hL->plan, &B = hR->plan;
+    if (hL->device != hR->device || A.W != B.W || A.H != B.H || A.nlevels != B.nlevels || A.kpCap != B.kpCap || A.pyrStride != B.pyrStride)
+        return set_err(hL, ORBB_ERR_ARG, "stereo: left/right extractors differ in geometry or parameters");
+    if (A.kpCap >= 65535) return set_err(hL, ORBB_ERR_UNSUPPORTED, "stereo: more than 65534 keypoints per image");
+    ORBB_CUDA(hL, cudaSetDevice(hL->device));
+    // the left stream waits for the right extractor's work
+    cudaEvent_t ev;
+    ORBB_CUDA(hL, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    ORBB_CUDA(hL, cudaEventRecord(ev, hR->stream));
+    ORBB_CUDA(hL, cudaStreamWaitEvent(hL->stream, ev, 0));
+    ORBB_CUDA(hL, cudaEventDestroy(ev));
+    k_stereo_match<<<dim3((A.kpCap + 7) / 8, nframes), 256, 0, hL->stream>>>(hL->dPlan, hL->b, hR->b, bf, b);
+    k_stereo_cut<<<nframes, 256, 0, hL->stream>>>(hL->dPlan, hL->b);
+    hL->launches += 2;
+    ORBB_CUDA(hL, cudaGetLastError());
+    return ORBB_OK;
+}
+
+int orbb_stereo_fetch(orbb_extractor* hL, int nframes, float* u_right, float* depth, int capacity) {
+    if (!hL || !hL->planValid || nframes < 1 || nframes > hL->lastFrames) return ORBB_ERR_ARG;
+    ORBB_CUDA(hL, cudaSetDevice(hL->device));
+    const Plan& P = hL->plan;
+    const int ncopy = std::min(capacity, P.kpCap);
+    if (u_right) ORBB_CUDA(hL, cudaMemcpy2DAsync(u_right, sizeof(float) * capacity, hL->b.uRight, sizeof(float) * P.kpCap, sizeof(float) * ncopy, nframes, cudaMemcpyDeviceToHost, hL->stream));
+    if (depth) ORBB_CUDA(hL, cudaMemcpy2DAsync(depth, sizeof(float) * capacity, hL->b.depth, sizeof(float) * P.kpCap, sizeof(float) * ncopy, nframes, cudaMemcpyDeviceToHost, hL->stream));
+    ORBB_CUDA(hL, cudaStreamSynchronize(hL->stream));
+    return ORBB_OK;
+}
+
+int orbb_stereo_match(orbb_extractor* hL, orbb_extractor* hR, int frame, float bf, float b, float* u_right, float* depth,
+                      int32_t* best_r, int32_t* sad, int capacity, int* n_left) {
+    if (!hL || !hR || frame < 0) return ORBB_ERR_ARG;
+    int rc = orbb_stereo_match_batch(hL, hR, frame + 1, bf, b);
+    if (rc) return rc;
+    const Plan& P = hL->plan;
+    int nL = 0;
+    ORBB_CUDA(hL, cudaMemcpyAsync(&nL, hL->b.outCount + 2 * frame, sizeof(int), cudaMemcpyDeviceToHost, hL->stream));
+    ORBB_CUDA(hL, cudaStreamSynchronize(hL->stream));
+    if (n_left) *n_left = nL;
+    if (nL > capacity) return set_err(hL, ORBB_ERR_CAPACITY, "stereo: %d left keypoints, capacity %d", nL, capacity);
+    const size_t fo = (size_t)frame * P.kpCap;
+    if (u_right) ORBB_CUDA(hL, cudaMemcpyAsync(u_right, hL->b.uRight + fo, sizeof(float) * nL, cudaMemcpyDeviceToHost, hL->stream));
+    if (depth) ORBB_CUDA(hL, cudaMemcpyAsync(depth, hL->b.depth + fo, sizeof(float) * nL, cudaMemcpyDeviceToHost, hL->stream));
+    if (best_r) ORBB_CUDA(hL, cudaMemcpyAsync(best_r, hL->b.bestR + fo, sizeof(int) * nL, cudaMemcpyDeviceToHost, hL->stream));
+    if (sad) ORBB_CUDA(hL, cudaMemcpyAsync(sad, hL->b.sad + fo, sizeof(int) * nL, cudaMemcpyDeviceToHost, hL->stream));
+    ORBB_CUDA(hL, cudaStreamSynchronize(hL->stream));
+    return ORBB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+"""Python mirror of the Hamming-matching part of ORB_SLAM3::ORBmatcher (reference orb_slam3/include/ORBmatcher.h:38-94,
+orb_slam3/src/ORBmatcher.cc) and of Frame's BFMatcher use (Frame.cc:1144-1151) on liborbb200.so.
+
+The projection geometry / MapPoint bookkeeping of the twelve Search*/Fuse methods stays in the reference's host C++
+(out of scope); what moves to the GPU is the scan itself: best/second-best over candidate lists
+(best2_csr) and the brute-force 2-NN (knn2) with the ratio test.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .constants import HISTO_LENGTH, TH_HIGH, TH_LOW
+
+INT_MAX = np.iinfo(np.int32).max
+
+
+class ORBmatcher:
+    TH_LOW = TH_LOW
+    TH_HIGH = TH_HIGH
+    HISTO_LENGTH = HISTO_LENGTH
+
+    def __init__(self, nnratio=0.6, check_ori=True, device=0):
+        self._lib = capi.load()
+        self.mfNNratio = np.float32(nnratio)
+        self.mbCheckOrientation = check_ori
+        self.device = device
+        self._m = C.c_void_p()
+        capi.check(self._lib.orbb_matcher_create(device, C.byref(self._m)))
+
+    def close(self):
+        if getattr(self, "_m", None):
+            self._lib.orbb_matcher_destroy(self._m)
+            self._m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def DescriptorDistance(a, b):
+        """ORBmatcher::DescriptorDistance (ORBmatcher.cc:2058-2074): host popcount, never a GPU round trip."""
+        a = np.ascontiguousarray(a, np.uint8)
+        b = np.ascontiguousarray(b, np.uint8)
+        return capi.load().orbb_hamming_distance(capi.ptr(a), capi.ptr(b))
+
+    # ---- brute-force 2-NN (Frame.cc:1144) ----
+    def knn2(self, query, train):
+        """host arrays [nq,32], [nd,32] uint8 -> idx[nq,2], dist[nq,2] (missing = -1 / INT_MAX)"""
+        q = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+        idx = np.full((len(q), 2), -1, np.int32)
+        dist = np.full((len(q), 2), INT_MAX, np.int32)
+        capi.check(self._lib.orbb_knn2(self._m, capi.ptr(q), len(q), capi.ptr(t), len(t), capi.ptr(idx), capi.ptr(dist)),
+                   self._m, matcher=True)
+        return idx, dist
+
+    def knn2_device(self, q_dev, nq, db_dev, nd, idx_dev, dist_dev, index_base=0):
+        """device pointers (ints / torch CUDA tensors); asynchronous on the matcher's stream"""
+        capi.check(self._lib.orbb_knn2_dev(self._m, capi.ptr(q_dev), nq, capi.ptr(db_dev), nd, index_base, capi.ptr(idx_dev),
+                                           capi.ptr(dist_dev)), self._m, matcher=True)
+
+    def merge_shards_device(self, idx_sh_dev, dist_sh_dev, nshards, nq, idx_dev, dist_dev):
+        capi.check(self._lib.orbb_knn2_merge_dev(self._m, capi.ptr(idx_sh_dev), capi.ptr(dist_sh_dev), nshards, nq,
+                                                 capi.ptr(idx_dev), capi.ptr(dist_dev)), self._m, matcher=True)
+
+    def ratio_test_device(self, idx_dev, dist_dev, nq, ratio, keep_dev):
+        capi.check(self._lib.orbb_ratio_test_dev(self._m, capi.ptr(idx_dev), capi.ptr(dist_dev), nq, float(ratio),
+                                                 capi.ptr(keep_dev)), self._m, matcher=True)
+
+    @property
+    def stream(self):
+        return self._lib.orbb_matcher_stream(self._m)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.orbb_matcher_launch_count(self._m))
+
+    # ---- best / second-best candidate scans (ORBmatcher.cc:77-120 and siblings) ----
+    def best2_csr(self, query, train, cand, rowptr, init=256):
+        q = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+        cand = np.ascontiguousarray(cand, np.int32)
+        rowptr = np.ascontiguousarray(rowptr, np.int32)
+        assert len(rowptr) == len(q) + 1
+        out = np.zeros((len(q), 4), np.int32)
+        capi.check(self._lib.orbb_best2_csr(self._m, capi.ptr(q), len(q), capi.ptr(t), len(t), capi.ptr(cand), capi.ptr(rowptr),
+                                            int(init), capi.ptr(out)), self._m, matcher=True)
+        return out
+
+    # ---- ComputeThreeMaxima (ORBmatcher.cc:2012-2053), host ----
+    @staticmethod
+    def ComputeThreeMaxima(histo_sizes):
+        max1 = max2 = max3 = 0
+        ind1 = ind2 = ind3 = -1
+        for i, s in enumerate(histo_sizes):
+            if s > max1:
+                max3, max2, max1 = max2, max1, s
+                ind3, ind2, ind1 = ind2, ind1, i
+            elif s > max2:
+                max3, max2 = max2, s
+                ind3, ind2 = ind2, i
+            elif s > max3:
+                max3, ind3 = s, i
+        if max2 < np.float32(0.1) * np.float32(max1):
+            ind2 = ind3 = -1
+        elif max3 < np.float32(0.1) * np.float32(max1):
+            ind3 = -1
+        return ind1, ind2, ind3
