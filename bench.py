@@ -1,0 +1,360 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200 ORB front-end (contract: see the task statement / DESIGN.md §Measurement).
+
+A "step" = one pass of ORB extraction (pyramid -> FAST -> quadtree -> orientation -> blur -> rBRIEF -> assembly) over one
+batch of 256 synthetic 752x480 frames, 1000 features, 8 levels, scale 1.2, FAST 20/7 (the shape BASELINE.json's metric is
+quoted on).  One process per GPU; frames are independent, so ranks get their own batches and no collective runs on the
+extraction path ("weak" scaling).  A second timed region measures the brute-force Hamming 2-NN (200k x 2M descriptors;
+database sharded over the ranks, per-shard top-2 all-gathered over NCCL and merged on the device).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          # our arm
+  python bench.py --impl reference ...                         # the reference's CPU path (oracle port) on the host cores
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "ORB extract frames/s (752x480, 1000 kp) at 1-8 B200; Hamming kNN Gpairs/s"
+W_, H_, NFEAT, NLEVELS, SCALE, INI_TH, MIN_TH = 752, 480, 1000, 8, 1.2, 20, 7
+LAPPING = (0, 1000)            # Frame.cc:311 -- the monocular call site passes {0,1000}
+BATCH = 256
+NSETS = 4                      # distinct input batches rotated through the timed steps (4 x 92 MB > 126 MB of L2)
+ALG_BYTES_PER_FRAME = W_ * H_ + 1117367 + 60 * NFEAT      # source + all pyramid levels + 60 B per keypoint
+KNN_NQ, KNN_ND = 200_000, 2_000_000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--knn-nq", type=int, default=KNN_NQ)
+    ap.add_argument("--knn-nd", type=int, default=KNN_ND)
+    ap.add_argument("--knn-steps", type=int, default=3)
+    ap.add_argument("--no-knn", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=32, help="frames in the bounded CPU sample")
+    return ap.parse_args()
+
+
+def make_frames(n, seed_offset=0):
+    from orb_slam3_ros_b200 import synth
+    return synth.sequence(H_, W_, n, base_seed=synth.BASE_SEED + 1000 * seed_offset)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation of the path (oracle port; the reference itself does not build here)
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_extract_rate(frames, threads):
+    from oracle import port          # checker / CPU baseline only
+    t0 = time.perf_counter()
+    port.extract_batch(frames, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, LAPPING, nthreads=threads, with_data=False)
+    return len(frames) / (time.perf_counter() - t0)
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = min(a.cpu_sample * max(1, cores // 8), a.batch)
+    frames = make_frames(sample)
+    for _ in range(a.warmup):
+        cpu_extract_rate(frames[: max(4, sample // 4)], cores)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        cpu_extract_rate(frames, cores)
+    dt = time.perf_counter() - t0
+    value = sample * a.steps / dt
+    knn = None
+    if not a.no_knn:
+        from oracle import port
+        from orb_slam3_ros_b200 import synth
+        nd = min(a.knn_nd, 2_000_000)
+        nq = 64 * cores
+        db, q = synth.descriptor_db(nd, nq, seed=77)
+        t1 = time.perf_counter()
+        port.knn2(q, db, nthreads=cores)
+        knn = {"value": nq * nd / (time.perf_counter() - t1) / 1e9, "unit": "Gpairs/s", "sample": f"{nq} queries x {nd} database rows"}
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"euroc_mono_{W_}x{H_}_nf{NFEAT}_nl{NLEVELS}_fast{INI_TH}/{MIN_TH}", "batch": sample,
+                   "note": "reference .cc files need OpenCV C++/Eigen/Sophus (absent): timed the oracle port, g++ -O3, all host threads"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} frames per step x {a.steps} steps, {cores} host threads"},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "knn": knn,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from orb_slam3_ros_b200 import capi, synth
+    from orb_slam3_ros_b200.extractor import ORBextractor
+    from orb_slam3_ros_b200.matcher import ORBmatcher
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: liborbb200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    B = a.batch
+    ext = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=B)
+    est = torch.cuda.ExternalStream(ext.stream, device=dev)
+    # ---- inputs: NSETS distinct batches per rank, resident in HBM before the timed region ----
+    host_sets = [torch.from_numpy(make_frames(B, seed_offset=rank * NSETS + s)).pin_memory() for s in range(NSETS)]
+    dev_sets = [h.to(dev) for h in host_sets]
+    torch.cuda.synchronize()
+
+    # ---- device-resident throughput: W warm-up steps, then EXACTLY K timed steps ----
+    for i in range(a.warmup):
+        ext.extract_batch_device(dev_sets[i % NSETS], B, W_, H_, lapping=LAPPING)
+    ext.sync()
+    counts0, _, _ = ext.fetch(B, with_data=False)
+    ext.set_profiling(True)
+    stage_acc = {}
+    launches0 = ext.launch_count
+    clocks = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    clocks.start()
+    with torch.cuda.stream(est):
+        e0.record()
+        for i in range(a.steps):
+            ext.extract_batch_device(dev_sets[i % NSETS], B, W_, H_, lapping=LAPPING)
+        e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = ext.launch_count - launches0
+    value = world * B * a.steps / (ms_total * 1e-3)
+
+    # per-stage device time (CUDA events recorded on the handle's stream inside the library), untimed extra steps
+    for i in range(3):
+        ext.extract_batch_device(dev_sets[i % NSETS], B, W_, H_, lapping=LAPPING)
+        for k, v in ext.stage_times().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v / 3
+    ext.set_profiling(False)
+
+    # ---- end to end through the public host API: pinned host frames in, keypoints + descriptors out ----
+    cap = ext.max_keypoints
+    out_k = torch.empty((B, cap, 24), dtype=torch.uint8).pin_memory()
+    out_d = torch.empty((B, cap, 32), dtype=torch.uint8).pin_memory()
+    out_c = torch.empty((B, 2), dtype=torch.int32).pin_memory()
+    outs = (out_k.numpy().view(capi.KP_DTYPE).reshape(B, cap), out_d.numpy(), out_c.numpy())
+    host_np = [h.numpy() for h in host_sets]
+    for i in range(a.warmup):
+        ext.extract_batch_host(host_np[i % NSETS], LAPPING, out=outs)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        ext.extract_batch_host(host_np[i % NSETS], LAPPING, out=outs)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * B * a.steps / e2e_s
+    clk = clocks.stop()
+    n_kp = int(outs[2][:, 0].sum())
+    h2d = B * W_ * H_
+    d2h = B * cap * (24 + 32) + B * 12
+
+    # ---- roofline of the dominant kernel (and of the whole path) ----
+    kernels = {k: v for k, v in stage_acc.items() if k not in ("h2d", "d2h") and v > 0}
+    dom = max(kernels, key=kernels.get) if kernels else "fast"
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    alg_bytes = ALG_BYTES_PER_FRAME * B
+    dom_ms = kernels.get(dom, ms_total / a.steps)
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.loads((ROOT / "profiles" / "roofline_traffic.json").read_text()).get(dom)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "kernel_ms": dom_ms,
+                "stage_ms": stage_acc,
+                "path": {"achieved": alg_bytes / (ms_total / a.steps * 1e-3) / 1e9,
+                         "frac": alg_bytes / (ms_total / a.steps * 1e-3) / 1e9 / hbm_peak}}
+
+    # ---- brute-force Hamming 2-NN: database sharded over ranks, all-gather of per-shard top-2, device merge ----
+    knn = None
+    if not a.no_knn:
+        nq, nd = a.knn_nq, a.knn_nd
+        db, q = synth.descriptor_db(nd, nq, seed=77)
+        lo, hi = rank * nd // world, (rank + 1) * nd // world
+        d_db = torch.from_numpy(db[lo:hi]).to(dev)
+        d_q = torch.from_numpy(q).to(dev)
+        m = ORBmatcher(device=local)
+        mst = torch.cuda.ExternalStream(m.stream, device=dev)
+        idx = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+        dst = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+        g_idx = torch.empty((world, nq, 2), dtype=torch.int32, device=dev)
+        g_dst = torch.empty((world, nq, 2), dtype=torch.int32, device=dev)
+        f_idx = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+        f_dst = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+        keep = torch.empty((nq,), dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+
+        def knn_step():
+            with torch.cuda.stream(mst):
+                m.knn2_device(d_q, nq, d_db, hi - lo, idx, dst, index_base=lo)
+                if world > 1:
+                    dist.all_gather_into_tensor(g_idx, idx)
+                    dist.all_gather_into_tensor(g_dst, dst)
+                    m.merge_shards_device(g_idx, g_dst, world, nq, f_idx, f_dst)
+                    m.ratio_test_device(f_idx, f_dst, nq, 0.7, keep)
+                else:
+                    m.ratio_test_device(idx, dst, nq, 0.7, keep)
+
+        knn_step()
+        barrier()
+        l0 = m.launch_count
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(mst):
+            k0.record()
+        for _ in range(a.knn_steps):
+            knn_step()
+        with torch.cuda.stream(mst):
+            k1.record()
+        barrier()
+        kms = max_over_ranks(k0.elapsed_time(k1)) / a.knn_steps
+        gp = nq * nd / (kms * 1e-3) / 1e9
+        sm_mhz = clk.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+        popc_peak_nominal = 148 * 16 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e9      # G popc/s per GPU at max clock
+        knn = {"value": gp, "unit": "Gpairs/s", "nq": nq, "nd": nd, "ms_per_step": kms, "steps": a.knn_steps, "scaling": "strong",
+               "sharding": f"database rows split over {world} rank(s); all-gather of per-shard top-2 + device merge" if world > 1 else "single shard",
+               "matched_ratio_0.7": int(keep.sum().item()),
+               "gpu_launches": m.launch_count - l0,
+               "roofline": {"bound": "popc", "achieved": 8 * gp / world, "peak": popc_peak_nominal, "unit": "Gpopc/s per GPU",
+                            "frac": 8 * gp / world / popc_peak_nominal,
+                            "peak_source": "148 SMs x 16 POPC/clk/SM x max SM clock (CUDA programming guide throughput table; see DESIGN.md)"}}
+        launches += m.launch_count - l0
+
+    # ---- CPU baseline on the box's host cores (rank 0, N=1 only), bounded sample of the same workload ----
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample = min(a.cpu_sample * max(1, cores // 8), B)
+        fr = host_np[0][:sample]
+        cpu_extract_rate(fr[:4], cores)
+        cpu = {"value": cpu_extract_rate(fr, cores), "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": f"first {sample} frames of batch 0, {cores} host threads, oracle port (g++ -O3)"}
+        cpu["single_thread_ms_per_frame"] = 1e3 / cpu_extract_rate(fr[:8], 1)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": f"euroc_mono_{W_}x{H_}_nf{NFEAT}_nl{NLEVELS}_fast{INI_TH}/{MIN_TH}", "batch": B,
+                       "frames_per_step_all_ranks": world * B, "lapping": list(LAPPING), "l2": f"{NSETS} distinct input batches "
+                       f"({NSETS * B * W_ * H_ / 1e6:.0f} MB) rotated; per-step working set (pyramids+workspaces) ~{B * 9.5 / 1e3:.1f} GB >> 126 MB L2",
+                       "parallelism": f"frames partitioned over {world} GPU(s), no collective"},
+            "keypoints_per_frame": n_kp / B,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / a.steps, "api": "orbb_extract_batch_host (pinned host frames -> keypoints+descriptors)"},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "knn": knn, "clocks": clk,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

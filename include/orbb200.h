@@ -101,6 +101,8 @@ int orbb_extract_batch_host(orbb_extractor* h, const uint8_t* host_imgs, int nfr
                             size_t row_stride, size_t frame_stride, int lap0, int lap1, orbb_keypoint* kps, uint8_t* desc,
                             int capacity, int32_t* counts);
 int orbb_sync(orbb_extractor* h);
+/* CUDA stream (cudaStream_t) the handle launches on, for callers that time with their own events */
+void* orbb_stream(orbb_extractor* h);
 /* counts: nframes*2 ints {n, mono_index}; kps/desc laid out with `capacity` entries per frame.  Synchronises. */
 int orbb_batch_fetch(orbb_extractor* h, int nframes, orbb_keypoint* kps, uint8_t* desc, int capacity, int32_t* counts);
 /* device views of the last batch's results (per-frame stride = orbb_max_keypoints entries) */

@@ -152,28 +152,58 @@ inline int fast9_arc_score(const uint8_t* p, ptrdiff_t stride) {
 
 struct RawKey { float x, y, response; };
 
+// true iff some 9-long arc of the ring is entirely brighter than v+t or entirely darker than v-t
+inline bool fast9_is_corner(const uint8_t* p, ptrdiff_t stride, int t) {
+    const int v = p[0], hi = v + t, lo = v - t;
+    // any 9-arc contains ring pixel 0 or 8, and 4 or 12 (cv::FAST's high-speed test)
+    const int p0 = p[3 * stride], p8 = p[-3 * stride];
+    bool dark = (p0 < lo) | (p8 < lo), bright = (p0 > hi) | (p8 > hi);
+    if (!(dark | bright)) return false;
+    const int p4 = p[3], p12 = p[-3];
+    dark &= (p4 < lo) | (p12 < lo);
+    bright &= (p4 > hi) | (p12 > hi);
+    if (!(dark | bright)) return false;
+    unsigned md = 0, mb = 0;
+    for (int k = 0; k < 16; k++) {
+        const int q = p[kRingDy[k] * stride + kRingDx[k]];
+        md |= (unsigned)(q < lo) << k;
+        mb |= (unsigned)(q > hi) << k;
+    }
+    auto arc9 = [](unsigned m) {
+        m |= m << 16;
+        unsigned r = m & (m >> 1);
+        r &= r >> 2;
+        r &= r >> 4;
+        r &= m >> 8;
+        return (r & 0xffffu) != 0;
+    };
+    return (dark && arc9(md)) || (bright && arc9(mb));
+}
+
 void fast9_nms(const uint8_t* img, int w, int h, size_t stride, int threshold, std::vector<RawKey>& out) {
     out.clear();
     if (w < 7 || h < 7) return;
     threshold = std::min(std::max(threshold, 0), 255);
-    std::vector<int> score((size_t)w * h, 0);
-    std::vector<uint8_t> corner((size_t)w * h, 0);
+    // three rolling score rows would do; cells are tiny (<= 76x76) so a full map is simplest
+    static thread_local std::vector<int> score;
+    score.assign((size_t)w * h, 0);
     for (int y = 3; y < h - 3; y++)
         for (int x = 3; x < w - 3; x++) {
-            int M = fast9_arc_score(img + (size_t)y * stride + x, (ptrdiff_t)stride);
-            if (M > threshold) { score[(size_t)y * w + x] = M - 1; corner[(size_t)y * w + x] = 1; }
+            const uint8_t* p = img + (size_t)y * stride + x;
+            if (!fast9_is_corner(p, (ptrdiff_t)stride, threshold)) continue;
+            // corner <=> arc score M > threshold; response = M - 1.  A corner whose response is 0 (M = 1 at
+            // threshold 0) can never win the strict '>' NMS and equals a non-corner as a neighbour.
+            score[(size_t)y * w + x] = fast9_arc_score(p, (ptrdiff_t)stride) - 1;
         }
     for (int y = 3; y < h - 3; y++)
         for (int x = 3; x < w - 3; x++) {
-            if (!corner[(size_t)y * w + x]) continue;
             const int s = score[(size_t)y * w + x];
-            bool keep = true;
-            for (int dy = -1; dy <= 1 && keep; dy++)
-                for (int dx = -1; dx <= 1; dx++) {
-                    if (!dx && !dy) continue;
-                    if (!(s > score[(size_t)(y + dy) * w + (x + dx)])) { keep = false; break; }
-                }
-            if (keep) out.push_back({(float)x, (float)y, (float)s});
+            if (s <= 0) continue;
+            const int* r0 = &score[(size_t)(y - 1) * w + x];
+            const int* r1 = r0 + w;
+            const int* r2 = r1 + w;
+            if (s > r0[-1] && s > r0[0] && s > r0[1] && s > r1[-1] && s > r1[1] && s > r2[-1] && s > r2[0] && s > r2[1])
+                out.push_back({(float)x, (float)y, (float)s});
         }
 }
 
@@ -184,20 +214,27 @@ void fast9_nms(const uint8_t* img, int w, int h, size_t stride, int threshold, s
 const int kGauss7[7] = {18, 34, 48, 56, 48, 34, 18};
 
 void gaussian7_u8(const uint8_t* src, int w, int h, size_t ss, uint8_t* dst, size_t ds) {
-    std::vector<uint16_t> hbuf((size_t)w * h);
+    static thread_local std::vector<uint16_t> hbuf;
+    hbuf.resize((size_t)w * h);
     for (int y = 0; y < h; y++) {
         const uint8_t* S = src + (size_t)y * ss;
+        uint16_t* H = &hbuf[(size_t)y * w];
         for (int x = 0; x < w; x++) {
-            unsigned acc = 0;
-            for (int k = -3; k <= 3; k++) acc += kGauss7[k + 3] * S[reflect101(x + k, w)];
-            hbuf[(size_t)y * w + x] = (uint16_t)acc;
+            if (x >= 3 && x < w - 3) {
+                H[x] = (uint16_t)(18 * (S[x - 3] + S[x + 3]) + 34 * (S[x - 2] + S[x + 2]) + 48 * (S[x - 1] + S[x + 1]) + 56 * S[x]);
+            } else {
+                unsigned acc = 0;
+                for (int k = -3; k <= 3; k++) acc += kGauss7[k + 3] * S[reflect101(x + k, w)];
+                H[x] = (uint16_t)acc;
+            }
         }
     }
     for (int y = 0; y < h; y++) {
         uint8_t* D = dst + (size_t)y * ds;
+        const uint16_t* r[7];
+        for (int k = -3; k <= 3; k++) r[k + 3] = &hbuf[(size_t)reflect101(y + k, h) * w];
         for (int x = 0; x < w; x++) {
-            unsigned acc = 0;
-            for (int k = -3; k <= 3; k++) acc += kGauss7[k + 3] * hbuf[(size_t)reflect101(y + k, h) * w + x];
+            const unsigned acc = 18u * (r[0][x] + r[6][x]) + 34u * (r[1][x] + r[5][x]) + 48u * (r[2][x] + r[4][x]) + 56u * r[3][x];
             D[x] = (uint8_t)((acc + (1u << 15)) >> 16);
         }
     }
@@ -554,6 +591,33 @@ void port_tables(void* h, float* scale, float* inv, float* sig2, float* invsig2,
 int port_extract(void* h, const uint8_t* img, int w, int hh, size_t stride, int lap0, int lap1, PortKP* kps, uint8_t* desc,
                  int cap, int* nOut, int* monoOut) {
     return ((Extractor*)h)->extract(img, w, hh, stride, lap0, lap1, kps, desc, cap, nOut, monoOut);
+}
+
+// All-core throughput: frames are independent, one Extractor per worker thread (the reference uses one extractor
+// instance per concurrently processed image, Frame.cc:122-125).  counts[f] = {n, mono}; kps/desc: cap per frame.
+int port_extract_batch(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh, const uint8_t* imgs, int nframes, int w,
+                       int hh, size_t rowStride, size_t frameStride, int lap0, int lap1, PortKP* kps, uint8_t* desc, int cap,
+                       int32_t* counts, int nthreads) {
+    nthreads = std::max(1, std::min(nthreads, nframes));
+    std::vector<int> rcs(nthreads, 0);
+    auto work = [&](int t) {
+        Extractor e(nfeatures, scaleFactor, nlevels, iniTh, minTh);
+        std::vector<PortKP> k(cap);
+        std::vector<uint8_t> d((size_t)cap * 32);
+        for (int f = t; f < nframes; f += nthreads) {
+            int n = 0, mono = 0;
+            int rc = e.extract(imgs + (size_t)f * frameStride, w, hh, rowStride, lap0, lap1, k.data(), d.data(), cap, &n, &mono);
+            if (rc) { rcs[t] = rc; return; }
+            counts[2 * f] = n; counts[2 * f + 1] = mono;
+            if (kps) memcpy(kps + (size_t)f * cap, k.data(), sizeof(PortKP) * n);
+            if (desc) memcpy(desc + (size_t)f * cap * 32, d.data(), (size_t)n * 32);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++) th.emplace_back(work, t);
+    for (auto& t : th) t.join();
+    for (int rc : rcs) if (rc) return rc;
+    return 0;
 }
 
 // bordered=1: pointer to the (w+38)x(h+38) buffer origin, else to the ROI origin

@@ -41,6 +41,9 @@ def _sig(lib):
     lib.port_extract.restype = C.c_int
     lib.port_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p,
                                  C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.port_extract_batch.restype = C.c_int
+    lib.port_extract_batch.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                       C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.port_level.restype = C.c_int
     lib.port_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int),
                                C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
@@ -155,6 +158,23 @@ class PortExtractor:
         if n:
             self._l.port_sel_keys(self._h, level, _ptr(a))
         return a
+
+
+def extract_batch(images, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, lapping=(0, 0), nthreads=1,
+                  with_data=True):
+    """All-core CPU extraction of a [n,h,w] uint8 stack -> counts[n,2], kps[n,cap], desc[n,cap,32]."""
+    images = np.ascontiguousarray(images, np.uint8)
+    n, h, w = images.shape
+    cap = nfeatures + 8 * nlevels + 64
+    counts = np.zeros((n, 2), np.int32)
+    kps = np.zeros((n, cap), KP_DTYPE) if with_data else None
+    desc = np.zeros((n, cap, 32), np.uint8) if with_data else None
+    rc = lib().port_extract_batch(nfeatures, scale_factor, nlevels, ini_th, min_th, _ptr(images), n, w, h, images.strides[1],
+                                  images.strides[0], int(lapping[0]), int(lapping[1]), _ptr(kps) if with_data else None,
+                                  _ptr(desc) if with_data else None, cap, _ptr(counts), nthreads)
+    if rc:
+        raise RuntimeError(f"port_extract_batch rc={rc}")
+    return counts, kps, desc
 
 
 def resize_linear(src, dw, dh):

@@ -46,6 +46,7 @@ SYMBOLS = [
     ("orbb_extract_batch", _I, [_VP, _VP, _I, _I, _I, _SZ, _SZ, _I, _I]),
     ("orbb_extract_batch_host", _I, [_VP, _VP, _I, _I, _I, _SZ, _SZ, _I, _I, _VP, _VP, _I, _VP]),
     ("orbb_sync", _I, [_VP]),
+    ("orbb_stream", _VP, [_VP]),
     ("orbb_batch_fetch", _I, [_VP, _I, _VP, _VP, _I, _VP]),
     ("orbb_batch_device_ptrs", _I, [_VP, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
     ("orbb_launch_count", _LL, [_VP]),

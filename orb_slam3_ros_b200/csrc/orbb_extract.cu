@@ -1088,6 +1088,7 @@ int orbb_max_keypoints(const orbb_extractor* h) {
 }
 
 long long orbb_launch_count(const orbb_extractor* h) { return h ? h->launches : 0; }
+void* orbb_stream(orbb_extractor* h) { return h ? (void*)h->stream : nullptr; }
 
 int orbb_set_profiling(orbb_extractor* h, int enabled) {
     if (!h) return ORBB_ERR_ARG;

@@ -144,6 +144,11 @@ class ORBextractor:
     def launch_count(self):
         return int(self._lib.orbb_launch_count(self._h))
 
+    @property
+    def stream(self):
+        """cudaStream_t of the handle (wrap with torch.cuda.ExternalStream to record events on it)"""
+        return self._lib.orbb_stream(self._h)
+
     # ---- stage taps (parity tests) ----
     def debug_level(self, frame, level, blurred=False, bordered=False):
         w, h = C.c_int(), C.c_int()

@@ -1,0 +1,195 @@
+"""GPU parity tests of the CUDA ORB extractor, through the C ABI (orbb_* via ctypes), against
+  (a) the oracle port (oracle/orb_port.cpp, pinned to python-cv2 by tests/test_oracle_*.py) on seeded inputs, and
+  (b) the committed golden fixtures produced with the cv2-backed oracle (tools/make_golden.py).
+Bar (BASELINE.json north_star): pyramid pixels, keypoints (pt, octave, size, response), their order and the mono index
+bit-exact; angles within 1e-3 deg; descriptor bit disagreement <= 1e-4.
+"""
+import zlib
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import port
+from orb_slam3_ros_b200 import capi, synth
+from orb_slam3_ros_b200.extractor import ORBextractor
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+ANGLE_TOL_DEG = 1e-3
+DESC_BIT_TOL = 1e-4
+
+
+def assert_same_features(k0, d0, m0, k1, d1, m1, ctx=""):
+    assert len(k0) == len(k1), f"{ctx}: keypoint count {len(k0)} vs {len(k1)}"
+    assert m0 == m1, f"{ctx}: mono index {m0} vs {m1}"
+    for f in ("x", "y", "size", "response", "octave"):
+        assert np.array_equal(k0[f], k1[f]), f"{ctx}: field {f} differs"
+    if len(k0):
+        assert np.abs(k0["angle"] - k1["angle"]).max() <= ANGLE_TOL_DEG, ctx
+        assert np.unpackbits(d0 ^ d1).sum() <= DESC_BIT_TOL * d0.size * 8, ctx
+
+
+def check_against_port(img, nf, nl, ini=20, mn=7, lap=(0, 0), stages=True):
+    pe = port.PortExtractor(nf, 1.2, nl, ini, mn)
+    rc, k0, d0, m0 = pe.extract(img, lap)
+    assert rc == 0
+    ge = ORBextractor(nf, 1.2, nl, ini, mn)
+    m1, k1, d1 = ge(img, None, lap)
+    if stages:
+        for l in range(nl):
+            assert np.array_equal(pe.level(l, bordered=True), ge.debug_level(0, l, bordered=True)), f"pyramid level {l}"
+            assert np.array_equal(pe.raw_keys(l), ge.debug_raw_keys(0, l)), f"vToDistributeKeys level {l}"
+            s = pe.selected(l)
+            want = np.stack([s["x"], s["y"], s["response"]], 1) if len(s) else np.zeros((0, 3), np.float32)
+            assert np.array_equal(want, ge.debug_selected(0, l)), f"DistributeOctTree level {l}"
+            if len(s):
+                assert np.array_equal(pe.level(l, blurred=True), ge.debug_level(0, l, blurred=True)), f"blur level {l}"
+    assert_same_features(k0, d0, m0, k1, d1, m1)
+    return ge, k1, d1
+
+
+@pytest.mark.parametrize("shape,nf,nl,lap", [
+    ((480, 752), 1000, 8, (0, 1000)),        # BASELINE config 1: EuRoC mono (Frame.cc:311 passes {0,1000})
+    ((376, 1241), 2000, 8, (0, 0)),          # config 2 shape: KITTI stereo eye
+    ((480, 640), 1000, 8, (0, 0)),           # config 3 shape: TUM RGB-D
+    ((480, 752), 5000, 8, (0, 1000)),        # monocular initialisation extractor (Tracking.cc:637: 5 x nFeatures)
+    ((134, 210), 100, 3, (0, 0)),
+    ((720, 1280), 3000, 12, (300, 900)),     # 12 levels, fisheye-style lapping split
+])
+def test_extract_matches_oracle(shape, nf, nl, lap):
+    check_against_port(synth.frame(shape[0], shape[1], nf % 17), nf, nl, lap=lap)
+
+
+def test_4k_12_levels_matches_oracle():
+    # BASELINE config 5: 3840x2160, 8000 features, 12 levels
+    check_against_port(synth.frame(2160, 3840, 5), 8000, 12, lap=(0, 0), stages=False)
+
+
+@pytest.mark.parametrize("name", ["mono_320x240", "wide_400x200", "noise_176x144", "fallback_260x200"])
+def test_golden_fixture(name):
+    g = np.load(GOLD / f"{name}.npz")
+    nf, nl, ini, mn, l0, l1 = [int(v) for v in g["params"]]
+    ge = ORBextractor(nf, 1.2, nl, ini, mn)
+    m1, k1, d1 = ge(g["image"], None, (l0, l1))
+    for l in range(nl):
+        assert zlib.crc32(ge.debug_level(0, l, bordered=True).tobytes()) == int(g["pyr_crc"][l]), f"pyramid level {l}"
+        assert len(ge.debug_raw_keys(0, l)) == int(g["raw_n"][l]), f"raw key count level {l}"
+        if int(g["blur_crc"][l]):
+            assert zlib.crc32(ge.debug_level(0, l, blurred=True).tobytes()) == int(g["blur_crc"][l]), f"blur level {l}"
+    sel = np.concatenate([np.concatenate([ge.debug_selected(0, l), np.full((len(ge.debug_selected(0, l)), 1), l, np.float32)], 1)
+                          for l in range(nl)])
+    assert np.array_equal(sel, g["sel"])
+    assert_same_features(g["kps"].view(capi.KP_DTYPE).reshape(-1), g["desc"], int(g["mono"]), k1, d1, m1, name)
+
+
+def test_empty_image_returns_minus_one():
+    ge = ORBextractor()
+    mono, k, d = ge(np.zeros((0, 0), np.uint8))
+    assert mono == -1 and len(k) == 0 and d.shape == (0, 32)              # ORBextractor.cc:1090-1091
+    lib = capi.load()
+    import ctypes as C
+    n, m = C.c_int(), C.c_int()
+    assert lib.orbb_extract(ge._h, None, 0, 0, 0, 0, 0, None, None, 0, C.byref(n), C.byref(m)) == capi.ORBB_ERR_EMPTY
+
+
+def test_flat_image_has_no_keypoints():
+    ge = ORBextractor(500, 1.2, 4)
+    mono, k, d = ge(np.full((200, 300), 90, np.uint8))
+    assert mono == 0 and len(k) == 0 and d.shape == (0, 32)               # _descriptors.release() :1108-1109
+    assert port.PortExtractor(500, 1.2, 4).extract(np.full((200, 300), 90, np.uint8))[1].size == 0
+
+
+def test_strided_input_and_handle_reuse_across_sizes():
+    big = synth.frame(300, 500, 2)
+    view = big[10:250, 20:420]                      # non-contiguous rows
+    ge, k1, d1 = check_against_port(np.ascontiguousarray(view), 400, 5)
+    m2, k2, d2 = ge(view, None, (0, 0))             # same pixels through a strided view
+    assert np.array_equal(k1, k2) and np.array_equal(d1, d2)
+    img2 = synth.frame(240, 320, 3)                 # the plan is rebuilt for a new image size
+    m3, k3, d3 = ge(img2, None, (0, 0))
+    rc, k0, d0, m0 = port.PortExtractor(400, 1.2, 5).extract(img2)
+    assert_same_features(k0, d0, m0, k3, d3, m3, "after resize")
+
+
+def test_noise_image_dense_corners_and_tie_heavy_quadtree():
+    rng = np.random.default_rng(8)
+    check_against_port(rng.integers(0, 256, (240, 320), dtype=np.uint8), 600, 5, lap=(100, 220))
+    check_against_port((rng.integers(0, 3, (200, 280)) * 100).astype(np.uint8), 300, 4)       # plateaus
+
+
+def test_thresholds_and_small_feature_budget():
+    img = synth.frame(240, 320, 9)
+    check_against_port(img, 40, 6, ini=12, mn=7)    # KITTI04-12 uses iniThFAST 12; N per level < 4*nIni at the top levels
+    check_against_port(img, 300, 4, ini=40, mn=3)
+
+
+def test_too_small_level_is_rejected():
+    ge = ORBextractor(100, 1.2, 8)
+    with pytest.raises(capi.OrbbError) as e:
+        ge(synth.frame(90, 120, 0))                 # level 7 would be 33x25: the reference divides by zero (nCols = 0)
+    assert e.value.code == capi.ORBB_ERR_UNSUPPORTED
+
+
+def test_pyramid_accessor_matches_mvImagePyramid():
+    img = synth.frame(240, 320, 4)
+    pe = port.PortExtractor(300, 1.2, 4)
+    pe.extract(img)
+    ge = ORBextractor(300, 1.2, 4)
+    ge(img)
+    for l in range(4):
+        assert np.array_equal(ge.image_pyramid(l), pe.level(l))
+        assert np.array_equal(ge.image_pyramid(l, with_border=True), pe.level(l, bordered=True))
+    assert np.array_equal(ge.GetScaleFactors(), pe.scale_factors)
+    assert np.array_equal(ge.GetInverseScaleFactors(), pe.inv_scale_factors)
+    assert np.array_equal(ge.GetScaleSigmaSquares(), pe.level_sigma2)
+    assert np.array_equal(ge.GetInverseScaleSigmaSquares(), pe.inv_level_sigma2)
+    assert np.array_equal(ge.features_per_level, pe.features_per_level)
+
+
+def test_batch_equals_single_and_host_equals_device_path():
+    import torch
+    frames = synth.sequence(240, 320, 6, canvas=512)
+    ge = ORBextractor(300, 1.2, 4, max_batch=6)
+    counts, kps, desc = ge.extract_batch_host(frames, (0, 1000))
+    single = ORBextractor(300, 1.2, 4)
+    for f in range(6):
+        m1, k1, d1 = single(frames[f], None, (0, 1000))
+        n = counts[f, 0]
+        assert n == len(k1) and counts[f, 1] == m1
+        assert np.array_equal(kps[f, :n], k1) and np.array_equal(desc[f, :n], d1)
+    dev = torch.from_numpy(frames).cuda()
+    ge.extract_batch_device(dev, 6, 320, 240, lapping=(0, 1000))
+    c2, k2, d2 = ge.fetch(6)
+    assert np.array_equal(c2, counts)
+    for f in range(6):
+        n = counts[f, 0]
+        assert np.array_equal(k2[f, :n], kps[f, :n]) and np.array_equal(d2[f, :n], desc[f, :n])
+
+
+def test_full_size_batch_properties():
+    """BASELINE-size batch (256 x 752x480): size-independent properties + spot checks against the oracle."""
+    import torch
+    B = 256
+    frames = synth.sequence(480, 752, B)
+    ge = ORBextractor(1000, 1.2, 8, max_batch=B)
+    dev = torch.from_numpy(frames).cuda()
+    ge.extract_batch_device(dev, B, 752, 480, lapping=(0, 1000))
+    c1, k1, d1 = ge.fetch(B)
+    ge.extract_batch_device(dev, B, 752, 480, lapping=(0, 1000))
+    c2, k2, d2 = ge.fetch(B)
+    assert np.array_equal(c1, c2) and np.array_equal(k1, k2) and np.array_equal(d1, d2)       # deterministic / idempotent
+    npl = ge.features_per_level
+    for f in range(B):
+        n = c1[f, 0]
+        assert 0 < n <= 1000 + 2 * 8 and c1[f, 1] == 0                   # width <= 1000: every keypoint is "lapping"
+        k = k1[f, :n]
+        assert (k["x"] >= 19).all() and (k["x"] <= 752 - 19).all() and (k["y"] >= 19).all() and (k["y"] <= 480 - 19).all()
+        assert (np.diff(k["octave"]) <= 0).all()                         # written from the back: octaves descend
+        per =np.bincount(k["octave"], minlength=8)
+        assert (per <= npl + 2).all()
+        assert ((k["angle"] >= 0) & (k["angle"] < 360)).all()
+    for f in (0, 97, 255):
+        rc, k0, d0, m0 = port.PortExtractor().extract(frames[f], (0, 1000))
+        n = c1[f, 0]
+        assert_same_features(k0, d0, m0, k1[f, :n], d1[f, :n], int(c1[f, 1]), f"frame {f}")

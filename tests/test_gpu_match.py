@@ -1,0 +1,148 @@
+"""GPU parity tests of the Hamming matcher and the stereo matcher, through the C ABI, against the oracle port
+(brute-force 2-NN pinned to cv2.BFMatcher in tests/test_oracle_primitives.py) and the committed cv2 golden vectors.
+Everything here is integer / index work: bit-exact."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import port
+from orb_slam3_ros_b200 import synth
+from orb_slam3_ros_b200.extractor import ORBextractor, compute_stereo_matches, stereo_fetch, stereo_match_batch
+from orb_slam3_ros_b200.matcher import INT_MAX, ORBmatcher
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def matcher():
+    m = ORBmatcher()
+    yield m
+    m.close()
+
+
+def test_descriptor_distance_known_answers():
+    z, f = np.zeros(32, np.uint8), np.full(32, 255, np.uint8)
+    assert ORBmatcher.DescriptorDistance(z, f) == 256 and ORBmatcher.DescriptorDistance(f, f) == 0
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        a, b = rng.integers(0, 256, (2, 32), dtype=np.uint8)
+        assert ORBmatcher.DescriptorDistance(a, b) == port.hamming(a, b)
+
+
+def test_knn2_golden_cv2_bfmatcher(matcher):
+    g = np.load(GOLD / "knn_300x4000.npz")
+    idx, dist = matcher.knn2(g["q"], g["db"])
+    assert np.array_equal(idx, g["idx"]) and np.array_equal(dist, g["dist"])
+
+
+def test_knn2_tie_rule_lowest_index(matcher):
+    q = np.zeros((3, 32), np.uint8)
+    tr = np.zeros((6, 32), np.uint8)
+    for i, d in enumerate([3, 1, 1, 2, 1, 1]):
+        tr[i, 0] = (1 << d) - 1
+    idx, dist = matcher.knn2(q, tr)
+    assert idx.tolist() == [[1, 2]] * 3 and dist.tolist() == [[1, 1]] * 3
+
+
+@pytest.mark.parametrize("nq,nd", [(1, 1), (5, 2), (1000, 1000), (1025, 70001), (3000, 300000), (17, 1 << 20)])
+def test_knn2_matches_oracle(matcher, nq, nd):
+    db, q = synth.descriptor_db(nd, nq, seed=nq + nd, dup_every=97)
+    i1, d1 = matcher.knn2(q, db)
+    i0, d0 = port.knn2(q, db, nthreads=8)
+    assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
+
+
+def test_knn2_degenerate_sizes(matcher):
+    db, q = synth.descriptor_db(10, 4, seed=1)
+    i1, d1 = matcher.knn2(q, db[:0])
+    assert (i1 == -1).all() and (d1 == INT_MAX).all()
+    i1, d1 = matcher.knn2(q, db[:1])
+    assert (i1[:, 0] == 0).all() and (i1[:, 1] == -1).all() and (d1[:, 1] == INT_MAX).all()
+    i1, d1 = matcher.knn2(q[:0], db)
+    assert i1.shape == (0, 2)
+
+
+def test_knn2_sharded_merge_equals_unsharded_and_ratio(matcher):
+    """config-4 semantics on one GPU: contiguous database shards, per-shard top-2 with global indices, merge by
+    (distance, index); the ratio test of Frame.cc:1151 afterwards."""
+    import torch
+    nq, nd, shards = 2000, 120000, 8
+    db, q = synth.descriptor_db(nd, nq, seed=4, dup_every=31)
+    d_q = torch.from_numpy(q).cuda()
+    g_idx = torch.empty((shards, nq, 2), dtype=torch.int32, device="cuda")
+    g_dst = torch.empty((shards, nq, 2), dtype=torch.int32, device="cuda")
+    parts = []
+    for s in range(shards):
+        lo, hi = s * nd // shards, (s + 1) * nd // shards
+        parts.append(torch.from_numpy(db[lo:hi]).cuda())
+        matcher.knn2_device(d_q, nq, parts[-1], hi - lo, g_idx[s], g_dst[s], index_base=lo)
+    f_idx = torch.empty((nq, 2), dtype=torch.int32, device="cuda")
+    f_dst = torch.empty((nq, 2), dtype=torch.int32, device="cuda")
+    keep = torch.empty((nq,), dtype=torch.uint8, device="cuda")
+    matcher.merge_shards_device(g_idx, g_dst, shards, nq, f_idx, f_dst)
+    matcher.ratio_test_device(f_idx, f_dst, nq, 0.7, keep)
+    torch.cuda.synchronize()
+    i0, d0 = port.knn2(q, db, nthreads=8)
+    assert np.array_equal(f_idx.cpu().numpy(), i0) and np.array_equal(f_dst.cpu().numpy(), d0)
+    want = (i0[:, 1] >= 0) & (d0[:, 0].astype(np.float32).astype(np.float64) < d0[:, 1].astype(np.float32).astype(np.float64) * 0.7)
+    got = keep.cpu().numpy().astype(bool)
+    assert np.array_equal(want, got) and 0 < got.sum() < nq
+
+
+def test_best2_csr_matches_oracle(matcher):
+    rng = np.random.default_rng(6)
+    db, q = synth.descriptor_db(5000, 800, seed=2, dup_every=13)
+    lens = rng.integers(0, 120, len(q))
+    lens[::7] = 0                                            # empty candidate lists
+    rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    cand = rng.integers(0, len(db), rowptr[-1]).astype(np.int32)
+    for init in (256, 100, 50, INT_MAX):                     # 256 (:77), TH_HIGH, TH_LOW, INT_MAX starts
+        assert np.array_equal(matcher.best2_csr(q, db, cand, rowptr, init), port.best2_csr(q, db, cand, rowptr, init)), init
+
+
+def _stereo_case(h, w, nf, idx):
+    left, right = synth.stereo_pair(h, w, idx)
+    pl, pr = port.PortExtractor(nf), port.PortExtractor(nf)
+    _, kl, dl, _ = pl.extract(left)
+    _, kr, dr, _ = pr.extract(right)
+    return left, right, pl, pr, kl, dl, kr, dr
+
+
+def test_stereo_matches_oracle_kitti_shape():
+    bf, b = np.float32(718.856 * 0.53716), np.float32(0.53716)      # config/Stereo/KITTI00-02.yaml
+    left, right, pl, pr, kl, dl, kr, dr = _stereo_case(376, 1241, 2000, 0)
+    ur0, dp0, br0, sad0, kept = port.stereo(pl, pr, kl, dl, kr, dr, bf, b)
+    gl, gr = ORBextractor(2000), ORBextractor(2000)
+    gl(left)
+    gr(right)
+    ur1, dp1, br1, sad1 = compute_stereo_matches(gl, gr, float(bf), float(b))
+    assert (ur0 >= 0).sum() > 0.3 * len(ur0)                        # the synthetic pair really exercises the matcher
+    assert np.array_equal(br0, br1) and np.array_equal(sad0, sad1)
+    assert np.array_equal(ur0, ur1) and np.array_equal(dp0, dp1)
+
+
+def test_stereo_batch_and_edge_cases():
+    import torch
+    bf, b = np.float32(380.0), np.float32(0.5)
+    pairs = [synth.stereo_pair(240, 400, i, dmax=40) for i in range(3)]
+    # pair 2: a right image without any texture -> no right keypoints -> no matches (empty vDistIdx guard)
+    pairs[2] = (pairs[2][0], np.full_like(pairs[2][1], 100))
+    L = np.stack([p[0] for p in pairs])
+    R = np.stack([p[1] for p in pairs])
+    gl, gr = ORBextractor(600, 1.2, 6, max_batch=3), ORBextractor(600, 1.2, 6, max_batch=3)
+    gl.extract_batch_device(torch.from_numpy(L).cuda(), 3, 400, 240)
+    gr.extract_batch_device(torch.from_numpy(R).cuda(), 3, 400, 240)
+    stereo_match_batch(gl, gr, 3, float(bf), float(b))
+    ur, dp = stereo_fetch(gl, 3)
+    counts, _, _ = gl.fetch(3, with_data=False)
+    for f in range(3):
+        pl, pr = port.PortExtractor(600, 1.2, 6), port.PortExtractor(600, 1.2, 6)
+        _, kl, dl, _ = pl.extract(L[f])
+        _, kr, dr, _ = pr.extract(R[f])
+        ur0, dp0, _, _, _ = port.stereo(pl, pr, kl, dl, kr, dr, bf, b)
+        n = counts[f, 0]
+        assert n == len(ur0)
+        assert np.array_equal(ur[f, :n], ur0) and np.array_equal(dp[f, :n], dp0), f
+    assert (ur[2, :counts[2, 0]] == -1).all()
