@@ -13,6 +13,7 @@
 // Compiled with -fmad=false: the un-fused float32 result is the specification.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -124,40 +125,52 @@ __global__ void __launch_bounds__(256) k_pyr_resize(const Plan* __restrict__ P, 
 // in 16 bit, vertical pass 32 bit, one rounding (acc + 2^15) >> 16; BORDER_REFLECT_101 at the IMAGE edge
 // (the reference blurs a clone of the level, so the pyramid apron is not used) (:1132-1133).
 // ------------------------------------------------------------------------------------------------
-constexpr int BLUR_TW = 64, BLUR_TH = 32;
+// One thread owns 4 adjacent columns (one 32-bit word) of a 16-row strip and slides a 7-row window of horizontal
+// sums down the strip entirely in registers: 3 aligned word loads per row (served by L1; neighbouring lanes share two
+// of them), the 7-tap horizontal sums as two IDP.4A each, the vertical pass as 4 IMAD + 3 IADD per pixel.  The
+// pyramid's own 19-px apron IS the reflect-101 extension of the level, so edge pixels need no special case.
+constexpr int BLUR_THREADS = 128, BLUR_STRIP = 16;
 
-__global__ void __launch_bounds__(256) k_blur(const Plan* __restrict__ P, Bufs B) {
-    __shared__ uint8_t sIn[BLUR_TH + 6][BLUR_TW + 8];
-    __shared__ unsigned short sH[BLUR_TH + 6][BLUR_TW];
+__device__ __forceinline__ unsigned hsum7(unsigned a, unsigned b) {
+    // a = bytes x-3..x (taps 18,34,48,56), b = bytes x+1..x+4 (taps 48,34,18,0)
+    return __dp4a(a, 0x38302212u, __dp4a(b, 0x00122230u, 0u));
+}
+
+__global__ void __launch_bounds__(BLUR_THREADS) k_blur(const Plan* __restrict__ P, Bufs B) {
     const int frame = blockIdx.y;
     int level = 0;
     while (level + 1 < P->nlevels && (int)blockIdx.x >= P->lv[level + 1].blurTileBase) level++;
     const LevelPlan& L = P->lv[level];
     if (B.selCount[frame * ORBB_MAX_LEVELS + level] == 0) return;     // :1128 levels without keypoints are skipped
-    const int t = blockIdx.x - L.blurTileBase;
-    const int tx0 = (t % L.blurTilesX) * BLUR_TW, ty0 = (t / L.blurTilesX) * BLUR_TH;
-    const uint8_t* roi = B.pyr + (size_t)frame * P->pyrStride + L.roiOff;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < (BLUR_TH + 6) * (BLUR_TW + 6); i += 256) {
-        const int r = i / (BLUR_TW + 6), c = i - r * (BLUR_TW + 6);
-        const int gy = reflect101(min(ty0 + r - 3, L.h + 2), L.h), gx = reflect101(min(tx0 + c - 3, L.w + 2), L.w);
-        sIn[r][c] = roi[(size_t)gy * L.pitch + gx];
-    }
-    __syncthreads();
-    for (int i = tid; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
-        const int r = i / BLUR_TW, c = i - r * BLUR_TW;
-        const uint8_t* p = &sIn[r][c];
-        sH[r][c] = (unsigned short)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
-    }
-    __syncthreads();
-    uint8_t* out = B.blur + (size_t)frame * P->blurStride + L.blurOff;
-    for (int i = tid; i < BLUR_TH * BLUR_TW; i += 256) {
-        const int r = i / BLUR_TW, c = i - r * BLUR_TW;
-        const int gx = tx0 + c, gy = ty0 + r;
-        if (gx < L.w && gy < L.h) {
-            const unsigned acc = 18u * (sH[r][c] + sH[r + 6][c]) + 34u * (sH[r + 1][c] + sH[r + 5][c]) +
-                                 48u * (sH[r + 2][c] + sH[r + 4][c]) + 56u * sH[r + 3][c];
-            out[(size_t)gy * L.bpitch + gx] = (uint8_t)((acc + 32768u) >> 16);
+    const int nwords = L.blurTilesX, nstrips = L.blurTilesY;
+    const int item = (blockIdx.x - L.blurTileBase) * BLUR_THREADS + threadIdx.x;
+    if (item >= nwords * nstrips) return;
+    const int strip = item / nwords, wc = item - strip * nwords;
+    const int y0 = strip * BLUR_STRIP;
+    const int rows = min(BLUR_STRIP, L.h - y0);
+    const uint8_t* src = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + 4 * wc;
+    uint8_t* out = B.blur + (size_t)frame * P->blurStride + L.blurOff + 4 * wc;
+    unsigned hw[7][4];
+#pragma unroll
+    for (int r = 0; r < BLUR_STRIP + 6; r++) {
+        if (r < rows + 6) {
+            const unsigned* row = reinterpret_cast<const unsigned*>(src + (ptrdiff_t)(y0 + r - 3) * L.pitch);
+            const unsigned w0 = __ldg(row - 1), w1 = __ldg(row), w2 = __ldg(row + 1);
+            unsigned* h = hw[r % 7];
+            h[0] = hsum7(__funnelshift_r(w0, w1, 8), __funnelshift_r(w1, w2, 8));
+            h[1] = hsum7(__funnelshift_r(w0, w1, 16), __funnelshift_r(w1, w2, 16));
+            h[2] = hsum7(__funnelshift_r(w0, w1, 24), __funnelshift_r(w1, w2, 24));
+            h[3] = hsum7(w1, w2);
+            if (r >= 6) {
+                unsigned o[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const unsigned acc = 18u * (hw[(r - 6) % 7][k] + hw[r % 7][k]) + 34u * (hw[(r - 5) % 7][k] + hw[(r - 1) % 7][k]) +
+                                         48u * (hw[(r - 4) % 7][k] + hw[(r - 2) % 7][k]) + 56u * hw[(r - 3) % 7][k] + 32768u;
+                    o[k] = acc >> 16;
+                }
+                *reinterpret_cast<unsigned*>(out + (size_t)(y0 + r - 6) * L.bpitch) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+            }
         }
     }
 }
@@ -218,7 +231,9 @@ __device__ __forceinline__ int fast_score(const uint8_t* c, int th) {
     return M - 1;
 }
 
-__global__ void __launch_bounds__(256) k_fast(const Plan* __restrict__ P, Bufs B) {
+// Straightforward formulation (one thread per pixel, full test in place).  Kept as the readable specification of
+// the per-cell semantics and selectable with ORBB_FAST_V0=1 for A/B debugging; production is k_fast in orbb_fast.cuh.
+__global__ void __launch_bounds__(256) k_fast_v0(const Plan* __restrict__ P, Bufs B) {
     __shared__ uint8_t sPix[kCellPix * kCellPix];
     __shared__ uint8_t sScore[kCellPix * kCellPix];
     __shared__ int sWarpCnt[8];
@@ -290,6 +305,8 @@ __global__ void __launch_bounds__(256) k_fast(const Plan* __restrict__ P, Bufs B
     }
     if (tid == 0) *cellCount = total;
 }
+
+#include "orbb_fast.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // K3: DistributeOctTree, one CTA per (frame, level).
@@ -885,7 +902,7 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
         if (L.nCols <= 0 || L.nRows <= 0)
             return set_err(h, ORBB_ERR_UNSUPPORTED, "level %d (%dx%d) is smaller than one 35-px FAST cell: the reference divides by zero here", l, L.w, L.h);
         L.wCell = (int)ceilf(width / L.nCols); L.hCell = (int)ceilf(height / L.nRows);
-        if (L.wCell + 6 > kCellPix || L.hCell + 6 > kCellPix) return set_err(h, ORBB_ERR_UNSUPPORTED, "cell %dx%d exceeds the kernel's tile", L.wCell, L.hCell);
+        if (L.wCell + 9 > kCellPix || L.hCell + 6 > kCellPix - 1) return set_err(h, ORBB_ERR_UNSUPPORTED, "cell %dx%d exceeds the kernel's tile", L.wCell, L.hCell);
         L.cellBase = cells;
         L.cellCap = ((L.wCell + 1) / 2) * ((L.hCell + 1) / 2);      // NMS survivors are never 8-adjacent
         L.cellKeyBase = cellKeys;
@@ -904,8 +921,8 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
         kpCap += L.selCap;
         L.scale = h->scale[l];
         L.kpSize = (float)(int)(31 * h->scale[l]);                   // :880 (PATCH_SIZE*mvScaleFactor -> int)
-        L.blurTilesX = (L.w + BLUR_TW - 1) / BLUR_TW; L.blurTilesY = (L.h + BLUR_TH - 1) / BLUR_TH;
-        L.blurTileBase = tiles; tiles += L.blurTilesX * L.blurTilesY;
+        L.blurTilesX = (L.w + 3) / 4; L.blurTilesY = (L.h + BLUR_STRIP - 1) / BLUR_STRIP;     // word columns x 16-row strips
+        L.blurTileBase = tiles; tiles += (L.blurTilesX * L.blurTilesY + BLUR_THREADS - 1) / BLUR_THREADS;
         // cv::resize tables for level l from level l-1
         if (l > 0) {
             const LevelPlan& S = P.lv[l - 1];
@@ -999,11 +1016,13 @@ static int run_batch(orbb_extractor* h, const uint8_t* dImgs, int nframes, size_
         h->launches++;
     }
     mark(h, ST_FAST);
-    k_fast<<<dim3(P.cellsTotal, nframes), 256, 0, st>>>(h->dPlan, B);
+    static const bool fastV0 = getenv("ORBB_FAST_V0") != nullptr;
+    if (fastV0) k_fast_v0<<<dim3(P.cellsTotal, nframes), 256, 0, st>>>(h->dPlan, B);
+    else k_fast<<<dim3(P.cellsTotal, nframes), FAST_THREADS, 0, st>>>(h->dPlan, B);
     mark(h, ST_OCTREE);
     k_octree<<<dim3(P.nlevels, nframes), OT_THREADS, 0, st>>>(h->dPlan, B);
     mark(h, ST_BLUR);
-    k_blur<<<dim3(P.blurTilesTotal, nframes), 256, 0, st>>>(h->dPlan, B);
+    k_blur<<<dim3(P.blurTilesTotal, nframes), BLUR_THREADS, 0, st>>>(h->dPlan, B);
     mark(h, ST_ASSEMBLE);
     k_assemble<<<nframes, 256, 0, st>>>(h->dPlan, B, lap0, lap1);
     mark(h, ST_ORIENT_DESC);
