@@ -62,62 +62,91 @@ __device__ __forceinline__ int warp_sum(int v) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1: pyramid.  Each thread produces one aligned 4-byte word of a bordered row.
+// K1: pyramid (ComputePyramid :1170-1195).  Three kernels: level 0 = copy of the source into its slab, level l =
+// cv::resize of level l-1 (image pixels only, 4 per thread), then ONE launch that fills the 19-px reflect-101 apron
+// of every level from the level's own pixels (copyMakeBorder BORDER_REFLECT_101 [| BORDER_ISOLATED]).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_pyr_level0(const Plan* __restrict__ P, Bufs B, const uint8_t* __restrict__ src,
                                                     size_t rowStride, size_t frameStride) {
     const LevelPlan& L = P->lv[0];
-    const int word = blockIdx.x * blockDim.x + threadIdx.x;
-    const int by = blockIdx.y;                      // bordered row 0 .. h+37
+    const int word = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     const int frame = blockIdx.z;
-    if (word * 4 >= L.pitch) return;
-    const int sy = reflect101(by - kEdge, L.h);
-    const uint8_t* s = src + (size_t)frame * frameStride + (size_t)sy * rowStride;
-    uint8_t out[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int ix = word * 4 + k - kRoiX;
-        out[k] = (ix >= -kEdge && ix < L.w + kEdge) ? __ldg(s + reflect101(ix, L.w)) : (uint8_t)0;
+    if (word * 4 >= L.w || y >= L.h) return;
+    const uint8_t* s = src + (size_t)frame * frameStride + (size_t)y * rowStride + word * 4;
+    unsigned v;
+    if ((((uintptr_t)s) & 3) == 0 && word * 4 + 3 < L.w) {
+        v = __ldg(reinterpret_cast<const unsigned*>(s));
+    } else {
+        const int n = min(4, L.w - word * 4);
+        v = 0;
+        for (int k = 0; k < n; k++) v |= (unsigned)__ldg(s + k) << (8 * k);
     }
-    uint8_t* d = B.pyr + (size_t)frame * P->pyrStride + L.pyrOff + (size_t)by * L.pitch;
-    *reinterpret_cast<uchar4*>(d + word * 4) = make_uchar4(out[0], out[1], out[2], out[3]);
+    uint8_t* d = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + (size_t)y * L.pitch;
+    reinterpret_cast<unsigned*>(d)[word] = v;
 }
 
-// cv::resize INTER_LINEAR 8UC1: tables hold (source index, packed int16 coefficient pair) per destination
-// column / row, computed on the host exactly as OpenCV does (build_plan).  The apron is produced in the same pass
-// by evaluating the reflected destination coordinate (copyMakeBorder BORDER_REFLECT_101 | BORDER_ISOLATED).
+// cv::resize INTER_LINEAR 8UC1 (imgproc/resize.cpp, HResizeLinear/VResizeLinear fixed point): tables hold (source
+// index, packed int16 coefficient pair) per destination column / row, computed on the host exactly as OpenCV does
+// (build_plan).  horizontal: S[sx]*a0 + S[sx+1]*a1 (x2048); vertical: (((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2) >> 2.
 __global__ void __launch_bounds__(256) k_pyr_resize(const Plan* __restrict__ P, Bufs B, int level) {
     const LevelPlan& L = P->lv[level];
     const LevelPlan& S = P->lv[level - 1];
-    const int word = blockIdx.x * blockDim.x + threadIdx.x;
-    const int by = blockIdx.y;
+    const int word = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int dy = blockIdx.y * 8 + (threadIdx.x >> 5);
     const int frame = blockIdx.z;
-    if (word * 4 >= L.pitch) return;
-    const uint8_t* slab = B.pyr + (size_t)frame * P->pyrStride;
-    const uint8_t* sroi = slab + S.roiOff;
-    const int2 ty = __ldg(B.tab + L.tabY + reflect101(by - kEdge, L.h));
+    if (word * 4 >= L.w || dy >= L.h) return;
+    const uint8_t* sroi = B.pyr + (size_t)frame * P->pyrStride + S.roiOff;
+    const int2 ty = __ldg(B.tab + L.tabY + dy);
     const int sy0 = min(max(ty.x, 0), S.h - 1), sy1 = min(max(ty.x + 1, 0), S.h - 1);
-    const int b0 = (short)(ty.y & 0xffff), b1 = (short)(ty.y >> 16);
+    const int b0 = (short)(ty.y & 0xffff), b1 = ty.y >> 16;
     const uint8_t* r0 = sroi + (size_t)sy0 * S.pitch;
     const uint8_t* r1 = sroi + (size_t)sy1 * S.pitch;
-    uint8_t out[4];
+    const int2* tx = B.tab + L.tabX + word * 4;     // the table is padded to a multiple of 4 entries
+    unsigned packed = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const int ix = word * 4 + k - kRoiX;
-        int v = 0;
-        if (ix >= -kEdge && ix < L.w + kEdge) {
-            const int2 tx = __ldg(B.tab + L.tabX + reflect101(ix, L.w));
-            const int sx = tx.x, sx1 = min(sx + 1, S.w - 1);
-            const int a0 = (short)(tx.y & 0xffff), a1 = (short)(tx.y >> 16);
-            const int h0 = r0[sx] * a0 + r0[sx1] * a1;
-            const int h1 = r1[sx] * a0 + r1[sx1] * a1;
-            v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-            v = min(max(v, 0), 255);
-        }
-        out[k] = (uint8_t)v;
+        const int2 t = __ldg(tx + k);
+        const int sx = t.x, sx1 = min(sx + 1, S.w - 1);
+        const int a0 = (short)(t.y & 0xffff), a1 = t.y >> 16;
+        const int h0 = r0[sx] * a0 + r0[sx1] * a1;
+        const int h1 = r1[sx] * a0 + r1[sx1] * a1;
+        const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        packed |= (unsigned)min(max(v, 0), 255) << (8 * k);
     }
-    uint8_t* d = B.pyr + (size_t)frame * P->pyrStride + L.pyrOff + (size_t)by * L.pitch;
-    *reinterpret_cast<uchar4*>(d + word * 4) = make_uchar4(out[0], out[1], out[2], out[3]);
+    uint8_t* d = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + (size_t)dy * L.pitch;
+    reinterpret_cast<unsigned*>(d)[word] = packed;
+}
+
+// apron of all levels in one launch: one warp per bordered row (8 rows per CTA); the lanes stride over the words of
+// that row that contain apron pixels -- the whole row in the top/bottom bands, ~11 words at the two ends otherwise.
+__global__ void __launch_bounds__(256) k_pyr_apron(const Plan* __restrict__ P, Bufs B, int totalRows) {
+    int by = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (by >= totalRows) return;
+    const int lane = threadIdx.x & 31, frame = blockIdx.y;
+    int level = 0;
+    while (by >= P->lv[level].h + 2 * kEdge) { by -= P->lv[level].h + 2 * kEdge; level++; }
+    const LevelPlan& L = P->lv[level];
+    const int iy = by - kEdge;
+    uint8_t* roi = B.pyr + (size_t)frame * P->pyrStride + L.roiOff;
+    const uint8_t* srow = roi + (ptrdiff_t)reflect101(iy, L.h) * L.pitch;
+    uint8_t* drow = roi + (ptrdiff_t)iy * L.pitch;
+    const int firstWord = (kRoiX - kEdge) >> 2, lastWord = (kRoiX + L.w + kEdge - 1) >> 2;      // words holding bordered columns
+    const bool band = iy < 0 || iy >= L.h;
+    const int leftEnd = (kRoiX >> 2) - 1;                   // last word left of the image
+    const int rightBegin = (kRoiX + L.w) >> 2;              // first word holding a column >= w
+    const int nLeft = leftEnd - firstWord + 1, nRight = lastWord - rightBegin + 1;
+    const int nItems = band ? lastWord - firstWord + 1 : nLeft + nRight;
+    for (int i = lane; i < nItems; i += 32) {
+        const int word = band ? firstWord + i : (i < nLeft ? firstWord + i : rightBegin + (i - nLeft));
+        const int ix0 = word * 4 - kRoiX;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int ix = ix0 + k;
+            const bool image = !band && ix >= 0 && ix < L.w;
+            if (!image && ix >= -kEdge && ix < L.w + kEdge) drow[ix] = srow[reflect101(ix, L.w)];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -307,6 +336,7 @@ __global__ void __launch_bounds__(256) k_fast_v0(const Plan* __restrict__ P, Buf
 }
 
 #include "orbb_fast.cuh"
+#include "orbb_fast2.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // K3: DistributeOctTree, one CTA per (frame, level).
@@ -733,10 +763,21 @@ __global__ void __launch_bounds__(256) k_assemble(const Plan* __restrict__ P, Bu
 // K4 + K5b: one warp per keypoint -- IC_Angle over the umax disc (:76-103), cv::fastAtan2 (un-fused float32),
 // then the 256 steered rBRIEF tests on the blurred level (:107-146).
 // ------------------------------------------------------------------------------------------------
-struct PatternT { signed char v[8][32][4]; };      // [test-in-byte][byte][x0,y0,x1,y1] -> conflict-free per lane
 __constant__ signed char cPattern[256][4] = {
 #include "orb_pattern.inc"
 };
+// the same table as floats, transposed so that lane i (descriptor byte i) finds its test j at [j*32 + i]; filled once
+// per process by k_init_pattern (identical for every handle)
+__device__ float4 gPatF[256];
+__global__ void k_init_pattern() {
+    const int i = threadIdx.x >> 3, j = threadIdx.x & 7;
+    const signed char* p = cPattern[8 * i + j];
+    gPatF[j * 32 + i] = make_float4((float)p[0], (float)p[1], (float)p[2], (float)p[3]);
+}
+
+// cvRound(float) for |v| < 2^22 without the F2I (XU pipe) instruction: adding 1.5*2^23 makes the FADD itself round
+// to nearest-even at integer granularity; the integer sits in the low mantissa bits.
+__device__ __forceinline__ int round_rne(float v) { return __float_as_int(__fadd_rn(v, 12582912.f)) - 0x4B400000; }
 
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     // cv::fastAtan2 scalar path; p-coefficients are the float products OpenCV stores
@@ -761,34 +802,27 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 }
 
 __global__ void __launch_bounds__(256) k_orient_desc(const Plan* __restrict__ P, Bufs B) {
-    __shared__ signed char sPat[8][32][4];
     const int frame = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    {   // transpose the pattern so that lane i (descriptor byte i) reads test j at [j][i]
-        const int i = tid >> 3, j = tid & 7;       // byte i, test j  <- pattern row 8*i + j
-#pragma unroll
-        for (int k = 0; k < 4; k++) sPat[j][i][k] = cPattern[8 * i + j][k];
-    }
-    __syncthreads();
     const int n = B.outCount[frame * 2];
     const int g = blockIdx.x * 8 + warp;
     if (g >= n) return;
     const WorkItem wi = B.work[(size_t)frame * P->kpCap + g];
     const LevelPlan& L = P->lv[wi.level];
-    // ---- IC_Angle: lane u-15 covers column u of every row of the disc ----
-    const uint8_t* center = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + (size_t)wi.y * L.pitch + wi.x;
-    const int u = lane - 15;
+    // ---- IC_Angle: lane u-15 covers column u of every row of the disc; umax (:453-468) for HALF_PATCH_SIZE 15 ----
+    constexpr int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+    const int u = lane - 15, au = u < 0 ? -u : u;
+    const uint8_t* center = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + (size_t)wi.y * L.pitch + wi.x + u;
     int m10 = 0, m01 = 0;
-#pragma unroll 1
+#pragma unroll
     for (int v = -15; v <= 15; v++) {
-        const int d = P->umax[v < 0 ? -v : v];
-        if (lane < 31 && u >= -d && u <= d) {
-            const int val = center[v * L.pitch + u];
-            m10 += u * val;
+        if (au <= kUmax[v < 0 ? -v : v]) {          // lane 31 (u = 16) is never inside the disc
+            const int val = center[v * L.pitch];
+            m10 += val;
             m01 += v * val;
         }
     }
-    m10 = warp_sum(m10);
+    m10 = warp_sum(m10 * u);
     m01 = warp_sum(m01);
     const float angle = fast_atan2_deg((float)m01, (float)m10);
     orbb_keypoint* kp = B.kps + (size_t)frame * P->kpCap + wi.pos;
@@ -802,12 +836,11 @@ __global__ void __launch_bounds__(256) k_orient_desc(const Plan* __restrict__ P,
     unsigned val = 0;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        const char4 pt = *reinterpret_cast<const char4*>(&sPat[j][lane][0]);
-        const float x0 = (float)pt.x, y0 = (float)pt.y, x1 = (float)pt.z, y1 = (float)pt.w;
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));      // :118
-        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));      // :119
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const float4 pt = __ldg(&gPatF[j * 32 + lane]);
+        const int r0 = round_rne(__fadd_rn(__fmul_rn(pt.x, b), __fmul_rn(pt.y, a)));      // :118
+        const int c0 = round_rne(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, b)));      // :119
+        const int r1 = round_rne(__fadd_rn(__fmul_rn(pt.z, b), __fmul_rn(pt.w, a)));
+        const int c1 = round_rne(__fsub_rn(__fmul_rn(pt.z, a), __fmul_rn(pt.w, b)));
         const int t0 = bc[r0 * step + c0], t1 = bc[r1 * step + c1];
         val |= (unsigned)(t0 < t1) << j;
     }
@@ -882,7 +915,7 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
     std::vector<int2> tab;
     size_t pyrBytes = 0, blurBytes = 0;
     unsigned cellKeys = 0, raw = 0, nodes = 0, sel = 0;
-    int cells = 0, tiles = 0, kpCap = 0;
+    int cells = 0, tiles = 0, kpCap = 0, fsTiles = 0;
     for (int l = 0; l < nl; l++) {
         LevelPlan& L = P.lv[l];
         L.w = cv_round_f((float)W * h->invScale[l]);                 // :1175
@@ -923,6 +956,9 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
         L.kpSize = (float)(int)(31 * h->scale[l]);                   // :880 (PATCH_SIZE*mvScaleFactor -> int)
         L.blurTilesX = (L.w + 3) / 4; L.blurTilesY = (L.h + BLUR_STRIP - 1) / BLUR_STRIP;     // word columns x 16-row strips
         L.blurTileBase = tiles; tiles += (L.blurTilesX * L.blurTilesY + BLUR_THREADS - 1) / BLUR_THREADS;
+        L.fsTilesX = ((L.w + 3) / 4 + 31) / 32;
+        L.fsGroups = ((L.h - 2 * kEdge + FS_R - 1) / FS_R + 3) / 4;
+        L.fsBase = fsTiles; fsTiles += L.fsTilesX * L.fsGroups;
         // cv::resize tables for level l from level l-1
         if (l > 0) {
             const LevelPlan& S = P.lv[l - 1];
@@ -938,6 +974,7 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
                 const short a0 = (short)cv_round_f((1.f - fx) * 2048.f), a1 = (short)cv_round_f(fx * 2048.f);
                 tab.push_back(make_int2(sx, (int)((unsigned short)a0 | ((unsigned)(unsigned short)a1 << 16))));
             }
+            while ((tab.size() - (size_t)L.tabX) % 4) tab.push_back(tab.back());     // k_pyr_resize reads 4 entries per thread
             L.tabY = (int)tab.size();
             for (int dy = 0; dy < L.h; dy++) {
                 float fy = (float)((dy + 0.5) * scale_y - 0.5);
@@ -948,7 +985,7 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
             }
         }
     }
-    P.cellsTotal = cells; P.blurTilesTotal = tiles; P.kpCap = kpCap;
+    P.cellsTotal = cells; P.blurTilesTotal = tiles; P.kpCap = kpCap; P.fsTotal = fsTiles;
     P.pyrStride = pyrBytes; P.blurStride = blurBytes;
     P.cellKeyStride = cellKeys; P.rawStride = raw; P.nodeStride = nodes; P.selStride = sel;
 
@@ -958,6 +995,7 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
 #define A(ptr, count) if ((rc = dev_alloc(h, &ptr, (count))) != ORBB_OK) return rc
     A(b.pyr, F * pyrBytes);
     A(b.blur, F * blurBytes);
+    A(b.score, F * blurBytes);
     A(b.tab, tab.size());
     A(b.cellCount, F * cells);
     A(b.cellOff, F * cells);
@@ -1008,17 +1046,30 @@ static int run_batch(orbb_extractor* h, const uint8_t* dImgs, int nframes, size_
     cudaStream_t st = h->stream;
     mark(h, ST_PYRAMID);
     ORBB_CUDA(h, cudaMemsetAsync(B.status, 0, sizeof(int) * nframes, st));
+    int borderedRows = 0, maxPitch = 0;
     for (int l = 0; l < P.nlevels; l++) {
         const LevelPlan& L = P.lv[l];
-        dim3 grid((L.pitch / 4 + 255) / 256, L.h + 2 * kEdge, nframes);
+        dim3 grid(((L.w + 3) / 4 + 31) / 32, (L.h + 7) / 8, nframes);
         if (l == 0) k_pyr_level0<<<grid, 256, 0, st>>>(h->dPlan, B, dImgs, rowStride, frameStride);
         else k_pyr_resize<<<grid, 256, 0, st>>>(h->dPlan, B, l);
         h->launches++;
+        borderedRows += L.h + 2 * kEdge;
+        maxPitch = std::max(maxPitch, L.pitch);
     }
+    k_pyr_apron<<<dim3((borderedRows + 7) / 8, nframes), 256, 0, st>>>(h->dPlan, B, borderedRows);
+    h->launches++;
     mark(h, ST_FAST);
-    static const bool fastV0 = getenv("ORBB_FAST_V0") != nullptr;
-    if (fastV0) k_fast_v0<<<dim3(P.cellsTotal, nframes), 256, 0, st>>>(h->dPlan, B);
-    else k_fast<<<dim3(P.cellsTotal, nframes), FAST_THREADS, 0, st>>>(h->dPlan, B);
+    static const char* fastMode = getenv("ORBB_FAST_MODE");      // debugging: "v0" / "cell" select the older formulations
+    if (fastMode && !strcmp(fastMode, "v0")) {
+        k_fast_v0<<<dim3(P.cellsTotal, nframes), 256, 0, st>>>(h->dPlan, B);
+    } else if (fastMode && !strcmp(fastMode, "cell")) {
+        k_fast<<<dim3(P.cellsTotal, nframes), FAST_THREADS, 0, st>>>(h->dPlan, B, 0);
+    } else {
+        k_fast_score<<<dim3(P.fsTotal, nframes), FS_THREADS, 0, st>>>(h->dPlan, B);
+        k_fast_cells<<<dim3(P.cellsTotal, nframes), FC_THREADS, 0, st>>>(h->dPlan, B);
+        k_fast<<<dim3(P.cellsTotal, nframes), FAST_THREADS, 0, st>>>(h->dPlan, B, 1);
+        h->launches += 2;
+    }
     mark(h, ST_OCTREE);
     k_octree<<<dim3(P.nlevels, nframes), OT_THREADS, 0, st>>>(h->dPlan, B);
     mark(h, ST_BLUR);
@@ -1069,6 +1120,12 @@ int orbb_create(const orbb_params* prm, orbb_extractor** out) {
         return ORBB_ERR_CUDA;
     }
     for (int i = 0; i <= ST_COUNT; i++) cudaEventCreate(&h->ev[i]);
+    k_init_pattern<<<1, 256, 0, h->stream>>>();
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) {
+        set_err(nullptr, ORBB_ERR_CUDA, "pattern init failed: %s", cudaGetErrorString(cudaGetLastError()));
+        orbb_destroy(h);
+        return ORBB_ERR_CUDA;
+    }
     *out = h;
     return ORBB_OK;
 }

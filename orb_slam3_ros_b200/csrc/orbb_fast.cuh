@@ -36,7 +36,9 @@ __device__ __forceinline__ bool arc9(unsigned m16) {
 __device__ __forceinline__ int min3i(int a, int b, int c) { return min(min(a, b), c); }
 __device__ __forceinline__ int max3i(int a, int b, int c) { return max(max(a, b), c); }
 
-__global__ void __launch_bounds__(FAST_THREADS) k_fast(const Plan* __restrict__ P, Bufs B) {
+// mode 0: both thresholds (iniTh, then minTh if the cell stays empty).  mode 1: only cells that k_fast_cells marked -1
+// (no corner at iniTh), minTh only.
+__global__ void __launch_bounds__(FAST_THREADS) k_fast(const Plan* __restrict__ P, Bufs B, int mode) {
     constexpr int PS = kCellPix;
     __shared__ __align__(16) uint8_t sPix[PS * PS];
     __shared__ __align__(16) uint8_t sScore[PS * PS];
@@ -53,6 +55,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(const Plan* __restrict__ 
     const int ci = c / L.nCols, cj = c - ci * L.nCols;
     const int tid = threadIdx.x, lane = tid & 31;
     int* cellCount = B.cellCount + (size_t)frame * P->cellsTotal + gcell;
+    if (mode == 1 && *cellCount != -1) return;
     const int iniX = kMinBorder + cj * L.wCell, iniY = kMinBorder + ci * L.hCell;
     const int maxX = min(iniX + L.wCell + 6, L.maxBX), maxY = min(iniY + L.hCell + 6, L.maxBY);
     const int rw = maxX - iniX, rh = maxY - iniY;
@@ -63,10 +66,11 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(const Plan* __restrict__ 
     // ---- stage the ROI with aligned 32-bit loads: tile column 0 = level column (iniX & ~3) ----
     const int sh = iniX & 3;                       // ROI column x lives at tile column x + sh
     const int nw = (rw + sh + 3) >> 2;             // words per tile row (<= 20)
+    const unsigned mw = (65536u + nw - 1) / nw;    // i / nw == (i * mw) >> 16 for i < 3276 (rh * nw <= 1600)
     {
         const uint8_t* g = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + (size_t)iniY * L.pitch + (iniX - sh);
         for (int i = tid; i < rh * nw; i += FAST_THREADS) {
-            const int r = i / nw, w = i - r * nw;
+            const int r = (int)(((unsigned)i * mw) >> 16), w = i - r * nw;
             reinterpret_cast<unsigned*>(sPix)[r * (PS / 4) + w] = __ldg(reinterpret_cast<const unsigned*>(g + (size_t)r * L.pitch) + w);
         }
     }
@@ -78,7 +82,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(const Plan* __restrict__ 
     unsigned* sSurv = reinterpret_cast<unsigned*>(sCand);
     int total = 0;
 
-    for (int pass = 0; pass < 2 && total == 0; pass++) {
+    for (int pass = mode; pass < 2 && total == 0; pass++) {
         const int th = min(max(pass == 0 ? P->iniTh : P->minTh, 0), 255);
         __syncthreads();
         if (tid < 3) sCnt[tid] = 0;
@@ -92,7 +96,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(const Plan* __restrict__ 
             unsigned cand = 0;
             int pos0 = 0;
             if (i < items) {
-                const int r = i / nw, w = i - r * nw;
+                const int r = (int)(((unsigned)i * mw) >> 16), w = i - r * nw;
                 const int y = r + 3;
                 const unsigned* row = reinterpret_cast<const unsigned*>(sPix) + y * (PS / 4) + w;
                 const unsigned wc = row[0];

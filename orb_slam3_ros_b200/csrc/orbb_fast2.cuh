@@ -1,0 +1,232 @@
+// K2, level-wide formulation (production path): the FAST score of a pixel does not depend on the 35-px cell it falls
+// in -- only the non-maximum suppression and the "no corner in this cell -> retry with minThFAST" decision do
+// (reference ORBextractor.cc:805-872).  So:
+//
+//   k_fast_score   regular tiles over each level, no cell geometry: quick reject (4 px / thread / row, sliding 7-row
+//                  register window, byte-SIMD) -> per-CTA candidate list -> 16-pixel ring test -> exact score.
+//                  Writes a score byte map (0 = not a corner at iniThFAST, else response = arc score - 1).
+//   k_fast_cells   one CTA per cell: loads the cell interior of the score map (zero outside: NMS never looks across a
+//                  cell border), NMS, raster-ordered output.  Cells without any survivor are marked -1 ...
+//   k_fast(mode 1) ... and only those run the per-cell pipeline of orbb_fast.cuh again at minThFAST.
+//
+// (included INSIDE namespace orbb, after orbb_fast.cuh)
+#pragma once
+
+constexpr int FS_THREADS = 128, FS_R = 8;
+constexpr int FS_CAP = FS_THREADS * FS_R * 4;       // pixels per CTA
+
+__device__ __forceinline__ unsigned quick_mask4(unsigned wl, unsigned wc, unsigned wr, unsigned wt, unsigned wb, unsigned K) {
+    const unsigned pl = __funnelshift_r(wl, wc, 8);      // bytes x-3 .. x
+    const unsigned pr = __funnelshift_r(wc, wr, 24);     // bytes x+3 .. x+6
+    const unsigned a0 = __vabsdiffu4(wc, wt), a8 = __vabsdiffu4(wc, wb);
+    const unsigned a4 = __vabsdiffu4(wc, pr), a12 = __vabsdiffu4(wc, pl);
+    const unsigned me = umin16x2(umax16x2(prmt(a0, 0, 0x4240), prmt(a8, 0, 0x4240)), umax16x2(prmt(a4, 0, 0x4240), prmt(a12, 0, 0x4240)));
+    const unsigned mo = umin16x2(umax16x2(prmt(a0, 0, 0x4341), prmt(a8, 0, 0x4341)), umax16x2(prmt(a4, 0, 0x4341), prmt(a12, 0, 0x4341)));
+    const unsigned te = me + K, to = mo + K;             // bit 15 / 31 of a 16-bit lane set  <=>  value > th
+    return ((te >> 15) & 1u) | ((to >> 14) & 2u) | ((te >> 29) & 4u) | ((to >> 28) & 8u);
+}
+
+__global__ void __launch_bounds__(FS_THREADS) k_fast_score(const Plan* __restrict__ P, Bufs B) {
+    __shared__ unsigned short sCand[FS_CAP];
+    __shared__ unsigned short sCorner[FS_CAP];
+    __shared__ int sCnt[2];
+    const int frame = blockIdx.y;
+    int level = 0;
+    while (level + 1 < P->nlevels && (int)blockIdx.x >= P->lv[level + 1].fsBase) level++;
+    const LevelPlan& L = P->lv[level];
+    const int t = blockIdx.x - L.fsBase;
+    const int gy = t / L.fsTilesX, gx = t - gy * L.fsTilesX;
+    const int tid = threadIdx.x, lane = tid & 31, ty = tid >> 5;
+    const int wcol = gx * 32 + lane;
+    const int y0 = kEdge + (gy * 4 + ty) * FS_R;
+    const int xlo = kEdge, xhi = L.w - kEdge, yhi = L.h - kEdge;      // union of the cell interiors: [19, w-19) x [19, h-19)
+    const int th = min(max(P->iniTh, 0), 255);
+    const unsigned K = (unsigned)(0x7fff - th) * 0x00010001u;
+    const uint8_t* roi = B.pyr + (size_t)frame * P->pyrStride + L.roiOff;
+    uint8_t* score = B.score + (size_t)frame * P->blurStride + L.blurOff;
+    if (tid < 2) sCnt[tid] = 0;
+    __syncthreads();
+
+    // ---- A: quick reject over FS_R rows, 4 pixels per thread and row ----
+    unsigned candAll = 0;
+    if (wcol * 4 < L.w && y0 < yhi) {
+        unsigned xmask = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) xmask |= (unsigned)(wcol * 4 + k >= xlo && wcol * 4 + k < xhi) << k;
+        const uint8_t* src = roi + 4 * wcol;
+        unsigned wl[7], wm[7], wr[7];
+#pragma unroll
+        for (int r = 0; r < FS_R + 6; r++) {
+            const unsigned* row = reinterpret_cast<const unsigned*>(src + (ptrdiff_t)(y0 - 3 + r) * L.pitch);
+            wm[r % 7] = __ldg(row);
+            if (r >= 3 && r < FS_R + 3) { wl[r % 7] = __ldg(row - 1); wr[r % 7] = __ldg(row + 1); }
+            if (r >= 6) {
+                const int yc = y0 + r - 6;
+                const int c = (r - 3) % 7;
+                const unsigned m = quick_mask4(wl[c], wm[c], wr[c], wm[r % 7], wm[(r - 6) % 7], K) & xmask;
+                if (yc < yhi) {
+                    *reinterpret_cast<unsigned*>(score + (size_t)yc * L.bpitch + 4 * wcol) = 0u;
+                    candAll |= m << (4 * (r - 6));
+                }
+            }
+        }
+    }
+    {
+        const int cnt = __popc(candAll);
+        const int inc = warp_incl_scan(cnt, lane);
+        const int wtot = __shfl_sync(0xffffffffu, inc, 31);
+        int wbase = 0;
+        if (lane == 31 && wtot) wbase = atomicAdd(&sCnt[0], wtot);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        int o = wbase + inc - cnt;
+        while (candAll) {
+            const int b = __ffs(candAll) - 1;
+            candAll &= candAll - 1;
+            sCand[o++] = (unsigned short)((ty << 10) | ((b >> 2) << 7) | (lane << 2) | (b & 3));
+        }
+    }
+    __syncthreads();
+
+    // ---- B: full ring test on the candidates ----
+    const int nCand = sCnt[0];
+    for (int base = 0; base < nCand; base += FS_THREADS) {
+        const int i = base + tid;
+        bool corner = false;
+        unsigned rec = 0;
+        if (i < nCand) {
+            const unsigned id = sCand[i];
+            const int x = (gx * 32 + (int)((id >> 2) & 31)) * 4 + (int)(id & 3);
+            const int y = kEdge + (gy * 4 + (int)(id >> 10)) * FS_R + (int)((id >> 7) & 7);
+            const uint8_t* q = roi + (size_t)y * L.pitch + x;
+            const int PS = L.pitch;
+            const int v = q[0], hi = v + th, lo = v - th;
+            unsigned mb = 0, md = 0;
+#define ORBB_RING(off)                                       \
+    {                                                        \
+        const int p = q[off];                                \
+        mb = __funnelshift_l((unsigned)(p - lo), mb, 1);     \
+        md = __funnelshift_l((unsigned)(hi - p), md, 1);     \
+    }
+            ORBB_RING(3 * PS) ORBB_RING(3 * PS + 1) ORBB_RING(2 * PS + 2) ORBB_RING(PS + 3)
+            ORBB_RING(3) ORBB_RING(-PS + 3) ORBB_RING(-2 * PS + 2) ORBB_RING(-3 * PS + 1)
+            ORBB_RING(-3 * PS) ORBB_RING(-3 * PS - 1) ORBB_RING(-2 * PS - 2) ORBB_RING(-PS - 3)
+            ORBB_RING(-3) ORBB_RING(PS - 3) ORBB_RING(2 * PS - 2) ORBB_RING(3 * PS - 1)
+#undef ORBB_RING
+            const bool cb = arc9(mb & 0xffffu), cd = arc9(md & 0xffffu);
+            corner = cb | cd;
+            rec = id | (cd ? 0x8000u : 0u);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, corner);
+        int wbase = 0;
+        if (lane == 0 && bal) wbase = atomicAdd(&sCnt[1], __popc(bal));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (corner) sCorner[wbase + __popc(bal & ((1u << lane) - 1))] = (unsigned short)rec;
+    }
+    __syncthreads();
+
+    // ---- C: exact score of the corners -> score map ----
+    const int nCorner = sCnt[1];
+    for (int i = tid; i < nCorner; i += FS_THREADS) {
+        const unsigned rec = sCorner[i];
+        const unsigned id = rec & 0x7fffu;
+        const int x = (gx * 32 + (int)((id >> 2) & 31)) * 4 + (int)(id & 3);
+        const int y = kEdge + (gy * 4 + (int)((id >> 10) & 3)) * FS_R + (int)((id >> 7) & 7);
+        const uint8_t* q = roi + (size_t)y * L.pitch + x;
+        const int PS = L.pitch;
+        const int v = q[0];
+        const int sgn = (rec & 0x8000u) ? -1 : 1;
+        int d[16];
+        d[0] = sgn * (v - q[3 * PS]);       d[1] = sgn * (v - q[3 * PS + 1]);   d[2] = sgn * (v - q[2 * PS + 2]);
+        d[3] = sgn * (v - q[PS + 3]);       d[4] = sgn * (v - q[3]);            d[5] = sgn * (v - q[-PS + 3]);
+        d[6] = sgn * (v - q[-2 * PS + 2]);  d[7] = sgn * (v - q[-3 * PS + 1]);  d[8] = sgn * (v - q[-3 * PS]);
+        d[9] = sgn * (v - q[-3 * PS - 1]);  d[10] = sgn * (v - q[-2 * PS - 2]); d[11] = sgn * (v - q[-PS - 3]);
+        d[12] = sgn * (v - q[-3]);          d[13] = sgn * (v - q[PS - 3]);      d[14] = sgn * (v - q[2 * PS - 2]);
+        d[15] = sgn * (v - q[3 * PS - 1]);
+        int m3[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) m3[k] = min3i(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+        int M = -256;
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {
+            const int e0 = min3i(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+            const int e1 = min3i(m3[k + 1], m3[(k + 4) & 15], m3[(k + 7) & 15]);
+            M = max3i(M, e0, e1);
+        }
+        score[(size_t)y * L.bpitch + x] = (uint8_t)(M - 1);
+    }
+}
+
+constexpr int FC_THREADS = 128;
+
+__global__ void __launch_bounds__(FC_THREADS) k_fast_cells(const Plan* __restrict__ P, Bufs B) {
+    constexpr int PS = kCellPix;
+    __shared__ __align__(16) uint8_t sS[PS * PS];
+    __shared__ unsigned sSurv[37 * 37 + 3];
+    __shared__ int sCnt;
+    const int frame = blockIdx.y;
+    const int gcell = blockIdx.x;
+    int level = 0;
+    while (level + 1 < P->nlevels && gcell >= P->lv[level + 1].cellBase) level++;
+    const LevelPlan& L = P->lv[level];
+    const int c = gcell - L.cellBase;
+    const int ci = c / L.nCols, cj = c - ci * L.nCols;
+    const int tid = threadIdx.x;
+    int* cellCount = B.cellCount + (size_t)frame * P->cellsTotal + gcell;
+    const int iniX = kMinBorder + cj * L.wCell, iniY = kMinBorder + ci * L.hCell;
+    const int maxX = min(iniX + L.wCell + 6, L.maxBX), maxY = min(iniY + L.hCell + 6, L.maxBY);
+    if (iniY >= L.maxBY - 3 || iniX >= L.maxBX - 6 || maxX - iniX < 7 || maxY - iniY < 7) {     // :810,:819
+        if (tid == 0) *cellCount = 0;
+        return;
+    }
+    const int gx0 = iniX + 3, gx1 = maxX - 3, gy0 = iniY + 3, gy1 = maxY - 3;     // cell interior, level coordinates
+    const int ih = gy1 - gy0;
+    const int a0 = (gx0 - 1) & ~3;                  // level column of tile column 0 (leaves >= 1 halo column)
+    const int nw = (gx1 + 1 - a0 + 3) >> 2;         // words per tile row (<= 20)
+    const unsigned mw = (65536u + nw - 1) / nw;
+    const uint8_t* score = B.score + (size_t)frame * P->blurStride + L.blurOff;
+    if (tid == 0) sCnt = 0;
+    // tile row r <-> level row gy0 - 1 + r ; everything outside the interior is zero
+    for (int i = tid; i < (ih + 2) * nw; i += FC_THREADS) {
+        const int r = (int)(((unsigned)i * mw) >> 16), w = i - r * nw;
+        unsigned v = 0;
+        if (r >= 1 && r <= ih) {
+            const int col0 = a0 + 4 * w;
+            const int lo = min(max(gx0 - col0, 0), 4), hi = min(max(gx1 - col0, 0), 4);
+            if (hi > lo) {
+                v = __ldg(reinterpret_cast<const unsigned*>(score + (size_t)(gy0 - 1 + r) * L.bpitch + col0));
+                v &= (0xffffffffu >> (8 * (4 - hi))) & (0xffffffffu << (8 * lo));
+            }
+        }
+        reinterpret_cast<unsigned*>(sS)[r * (PS / 4) + w] = v;
+    }
+    __syncthreads();
+    // ---- NMS: strict '>' against the 8 neighbours (cv::FAST, fast.cpp) ----
+    for (int i = tid; i < ih * nw; i += FC_THREADS) {
+        const int r = (int)(((unsigned)i * mw) >> 16), w = i - r * nw;
+        const unsigned word = reinterpret_cast<const unsigned*>(sS)[(r + 1) * (PS / 4) + w];
+        if (word == 0) continue;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int s = (word >> (8 * k)) & 0xff;
+            if (s == 0) continue;
+            const int pos = (r + 1) * PS + 4 * w + k;
+            const uint8_t* q = &sS[pos];
+            if (s > q[-1] && s > q[1] && s > q[-PS - 1] && s > q[-PS] && s > q[-PS + 1] && s > q[PS - 1] && s > q[PS] && s > q[PS + 1])
+                sSurv[atomicAdd(&sCnt, 1)] = ((unsigned)pos << 8) | (unsigned)s;
+        }
+    }
+    __syncthreads();
+    // ---- raster order by rank counting; keys are relative to the 16-px border (:865-866) ----
+    const int nSurv = sCnt;
+    u64* out = B.cellKeys + (size_t)frame * P->cellKeyStride + L.cellKeyBase + (size_t)c * L.cellCap;
+    for (int i = tid; i < nSurv; i += FC_THREADS) {
+        const unsigned rec = sSurv[i];
+        int rank = 0;
+        for (int j = 0; j < nSurv; j++) rank += sSurv[j] < rec;
+        const int pos = (int)(rec >> 8);
+        const int r = pos / PS, col = pos - r * PS;
+        const int x = a0 + col - kMinBorder, y = gy0 - 1 + r - kMinBorder;
+        out[rank] = (u64)(unsigned)x | ((u64)(unsigned)y << 16) | ((u64)(rec & 0xffu) << 32);
+    }
+    if (tid == 0) *cellCount = nSurv ? nSurv : -1;     // -1: retry this cell with minThFAST (k_fast, mode 1)
+}

@@ -38,12 +38,12 @@ struct LevelPlan {
     int selCap;
     float scale, kpSize;
     int blurTileBase, blurTilesX, blurTilesY;
-    int pad0;
+    int fsBase, fsTilesX, fsGroups;    // k_fast_score tiling: 32 word-columns x (4 strips of 8 rows) per CTA
 };
 
 struct Plan {
     int nlevels, W, H;
-    int cellsTotal, blurTilesTotal;
+    int cellsTotal, blurTilesTotal, fsTotal;
     int kpCap;
     int iniTh, minTh;
     u64 pyrStride, blurStride;                                  // bytes per frame
@@ -64,6 +64,7 @@ struct WorkItem { int level, x, y, pos; };
 struct Bufs {
     uint8_t* pyr;
     uint8_t* blur;
+    uint8_t* score;                // FAST response map per level (same layout as blur)
     int2* tab;                     // resize tables (shared by all frames)
     int* cellCount;
     int* cellOff;
