@@ -118,8 +118,9 @@ __global__ void __launch_bounds__(256) k_pyr_resize(const Plan* __restrict__ P, 
     reinterpret_cast<unsigned*>(d)[word] = packed;
 }
 
-// apron of all levels in one launch: one warp per bordered row (8 rows per CTA); the lanes stride over the words of
-// that row that contain apron pixels -- the whole row in the top/bottom bands, ~11 words at the two ends otherwise.
+// apron of all levels in one launch: one warp per bordered row (8 rows per CTA).  Rows above / below the image copy
+// the reflected image row word by word; every row then fixes the (at most 12) words at its two ends byte by byte.
+// |offset| <= 19 < image size, so reflect-101 is a single fold.
 __global__ void __launch_bounds__(256) k_pyr_apron(const Plan* __restrict__ P, Bufs B, int totalRows) {
     int by = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (by >= totalRows) return;
@@ -128,25 +129,18 @@ __global__ void __launch_bounds__(256) k_pyr_apron(const Plan* __restrict__ P, B
     while (by >= P->lv[level].h + 2 * kEdge) { by -= P->lv[level].h + 2 * kEdge; level++; }
     const LevelPlan& L = P->lv[level];
     const int iy = by - kEdge;
+    const int sy = iy < 0 ? -iy : (iy >= L.h ? 2 * L.h - 2 - iy : iy);
     uint8_t* roi = B.pyr + (size_t)frame * P->pyrStride + L.roiOff;
-    const uint8_t* srow = roi + (ptrdiff_t)reflect101(iy, L.h) * L.pitch;
+    const uint8_t* srow = roi + (ptrdiff_t)sy * L.pitch;
     uint8_t* drow = roi + (ptrdiff_t)iy * L.pitch;
-    const int firstWord = (kRoiX - kEdge) >> 2, lastWord = (kRoiX + L.w + kEdge - 1) >> 2;      // words holding bordered columns
-    const bool band = iy < 0 || iy >= L.h;
-    const int leftEnd = (kRoiX >> 2) - 1;                   // last word left of the image
-    const int rightBegin = (kRoiX + L.w) >> 2;              // first word holding a column >= w
-    const int nLeft = leftEnd - firstWord + 1, nRight = lastWord - rightBegin + 1;
-    const int nItems = band ? lastWord - firstWord + 1 : nLeft + nRight;
-    for (int i = lane; i < nItems; i += 32) {
-        const int word = band ? firstWord + i : (i < nLeft ? firstWord + i : rightBegin + (i - nLeft));
-        const int ix0 = word * 4 - kRoiX;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int ix = ix0 + k;
-            const bool image = !band && ix >= 0 && ix < L.w;
-            if (!image && ix >= -kEdge && ix < L.w + kEdge) drow[ix] = srow[reflect101(ix, L.w)];
-        }
+    if (sy != iy) {
+        const int nfull = L.w >> 2;          // image words copied whole (source row is final: written by an earlier kernel)
+        for (int w = lane; w < nfull; w += 32) reinterpret_cast<unsigned*>(drow)[w] = reinterpret_cast<const unsigned*>(srow)[w];
     }
+    // columns [-19, 0) and [w & ~3, w + 19): lanes 0..18 left, lanes 0..21 right (one byte each)
+    if (lane < kEdge) drow[-1 - lane] = srow[1 + lane];
+    const int x = (L.w & ~3) + lane;
+    if (lane < kEdge + 3 && x < L.w + kEdge && (sy != iy || x >= L.w)) drow[x] = srow[x >= L.w ? 2 * L.w - 2 - x : x];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -913,6 +907,7 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
     P.iniTh = h->prm.ini_th_fast; P.minTh = h->prm.min_th_fast;
     for (int i = 0; i < 16; i++) P.umax[i] = h->umax[i];
     std::vector<int2> tab;
+    std::vector<CellDesc> cellDesc;
     size_t pyrBytes = 0, blurBytes = 0;
     unsigned cellKeys = 0, raw = 0, nodes = 0, sel = 0;
     int cells = 0, tiles = 0, kpCap = 0, fsTiles = 0;
@@ -939,6 +934,18 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
         L.cellBase = cells;
         L.cellCap = ((L.wCell + 1) / 2) * ((L.hCell + 1) / 2);      // NMS survivors are never 8-adjacent
         L.cellKeyBase = cellKeys;
+        for (int ci = 0; ci < L.nRows; ci++)
+            for (int cj = 0; cj < L.nCols; cj++) {                   // :805-822
+                const int iniX = kMinBorder + cj * L.wCell, iniY = kMinBorder + ci * L.hCell;
+                const int maxX = std::min(iniX + L.wCell + 6, L.maxBX), maxY = std::min(iniY + L.hCell + 6, L.maxBY);
+                CellDesc d;
+                const bool skip = iniY >= L.maxBY - 3 || iniX >= L.maxBX - 6 || maxX - iniX < 7 || maxY - iniY < 7;
+                d.gx0 = (short)(iniX + 3); d.gx1 = (short)(skip ? iniX + 3 : maxX - 3);
+                d.gy0 = (short)(iniY + 3); d.gy1 = (short)(skip ? iniY + 3 : maxY - 3);
+                d.level = l;
+                d.outOff = L.cellKeyBase + (unsigned)((ci * L.nCols + cj) * L.cellCap);
+                cellDesc.push_back(d);
+            }
         cells += L.nCols * L.nRows;
         cellKeys += (unsigned)(L.nCols * L.nRows * L.cellCap);
         // quadtree (:559-561)
@@ -997,7 +1004,12 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
     A(b.blur, F * blurBytes);
     A(b.score, F * blurBytes);
     A(b.tab, tab.size());
+    CellDesc* dCellDesc = nullptr;
+    A(dCellDesc, cellDesc.size());
+    b.cellDesc = dCellDesc;
     A(b.cellCount, F * cells);
+    A(b.fbList, F * cells);
+    A(b.fbCount, F);
     A(b.cellOff, F * cells);
     A(b.cellKeys, F * cellKeys);
     A(b.keys, F * 2 * raw);
@@ -1021,6 +1033,7 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
     A(h->dPlan, 1);
 #undef A
     if (!tab.empty()) ORBB_CUDA(h, cudaMemcpyAsync(b.tab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+    ORBB_CUDA(h, cudaMemcpyAsync(dCellDesc, cellDesc.data(), cellDesc.size() * sizeof(CellDesc), cudaMemcpyHostToDevice, h->stream));
     ORBB_CUDA(h, cudaMemcpyAsync(h->dPlan, &P, sizeof P, cudaMemcpyHostToDevice, h->stream));
     ORBB_CUDA(h, cudaStreamSynchronize(h->stream));
     h->capacity = frames;
@@ -1039,13 +1052,29 @@ static void mark(orbb_extractor* h, int stage) {
     if (h->profiling) cudaEventRecord(h->ev[stage], h->stream);
 }
 
-// the launch sequence for `nframes` device-resident frames
-static int run_batch(orbb_extractor* h, const uint8_t* dImgs, int nframes, size_t rowStride, size_t frameStride, int lap0, int lap1) {
+// view of the per-frame buffers starting at frame f0 (kernels index frames from 0)
+static Bufs shift_bufs(const Bufs& b, const Plan& P, int f0) {
+    Bufs s = b;
+    const size_t f = (size_t)f0;
+    s.pyr += f * P.pyrStride; s.blur += f * P.blurStride; s.score += f * P.blurStride;
+    s.cellCount += f * P.cellsTotal; s.cellOff += f * P.cellsTotal; s.fbList += f * P.cellsTotal; s.fbCount += f;
+    s.cellKeys += f * P.cellKeyStride; s.keys += f * 2 * P.rawStride; s.nodes += f * 2 * P.nodeStride;
+    s.rec += f * P.nodeStride; s.cnt4 += f * P.nodeStride; s.pend += f * 2 * P.nodeStride; s.elist += f * P.nodeStride;
+    s.erased += f * P.nodeStride; s.sel += f * P.selStride; s.selCount += f * ORBB_MAX_LEVELS;
+    s.work += f * P.kpCap; s.kps += f * P.kpCap; s.desc += f * P.kpCap * 32; s.outCount += f * 2; s.status += f;
+    s.uRight += f * P.kpCap; s.depth += f * P.kpCap; s.bestR += f * P.kpCap; s.sad += f * P.kpCap;
+    return s;
+}
+
+// the launch sequence for `nframes` device-resident frames whose buffers start at frame f0
+static int run_batch(orbb_extractor* h, const uint8_t* dImgs, int nframes, size_t rowStride, size_t frameStride, int lap0, int lap1,
+                     int f0 = 0) {
     const Plan& P = h->plan;
-    const Bufs& B = h->b;
+    const Bufs B = f0 ? shift_bufs(h->b, P, f0) : h->b;
     cudaStream_t st = h->stream;
     mark(h, ST_PYRAMID);
     ORBB_CUDA(h, cudaMemsetAsync(B.status, 0, sizeof(int) * nframes, st));
+    ORBB_CUDA(h, cudaMemsetAsync(B.fbCount, 0, sizeof(int) * nframes, st));
     int borderedRows = 0, maxPitch = 0;
     for (int l = 0; l < P.nlevels; l++) {
         const LevelPlan& L = P.lv[l];
@@ -1067,7 +1096,7 @@ static int run_batch(orbb_extractor* h, const uint8_t* dImgs, int nframes, size_
     } else {
         k_fast_score<<<dim3(P.fsTotal, nframes), FS_THREADS, 0, st>>>(h->dPlan, B);
         k_fast_cells<<<dim3(P.cellsTotal, nframes), FC_THREADS, 0, st>>>(h->dPlan, B);
-        k_fast<<<dim3(P.cellsTotal, nframes), FAST_THREADS, 0, st>>>(h->dPlan, B, 1);
+        k_fast<<<dim3(std::min(P.cellsTotal, 48), nframes), FAST_THREADS, 0, st>>>(h->dPlan, B, 1);
         h->launches += 2;
     }
     mark(h, ST_OCTREE);
@@ -1081,7 +1110,7 @@ static int run_batch(orbb_extractor* h, const uint8_t* dImgs, int nframes, size_
     mark(h, ST_D2H);
     h->launches += 5;
     ORBB_CUDA(h, cudaGetLastError());
-    h->lastFrames = nframes;
+    h->lastFrames = f0 + nframes;
     h->hPyrFresh = false;
     return ORBB_OK;
 }
@@ -1120,6 +1149,12 @@ int orbb_create(const orbb_params* prm, orbb_extractor** out) {
         return ORBB_ERR_CUDA;
     }
     for (int i = 0; i <= ST_COUNT; i++) cudaEventCreate(&h->ev[i]);
+    cudaStreamCreateWithFlags(&h->h2dStream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&h->d2hStream, cudaStreamNonBlocking);
+    for (int i = 0; i < 8; i++) {
+        cudaEventCreateWithFlags(&h->evH2D[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&h->evDone[i], cudaEventDisableTiming);
+    }
     k_init_pattern<<<1, 256, 0, h->stream>>>();
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) {
         set_err(nullptr, ORBB_ERR_CUDA, "pattern init failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1139,6 +1174,9 @@ void orbb_destroy(orbb_extractor* h) {
     if (h->hPyr) cudaFreeHost(h->hPyr);
     if (h->hCounts) cudaFreeHost(h->hCounts);
     for (int i = 0; i <= ST_COUNT; i++) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < 8; i++) { if (h->evH2D[i]) cudaEventDestroy(h->evH2D[i]); if (h->evDone[i]) cudaEventDestroy(h->evDone[i]); }
+    if (h->h2dStream) cudaStreamDestroy(h->h2dStream);
+    if (h->d2hStream) cudaStreamDestroy(h->d2hStream);
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1207,6 +1245,9 @@ int orbb_sync(orbb_extractor* h) {
     return ORBB_OK;
 }
 
+static cudaError_t copy_rows(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows, cudaMemcpyKind kind,
+                             cudaStream_t st);
+
 static int ensure_counts(orbb_extractor* h, int nframes) {
     if (h->hCountsCap >= nframes) return ORBB_OK;
     if (h->hCounts) cudaFreeHost(h->hCounts);
@@ -1227,11 +1268,11 @@ int orbb_batch_fetch(orbb_extractor* h, int nframes, orbb_keypoint* kps, uint8_t
     ORBB_CUDA(h, cudaMemcpyAsync(h->hCounts + 2 * nframes, h->b.status, sizeof(int) * nframes, cudaMemcpyDeviceToHost, h->stream));
     const int ncopy = std::min(capacity, P.kpCap);
     if (kps && ncopy > 0)
-        ORBB_CUDA(h, cudaMemcpy2DAsync(kps, sizeof(orbb_keypoint) * capacity, h->b.kps, sizeof(orbb_keypoint) * P.kpCap,
-                                       sizeof(orbb_keypoint) * ncopy, nframes, cudaMemcpyDeviceToHost, h->stream));
+        ORBB_CUDA(h, copy_rows(kps, sizeof(orbb_keypoint) * capacity, h->b.kps, sizeof(orbb_keypoint) * P.kpCap,
+                               sizeof(orbb_keypoint) * ncopy, nframes, cudaMemcpyDeviceToHost, h->stream));
     if (desc && ncopy > 0)
-        ORBB_CUDA(h, cudaMemcpy2DAsync(desc, (size_t)32 * capacity, h->b.desc, (size_t)32 * P.kpCap, (size_t)32 * ncopy, nframes,
-                                       cudaMemcpyDeviceToHost, h->stream));
+        ORBB_CUDA(h, copy_rows(desc, (size_t)32 * capacity, h->b.desc, (size_t)32 * P.kpCap, (size_t)32 * ncopy, nframes,
+                               cudaMemcpyDeviceToHost, h->stream));
     ORBB_CUDA(h, cudaStreamSynchronize(h->stream));
     for (int f = 0; f < nframes; f++) {
         counts[2 * f] = h->hCounts[2 * f];
@@ -1250,32 +1291,76 @@ int orbb_batch_device_ptrs(orbb_extractor* h, const orbb_keypoint** kps, const u
     return ORBB_OK;
 }
 
+// strided-or-contiguous async copy of `rows` rows of `width` bytes
+static cudaError_t copy_rows(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows, cudaMemcpyKind kind,
+                             cudaStream_t st) {
+    if (dpitch == width && spitch == width) return cudaMemcpyAsync(dst, src, width * rows, kind, st);      // one linear DMA
+    return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, st);
+}
+
 int orbb_extract_batch_host(orbb_extractor* h, const uint8_t* host_imgs, int nframes, int width, int height, size_t row_stride,
                             size_t frame_stride, int lap0, int lap1, orbb_keypoint* kps, uint8_t* desc, int capacity, int32_t* counts) {
-    if (!h) return ORBB_ERR_ARG;
+    if (!h || !counts) return ORBB_ERR_ARG;
     if (!host_imgs || nframes <= 0 || width <= 0 || height <= 0) return set_err(h, ORBB_ERR_EMPTY, "empty image");
     ORBB_CUDA(h, cudaSetDevice(h->device));
     int rc = ensure_plan(h, width, height, nframes);
     if (rc) return rc;
+    if ((rc = ensure_counts(h, nframes))) return rc;
+    const Plan& P = h->plan;
     // device staging area for the raw frames: tightly packed WxH
-    const size_t need = (size_t)nframes * width * height;
+    const size_t fbytes = (size_t)width * height, need = (size_t)nframes * fbytes;
     if (h->hImgBytes < need) {
         if (h->hImg) cudaFree(h->hImg);
         h->hImg = nullptr; h->hImgBytes = 0;
         ORBB_CUDA(h, cudaMalloc((void**)&h->hImg, need));
         h->hImgBytes = need;
     }
+    // Pipeline in up to 8 chunks of frames: H2D (copy engine 1) -> kernels (handle stream) -> D2H (copy engine 2), so the
+    // upload of chunk c+1 and the download of chunk c-1 overlap the kernels of chunk c.
+    const int nchunks = nframes >= 64 ? 8 : (nframes >= 8 ? 2 : 1);
+    const int per = (nframes + nchunks - 1) / nchunks;
+    const int ncopy = std::min(capacity, P.kpCap);
+    ORBB_CUDA(h, cudaEventRecord(h->evDone[0], h->stream));                  // earlier work on the handle's stream ...
+    ORBB_CUDA(h, cudaStreamWaitEvent(h->h2dStream, h->evDone[0], 0));       // ... must finish before the staging area is reused
     mark(h, ST_H2D);
-    if (frame_stride == (size_t)height * row_stride) {
-        ORBB_CUDA(h, cudaMemcpy2DAsync(h->hImg, width, host_imgs, row_stride, width, (size_t)height * nframes, cudaMemcpyHostToDevice, h->stream));
-    } else {
-        for (int f = 0; f < nframes; f++)
-            ORBB_CUDA(h, cudaMemcpy2DAsync(h->hImg + (size_t)f * width * height, width, host_imgs + (size_t)f * frame_stride, row_stride, width,
-                                           height, cudaMemcpyHostToDevice, h->stream));
+    for (int c = 0; c < nchunks; c++) {
+        const int f0 = c * per, n = std::min(per, nframes - f0);
+        if (n <= 0) break;
+        const uint8_t* src = host_imgs + (size_t)f0 * frame_stride;
+        if (frame_stride == (size_t)height * row_stride) {
+            ORBB_CUDA(h, copy_rows(h->hImg + f0 * fbytes, width, src, row_stride, width, (size_t)height * n, cudaMemcpyHostToDevice, h->h2dStream));
+        } else {
+            for (int f = 0; f < n; f++)
+                ORBB_CUDA(h, copy_rows(h->hImg + (f0 + f) * fbytes, width, src + (size_t)f * frame_stride, row_stride, width, height,
+                                       cudaMemcpyHostToDevice, h->h2dStream));
+        }
+        ORBB_CUDA(h, cudaEventRecord(h->evH2D[c], h->h2dStream));
     }
-    rc = run_batch(h, h->hImg, nframes, (size_t)width, (size_t)width * height, lap0, lap1);
-    if (rc) return rc;
-    return orbb_batch_fetch(h, nframes, kps, desc, capacity, counts);
+    for (int c = 0; c < nchunks; c++) {
+        const int f0 = c * per, n = std::min(per, nframes - f0);
+        if (n <= 0) break;
+        ORBB_CUDA(h, cudaStreamWaitEvent(h->stream, h->evH2D[c], 0));
+        if ((rc = run_batch(h, h->hImg + f0 * fbytes, n, (size_t)width, fbytes, lap0, lap1, f0))) return rc;
+        ORBB_CUDA(h, cudaEventRecord(h->evDone[c], h->stream));
+        ORBB_CUDA(h, cudaStreamWaitEvent(h->d2hStream, h->evDone[c], 0));
+        ORBB_CUDA(h, cudaMemcpyAsync(h->hCounts + 2 * f0, h->b.outCount + 2 * f0, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, h->d2hStream));
+        ORBB_CUDA(h, cudaMemcpyAsync(h->hCounts + 2 * nframes + f0, h->b.status + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, h->d2hStream));
+        if (kps && ncopy > 0)
+            ORBB_CUDA(h, copy_rows(kps + (size_t)f0 * capacity, sizeof(orbb_keypoint) * capacity, h->b.kps + (size_t)f0 * P.kpCap,
+                                   sizeof(orbb_keypoint) * P.kpCap, sizeof(orbb_keypoint) * ncopy, n, cudaMemcpyDeviceToHost, h->d2hStream));
+        if (desc && ncopy > 0)
+            ORBB_CUDA(h, copy_rows(desc + (size_t)f0 * capacity * 32, (size_t)32 * capacity, h->b.desc + (size_t)f0 * P.kpCap * 32,
+                                   (size_t)32 * P.kpCap, (size_t)32 * ncopy, n, cudaMemcpyDeviceToHost, h->d2hStream));
+    }
+    ORBB_CUDA(h, cudaStreamSynchronize(h->d2hStream));
+    ORBB_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int f = 0; f < nframes; f++) {
+        counts[2 * f] = h->hCounts[2 * f];
+        counts[2 * f + 1] = h->hCounts[2 * f + 1];
+        if (h->hCounts[2 * nframes + f]) return set_err(h, ORBB_ERR_INTERNAL, "frame %d: device status 0x%x (capacity overflow)", f, h->hCounts[2 * nframes + f]);
+        if (counts[2 * f] > capacity && (kps || desc)) return set_err(h, ORBB_ERR_CAPACITY, "frame %d has %d keypoints, capacity %d", f, counts[2 * f], capacity);
+    }
+    return ORBB_OK;
 }
 
 int orbb_extract(orbb_extractor* h, const uint8_t* img, int width, int height, size_t stride, int lap0, int lap1,

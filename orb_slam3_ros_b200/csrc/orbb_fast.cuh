@@ -47,22 +47,21 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(const Plan* __restrict__ 
     __shared__ int sCnt[3];
 
     const int frame = blockIdx.y;
-    const int gcell = blockIdx.x;
-    int level = 0;
-    while (level + 1 < P->nlevels && gcell >= P->lv[level + 1].cellBase) level++;
-    const LevelPlan& L = P->lv[level];
-    const int c = gcell - L.cellBase;
-    const int ci = c / L.nCols, cj = c - ci * L.nCols;
     const int tid = threadIdx.x, lane = tid & 31;
+    // mode 1: persistent CTAs walk the frame's list of cells that stayed empty at iniThFAST
+    const int nWork = mode == 1 ? B.fbCount[frame] : P->cellsTotal;
+    for (int work = blockIdx.x; work < nWork; work += gridDim.x) {
+    const int gcell = mode == 1 ? B.fbList[(size_t)frame * P->cellsTotal + work] : work;
+    const CellDesc cd = B.cellDesc[gcell];
+    const LevelPlan& L = P->lv[cd.level];
     int* cellCount = B.cellCount + (size_t)frame * P->cellsTotal + gcell;
-    if (mode == 1 && *cellCount != -1) return;
-    const int iniX = kMinBorder + cj * L.wCell, iniY = kMinBorder + ci * L.hCell;
-    const int maxX = min(iniX + L.wCell + 6, L.maxBX), maxY = min(iniY + L.hCell + 6, L.maxBY);
-    const int rw = maxX - iniX, rh = maxY - iniY;
-    if (iniY >= L.maxBY - 3 || iniX >= L.maxBX - 6 || rw < 7 || rh < 7) {     // :810,:819; FAST_t on a <7-px ROI
+    const int iniX = cd.gx0 - 3, iniY = cd.gy0 - 3;
+    const int rw = cd.gx1 - cd.gx0 + 6, rh = cd.gy1 - cd.gy0 + 6;
+    if (cd.gx1 <= cd.gx0) {                        // cell skipped by the reference (:810,:819) or smaller than 7 px
         if (tid == 0) *cellCount = 0;
-        return;
+        continue;
     }
+    __syncthreads();                               // previous work item is done with the shared tiles
     // ---- stage the ROI with aligned 32-bit loads: tile column 0 = level column (iniX & ~3) ----
     const int sh = iniX & 3;                       // ROI column x lives at tile column x + sh
     const int nw = (rw + sh + 3) >> 2;             // words per tile row (<= 20)
@@ -77,8 +76,8 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(const Plan* __restrict__ 
     const int ih = rh - 6;
     const int x0 = 3 + sh, x1 = rw - 3 + sh;       // interior tile columns [x0, x1)
     const int items = ih * nw;
-    u64* out = B.cellKeys + (size_t)frame * P->cellKeyStride + L.cellKeyBase + (size_t)c * L.cellCap;
-    const int kx = cj * L.wCell - sh, ky = ci * L.hCell;          // :865-866 (tile column -> ROI column)
+    u64* out = B.cellKeys + (size_t)frame * P->cellKeyStride + cd.outOff;
+    const int kx = iniX - kMinBorder - sh, ky = iniY - kMinBorder;          // :865-866 (tile column -> ROI column)
     unsigned* sSurv = reinterpret_cast<unsigned*>(sCand);
     int total = 0;
 
@@ -229,5 +228,6 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(const Plan* __restrict__ 
         total = nSurv;
     }
     if (tid == 0) *cellCount = total;
+    }
 }
 

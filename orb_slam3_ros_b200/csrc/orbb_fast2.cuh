@@ -26,9 +26,14 @@ __device__ __forceinline__ unsigned quick_mask4(unsigned wl, unsigned wc, unsign
     return ((te >> 15) & 1u) | ((to >> 14) & 2u) | ((te >> 29) & 4u) | ((to >> 28) & 8u);
 }
 
+// tile of one CTA: 32 word-columns (+1 halo word each side) x (4 strips x FS_R rows + 6 halo rows)
+constexpr int FS_TP = 34 * 4 + 8;                   // tile pitch in bytes (144: rows stay 16-byte aligned)
+constexpr int FS_TROWS = 4 * FS_R + 6;
+
 __global__ void __launch_bounds__(FS_THREADS) k_fast_score(const Plan* __restrict__ P, Bufs B) {
-    __shared__ unsigned short sCand[FS_CAP];
-    __shared__ unsigned short sCorner[FS_CAP];
+    __shared__ __align__(16) uint8_t sTile[FS_TROWS * FS_TP];
+    __shared__ unsigned short sCand[FS_CAP];         // tile position of each candidate
+    __shared__ unsigned short sCorner[FS_CAP];       // tile position | polarity << 15
     __shared__ int sCnt[2];
     const int frame = blockIdx.y;
     int level = 0;
@@ -37,37 +42,43 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_score(const Plan* __restric
     const int t = blockIdx.x - L.fsBase;
     const int gy = t / L.fsTilesX, gx = t - gy * L.fsTilesX;
     const int tid = threadIdx.x, lane = tid & 31, ty = tid >> 5;
-    const int wcol = gx * 32 + lane;
-    const int y0 = kEdge + (gy * 4 + ty) * FS_R;
+    const int xw0 = gx * 32 - 1;                     // level word-column of tile word 0
+    const int yt0 = kEdge + gy * 4 * FS_R - 3;       // level row of tile row 0
     const int xlo = kEdge, xhi = L.w - kEdge, yhi = L.h - kEdge;      // union of the cell interiors: [19, w-19) x [19, h-19)
     const int th = min(max(P->iniTh, 0), 255);
     const unsigned K = (unsigned)(0x7fff - th) * 0x00010001u;
     const uint8_t* roi = B.pyr + (size_t)frame * P->pyrStride + L.roiOff;
     uint8_t* score = B.score + (size_t)frame * P->blurStride + L.blurOff;
     if (tid < 2) sCnt[tid] = 0;
+    // ---- stage the tile (rows beyond the bottom apron / words beyond the right apron are never used: clamp) ----
+    {
+        const int maxRow = L.h + kEdge - 1, maxWord = (L.w + kEdge - 1) >> 2;
+        for (int i = tid; i < FS_TROWS * 34; i += FS_THREADS) {
+            const int r = i / 34, w = i - r * 34;
+            const int gyy = min(yt0 + r, maxRow), gw = min(xw0 + w, maxWord);
+            reinterpret_cast<unsigned*>(sTile)[r * (FS_TP / 4) + w] =
+                __ldg(reinterpret_cast<const unsigned*>(roi + (ptrdiff_t)gyy * L.pitch) + gw);
+        }
+    }
     __syncthreads();
 
     // ---- A: quick reject over FS_R rows, 4 pixels per thread and row ----
+    const int wcol = gx * 32 + lane;
+    const int y0 = kEdge + (gy * 4 + ty) * FS_R;
     unsigned candAll = 0;
     if (wcol * 4 < L.w && y0 < yhi) {
         unsigned xmask = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) xmask |= (unsigned)(wcol * 4 + k >= xlo && wcol * 4 + k < xhi) << k;
-        const uint8_t* src = roi + 4 * wcol;
-        unsigned wl[7], wm[7], wr[7];
+        const unsigned* tw = reinterpret_cast<const unsigned*>(sTile) + (ty * FS_R) * (FS_TP / 4) + lane + 1;
+        unsigned* srow = reinterpret_cast<unsigned*>(score + (size_t)y0 * L.bpitch + 4 * wcol);
 #pragma unroll
-        for (int r = 0; r < FS_R + 6; r++) {
-            const unsigned* row = reinterpret_cast<const unsigned*>(src + (ptrdiff_t)(y0 - 3 + r) * L.pitch);
-            wm[r % 7] = __ldg(row);
-            if (r >= 3 && r < FS_R + 3) { wl[r % 7] = __ldg(row - 1); wr[r % 7] = __ldg(row + 1); }
-            if (r >= 6) {
-                const int yc = y0 + r - 6;
-                const int c = (r - 3) % 7;
-                const unsigned m = quick_mask4(wl[c], wm[c], wr[c], wm[r % 7], wm[(r - 6) % 7], K) & xmask;
-                if (yc < yhi) {
-                    *reinterpret_cast<unsigned*>(score + (size_t)yc * L.bpitch + 4 * wcol) = 0u;
-                    candAll |= m << (4 * (r - 6));
-                }
+        for (int r = 0; r < FS_R; r++) {
+            const unsigned* c = tw + (r + 3) * (FS_TP / 4);
+            const unsigned m = quick_mask4(c[-1], c[0], c[1], c[3 * (FS_TP / 4)], c[-3 * (FS_TP / 4)], K) & xmask;
+            if (y0 + r < yhi) {
+                srow[(size_t)r * (L.bpitch / 4)] = 0u;
+                candAll |= m << (4 * r);
             }
         }
     }
@@ -79,26 +90,25 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_score(const Plan* __restric
         if (lane == 31 && wtot) wbase = atomicAdd(&sCnt[0], wtot);
         wbase = __shfl_sync(0xffffffffu, wbase, 31);
         int o = wbase + inc - cnt;
+        const int pos0 = (ty * FS_R + 3) * FS_TP + (lane + 1) * 4;
         while (candAll) {
             const int b = __ffs(candAll) - 1;
             candAll &= candAll - 1;
-            sCand[o++] = (unsigned short)((ty << 10) | ((b >> 2) << 7) | (lane << 2) | (b & 3));
+            sCand[o++] = (unsigned short)(pos0 + (b >> 2) * FS_TP + (b & 3));
         }
     }
     __syncthreads();
 
     // ---- B: full ring test on the candidates ----
+    constexpr int PS = FS_TP;
     const int nCand = sCnt[0];
     for (int base = 0; base < nCand; base += FS_THREADS) {
         const int i = base + tid;
         bool corner = false;
         unsigned rec = 0;
         if (i < nCand) {
-            const unsigned id = sCand[i];
-            const int x = (gx * 32 + (int)((id >> 2) & 31)) * 4 + (int)(id & 3);
-            const int y = kEdge + (gy * 4 + (int)(id >> 10)) * FS_R + (int)((id >> 7) & 7);
-            const uint8_t* q = roi + (size_t)y * L.pitch + x;
-            const int PS = L.pitch;
+            const unsigned pos = sCand[i];
+            const uint8_t* q = &sTile[pos];
             const int v = q[0], hi = v + th, lo = v - th;
             unsigned mb = 0, md = 0;
 #define ORBB_RING(off)                                       \
@@ -114,7 +124,7 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_score(const Plan* __restric
 #undef ORBB_RING
             const bool cb = arc9(mb & 0xffffu), cd = arc9(md & 0xffffu);
             corner = cb | cd;
-            rec = id | (cd ? 0x8000u : 0u);
+            rec = pos | (cd ? 0x8000u : 0u);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, corner);
         int wbase = 0;
@@ -128,11 +138,8 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_score(const Plan* __restric
     const int nCorner = sCnt[1];
     for (int i = tid; i < nCorner; i += FS_THREADS) {
         const unsigned rec = sCorner[i];
-        const unsigned id = rec & 0x7fffu;
-        const int x = (gx * 32 + (int)((id >> 2) & 31)) * 4 + (int)(id & 3);
-        const int y = kEdge + (gy * 4 + (int)((id >> 10) & 3)) * FS_R + (int)((id >> 7) & 7);
-        const uint8_t* q = roi + (size_t)y * L.pitch + x;
-        const int PS = L.pitch;
+        const int pos = rec & 0x7fff;
+        const uint8_t* q = &sTile[pos];
         const int v = q[0];
         const int sgn = (rec & 0x8000u) ? -1 : 1;
         int d[16];
@@ -152,11 +159,12 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_score(const Plan* __restric
             const int e1 = min3i(m3[k + 1], m3[(k + 4) & 15], m3[(k + 7) & 15]);
             M = max3i(M, e0, e1);
         }
-        score[(size_t)y * L.bpitch + x] = (uint8_t)(M - 1);
+        const int r = pos / PS, col = pos - r * PS;
+        score[(size_t)(yt0 + r) * L.bpitch + (xw0 * 4 + col)] = (uint8_t)(M - 1);
     }
 }
 
-constexpr int FC_THREADS = 128;
+constexpr int FC_THREADS = 64;
 
 __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(const Plan* __restrict__ P, Bufs B) {
     constexpr int PS = kCellPix;
@@ -165,20 +173,15 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(const Plan* __restric
     __shared__ int sCnt;
     const int frame = blockIdx.y;
     const int gcell = blockIdx.x;
-    int level = 0;
-    while (level + 1 < P->nlevels && gcell >= P->lv[level + 1].cellBase) level++;
-    const LevelPlan& L = P->lv[level];
-    const int c = gcell - L.cellBase;
-    const int ci = c / L.nCols, cj = c - ci * L.nCols;
     const int tid = threadIdx.x;
+    const CellDesc cd = B.cellDesc[gcell];
     int* cellCount = B.cellCount + (size_t)frame * P->cellsTotal + gcell;
-    const int iniX = kMinBorder + cj * L.wCell, iniY = kMinBorder + ci * L.hCell;
-    const int maxX = min(iniX + L.wCell + 6, L.maxBX), maxY = min(iniY + L.hCell + 6, L.maxBY);
-    if (iniY >= L.maxBY - 3 || iniX >= L.maxBX - 6 || maxX - iniX < 7 || maxY - iniY < 7) {     // :810,:819
+    if (cd.gx1 <= cd.gx0) {                         // :810,:819
         if (tid == 0) *cellCount = 0;
         return;
     }
-    const int gx0 = iniX + 3, gx1 = maxX - 3, gy0 = iniY + 3, gy1 = maxY - 3;     // cell interior, level coordinates
+    const LevelPlan& L = P->lv[cd.level];
+    const int gx0 = cd.gx0, gx1 = cd.gx1, gy0 = cd.gy0, gy1 = cd.gy1;     // cell interior, level coordinates
     const int ih = gy1 - gy0;
     const int a0 = (gx0 - 1) & ~3;                  // level column of tile column 0 (leaves >= 1 halo column)
     const int nw = (gx1 + 1 - a0 + 3) >> 2;         // words per tile row (<= 20)
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(const Plan* __restric
     __syncthreads();
     // ---- raster order by rank counting; keys are relative to the 16-px border (:865-866) ----
     const int nSurv = sCnt;
-    u64* out = B.cellKeys + (size_t)frame * P->cellKeyStride + L.cellKeyBase + (size_t)c * L.cellCap;
+    u64* out = B.cellKeys + (size_t)frame * P->cellKeyStride + cd.outOff;
     for (int i = tid; i < nSurv; i += FC_THREADS) {
         const unsigned rec = sSurv[i];
         int rank = 0;
@@ -228,5 +231,11 @@ __global__ void __launch_bounds__(FC_THREADS) k_fast_cells(const Plan* __restric
         const int x = a0 + col - kMinBorder, y = gy0 - 1 + r - kMinBorder;
         out[rank] = (u64)(unsigned)x | ((u64)(unsigned)y << 16) | ((u64)(rec & 0xffu) << 32);
     }
-    if (tid == 0) *cellCount = nSurv ? nSurv : -1;     // -1: retry this cell with minThFAST (k_fast, mode 1)
+    if (tid == 0) {
+        *cellCount = nSurv;
+        if (nSurv == 0) {                           // retry this cell with minThFAST (k_fast, mode 1)
+            const int slot = atomicAdd(&B.fbCount[frame], 1);
+            B.fbList[(size_t)frame * P->cellsTotal + slot] = gcell;
+        }
+    }
 }

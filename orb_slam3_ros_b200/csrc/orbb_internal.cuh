@@ -60,13 +60,20 @@ struct QNode {                     // quadtree node: UL=(x0,y0) BR=(x1,y1); keys
 
 struct WorkItem { int level, x, y, pos; };
 
+// FAST cell (host-built, shared by all frames): interior [gx0,gx1) x [gy0,gy1) in level coordinates (empty when the
+// reference skips the cell, ORBextractor.cc:810,:819), first key slot of the cell inside the frame's cellKeys.
+struct CellDesc { short gx0, gx1, gy0, gy1; int level; unsigned outOff; };
+
 // Device buffers of one extractor handle, sized for `capacity` frames.
 struct Bufs {
     uint8_t* pyr;
     uint8_t* blur;
     uint8_t* score;                // FAST response map per level (same layout as blur)
     int2* tab;                     // resize tables (shared by all frames)
+    const CellDesc* cellDesc;      // [cellsTotal]
     int* cellCount;
+    int* fbList;                   // [frame][cellsTotal] cells that need the minThFAST retry
+    int* fbCount;                  // [frame]
     int* cellOff;
     u64* cellKeys;                 // key = x | y<<16 | score<<32 (x,y relative to the 16-px border)
     u64* keys;                     // [frame][2][rawStride]
@@ -100,6 +107,8 @@ struct orbb_extractor {
     int umax[16];
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t h2dStream = nullptr, d2hStream = nullptr;   // copy engines for the pipelined host path
+    cudaEvent_t evH2D[8]{}, evDone[8]{};
     // plan for the current image size
     orbb::Plan plan;
     orbb::Plan* dPlan = nullptr;

@@ -149,20 +149,21 @@ def test_pyramid_accessor_matches_mvImagePyramid():
 
 def test_batch_equals_single_and_host_equals_device_path():
     import torch
-    frames = synth.sequence(240, 320, 6, canvas=512)
-    ge = ORBextractor(300, 1.2, 4, max_batch=6)
+    NF = 9                                          # >= 8 frames: the host path pipelines two chunks (5 + 4)
+    frames = synth.sequence(240, 320, NF, canvas=512)
+    ge = ORBextractor(300, 1.2, 4, max_batch=NF)
     counts, kps, desc = ge.extract_batch_host(frames, (0, 1000))
     single = ORBextractor(300, 1.2, 4)
-    for f in range(6):
+    for f in range(NF):
         m1, k1, d1 = single(frames[f], None, (0, 1000))
         n = counts[f, 0]
         assert n == len(k1) and counts[f, 1] == m1
         assert np.array_equal(kps[f, :n], k1) and np.array_equal(desc[f, :n], d1)
     dev = torch.from_numpy(frames).cuda()
-    ge.extract_batch_device(dev, 6, 320, 240, lapping=(0, 1000))
-    c2, k2, d2 = ge.fetch(6)
+    ge.extract_batch_device(dev, NF, 320, 240, lapping=(0, 1000))
+    c2, k2, d2 = ge.fetch(NF)
     assert np.array_equal(c2, counts)
-    for f in range(6):
+    for f in range(NF):
         n = counts[f, 0]
         assert np.array_equal(k2[f, :n], kps[f, :n]) and np.array_equal(d2[f, :n], desc[f, :n])
 
