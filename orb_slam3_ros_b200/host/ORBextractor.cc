@@ -1,0 +1,86 @@
+// Host adapter: ORB_SLAM3::ORBextractor on top of liborbb200.so (see ORBextractor.h).  Mirrors the calling
+// conventions of the reference's ORBextractor.cc:1086-1168: input must be CV_8UC1, empty input returns -1, the callee
+// replaces _keypoints and (re)creates _descriptors as n x 32 CV_8U (released when n == 0).
+#include "ORBextractor.h"
+
+#include <cassert>
+#include <stdexcept>
+#include <string>
+
+#include "orbb200.h"
+
+namespace ORB_SLAM3 {
+
+ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST)
+    : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST), minThFAST(_minThFAST),
+      mpHandle(nullptr), mbDownloadPyramid(true) {
+    orbb_params prm;
+    prm.nfeatures = _nfeatures;
+    prm.scale_factor = _scaleFactor;
+    prm.nlevels = _nlevels;
+    prm.ini_th_fast = _iniThFAST;
+    prm.min_th_fast = _minThFAST;
+    prm.device = 0;
+    prm.max_batch = 1;
+    const int rc = orbb_create(&prm, &mpHandle);
+    if (rc != ORBB_OK) throw std::runtime_error(std::string("orbb_create failed: ") + orbb_last_error(nullptr));
+    mvScaleFactor.resize(nlevels);
+    mvInvScaleFactor.resize(nlevels);
+    mvLevelSigma2.resize(nlevels);
+    mvInvLevelSigma2.resize(nlevels);
+    mnFeaturesPerLevel.resize(nlevels);
+    orbb_get_tables(mpHandle, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(), mvInvLevelSigma2.data(),
+                    mnFeaturesPerLevel.data());
+    mvImagePyramid.resize(nlevels);
+}
+
+ORBextractor::~ORBextractor() { orbb_destroy(mpHandle); }
+
+int ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*_mask*/, std::vector<cv::KeyPoint>& _keypoints,
+                             cv::OutputArray _descriptors, std::vector<int>& vLappingArea) {
+    if (_image.empty()) return -1;
+    cv::Mat image = _image.getMat();
+    assert(image.type() == CV_8UC1);
+
+    const int cap = orbb_max_keypoints(mpHandle);
+    mvKeypointStaging.resize((size_t)cap * sizeof(orbb_keypoint));
+    mvDescStaging.resize((size_t)cap * 32);
+    orbb_keypoint* kps = reinterpret_cast<orbb_keypoint*>(mvKeypointStaging.data());
+    int n = 0, monoIndex = 0;
+    const int rc = orbb_extract(mpHandle, image.data, image.cols, image.rows, (size_t)image.step, vLappingArea[0], vLappingArea[1],
+                                kps, mvDescStaging.data(), cap, &n, &monoIndex);
+    if (rc == ORBB_ERR_EMPTY) return -1;
+    if (rc != ORBB_OK) throw std::runtime_error(std::string("orbb_extract failed: ") + orbb_last_error(mpHandle));
+
+    if (n == 0) {
+        _descriptors.release();
+    } else {
+        _descriptors.create(n, 32, CV_8U);
+        cv::Mat descriptors = _descriptors.getMat();
+        for (int i = 0; i < n; i++) memcpy(descriptors.ptr(i), mvDescStaging.data() + (size_t)i * 32, 32);
+    }
+    _keypoints = std::vector<cv::KeyPoint>(n);
+    for (int i = 0; i < n; i++) {
+        cv::KeyPoint& kp = _keypoints[i];
+        kp.pt.x = kps[i].x;
+        kp.pt.y = kps[i].y;
+        kp.size = kps[i].size;
+        kp.angle = kps[i].angle;
+        kp.response = kps[i].response;
+        kp.octave = kps[i].octave;
+        kp.class_id = -1;
+    }
+    if (mbDownloadPyramid) {
+        for (int level = 0; level < nlevels; ++level) {
+            const uint8_t* p = nullptr;
+            int w = 0, h = 0;
+            size_t stride = 0;
+            if (orbb_pyramid_level(mpHandle, level, &p, &w, &h, &stride) != ORBB_OK)
+                throw std::runtime_error(std::string("orbb_pyramid_level failed: ") + orbb_last_error(mpHandle));
+            mvImagePyramid[level] = cv::Mat(h, w, CV_8UC1, const_cast<uint8_t*>(p), stride);
+        }
+    }
+    return monoIndex;
+}
+
+}  // namespace ORB_SLAM3

@@ -1,0 +1,65 @@
+// Drop-in replacement for orb_slam3/include/ORBextractor.h of giltchcity/orb_slam3_ros: same namespace, class name,
+// constructor, operator(), getters and the public mvImagePyramid member (reference ORBextractor.h:43-109), so that
+// Frame.cc (:110-125, :222, :311, :418-425, :818-923, :1059-1060) and Tracking.cc (:631-637, :1319-1325) compile
+// unchanged.  All computation happens in liborbb200.so (CUDA, sm_100a) through the C ABI of include/orbb200.h;
+// there is no CPU implementation behind this class.
+#ifndef ORBEXTRACTOR_H
+#define ORBEXTRACTOR_H
+
+#include <list>
+#include <vector>
+#include <opencv2/opencv.hpp>
+
+struct orbb_extractor;
+
+namespace ORB_SLAM3 {
+
+class ORBextractor {
+public:
+    enum { HARRIS_SCORE = 0, FAST_SCORE = 1 };
+
+    ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST);
+    ~ORBextractor();
+    ORBextractor(const ORBextractor&) = delete;
+    ORBextractor& operator=(const ORBextractor&) = delete;
+
+    // Compute the ORB features and descriptors on an image; mask is ignored (as in the reference).
+    // Returns the number of keypoints outside vLappingArea (written at the front), -1 on an empty image.
+    int operator()(cv::InputArray _image, cv::InputArray _mask, std::vector<cv::KeyPoint>& _keypoints,
+                   cv::OutputArray _descriptors, std::vector<int>& vLappingArea);
+
+    int inline GetLevels() { return nlevels; }
+    float inline GetScaleFactor() { return scaleFactor; }
+    std::vector<float> inline GetScaleFactors() { return mvScaleFactor; }
+    std::vector<float> inline GetInverseScaleFactors() { return mvInvScaleFactor; }
+    std::vector<float> inline GetScaleSigmaSquares() { return mvLevelSigma2; }
+    std::vector<float> inline GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
+
+    // Views into a host copy of the device pyramid of the last frame (valid until the next call), refreshed after
+    // every operator() unless SetPyramidDownload(false) -- only Frame::ComputeStereoMatches reads them.
+    std::vector<cv::Mat> mvImagePyramid;
+
+    // ---- extensions (not in the reference) ----
+    void SetPyramidDownload(bool enabled) { mbDownloadPyramid = enabled; }
+    orbb_extractor* Handle() { return mpHandle; }          // for orbb_stereo_match(hL, hR, ...)
+
+protected:
+    int nfeatures;
+    double scaleFactor;
+    int nlevels;
+    int iniThFAST;
+    int minThFAST;
+    std::vector<int> mnFeaturesPerLevel;
+    std::vector<float> mvScaleFactor;
+    std::vector<float> mvInvScaleFactor;
+    std::vector<float> mvLevelSigma2;
+    std::vector<float> mvInvLevelSigma2;
+
+    orbb_extractor* mpHandle;
+    bool mbDownloadPyramid;
+    std::vector<unsigned char> mvKeypointStaging, mvDescStaging;
+};
+
+}  // namespace ORB_SLAM3
+
+#endif

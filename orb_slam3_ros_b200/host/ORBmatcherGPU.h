@@ -1,0 +1,66 @@
+// GPU-backed building blocks for ORB_SLAM3::ORBmatcher (reference orb_slam3/include/ORBmatcher.h:38-94,
+// orb_slam3/src/ORBmatcher.cc).  The twelve Search*/Fuse methods keep their host geometry (projection, grid lookup,
+// MapPoint bookkeeping -- out of scope); what they all share is
+//      "scan a candidate list with DescriptorDistance keeping best / second best with strict '<'"
+// and that scan is what this header provides, plus the brute-force kNN-2 that Frame::ComputeStereoFishEyeMatches
+// obtains from cv::BFMatcher (Frame.cc:1144).  INTEGRATION.md shows the call-site changes.
+#ifndef ORBMATCHER_GPU_H
+#define ORBMATCHER_GPU_H
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include <opencv2/opencv.hpp>
+
+#include "orbb200.h"
+
+namespace ORB_SLAM3 {
+
+class ORBmatcherGPU {
+public:
+    static const int TH_LOW = 50;        // ORBmatcher.cc:36
+    static const int TH_HIGH = 100;      // ORBmatcher.cc:35
+    static const int HISTO_LENGTH = 30;  // ORBmatcher.cc:37
+
+    explicit ORBmatcherGPU(int device = 0) : mpMatcher(nullptr) {
+        if (orbb_matcher_create(device, &mpMatcher) != ORBB_OK)
+            throw std::runtime_error(std::string("orbb_matcher_create failed: ") + orbb_matcher_last_error(nullptr));
+    }
+    ~ORBmatcherGPU() { orbb_matcher_destroy(mpMatcher); }
+    ORBmatcherGPU(const ORBmatcherGPU&) = delete;
+    ORBmatcherGPU& operator=(const ORBmatcherGPU&) = delete;
+
+    // ORBmatcher::DescriptorDistance (ORBmatcher.cc:2058-2074): one pair stays on the host.
+    static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b) { return orbb_hamming_distance(a.ptr<uchar>(), b.ptr<uchar>()); }
+
+    struct BestTwo { int bestDist, bestIdx, secondDist, secondIdx; };
+
+    // queries: nq x 32 CV_8U; train: nt x 32 CV_8U (e.g. Frame::mDescriptors); candidates of query i are
+    // cand[rowPtr[i] .. rowPtr[i+1]); both distances start at `init` (256 at ORBmatcher.cc:77, TH_LOW/TH_HIGH/INT_MAX elsewhere)
+    std::vector<BestTwo> BestTwoCSR(const cv::Mat& queries, const cv::Mat& train, const std::vector<int>& cand,
+                                    const std::vector<int>& rowPtr, int init = 256) {
+        std::vector<BestTwo> out(queries.rows);
+        if (queries.rows == 0) return out;
+        if (!queries.isContinuous() || !train.isContinuous()) throw std::runtime_error("descriptor matrices must be continuous");
+        const int rc = orbb_best2_csr(mpMatcher, queries.ptr<uchar>(), queries.rows, train.ptr<uchar>(), train.rows, cand.data(),
+                                      rowPtr.data(), init, reinterpret_cast<int32_t*>(out.data()));
+        if (rc != ORBB_OK) throw std::runtime_error(std::string("orbb_best2_csr failed: ") + orbb_matcher_last_error(mpMatcher));
+        return out;
+    }
+
+    // cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, matches, 2): idx/dist are nq x 2, missing = (-1, INT_MAX)
+    void KnnMatch2(const cv::Mat& query, const cv::Mat& train, std::vector<int>& idx, std::vector<int>& dist) {
+        idx.assign((size_t)query.rows * 2, -1);
+        dist.assign((size_t)query.rows * 2, 0x7fffffff);
+        if (query.rows == 0) return;
+        const int rc = orbb_knn2(mpMatcher, query.ptr<uchar>(), query.rows, train.ptr<uchar>(), train.rows, idx.data(), dist.data());
+        if (rc != ORBB_OK) throw std::runtime_error(std::string("orbb_knn2 failed: ") + orbb_matcher_last_error(mpMatcher));
+    }
+
+private:
+    orbb_matcher* mpMatcher;
+};
+
+}  // namespace ORB_SLAM3
+
+#endif

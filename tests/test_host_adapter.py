@@ -1,0 +1,58 @@
+"""The C++ host adapter (orb_slam3_ros_b200/host: namespace ORB_SLAM3, class ORBextractor with the reference's
+interface) compiled with the reference's language level (C++14) against a stand-in for the OpenCV types, exercised with
+the reference's own call sequence (Tracking.cc:631, Frame.cc:110-116, :418-425, :818-923).  CPU: it compiles and links.
+GPU: its output equals what the C ABI returns through the python binding."""
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+EXE = ROOT / "tests" / "models" / "_build" / "adapter_check"
+
+
+def _build():
+    from orb_slam3_ros_b200 import build
+    build.build_library()
+    EXE.parent.mkdir(exist_ok=True)
+    pkg = ROOT / "orb_slam3_ros_b200"
+    cmd = ["g++", "-std=c++14", "-O2", f"-I{ROOT / 'tests' / 'cvstub'}", f"-I{ROOT / 'include'}", f"-I{pkg / 'host'}",
+           str(ROOT / "tests" / "host" / "adapter_check.cpp"), str(pkg / "host" / "ORBextractor.cc"), f"-L{pkg}", "-lorbb200",
+           f"-Wl,-rpath,{pkg}", "-L/usr/local/cuda/lib64", "-lcudart", "-o", str(EXE)]
+    subprocess.check_call(cmd)
+
+
+def test_adapter_compiles_and_links_as_cxx14():
+    _build()
+    assert EXE.exists()
+
+
+@pytest.mark.gpu
+def test_adapter_matches_c_abi(tmp_path):
+    from orb_slam3_ros_b200 import synth
+    from orb_slam3_ros_b200.extractor import ORBextractor
+    from orb_slam3_ros_b200.matcher import ORBmatcher
+    _build()
+    img = synth.frame(240, 320, 21)
+    raw = tmp_path / "img.raw"
+    img.tofile(raw)
+    out = subprocess.run([str(EXE), str(raw), "320", "240"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    got = dict(kv.split("=") for kv in out.stdout.split())
+    ge = ORBextractor(300, 1.2, 4, 20, 7)
+    mono, k, d = ge(img, None, (0, 1000))
+    s = 0
+    M = (1 << 64) - 1
+    for i in range(len(k)):
+        s = (s * 1000003 + int(np.float32(k["x"][i]) * np.float32(16)) + 7 * int(np.float32(k["y"][i]) * np.float32(16)) + 13 * int(k["octave"][i])
+             + 17 * int(k["response"][i]) + 19 * int(k["size"][i])) & M
+        for b in d[i]:
+            s = (s * 31 + int(b)) & M
+    p1 = ge.image_pyramid(1)
+    win = p1[10:21, 12:23].astype(np.uint64)
+    psum = int((win * (np.arange(11)[:, None] * 11 + np.arange(11)[None, :] + 1).astype(np.uint64)).sum())
+    assert int(got["n"]) == len(k) and int(got["mono"]) == mono and got["desc"] == f"{len(k)}x32"
+    assert int(got["sum"]) == s
+    assert got["pyr1"] == f"{p1.shape[1]}x{p1.shape[0]}" and int(got["psum"]) == psum
+    assert int(got["d01"]) == ORBmatcher.DescriptorDistance(d[0], d[1])
