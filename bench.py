@@ -68,7 +68,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                        "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -150,7 +150,7 @@ def run_reference(a):
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "knn": knn,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -194,6 +194,8 @@ def run_ours(a):
     torch.cuda.synchronize()
 
     # ---- device-resident throughput: W warm-up steps, then EXACTLY K timed steps ----
+    clocks = ClockSampler(local)
+    clocks.start()                      # sampling spans warm-up, both extraction regions and the kNN region
     for i in range(a.warmup):
         ext.extract_batch_device(dev_sets[i % NSETS], B, W_, H_, lapping=LAPPING)
     ext.sync()
@@ -201,10 +203,8 @@ def run_ours(a):
     ext.set_profiling(True)
     stage_acc = {}
     launches0 = ext.launch_count
-    clocks = ClockSampler(local)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    clocks.start()
     with torch.cuda.stream(est):
         e0.record()
         for i in range(a.steps):
@@ -238,7 +238,6 @@ def run_ours(a):
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * B * a.steps / e2e_s
-    clk = clocks.stop()
     n_kp = int(outs[2][:, 0].sum())
     h2d = B * W_ * H_
     d2h = B * cap * (24 + 32) + B * 12
@@ -310,7 +309,6 @@ def run_ours(a):
         barrier()
         kms = max_over_ranks(k0.elapsed_time(k1)) / a.knn_steps
         gp = nq * nd / (kms * 1e-3) / 1e9
-        sm_mhz = clk.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
         popc_peak_nominal = 148 * 16 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e9      # G popc/s per GPU at max clock
         knn = {"value": gp, "unit": "Gpairs/s", "nq": nq, "nd": nd, "ms_per_step": kms, "steps": a.knn_steps, "scaling": "strong",
                "sharding": f"database rows split over {world} rank(s); all-gather of per-shard top-2 + device merge" if world > 1 else "single shard",
@@ -320,6 +318,8 @@ def run_ours(a):
                             "frac": 8 * gp / world / popc_peak_nominal,
                             "peak_source": "148 SMs x 16 POPC/clk/SM x max SM clock (CUDA programming guide throughput table; see DESIGN.md)"}}
         launches += m.launch_count - l0
+
+    clk = clocks.stop()
 
     # ---- CPU baseline on the box's host cores (rank 0, N=1 only), bounded sample of the same workload ----
     cpu = None
@@ -347,12 +347,21 @@ def run_ours(a):
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "knn": knn, "clocks": clk,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _emit(line):
+    """the ONE JSON line goes to the real stdout; everything else (NCCL banners, library chatter) went to stderr"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 if __name__ == "__main__":
+    # C-level writers (NCCL prints its version banner to stdout) must not pollute the single JSON line
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         run_reference(args)
