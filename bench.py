@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--knn-nd", type=int, default=KNN_ND)
     ap.add_argument("--knn-steps", type=int, default=3)
     ap.add_argument("--no-knn", action="store_true")
+    ap.add_argument("--no-stereo", action="store_true")
+    ap.add_argument("--stereo-pairs", type=int, default=256)
+    ap.add_argument("--stereo-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=32, help="frames in the bounded CPU sample")
     return ap.parse_args()
@@ -316,9 +319,62 @@ def run_ours(a):
                "gpu_launches": m.launch_count - l0,
                "roofline": {"bound": "popc", "achieved": 8 * gp / world, "peak": popc_peak_nominal, "unit": "Gpopc/s per GPU",
                             "frac": 8 * gp / world / popc_peak_nominal,
-                            "peak_source": "148 SMs x 16 POPC/clk/SM x max SM clock (CUDA programming guide throughput table; see DESIGN.md)"}}
+                            "peak_source": "148 SMs x 16 POPC/clk/SM x max SM clock; algorithmic work = 8 POPC per pair (SURVEY.md 8d)",
+                            "note": "frac > 1 is real: the kernel compresses the 8 XOR words with LOP3 carry-save adders and issues only 5 "
+                                    "POPC per pair; the binding limit is the POPC/ALU pipe balance (5/16 + 20/64 clk per pair -> 3.2 pairs/clk/SM "
+                                    "= 931 Gpairs/s at 1.965 GHz), see DESIGN.md section 5",
+                            "two_pipe_bound_gpairs": 148 * 3.2 * float(peaks.get("sm_max_mhz", 1965.0)) / 1e3,
+                            "frac_of_two_pipe_bound": gp / world / (148 * 3.2 * float(peaks.get("sm_max_mhz", 1965.0)) / 1e3)}}
         launches += m.launch_count - l0
 
+    # ---- BASELINE config 2: KITTI-shape stereo, 1241x376 left+right, 2000 features/eye + ComputeStereoMatches ----
+    stereo = None
+    if not a.no_stereo:
+        from orb_slam3_ros_b200.extractor import stereo_fetch, stereo_match_batch
+        SP, SW, SH, SNF = a.stereo_pairs, 1241, 376, 2000
+        bf, bl = 718.856 * 0.53716, 0.53716                    # config/Stereo/KITTI00-02.yaml: Camera.fx * b, b
+        Lh, Rh = synth.stereo_sequence(SH, SW, SP, base_seed=synth.BASE_SEED + 17 * rank)
+        dL, dR = torch.from_numpy(Lh).to(dev), torch.from_numpy(Rh).to(dev)
+        eL = ORBextractor(SNF, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=SP)
+        eR = ORBextractor(SNF, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=SP)
+        sst = torch.cuda.ExternalStream(eL.stream, device=dev)
+
+        def stereo_step():
+            eL.extract_batch_device(dL, SP, SW, SH)             # two handles = two streams, like the reference's two
+            eR.extract_batch_device(dR, SP, SW, SH)             # threads (Frame.cc:122-125)
+            stereo_match_batch(eL, eR, SP, bf, bl)              # left stream waits for the right one
+
+        stereo_step()
+        barrier()
+        sl0 = eL.launch_count + eR.launch_count
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eR.sync()
+        with torch.cuda.stream(sst):
+            s0.record()
+        for _ in range(a.stereo_steps):
+            stereo_step()
+        with torch.cuda.stream(sst):
+            s1.record()
+        barrier()
+        sms = max_over_ranks(s0.elapsed_time(s1)) / a.stereo_steps
+        ur, dp = stereo_fetch(eL, SP)
+        cnts, _, _ = eL.fetch(SP, with_data=False)
+        matched = float(np.mean([(ur[f, :cnts[f, 0]] >= 0).mean() for f in range(SP)]))
+        stereo = {"value": world * SP / (sms * 1e-3), "unit": "stereo pairs/s", "pairs_per_step": SP, "ms_per_step": sms,
+                  "shape": f"{SW}x{SH} x2, {SNF} features/eye, ComputeStereoMatches", "matched_fraction": matched,
+                  "keypoints_left": float(cnts[:, 0].mean()), "gpu_launches": eL.launch_count + eR.launch_count - sl0}
+        launches += stereo["gpu_launches"]
+        if rank == 0 and world == 1 and not a.no_cpu_baseline:
+            from oracle import port
+            t0 = time.perf_counter()
+            npairs = 4
+            for f in range(npairs):
+                pl, pr = port.PortExtractor(SNF), port.PortExtractor(SNF)
+                _, kl, dl, _ = pl.extract(Lh[f])
+                _, kr, dr, _ = pr.extract(Rh[f])
+                port.stereo(pl, pr, kl, dl, kr, dr, np.float32(bf), np.float32(bl))
+            stereo["cpu_single_thread_pairs_per_s"] = npairs / (time.perf_counter() - t0)
+        del eL, eR, dL, dR
     clk = clocks.stop()
 
     # ---- CPU baseline on the box's host cores (rank 0, N=1 only), bounded sample of the same workload ----
@@ -345,7 +401,7 @@ def run_ours(a):
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / a.steps, "api": "orbb_extract_batch_host (pinned host frames -> keypoints+descriptors)"},
             "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "knn": knn, "clocks": clk,
+            "roofline": roofline, "cpu_baseline": cpu, "knn": knn, "stereo": stereo, "clocks": clk,
         }
         _emit(line)
     if world > 1:

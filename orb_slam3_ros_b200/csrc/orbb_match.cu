@@ -5,11 +5,14 @@
 //   k_best2_csr                     best / second-best candidate scans               ORBmatcher.cc:77-120 (and siblings)
 //   k_stereo_match / k_stereo_cut   Frame::ComputeStereoMatches                      Frame.cc:811-981
 //
-// The 2-NN kernel is integer work on the CUDA cores (8 x 32-bit XOR + POPC per pair, no tensor cores): queries live in
-// registers (4 per thread), database tiles are staged in shared memory with 1-D TMA bulk copies (cp.async.bulk +
-// mbarrier, 3 stages) and every thread of a warp reads the same database row (shared-memory broadcast).
+// The 2-NN kernel is integer work on the CUDA cores (XOR + POPC over 32-bit lanes, no tensor cores): queries live in
+// registers (3 per thread), database tiles are staged in shared memory with 1-D TMA bulk copies (cp.async.bulk +
+// mbarrier, 3 stages) and every thread of a warp reads the same database row (shared-memory broadcast).  The direct
+// form (8 POPC per pair) is bound by the POPC pipe (16 lanes/clk/SM); a carry-save compressor in LOP3s first
+// (hamming_c332: 5 POPC + 14 LOP3 per pair) balances the POPC and integer-ALU pipes and is 1.56x faster.
 #include <limits.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -78,8 +81,6 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigne
 // brute-force Hamming 2-NN
 // ------------------------------------------------------------------------------------------------
 constexpr int KNN_THREADS = 256;
-constexpr int KNN_QPT = 4;                         // queries per thread
-constexpr int KNN_QTILE = KNN_THREADS * KNN_QPT;   // queries per CTA
 constexpr int KNN_ROWS = 256;                      // database rows per shared-memory tile (8 KB)
 constexpr int KNN_STAGES = 3;
 constexpr unsigned KNN_IDX_BITS = 22;              // packed key = dist << 22 | chunk-local index
@@ -91,10 +92,73 @@ __device__ __forceinline__ void top2_insert(unsigned& k1, unsigned& k2, unsigned
     k2 = min(k2, hi);
 }
 
+// Hamming distance, the direct way: 8 XOR + 8 POPC (+ adds).  POPC issues at 16 lanes/clk/SM on B200, a quarter of
+// the integer-ALU rate, so a kernel made only of this is POPC-pipe bound at 2 pairs/clk/SM.
+__device__ __forceinline__ int hamming_popc(const unsigned (&q)[8], const uint4 a, const uint4 b) {
+    return __popc(q[0] ^ a.x) + __popc(q[1] ^ a.y) + __popc(q[2] ^ a.z) + __popc(q[3] ^ a.w) + __popc(q[4] ^ b.x) +
+           __popc(q[5] ^ b.y) + __popc(q[6] ^ b.z) + __popc(q[7] ^ b.w);
+}
+
+// The same distance through a carry-save adder tree (Harley-Seal): the eight XOR words are compressed bit-slice-wise
+// into ones / twos / fours / eights words with 3-input LOP3s (sum = a^b^c, carry = majority), so only 4 POPC remain:
+// d = popc(ones) + 2 popc(twos) + 4 popc(fours) + 8 popc(eights).  It trades POPC-pipe work for ALU-pipe work; mixing
+// both forms per thread balances the two pipes (about two CSA pairs per direct pair).
+__device__ __forceinline__ unsigned maj3(unsigned a, unsigned b, unsigned c) {      // carry of a full adder: one LOP3
+    unsigned r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ unsigned xor3(unsigned a, unsigned b, unsigned c) {      // sum of a full adder: one LOP3
+    unsigned r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ int hamming_csa(const unsigned (&q)[8], const uint4 a, const uint4 b) {
+    const unsigned x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, x2 = q[2] ^ a.z, x3 = q[3] ^ a.w;
+    const unsigned x4 = q[4] ^ b.x, x5 = q[5] ^ b.y, x6 = q[6] ^ b.z, x7 = q[7] ^ b.w;
+    const unsigned o1 = xor3(x0, x1, x2), t1 = maj3(x0, x1, x2);
+    const unsigned o2 = xor3(x3, x4, x5), t2 = maj3(x3, x4, x5);
+    const unsigned o3 = xor3(o1, o2, x6), t3 = maj3(o1, o2, x6);
+    const unsigned ones = o3 ^ x7, t4 = o3 & x7;
+    const unsigned w1 = xor3(t1, t2, t3), f1 = maj3(t1, t2, t3);
+    const unsigned twos = w1 ^ t4, f2 = w1 & t4;
+    const unsigned fours = f1 ^ f2, eights = f1 & f2;
+    return __popc(ones) + 2 * __popc(twos) + 4 * __popc(fours) + 8 * __popc(eights);
+}
+
+// Shallower compressors: fewer LOP3s per pair at the price of one or two more POPCs.
+//   hamming_c71: 7 words -> 3 bit-slices with 4 full adders, the 8th word counted directly (16 LOP3, 4 POPC)
+//   hamming_c332: full adders on (x0,x1,x2), (x3,x4,x5), (s1,s2,x6); x7 direct (14 LOP3, 5 POPC) -- close to the
+//                 ALU : POPC = 4 : 1 balance of the two pipes on its own
+__device__ __forceinline__ int hamming_c71(const unsigned (&q)[8], const uint4 a, const uint4 b) {
+    const unsigned x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, x2 = q[2] ^ a.z, x3 = q[3] ^ a.w;
+    const unsigned x4 = q[4] ^ b.x, x5 = q[5] ^ b.y, x6 = q[6] ^ b.z, x7 = q[7] ^ b.w;
+    const unsigned s1 = xor3(x0, x1, x2), c1 = maj3(x0, x1, x2);
+    const unsigned s2 = xor3(x3, x4, x5), c2 = maj3(x3, x4, x5);
+    const unsigned ones = xor3(s1, s2, x6), c3 = maj3(s1, s2, x6);
+    const unsigned twos = xor3(c1, c2, c3), fours = maj3(c1, c2, c3);
+    return __popc(ones) + __popc(x7) + 2 * __popc(twos) + 4 * __popc(fours);
+}
+__device__ __forceinline__ int hamming_c332(const unsigned (&q)[8], const uint4 a, const uint4 b) {
+    const unsigned x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, x2 = q[2] ^ a.z, x3 = q[3] ^ a.w;
+    const unsigned x4 = q[4] ^ b.x, x5 = q[5] ^ b.y, x6 = q[6] ^ b.z, x7 = q[7] ^ b.w;
+    const unsigned s1 = xor3(x0, x1, x2), c1 = maj3(x0, x1, x2);
+    const unsigned s2 = xor3(x3, x4, x5), c2 = maj3(x3, x4, x5);
+    const unsigned ones = xor3(s1, s2, x6), c3 = maj3(s1, s2, x6);
+    return __popc(ones) + __popc(x7) + 2 * (__popc(c1) + __popc(c2) + __popc(c3));
+}
+template <int METHOD>
+__device__ __forceinline__ int hamming_by(const unsigned (&q)[8], const uint4 a, const uint4 b) {
+    return METHOD == 0 ? hamming_popc(q, a, b) : METHOD == 1 ? hamming_csa(q, a, b) : METHOD == 2 ? hamming_c71(q, a, b) : hamming_c332(q, a, b);
+}
+
 // grid (query tiles, database chunks).  A chunk is < 2^22 rows; packed keys make "lowest index wins ties" the
-// natural order of an unsigned min.
+// natural order of an unsigned min.  NC queries per thread use the CSA form, NS the direct form.
+template <int NC, int NS, int MC = 1, int MS = 0>
 __global__ void __launch_bounds__(KNN_THREADS) k_knn2_partial(const uint4* __restrict__ q, int nq, const uint4* __restrict__ db,
                                                              long long nd, int chunkRows, unsigned* __restrict__ partial) {
+    constexpr int QPT = NC + NS;
+    constexpr int QTILE = KNN_THREADS * QPT;
     __shared__ __align__(128) uint4 sDb[KNN_STAGES][KNN_ROWS * 2];
     __shared__ __align__(8) unsigned long long sBar[KNN_STAGES];
     const int tid = threadIdx.x;
@@ -115,17 +179,17 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn2_partial(const uint4* __res
     if (tid == 0)
         for (int t = 0; t < KNN_STAGES && t < ntiles; t++) issue(t);
 
-    unsigned qa[KNN_QPT][8];
+    unsigned qa[QPT][8];
 #pragma unroll
-    for (int k = 0; k < KNN_QPT; k++) {
-        const int qi = min(blockIdx.x * KNN_QTILE + k * KNN_THREADS + tid, nq - 1);
+    for (int k = 0; k < QPT; k++) {
+        const int qi = min(blockIdx.x * QTILE + k * KNN_THREADS + tid, nq - 1);
         const uint4 a = __ldg(q + (size_t)qi * 2), b = __ldg(q + (size_t)qi * 2 + 1);
         qa[k][0] = a.x; qa[k][1] = a.y; qa[k][2] = a.z; qa[k][3] = a.w;
         qa[k][4] = b.x; qa[k][5] = b.y; qa[k][6] = b.z; qa[k][7] = b.w;
     }
-    unsigned k1[KNN_QPT], k2[KNN_QPT];
+    unsigned k1[QPT], k2[QPT];
 #pragma unroll
-    for (int k = 0; k < KNN_QPT; k++) k1[k] = k2[k] = KNN_NONE;
+    for (int k = 0; k < QPT; k++) k1[k] = k2[k] = KNN_NONE;
 
     for (int t = 0; t < ntiles; t++) {
         const int s = t % KNN_STAGES;
@@ -137,9 +201,8 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn2_partial(const uint4* __res
         for (int j = 0; j < r; j++) {
             const uint4 a = tile[2 * j], b = tile[2 * j + 1];
 #pragma unroll
-            for (int k = 0; k < KNN_QPT; k++) {
-                const int d = __popc(qa[k][0] ^ a.x) + __popc(qa[k][1] ^ a.y) + __popc(qa[k][2] ^ a.z) + __popc(qa[k][3] ^ a.w) +
-                              __popc(qa[k][4] ^ b.x) + __popc(qa[k][5] ^ b.y) + __popc(qa[k][6] ^ b.z) + __popc(qa[k][7] ^ b.w);
+            for (int k = 0; k < QPT; k++) {
+                const int d = k < NC ? hamming_by<MC>(qa[k], a, b) : hamming_by<MS>(qa[k], a, b);
                 top2_insert(k1[k], k2[k], ((unsigned)d << KNN_IDX_BITS) + (jbase + (unsigned)j));
             }
         }
@@ -147,8 +210,8 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn2_partial(const uint4* __res
         if (tid == 0 && t + KNN_STAGES < ntiles) issue(t + KNN_STAGES);
     }
 #pragma unroll
-    for (int k = 0; k < KNN_QPT; k++) {
-        const int qi = blockIdx.x * KNN_QTILE + k * KNN_THREADS + tid;
+    for (int k = 0; k < QPT; k++) {
+        const int qi = blockIdx.x * QTILE + k * KNN_THREADS + tid;
         if (qi < nq) {
             unsigned* o = partial + ((size_t)blockIdx.y * nq + qi) * 2;
             o[0] = k1[k];
@@ -491,7 +554,16 @@ int orbb_knn2_dev(orbb_matcher* m, const uint8_t* q_dev, int nq, const uint8_t* 
     if (((uintptr_t)q_dev | (uintptr_t)db_dev) & 15) return m_err(m, ORBB_ERR_ARG, "descriptor arrays must be 16-byte aligned");
     if (nd + (int64_t)index_base > INT_MAX) return m_err(m, ORBB_ERR_ARG, "database too large for 32-bit indices");
     ORBM_CUDA(m, cudaSetDevice(m->device));
-    const int qtiles = (nq + KNN_QTILE - 1) / KNN_QTILE;
+    // (CSA, direct) queries per thread; ORBB_KNN_MIX=c,s overrides for experiments
+    // default: 3 queries per thread, all through the 3-3-2 compressor (measured best: 820 Gpairs/s vs 526 direct)
+    static int mixC = -1, mixS = -1, mixM = 3;
+    if (mixC < 0) {
+        mixC = 3; mixS = 0;
+        if (const char* e = getenv("ORBB_KNN_MIX")) sscanf(e, "%d,%d,%d", &mixC, &mixS, &mixM);
+    }
+    const int qpt = mixC + mixS;
+    const int qtile = KNN_THREADS * qpt;
+    const int qtiles = (nq + qtile - 1) / qtile;
     // database chunks: enough CTAs to fill 148 SMs several times over, chunk a multiple of the tile, < 2^22 rows
     int nchunks = 1;
     if (nd > 0) {
@@ -507,7 +579,30 @@ int orbb_knn2_dev(orbb_matcher* m, const uint8_t* q_dev, int nq, const uint8_t* 
             ORBM_CUDA(m, cudaMalloc((void**)&m->partial, need));
             m->partialCap = need;
         }
-        k_knn2_partial<<<dim3(qtiles, nchunks), KNN_THREADS, 0, m->stream>>>((const uint4*)q_dev, nq, (const uint4*)db_dev, nd, (int)rowsPer, m->partial);
+#define ORBB_KNN_LAUNCH(C, S)                                                                                                  \
+    k_knn2_partial<C, S><<<dim3(qtiles, nchunks), KNN_THREADS, 0, m->stream>>>((const uint4*)q_dev, nq, (const uint4*)db_dev, nd, \
+                                                                              (int)rowsPer, m->partial)
+#define ORBB_KNN_LAUNCH_M(C, S, M)                                                                                                \
+    k_knn2_partial<C, S, M, 0><<<dim3(qtiles, nchunks), KNN_THREADS, 0, m->stream>>>((const uint4*)q_dev, nq, (const uint4*)db_dev, \
+                                                                                    nd, (int)rowsPer, m->partial)
+        if (mixM == 2 && mixC == 2 && mixS == 1) ORBB_KNN_LAUNCH_M(2, 1, 2);
+        else if (mixM == 2 && mixC == 3 && mixS == 1) ORBB_KNN_LAUNCH_M(3, 1, 2);
+        else if (mixM == 2 && mixC == 5 && mixS == 2) ORBB_KNN_LAUNCH_M(5, 2, 2);
+        else if (mixM == 2 && mixC == 3 && mixS == 0) ORBB_KNN_LAUNCH_M(3, 0, 2);
+        else if (mixM == 3 && mixC == 3 && mixS == 0) ORBB_KNN_LAUNCH_M(3, 0, 3);
+        else if (mixM == 3 && mixC == 4 && mixS == 0) ORBB_KNN_LAUNCH_M(4, 0, 3);
+        else if (mixM == 3 && mixC == 5 && mixS == 0) ORBB_KNN_LAUNCH_M(5, 0, 3);
+        else if (mixM == 3 && mixC == 4 && mixS == 1) ORBB_KNN_LAUNCH_M(4, 1, 3);
+        else if (mixC == 0 && mixS == 4) ORBB_KNN_LAUNCH(0, 4);
+        else if (mixC == 2 && mixS == 1) ORBB_KNN_LAUNCH(2, 1);
+        else if (mixC == 3 && mixS == 1) ORBB_KNN_LAUNCH(3, 1);
+        else if (mixC == 2 && mixS == 2) ORBB_KNN_LAUNCH(2, 2);
+        else if (mixC == 4 && mixS == 2) ORBB_KNN_LAUNCH(4, 2);
+        else if (mixC == 3 && mixS == 0) ORBB_KNN_LAUNCH(3, 0);
+        else if (mixC == 4 && mixS == 0) ORBB_KNN_LAUNCH(4, 0);
+        else return m_err(m, ORBB_ERR_ARG, "unsupported ORBB_KNN_MIX=%d,%d", mixC, mixS);
+#undef ORBB_KNN_LAUNCH
+#undef ORBB_KNN_LAUNCH_M
         m->launches++;
         k_knn2_merge_chunks<<<(nq + 255) / 256, 256, 0, m->stream>>>(m->partial, nchunks, nq, (int)rowsPer, index_base, idx2_dev, dist2_dev);
         m->launches++;

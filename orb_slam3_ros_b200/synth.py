@@ -111,6 +111,26 @@ def stereo_pair(h, w, index=0, base_seed=BASE_SEED, dmin=4, dmax=64, band=47):
     return left, right
 
 
+def stereo_sequence(h, w, n, base_seed=BASE_SEED, dmin=4, dmax=64, band=47, step=5):
+    """n rectified pairs cut from one wide texture (cheap enough for a 256-pair benchmark batch): the left image of
+    pair i is the crop at column offset i*step; right[y, x] = left-texture[y, x + d_i(y)] with a per-pair, per-band
+    constant disparity, plus +-1 noise.  -> (left[n,h,w], right[n,h,w]) uint8"""
+    rng = np.random.default_rng(np.random.PCG64(base_seed + 104729))
+    wide = np.clip(np.rint(texture(h, w + dmax + n * step, base_seed + 31)), 0, 255).astype(np.uint8)
+    left = np.empty((n, h, w), np.uint8)
+    right = np.empty((n, h, w), np.uint8)
+    cols = np.arange(w)
+    for i in range(n):
+        off = i * step
+        left[i] = wide[:, off:off + w]
+        for y0 in range(0, h, band):
+            d = int(rng.integers(dmin, dmax + 1))
+            right[i, y0:y0 + band] = wide[y0:y0 + band][:, off + d + cols]
+    noise = rng.integers(-1, 2, size=right.shape, dtype=np.int8)
+    right = np.clip(right.astype(np.int16) + noise, 0, 255).astype(np.uint8)
+    return left, right
+
+
 def descriptor_db(n_db, n_query, seed=BASE_SEED, max_flips=40, dup_every=997):
     """kNN workload (BASELINE config 4 recipe): uniform random 256-bit database; half of the queries are
     database rows with k in [0, max_flips] random bit flips (planted neighbours), half uniform random;
