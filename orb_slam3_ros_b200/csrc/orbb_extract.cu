@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(256) k_fast_v0(const Plan* __restrict__ P, Buf
 // ------------------------------------------------------------------------------------------------
 // K3: DistributeOctTree, one CTA per (frame, level).
 // ------------------------------------------------------------------------------------------------
-constexpr int OT_THREADS = 256;
+constexpr int OT_THREADS = 128;
 constexpr int OT_WARPS = OT_THREADS / 32;
 constexpr int OT_SORT_SMEM = 2048;
 
@@ -944,6 +944,8 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
                 d.gy0 = (short)(iniY + 3); d.gy1 = (short)(skip ? iniY + 3 : maxY - 3);
                 d.level = l;
                 d.outOff = L.cellKeyBase + (unsigned)((ci * L.nCols + cj) * L.cellCap);
+                d.scoreOff = L.blurOff;
+                d.bpitch = L.bpitch;
                 cellDesc.push_back(d);
             }
         cells += L.nCols * L.nRows;
@@ -1093,9 +1095,16 @@ static int run_batch(orbb_extractor* h, const uint8_t* dImgs, int nframes, size_
         k_fast_v0<<<dim3(P.cellsTotal, nframes), 256, 0, st>>>(h->dPlan, B);
     } else if (fastMode && !strcmp(fastMode, "cell")) {
         k_fast<<<dim3(P.cellsTotal, nframes), FAST_THREADS, 0, st>>>(h->dPlan, B, 0);
+    }
+    const bool legacyFast = fastMode && (!strcmp(fastMode, "v0") || !strcmp(fastMode, "cell"));
+    if (legacyFast) {
+        mark(h, ST_FAST_CELLS);
+        mark(h, ST_FAST_RETRY);
     } else {
         k_fast_score<<<dim3(P.fsTotal, nframes), FS_THREADS, 0, st>>>(h->dPlan, B);
-        k_fast_cells<<<dim3(P.cellsTotal, nframes), FC_THREADS, 0, st>>>(h->dPlan, B);
+        mark(h, ST_FAST_CELLS);
+        k_fast_cells<<<dim3(P.cellsTotal, nframes), FC_THREADS, 0, st>>>(B, P.cellsTotal, P.blurStride, P.cellKeyStride);
+        mark(h, ST_FAST_RETRY);
         k_fast<<<dim3(std::min(P.cellsTotal, 48), nframes), FAST_THREADS, 0, st>>>(h->dPlan, B, 1);
         h->launches += 2;
     }
@@ -1211,7 +1220,7 @@ int orbb_set_profiling(orbb_extractor* h, int enabled) {
 }
 
 const char* orbb_stage_name(int i) {
-    static const char* names[ST_COUNT] = {"h2d", "pyramid", "fast", "octree", "blur", "assemble", "orient_desc", "d2h"};
+    static const char* names[ST_COUNT] = {"h2d", "pyramid", "fast_score", "fast_cells", "fast_retry", "octree", "blur", "assemble", "orient_desc", "d2h"};
     return (i >= 0 && i < ST_COUNT) ? names[i] : "";
 }
 

@@ -165,77 +165,96 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_score(const Plan* __restric
 }
 
 constexpr int FC_THREADS = 64;
+constexpr int FC_CAP = 1408;                        // >= max NMS survivors of one cell (37 x 37)
 
-__global__ void __launch_bounds__(FC_THREADS) k_fast_cells(const Plan* __restrict__ P, Bufs B) {
-    constexpr int PS = kCellPix;
-    __shared__ __align__(16) uint8_t sS[PS * PS];
-    __shared__ unsigned sSurv[37 * 37 + 3];
-    __shared__ int sCnt;
+// One CTA per cell; 5.6 KB of shared memory so that 32 CTAs fit an SM (the kernel is a chain of dependent loads, not
+// arithmetic).  Corners are sparse (~1 % of the pixels): the cell's part of the score map is scanned straight from
+// global memory one word (4 px) per thread; non-zero bytes go to a small list, and only those are compared with their 8
+// neighbours (read from the map again, zero outside the cell interior: cv::FAST ran on the cell alone).  Survivors are
+// parked in the cell's output segment, then reloaded, ranked by raster position and written back in order.
+__global__ void __launch_bounds__(FC_THREADS) k_fast_cells(Bufs B, int cellsTotal, u64 scoreStride, unsigned cellKeyStride) {
+    __shared__ unsigned sList[FC_CAP];              // (row << 16 | col << 8 | score)
+    __shared__ int sCnt[2];
     const int frame = blockIdx.y;
     const int gcell = blockIdx.x;
     const int tid = threadIdx.x;
     const CellDesc cd = B.cellDesc[gcell];
-    int* cellCount = B.cellCount + (size_t)frame * P->cellsTotal + gcell;
+    int* cellCount = B.cellCount + (size_t)frame * cellsTotal + gcell;
     if (cd.gx1 <= cd.gx0) {                         // :810,:819
         if (tid == 0) *cellCount = 0;
         return;
     }
-    const LevelPlan& L = P->lv[cd.level];
     const int gx0 = cd.gx0, gx1 = cd.gx1, gy0 = cd.gy0, gy1 = cd.gy1;     // cell interior, level coordinates
-    const int ih = gy1 - gy0;
-    const int a0 = (gx0 - 1) & ~3;                  // level column of tile column 0 (leaves >= 1 halo column)
-    const int nw = (gx1 + 1 - a0 + 3) >> 2;         // words per tile row (<= 20)
+    const int ih = gy1 - gy0, bp = cd.bpitch;
+    const int a0 = gx0 & ~3;
+    const int nw = (gx1 - a0 + 3) >> 2;             // words per interior row (<= 20)
     const unsigned mw = (65536u + nw - 1) / nw;
-    const uint8_t* score = B.score + (size_t)frame * P->blurStride + L.blurOff;
-    if (tid == 0) sCnt = 0;
-    // tile row r <-> level row gy0 - 1 + r ; everything outside the interior is zero
-    for (int i = tid; i < (ih + 2) * nw; i += FC_THREADS) {
-        const int r = (int)(((unsigned)i * mw) >> 16), w = i - r * nw;
-        unsigned v = 0;
-        if (r >= 1 && r <= ih) {
+    const uint8_t* score = B.score + (size_t)frame * scoreStride + cd.scoreOff;
+    u64* out = B.cellKeys + (size_t)frame * cellKeyStride + cd.outOff;
+    unsigned* park = reinterpret_cast<unsigned*>(out);      // survivors before ordering (the segment holds >= 37*37 keys)
+    if (tid < 2) sCnt[tid] = 0;
+    const int bandRows = max(1, FC_CAP / (4 * nw));          // a band can never overflow the list (one band for normal cells)
+    for (int rb = 0; rb < ih; rb += bandRows) {
+        const int rows = min(bandRows, ih - rb);
+        __syncthreads();
+        if (tid == 0) sCnt[0] = 0;
+        __syncthreads();
+        for (int i = tid; i < rows * nw; i += FC_THREADS) {
+            const int rr = (int)(((unsigned)i * mw) >> 16), w = i - rr * nw;
+            const int r = rb + rr;
             const int col0 = a0 + 4 * w;
-            const int lo = min(max(gx0 - col0, 0), 4), hi = min(max(gx1 - col0, 0), 4);
-            if (hi > lo) {
-                v = __ldg(reinterpret_cast<const unsigned*>(score + (size_t)(gy0 - 1 + r) * L.bpitch + col0));
-                v &= (0xffffffffu >> (8 * (4 - hi))) & (0xffffffffu << (8 * lo));
+            const int lo = max(gx0 - col0, 0), hi = min(gx1 - col0, 4);
+            unsigned v = __ldg(reinterpret_cast<const unsigned*>(score + (size_t)(gy0 + r) * bp + col0));
+            v &= (0xffffffffu >> (8 * (4 - hi))) & (0xffffffffu << (8 * lo));
+            while (v) {
+                const int k = (__ffs(v) - 1) >> 3;
+                const unsigned sc = (v >> (8 * k)) & 0xffu;
+                v &= ~(0xffu << (8 * k));
+                sList[atomicAdd(&sCnt[0], 1)] = ((unsigned)r << 16) | ((unsigned)(col0 + k - gx0) << 8) | sc;
             }
         }
-        reinterpret_cast<unsigned*>(sS)[r * (PS / 4) + w] = v;
-    }
-    __syncthreads();
-    // ---- NMS: strict '>' against the 8 neighbours (cv::FAST, fast.cpp) ----
-    for (int i = tid; i < ih * nw; i += FC_THREADS) {
-        const int r = (int)(((unsigned)i * mw) >> 16), w = i - r * nw;
-        const unsigned word = reinterpret_cast<const unsigned*>(sS)[(r + 1) * (PS / 4) + w];
-        if (word == 0) continue;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int s = (word >> (8 * k)) & 0xff;
-            if (s == 0) continue;
-            const int pos = (r + 1) * PS + 4 * w + k;
-            const uint8_t* q = &sS[pos];
-            if (s > q[-1] && s > q[1] && s > q[-PS - 1] && s > q[-PS] && s > q[-PS + 1] && s > q[PS - 1] && s > q[PS] && s > q[PS + 1])
-                sSurv[atomicAdd(&sCnt, 1)] = ((unsigned)pos << 8) | (unsigned)s;
+        __syncthreads();
+        // ---- NMS: strict '>' against the 8 neighbours (cv::FAST, fast.cpp) ----
+        const int nCorner = sCnt[0];
+        for (int i = tid; i < nCorner; i += FC_THREADS) {
+            const unsigned rec = sList[i];
+            const int r = (int)(rec >> 16), cx = (int)((rec >> 8) & 0xffu), sc = (int)(rec & 0xffu);
+            const int x = gx0 + cx, y = gy0 + r;
+            const uint8_t* q = score + (size_t)y * bp + x;
+            const bool left = x > gx0, right = x + 1 < gx1, up = y > gy0, down = y + 1 < gy1;
+            bool keep = true;
+            if (left) keep &= sc > q[-1];
+            if (right) keep &= sc > q[1];
+            if (up) {
+                keep &= sc > q[-bp];
+                if (left) keep &= sc > q[-bp - 1];
+                if (right) keep &= sc > q[-bp + 1];
+            }
+            if (down) {
+                keep &= sc > q[bp];
+                if (left) keep &= sc > q[bp - 1];
+                if (right) keep &= sc > q[bp + 1];
+            }
+            if (keep) park[atomicAdd(&sCnt[1], 1)] = rec;    // rec orders by (row, col): the raster key
         }
     }
     __syncthreads();
     // ---- raster order by rank counting; keys are relative to the 16-px border (:865-866) ----
-    const int nSurv = sCnt;
-    u64* out = B.cellKeys + (size_t)frame * P->cellKeyStride + cd.outOff;
+    const int nSurv = sCnt[1];
+    for (int i = tid; i < nSurv; i += FC_THREADS) sList[i] = park[i];
+    __syncthreads();
     for (int i = tid; i < nSurv; i += FC_THREADS) {
-        const unsigned rec = sSurv[i];
+        const unsigned rec = sList[i];
         int rank = 0;
-        for (int j = 0; j < nSurv; j++) rank += sSurv[j] < rec;
-        const int pos = (int)(rec >> 8);
-        const int r = pos / PS, col = pos - r * PS;
-        const int x = a0 + col - kMinBorder, y = gy0 - 1 + r - kMinBorder;
+        for (int j = 0; j < nSurv; j++) rank += sList[j] < rec;
+        const int x = gx0 + (int)((rec >> 8) & 0xffu) - kMinBorder, y = gy0 + (int)(rec >> 16) - kMinBorder;
         out[rank] = (u64)(unsigned)x | ((u64)(unsigned)y << 16) | ((u64)(rec & 0xffu) << 32);
     }
     if (tid == 0) {
         *cellCount = nSurv;
         if (nSurv == 0) {                           // retry this cell with minThFAST (k_fast, mode 1)
             const int slot = atomicAdd(&B.fbCount[frame], 1);
-            B.fbList[(size_t)frame * P->cellsTotal + slot] = gcell;
+            B.fbList[(size_t)frame * cellsTotal + slot] = gcell;
         }
     }
 }

@@ -62,7 +62,7 @@ struct WorkItem { int level, x, y, pos; };
 
 // FAST cell (host-built, shared by all frames): interior [gx0,gx1) x [gy0,gy1) in level coordinates (empty when the
 // reference skips the cell, ORBextractor.cc:810,:819), first key slot of the cell inside the frame's cellKeys.
-struct CellDesc { short gx0, gx1, gy0, gy1; int level; unsigned outOff; };
+struct CellDesc { short gx0, gx1, gy0, gy1; int level; unsigned outOff; unsigned scoreOff; int bpitch; };
 
 // Device buffers of one extractor handle, sized for `capacity` frames.
 struct Bufs {
@@ -96,7 +96,7 @@ struct Bufs {
     int* sad;
 };
 
-enum Stage { ST_H2D = 0, ST_PYRAMID, ST_FAST, ST_OCTREE, ST_BLUR, ST_ASSEMBLE, ST_ORIENT_DESC, ST_D2H, ST_COUNT };
+enum Stage { ST_H2D = 0, ST_PYRAMID, ST_FAST, ST_FAST_CELLS, ST_FAST_RETRY, ST_OCTREE, ST_BLUR, ST_ASSEMBLE, ST_ORIENT_DESC, ST_D2H, ST_COUNT };
 
 }  // namespace orbb
 
