@@ -100,6 +100,13 @@ int orbb_extract_batch(orbb_extractor* h, const uint8_t* dev_imgs, int nframes, 
 int orbb_extract_batch_host(orbb_extractor* h, const uint8_t* host_imgs, int nframes, int width, int height,
                             size_t row_stride, size_t frame_stride, int lap0, int lap1, orbb_keypoint* kps, uint8_t* desc,
                             int capacity, int32_t* counts);
+/* The same call split in two so that a caller can overlap batches on two handles (handle A uploads batch i+1 while
+ * handle B computes batch i): _submit enqueues H2D + kernels + D2H and returns; the host buffers must stay valid until
+ * _wait, which synchronises and fills counts. */
+int orbb_extract_batch_host_submit(orbb_extractor* h, const uint8_t* host_imgs, int nframes, int width, int height,
+                                   size_t row_stride, size_t frame_stride, int lap0, int lap1, orbb_keypoint* kps,
+                                   uint8_t* desc, int capacity);
+int orbb_extract_batch_host_wait(orbb_extractor* h, int32_t* counts);
 int orbb_sync(orbb_extractor* h);
 /* CUDA stream (cudaStream_t) the handle launches on, for callers that time with their own events */
 void* orbb_stream(orbb_extractor* h);

@@ -45,6 +45,8 @@ SYMBOLS = [
     ("orbb_pyramid_level", _I, [_VP, _I, C.POINTER(_VP), _PI, _PI, C.POINTER(_SZ)]),
     ("orbb_extract_batch", _I, [_VP, _VP, _I, _I, _I, _SZ, _SZ, _I, _I]),
     ("orbb_extract_batch_host", _I, [_VP, _VP, _I, _I, _I, _SZ, _SZ, _I, _I, _VP, _VP, _I, _VP]),
+    ("orbb_extract_batch_host_submit", _I, [_VP, _VP, _I, _I, _I, _SZ, _SZ, _I, _I, _VP, _VP, _I]),
+    ("orbb_extract_batch_host_wait", _I, [_VP, _VP]),
     ("orbb_sync", _I, [_VP]),
     ("orbb_stream", _VP, [_VP]),
     ("orbb_batch_fetch", _I, [_VP, _I, _VP, _VP, _I, _VP]),

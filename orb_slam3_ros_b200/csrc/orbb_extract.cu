@@ -11,6 +11,7 @@
 //   k_orient_desc                 IC_Angle + fastAtan2 + computeOrbDescriptor :76-146
 //
 // Compiled with -fmad=false: the un-fused float32 result is the specification.
+#include <limits.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -1307,9 +1308,10 @@ static cudaError_t copy_rows(void* dst, size_t dpitch, const void* src, size_t s
     return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, st);
 }
 
-int orbb_extract_batch_host(orbb_extractor* h, const uint8_t* host_imgs, int nframes, int width, int height, size_t row_stride,
-                            size_t frame_stride, int lap0, int lap1, orbb_keypoint* kps, uint8_t* desc, int capacity, int32_t* counts) {
-    if (!h || !counts) return ORBB_ERR_ARG;
+int orbb_extract_batch_host_submit(orbb_extractor* h, const uint8_t* host_imgs, int nframes, int width, int height, size_t row_stride,
+                                   size_t frame_stride, int lap0, int lap1, orbb_keypoint* kps, uint8_t* desc, int capacity) {
+    if (!h) return ORBB_ERR_ARG;
+    h->pendingFrames = 0;
     if (!host_imgs || nframes <= 0 || width <= 0 || height <= 0) return set_err(h, ORBB_ERR_EMPTY, "empty image");
     ORBB_CUDA(h, cudaSetDevice(h->device));
     int rc = ensure_plan(h, width, height, nframes);
@@ -1326,7 +1328,8 @@ int orbb_extract_batch_host(orbb_extractor* h, const uint8_t* host_imgs, int nfr
     }
     // Pipeline in up to 8 chunks of frames: H2D (copy engine 1) -> kernels (handle stream) -> D2H (copy engine 2), so the
     // upload of chunk c+1 and the download of chunk c-1 overlap the kernels of chunk c.
-    const int nchunks = nframes >= 64 ? 8 : (nframes >= 8 ? 2 : 1);
+    static const int chunkOverride = getenv("ORBB_CHUNKS") ? atoi(getenv("ORBB_CHUNKS")) : 0;
+    const int nchunks = chunkOverride > 0 ? std::min(std::min(chunkOverride, 8), nframes) : (nframes >= 64 ? 3 : (nframes >= 8 ? 2 : 1));
     const int per = (nframes + nchunks - 1) / nchunks;
     const int ncopy = std::min(capacity, P.kpCap);
     ORBB_CUDA(h, cudaEventRecord(h->evDone[0], h->stream));                  // earlier work on the handle's stream ...
@@ -1361,15 +1364,34 @@ int orbb_extract_batch_host(orbb_extractor* h, const uint8_t* host_imgs, int nfr
             ORBB_CUDA(h, copy_rows(desc + (size_t)f0 * capacity * 32, (size_t)32 * capacity, h->b.desc + (size_t)f0 * P.kpCap * 32,
                                    (size_t)32 * P.kpCap, (size_t)32 * ncopy, n, cudaMemcpyDeviceToHost, h->d2hStream));
     }
+    h->pendingFrames = nframes;
+    h->pendingCapacity = (kps || desc) ? capacity : INT_MAX;
+    return ORBB_OK;
+}
+
+int orbb_extract_batch_host_wait(orbb_extractor* h, int32_t* counts) {
+    if (!h || !counts) return ORBB_ERR_ARG;
+    if (h->pendingFrames <= 0) return set_err(h, ORBB_ERR_ARG, "no submitted batch to wait for");
+    ORBB_CUDA(h, cudaSetDevice(h->device));
     ORBB_CUDA(h, cudaStreamSynchronize(h->d2hStream));
     ORBB_CUDA(h, cudaStreamSynchronize(h->stream));
+    const int nframes = h->pendingFrames;
+    h->pendingFrames = 0;
     for (int f = 0; f < nframes; f++) {
         counts[2 * f] = h->hCounts[2 * f];
         counts[2 * f + 1] = h->hCounts[2 * f + 1];
         if (h->hCounts[2 * nframes + f]) return set_err(h, ORBB_ERR_INTERNAL, "frame %d: device status 0x%x (capacity overflow)", f, h->hCounts[2 * nframes + f]);
-        if (counts[2 * f] > capacity && (kps || desc)) return set_err(h, ORBB_ERR_CAPACITY, "frame %d has %d keypoints, capacity %d", f, counts[2 * f], capacity);
+        if (counts[2 * f] > h->pendingCapacity) return set_err(h, ORBB_ERR_CAPACITY, "frame %d has %d keypoints, capacity %d", f, counts[2 * f], h->pendingCapacity);
     }
     return ORBB_OK;
+}
+
+int orbb_extract_batch_host(orbb_extractor* h, const uint8_t* host_imgs, int nframes, int width, int height, size_t row_stride,
+                            size_t frame_stride, int lap0, int lap1, orbb_keypoint* kps, uint8_t* desc, int capacity, int32_t* counts) {
+    if (!h || !counts) return ORBB_ERR_ARG;
+    const int rc = orbb_extract_batch_host_submit(h, host_imgs, nframes, width, height, row_stride, frame_stride, lap0, lap1, kps, desc, capacity);
+    if (rc) return rc;
+    return orbb_extract_batch_host_wait(h, counts);
 }
 
 int orbb_extract(orbb_extractor* h, const uint8_t* img, int width, int height, size_t stride, int lap0, int lap1,

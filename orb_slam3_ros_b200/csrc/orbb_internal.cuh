@@ -117,6 +117,7 @@ struct orbb_extractor {
     orbb::Bufs b{};
     std::vector<void*> allocs;
     int lastFrames = 0;
+    int pendingFrames = 0, pendingCapacity = 0;   // orbb_extract_batch_host_submit -> _wait
     long long launches = 0;
     bool profiling = false;
     cudaEvent_t ev[orbb::ST_COUNT + 1]{};

@@ -132,6 +132,22 @@ class ORBextractor:
         capi.check(rc, self._h)
         return counts, kps, desc
 
+    def submit_batch_host(self, images, lapping=(0, 0), out=None):
+        """asynchronous half of extract_batch_host: enqueue upload + kernels + download; call wait_batch_host() later.
+        images / out must stay alive (and should be pinned) until then."""
+        n, h, w = images.shape
+        kps, desc, counts = out
+        self._pending = (images, out)
+        capi.check(self._lib.orbb_extract_batch_host_submit(self._h, capi.ptr(images), n, w, h, images.strides[1], images.strides[0],
+                                                            int(lapping[0]), int(lapping[1]), capi.ptr(kps), capi.ptr(desc),
+                                                            kps.shape[1]), self._h)
+
+    def wait_batch_host(self):
+        images, (kps, desc, counts) = self._pending
+        capi.check(self._lib.orbb_extract_batch_host_wait(self._h, capi.ptr(counts)), self._h)
+        self._pending = None
+        return counts, kps, desc
+
     def set_profiling(self, on=True):
         capi.check(self._lib.orbb_set_profiling(self._h, int(on)), self._h)
 

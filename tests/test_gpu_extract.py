@@ -194,3 +194,28 @@ def test_full_size_batch_properties():
         rc, k0, d0, m0 = port.PortExtractor().extract(frames[f], (0, 1000))
         n = c1[f, 0]
         assert_same_features(k0, d0, m0, k1[f, :n], d1[f, :n], int(c1[f, 1]), f"frame {f}")
+
+
+def test_submit_wait_on_two_handles_equals_sync_call():
+    """orbb_extract_batch_host_submit/_wait: two handles overlapping their batches give the results of the sync call"""
+    NF = 12
+    frames = [synth.sequence(240, 320, NF, canvas=512, base_seed=100 + i) for i in range(3)]
+    a, b = ORBextractor(300, 1.2, 4, max_batch=NF), ORBextractor(300, 1.2, 4, max_batch=NF)
+    cap = a.max_keypoints
+
+    def bufs():
+        return (np.zeros((NF, cap), capi.KP_DTYPE), np.zeros((NF, cap, 32), np.uint8), np.zeros((NF, 2), np.int32))
+
+    want = [a.extract_batch_host(f, (0, 1000), out=bufs()) for f in frames]
+    outs = [bufs() for _ in frames]
+    a.submit_batch_host(frames[0], (0, 1000), out=outs[0])
+    b.submit_batch_host(frames[1], (0, 1000), out=outs[1])
+    a.wait_batch_host()
+    a.submit_batch_host(frames[2], (0, 1000), out=outs[2])
+    b.wait_batch_host()
+    a.wait_batch_host()
+    for (c0, k0, d0), (k1, d1, c1) in zip(want, outs):
+        assert np.array_equal(c0, c1)
+        for f in range(NF):
+            n = c0[f, 0]
+            assert np.array_equal(k0[f, :n], k1[f, :n]) and np.array_equal(d0[f, :n], d1[f, :n])
