@@ -993,6 +993,8 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
                 const short b0 = (short)cv_round_f((1.f - fy) * 2048.f), b1 = (short)cv_round_f(fy * 2048.f);
                 tab.push_back(make_int2(sy, (int)((unsigned short)b0 | ((unsigned)(unsigned short)b1 << 16))));
             }
+            while (tab.size() % 4) tab.push_back(tab.back());
+
         }
     }
     P.cellsTotal = cells; P.blurTilesTotal = tiles; P.kpCap = kpCap; P.fsTotal = fsTiles;

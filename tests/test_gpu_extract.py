@@ -219,3 +219,18 @@ def test_submit_wait_on_two_handles_equals_sync_call():
         for f in range(NF):
             n = c0[f, 0]
             assert np.array_equal(k0[f, :n], k1[f, :n]) and np.array_equal(d0[f, :n], d1[f, :n])
+
+
+@pytest.mark.parametrize("sf,nl", [(1.5, 4), (2.0, 3), (1.1, 6)])
+def test_other_scale_factors(sf, nl):
+    """scaleFactor is a user setting (ORBextractor.scaleFactor in the YAML files); 2.0 is the exact-decimation case in
+    which cv::resize silently switches INTER_LINEAR to INTER_AREA (same numbers as the fixed-point bilinear path)."""
+    img = synth.frame(480, 640, 1)
+    pe = port.PortExtractor(500, sf, nl)
+    rc, k0, d0, m0 = pe.extract(img)
+    ge = ORBextractor(500, sf, nl)
+    m1, k1, d1 = ge(img)
+    for l in range(nl):
+        assert np.array_equal(pe.level(l, bordered=True), ge.debug_level(0, l, bordered=True)), l
+    assert_same_features(k0, d0, m0, k1, d1, m1, f"scale {sf}")
+    assert np.array_equal(ge.GetScaleFactors(), pe.scale_factors)

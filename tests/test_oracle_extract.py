@@ -86,3 +86,14 @@ def test_port_stereo_and_best2_sanity():
     for i in range(20):
         ds = [port.hamming(dl[i], dr[c]) for c in cand[rowptr[i]:rowptr[i + 1]]]
         assert out[i, 0] == min(ds) and out[i, 1] == cand[rowptr[i] + int(np.argmin(ds))]
+
+
+@pytest.mark.parametrize("sf,nl", [(1.5, 4), (2.0, 3), (1.1, 6)])
+def test_port_equals_cv2_reference_other_scale_factors(sf, nl):
+    img = synth.frame(480, 640, 1)
+    pe, re_ = port.PortExtractor(500, sf, nl), orb_ref.RefExtractor(500, sf, nl)
+    rc, k0, d0, m0 = pe.extract(img)
+    rc2, k1, d1, m1 = re_.extract(img)
+    for l in range(nl):
+        assert np.array_equal(pe.level(l, bordered=True), re_.pyramid[l])
+    _same(k0, d0, m0, k1, d1, m1)
