@@ -265,6 +265,17 @@ def run_ours(a):
     e2e_sync_s = max_over_ranks(time.perf_counter() - t0)
     del ext2
 
+    # ---- BASELINE config 1: ONE 752x480 frame through the synchronous call the SLAM thread makes (latency, not throughput)
+    ext1 = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=1)
+    one = np.ascontiguousarray(host_np[0][0])
+    for _ in range(5):
+        ext1(one, None, LAPPING)
+    t0 = time.perf_counter()
+    for _ in range(50):
+        ext1(one, None, LAPPING)
+    single_ms = (time.perf_counter() - t0) / 50 * 1e3
+    del ext1
+
     # ---- roofline of the dominant kernel (and of the whole path) ----
     # "pyramid" is a stage of 9 launches (level0, 7 resizes, apron); the other entries are single kernels
     kernels = {k: v for k, v in stage_acc.items() if k not in ("h2d", "d2h", "pyramid") and v > 0}
@@ -419,6 +430,7 @@ def run_ours(a):
                        f"({NSETS * B * W_ * H_ / 1e6:.0f} MB) rotated; per-step working set (pyramids+workspaces) ~{B * 9.5 / 1e3:.1f} GB >> 126 MB L2",
                        "parallelism": f"frames partitioned over {world} GPU(s), no collective"},
             "keypoints_per_frame": n_kp / B,
+            "single_frame_latency_ms": single_ms,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / a.steps,
                     "api": "orbb_extract_batch_host_submit/_wait on two alternating handles (pinned host frames -> keypoints+descriptors)",

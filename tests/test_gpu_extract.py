@@ -234,3 +234,24 @@ def test_other_scale_factors(sf, nl):
         assert np.array_equal(pe.level(l, bordered=True), ge.debug_level(0, l, bordered=True)), l
     assert_same_features(k0, d0, m0, k1, d1, m1, f"scale {sf}")
     assert np.array_equal(ge.GetScaleFactors(), pe.scale_factors)
+
+
+def test_frame_partition_is_result_invariant():
+    """BASELINE config 3 semantics at reduced size: a TUM-shape sequence partitioned over ranks (contiguous blocks, no
+    collective) gives, frame for frame, what one extractor gives for the whole sequence."""
+    import torch
+    from orb_slam3_ros_b200 import sharding
+    NF, world = 24, 3
+    frames = synth.sequence(480, 640, NF, canvas=1024)
+    whole = ORBextractor(1000, 1.2, 8, max_batch=NF)
+    whole.extract_batch_device(torch.from_numpy(frames).cuda(), NF, 640, 480)
+    c0, k0, d0 = whole.fetch(NF)
+    for rank in range(world):
+        lo, hi = sharding.block_bounds(NF, world, rank)
+        part = ORBextractor(1000, 1.2, 8, max_batch=hi - lo)
+        part.extract_batch_device(torch.from_numpy(frames[lo:hi]).cuda(), hi - lo, 640, 480)
+        c1, k1, d1 = part.fetch(hi - lo)
+        assert np.array_equal(c0[lo:hi], c1)
+        for f in range(hi - lo):
+            n = c1[f, 0]
+            assert np.array_equal(k0[lo + f, :n], k1[f, :n]) and np.array_equal(d0[lo + f, :n], d1[f, :n])
