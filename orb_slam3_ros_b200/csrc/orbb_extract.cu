@@ -1005,7 +1005,7 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
     const size_t F = (size_t)frames;
     int rc;
 #define A(ptr, count) if ((rc = dev_alloc(h, &ptr, (count))) != ORBB_OK) return rc
-    A(b.pyr, F * pyrBytes);
+    A(b.pyr, F * pyrBytes + 512);          // slack: tile rows of the last level may be read a few bytes past their pitch
     A(b.blur, F * blurBytes);
     A(b.score, F * blurBytes);
     A(b.tab, tab.size());

@@ -26,12 +26,15 @@ __device__ __forceinline__ unsigned quick_mask4(unsigned wl, unsigned wc, unsign
     return ((te >> 15) & 1u) | ((to >> 14) & 2u) | ((te >> 29) & 4u) | ((to >> 28) & 8u);
 }
 
-// tile of one CTA: 32 word-columns (+1 halo word each side) x (4 strips x FS_R rows + 6 halo rows)
-constexpr int FS_TP = 34 * 4 + 8;                   // tile pitch in bytes (144: rows stay 16-byte aligned)
+// tile of one CTA: 32 word-columns with 16 halo bytes on each side (so every tile row starts 16-byte aligned in global
+// memory and can be fetched by one TMA bulk copy) x (4 strips x FS_R rows + 6 halo rows)
+constexpr int FS_TP = 128 + 32;                     // tile pitch in bytes
+constexpr int FS_XOFF = 16;                         // tile byte of the CTA's first image column
 constexpr int FS_TROWS = 4 * FS_R + 6;
 
 __global__ void __launch_bounds__(FS_THREADS) k_fast_score(const Plan* __restrict__ P, Bufs B) {
-    __shared__ __align__(16) uint8_t sTile[FS_TROWS * FS_TP];
+    __shared__ __align__(128) uint8_t sTile[FS_TROWS * FS_TP];
+    __shared__ __align__(8) unsigned long long sBar;
     __shared__ unsigned short sCand[FS_CAP];         // tile position of each candidate
     __shared__ unsigned short sCorner[FS_CAP];       // tile position | polarity << 15
     __shared__ int sCnt[2];
@@ -42,7 +45,7 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_score(const Plan* __restric
     const int t = blockIdx.x - L.fsBase;
     const int gy = t / L.fsTilesX, gx = t - gy * L.fsTilesX;
     const int tid = threadIdx.x, lane = tid & 31, ty = tid >> 5;
-    const int xw0 = gx * 32 - 1;                     // level word-column of tile word 0
+    const int xt0 = gx * 128 - FS_XOFF;              // level column of tile byte 0
     const int yt0 = kEdge + gy * 4 * FS_R - 3;       // level row of tile row 0
     const int xlo = kEdge, xhi = L.w - kEdge, yhi = L.h - kEdge;      // union of the cell interiors: [19, w-19) x [19, h-19)
     const int th = min(max(P->iniTh, 0), 255);
@@ -50,17 +53,20 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_score(const Plan* __restric
     const uint8_t* roi = B.pyr + (size_t)frame * P->pyrStride + L.roiOff;
     uint8_t* score = B.score + (size_t)frame * P->blurStride + L.blurOff;
     if (tid < 2) sCnt[tid] = 0;
-    // ---- stage the tile (rows beyond the bottom apron / words beyond the right apron are never used: clamp) ----
-    {
-        const int maxRow = L.h + kEdge - 1, maxWord = (L.w + kEdge - 1) >> 2;
-        for (int i = tid; i < FS_TROWS * 34; i += FS_THREADS) {
-            const int r = i / 34, w = i - r * 34;
-            const int gyy = min(yt0 + r, maxRow), gw = min(xw0 + w, maxWord);
-            reinterpret_cast<unsigned*>(sTile)[r * (FS_TP / 4) + w] =
-                __ldg(reinterpret_cast<const unsigned*>(roi + (ptrdiff_t)gyy * L.pitch) + gw);
-        }
+    // ---- stage the tile: one 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) per tile row, all completing on one mbarrier.
+    // Rows below the bottom apron are clamped (never used); bytes right of the apron come from the row's alignment
+    // padding / the next row (never used either).
+    if (tid == 0) {
+        mbar_init(&sBar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&sBar, FS_TROWS * FS_TP);
     }
     __syncthreads();
+    if (tid < FS_TROWS) {
+        const int gyy = min(yt0 + tid, L.h + kEdge - 1);
+        tma_bulk_g2s(sTile + tid * FS_TP, roi + (ptrdiff_t)gyy * L.pitch + xt0, FS_TP, &sBar);
+    }
+    mbar_wait(&sBar, 0);
 
     // ---- A: quick reject over FS_R rows, 4 pixels per thread and row ----
     const int wcol = gx * 32 + lane;
@@ -70,7 +76,7 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_score(const Plan* __restric
         unsigned xmask = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) xmask |= (unsigned)(wcol * 4 + k >= xlo && wcol * 4 + k < xhi) << k;
-        const unsigned* tw = reinterpret_cast<const unsigned*>(sTile) + (ty * FS_R) * (FS_TP / 4) + lane + 1;
+        const unsigned* tw = reinterpret_cast<const unsigned*>(sTile) + (ty * FS_R) * (FS_TP / 4) + lane + FS_XOFF / 4;
         unsigned* srow = reinterpret_cast<unsigned*>(score + (size_t)y0 * L.bpitch + 4 * wcol);
 #pragma unroll
         for (int r = 0; r < FS_R; r++) {
@@ -90,7 +96,7 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_score(const Plan* __restric
         if (lane == 31 && wtot) wbase = atomicAdd(&sCnt[0], wtot);
         wbase = __shfl_sync(0xffffffffu, wbase, 31);
         int o = wbase + inc - cnt;
-        const int pos0 = (ty * FS_R + 3) * FS_TP + (lane + 1) * 4;
+        const int pos0 = (ty * FS_R + 3) * FS_TP + lane * 4 + FS_XOFF;
         while (candAll) {
             const int b = __ffs(candAll) - 1;
             candAll &= candAll - 1;
@@ -160,7 +166,7 @@ __global__ void __launch_bounds__(FS_THREADS) k_fast_score(const Plan* __restric
             M = max3i(M, e0, e1);
         }
         const int r = pos / PS, col = pos - r * PS;
-        score[(size_t)(yt0 + r) * L.bpitch + (xw0 * 4 + col)] = (uint8_t)(M - 1);
+        score[(size_t)(yt0 + r) * L.bpitch + (xt0 + col)] = (uint8_t)(M - 1);
     }
 }
 
