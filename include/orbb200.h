@@ -19,6 +19,8 @@
  *                                                                         :1743-1768 ...: same loop shape)
  *   orbb_knn2 / orbb_knn2_partial   cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, 2)   orb_slam3/src/Frame.cc:1144
  *   orbb_knn2_merge                 (top-2 merge of database shards after an all-gather; no reference counterpart)
+ *   orbb_distinctive_csr            MapPoint::ComputeDistinctiveDescriptors   orb_slam3/src/MapPoint.cc:329-403   ("next" row)
+ *   orbb_extract_color / _batch_color   cv::cvtColor(..., COLOR_*2GRAY) + extraction   orb_slam3/src/Tracking.cc:1498-1525, :1605-1618 ("next" row)
  *
  * Threading: one thread per handle at a time; distinct handles are independent (own stream, own workspace).
  * Errors: every function returns ORBB_OK (0) or a negative code; orbb_last_error() gives the text.
@@ -107,6 +109,13 @@ int orbb_extract_batch_host_submit(orbb_extractor* h, const uint8_t* host_imgs, 
                                    size_t row_stride, size_t frame_stride, int lap0, int lap1, orbb_keypoint* kps,
                                    uint8_t* desc, int capacity);
 int orbb_extract_batch_host_wait(orbb_extractor* h, int32_t* counts);
+/* Colour input ("next" row of the scope table): the cv::cvtColor(COLOR_{RGB,BGR,RGBA,BGRA}2GRAY) that Tracking applies
+ * before building a Frame (Tracking.cc:1498-1525) runs on the device, then the normal extraction.  channels = 3 or 4,
+ * rgb_order = 1 for RGB(A), 0 for BGR(A) (Tracking's mbRGB).  Fixed point of OpenCV 4.x: (R*9798 + G*19235 + B*3735 + 2^14) >> 15. */
+int orbb_extract_color(orbb_extractor* h, const uint8_t* img, int width, int height, size_t stride, int channels, int rgb_order,
+                       int lap0, int lap1, orbb_keypoint* kps, uint8_t* desc, int capacity, int* n_out, int* mono_index);
+int orbb_extract_batch_color(orbb_extractor* h, const uint8_t* dev_imgs, int nframes, int width, int height, size_t row_stride,
+                             size_t frame_stride, int channels, int rgb_order, int lap0, int lap1);
 int orbb_sync(orbb_extractor* h);
 /* CUDA stream (cudaStream_t) the handle launches on, for callers that time with their own events */
 void* orbb_stream(orbb_extractor* h);
@@ -174,6 +183,11 @@ int orbb_ratio_test_dev(orbb_matcher* m, const int32_t* idx2_dev, const int32_t*
  * out4[i] = {bestDist, bestIdx, secondDist, secondIdx} (idx -1 if none).  Host pointers; synchronous. */
 int orbb_best2_csr(orbb_matcher* m, const uint8_t* q, int nq, const uint8_t* train, int ntrain, const int32_t* cand,
                    const int32_t* rowptr, int init, int32_t* out4);
+
+/* MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:329-403) for many map points at once: group g holds the
+ * descriptors desc[rowptr[g] .. rowptr[g+1]) (32 bytes each, host memory); best[g] = index within the group of the
+ * descriptor with the least median Hamming distance to the others (first minimum), -1 for an empty group. */
+int orbb_distinctive_csr(orbb_matcher* m, const uint8_t* desc, int ntotal, const int32_t* rowptr, int ngroups, int32_t* best);
 
 /* pinned host memory helpers (so callers without a CUDA runtime can stage asynchronously) */
 void* orbb_host_alloc(size_t bytes);

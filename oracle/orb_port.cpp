@@ -729,6 +729,46 @@ void port_best2_csr(const uint8_t* q, int nq, const uint8_t* train, const int32_
     }
 }
 
+// ---- MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:329-403), batched over groups ------------------------
+// group g = descriptors desc[rowptr[g] .. rowptr[g+1]); best[g] = index (within the group) of the descriptor with the
+// least median distance to the others (first minimum; median = sorted[(size_t)(0.5*(N-1))], self distance 0 included);
+// -1 for an empty group (the reference returns early, :367-368)
+void port_distinctive(const uint8_t* desc, const int32_t* rowptr, int ngroups, int32_t* best) {
+    for (int g = 0; g < ngroups; g++) {
+        const int N = rowptr[g + 1] - rowptr[g];
+        const uint8_t* d = desc + (size_t)rowptr[g] * 32;
+        if (N <= 0) { best[g] = -1; continue; }
+        std::vector<float> dist((size_t)N * N);
+        for (int i = 0; i < N; i++) {                                                     // :372-383
+            dist[(size_t)i * N + i] = 0;
+            for (int j = i + 1; j < N; j++) {
+                const int dij = descriptor_distance(d + (size_t)i * 32, d + (size_t)j * 32);
+                dist[(size_t)i * N + j] = (float)dij;
+                dist[(size_t)j * N + i] = (float)dij;
+            }
+        }
+        int bestMedian = INT_MAX, bestIdx = 0;                                            // :386-399
+        for (int i = 0; i < N; i++) {
+            std::vector<int> v(dist.begin() + (size_t)i * N, dist.begin() + (size_t)(i + 1) * N);
+            std::sort(v.begin(), v.end());
+            const int median = v[(size_t)(0.5 * (N - 1))];
+            if (median < bestMedian) { bestMedian = median; bestIdx = i; }
+        }
+        best[g] = bestIdx;
+    }
+}
+
+// ---- cv::cvtColor(src, dst, COLOR_{RGB,BGR,RGBA,BGRA}2GRAY) for 8-bit images (Tracking.cc:1498-1525) ----------------
+// OpenCV 4.x fixed point: (R*9798 + G*19235 + B*3735 + 2^14) >> 15   (color_rgb.simd.hpp, RGB2Gray<uchar>)
+void port_gray(const uint8_t* src, int w, int h, size_t stride, int channels, int rgb, uint8_t* dst, size_t dstride) {
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const uint8_t* p = src + (size_t)y * stride + (size_t)x * channels;
+            const int r = rgb ? p[0] : p[2], g = p[1], b = rgb ? p[2] : p[0];
+            dst[(size_t)y * dstride + x] = (uint8_t)((r * 9798 + g * 19235 + b * 3735 + (1 << 14)) >> 15);
+        }
+}
+
 // ---- Frame::ComputeStereoMatches (Frame.cc:811-981) ----------------------------------------------------
 // hL/hR: extractors that have just processed the left/right image (their pyramids are read, :908,:923).
 // Returns the number of surviving matches, or -1 on error.  sadOut (optional): best SAD per left kp (-1 none).

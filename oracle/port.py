@@ -72,6 +72,8 @@ def _sig(lib):
     lib.port_hamming.argtypes = [C.c_void_p, C.c_void_p]
     lib.port_knn2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int]
     lib.port_best2_csr.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.port_distinctive.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.port_gray.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     lib.port_stereo.restype = C.c_int
     lib.port_stereo.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -261,6 +263,24 @@ def best2_csr(q, train, cand, rowptr, init=256):
     rowptr = np.ascontiguousarray(rowptr, np.int32)
     out = np.zeros((len(q), 4), np.int32)
     lib().port_best2_csr(_ptr(q), len(q), _ptr(train), _ptr(cand), _ptr(rowptr), init, _ptr(out))
+    return out
+
+
+def distinctive(desc, rowptr):
+    """MapPoint::ComputeDistinctiveDescriptors per CSR group -> best index within each group (-1 for empty groups)"""
+    desc = _u8c(desc)
+    rowptr = np.ascontiguousarray(rowptr, np.int32)
+    best = np.zeros(len(rowptr) - 1, np.int32)
+    lib().port_distinctive(_ptr(desc), _ptr(rowptr), len(best), _ptr(best))
+    return best
+
+
+def gray(img, rgb=True):
+    """cv::cvtColor(..., COLOR_{RGB,BGR,RGBA,BGRA}2GRAY) on an [h,w,3|4] uint8 image"""
+    img = _u8c(img)
+    h, w, c = img.shape
+    out = np.zeros((h, w), np.uint8)
+    lib().port_gray(_ptr(img), w, h, img.strides[0], c, int(rgb), _ptr(out), out.strides[0])
     return out
 
 

@@ -47,6 +47,8 @@ SYMBOLS = [
     ("orbb_extract_batch_host", _I, [_VP, _VP, _I, _I, _I, _SZ, _SZ, _I, _I, _VP, _VP, _I, _VP]),
     ("orbb_extract_batch_host_submit", _I, [_VP, _VP, _I, _I, _I, _SZ, _SZ, _I, _I, _VP, _VP, _I]),
     ("orbb_extract_batch_host_wait", _I, [_VP, _VP]),
+    ("orbb_extract_color", _I, [_VP, _VP, _I, _I, _SZ, _I, _I, _I, _I, _VP, _VP, _I, _PI, _PI]),
+    ("orbb_extract_batch_color", _I, [_VP, _VP, _I, _I, _I, _SZ, _SZ, _I, _I, _I, _I]),
     ("orbb_sync", _I, [_VP]),
     ("orbb_stream", _VP, [_VP]),
     ("orbb_batch_fetch", _I, [_VP, _I, _VP, _VP, _I, _VP]),
@@ -72,6 +74,7 @@ SYMBOLS = [
     ("orbb_knn2_merge_dev", _I, [_VP, _VP, _VP, _I, _I, _VP, _VP]),
     ("orbb_ratio_test_dev", _I, [_VP, _VP, _VP, _I, _D, _VP]),
     ("orbb_best2_csr", _I, [_VP, _VP, _I, _VP, _I, _VP, _VP, _I, _VP]),
+    ("orbb_distinctive_csr", _I, [_VP, _VP, _I, _VP, _I, _VP]),
     ("orbb_host_alloc", _VP, [_SZ]),
     ("orbb_host_free", None, [_VP]),
 ]

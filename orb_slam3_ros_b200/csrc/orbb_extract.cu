@@ -63,6 +63,25 @@ __device__ __forceinline__ int warp_sum(int v) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// K0 ("next" row): cv::cvtColor(COLOR_{RGB,BGR,RGBA,BGRA}2GRAY) for 8-bit input (Tracking.cc:1498-1525), OpenCV 4.x fixed
+// point.  4 output pixels per thread into the tightly packed gray staging frame.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gray(const uint8_t* __restrict__ src, size_t rowStride, size_t frameStride, int channels,
+                                              int rgbOrder, uint8_t* __restrict__ dst, int w, int h) {
+    const int word = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int frame = blockIdx.z;
+    if (word * 4 >= w || y >= h) return;
+    const uint8_t* p = src + (size_t)frame * frameStride + (size_t)y * rowStride + (size_t)word * 4 * channels;
+    uint8_t* d = dst + ((size_t)frame * h + y) * w + word * 4;
+    const int n = min(4, w - word * 4);
+    for (int k = 0; k < n; k++, p += channels) {
+        const int r = rgbOrder ? p[0] : p[2], g = p[1], b = rgbOrder ? p[2] : p[0];
+        d[k] = (uint8_t)((r * 9798 + g * 19235 + b * 3735 + (1 << 14)) >> 15);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1: pyramid (ComputePyramid :1170-1195).  Three kernels: level 0 = copy of the source into its slab, level l =
 // cv::resize of level l-1 (image pixels only, 4 per thread), then ONE launch that fills the 19-px reflect-101 apron
 // of every level from the level's own pixels (copyMakeBorder BORDER_REFLECT_101 [| BORDER_ISOLATED]).
@@ -1183,6 +1202,7 @@ void orbb_destroy(orbb_extractor* h) {
     cudaStreamSynchronize(h->stream);
     free_bufs(h);
     if (h->hImg) cudaFree(h->hImg);
+    if (h->dColor) cudaFree(h->dColor);
     if (h->hPyr) cudaFreeHost(h->hPyr);
     if (h->hCounts) cudaFreeHost(h->hCounts);
     for (int i = 0; i <= ST_COUNT; i++) cudaEventDestroy(h->ev[i]);
@@ -1248,6 +1268,55 @@ int orbb_extract_batch(orbb_extractor* h, const uint8_t* dev_imgs, int nframes, 
     int rc = ensure_plan(h, width, height, nframes);
     if (rc) return rc;
     return run_batch(h, dev_imgs, nframes, row_stride, frame_stride, lap0, lap1);
+}
+
+static int ensure_staging(orbb_extractor* h, size_t need) {
+    if (h->hImgBytes >= need) return ORBB_OK;
+    if (h->hImg) cudaFree(h->hImg);
+    h->hImg = nullptr; h->hImgBytes = 0;
+    ORBB_CUDA(h, cudaMalloc((void**)&h->hImg, need));
+    h->hImgBytes = need;
+    return ORBB_OK;
+}
+
+int orbb_extract_batch_color(orbb_extractor* h, const uint8_t* dev_imgs, int nframes, int width, int height, size_t row_stride,
+                             size_t frame_stride, int channels, int rgb_order, int lap0, int lap1) {
+    if (!h) return ORBB_ERR_ARG;
+    if (!dev_imgs || nframes <= 0 || width <= 0 || height <= 0) return set_err(h, ORBB_ERR_EMPTY, "empty image");
+    if (channels != 3 && channels != 4) return set_err(h, ORBB_ERR_ARG, "channels must be 3 or 4 (got %d)", channels);
+    ORBB_CUDA(h, cudaSetDevice(h->device));
+    int rc = ensure_plan(h, width, height, nframes);
+    if (rc) return rc;
+    if ((rc = ensure_staging(h, (size_t)nframes * width * height))) return rc;
+    dim3 grid(((width + 3) / 4 + 31) / 32, (height + 7) / 8, nframes);
+    k_gray<<<grid, 256, 0, h->stream>>>(dev_imgs, row_stride, frame_stride, channels, rgb_order, h->hImg, width, height);
+    h->launches++;
+    return run_batch(h, h->hImg, nframes, (size_t)width, (size_t)width * height, lap0, lap1);
+}
+
+int orbb_extract_color(orbb_extractor* h, const uint8_t* img, int width, int height, size_t stride, int channels, int rgb_order,
+                       int lap0, int lap1, orbb_keypoint* kps, uint8_t* desc, int capacity, int* n_out, int* mono_index) {
+    if (!h) return ORBB_ERR_ARG;
+    if (n_out) *n_out = 0;
+    if (mono_index) *mono_index = 0;
+    if (!img || width <= 0 || height <= 0) return set_err(h, ORBB_ERR_EMPTY, "empty image");
+    if (channels != 3 && channels != 4) return set_err(h, ORBB_ERR_ARG, "channels must be 3 or 4 (got %d)", channels);
+    ORBB_CUDA(h, cudaSetDevice(h->device));
+    const size_t rowBytes = (size_t)width * channels;
+    if (h->colorBytes < rowBytes * height) {
+        if (h->dColor) cudaFree(h->dColor);
+        h->dColor = nullptr; h->colorBytes = 0;
+        ORBB_CUDA(h, cudaMalloc((void**)&h->dColor, rowBytes * height));
+        h->colorBytes = rowBytes * height;
+    }
+    ORBB_CUDA(h, cudaMemcpy2DAsync(h->dColor, rowBytes, img, stride, rowBytes, height, cudaMemcpyHostToDevice, h->stream));
+    int rc = orbb_extract_batch_color(h, h->dColor, 1, width, height, rowBytes, rowBytes * height, channels, rgb_order, lap0, lap1);
+    if (rc) return rc;
+    int32_t counts[2] = {0, 0};
+    rc = orbb_batch_fetch(h, 1, kps, desc, capacity, counts);
+    if (n_out) *n_out = counts[0];
+    if (mono_index) *mono_index = counts[1];
+    return rc;
 }
 
 int orbb_sync(orbb_extractor* h) {

@@ -286,6 +286,43 @@ __global__ void __launch_bounds__(256) k_best2_csr(const uint4* __restrict__ q, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:329-403): one warp per map point.  Lane i owns row i of the
+// N x N distance matrix (rows beyond 32 in further passes); the median sorted[(size_t)(0.5*(N-1))] of a row is found by
+// bisection on the distance value (count of entries <= v), so no matrix and no sort are needed.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_distinctive(const uint4* __restrict__ desc, const int* __restrict__ rowptr, int ngroups,
+                                                    int* __restrict__ best) {
+    const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (g >= ngroups) return;
+    const int beg = rowptr[g], N = rowptr[g + 1] - beg;
+    if (N <= 0) {
+        if (lane == 0) best[g] = -1;
+        return;
+    }
+    const uint4* d = desc + (size_t)beg * 2;
+    const int kth = (int)(0.5 * (N - 1));                     // :392
+    unsigned bestKey = 0xffffffffu;                           // median << 16 | row  (first minimum = smallest key)
+    for (int base = 0; base < N; base += 32) {
+        const int i = base + lane;
+        if (i < N) {
+            const uint4 a0 = __ldg(d + 2 * i), a1 = __ldg(d + 2 * i + 1);
+            int lo = 0, hi = 256;                             // smallest v with #{j : d_ij <= v} > kth
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                int cnt = 0;
+                for (int j = 0; j < N; j++) cnt += hamming256(a0, a1, __ldg(d + 2 * j), __ldg(d + 2 * j + 1)) <= mid;
+                if (cnt > kth) hi = mid; else lo = mid + 1;
+            }
+            bestKey = min(bestKey, ((unsigned)lo << 16) | (unsigned)i);
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) bestKey = min(bestKey, __shfl_xor_sync(0xffffffffu, bestKey, off));
+    if (lane == 0) best[g] = (int)(bestKey & 0xffffu);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Frame::ComputeStereoMatches (Frame.cc:811-981): one warp per left keypoint
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int warp_sum_i(int v) {
@@ -647,6 +684,26 @@ int orbb_best2_csr(orbb_matcher* m, const uint8_t* q, int nq, const uint8_t* tra
     m->launches++;
     ORBM_CUDA(m, cudaGetLastError());
     ORBM_CUDA(m, cudaMemcpyAsync(out4, m->scratch[3], bo, cudaMemcpyDeviceToHost, m->stream));
+    ORBM_CUDA(m, cudaStreamSynchronize(m->stream));
+    return ORBB_OK;
+}
+
+int orbb_distinctive_csr(orbb_matcher* m, const uint8_t* desc, int ntotal, const int32_t* rowptr, int ngroups, int32_t* best) {
+    if (!m || !rowptr || !best || ngroups < 0 || ntotal < 0) return m_err(m, ORBB_ERR_ARG, "bad argument");
+    if (ngroups == 0) return ORBB_OK;
+    if (rowptr[ngroups] > ntotal) return m_err(m, ORBB_ERR_ARG, "rowptr exceeds the descriptor array");
+    for (int g = 0; g < ngroups; g++)
+        if (rowptr[g + 1] - rowptr[g] > 65535) return m_err(m, ORBB_ERR_UNSUPPORTED, "group %d has more than 65535 descriptors", g);
+    ORBM_CUDA(m, cudaSetDevice(m->device));
+    const size_t bd = std::max<size_t>((size_t)ntotal * 32, 32), br = (size_t)(ngroups + 1) * 4, bo = (size_t)ngroups * 4;
+    int rc;
+    if ((rc = ensure_scratch(m, 0, bd)) || (rc = ensure_scratch(m, 2, br)) || (rc = ensure_scratch(m, 3, bo))) return rc;
+    if (ntotal > 0) ORBM_CUDA(m, cudaMemcpyAsync(m->scratch[0], desc, (size_t)ntotal * 32, cudaMemcpyHostToDevice, m->stream));
+    ORBM_CUDA(m, cudaMemcpyAsync(m->scratch[2], rowptr, br, cudaMemcpyHostToDevice, m->stream));
+    k_distinctive<<<(ngroups + 3) / 4, 128, 0, m->stream>>>((const uint4*)m->scratch[0], (const int*)m->scratch[2], ngroups, (int*)m->scratch[3]);
+    m->launches++;
+    ORBM_CUDA(m, cudaGetLastError());
+    ORBM_CUDA(m, cudaMemcpyAsync(best, m->scratch[3], bo, cudaMemcpyDeviceToHost, m->stream));
     ORBM_CUDA(m, cudaStreamSynchronize(m->stream));
     return ORBB_OK;
 }

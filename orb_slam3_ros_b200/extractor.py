@@ -88,6 +88,20 @@ class ORBextractor:
         capi.check(rc, self._h)
         return mono.value, kps[:n.value].copy(), desc[:n.value].copy()
 
+    def extract_color(self, image, rgb=True, lapping=(0, 0)):
+        """colour frame [h,w,3|4] uint8: cv::cvtColor(..2GRAY) on the device (Tracking.cc:1498-1525), then operator()"""
+        if image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] not in (3, 4):
+            raise TypeError("image must be [h, w, 3|4] uint8")
+        image = np.ascontiguousarray(image)
+        h, w, c = image.shape
+        cap = self.max_keypoints
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n, mono = C.c_int(0), C.c_int(0)
+        capi.check(self._lib.orbb_extract_color(self._h, capi.ptr(image), w, h, image.strides[0], c, int(rgb), int(lapping[0]),
+                                                int(lapping[1]), capi.ptr(kps), capi.ptr(desc), cap, C.byref(n), C.byref(mono)), self._h)
+        return mono.value, kps[:n.value].copy(), desc[:n.value].copy()
+
     def image_pyramid(self, level, with_border=False):
         """mvImagePyramid[level] of the last frame (ORBextractor.h:84), as a numpy copy."""
         p, w, h, s = C.c_void_p(), C.c_int(), C.c_int(), C.c_size_t()

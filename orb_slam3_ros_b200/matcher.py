@@ -90,6 +90,15 @@ class ORBmatcher:
                                             int(init), capi.ptr(out)), self._m, matcher=True)
         return out
 
+    # ---- MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:329-403), batched ----
+    def distinctive(self, desc, rowptr):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        rowptr = np.ascontiguousarray(rowptr, np.int32)
+        best = np.zeros(len(rowptr) - 1, np.int32)
+        capi.check(self._lib.orbb_distinctive_csr(self._m, capi.ptr(desc), len(desc), capi.ptr(rowptr), len(best), capi.ptr(best)),
+                   self._m, matcher=True)
+        return best
+
     # ---- ComputeThreeMaxima (ORBmatcher.cc:2012-2053), host ----
     @staticmethod
     def ComputeThreeMaxima(histo_sizes):

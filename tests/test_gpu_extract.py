@@ -255,3 +255,19 @@ def test_frame_partition_is_result_invariant():
         for f in range(hi - lo):
             n = c1[f, 0]
             assert np.array_equal(k0[lo + f, :n], k1[f, :n]) and np.array_equal(d0[lo + f, :n], d1[f, :n])
+
+
+def test_color_input_matches_cvtcolor_then_extract():
+    """Tracking.cc:1498-1525 ("next" row): colour frames are converted with cv::cvtColor(..2GRAY) before extraction; the
+    device conversion + extraction must equal the oracle's conversion + the gray extraction."""
+    rng = np.random.default_rng(4)
+    gray = synth.frame(240, 320, 6).astype(np.int32)
+    for channels in (3, 4):
+        for rgb in (True, False):
+            img = np.clip(np.stack([gray + rng.integers(-20, 21, gray.shape) for _ in range(channels)], -1), 0, 255).astype(np.uint8)
+            g = port.gray(img, rgb)
+            rc, k0, d0, m0 = port.PortExtractor(300, 1.2, 4).extract(g, (0, 1000))
+            ge = ORBextractor(300, 1.2, 4)
+            m1, k1, d1 = ge.extract_color(img, rgb, (0, 1000))
+            assert np.array_equal(ge.debug_level(0, 0), g), (channels, rgb)
+            assert_same_features(k0, d0, m0, k1, d1, m1, f"channels={channels} rgb={rgb}")

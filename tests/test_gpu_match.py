@@ -146,3 +146,17 @@ def test_stereo_batch_and_edge_cases():
         assert n == len(ur0)
         assert np.array_equal(ur[f, :n], ur0) and np.array_equal(dp[f, :n], dp0), f
     assert (ur[2, :counts[2, 0]] == -1).all()
+
+
+def test_distinctive_descriptors_match_oracle(matcher):
+    """MapPoint::ComputeDistinctiveDescriptors ("next" row), batched over map points"""
+    rng = np.random.default_rng(21)
+    sizes = list(rng.integers(0, 40, 300)) + [1, 2, 3, 64, 97, 200, 0]
+    rowptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    db, _ = synth.descriptor_db(len(sizes), 2, seed=8)
+    desc = np.repeat(db, sizes, axis=0)
+    flip = rng.integers(0, 256, (len(desc), 12))
+    bits = np.unpackbits(desc, axis=1)
+    np.bitwise_xor.at(bits, (np.repeat(np.arange(len(desc)), 12), flip.ravel()), 1)
+    desc = np.packbits(bits, axis=1)
+    assert np.array_equal(matcher.distinctive(desc, rowptr), port.distinctive(desc, rowptr))

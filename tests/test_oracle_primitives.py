@@ -134,3 +134,40 @@ def test_matcher_constants():
     # ORBmatcher.cc:35-37, Frame.cc:816
     from orb_slam3_ros_b200 import constants as c
     assert (c.TH_LOW, c.TH_HIGH, c.HISTO_LENGTH, (c.TH_HIGH + c.TH_LOW) // 2) == (50, 100, 30, 75)
+
+
+def test_gray_matches_cv2_cvtcolor():
+    """Tracking.cc:1498-1525 converts colour input with cv::cvtColor before building a Frame ("next" row)."""
+    rng = np.random.default_rng(12)
+    for c, rgb_code, bgr_code in ((3, cv2.COLOR_RGB2GRAY, cv2.COLOR_BGR2GRAY), (4, cv2.COLOR_RGBA2GRAY, cv2.COLOR_BGRA2GRAY)):
+        img = rng.integers(0, 256, (61, 83, c), dtype=np.uint8)
+        assert np.array_equal(port.gray(img, True), cv2.cvtColor(img, rgb_code))
+        assert np.array_equal(port.gray(img, False), cv2.cvtColor(img, bgr_code))
+    ramp = np.stack(np.meshgrid(np.arange(256), np.arange(256)), -1).astype(np.uint8)
+    ramp = np.concatenate([ramp, (ramp[..., :1] // 2 + ramp[..., 1:] // 3)], -1)
+    assert np.array_equal(port.gray(ramp, True), cv2.cvtColor(ramp, cv2.COLOR_RGB2GRAY))
+
+
+def test_distinctive_descriptor_reference_semantics():
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:329-403) restated in numpy vs the port"""
+    rng = np.random.default_rng(13)
+    sizes = [1, 2, 3, 4, 7, 20, 33, 64, 0, 5]
+    rowptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    base = rng.integers(0, 256, (len(sizes), 32), dtype=np.uint8)
+    desc = np.zeros((rowptr[-1], 32), np.uint8)
+    for g, n in enumerate(sizes):
+        for i in range(n):
+            d = base[g].copy()
+            flips = rng.integers(0, 256, rng.integers(0, 30))
+            bits = np.unpackbits(d)
+            bits[flips] ^= 1
+            desc[rowptr[g] + i] = np.packbits(bits)
+    got = port.distinctive(desc, rowptr)
+    for g, n in enumerate(sizes):
+        if n == 0:
+            assert got[g] == -1
+            continue
+        d = desc[rowptr[g]:rowptr[g + 1]]
+        dist = np.unpackbits(d[:, None, :] ^ d[None, :, :], axis=2).sum(2)
+        med = np.sort(dist, axis=1)[:, int(0.5 * (n - 1))]
+        assert got[g] == int(np.argmin(med))          # first minimum
