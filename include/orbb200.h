@@ -19,6 +19,7 @@
  *                                                                         :1743-1768 ...: same loop shape)
  *   orbb_knn2 / orbb_knn2_partial   cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, 2)   orb_slam3/src/Frame.cc:1144
  *   orbb_knn2_merge                 (top-2 merge of database shards after an all-gather; no reference counterpart)
+ *   orbb_search_area_best2          Frame::GetFeaturesInArea + SearchByProjection scan   orb_slam3/src/Frame.cc:657-723, ORBmatcher.cc:71-120 ("next" row)
  *   orbb_distinctive_csr            MapPoint::ComputeDistinctiveDescriptors   orb_slam3/src/MapPoint.cc:329-403   ("next" row)
  *   orbb_extract_color / _batch_color   cv::cvtColor(..., COLOR_*2GRAY) + extraction   orb_slam3/src/Tracking.cc:1498-1525, :1605-1618 ("next" row)
  *
@@ -183,6 +184,20 @@ int orbb_ratio_test_dev(orbb_matcher* m, const int32_t* idx2_dev, const int32_t*
  * out4[i] = {bestDist, bestIdx, secondDist, secondIdx} (idx -1 if none).  Host pointers; synchronous. */
 int orbb_best2_csr(orbb_matcher* m, const uint8_t* q, int nq, const uint8_t* train, int ntrain, const int32_t* cand,
                    const int32_t* rowptr, int init, int32_t* out4);
+
+/* Frame::GetFeaturesInArea (Frame.cc:657-723, 64x48 grid of Frame::AssignFeaturesToGrid :385-416) fused with the best /
+ * second-best scan of ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&) (ORBmatcher.cc:71-120), all projected map
+ * points of a frame in one call.  Host pointers; synchronous.
+ *   kps_xy  n x {x, y}   undistorted keypoints (Frame::mvKeysUn);  octaves n;  train n x 32 (Frame::mDescriptors)
+ *   grid4   {mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv}
+ *   queries nq x {x, y, r, projXR};  qlev nq x {minLevel, maxLevel};  qdesc nq x 32 (MapPoint::GetDescriptor)
+ *   skip    optional n bytes: 1 = keypoint already bound to an observed MapPoint (ORBmatcher.cc:88-90)
+ *   u_right optional n floats: Frame::mvuRight; when > 0 the candidate is dropped if |projXR - uRight| > r (:92-97)
+ *   out4[i] = {bestDist, bestIdx, secondDist, secondIdx}, distances start at `init`, first minimum in the reference's
+ *   candidate order (cell column, cell row, keypoint index) wins ties. */
+int orbb_search_area_best2(orbb_matcher* m, const float* kps_xy, const int32_t* octaves, const uint8_t* train, int n, const float* grid4,
+                           const float* queries, const int32_t* qlev, const uint8_t* qdesc, int nq, const uint8_t* skip,
+                           const float* u_right, int init, int32_t* out4);
 
 /* MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:329-403) for many map points at once: group g holds the
  * descriptors desc[rowptr[g] .. rowptr[g+1]) (32 bytes each, host memory); best[g] = index within the group of the

@@ -729,6 +729,64 @@ void port_best2_csr(const uint8_t* q, int nq, const uint8_t* train, const int32_
     }
 }
 
+// ---- Frame::AssignFeaturesToGrid (Frame.cc:385-416) + GetFeaturesInArea (:657-723) + the best/second scan of
+// ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&) (ORBmatcher.cc:71-120), batched over queries --------------
+// kps: n x {x, y} (undistorted), oct: n octaves, train: n x 32.  grid4 = {mnMinX, mnMinY, mfGridElementWidthInv,
+// mfGridElementHeightInv}.  queries: nq x {x, y, r, projXR}; qlev: nq x {minLevel, maxLevel}; qdesc: nq x 32.
+// skip (optional, n bytes): keypoint already holds an observed MapPoint (:88-90).  uRight (optional, n floats): stereo
+// coordinate, checked against projXR when > 0 (:92-97).  out4[i] = {bestDist, bestIdx, secondDist, secondIdx}.
+void port_search_area_best2(const float* kps, const int32_t* oct, const uint8_t* train, int n, const float* grid4, const float* queries,
+                            const int32_t* qlev, const uint8_t* qdesc, int nq, const uint8_t* skip, const float* uRight, int init,
+                            int32_t* out4) {
+    const int COLS = 64, ROWS = 48;                                                      // Frame.h:44-45
+    const float minX = grid4[0], minY = grid4[1], invW = grid4[2], invH = grid4[3];
+    std::vector<std::vector<size_t>> grid((size_t)COLS * ROWS);
+    for (int i = 0; i < n; i++) {                                                         // :403-415, PosInGrid :725-735
+        const int px = (int)std::round((kps[2 * i] - minX) * invW), py = (int)std::round((kps[2 * i + 1] - minY) * invH);
+        if (px < 0 || px >= COLS || py < 0 || py >= ROWS) continue;
+        grid[(size_t)px * ROWS + py].push_back((size_t)i);
+    }
+    for (int q = 0; q < nq; q++) {
+        const float x = queries[4 * q], y = queries[4 * q + 1], r = queries[4 * q + 2], xr = queries[4 * q + 3];
+        const int minLevel = qlev[2 * q], maxLevel = qlev[2 * q + 1];
+        std::vector<size_t> idxs;
+        do {                                                                              // :657-723
+            const float factorX = r, factorY = r;
+            const int nMinCellX = std::max(0, (int)std::floor((x - minX - factorX) * invW));
+            if (nMinCellX >= COLS) break;
+            const int nMaxCellX = std::min(COLS - 1, (int)std::ceil((x - minX + factorX) * invW));
+            if (nMaxCellX < 0) break;
+            const int nMinCellY = std::max(0, (int)std::floor((y - minY - factorY) * invH));
+            if (nMinCellY >= ROWS) break;
+            const int nMaxCellY = std::min(ROWS - 1, (int)std::ceil((y - minY + factorY) * invH));
+            if (nMaxCellY < 0) break;
+            const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+            for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+                for (int iy = nMinCellY; iy <= nMaxCellY; iy++)
+                    for (size_t j : grid[(size_t)ix * ROWS + iy]) {
+                        if (bCheckLevels) {
+                            if (oct[j] < minLevel) continue;
+                            if (maxLevel >= 0 && oct[j] > maxLevel) continue;
+                        }
+                        const float distx = kps[2 * j] - x, disty = kps[2 * j + 1] - y;
+                        if (std::fabs(distx) < factorX && std::fabs(disty) < factorY) idxs.push_back(j);
+                    }
+        } while (false);
+        int bestDist = init, bestDist2 = init, bestIdx = -1, bestIdx2 = -1;               // ORBmatcher.cc:77-120
+        for (size_t idx : idxs) {
+            if (skip && skip[idx]) continue;
+            if (uRight && uRight[idx] > 0) {
+                const float er = std::fabs(xr - uRight[idx]);
+                if (er > r) continue;
+            }
+            const int dist = descriptor_distance(qdesc + (size_t)q * 32, train + idx * 32);
+            if (dist < bestDist) { bestDist2 = bestDist; bestIdx2 = bestIdx; bestDist = dist; bestIdx = (int)idx; }
+            else if (dist < bestDist2) { bestDist2 = dist; bestIdx2 = (int)idx; }
+        }
+        out4[4 * q] = bestDist; out4[4 * q + 1] = bestIdx; out4[4 * q + 2] = bestDist2; out4[4 * q + 3] = bestIdx2;
+    }
+}
+
 // ---- MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:329-403), batched over groups ------------------------
 // group g = descriptors desc[rowptr[g] .. rowptr[g+1]); best[g] = index (within the group) of the descriptor with the
 // least median distance to the others (first minimum; median = sorted[(size_t)(0.5*(N-1))], self distance 0 included);

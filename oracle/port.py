@@ -72,6 +72,8 @@ def _sig(lib):
     lib.port_hamming.argtypes = [C.c_void_p, C.c_void_p]
     lib.port_knn2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int]
     lib.port_best2_csr.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.port_search_area_best2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.port_distinctive.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.port_gray.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     lib.port_stereo.restype = C.c_int
@@ -263,6 +265,24 @@ def best2_csr(q, train, cand, rowptr, init=256):
     rowptr = np.ascontiguousarray(rowptr, np.int32)
     out = np.zeros((len(q), 4), np.int32)
     lib().port_best2_csr(_ptr(q), len(q), _ptr(train), _ptr(cand), _ptr(rowptr), init, _ptr(out))
+    return out
+
+
+def search_area_best2(kps_xy, octaves, train, grid4, queries, qlev, qdesc, skip=None, u_right=None, init=256):
+    """grid lookup (Frame::GetFeaturesInArea) + best/second scan (ORBmatcher::SearchByProjection) per query"""
+    kps_xy = np.ascontiguousarray(kps_xy, np.float32).reshape(-1, 2)
+    octaves = np.ascontiguousarray(octaves, np.int32)
+    train = _u8c(train)
+    grid4 = np.ascontiguousarray(grid4, np.float32)
+    queries = np.ascontiguousarray(queries, np.float32).reshape(-1, 4)
+    qlev = np.ascontiguousarray(qlev, np.int32).reshape(-1, 2)
+    qdesc = _u8c(qdesc)
+    out = np.zeros((len(queries), 4), np.int32)
+    sk = None if skip is None else np.ascontiguousarray(skip, np.uint8)
+    ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+    lib().port_search_area_best2(_ptr(kps_xy), _ptr(octaves), _ptr(train), len(kps_xy), _ptr(grid4), _ptr(queries), _ptr(qlev),
+                                 _ptr(qdesc), len(queries), None if sk is None else _ptr(sk), None if ur is None else _ptr(ur),
+                                 init, _ptr(out))
     return out
 
 

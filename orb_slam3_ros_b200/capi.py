@@ -74,6 +74,7 @@ SYMBOLS = [
     ("orbb_knn2_merge_dev", _I, [_VP, _VP, _VP, _I, _I, _VP, _VP]),
     ("orbb_ratio_test_dev", _I, [_VP, _VP, _VP, _I, _D, _VP]),
     ("orbb_best2_csr", _I, [_VP, _VP, _I, _VP, _I, _VP, _VP, _I, _VP]),
+    ("orbb_search_area_best2", _I, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _VP]),
     ("orbb_distinctive_csr", _I, [_VP, _VP, _I, _VP, _I, _VP]),
     ("orbb_host_alloc", _VP, [_SZ]),
     ("orbb_host_free", None, [_VP]),

@@ -286,6 +286,72 @@ __global__ void __launch_bounds__(256) k_best2_csr(const uint4* __restrict__ q, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Frame::GetFeaturesInArea (Frame.cc:657-723) fused with the best / second-best scan of ORBmatcher::SearchByProjection
+// (ORBmatcher.cc:71-120): one warp per query.  No grid is materialised: a keypoint's grid cell (PosInGrid, :725-735) is a
+// pure function of its coordinates, so every lane tests keypoints directly against the query's cell window, level range
+// and radius.  The reference visits candidates cell by cell (ix, then iy, then keypoint index) and keeps the FIRST minimum;
+// the same tie rule falls out of an unsigned min over  dist << 32 | ix << 26 | iy << 20 | index.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_search_area_best2(const float2* __restrict__ kps, const int* __restrict__ oct,
+                                                          const uint4* __restrict__ train, int n, float minX, float minY, float invW,
+                                                          float invH, const float4* __restrict__ queries, const int2* __restrict__ qlev,
+                                                          const uint4* __restrict__ qdesc, int nq, const uint8_t* __restrict__ skip,
+                                                          const float* __restrict__ uRight, int init, int* __restrict__ out4) {
+    const int qi = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (qi >= nq) return;
+    const float4 q = __ldg(queries + qi);                      // x, y, r, projXR
+    const int2 lev = __ldg(qlev + qi);
+    const float x = q.x, y = q.y, r = q.z;
+    unsigned long long k1 = ~0ull, k2 = ~0ull;
+    const int nMinCellX = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, minX), r), invW)));
+    const int nMaxCellX = min(63, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, minX), r), invW)));
+    const int nMinCellY = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, minY), r), invH)));
+    const int nMaxCellY = min(47, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, minY), r), invH)));
+    if (nMinCellX < 64 && nMaxCellX >= 0 && nMinCellY < 48 && nMaxCellY >= 0) {
+        const bool bCheckLevels = lev.x > 0 || lev.y >= 0;
+        const uint4 a0 = __ldg(qdesc + (size_t)qi * 2), a1 = __ldg(qdesc + (size_t)qi * 2 + 1);
+        for (int j = lane; j < n; j += 32) {
+            const float2 kp = __ldg(kps + j);
+            const int px = (int)roundf(__fmul_rn(__fsub_rn(kp.x, minX), invW)), py = (int)roundf(__fmul_rn(__fsub_rn(kp.y, minY), invH));
+            if (px < nMinCellX || px > nMaxCellX || py < nMinCellY || py > nMaxCellY) continue;   // also drops cells outside the grid
+            if (bCheckLevels) {
+                const int o = __ldg(oct + j);
+                if (o < lev.x || (lev.y >= 0 && o > lev.y)) continue;
+            }
+            if (!(fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r)) continue;
+            if (skip && skip[j]) continue;
+            if (uRight) {
+                const float ur = __ldg(uRight + j);
+                if (ur > 0 && fabsf(__fsub_rn(q.w, ur)) > r) continue;
+            }
+            const int d = hamming256(a0, a1, __ldg(train + (size_t)j * 2), __ldg(train + (size_t)j * 2 + 1));
+            if (d < init) {
+                const unsigned long long k = ((unsigned long long)(unsigned)d << 32) | ((unsigned long long)px << 26) |
+                                             ((unsigned long long)py << 20) | (unsigned)j;
+                const unsigned long long hi = max(k1, k);
+                k1 = min(k1, k);
+                k2 = min(k2, hi);
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, k1, off), o2 = __shfl_xor_sync(0xffffffffu, k2, off);
+        const unsigned long long lo = min(k1, o1), hi = max(k1, o1);
+        k2 = min(min(k2, o2), hi);
+        k1 = lo;
+    }
+    if (lane == 0) {
+        int* o = out4 + (size_t)qi * 4;
+        o[0] = k1 == ~0ull ? init : (int)(k1 >> 32);
+        o[1] = k1 == ~0ull ? -1 : (int)(k1 & 0xfffffu);
+        o[2] = k2 == ~0ull ? init : (int)(k2 >> 32);
+        o[3] = k2 == ~0ull ? -1 : (int)(k2 & 0xfffffu);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:329-403): one warp per map point.  Lane i owns row i of the
 // N x N distance matrix (rows beyond 32 in further passes); the median sorted[(size_t)(0.5*(N-1))] of a row is found by
 // bisection on the distance value (count of entries <= v), so no matrix and no sort are needed.
@@ -684,6 +750,36 @@ int orbb_best2_csr(orbb_matcher* m, const uint8_t* q, int nq, const uint8_t* tra
     m->launches++;
     ORBM_CUDA(m, cudaGetLastError());
     ORBM_CUDA(m, cudaMemcpyAsync(out4, m->scratch[3], bo, cudaMemcpyDeviceToHost, m->stream));
+    ORBM_CUDA(m, cudaStreamSynchronize(m->stream));
+    return ORBB_OK;
+}
+
+int orbb_search_area_best2(orbb_matcher* m, const float* kps_xy, const int32_t* octaves, const uint8_t* train, int n, const float* grid4,
+                           const float* queries, const int32_t* qlev, const uint8_t* qdesc, int nq, const uint8_t* skip, const float* u_right,
+                           int init, int32_t* out4) {
+    if (!m || !grid4 || !out4 || n < 0 || nq < 0) return m_err(m, ORBB_ERR_ARG, "bad argument");
+    if (nq == 0) return ORBB_OK;
+    if (n >= (1 << 20)) return m_err(m, ORBB_ERR_UNSUPPORTED, "more than 2^20 keypoints per frame");
+    ORBM_CUDA(m, cudaSetDevice(m->device));
+    // one staging buffer: [kps n*8][oct n*4][train n*32][queries nq*16][qlev nq*8][qdesc nq*32][skip n][uRight n*4][out nq*16], 256-B aligned parts
+    size_t off[10], cur = 0;
+    const size_t sz[9] = {(size_t)n * 8, (size_t)n * 4, (size_t)n * 32, (size_t)nq * 16, (size_t)nq * 8, (size_t)nq * 32,
+                          skip ? (size_t)n : 0, u_right ? (size_t)n * 4 : 0, (size_t)nq * 16};
+    for (int i = 0; i < 9; i++) { off[i] = cur; cur += (sz[i] + 255) / 256 * 256; }
+    int rc;
+    if ((rc = ensure_scratch(m, 0, cur + 256))) return rc;
+    char* base = (char*)m->scratch[0];
+    const void* src[8] = {kps_xy, octaves, train, queries, qlev, qdesc, skip, u_right};
+    for (int i = 0; i < 8; i++)
+        if (sz[i]) ORBM_CUDA(m, cudaMemcpyAsync(base + off[i], src[i], sz[i], cudaMemcpyHostToDevice, m->stream));
+    k_search_area_best2<<<(nq + 7) / 8, 256, 0, m->stream>>>((const float2*)(base + off[0]), (const int*)(base + off[1]), (const uint4*)(base + off[2]), n,
+                                                            grid4[0], grid4[1], grid4[2], grid4[3], (const float4*)(base + off[3]),
+                                                            (const int2*)(base + off[4]), (const uint4*)(base + off[5]), nq,
+                                                            skip ? (const uint8_t*)(base + off[6]) : nullptr,
+                                                            u_right ? (const float*)(base + off[7]) : nullptr, init, (int*)(base + off[8]));
+    m->launches++;
+    ORBM_CUDA(m, cudaGetLastError());
+    ORBM_CUDA(m, cudaMemcpyAsync(out4, base + off[8], sz[8], cudaMemcpyDeviceToHost, m->stream));
     ORBM_CUDA(m, cudaStreamSynchronize(m->stream));
     return ORBB_OK;
 }

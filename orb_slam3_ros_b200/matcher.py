@@ -90,6 +90,23 @@ class ORBmatcher:
                                             int(init), capi.ptr(out)), self._m, matcher=True)
         return out
 
+    # ---- Frame::GetFeaturesInArea + SearchByProjection scan (Frame.cc:657-723, ORBmatcher.cc:71-120), batched ----
+    def search_area_best2(self, kps_xy, octaves, train, grid4, queries, qlev, qdesc, skip=None, u_right=None, init=256):
+        kps_xy = np.ascontiguousarray(kps_xy, np.float32).reshape(-1, 2)
+        octaves = np.ascontiguousarray(octaves, np.int32)
+        train = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+        grid4 = np.ascontiguousarray(grid4, np.float32)
+        queries = np.ascontiguousarray(queries, np.float32).reshape(-1, 4)
+        qlev = np.ascontiguousarray(qlev, np.int32).reshape(-1, 2)
+        qdesc = np.ascontiguousarray(qdesc, np.uint8).reshape(-1, 32)
+        sk = None if skip is None else np.ascontiguousarray(skip, np.uint8)
+        ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+        out = np.zeros((len(queries), 4), np.int32)
+        capi.check(self._lib.orbb_search_area_best2(self._m, capi.ptr(kps_xy), capi.ptr(octaves), capi.ptr(train), len(kps_xy),
+                                                    capi.ptr(grid4), capi.ptr(queries), capi.ptr(qlev), capi.ptr(qdesc), len(queries),
+                                                    capi.ptr(sk), capi.ptr(ur), int(init), capi.ptr(out)), self._m, matcher=True)
+        return out
+
     # ---- MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:329-403), batched ----
     def distinctive(self, desc, rowptr):
         desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
