@@ -19,6 +19,8 @@
  *                                                                         :1743-1768 ...: same loop shape)
  *   orbb_knn2 / orbb_knn2_partial   cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, 2)   orb_slam3/src/Frame.cc:1144
  *   orbb_knn2_merge                 (top-2 merge of database shards after an all-gather; no reference counterpart)
+ *   orbb_vocab_create / orbb_bow_transform   DBoW2 TemplatedVocabulary::transform via Frame::ComputeBoW   orb_slam3/src/Frame.cc:738-745,
+ *                                   orb_slam3/Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1139-1275 ("next" row)
  *   orbb_search_area_best2          Frame::GetFeaturesInArea + SearchByProjection scan   orb_slam3/src/Frame.cc:657-723, ORBmatcher.cc:71-120 ("next" row)
  *   orbb_distinctive_csr            MapPoint::ComputeDistinctiveDescriptors   orb_slam3/src/MapPoint.cc:329-403   ("next" row)
  *   orbb_extract_color / _batch_color   cv::cvtColor(..., COLOR_*2GRAY) + extraction   orb_slam3/src/Tracking.cc:1498-1525, :1605-1618 ("next" row)
@@ -203,6 +205,27 @@ int orbb_search_area_best2(orbb_matcher* m, const float* kps_xy, const int32_t* 
  * descriptors desc[rowptr[g] .. rowptr[g+1]) (32 bytes each, host memory); best[g] = index within the group of the
  * descriptor with the least median Hamming distance to the others (first minimum), -1 for an empty group. */
 int orbb_distinctive_csr(orbb_matcher* m, const uint8_t* desc, int ntotal, const int32_t* rowptr, int ngroups, int32_t* best);
+
+/* ---- bag of words ("next" row) ------------------------------------------------------------------------------------ */
+/* Vocabulary tree as flat arrays (what an adapter reads out of DBoW2's m_nodes): node 0 is the root; the children of node
+ * i are child_list[child_begin[i] .. child_begin[i] + child_count[i]) in DBoW2's visiting order; a node without children
+ * is a leaf (= word) with word id node_word_id[i] and tf-idf weight node_weight[i]; depth = m_L. */
+typedef struct orbb_vocab orbb_vocab;
+int orbb_vocab_create(int device, int nnodes, const int32_t* child_begin, const int32_t* child_count, const int32_t* child_list,
+                      int nchildren, const uint8_t* node_desc, const double* node_weight, const int32_t* node_word_id, int depth,
+                      orbb_vocab** out);
+void orbb_vocab_destroy(orbb_vocab* v);
+const char* orbb_vocab_last_error(const orbb_vocab* v);
+long long orbb_vocab_launch_count(const orbb_vocab* v);
+/* TemplatedVocabulary::transform(features, BowVector, FeatureVector, levelsup) for nsets descriptor sets at once (set s =
+ * descriptors rowptr[s] .. rowptr[s+1], 32 bytes each, host memory).  norm: 1 = L1 (ORB-SLAM3's vocabulary), 2 = L2,
+ * 0 = none.  Outputs are laid out per set at offset rowptr[s] (capacity = the set's feature count):
+ *   bow_id / bow_val   the BowVector in ascending word order, counts[3s] entries
+ *   fv_node / fv_start the FeatureVector in ascending node order, counts[3s+1] entries; node k owns
+ *                      fv_feat[rowptr[s] + fv_start[k] .. next start or counts[3s+2]) (feature indices within the set, ascending)
+ *   counts[3s+2]       features with a positive word weight ("not stopped") */
+int orbb_bow_transform(orbb_vocab* v, const uint8_t* desc, const int32_t* rowptr, int nsets, int levelsup, int norm, int32_t* bow_id,
+                       double* bow_val, int32_t* fv_node, int32_t* fv_start, int32_t* fv_feat, int32_t* counts);
 
 /* pinned host memory helpers (so callers without a CUDA runtime can stage asynchronously) */
 void* orbb_host_alloc(size_t bytes);

@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <list>
+#include <map>
 #include <thread>
 #include <utility>
 #include <vector>
@@ -785,6 +786,62 @@ void port_search_area_best2(const float* kps, const int32_t* oct, const uint8_t*
         }
         out4[4 * q] = bestDist; out4[4 * q + 1] = bestIdx; out4[4 * q + 2] = bestDist2; out4[4 * q + 3] = bestIdx2;
     }
+}
+
+// ---- DBoW2 TemplatedVocabulary<FORB>::transform(features, BowVector, FeatureVector, levelsup)
+// (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1139-1213, :1230-1275; BowVector.cpp:30-80; FeatureVector.cpp:31-45), the call
+// behind Frame::ComputeBoW (Frame.cc:738-745).  TF / TF_IDF weighting (addWeight).  Tree as flat arrays, see orbb200.h.
+// Outputs packed per call: bow ids/values ascending; fv nodes ascending with their feature lists concatenated.
+int port_bow_transform(int nnodes, const int32_t* childBegin, const int32_t* childCount, const int32_t* childList, const uint8_t* nodeDesc,
+                       const double* nodeWeight, const int32_t* nodeWord, int depth, const uint8_t* desc, int n, int levelsup, int norm,
+                       int32_t* bowId, double* bowVal, int32_t* fvNode, int32_t* fvStart, int32_t* fvFeat, int32_t* counts) {
+    (void)nnodes;
+    std::map<int, double> bow;                      // BowVector: std::map<WordId, WordValue>
+    std::map<int, std::vector<unsigned>> fv;        // FeatureVector
+    const int nidLevel = depth - levelsup;
+    for (int f = 0; f < n; f++) {
+        int nid = 0, finalId = 0, level = 0;         // :1240-1243
+        do {                                          // :1245-1268
+            ++level;
+            const int beg = childBegin[finalId], cnt = childCount[finalId];
+            int cur = childList[beg];
+            double bestD = (double)descriptor_distance(desc + (size_t)f * 32, nodeDesc + (size_t)cur * 32);
+            for (int c = 1; c < cnt; c++) {
+                const int id = childList[beg + c];
+                const double d = (double)descriptor_distance(desc + (size_t)f * 32, nodeDesc + (size_t)id * 32);
+                if (d < bestD) { bestD = d; cur = id; }
+            }
+            finalId = cur;
+            if (level == nidLevel) nid = finalId;
+        } while (childCount[finalId] > 0);
+        const double w = nodeWeight[finalId];
+        if (w > 0) {                                  // :1169-1173
+            auto it = bow.lower_bound(nodeWord[finalId]);
+            if (it != bow.end() && !(nodeWord[finalId] < it->first)) it->second += w;
+            else bow.insert(it, std::make_pair(nodeWord[finalId], w));
+            fv[nid].push_back((unsigned)f);
+        }
+    }
+    if (!norm && !bow.empty()) {                      // :1176-1182 (scoring without normalisation)
+        const double nd = (double)bow.size();
+        for (auto& kv : bow) kv.second /= nd;
+    }
+    if (norm) {                                       // BowVector::normalize
+        double nrm = 0.0;
+        if (norm == 1) for (auto& kv : bow) nrm += std::fabs(kv.second);
+        else { for (auto& kv : bow) nrm += kv.second * kv.second; nrm = std::sqrt(nrm); }
+        if (nrm > 0.0) for (auto& kv : bow) kv.second /= nrm;
+    }
+    int k = 0;
+    for (auto& kv : bow) { bowId[k] = kv.first; bowVal[k] = kv.second; k++; }
+    counts[0] = k;
+    int m = 0, pos = 0;
+    for (auto& kv : fv) {
+        fvNode[m] = kv.first; fvStart[m] = pos; m++;
+        for (unsigned f : kv.second) fvFeat[pos++] = (int)f;
+    }
+    counts[1] = m; counts[2] = pos;
+    return 0;
 }
 
 // ---- MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:329-403), batched over groups ------------------------

@@ -72,6 +72,7 @@ def _sig(lib):
     lib.port_hamming.argtypes = [C.c_void_p, C.c_void_p]
     lib.port_knn2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int]
     lib.port_best2_csr.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.port_bow_transform.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6
     lib.port_search_area_best2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.port_distinctive.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -266,6 +267,21 @@ def best2_csr(q, train, cand, rowptr, init=256):
     out = np.zeros((len(q), 4), np.int32)
     lib().port_best2_csr(_ptr(q), len(q), _ptr(train), _ptr(cand), _ptr(rowptr), init, _ptr(out))
     return out
+
+
+def bow_transform(vocab, desc, levelsup=4, norm=1):
+    """DBoW2 transform of one descriptor set.  vocab = dict(child_begin, child_count, child_list, node_desc, node_weight,
+    node_word, depth).  -> (bow_id, bow_val, fv_node, fv_start, fv_feat, n_valid)"""
+    desc = _u8c(desc).reshape(-1, 32)
+    n = len(desc)
+    v = {k: np.ascontiguousarray(a) for k, a in vocab.items() if k != "depth"}
+    bow_id, bow_val = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.float64)
+    fv_node, fv_start, fv_feat = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32)
+    counts = np.zeros(3, np.int32)
+    lib().port_bow_transform(len(v["child_begin"]), _ptr(v["child_begin"]), _ptr(v["child_count"]), _ptr(v["child_list"]),
+                             _ptr(v["node_desc"]), _ptr(v["node_weight"]), _ptr(v["node_word"]), int(vocab["depth"]), _ptr(desc), n,
+                             levelsup, norm, _ptr(bow_id), _ptr(bow_val), _ptr(fv_node), _ptr(fv_start), _ptr(fv_feat), _ptr(counts))
+    return bow_id[:counts[0]], bow_val[:counts[0]], fv_node[:counts[1]], fv_start[:counts[1]], fv_feat[:counts[2]], int(counts[2])
 
 
 def search_area_best2(kps_xy, octaves, train, grid4, queries, qlev, qdesc, skip=None, u_right=None, init=256):

@@ -12,7 +12,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "liborbb200.so"
-SOURCES = ["orbb_extract.cu", "orbb_match.cu"]
+SOURCES = ["orbb_extract.cu", "orbb_match.cu", "orbb_bow.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2", "--shared", "-cudart", "shared",

@@ -76,6 +76,11 @@ SYMBOLS = [
     ("orbb_best2_csr", _I, [_VP, _VP, _I, _VP, _I, _VP, _VP, _I, _VP]),
     ("orbb_search_area_best2", _I, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _VP]),
     ("orbb_distinctive_csr", _I, [_VP, _VP, _I, _VP, _I, _VP]),
+    ("orbb_vocab_create", _I, [_I, _I, _VP, _VP, _VP, _I, _VP, _VP, _VP, _I, C.POINTER(_VP)]),
+    ("orbb_vocab_destroy", None, [_VP]),
+    ("orbb_vocab_last_error", C.c_char_p, [_VP]),
+    ("orbb_vocab_launch_count", _LL, [_VP]),
+    ("orbb_bow_transform", _I, [_VP, _VP, _VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     ("orbb_host_alloc", _VP, [_SZ]),
     ("orbb_host_free", None, [_VP]),
 ]

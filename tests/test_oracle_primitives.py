@@ -171,3 +171,38 @@ def test_distinctive_descriptor_reference_semantics():
         dist = np.unpackbits(d[:, None, :] ^ d[None, :, :], axis=2).sum(2)
         med = np.sort(dist, axis=1)[:, int(0.5 * (n - 1))]
         assert got[g] == int(np.argmin(med))          # first minimum
+
+
+def test_bow_oracle_against_plain_python():
+    """oracle/port.bow_transform (std::map restatement of DBoW2 transform) against a dict-based Python walk"""
+    from orb_slam3_ros_b200.bow import synthetic_vocabulary
+    vocab = synthetic_vocabulary(5, 3, seed=9, ragged=True)
+    rng = np.random.default_rng(4)
+    desc = rng.integers(0, 256, (300, 32), dtype=np.uint8)
+    desc[::3] = vocab["node_desc"][rng.integers(1, len(vocab["child_begin"]), 100)]
+    levelsup = 1
+    bow, fv = {}, {}
+    for f, d in enumerate(desc):
+        node, level, nid = 0, 0, 0
+        while vocab["child_count"][node] > 0:
+            level += 1
+            b, c = vocab["child_begin"][node], vocab["child_count"][node]
+            ids = vocab["child_list"][b:b + c]
+            dist = np.unpackbits(vocab["node_desc"][ids] ^ d, axis=1).sum(1)
+            node = int(ids[int(np.argmin(dist))])           # argmin = first minimum
+            if level == vocab["depth"] - levelsup:
+                nid = node
+        w = float(vocab["node_weight"][node])
+        if w > 0:
+            bow[int(vocab["node_word"][node])] = bow.get(int(vocab["node_word"][node]), 0.0) + w
+            fv.setdefault(nid, []).append(f)
+    ids = sorted(bow)
+    nrm = 0.0
+    for i in ids:
+        nrm += abs(bow[i])
+    got = port.bow_transform(vocab, desc, levelsup, 1)
+    assert got[0].tolist() == ids
+    assert got[1].tolist() == [bow[i] / nrm for i in ids]
+    assert got[2].tolist() == sorted(fv)
+    assert got[4].tolist() == [f for n in sorted(fv) for f in fv[n]]
+    assert got[5] == sum(len(v) for v in fv.values())
