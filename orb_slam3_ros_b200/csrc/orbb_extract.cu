@@ -163,6 +163,8 @@ __global__ void __launch_bounds__(256) k_pyr_apron(const Plan* __restrict__ P, B
     if (lane < kEdge + 3 && x < L.w + kEdge && (sy != iy || x >= L.w)) drow[x] = srow[x >= L.w ? 2 * L.w - 2 - x : x];
 }
 
+#include "orbb_pyr.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // K5a: GaussianBlur 7x7 sigma 2, OpenCV's 8.8 fixed-point path: taps {18,34,48,56,48,34,18}/256, horizontal pass
 // in 16 bit, vertical pass 32 bit, one rounding (acc + 2^15) >> 16; BORDER_REFLECT_101 at the IMAGE edge
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(BLUR_THREADS) k_blur(const Plan* __restrict__ 
     int level = 0;
     while (level + 1 < P->nlevels && (int)blockIdx.x >= P->lv[level + 1].blurTileBase) level++;
     const LevelPlan& L = P->lv[level];
-    if (B.selCount[frame * ORBB_MAX_LEVELS + level] == 0) return;     // :1128 levels without keypoints are skipped
+    // (the reference skips levels without keypoints, :1128; here the blur runs beside the detector, before that is known)
     const int nwords = L.blurTilesX, nstrips = L.blurTilesY;
     const int item = (blockIdx.x - L.blurTileBase) * BLUR_THREADS + threadIdx.x;
     if (item >= nwords * nstrips) return;
@@ -1004,6 +1006,9 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
                 tab.push_back(make_int2(sx, (int)((unsigned short)a0 | ((unsigned)(unsigned short)a1 << 16))));
             }
             while ((tab.size() - (size_t)L.tabX) % 4) tab.push_back(tab.back());     // k_pyr_resize reads 4 entries per thread
+            L.fastResize = 1;
+            for (size_t g = (size_t)L.tabX; g < tab.size(); g += 4)
+                if (tab[g + 3].x - 4 * (tab[g].x >> 2) > 7 || tab[g + 3].x < tab[g].x) L.fastResize = 0;      // taps must lie in bytes 0..8
             L.tabY = (int)tab.size();
             for (int dy = 0; dy < L.h; dy++) {
                 float fy = (float)((dy + 0.5) * scale_y - 0.5);
@@ -1015,6 +1020,19 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
             while (tab.size() % 4) tab.push_back(tab.back());
 
         }
+    }
+    {
+        int items = 0;
+        for (int l = 0; l < nl; l++) {
+            const LevelPlan& L = P.lv[l];
+            ApronLevel& A = P.apron[l];
+            A.itemBase = items;
+            A.rowChunks = (kRoiX + L.w + kEdge + 15) / 16;
+            A.rightChunk0 = (kRoiX + L.w) / 16;
+            A.sideChunks = 2 + (kRoiX + L.w + kEdge - 1) / 16 - A.rightChunk0 + 1;
+            items += 2 * kEdge * A.rowChunks + L.h * A.sideChunks;
+        }
+        P.apronItems = items;
     }
     P.cellsTotal = cells; P.blurTilesTotal = tiles; P.kpCap = kpCap; P.fsTotal = fsTiles;
     P.pyrStride = pyrBytes; P.blurStride = blurBytes;
@@ -1099,18 +1117,29 @@ static int run_batch(orbb_extractor* h, const uint8_t* dImgs, int nframes, size_
     mark(h, ST_PYRAMID);
     ORBB_CUDA(h, cudaMemsetAsync(B.status, 0, sizeof(int) * nframes, st));
     ORBB_CUDA(h, cudaMemsetAsync(B.fbCount, 0, sizeof(int) * nframes, st));
-    int borderedRows = 0, maxPitch = 0;
+    static const bool legacyPyr = getenv("ORBB_PYR_LEGACY") != nullptr;      // debugging: the first (generic) formulation
+    int borderedRows = 0;
     for (int l = 0; l < P.nlevels; l++) {
         const LevelPlan& L = P.lv[l];
         dim3 grid(((L.w + 3) / 4 + 31) / 32, (L.h + 7) / 8, nframes);
-        if (l == 0) k_pyr_level0<<<grid, 256, 0, st>>>(h->dPlan, B, dImgs, rowStride, frameStride);
-        else k_pyr_resize<<<grid, 256, 0, st>>>(h->dPlan, B, l);
+        if (l == 0) {
+            if (legacyPyr) k_pyr_level0<<<grid, 256, 0, st>>>(h->dPlan, B, dImgs, rowStride, frameStride);
+            else {
+                const int aligned16 = ((uintptr_t)dImgs % 16 == 0) && rowStride % 16 == 0 && frameStride % 16 == 0;
+                k_pyr_level0_v<<<dim3(((L.w + 15) / 16 + 31) / 32, (L.h + 7) / 8, nframes), 256, 0, st>>>(h->dPlan, B, dImgs, rowStride,
+                                                                                                      frameStride, aligned16);
+            }
+        } else if (L.fastResize && !legacyPyr) {
+            constexpr int rowsPerCta = PR_ROWS * (PR_THREADS / 32);
+            k_pyr_resize_s<<<dim3(grid.x, (L.h + rowsPerCta - 1) / rowsPerCta, nframes), PR_THREADS, 0, st>>>(h->dPlan, B, l);
+        } else k_pyr_resize<<<grid, 256, 0, st>>>(h->dPlan, B, l);
         h->launches++;
         borderedRows += L.h + 2 * kEdge;
-        maxPitch = std::max(maxPitch, L.pitch);
     }
-    k_pyr_apron<<<dim3((borderedRows + 7) / 8, nframes), 256, 0, st>>>(h->dPlan, B, borderedRows);
+    if (legacyPyr) k_pyr_apron<<<dim3((borderedRows + 7) / 8, nframes), 256, 0, st>>>(h->dPlan, B, borderedRows);
+    else k_pyr_apron16<<<dim3((P.apronItems + 255) / 256, nframes), 256, 0, st>>>(h->dPlan, B, P.apronItems);
     h->launches++;
+    const bool fork = !h->profiling;
     mark(h, ST_FAST);
     static const char* fastMode = getenv("ORBB_FAST_MODE");      // debugging: "v0" / "cell" select the older formulations
     if (fastMode && !strcmp(fastMode, "v0")) {
@@ -1131,9 +1160,18 @@ static int run_batch(orbb_extractor* h, const uint8_t* dImgs, int nframes, size_
         h->launches += 2;
     }
     mark(h, ST_OCTREE);
+    // fork: the blur only needs the pyramid; on its own stream it fills the SMs that the latency-bound quadtree leaves idle.
+    // With stage profiling on, everything stays on one stream so that the stage events mean what they say.
+    if (fork) ORBB_CUDA(h, cudaEventRecord(h->evFork, st));
     k_octree<<<dim3(P.nlevels, nframes), OT_THREADS, 0, st>>>(h->dPlan, B);
+    if (fork) {
+        ORBB_CUDA(h, cudaStreamWaitEvent(h->blurStream, h->evFork, 0));
+        k_blur<<<dim3(P.blurTilesTotal, nframes), BLUR_THREADS, 0, h->blurStream>>>(h->dPlan, B);
+        ORBB_CUDA(h, cudaEventRecord(h->evJoin, h->blurStream));
+    }
     mark(h, ST_BLUR);
-    k_blur<<<dim3(P.blurTilesTotal, nframes), BLUR_THREADS, 0, st>>>(h->dPlan, B);
+    if (fork) ORBB_CUDA(h, cudaStreamWaitEvent(st, h->evJoin, 0));
+    else k_blur<<<dim3(P.blurTilesTotal, nframes), BLUR_THREADS, 0, st>>>(h->dPlan, B);
     mark(h, ST_ASSEMBLE);
     k_assemble<<<nframes, 256, 0, st>>>(h->dPlan, B, lap0, lap1);
     mark(h, ST_ORIENT_DESC);
@@ -1182,6 +1220,9 @@ int orbb_create(const orbb_params* prm, orbb_extractor** out) {
     for (int i = 0; i <= ST_COUNT; i++) cudaEventCreate(&h->ev[i]);
     cudaStreamCreateWithFlags(&h->h2dStream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&h->d2hStream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&h->blurStream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming);
     for (int i = 0; i < 8; i++) {
         cudaEventCreateWithFlags(&h->evH2D[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&h->evDone[i], cudaEventDisableTiming);
@@ -1209,6 +1250,9 @@ void orbb_destroy(orbb_extractor* h) {
     for (int i = 0; i < 8; i++) { if (h->evH2D[i]) cudaEventDestroy(h->evH2D[i]); if (h->evDone[i]) cudaEventDestroy(h->evDone[i]); }
     if (h->h2dStream) cudaStreamDestroy(h->h2dStream);
     if (h->d2hStream) cudaStreamDestroy(h->d2hStream);
+    if (h->blurStream) cudaStreamDestroy(h->blurStream);
+    if (h->evFork) cudaEventDestroy(h->evFork);
+    if (h->evJoin) cudaEventDestroy(h->evJoin);
     cudaStreamDestroy(h->stream);
     delete h;
 }

@@ -39,7 +39,11 @@ struct LevelPlan {
     float scale, kpSize;
     int blurTileBase, blurTilesX, blurTilesY;
     int fsBase, fsTilesX, fsGroups;    // k_fast_score tiling: 32 word-columns x (4 strips of 8 rows) per CTA
+    int fastResize;                    // 1: the 4 source taps of every column group fit 3 aligned words (k_pyr_resize_s)
 };
+
+// k_pyr_apron16 work decomposition of one level (16-byte chunks that contain apron bytes)
+struct ApronLevel { int itemBase, sideChunks, rightChunk0, rowChunks; };
 
 struct Plan {
     int nlevels, W, H;
@@ -50,6 +54,8 @@ struct Plan {
     unsigned cellKeyStride, rawStride, nodeStride, selStride;   // entries per frame
     int umax[16];
     LevelPlan lv[ORBB_MAX_LEVELS];
+    ApronLevel apron[ORBB_MAX_LEVELS];
+    int apronItems;
 };
 
 struct QNode {                     // quadtree node: UL=(x0,y0) BR=(x1,y1); keys = segment of a ping-pong buffer
@@ -140,6 +146,8 @@ struct orbb_extractor {
     cudaStream_t stream = nullptr;
     cudaStream_t h2dStream = nullptr, d2hStream = nullptr;   // copy engines for the pipelined host path
     cudaEvent_t evH2D[8]{}, evDone[8]{};
+    cudaStream_t blurStream = nullptr;                       // k_blur runs beside FAST + quadtree (both only read the pyramid)
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
     // plan for the current image size
     orbb::Plan plan;
     orbb::Plan* dPlan = nullptr;

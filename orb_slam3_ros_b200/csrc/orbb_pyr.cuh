@@ -1,0 +1,155 @@
+// K1, production pyramid kernels (ComputePyramid, reference ORBextractor.cc:1170-1195).  (included INSIDE namespace orbb)
+//
+//   k_pyr_level0     copy of the source into its bordered slab, 16 bytes per thread.
+//   k_pyr_resize_s   cv::resize INTER_LINEAR for scale steps up to ~1.3 (the reference's 1.2): a thread owns FOUR destination columns and walks
+//                    down PR_ROWS destination rows.  cv::resize's horizontal pass (HResizeLinear) of a source row is
+//                    computed once and reused by the next destination row (consecutive destination rows share a source
+//                    row at scale 1.2): three aligned word loads cover the <= 9 source bytes of the four columns, the two
+//                    taps of a column come out of them with one funnel shift, the tap sum is one IDP.2A
+//                    (u16 coefficients x u8 pixels).  The vertical pass is two IMAD.HI per pixel.
+//   k_pyr_apron16    reflect-101 apron of every level: one thread per 16-byte chunk that touches the apron.
+//
+// The generic k_pyr_resize (orbb_extract.cu) stays as the fallback for larger scale steps.
+#pragma once
+
+constexpr int PR_ROWS = 8;            // destination rows per thread
+constexpr int PR_THREADS = 128;       // 32 word-columns x 4 row strips
+
+__global__ void __launch_bounds__(256) k_pyr_level0_v(const Plan* __restrict__ P, Bufs B, const uint8_t* __restrict__ src,
+                                                      size_t rowStride, size_t frameStride, int aligned16) {
+    const LevelPlan& L = P->lv[0];
+    const int chunk = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int frame = blockIdx.z;
+    const int x0 = chunk * 16;
+    if (x0 >= L.w || y >= L.h) return;
+    const uint8_t* s = src + (size_t)frame * frameStride + (size_t)y * rowStride + x0;
+    uint8_t* d = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + (size_t)y * L.pitch + x0;      // roiOff, pitch: 16-byte aligned
+    if (aligned16 && x0 + 16 <= L.w) {
+        *reinterpret_cast<uint4*>(d) = __ldg(reinterpret_cast<const uint4*>(s));
+    } else {
+        const int n = min(16, L.w - x0);
+        for (int k = 0; k < n; k++) d[k] = __ldg(s + k);
+    }
+}
+
+struct ResizeCol { unsigned coef; int sh; bool hi; };
+
+__device__ __forceinline__ void hresize4(const unsigned* __restrict__ rp, const ResizeCol (&c)[4], int (&h)[4]) {
+    const unsigned wa = __ldg(rp), wb = __ldg(rp + 1), wc = __ldg(rp + 2);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const unsigned lo = c[k].hi ? wb : wa, hi = c[k].hi ? wc : wb;
+        h[k] = (int)(__dp2a_lo(c[k].coef, __funnelshift_r(lo, hi, c[k].sh), 0u) >> 4);      // (S[sx]*a0 + S[sx+1]*a1) >> 4
+    }
+}
+
+__global__ void __launch_bounds__(PR_THREADS) k_pyr_resize_s(const Plan* __restrict__ P, Bufs B, int level) {
+    const LevelPlan& L = P->lv[level];
+    const LevelPlan& S = P->lv[level - 1];
+    const int word = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int dy0 = (blockIdx.y * (PR_THREADS / 32) + (threadIdx.x >> 5)) * PR_ROWS;
+    const int frame = blockIdx.z;
+    if (word * 4 >= L.w || dy0 >= L.h) return;
+    const int4* tx = reinterpret_cast<const int4*>(B.tab + L.tabX + word * 4);      // 4 entries (sx, a0 | a1 << 16), padded
+    const int4 t01 = __ldg(tx), t23 = __ldg(tx + 1);
+    const int wbase = t01.x >> 2;
+    ResizeCol c[4];
+    {
+        const int sx[4] = {t01.x, t01.z, t23.x, t23.z};
+        const int cf[4] = {t01.y, t01.w, t23.y, t23.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int o = sx[k] - 4 * wbase;                 // 0 .. 7 (checked on the host: LevelPlan::fastResize)
+            c[k].coef = (unsigned)cf[k];
+            c[k].sh = 8 * (o & 3);
+            c[k].hi = o >= 4;
+        }
+    }
+    const uint8_t* sroi = B.pyr + (size_t)frame * P->pyrStride + S.roiOff + 4 * wbase;
+    uint8_t* d = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + (size_t)dy0 * L.pitch + 4 * word;
+    const int2* ty = B.tab + L.tabY + dy0;
+    const int rows = min(PR_ROWS, L.h - dy0);
+    int cached = -1, hc[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int r = 0; r < PR_ROWS; r++) {
+        if (r < rows) {
+            const int2 t = __ldg(ty + r);
+            const int r0 = min(max(t.x, 0), S.h - 1), r1 = min(max(t.x + 1, 0), S.h - 1);
+            const int b0 = (int)(t.y << 16), b1 = (int)(t.y & 0xffff0000);      // coefficient << 16: mulhi == (b * h) >> 16
+            int h0[4];
+            if (r0 == cached) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) h0[k] = hc[k];
+            } else {
+                hresize4(reinterpret_cast<const unsigned*>(sroi + (size_t)r0 * S.pitch), c, h0);
+            }
+            if (r1 != r0) hresize4(reinterpret_cast<const unsigned*>(sroi + (size_t)r1 * S.pitch), c, hc);
+            else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) hc[k] = h0[k];
+            }
+            cached = r1;
+            unsigned out = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int v = (__mulhi(b0, h0[k]) + __mulhi(b1, hc[k]) + 2) >> 2;      // 0 .. 255 (coefficients sum to 2048)
+                out |= (unsigned)v << (8 * k);
+            }
+            *reinterpret_cast<unsigned*>(d + (size_t)r * L.pitch) = out;
+        }
+    }
+}
+
+// Apron of every level in one launch.  Work item = one 16-byte chunk of a bordered row that contains apron bytes: all
+// chunks of the 19 rows above / below the image, and the chunks at the two ends of every image row.  Each item computes
+// its 16 bytes by reflect-101 from final image pixels (copyMakeBorder BORDER_REFLECT_101; |offset| <= 19 < size: one
+// fold) and stores them with one 16-byte store; chunk bytes outside the apron (row padding) are don't-care, image
+// bytes inside an end chunk are rewritten with their own value.
+__global__ void __launch_bounds__(256) k_pyr_apron16(const Plan* __restrict__ P, Bufs B, int totalItems) {
+    int item = blockIdx.x * 256 + threadIdx.x;
+    if (item >= totalItems) return;
+    const int frame = blockIdx.y;
+    int level = 0;
+    while (level + 1 < P->nlevels && item >= P->apron[level + 1].itemBase) level++;
+    const LevelPlan& L = P->lv[level];
+    const ApronLevel A = P->apron[level];
+    item -= A.itemBase;
+    int by, chunk;                                          // bordered row (0 = top apron row), chunk within the row
+    const int nTB = 2 * kEdge * A.rowChunks;
+    if (item < nTB) {
+        by = item / A.rowChunks;
+        chunk = item - by * A.rowChunks;
+        if (by >= kEdge) by += L.h;
+    } else {
+        item -= nTB;
+        by = kEdge + item / A.sideChunks;
+        const int s = item - (by - kEdge) * A.sideChunks;
+        chunk = s < 2 ? s : A.rightChunk0 + s - 2;
+    }
+    const int iy = by - kEdge;
+    const int sy = iy < 0 ? -iy : (iy >= L.h ? 2 * L.h - 2 - iy : iy);
+    uint8_t* roi = B.pyr + (size_t)frame * P->pyrStride + L.roiOff;
+    const uint8_t* srow = roi + (ptrdiff_t)sy * L.pitch;
+    const int x0 = chunk * 16 - kRoiX;                      // image column of the chunk's first byte
+    uint4 v;
+    if (x0 >= 0 && x0 + 16 <= L.w) {
+        v = *reinterpret_cast<const uint4*>(srow + x0);
+    } else {
+        unsigned w[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            unsigned acc = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int x = x0 + 4 * q + k;
+                x = x < 0 ? -x : (x >= L.w ? 2 * L.w - 2 - x : x);
+                x = min(max(x, 0), L.w - 1);                // padding bytes beyond the apron: any valid pixel
+                acc |= (unsigned)srow[x] << (8 * k);
+            }
+            w[q] = acc;
+        }
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    *reinterpret_cast<uint4*>(roi + (ptrdiff_t)iy * L.pitch + x0) = v;
+}
