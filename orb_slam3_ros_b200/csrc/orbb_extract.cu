@@ -353,6 +353,7 @@ __global__ void __launch_bounds__(256) k_fast_v0(const Plan* __restrict__ P, Buf
 
 #include "orbb_fast.cuh"
 #include "orbb_fast2.cuh"
+#include "orbb_fast3.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // K3: DistributeOctTree, one CTA per (frame, level).
@@ -930,6 +931,8 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
     for (int i = 0; i < 16; i++) P.umax[i] = h->umax[i];
     std::vector<int2> tab;
     std::vector<CellDesc> cellDesc;
+    std::vector<BandDesc> bands;
+    int bandSmem = 0;
     size_t pyrBytes = 0, blurBytes = 0;
     unsigned cellKeys = 0, raw = 0, nodes = 0, sel = 0;
     int cells = 0, tiles = 0, kpCap = 0, fsTiles = 0;
@@ -970,6 +973,24 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
                 d.bpitch = L.bpitch;
                 cellDesc.push_back(d);
             }
+        {   // k_fast_band work items: per cell row, runs of cells whose pixels fit one FB_TP-wide tile
+            const int maxCells = std::max(1, std::min(FB_MAXCELLS, FB_MAXW / L.wCell));
+            const int nSeg = (L.nCols + maxCells - 1) / maxCells, per = (L.nCols + nSeg - 1) / nSeg;
+            for (int ci = 0; ci < L.nRows; ci++) {
+                const int iniY = kMinBorder + ci * L.hCell, maxY = std::min(iniY + L.hCell + 6, L.maxBY);
+                const bool skipRow = iniY >= L.maxBY - 3 || maxY - iniY < 7;
+                for (int c0 = 0; c0 < L.nCols; c0 += per) {
+                    BandDesc bd;
+                    bd.level = l; bd.ci = (short)ci; bd.c0 = (short)c0; bd.c1 = (short)std::min(c0 + per, L.nCols);
+                    bd.gy0 = (short)(iniY + 3); bd.ih = (short)(skipRow ? 0 : maxY - 3 - (iniY + 3));
+                    bd.X0 = (short)((kMinBorder + c0 * L.wCell) & ~15);
+                    bands.push_back(bd);
+                    if (bd.ih > 0)
+                        bandSmem = std::max(bandSmem, (int)(align_up((size_t)(bd.ih + 6) * FB_TP, 128) + align_up((size_t)(bd.ih + 2) * FB_TP, 128)) +
+                                                          FB_WARPS * FB_WARP_SMEM);
+                }
+            }
+        }
         cells += L.nCols * L.nRows;
         cellKeys += (unsigned)(L.nCols * L.nRows * L.cellCap);
         // quadtree (:559-561)
@@ -1034,6 +1055,7 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
         }
         P.apronItems = items;
     }
+    P.bandsTotal = (int)bands.size(); P.bandSmem = bandSmem;
     P.cellsTotal = cells; P.blurTilesTotal = tiles; P.kpCap = kpCap; P.fsTotal = fsTiles;
     P.pyrStride = pyrBytes; P.blurStride = blurBytes;
     P.cellKeyStride = cellKeys; P.rawStride = raw; P.nodeStride = nodes; P.selStride = sel;
@@ -1049,6 +1071,9 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
     CellDesc* dCellDesc = nullptr;
     A(dCellDesc, cellDesc.size());
     b.cellDesc = dCellDesc;
+    BandDesc* dBands = nullptr;
+    A(dBands, bands.size());
+    b.bands = dBands;
     A(b.cellCount, F * cells);
     A(b.fbList, F * cells);
     A(b.fbCount, F);
@@ -1076,6 +1101,8 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
 #undef A
     if (!tab.empty()) ORBB_CUDA(h, cudaMemcpyAsync(b.tab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
     ORBB_CUDA(h, cudaMemcpyAsync(dCellDesc, cellDesc.data(), cellDesc.size() * sizeof(CellDesc), cudaMemcpyHostToDevice, h->stream));
+    ORBB_CUDA(h, cudaMemcpyAsync(dBands, bands.data(), bands.size() * sizeof(BandDesc), cudaMemcpyHostToDevice, h->stream));
+    ORBB_CUDA(h, cudaFuncSetAttribute(k_fast_band, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(bandSmem, 1024)));
     ORBB_CUDA(h, cudaMemcpyAsync(h->dPlan, &P, sizeof P, cudaMemcpyHostToDevice, h->stream));
     ORBB_CUDA(h, cudaStreamSynchronize(h->stream));
     h->capacity = frames;
@@ -1151,6 +1178,11 @@ static int run_batch(orbb_extractor* h, const uint8_t* dImgs, int nframes, size_
     if (legacyFast) {
         mark(h, ST_FAST_CELLS);
         mark(h, ST_FAST_RETRY);
+    } else if (!fastMode || strcmp(fastMode, "split")) {
+        k_fast_band<<<dim3(P.bandsTotal, nframes), FB_THREADS, P.bandSmem, st>>>(h->dPlan, B, B.bands);
+        mark(h, ST_FAST_CELLS);
+        mark(h, ST_FAST_RETRY);
+        h->launches++;
     } else {
         k_fast_score<<<dim3(P.fsTotal, nframes), FS_THREADS, 0, st>>>(h->dPlan, B);
         mark(h, ST_FAST_CELLS);

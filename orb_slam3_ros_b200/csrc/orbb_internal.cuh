@@ -48,6 +48,7 @@ struct ApronLevel { int itemBase, sideChunks, rightChunk0, rowChunks; };
 struct Plan {
     int nlevels, W, H;
     int cellsTotal, blurTilesTotal, fsTotal;
+    int bandsTotal, bandSmem;      // k_fast_band: CTAs per frame, dynamic shared memory per CTA
     int kpCap;
     int iniTh, minTh;
     u64 pyrStride, blurStride;                                  // bytes per frame
@@ -70,6 +71,14 @@ struct WorkItem { int level, x, y, pos; };
 // reference skips the cell, ORBextractor.cc:810,:819), first key slot of the cell inside the frame's cellKeys.
 struct CellDesc { short gx0, gx1, gy0, gy1; int level; unsigned outOff; unsigned scoreOff; int bpitch; };
 
+// k_fast_band work item (host-built, one per CTA, shared by all frames): a run of adjacent cells of one cell row
+struct BandDesc {
+    int level;
+    short ci, c0, c1;              // cell row; cells [c0, c1) of that row
+    short gy0, ih;                 // interior rows [gy0, gy0 + ih) in level coordinates (ih <= 0: skipped cell row)
+    short X0;                      // level column of tile byte 0 (multiple of 16)
+};
+
 // Device buffers of one extractor handle, sized for `capacity` frames.
 struct Bufs {
     uint8_t* pyr;
@@ -77,6 +86,7 @@ struct Bufs {
     uint8_t* score;                // FAST response map per level (same layout as blur)
     int2* tab;                     // resize tables (shared by all frames)
     const CellDesc* cellDesc;      // [cellsTotal]
+    const BandDesc* bands;         // [bandsTotal]
     int* cellCount;
     int* fbList;                   // [frame][cellsTotal] cells that need the minThFAST retry
     int* fbCount;                  // [frame]
