@@ -1,6 +1,6 @@
 // K2, fused band formulation (production path).  (included INSIDE namespace orbb, after orbb_fast.cuh / orbb_fast2.cuh)
 //
-// One CTA stages a BAND SEGMENT -- a run of up to 8 adjacent 35-px cells of one cell row of one level -- and then each
+// One CTA stages a BAND SEGMENT -- a run of up to 4 adjacent 35-px cells of one cell row of one level -- and then each
 // WARP finishes one cell on its own (reference ORBextractor.cc:805-872: cv::FAST on each cell at iniThFAST, again at
 // minThFAST when the cell stays empty).  The cell interiors tile the level and the non-maximum suppression of cv::FAST never
 // looks across a cell border, so after the tile is in shared memory there is no CTA-wide barrier any more:
@@ -19,15 +19,31 @@
 // retry does not reload the cell, and ring test / score never run with a partly filled warp except once per cell.
 #pragma once
 
-constexpr int FB_WARPS = 8;                // = max cells per segment
+constexpr int FB_WARPS = 4;                // = max cells per segment
 constexpr int FB_THREADS = 32 * FB_WARPS;
-constexpr int FB_TP = 336;                 // tile pitch (bytes): 16-byte aligned window of <= 300 interior px + margins
+constexpr int FB_TP = 192;                 // tile pitch (bytes): 16-byte aligned window of <= 156 interior px + margins
 constexpr int FB_MAXW = FB_TP - 36;        // max interior width of a segment (+6 margin +30 alignment slop)
 constexpr int FB_MAXCELLS = FB_WARPS;
 constexpr int FB_CANDS = 32 + 256;         // candidate stack: < 32 left over + one round of phase A (32 lanes x 8 px)
 constexpr int FB_CORNS = 64;               // corner stack: < 32 left over + one round of phase B
 constexpr int FB_NC = 256;                 // corners of one cell kept for the list-driven NMS (more: NMS scans the score map)
 constexpr int FB_WARP_SMEM = 2 * (FB_CANDS + FB_CORNS + FB_NC);      // bytes of stacks per warp
+
+// Quick reject of 4 pixels (one word) as a byte mask: bit 7 of byte k is set when pixel k can still be a corner, i.e.
+// (|v-p0| > th or |v-p8| > th) and (|v-p4| > th or |v-p12| > th).  Per-byte unsigned "x > th" without widening:
+// s = (x & 0x7f) + (0x7f - (th & 0x7f)) carries into bit 7 iff low7(x) > low7(th); for th < 128 the answer is s | x, for
+// th >= 128 it is s & x (bit 7).  K7 = (0x7f - (th & 0x7f)) * 0x01010101, M = th >= 128 ? ~0u : 0.
+__device__ __forceinline__ unsigned gt_bytes(unsigned x, unsigned K7, unsigned M) {
+    const unsigned s = (x & 0x7f7f7f7fu) + K7;
+    return (M & s & x) | (~M & (s | x));
+}
+__device__ __forceinline__ unsigned quick_bytes4(unsigned wl, unsigned wc, unsigned wr, unsigned wt, unsigned wb, unsigned K7, unsigned M) {
+    const unsigned pl = __funnelshift_r(wl, wc, 8);      // bytes x-3 .. x
+    const unsigned pr = __funnelshift_r(wc, wr, 24);     // bytes x+3 .. x+6
+    const unsigned v = gt_bytes(__vabsdiffu4(wc, wt), K7, M) | gt_bytes(__vabsdiffu4(wc, wb), K7, M);
+    const unsigned h = gt_bytes(__vabsdiffu4(wc, pr), K7, M) | gt_bytes(__vabsdiffu4(wc, pl), K7, M);
+    return v & h;
+}
 
 // One cell, one warp.  tile: row t = level row gy0 - 3 + t, column = level column - X0.  score: row s = interior row s - 1.
 // Returns the number of NMS survivors parked in `park`.
@@ -38,7 +54,7 @@ __device__ __forceinline__ int cell_pass(const uint8_t* __restrict__ tile, uint8
     const int wa = cx0 >> 2, nwc = max(((cx1 + 3) >> 2) - wa, 2);        // (>= 2 keeps the reciprocal in 32 bits; extra words are masked)
     const unsigned mInv = 0xffffffffu / (unsigned)nwc + 1u;
     const int items = ((ih + 1) >> 1) * nwc;
-    const unsigned K = (unsigned)(0x7fff - th) * 0x00010001u;
+    const unsigned K7 = (unsigned)(0x7f - (th & 0x7f)) * 0x01010101u, M = th >= 128 ? 0xffffffffu : 0u;
     int nCand = 0, nCorn = 0, nAll = 0, base = 0;
     for (;;) {
         const bool aDone = base >= items;
@@ -120,10 +136,11 @@ __device__ __forceinline__ int cell_pass(const uint8_t* __restrict__ tile, uint8
                 const int r0 = 2 * s;
                 const int xb0 = 4 * w;
                 const int lo = max(cx0 - xb0, 0), hi = max(min(cx1 - xb0, 4), 0);
-                const unsigned xmask = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+                const unsigned xm1 = hi > lo ? ((0x01010101u >> (8 * (4 - hi))) >> (8 * lo)) << (8 * lo) : 0u;      // 0x01 in the bytes of columns [cx0, cx1)
                 const unsigned* q = reinterpret_cast<const unsigned*>(tile) + (r0 + 3) * TPW + w;
-                cand = quick_mask4(q[-1], q[0], q[1], q[3 * TPW], q[-3 * TPW], K) & xmask;
-                if (r0 + 1 < ih) cand |= (quick_mask4(q[TPW - 1], q[TPW], q[TPW + 1], q[4 * TPW], q[-2 * TPW], K) & xmask) << 4;
+                cand = (quick_bytes4(q[-1], q[0], q[1], q[3 * TPW], q[-3 * TPW], K7, M) >> 7) & xm1;      // bit 8k: pixel k of row r0
+                if (r0 + 1 < ih)                                                                              // bit 8k + 1: row r0 + 1
+                    cand |= ((quick_bytes4(q[TPW - 1], q[TPW], q[TPW + 1], q[4 * TPW], q[-2 * TPW], K7, M) >> 7) & xm1) << 1;
                 pos0 = (r0 + 3) * FB_TP + xb0;
             }
             const int cnt = __popc(cand);
@@ -133,7 +150,7 @@ __device__ __forceinline__ int cell_pass(const uint8_t* __restrict__ tile, uint8
             while (cand) {
                 const int b = __ffs(cand) - 1;
                 cand &= cand - 1;
-                candS[o++] = (unsigned short)(pos0 + (b >> 2) * FB_TP + (b & 3));
+                candS[o++] = (unsigned short)(pos0 + (b & 1) * FB_TP + (b >> 3));
             }
             base += 32;
             __syncwarp();
@@ -176,7 +193,7 @@ __device__ __forceinline__ int cell_pass(const uint8_t* __restrict__ tile, uint8
     return nSurv;
 }
 
-__global__ void __launch_bounds__(FB_THREADS) k_fast_band(const Plan* __restrict__ P, Bufs B, const BandDesc* __restrict__ bands) {
+__global__ void __launch_bounds__(FB_THREADS, 10) k_fast_band(const Plan* __restrict__ P, Bufs B, const BandDesc* __restrict__ bands) {
     extern __shared__ __align__(128) uint8_t fbSmem[];
     __shared__ __align__(8) unsigned long long sBar;
     const BandDesc bd = bands[blockIdx.x];
