@@ -864,6 +864,116 @@ __global__ void __launch_bounds__(256) k_orient_desc(const Plan* __restrict__ P,
     B.desc[((size_t)frame * P->kpCap + wi.pos) * 32 + lane] = (uint8_t)val;
 }
 
+// Production version: one warp takes OD_KPW keypoints of a frame through three phases, so that the per-keypoint scalar
+// work (fastAtan2, the double-precision cos / sin) runs once per LANE instead of once per warp:
+//   1. moments: the 31 x 31 window around the keypoint is read as 31 rows x 9 aligned words, consecutive lanes taking
+//      consecutive words (coalesced); each word is dotted (IDP.4A) with two weight words from a table indexed by the
+//      keypoint column's alignment -- u and v of the four pixels as int8, zero outside the umax circle -- which gives
+//      m10 = sum(u*I) and m01 = sum(v*I) directly; warp-sum; lane k keeps keypoint k's moments.
+//   2. lanes 0..OD_KPW-1: fastAtan2 + cos/sin of their own keypoint.
+//   3. per keypoint, lane = descriptor byte: the 8 steered tests, pattern points held in registers.
+constexpr int OD_THREADS = 256;
+constexpr int OD_KPW = 8;
+constexpr int OD_ITEMS = 31 * 9;                              // words of the moment window
+
+__device__ int2 gMomW[4][9][32];                             // [column alignment][round][lane] -> (u weights, v weights)
+__global__ void k_init_moment_weights() {
+    constexpr int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+    for (int i = threadIdx.x; i < 4 * 9 * 32; i += blockDim.x) {
+        const int sh = i / (9 * 32), t = i % (9 * 32);       // t = round * 32 + lane = row * 9 + word
+        unsigned wu = 0, wv = 0;
+        if (t < OD_ITEMS) {
+            const int row = t / 9, wq = t % 9, v = row - 15;
+            for (int j = 0; j < 4; j++) {
+                const int u = 4 * wq + j - sh - 15;          // word 0 starts at column (x - 15) & ~3
+                if (u >= -15 && u <= 15 && (u < 0 ? -u : u) <= kUmax[v < 0 ? -v : v]) {
+                    wu |= (unsigned)(u & 0xff) << (8 * j);
+                    wv |= (unsigned)(v & 0xff) << (8 * j);
+                }
+            }
+        }
+        (&gMomW[0][0][0])[i] = make_int2((int)wu, (int)wv);
+    }
+}
+
+__device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) {         // unsigned bytes x signed bytes
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+__global__ void __launch_bounds__(OD_THREADS, 4) k_orient_desc32(const Plan* __restrict__ P, Bufs B) {
+    const int frame = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = B.outCount[frame * 2];
+    const int g0 = (blockIdx.x * (OD_THREADS / 32) + warp) * OD_KPW;
+    if (g0 >= n) return;
+    const int cnt = min(OD_KPW, n - g0);
+    const WorkItem* work = B.work + (size_t)frame * P->kpCap + g0;
+    const uint8_t* pyr = B.pyr + (size_t)frame * P->pyrStride;
+    // ---- 1. IC_Angle moments (:76-103) ----
+    int M10 = 0, M01 = 0;
+    int rowOff[9], colOff[9];
+#pragma unroll
+    for (int q = 0; q < 9; q++) {
+        const int t = min(q * 32 + lane, OD_ITEMS - 1);      // (lanes past the window re-read its last word with zero weights)
+        rowOff[q] = t / 9 - 15;
+        colOff[q] = 4 * (t % 9);
+    }
+    for (int k = 0; k < cnt; k++) {
+        const WorkItem wi = work[k];
+        const LevelPlan& L = P->lv[wi.level];
+        const int xl = wi.x - 15;                            // level column of u = -15
+        const uint8_t* base = pyr + L.roiOff + (ptrdiff_t)wi.y * L.pitch + (xl & ~3);
+        const int2* wt = &gMomW[xl & 3][0][lane];
+        int su = 0, sv = 0;
+#pragma unroll
+        for (int q = 0; q < 9; q++) {
+            const unsigned a = __ldg(reinterpret_cast<const unsigned*>(base + rowOff[q] * L.pitch + colOff[q]));
+            const int2 w = __ldg(wt + q * 32);
+            su = dp4a_us(a, w.x, su);
+            sv = dp4a_us(a, w.y, sv);
+        }
+        const int m10 = warp_sum(su), m01 = warp_sum(sv);
+        if (lane == k) { M10 = m10; M01 = m01; }
+    }
+    // ---- 2. angle, cos, sin of lane's own keypoint ----
+    float ca = 1.f, sa = 0.f;
+    if (lane < cnt) {
+        const float angle = fast_atan2_deg((float)M01, (float)M10);
+        B.kps[(size_t)frame * P->kpCap + work[lane].pos].angle = angle;
+        const float factorPI = (float)(3.141592653589793238462643383279502884197 / 180.f);     // :106
+        const float rad = __fmul_rn(angle, factorPI);
+        ca = (float)cos((double)rad); sa = (float)sin((double)rad);                            // :112 (correctly rounded)
+    }
+    // ---- 3. steered BRIEF on the blurred level (:107-146) ----
+    float4 pat[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) pat[j] = __ldg(&gPatF[j * 32 + lane]);
+    for (int k = 0; k < cnt; k++) {
+        const WorkItem wi = work[k];
+        const LevelPlan& L = P->lv[wi.level];
+        const float a = __shfl_sync(0xffffffffu, ca, k), b = __shfl_sync(0xffffffffu, sa, k);
+        const int step = L.bpitch;
+        // the rounding trick (see round_rne) leaves the integer biased by 0x4B400000; the bias of row and column is folded
+        // into the base pointer
+        const uint8_t* bc = B.blur + (size_t)frame * P->blurStride + L.blurOff + (ptrdiff_t)wi.y * step + wi.x -
+                            ((ptrdiff_t)0x4B400000 * step + 0x4B400000);
+        unsigned val = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float4 pt = pat[j];
+            const int r0 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(pt.x, b), __fmul_rn(pt.y, a)), 12582912.f));      // :118
+            const int c0 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, b)), 12582912.f));      // :119
+            const int r1 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(pt.z, b), __fmul_rn(pt.w, a)), 12582912.f));
+            const int c1 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(pt.z, a), __fmul_rn(pt.w, b)), 12582912.f));
+            const int t0 = bc[(ptrdiff_t)r0 * step + c0], t1 = bc[(ptrdiff_t)r1 * step + c1];
+            val |= (unsigned)(t0 < t1) << j;
+        }
+        B.desc[((size_t)frame * P->kpCap + wi.pos) * 32 + lane] = (uint8_t)val;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -1207,7 +1317,9 @@ static int run_batch(orbb_extractor* h, const uint8_t* dImgs, int nframes, size_
     mark(h, ST_ASSEMBLE);
     k_assemble<<<nframes, 256, 0, st>>>(h->dPlan, B, lap0, lap1);
     mark(h, ST_ORIENT_DESC);
-    k_orient_desc<<<dim3((P.kpCap + 7) / 8, nframes), 256, 0, st>>>(h->dPlan, B);
+    static const bool legacyDesc = getenv("ORBB_DESC_LEGACY") != nullptr;
+    if (legacyDesc) k_orient_desc<<<dim3((P.kpCap + 7) / 8, nframes), 256, 0, st>>>(h->dPlan, B);
+    else k_orient_desc32<<<dim3((P.kpCap + OD_THREADS / 32 * OD_KPW - 1) / (OD_THREADS / 32 * OD_KPW), nframes), OD_THREADS, 0, st>>>(h->dPlan, B);
     mark(h, ST_D2H);
     h->launches += 5;
     ORBB_CUDA(h, cudaGetLastError());
@@ -1260,6 +1372,7 @@ int orbb_create(const orbb_params* prm, orbb_extractor** out) {
         cudaEventCreateWithFlags(&h->evDone[i], cudaEventDisableTiming);
     }
     k_init_pattern<<<1, 256, 0, h->stream>>>();
+    k_init_moment_weights<<<1, 256, 0, h->stream>>>();
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) {
         set_err(nullptr, ORBB_ERR_CUDA, "pattern init failed: %s", cudaGetErrorString(cudaGetLastError()));
         orbb_destroy(h);
