@@ -947,6 +947,7 @@ __global__ void __launch_bounds__(OD_THREADS, 4) k_orient_desc32(const Plan* __r
         ca = (float)cos((double)rad); sa = (float)sin((double)rad);                            // :112 (correctly rounded)
     }
     // ---- 3. steered BRIEF on the blurred level (:107-146) ----
+    // (staging the 37 x 37 patch in shared memory first was measured slower than gathering through L1: 0.29 vs 0.25 ms)
     float4 pat[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) pat[j] = __ldg(&gPatF[j * 32 + lane]);
@@ -1175,7 +1176,7 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
     int rc;
 #define A(ptr, count) if ((rc = dev_alloc(h, &ptr, (count))) != ORBB_OK) return rc
     A(b.pyr, F * pyrBytes + 512);          // slack: tile rows of the last level may be read a few bytes past their pitch
-    A(b.blur, F * blurBytes);
+    A(b.blur, F * blurBytes + 256);        // slack: descriptor patch rows are read as whole words
     A(b.score, F * blurBytes);
     A(b.tab, tab.size());
     CellDesc* dCellDesc = nullptr;
@@ -1246,11 +1247,12 @@ static Bufs shift_bufs(const Bufs& b, const Plan& P, int f0) {
 }
 
 // the launch sequence for `nframes` device-resident frames whose buffers start at frame f0
-static int run_batch(orbb_extractor* h, const uint8_t* dImgs, int nframes, size_t rowStride, size_t frameStride, int lap0, int lap1,
-                     int f0 = 0) {
+static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nframes, size_t rowStride, size_t frameStride, int lap0, int lap1,
+                    int f0) {
     const Plan& P = h->plan;
     const Bufs B = f0 ? shift_bufs(h->b, P, f0) : h->b;
-    cudaStream_t st = h->stream;
+    const orbb_extractor::Lane& ln = h->lanes[lane];
+    cudaStream_t st = ln.st;
     mark(h, ST_PYRAMID);
     ORBB_CUDA(h, cudaMemsetAsync(B.status, 0, sizeof(int) * nframes, st));
     ORBB_CUDA(h, cudaMemsetAsync(B.fbCount, 0, sizeof(int) * nframes, st));
@@ -1304,15 +1306,15 @@ static int run_batch(orbb_extractor* h, const uint8_t* dImgs, int nframes, size_
     mark(h, ST_OCTREE);
     // fork: the blur only needs the pyramid; on its own stream it fills the SMs that the latency-bound quadtree leaves idle.
     // With stage profiling on, everything stays on one stream so that the stage events mean what they say.
-    if (fork) ORBB_CUDA(h, cudaEventRecord(h->evFork, st));
+    if (fork) ORBB_CUDA(h, cudaEventRecord(ln.evFork, st));
     k_octree<<<dim3(P.nlevels, nframes), OT_THREADS, 0, st>>>(h->dPlan, B);
     if (fork) {
-        ORBB_CUDA(h, cudaStreamWaitEvent(h->blurStream, h->evFork, 0));
-        k_blur<<<dim3(P.blurTilesTotal, nframes), BLUR_THREADS, 0, h->blurStream>>>(h->dPlan, B);
-        ORBB_CUDA(h, cudaEventRecord(h->evJoin, h->blurStream));
+        ORBB_CUDA(h, cudaStreamWaitEvent(ln.blurSt, ln.evFork, 0));
+        k_blur<<<dim3(P.blurTilesTotal, nframes), BLUR_THREADS, 0, ln.blurSt>>>(h->dPlan, B);
+        ORBB_CUDA(h, cudaEventRecord(ln.evJoin, ln.blurSt));
     }
     mark(h, ST_BLUR);
-    if (fork) ORBB_CUDA(h, cudaStreamWaitEvent(st, h->evJoin, 0));
+    if (fork) ORBB_CUDA(h, cudaStreamWaitEvent(st, ln.evJoin, 0));
     else k_blur<<<dim3(P.blurTilesTotal, nframes), BLUR_THREADS, 0, st>>>(h->dPlan, B);
     mark(h, ST_ASSEMBLE);
     k_assemble<<<nframes, 256, 0, st>>>(h->dPlan, B, lap0, lap1);
@@ -1323,6 +1325,27 @@ static int run_batch(orbb_extractor* h, const uint8_t* dImgs, int nframes, size_
     mark(h, ST_D2H);
     h->launches += 5;
     ORBB_CUDA(h, cudaGetLastError());
+    return ORBB_OK;
+}
+
+// the launch sequence for `nframes` device-resident frames whose buffers start at frame f0: contiguous parts of the batch
+// go to the handle's lanes (all ordered after what is already queued on h->stream, and joined back into it)
+static int run_batch(orbb_extractor* h, const uint8_t* dImgs, int nframes, size_t rowStride, size_t frameStride, int lap0, int lap1,
+                     int f0 = 0) {
+    const int lanes = (h->profiling || nframes < 16 * h->nLanes) ? 1 : h->nLanes;
+    if (lanes > 1) ORBB_CUDA(h, cudaEventRecord(h->lanes[0].evStart, h->stream));
+    int done = 0;
+    for (int l = 0; l < lanes; l++) {
+        const int n = (nframes - done) / (lanes - l);
+        if (l > 0) ORBB_CUDA(h, cudaStreamWaitEvent(h->lanes[l].st, h->lanes[0].evStart, 0));
+        const int rc = run_lane(h, l, dImgs + (size_t)done * frameStride, n, rowStride, frameStride, lap0, lap1, f0 + done);
+        if (rc) return rc;
+        if (l > 0) {
+            ORBB_CUDA(h, cudaEventRecord(h->lanes[l].evDone, h->lanes[l].st));
+            ORBB_CUDA(h, cudaStreamWaitEvent(h->stream, h->lanes[l].evDone, 0));
+        }
+        done += n;
+    }
     h->lastFrames = f0 + nframes;
     h->hPyrFresh = false;
     return ORBB_OK;
@@ -1364,9 +1387,17 @@ int orbb_create(const orbb_params* prm, orbb_extractor** out) {
     for (int i = 0; i <= ST_COUNT; i++) cudaEventCreate(&h->ev[i]);
     cudaStreamCreateWithFlags(&h->h2dStream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&h->d2hStream, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&h->blurStream, cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming);
+    if (const char* e = getenv("ORBB_LANES")) h->nLanes = std::min(4, std::max(1, atoi(e)));
+    for (int l = 0; l < 4; l++) {
+        orbb_extractor::Lane& ln = h->lanes[l];
+        if (l == 0) ln.st = h->stream;
+        else cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&ln.blurSt, cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&ln.evFork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ln.evJoin, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ln.evStart, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ln.evDone, cudaEventDisableTiming);
+    }
     for (int i = 0; i < 8; i++) {
         cudaEventCreateWithFlags(&h->evH2D[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&h->evDone[i], cudaEventDisableTiming);
@@ -1395,9 +1426,15 @@ void orbb_destroy(orbb_extractor* h) {
     for (int i = 0; i < 8; i++) { if (h->evH2D[i]) cudaEventDestroy(h->evH2D[i]); if (h->evDone[i]) cudaEventDestroy(h->evDone[i]); }
     if (h->h2dStream) cudaStreamDestroy(h->h2dStream);
     if (h->d2hStream) cudaStreamDestroy(h->d2hStream);
-    if (h->blurStream) cudaStreamDestroy(h->blurStream);
-    if (h->evFork) cudaEventDestroy(h->evFork);
-    if (h->evJoin) cudaEventDestroy(h->evJoin);
+    for (int l = 0; l < 4; l++) {
+        orbb_extractor::Lane& ln = h->lanes[l];
+        if (l > 0 && ln.st) { cudaStreamSynchronize(ln.st); cudaStreamDestroy(ln.st); }
+        if (ln.blurSt) { cudaStreamSynchronize(ln.blurSt); cudaStreamDestroy(ln.blurSt); }
+        if (ln.evFork) cudaEventDestroy(ln.evFork);
+        if (ln.evJoin) cudaEventDestroy(ln.evJoin);
+        if (ln.evStart) cudaEventDestroy(ln.evStart);
+        if (ln.evDone) cudaEventDestroy(ln.evDone);
+    }
     cudaStreamDestroy(h->stream);
     delete h;
 }

@@ -156,8 +156,12 @@ struct orbb_extractor {
     cudaStream_t stream = nullptr;
     cudaStream_t h2dStream = nullptr, d2hStream = nullptr;   // copy engines for the pipelined host path
     cudaEvent_t evH2D[8]{}, evDone[8]{};
-    cudaStream_t blurStream = nullptr;                       // k_blur runs beside FAST + quadtree (both only read the pyramid)
-    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    // execution lanes of the resident batch path: the frames of a batch are split over ORBB_LANES streams so that the
+    // latency-bound kernels of one part (quadtree, descriptors) share the SMs with the issue-bound ones of another; inside a
+    // lane the blur runs on a side stream beside the quadtree (both only read the pyramid).  Lane 0 uses `stream`.
+    struct Lane { cudaStream_t st = nullptr, blurSt = nullptr; cudaEvent_t evFork = nullptr, evJoin = nullptr, evStart = nullptr, evDone = nullptr; };
+    Lane lanes[4];
+    int nLanes = 1;                // measured on B200: 2 lanes +1.7 % resident, -11 % end to end -> off by default (ORBB_LANES)
     // plan for the current image size
     orbb::Plan plan;
     orbb::Plan* dPlan = nullptr;

@@ -33,13 +33,15 @@ __global__ void __launch_bounds__(256) k_pyr_level0_v(const Plan* __restrict__ P
     }
 }
 
-struct ResizeCol { unsigned coef; int sh; bool hi; };
+// per-thread constants of one destination column: packed coefficients, byte shift inside the word pair, and a mask that
+// selects the word pair (words 0/1 or 1/2 of the three loaded ones)
+struct ResizeCol { unsigned coef, sh, m; };
 
 __device__ __forceinline__ void hresize4(const unsigned* __restrict__ rp, const ResizeCol (&c)[4], int (&h)[4]) {
     const unsigned wa = __ldg(rp), wb = __ldg(rp + 1), wc = __ldg(rp + 2);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const unsigned lo = c[k].hi ? wb : wa, hi = c[k].hi ? wc : wb;
+        const unsigned lo = (wa & ~c[k].m) | (wb & c[k].m), hi = (wb & ~c[k].m) | (wc & c[k].m);      // one LOP3 each
         h[k] = (int)(__dp2a_lo(c[k].coef, __funnelshift_r(lo, hi, c[k].sh), 0u) >> 4);      // (S[sx]*a0 + S[sx+1]*a1) >> 4
     }
 }
@@ -50,7 +52,8 @@ __global__ void __launch_bounds__(PR_THREADS) k_pyr_resize_s(const Plan* __restr
     const int word = blockIdx.x * 32 + (threadIdx.x & 31);
     const int dy0 = (blockIdx.y * (PR_THREADS / 32) + (threadIdx.x >> 5)) * PR_ROWS;
     const int frame = blockIdx.z;
-    if (word * 4 >= L.w || dy0 >= L.h) return;
+    const int Lw = L.w, Lh = L.h, Lpitch = L.pitch, Sh1 = S.h - 1, Spitch = S.pitch;
+    if (word * 4 >= Lw || dy0 >= Lh) return;
     const int4* tx = reinterpret_cast<const int4*>(B.tab + L.tabX + word * 4);      // 4 entries (sx, a0 | a1 << 16), padded
     const int4 t01 = __ldg(tx), t23 = __ldg(tx + 1);
     const int wbase = t01.x >> 2;
@@ -62,29 +65,31 @@ __global__ void __launch_bounds__(PR_THREADS) k_pyr_resize_s(const Plan* __restr
         for (int k = 0; k < 4; k++) {
             const int o = sx[k] - 4 * wbase;                 // 0 .. 7 (checked on the host: LevelPlan::fastResize)
             c[k].coef = (unsigned)cf[k];
-            c[k].sh = 8 * (o & 3);
-            c[k].hi = o >= 4;
+            c[k].sh = 8u * (o & 3);
+            c[k].m = o >= 4 ? 0xffffffffu : 0u;
+            // keep the three as live registers: ptxas otherwise re-derives them from `o` in every row
+            asm volatile("" : "+r"(c[k].sh), "+r"(c[k].m));
         }
     }
     const uint8_t* sroi = B.pyr + (size_t)frame * P->pyrStride + S.roiOff + 4 * wbase;
-    uint8_t* d = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + (size_t)dy0 * L.pitch + 4 * word;
+    uint8_t* d = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + (size_t)dy0 * Lpitch + 4 * word;
     const int2* ty = B.tab + L.tabY + dy0;
-    const int rows = min(PR_ROWS, L.h - dy0);
+    const int rows = min(PR_ROWS, Lh - dy0);
     int cached = -1, hc[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int r = 0; r < PR_ROWS; r++) {
         if (r < rows) {
             const int2 t = __ldg(ty + r);
-            const int r0 = min(max(t.x, 0), S.h - 1), r1 = min(max(t.x + 1, 0), S.h - 1);
+            const int r0 = min(max(t.x, 0), Sh1), r1 = min(max(t.x + 1, 0), Sh1);
             const int b0 = (int)(t.y << 16), b1 = (int)(t.y & 0xffff0000);      // coefficient << 16: mulhi == (b * h) >> 16
             int h0[4];
             if (r0 == cached) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) h0[k] = hc[k];
             } else {
-                hresize4(reinterpret_cast<const unsigned*>(sroi + (size_t)r0 * S.pitch), c, h0);
+                hresize4(reinterpret_cast<const unsigned*>(sroi + (size_t)r0 * Spitch), c, h0);
             }
-            if (r1 != r0) hresize4(reinterpret_cast<const unsigned*>(sroi + (size_t)r1 * S.pitch), c, hc);
+            if (r1 != r0) hresize4(reinterpret_cast<const unsigned*>(sroi + (size_t)r1 * Spitch), c, hc);
             else {
 #pragma unroll
                 for (int k = 0; k < 4; k++) hc[k] = h0[k];
@@ -96,7 +101,7 @@ __global__ void __launch_bounds__(PR_THREADS) k_pyr_resize_s(const Plan* __restr
                 const int v = (__mulhi(b0, h0[k]) + __mulhi(b1, hc[k]) + 2) >> 2;      // 0 .. 255 (coefficients sum to 2048)
                 out |= (unsigned)v << (8 * k);
             }
-            *reinterpret_cast<unsigned*>(d + (size_t)r * L.pitch) = out;
+            *reinterpret_cast<unsigned*>(d + (size_t)r * Lpitch) = out;
         }
     }
 }
