@@ -170,17 +170,29 @@ __global__ void __launch_bounds__(256) k_pyr_apron(const Plan* __restrict__ P, B
 // in 16 bit, vertical pass 32 bit, one rounding (acc + 2^15) >> 16; BORDER_REFLECT_101 at the IMAGE edge
 // (the reference blurs a clone of the level, so the pyramid apron is not used) (:1132-1133).
 // ------------------------------------------------------------------------------------------------
-// One thread owns 4 adjacent columns (one 32-bit word) of a 16-row strip and slides a 7-row window of horizontal
-// sums down the strip entirely in registers: 3 aligned word loads per row (served by L1; neighbouring lanes share two
-// of them), the 7-tap horizontal sums as two IDP.4A each, the vertical pass as 4 IMAD + 3 IADD per pixel.  The
-// pyramid's own 19-px apron IS the reflect-101 extension of the level, so edge pixels need no special case.
-constexpr int BLUR_THREADS = 128, BLUR_STRIP = 16;
+// No shared memory: 3 aligned word loads per row (served by L1; neighbouring lanes share two of them), the 7-tap
+// horizontal sums as two IDP.4A each.  The pyramid's own 19-px apron IS the reflect-101 extension of the level, so edge
+// pixels need no special case.
+constexpr int BLUR_THREADS = 128, BLUR_STRIP = 32;
 
 __device__ __forceinline__ unsigned hsum7(unsigned a, unsigned b) {
-    // a = bytes x-3..x (taps 18,34,48,56), b = bytes x+1..x+4 (taps 48,34,18,0)
+    // a = bytes x-3..x (taps 18,34,48,56), b = bytes x+1..x+4 (taps 48,34,18,0); result <= 255 * 256 fits 16 bits
     return __dp4a(a, 0x38302212u, __dp4a(b, 0x00122230u, 0u));
 }
 
+// horizontal sums of the 4 columns of one word for one input row
+__device__ __forceinline__ void blur_hrow(const unsigned* __restrict__ row, unsigned (&h)[4]) {
+    const unsigned w0 = __ldg(row - 1), w1 = __ldg(row), w2 = __ldg(row + 1);
+    h[0] = hsum7(__funnelshift_r(w0, w1, 8), __funnelshift_r(w1, w2, 8));
+    h[1] = hsum7(__funnelshift_r(w0, w1, 16), __funnelshift_r(w1, w2, 16));
+    h[2] = hsum7(__funnelshift_r(w0, w1, 24), __funnelshift_r(w1, w2, 24));
+    h[3] = hsum7(w1, w2);
+}
+
+// One thread owns 4 adjacent columns (one word) of a 32-row strip.  The horizontal sums of two consecutive input rows are
+// kept PACKED in one register (u16 | u16 << 16), so the vertical 7-tap pass of one pixel is four IDP.2A (u16 x u8 dot
+// products with the tap pairs) over the four row pairs that cover its window -- for even and for odd output rows with
+// different tap constants -- instead of 4 multiplies + 3 adds on unpacked sums.
 __global__ void __launch_bounds__(BLUR_THREADS) k_blur(const Plan* __restrict__ P, Bufs B) {
     const int frame = blockIdx.y;
     int level = 0;
@@ -193,29 +205,39 @@ __global__ void __launch_bounds__(BLUR_THREADS) k_blur(const Plan* __restrict__ 
     const int strip = item / nwords, wc = item - strip * nwords;
     const int y0 = strip * BLUR_STRIP;
     const int rows = min(BLUR_STRIP, L.h - y0);
-    const uint8_t* src = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + 4 * wc;
-    uint8_t* out = B.blur + (size_t)frame * P->blurStride + L.blurOff + 4 * wc;
-    unsigned hw[7][4];
+    const int pitch = L.pitch, bpitch = L.bpitch;
+    // input row i of the strip = level row y0 - 3 + i; output row i uses input rows i .. i + 6
+    const uint8_t* src = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + 4 * wc + (ptrdiff_t)(y0 - 3) * pitch;
+    uint8_t* out = B.blur + (size_t)frame * P->blurStride + L.blurOff + 4 * wc + (size_t)y0 * bpitch;
+    unsigned pk[4][4];                                       // 4 row pairs x 4 columns
+    auto load_pair = [&](unsigned (&dst)[4]) {
+        unsigned h0[4], h1[4];
+        blur_hrow(reinterpret_cast<const unsigned*>(src), h0);
+        blur_hrow(reinterpret_cast<const unsigned*>(src + pitch), h1);
+        src += 2 * pitch;
 #pragma unroll
-    for (int r = 0; r < BLUR_STRIP + 6; r++) {
-        if (r < rows + 6) {
-            const unsigned* row = reinterpret_cast<const unsigned*>(src + (ptrdiff_t)(y0 + r - 3) * L.pitch);
-            const unsigned w0 = __ldg(row - 1), w1 = __ldg(row), w2 = __ldg(row + 1);
-            unsigned* h = hw[r % 7];
-            h[0] = hsum7(__funnelshift_r(w0, w1, 8), __funnelshift_r(w1, w2, 8));
-            h[1] = hsum7(__funnelshift_r(w0, w1, 16), __funnelshift_r(w1, w2, 16));
-            h[2] = hsum7(__funnelshift_r(w0, w1, 24), __funnelshift_r(w1, w2, 24));
-            h[3] = hsum7(w1, w2);
-            if (r >= 6) {
-                unsigned o[4];
+        for (int k = 0; k < 4; k++) dst[k] = h0[k] | (h1[k] << 16);
+    };
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const unsigned acc = 18u * (hw[(r - 6) % 7][k] + hw[r % 7][k]) + 34u * (hw[(r - 5) % 7][k] + hw[(r - 1) % 7][k]) +
-                                         48u * (hw[(r - 4) % 7][k] + hw[(r - 2) % 7][k]) + 56u * hw[(r - 3) % 7][k] + 32768u;
-                    o[k] = acc >> 16;
-                }
-                *reinterpret_cast<unsigned*>(out + (size_t)(y0 + r - 6) * L.bpitch) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+    for (int j = 0; j < 3; j++) load_pair(pk[j]);
+#pragma unroll
+    for (int m = 0; m < BLUR_STRIP / 2; m++) {
+        if (2 * m < rows) {                                  // (input rows up to rows + 6 lie inside the 19-px apron)
+            load_pair(pk[(m + 3) & 3]);
+            unsigned e[4], o[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const unsigned p0 = pk[m & 3][k], p1 = pk[(m + 1) & 3][k], p2 = pk[(m + 2) & 3][k], p3 = pk[(m + 3) & 3][k];
+                // even output row 2m: rows 2m..2m+6 = (18,34) (48,56) (48,34) (18,-)
+                e[k] = __dp2a_lo(p0, 0x2212u, __dp2a_lo(p1, 0x3830u, __dp2a_lo(p2, 0x2230u, __dp2a_lo(p3, 0x0012u, 32768u))));
+                // odd output row 2m+1: rows 2m+1..2m+7 = (-,18) (34,48) (56,48) (34,18)
+                o[k] = __dp2a_lo(p0, 0x1200u, __dp2a_lo(p1, 0x3022u, __dp2a_lo(p2, 0x3038u, __dp2a_lo(p3, 0x1222u, 32768u))));
             }
+            // byte 2 of every accumulator = (acc + 2^15) >> 16
+            *reinterpret_cast<unsigned*>(out) = __byte_perm(__byte_perm(e[0], e[1], 0x0062), __byte_perm(e[2], e[3], 0x0062), 0x5410);
+            if (2 * m + 1 < rows)
+                *reinterpret_cast<unsigned*>(out + bpitch) = __byte_perm(__byte_perm(o[0], o[1], 0x0062), __byte_perm(o[2], o[3], 0x0062), 0x5410);
+            out += 2 * bpitch;
         }
     }
 }
@@ -1117,7 +1139,7 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
         kpCap += L.selCap;
         L.scale = h->scale[l];
         L.kpSize = (float)(int)(31 * h->scale[l]);                   // :880 (PATCH_SIZE*mvScaleFactor -> int)
-        L.blurTilesX = (L.w + 3) / 4; L.blurTilesY = (L.h + BLUR_STRIP - 1) / BLUR_STRIP;     // word columns x 16-row strips
+        L.blurTilesX = (L.w + 3) / 4; L.blurTilesY = (L.h + BLUR_STRIP - 1) / BLUR_STRIP;     // word columns x 32-row strips
         L.blurTileBase = tiles; tiles += (L.blurTilesX * L.blurTilesY + BLUR_THREADS - 1) / BLUR_THREADS;
         L.fsTilesX = ((L.w + 3) / 4 + 31) / 32;
         L.fsGroups = ((L.h - 2 * kEdge + FS_R - 1) / FS_R + 3) / 4;
@@ -1162,6 +1184,8 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
             A.rowChunks = (kRoiX + L.w + kEdge + 15) / 16;
             A.rightChunk0 = (kRoiX + L.w) / 16;
             A.sideChunks = 2 + (kRoiX + L.w + kEdge - 1) / 16 - A.rightChunk0 + 1;
+            A.invRow = 0xffffffffu / (unsigned)A.rowChunks + 1u;
+            A.invSide = 0xffffffffu / (unsigned)A.sideChunks + 1u;
             items += 2 * kEdge * A.rowChunks + L.h * A.sideChunks;
         }
         P.apronItems = items;
@@ -1276,7 +1300,11 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
         borderedRows += L.h + 2 * kEdge;
     }
     if (legacyPyr) k_pyr_apron<<<dim3((borderedRows + 7) / 8, nframes), 256, 0, st>>>(h->dPlan, B, borderedRows);
-    else k_pyr_apron16<<<dim3((P.apronItems + 255) / 256, nframes), 256, 0, st>>>(h->dPlan, B, P.apronItems);
+    else {
+        ApronTable T;
+        for (int l = 0; l <= ORBB_MAX_LEVELS; l++) T.base[l] = l < P.nlevels ? P.apron[l].itemBase : P.apronItems;
+        k_pyr_apron16<<<dim3((P.apronItems + 255) / 256, nframes), 256, 0, st>>>(h->dPlan, B, T, P.nlevels);
+    }
     h->launches++;
     const bool fork = !h->profiling;
     mark(h, ST_FAST);

@@ -110,51 +110,65 @@ __global__ void __launch_bounds__(PR_THREADS) k_pyr_resize_s(const Plan* __restr
 // chunks of the 19 rows above / below the image, and the chunks at the two ends of every image row.  Each item computes
 // its 16 bytes by reflect-101 from final image pixels (copyMakeBorder BORDER_REFLECT_101; |offset| <= 19 < size: one
 // fold) and stores them with one 16-byte store; chunk bytes outside the apron (row padding) are don't-care, image
-// bytes inside an end chunk are rewritten with their own value.
-__global__ void __launch_bounds__(256) k_pyr_apron16(const Plan* __restrict__ P, Bufs B, int totalItems) {
+// bytes inside an end chunk are rewritten with their own value.  Words left of the image are a byte-reversed pair of
+// image words (one PRMT); words inside the image are copied; only the words that straddle the right edge go byte by byte.
+struct ApronTable { int base[ORBB_MAX_LEVELS + 1]; };        // first item of every level (kernel parameter: constant bank)
+
+__global__ void __launch_bounds__(256) k_pyr_apron16(const Plan* __restrict__ P, Bufs B, const ApronTable T, int nlevels) {
     int item = blockIdx.x * 256 + threadIdx.x;
-    if (item >= totalItems) return;
+    if (item >= T.base[nlevels]) return;
     const int frame = blockIdx.y;
     int level = 0;
-    while (level + 1 < P->nlevels && item >= P->apron[level + 1].itemBase) level++;
+#pragma unroll
+    for (int l = 1; l < ORBB_MAX_LEVELS; l++) level += (l < nlevels && item >= T.base[l]);
     const LevelPlan& L = P->lv[level];
     const ApronLevel A = P->apron[level];
+    const int w = L.w, h = L.h, pitch = L.pitch;
     item -= A.itemBase;
     int by, chunk;                                          // bordered row (0 = top apron row), chunk within the row
     const int nTB = 2 * kEdge * A.rowChunks;
     if (item < nTB) {
-        by = item / A.rowChunks;
+        by = (int)__umulhi((unsigned)item, A.invRow);
         chunk = item - by * A.rowChunks;
-        if (by >= kEdge) by += L.h;
+        if (by >= kEdge) by += h;
     } else {
         item -= nTB;
-        by = kEdge + item / A.sideChunks;
-        const int s = item - (by - kEdge) * A.sideChunks;
+        const int r = (int)__umulhi((unsigned)item, A.invSide);
+        by = kEdge + r;
+        const int s = item - r * A.sideChunks;
         chunk = s < 2 ? s : A.rightChunk0 + s - 2;
     }
     const int iy = by - kEdge;
-    const int sy = iy < 0 ? -iy : (iy >= L.h ? 2 * L.h - 2 - iy : iy);
+    const int sy = iy < 0 ? -iy : (iy >= h ? 2 * h - 2 - iy : iy);
     uint8_t* roi = B.pyr + (size_t)frame * P->pyrStride + L.roiOff;
-    const uint8_t* srow = roi + (ptrdiff_t)sy * L.pitch;
+    const uint8_t* srow = roi + (ptrdiff_t)sy * pitch;
     const int x0 = chunk * 16 - kRoiX;                      // image column of the chunk's first byte
     uint4 v;
-    if (x0 >= 0 && x0 + 16 <= L.w) {
+    if (x0 >= 0 && x0 + 16 <= w) {
         v = *reinterpret_cast<const uint4*>(srow + x0);
     } else {
-        unsigned w[4];
+        unsigned o[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
+            const int X = x0 + 4 * q;
             unsigned acc = 0;
+            if (X >= 0 && X + 4 <= w) {
+                acc = *reinterpret_cast<const unsigned*>(srow + X);
+            } else if (X + 3 < 0) {
+                if (X >= -20) {                             // bytes X..X+3 <- image columns -X, -X-1, -X-2, -X-3
+                    const unsigned* p = reinterpret_cast<const unsigned*>(srow - X);
+                    acc = __byte_perm(p[-1], p[0], 0x1234);
+                }
+            } else if (X < w + kEdge) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                int x = x0 + 4 * q + k;
-                x = x < 0 ? -x : (x >= L.w ? 2 * L.w - 2 - x : x);
-                x = min(max(x, 0), L.w - 1);                // padding bytes beyond the apron: any valid pixel
-                acc |= (unsigned)srow[x] << (8 * k);
+                for (int k = 0; k < 4; k++) {
+                    const int x = X + k;
+                    if (x < w + kEdge) acc |= (unsigned)srow[x >= w ? 2 * w - 2 - x : x] << (8 * k);
+                }
             }
-            w[q] = acc;
+            o[q] = acc;
         }
-        v = make_uint4(w[0], w[1], w[2], w[3]);
+        v = make_uint4(o[0], o[1], o[2], o[3]);
     }
-    *reinterpret_cast<uint4*>(roi + (ptrdiff_t)iy * L.pitch + x0) = v;
+    *reinterpret_cast<uint4*>(roi + (ptrdiff_t)iy * pitch + x0) = v;
 }
