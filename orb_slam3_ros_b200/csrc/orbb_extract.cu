@@ -466,7 +466,9 @@ __device__ __forceinline__ int nonempty4(const int4 c) { return (c.x > 0) + (c.y
 __device__ __forceinline__ int multi4(const int4 c) { return (c.x > 1) + (c.y > 1) + (c.z > 1) + (c.w > 1); }
 
 __global__ void __launch_bounds__(OT_THREADS) k_octree(const Plan* __restrict__ P, Bufs B) {
-    const int level = blockIdx.x, frame = blockIdx.y;
+    // grid = (frames, levels): CTAs are dispatched x-fastest, so the long-running low levels of ALL frames start first and
+    // the short high levels fill the tail
+    const int level = blockIdx.y, frame = blockIdx.x;
     const LevelPlan& L = P->lv[level];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = L.nFeat;
@@ -1181,12 +1183,12 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
             const LevelPlan& L = P.lv[l];
             ApronLevel& A = P.apron[l];
             A.itemBase = items;
-            A.rowChunks = (kRoiX + L.w + kEdge + 15) / 16;
-            A.rightChunk0 = (kRoiX + L.w) / 16;
-            A.sideChunks = 2 + (kRoiX + L.w + kEdge - 1) / 16 - A.rightChunk0 + 1;
-            A.invRow = 0xffffffffu / (unsigned)A.rowChunks + 1u;
-            A.invSide = 0xffffffffu / (unsigned)A.sideChunks + 1u;
-            items += 2 * kEdge * A.rowChunks + L.h * A.sideChunks;
+            A.rightChunk0 = (kRoiX + L.w) / 16;                                   // first chunk with a column >= w
+            A.nRight = (kRoiX + L.w + kEdge - 1) / 16 - A.rightChunk0 + 1;
+            A.interiorChunks = std::max(A.rightChunk0 - 2, 1);                    // chunks 2 .. rightChunk0-1 lie inside the image
+            A.invIC = A.interiorChunks > 1 ? 0xffffffffu / (unsigned)A.interiorChunks + 1u : 0u;
+            A.invNR = A.nRight > 1 ? 0xffffffffu / (unsigned)A.nRight + 1u : 0u;
+            items += 2 * kEdge * A.interiorChunks + (L.h + 2 * kEdge) * (2 + A.nRight);
         }
         P.apronItems = items;
     }
@@ -1335,7 +1337,7 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
     // fork: the blur only needs the pyramid; on its own stream it fills the SMs that the latency-bound quadtree leaves idle.
     // With stage profiling on, everything stays on one stream so that the stage events mean what they say.
     if (fork) ORBB_CUDA(h, cudaEventRecord(ln.evFork, st));
-    k_octree<<<dim3(P.nlevels, nframes), OT_THREADS, 0, st>>>(h->dPlan, B);
+    k_octree<<<dim3(nframes, P.nlevels), OT_THREADS, 0, st>>>(h->dPlan, B);
     if (fork) {
         ORBB_CUDA(h, cudaStreamWaitEvent(ln.blurSt, ln.evFork, 0));
         k_blur<<<dim3(P.blurTilesTotal, nframes), BLUR_THREADS, 0, ln.blurSt>>>(h->dPlan, B);

@@ -43,7 +43,7 @@ struct LevelPlan {
 };
 
 // k_pyr_apron16 work decomposition of one level (16-byte chunks that contain apron bytes)
-struct ApronLevel { int itemBase, sideChunks, rightChunk0, rowChunks; unsigned invRow, invSide; };     // inv* = 2^32 / n + 1
+struct ApronLevel { int itemBase, interiorChunks, rightChunk0, nRight; unsigned invIC, invNR; };     // inv* = 2^32 / n + 1
 
 struct Plan {
     int nlevels, W, H;

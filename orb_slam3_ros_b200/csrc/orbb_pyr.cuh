@@ -125,18 +125,23 @@ __global__ void __launch_bounds__(256) k_pyr_apron16(const Plan* __restrict__ P,
     const ApronLevel A = P->apron[level];
     const int w = L.w, h = L.h, pitch = L.pitch;
     item -= A.itemBase;
+    // three item classes per level, each row-major (coalesced) and each taking ONE path below in all lanes of a warp:
+    // chunks inside the image of the 38 apron rows (copy), the two left chunks of every bordered row (reflection by PRMT),
+    // the right-edge chunks of every bordered row (bytes)
     int by, chunk;                                          // bordered row (0 = top apron row), chunk within the row
-    const int nTB = 2 * kEdge * A.rowChunks;
-    if (item < nTB) {
-        by = (int)__umulhi((unsigned)item, A.invRow);
-        chunk = item - by * A.rowChunks;
+    const int nI = 2 * kEdge * A.interiorChunks, nL = 2 * (h + 2 * kEdge);
+    if (item < nI) {
+        by = A.interiorChunks == 1 ? item : (int)__umulhi((unsigned)item, A.invIC);
+        chunk = 2 + item - by * A.interiorChunks;
         if (by >= kEdge) by += h;
+    } else if (item < nI + nL) {
+        item -= nI;
+        by = item >> 1;
+        chunk = item & 1;
     } else {
-        item -= nTB;
-        const int r = (int)__umulhi((unsigned)item, A.invSide);
-        by = kEdge + r;
-        const int s = item - r * A.sideChunks;
-        chunk = s < 2 ? s : A.rightChunk0 + s - 2;
+        item -= nI + nL;
+        by = A.nRight == 1 ? item : (int)__umulhi((unsigned)item, A.invNR);
+        chunk = A.rightChunk0 + item - by * A.nRight;
     }
     const int iy = by - kEdge;
     const int sy = iy < 0 ? -iy : (iy >= h ? 2 * h - 2 - iy : iy);
