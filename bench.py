@@ -297,7 +297,8 @@ def run_ours(a):
         traffic = json.loads((ROOT / "profiles" / "roofline_traffic.json").read_text()).get(dom)
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+    kernel_names = {"fast": "k_fast_band", "octree": "k_octree", "blur": "k_blur", "orient_desc": "k_orient_desc32", "assemble": "k_assemble"}
+    roofline = {"bound": "hbm", "kernel": kernel_names.get(dom, dom), "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "kernel_ms": dom_ms,
                 "stage_ms": stage_acc,
                 "path": {"achieved": alg_bytes / (ms_total / a.steps * 1e-3) / 1e9,

@@ -1234,6 +1234,8 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
     A(b.depth, F * kpCap);
     A(b.bestR, F * kpCap);
     A(b.sad, F * kpCap);
+    A(b.stRec, F * kpCap);
+    A(b.stRowStart, F * (H + 2));
     A(h->dPlan, 1);
 #undef A
     if (!tab.empty()) ORBB_CUDA(h, cudaMemcpyAsync(b.tab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
@@ -1269,6 +1271,7 @@ static Bufs shift_bufs(const Bufs& b, const Plan& P, int f0) {
     s.erased += f * P.nodeStride; s.sel += f * P.selStride; s.selCount += f * ORBB_MAX_LEVELS;
     s.work += f * P.kpCap; s.kps += f * P.kpCap; s.desc += f * P.kpCap * 32; s.outCount += f * 2; s.status += f;
     s.uRight += f * P.kpCap; s.depth += f * P.kpCap; s.bestR += f * P.kpCap; s.sad += f * P.kpCap;
+    s.stRec += f * P.kpCap; s.stRowStart += f * (P.H + 2);
     return s;
 }
 
@@ -1499,7 +1502,7 @@ int orbb_set_profiling(orbb_extractor* h, int enabled) {
 }
 
 const char* orbb_stage_name(int i) {
-    static const char* names[ST_COUNT] = {"h2d", "pyramid", "fast_score", "fast_cells", "fast_retry", "octree", "blur", "assemble", "orient_desc", "d2h"};
+    static const char* names[ST_COUNT] = {"h2d", "pyramid", "fast", "fast_cells", "fast_retry", "octree", "blur", "assemble", "orient_desc", "d2h"};
     return (i >= 0 && i < ST_COUNT) ? names[i] : "";
 }
 

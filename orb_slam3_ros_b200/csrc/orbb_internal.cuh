@@ -110,6 +110,8 @@ struct Bufs {
     float* depth;
     int* bestR;
     int* sad;
+    uint4* stRec;                  // [frame][kpCap] stereo: this image's keypoints bucketed by row {x, minr | maxr << 16, octave, index}
+    int* stRowStart;               // [frame][H + 2] first record of every row bucket
 };
 
 #ifdef __CUDACC__

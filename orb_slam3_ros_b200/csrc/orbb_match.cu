@@ -397,7 +397,55 @@ __device__ __forceinline__ int warp_sum_i(int v) {
     return v;
 }
 
-__global__ void __launch_bounds__(256) k_stereo_match(const Plan* __restrict__ P, Bufs BL, Bufs BR, float mbf, float mb) {
+// Right-image keypoints bucketed by row (counting sort on (int)y, one CTA per frame): the reference's vRowIndices table
+// (Frame.cc:824-838) lists for every row the right keypoints whose band [y - r, y + r] covers it; here a left keypoint
+// scans the buckets of the rows within the largest band radius of its own row and applies the exact band test per
+// candidate.  The candidate set is the same, and the packed (distance, index) minimum does not depend on the visiting order.
+__global__ void __launch_bounds__(256) k_stereo_rows(const Plan* __restrict__ P, Bufs BR) {
+    extern __shared__ int sRow[];                            // [H + 1] counts -> starts, [H + 1] running positions
+    const int frame = blockIdx.x, tid = threadIdx.x;
+    const int H = P->H, nR = BR.outCount[frame * 2];
+    int* cnt = sRow;
+    int* pos = sRow + H + 1;
+    __shared__ int sPart[256];
+    const size_t fo = (size_t)frame * P->kpCap;
+    const orbb_keypoint* kR = BR.kps + fo;
+    for (int i = tid; i <= H; i += 256) cnt[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < nR; i += 256) atomicAdd(&cnt[min(max((int)kR[i].y, 0), H - 1)], 1);
+    __syncthreads();
+    // exclusive scan of cnt[0..H]: each thread owns a contiguous chunk
+    const int chunk = (H + 1 + 255) / 256, c0 = tid * chunk, c1 = min(c0 + chunk, H + 1);
+    int sum = 0;
+    for (int i = c0; i < c1; i++) sum += cnt[i];
+    sPart[tid] = sum;
+    __syncthreads();
+    for (int off = 1; off < 256; off <<= 1) {
+        const int v = tid >= off ? sPart[tid - off] : 0;
+        __syncthreads();
+        sPart[tid] += v;
+        __syncthreads();
+    }
+    int run = sPart[tid] - sum;
+    int* rowStart = BR.stRowStart + (size_t)frame * (H + 2);
+    for (int i = c0; i < c1; i++) {
+        const int c = cnt[i];
+        pos[i] = run;
+        rowStart[i] = run;
+        run += c;
+    }
+    if (tid == 255) rowStart[H + 1] = sPart[255];
+    __syncthreads();
+    for (int i = tid; i < nR; i += 256) {
+        const orbb_keypoint kp = kR[i];
+        const float r = __fmul_rn(2.0f, P->lv[kp.octave].scale);                           // :832
+        const int maxr = (int)ceilf(__fadd_rn(kp.y, r)), minr = (int)floorf(__fsub_rn(kp.y, r));
+        const int slot = atomicAdd(&pos[min(max((int)kp.y, 0), H - 1)], 1);
+        BR.stRec[fo + slot] = make_uint4(__float_as_uint(kp.x), ((unsigned)minr & 0xffffu) | ((unsigned)maxr << 16), (unsigned)kp.octave, (unsigned)i);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_stereo_match(const Plan* __restrict__ P, Bufs BL, Bufs BR, float mbf, float mb, int useRows) {
     const int frame = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int iL = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -425,6 +473,25 @@ __global__ void __launch_bounds__(256) k_stereo_match(const Plan* __restrict__ P
     if (alive) {
         const uint4* dl = reinterpret_cast<const uint4*>(BL.desc + (fo + iL) * 32);
         const uint4 a0 = dl[0], a1 = dl[1];
+        if (useRows) {
+            // row buckets within the largest band radius (+2: the ceil / floor of the band ends) of rowL
+            const int R = (int)ceilf(2.0f * P->lv[P->nlevels - 1].scale) + 2;
+            const int* rowStart = BR.stRowStart + (size_t)frame * (nRows + 2);
+            const int beg = rowStart[max(rowL - R, 0)], end = rowStart[min(rowL + R, nRows - 1) + 1];
+            const uint4* rec = BR.stRec + fo;
+            for (int base = beg; base < end; base += 32) {
+                if (base + lane < end) {
+                    const uint4 rc = __ldg(rec + base + lane);
+                    const int minr = (int)(short)(rc.y & 0xffffu), maxr = (int)rc.y >> 16, oct = (int)rc.z;
+                    const float x = __uint_as_float(rc.x);
+                    if (rowL >= minr && rowL <= maxr && oct >= levelL - 1 && oct <= levelL + 1 && x >= minU && x <= maxU) {
+                        const uint4* dr = reinterpret_cast<const uint4*>(BR.desc + (fo + rc.w) * 32);
+                        const int d = hamming256(a0, a1, dr[0], dr[1]);
+                        if (d < 100) best = min(best, ((unsigned)d << 16) | rc.w);
+                    }
+                }
+            }
+        } else {
         const orbb_keypoint* kR = BR.kps + fo;
         for (int base = 0; base < nR; base += 32) {
             const int iR = base + lane;
@@ -439,6 +506,7 @@ __global__ void __launch_bounds__(256) k_stereo_match(const Plan* __restrict__ P
                     if (d < 100) best = min(best, ((unsigned)d << 16) | (unsigned)iR);
                 }
             }
+        }
         }
     }
 #pragma unroll
@@ -820,7 +888,14 @@ int orbb_stereo_match_batch(orbb_extractor* hL, orbb_extractor* hR, int nframes,
     ORBB_CUDA(hL, cudaEventRecord(ev, hR->stream));
     ORBB_CUDA(hL, cudaStreamWaitEvent(hL->stream, ev, 0));
     ORBB_CUDA(hL, cudaEventDestroy(ev));
-    k_stereo_match<<<dim3((A.kpCap + 7) / 8, nframes), 256, 0, hL->stream>>>(hL->dPlan, hL->b, hR->b, bf, b);
+    // right keypoints bucketed by row (dynamic shared memory: two ints per image row); taller images scan all candidates
+    const size_t rowSmem = (size_t)(A.H + 1) * 2 * sizeof(int);
+    const int useRows = rowSmem <= 40 * 1024 && A.H <= 32767;
+    if (useRows) {
+        k_stereo_rows<<<nframes, 256, rowSmem, hL->stream>>>(hR->dPlan, hR->b);
+        hL->launches++;
+    }
+    k_stereo_match<<<dim3((A.kpCap + 7) / 8, nframes), 256, 0, hL->stream>>>(hL->dPlan, hL->b, hR->b, bf, b, useRows);
     k_stereo_cut<<<nframes, 256, 0, hL->stream>>>(hL->dPlan, hL->b);
     hL->launches += 2;
     ORBB_CUDA(hL, cudaGetLastError());
