@@ -1044,6 +1044,9 @@ static void free_bufs(orbb_extractor* h) {
     memset(&h->b, 0, sizeof h->b);
     h->capacity = 0;
     h->planValid = false;
+    if (h->g1Exec) cudaGraphExecDestroy(h->g1Exec);
+    h->g1Exec = nullptr;
+    h->g1Valid = false;
 }
 
 template <typename T>
@@ -1655,6 +1658,41 @@ int orbb_extract_batch_host_submit(orbb_extractor* h, const uint8_t* host_imgs, 
         h->hImg = nullptr; h->hImgBytes = 0;
         ORBB_CUDA(h, cudaMalloc((void**)&h->hImg, need));
         h->hImgBytes = need;
+    }
+    static const bool noGraph = getenv("ORBB_NO_GRAPH") != nullptr;
+    if (nframes == 1 && !h->profiling && !noGraph) {
+        // ---- latency path: one stream, the kernels of the frame replayed as a CUDA graph ----
+        cudaStream_t st = h->stream;
+        ORBB_CUDA(h, copy_rows(h->hImg, width, host_imgs, row_stride, width, height, cudaMemcpyHostToDevice, st));
+        if (!h->g1Valid || h->g1Lap0 != lap0 || h->g1Lap1 != lap1) {
+            if (h->g1Exec) { cudaGraphExecDestroy(h->g1Exec); h->g1Exec = nullptr; }
+            h->g1Valid = false;
+            cudaGraph_t graph = nullptr;
+            const long long before = h->launches;
+            ORBB_CUDA(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            rc = run_batch(h, h->hImg, 1, (size_t)width, fbytes, lap0, lap1, 0);
+            const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess) return set_err(h, ORBB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+            const cudaError_t ie = cudaGraphInstantiate(&h->g1Exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ie != cudaSuccess) return set_err(h, ORBB_ERR_CUDA, "graph instantiation failed: %s", cudaGetErrorString(ie));
+            h->g1Launches = h->launches - before;
+            h->launches = before;
+            h->g1Lap0 = lap0; h->g1Lap1 = lap1; h->g1Valid = true;
+        }
+        ORBB_CUDA(h, cudaGraphLaunch(h->g1Exec, st));
+        h->launches += h->g1Launches;
+        h->lastFrames = 1;
+        h->hPyrFresh = false;
+        const int ncopy1 = std::min(capacity, P.kpCap);
+        ORBB_CUDA(h, cudaMemcpyAsync(h->hCounts, h->b.outCount, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+        ORBB_CUDA(h, cudaMemcpyAsync(h->hCounts + 2, h->b.status, sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (kps && ncopy1 > 0) ORBB_CUDA(h, cudaMemcpyAsync(kps, h->b.kps, sizeof(orbb_keypoint) * ncopy1, cudaMemcpyDeviceToHost, st));
+        if (desc && ncopy1 > 0) ORBB_CUDA(h, cudaMemcpyAsync(desc, h->b.desc, (size_t)32 * ncopy1, cudaMemcpyDeviceToHost, st));
+        h->pendingFrames = 1;
+        h->pendingCapacity = (kps || desc) ? capacity : INT_MAX;
+        return ORBB_OK;
     }
     // Pipeline in up to 8 chunks of frames: H2D (copy engine 1) -> kernels (handle stream) -> D2H (copy engine 2), so the
     // upload of chunk c+1 and the download of chunk c-1 overlap the kernels of chunk c.

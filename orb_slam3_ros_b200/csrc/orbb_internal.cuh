@@ -175,6 +175,9 @@ struct orbb_extractor {
     int pendingFrames = 0, pendingCapacity = 0;   // orbb_extract_batch_host_submit -> _wait
     long long launches = 0;
     bool profiling = false;
+    // single-frame calls (the SLAM thread's operator()) replay the launch sequence as a CUDA graph: 14 launches + the blur
+    // fork/join cost more host time than the kernels of one frame take
+    cudaGraphExec_t g1Exec = nullptr; int g1Lap0 = 0, g1Lap1 = 0; long long g1Launches = 0; bool g1Valid = false;
     cudaEvent_t ev[orbb::ST_COUNT + 1]{};
     bool evValid = false;
     bool stageRan[orbb::ST_COUNT]{};
