@@ -508,9 +508,13 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const Plan* __restrict__ 
     if (tid < kMaxIni) sSlotCnt[tid] = 0;
     __syncthreads();
     const int n = sN;
-    for (int c = warp; c < nCells; c += OT_WARPS) {
-        const int cnt = cellCount[c], off = cellOff[c];
-        for (int i = lane; i < cnt; i += 32) k0[off + i] = cellKeys[(size_t)c * L.cellCap + i];
+    // one thread per cell: the loads of a cell's keys are independent (read-only path), so their latencies overlap instead
+    // of adding up cell after cell
+    for (int c = tid; c < nCells; c += OT_THREADS) {
+        const int cnt = __ldg(cellCount + c), off = cellOff[c];
+        const u64* src = cellKeys + (size_t)c * L.cellCap;
+#pragma unroll 4
+        for (int i = 0; i < cnt; i++) k0[off + i] = __ldg(src + i);
     }
     __syncthreads();
 
@@ -520,42 +524,50 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const Plan* __restrict__ 
     int rootBuf = 0;
     if (nIni > 1) {
         rootBuf = 1;
-        for (int i = tid; i < n; i += OT_THREADS) {
-            int s = __float2int_rz(__fdiv_rn((float)(int)(k0[i] & 0xffff), hX));
-            atomicAdd(&sSlotCnt[min(s, nIni - 1)], 1);
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int acc = 0;
-            for (int s = 0; s < nIni; s++) { sSlotStart[s] = acc; acc += sSlotCnt[s]; }
-        }
-        __syncthreads();
-        int runSlot[kMaxIni];
+        // each warp owns a contiguous quarter of the keys: count per root, then write in order behind the warps before it
+        const int seg = (n + OT_WARPS - 1) / OT_WARPS, s0 = min(warp * seg, n), s1 = min(s0 + seg, n);
+        int cntS[kMaxIni];
 #pragma unroll
-        for (int s = 0; s < kMaxIni; s++) runSlot[s] = 0;
-        for (int base = 0; base < n; base += OT_THREADS) {
-            const int i = base + tid;
-            const bool valid = i < n;
+        for (int s = 0; s < kMaxIni; s++) cntS[s] = 0;
+        for (int base = s0; base < s1; base += 32) {
+            const int i = base + lane;
+            const int slot = i < s1 ? min(__float2int_rz(__fdiv_rn((float)(int)(k0[i] & 0xffff), hX)), nIni - 1) : -1;
+#pragma unroll
+            for (int s = 0; s < kMaxIni; s++)
+                if (s < nIni) cntS[s] += __popc(__ballot_sync(0xffffffffu, slot == s));
+        }
+#pragma unroll
+        for (int s = 0; s < kMaxIni; s++)
+            if (s < nIni && lane == 0) sWarpSlot[warp][s] = cntS[s];
+        __syncthreads();
+        int dstS[kMaxIni];                                   // first output position of this warp's keys of root s
+        {
+            int acc = 0;
+#pragma unroll
+            for (int s = 0; s < kMaxIni; s++) {
+                dstS[s] = 0;
+                if (s < nIni) {
+                    int tot = 0, before = 0;
+                    for (int w = 0; w < OT_WARPS; w++) { const int v = sWarpSlot[w][s]; tot += v; if (w < warp) before += v; }
+                    dstS[s] = acc + before;
+                    if (tid == 0) { sSlotStart[s] = acc; sSlotCnt[s] = tot; }
+                    acc += tot;
+                }
+            }
+        }
+        for (int base = s0; base < s1; base += 32) {
+            const int i = base + lane;
+            const bool valid = i < s1;
             const u64 k = valid ? k0[i] : 0;
             const int slot = valid ? min(__float2int_rz(__fdiv_rn((float)(int)(k & 0xffff), hX)), nIni - 1) : -1;
-            int myRank = 0;
-            for (int s = 0; s < nIni; s++) {
-                const unsigned bal = __ballot_sync(0xffffffffu, slot == s);
-                if (lane == 0) sWarpSlot[warp][s] = __popc(bal);
-                if (slot == s) myRank = __popc(bal & ((1u << lane) - 1));
+#pragma unroll
+            for (int s = 0; s < kMaxIni; s++) {
+                if (s < nIni) {
+                    const unsigned bal = __ballot_sync(0xffffffffu, slot == s);
+                    if (slot == s) k1[dstS[s] + __popc(bal & ((1u << lane) - 1))] = k;
+                    dstS[s] += __popc(bal);
+                }
             }
-            __syncthreads();
-            if (valid) {
-                int woff = 0;
-                for (int w = 0; w < warp; w++) woff += sWarpSlot[w][slot];
-                k1[sSlotStart[slot] + runSlot[slot] + woff + myRank] = k;
-            }
-            for (int s = 0; s < nIni; s++) {
-                int tot = 0;
-                for (int w = 0; w < OT_WARPS; w++) tot += sWarpSlot[w][s];
-                runSlot[s] += tot;
-            }
-            __syncthreads();
         }
     } else if (tid == 0) {
         sSlotCnt[0] = n;
