@@ -11,6 +11,10 @@
 // Record layout: key = rec >> ORBB_SORT_PAYLOAD_BITS (compared), low bits = payload (moved along, never compared).
 #pragma once
 #include <stdint.h>
+#ifndef __CUDACC__
+#include <algorithm>
+#include <vector>
+#endif
 typedef unsigned long long orbb_rec_t;
 
 #ifdef __CUDACC__
@@ -172,5 +176,63 @@ ORBB_HD void std_sort_emul(orbb_rec_t* a, int n) {
         insertion_sort(a, 0, n);
     }
 }
+
+
+// ---- parallel formulation ------------------------------------------------------------------------------------------
+// The same arrangement as std_sort_emul, restated so that the work inside one step is order-free (the device version,
+// sort_emul_cta in orbb_extract.cu, executes each step with a warp / the CTA; this host restatement is what
+// tests/test_introsort_model.py checks against the real std::sort):
+//  * __unguarded_partition(first+1, last, pivot at first): let l_1 < l_2 < ... be the positions in [first+1, last) whose
+//    element is NOT less than the pivot and r_1 > r_2 > ... the positions in [first, last) whose element is NOT greater.
+//    The sequential two-pointer loop swaps exactly the pairs (l_k, r_k) with l_k < r_k, k = 1..K -- positions between
+//    l_k and r_k are untouched when the pointers pass them -- and returns cut = min(l_{K+1}, r_K): after K swaps the
+//    upward scan stops at the next original l or at r_K, which now holds an element >= pivot.
+//  * the ranges left by __introsort_loop are disjoint, so the order in which they are partitioned is irrelevant.
+//  * __final_insertion_sort is a stable insertion sort of the whole array; since everything left of a cut is <= everything
+//    right of it and an element only moves past STRICTLY greater ones, it permutes only inside the leaf ranges
+//    (<= 16 elements) -- one independent insertion sort per leaf range.  Ranges finished by the heapsort fallback are
+//    already sorted and stay as they are.
+#ifndef __CUDACC__
+inline void std_sort_emul_pf(orbb_rec_t* a, int n) {
+    if (n <= 1) return;
+    const int kThreshold = 16, INF = 0x7fffffff;
+    int lg = 0;
+    for (int t = n; t > 1; t >>= 1) lg++;
+    std::vector<int> stF, stL, stD, leafF, leafL, L, R;
+    stF.push_back(0); stL.push_back(n); stD.push_back(2 * lg);
+    while (!stF.empty()) {
+        int first = stF.back(), last = stL.back(), depth = stD.back();
+        stF.pop_back(); stL.pop_back(); stD.pop_back();
+        bool heap = false;
+        while (last - first > kThreshold) {
+            if (depth == 0) { heap_sort_range(a, first, last); heap = true; break; }
+            --depth;
+            const int mid = first + (last - first) / 2;
+            {
+                const int x = first + 1, y = mid, z = last - 1;
+                if (rec_less(a[x], a[y])) {
+                    if (rec_less(a[y], a[z])) rec_swap(a, first, y);
+                    else if (rec_less(a[x], a[z])) rec_swap(a, first, z);
+                    else rec_swap(a, first, x);
+                } else if (rec_less(a[x], a[z])) rec_swap(a, first, x);
+                else if (rec_less(a[y], a[z])) rec_swap(a, first, z);
+                else rec_swap(a, first, y);
+            }
+            const orbb_rec_t pivot = a[first];
+            L.clear(); R.clear();
+            for (int p = first + 1; p < last; p++) if (!rec_less(a[p], pivot)) L.push_back(p);
+            for (int p = last - 1; p >= first; p--) if (!rec_less(pivot, a[p])) R.push_back(p);
+            int K = 0;
+            for (size_t k = 0; k < L.size() && k < R.size(); k++) K += L[k] < R[k];
+            for (int k = 0; k < K; k++) rec_swap(a, L[k], R[k]);            // simultaneous: all positions distinct
+            const int cut = std::min(K < (int)L.size() ? L[K] : INF, K > 0 ? R[K - 1] : INF);
+            stF.push_back(cut); stL.push_back(last); stD.push_back(depth);
+            last = cut;
+        }
+        if (!heap) { leafF.push_back(first); leafL.push_back(last); }
+    }
+    for (size_t s = 0; s < leafF.size(); s++) insertion_sort(a, leafF[s], leafL[s]);      // independent of each other
+}
+#endif
 
 }  // namespace orbb

@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(256) k_fast_v0(const Plan* __restrict__ P, Buf
 // ------------------------------------------------------------------------------------------------
 constexpr int OT_THREADS = 128;
 constexpr int OT_WARPS = OT_THREADS / 32;
-constexpr int OT_SORT_SMEM = 2048;
+constexpr int OT_SORT_SMEM = 1024;
 
 __device__ __forceinline__ int node_count(const QNode& n) { return n.cntbuf & 0x7fffffff; }
 __device__ __forceinline__ int node_buf(const QNode& n) { return (unsigned)n.cntbuf >> 31; }
@@ -465,6 +465,86 @@ __device__ __forceinline__ void emit_children(const QNode& p, const int4 c, int 
 __device__ __forceinline__ int nonempty4(const int4 c) { return (c.x > 0) + (c.y > 0) + (c.z > 0) + (c.w > 0); }
 __device__ __forceinline__ int multi4(const int4 c) { return (c.x > 1) + (c.y > 1) + (c.z > 1) + (c.w > 1); }
 
+// std::sort(a, a + n, compareNodes) by the whole CTA: the parallel formulation of introsort.cuh (std_sort_emul_pf is its
+// host restatement, checked against the real std::sort).  Warp 0 runs the partition steps -- the positions l_k / r_k that
+// the sequential two-pointer loop would stop at are listed with ballots, the K swaps happen at once -- and collects the
+// leaf ranges; then one thread per leaf range does its insertion sort.  Lp, Rp: int[n]; leaf: unsigned[n]; stk: int[192].
+__device__ void sort_emul_cta(u64* a, int n, int* Lp, int* Rp, unsigned* leaf, int* stk, int* sNLeaf, int tid) {
+    if (n <= 1) return;                                     // (uniform)
+    const int lane = tid & 31;
+    if (tid < 32) {
+        const int INF = 0x7fffffff;
+        const unsigned lt = (1u << lane) - 1;
+        int lg = 0;
+        for (int t = n; t > 1; t >>= 1) lg++;
+        int sp = 0, nLeaf = 0, first = 0, last = n, depth = 2 * lg;
+        while (true) {
+            bool heap = false;
+            while (last - first > 16) {
+                if (depth == 0) {                           // depth limit: heapsort of the range, serial (adversarial inputs only)
+                    if (lane == 0) heap_sort_range(a, first, last);
+                    __syncwarp();
+                    heap = true;
+                    break;
+                }
+                --depth;
+                if (lane == 0) {                            // std::__move_median_to_first(first, first+1, mid, last-1)
+                    const int x = first + 1, y = first + (last - first) / 2, z = last - 1;
+                    if (rec_less(a[x], a[y])) {
+                        if (rec_less(a[y], a[z])) rec_swap(a, first, y);
+                        else if (rec_less(a[x], a[z])) rec_swap(a, first, z);
+                        else rec_swap(a, first, x);
+                    } else if (rec_less(a[x], a[z])) rec_swap(a, first, x);
+                    else if (rec_less(a[y], a[z])) rec_swap(a, first, z);
+                    else rec_swap(a, first, y);
+                }
+                __syncwarp();
+                const u64 pk = a[first] >> ORBB_SORT_PAYLOAD_BITS;
+                int nl = 0, nr = 0;
+                for (int base = first + 1; base < last; base += 32) {
+                    const int p = base + lane;
+                    const bool f = p < last && !((a[min(p, last - 1)] >> ORBB_SORT_PAYLOAD_BITS) < pk);
+                    const unsigned bal = __ballot_sync(0xffffffffu, f);
+                    if (f) Lp[nl + __popc(bal & lt)] = p;
+                    nl += __popc(bal);
+                }
+                for (int base = last - 1; base >= first; base -= 32) {
+                    const int p = base - lane;
+                    const bool f = p >= first && !(pk < (a[max(p, first)] >> ORBB_SORT_PAYLOAD_BITS));
+                    const unsigned bal = __ballot_sync(0xffffffffu, f);
+                    if (f) Rp[nr + __popc(bal & lt)] = p;
+                    nr += __popc(bal);
+                }
+                __syncwarp();
+                const int m = min(nl, nr);
+                int K = 0;
+                for (int base = 0; base < m; base += 32) {
+                    const int k = base + lane;
+                    K += __popc(__ballot_sync(0xffffffffu, k < m && Lp[k] < Rp[k]));
+                }
+                for (int k = lane; k < K; k += 32) rec_swap(a, Lp[k], Rp[k]);
+                const int cut = min(K < nl ? Lp[K] : INF, K > 0 ? Rp[K - 1] : INF);
+                __syncwarp();
+                if (lane == 0) { stk[3 * sp] = cut; stk[3 * sp + 1] = last; stk[3 * sp + 2] = depth; }
+                sp++;
+                last = cut;
+            }
+            if (!heap) {
+                if (lane == 0) leaf[nLeaf] = (unsigned)first | ((unsigned)last << 16);
+                nLeaf++;
+            }
+            if (sp == 0) break;
+            sp--;
+            __syncwarp();
+            first = stk[3 * sp]; last = stk[3 * sp + 1]; depth = stk[3 * sp + 2];
+        }
+        if (lane == 0) *sNLeaf = nLeaf;
+    }
+    __syncthreads();
+    const int nLeaf = *sNLeaf;
+    for (int s = tid; s < nLeaf; s += OT_THREADS) insertion_sort(a, (int)(leaf[s] & 0xffffu), (int)(leaf[s] >> 16));
+}
+
 __global__ void __launch_bounds__(OT_THREADS) k_octree(const Plan* __restrict__ P, Bufs B) {
     // grid = (frames, levels): CTAs are dispatched x-fastest, so the long-running low levels of ALL frames start first and
     // the short high levels fill the tail
@@ -491,6 +571,8 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const Plan* __restrict__ 
     __shared__ int sSlotCnt[kMaxIni], sSlotStart[kMaxIni];
     __shared__ int sWarpSlot[OT_WARPS][kMaxIni];
     __shared__ u64 sRec[OT_SORT_SMEM];
+    __shared__ int sSortL[OT_SORT_SMEM], sSortR[OT_SORT_SMEM], sSortStk[192], sSortLeaves;
+    __shared__ unsigned sSortLeaf[OT_SORT_SMEM];
 
     // ---- 1. gather vToDistributeKeys in the reference's order: cell-row-major, raster inside the cell ----
     const int nCells = L.nCols * L.nRows;
@@ -675,7 +757,12 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const Plan* __restrict__ 
                     srt[e] = ((u64)(unsigned)node_count(nd) << 40) | ((u64)(unsigned short)nd.x0 << 24) | (u64)(unsigned)idx;
             }
             __syncthreads();
-            if (tid == 0) std_sort_emul(srt, len);                  // std::sort(..., compareNodes) :700
+            // std::sort(..., compareNodes) :700
+            if (len <= OT_SORT_SMEM) sort_emul_cta(srt, len, sSortL, sSortR, sSortLeaf, sSortStk, &sSortLeaves, tid);
+            else {
+                int* tmp = B.sortTmp + (size_t)frame * 3 * P->nodeStride + 3 * (size_t)L.nodeBase;
+                sort_emul_cta(srt, len, tmp, tmp + L.maxNodes, reinterpret_cast<unsigned*>(tmp + 2 * L.maxNodes), sSortStk, &sSortLeaves, tid);
+            }
             __syncthreads();
             if (warp == 0) {
                 // processing order i = 0..len-1 is the sorted vector walked from the back (:701)
@@ -1238,6 +1325,7 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
     A(b.pend, F * 2 * nodes);
     A(b.elist, F * nodes);
     A(b.erased, F * nodes);
+    A(b.sortTmp, F * 3 * nodes);
     A(b.sel, F * sel);
     A(b.selCount, F * ORBB_MAX_LEVELS);
     A(b.work, F * kpCap);
@@ -1283,7 +1371,7 @@ static Bufs shift_bufs(const Bufs& b, const Plan& P, int f0) {
     s.cellCount += f * P.cellsTotal; s.cellOff += f * P.cellsTotal; s.fbList += f * P.cellsTotal; s.fbCount += f;
     s.cellKeys += f * P.cellKeyStride; s.keys += f * 2 * P.rawStride; s.nodes += f * 2 * P.nodeStride;
     s.rec += f * P.nodeStride; s.cnt4 += f * P.nodeStride; s.pend += f * 2 * P.nodeStride; s.elist += f * P.nodeStride;
-    s.erased += f * P.nodeStride; s.sel += f * P.selStride; s.selCount += f * ORBB_MAX_LEVELS;
+    s.erased += f * P.nodeStride; s.sortTmp += f * 3 * P.nodeStride; s.sel += f * P.selStride; s.selCount += f * ORBB_MAX_LEVELS;
     s.work += f * P.kpCap; s.kps += f * P.kpCap; s.desc += f * P.kpCap * 32; s.outCount += f * 2; s.status += f;
     s.uRight += f * P.kpCap; s.depth += f * P.kpCap; s.bestR += f * P.kpCap; s.sad += f * P.kpCap;
     s.stRec += f * P.kpCap; s.stRowStart += f * (P.H + 2);

@@ -99,6 +99,7 @@ struct Bufs {
     int* pend;                     // [frame][2][nodeStride]
     int* elist;                    // [frame][nodeStride]
     uint8_t* erased;               // [frame][nodeStride]
+    int* sortTmp;                  // [frame][3][nodeStride] scratch of the parallel std::sort emulation (large levels)
     u64* sel;                      // [frame][selStride] selected keys (level coordinates)
     int* selCount;                 // [frame][ORBB_MAX_LEVELS]
     WorkItem* work;                // [frame][kpCap]

@@ -18,6 +18,15 @@ void model_sort_nodes(const int* sizes, const int* x0s, int n, int* perm) {
     for (int i = 0; i < n; i++) perm[i] = (int)(v[i] & 0xFFFFFF);
 }
 
+// the same through the parallel formulation (std_sort_emul_pf) that the CUDA kernel follows
+void model_sort_nodes_pf(const int* sizes, const int* x0s, int n, int* perm) {
+    std::vector<orbb_rec_t> v(n);
+    for (int i = 0; i < n; i++)
+        v[i] = ((orbb_rec_t)(uint32_t)sizes[i] << 40) | ((orbb_rec_t)(uint16_t)x0s[i] << 24) | (orbb_rec_t)i;
+    orbb::std_sort_emul_pf(v.data(), n);
+    for (int i = 0; i < n; i++) perm[i] = (int)(v[i] & 0xFFFFFF);
+}
+
 // McIlroy's "A Killer Adversary for Quicksort": builds the key sequence that drives THIS libstdc++ std::sort
 // into its depth-limit (heapsort) fallback.  Output: keys[n] (distinct ints).
 static int g_nsolid, g_candidate, g_gas;

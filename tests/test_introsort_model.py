@@ -24,14 +24,19 @@ def model():
     lib = C.CDLL(str(so))
     lib.model_sort_nodes.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.model_killer_sequence.argtypes = [C.c_int, C.c_void_p]
+    lib.model_sort_nodes_pf.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     return lib
 
 
 def _model_sort(lib, sizes, x0s):
+    """serial emulation; the parallel formulation (what the CUDA kernel executes) must give the same arrangement"""
     sizes = np.ascontiguousarray(sizes, np.int32)
     x0s = np.ascontiguousarray(x0s, np.int32)
     perm = np.zeros(len(sizes), np.int32)
     lib.model_sort_nodes(sizes.ctypes.data, x0s.ctypes.data, len(sizes), perm.ctypes.data)
+    perm_pf = np.zeros(len(sizes), np.int32)
+    lib.model_sort_nodes_pf(sizes.ctypes.data, x0s.ctypes.data, len(sizes), perm_pf.ctypes.data)
+    assert np.array_equal(perm, perm_pf), "parallel formulation differs from the serial emulation"
     return perm
 
 
