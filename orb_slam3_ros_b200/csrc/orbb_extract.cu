@@ -1794,10 +1794,10 @@ int orbb_extract_batch_host_submit(orbb_extractor* h, const uint8_t* host_imgs, 
         h->pendingCapacity = (kps || desc) ? capacity : INT_MAX;
         return ORBB_OK;
     }
-    // Pipeline in up to 8 chunks of frames: H2D (copy engine 1) -> kernels (handle stream) -> D2H (copy engine 2), so the
+    // Pipeline in chunks of frames (2 by default, up to 8 with ORBB_CHUNKS): H2D (copy engine 1) -> kernels (handle stream) -> D2H (copy engine 2), so the
     // upload of chunk c+1 and the download of chunk c-1 overlap the kernels of chunk c.
     static const int chunkOverride = getenv("ORBB_CHUNKS") ? atoi(getenv("ORBB_CHUNKS")) : 0;
-    const int nchunks = chunkOverride > 0 ? std::min(std::min(chunkOverride, 8), nframes) : (nframes >= 64 ? 3 : (nframes >= 8 ? 2 : 1));
+    const int nchunks = chunkOverride > 0 ? std::min(std::min(chunkOverride, 8), nframes) : (nframes >= 8 ? 2 : 1);      // measured: 2 chunks 127.7k frames/s end to end, 1: 122k, 3: 121k, 4: 118k
     const int per = (nframes + nchunks - 1) / nchunks;
     const int ncopy = std::min(capacity, P.kpCap);
     ORBB_CUDA(h, cudaEventRecord(h->evDone[0], h->stream));                  // earlier work on the handle's stream ...
