@@ -24,6 +24,9 @@
  *   orbb_search_area_best2          Frame::GetFeaturesInArea + SearchByProjection scan   orb_slam3/src/Frame.cc:657-723, ORBmatcher.cc:71-120 ("next" row)
  *   orbb_distinctive_csr            MapPoint::ComputeDistinctiveDescriptors   orb_slam3/src/MapPoint.cc:329-403   ("next" row)
  *   orbb_extract_color / _batch_color   cv::cvtColor(..., COLOR_*2GRAY) + extraction   orb_slam3/src/Tracking.cc:1498-1525, :1605-1618 ("next" row)
+ *   orbb_rectifier_* / orbb_remap / orbb_extract_rectified / _batch_rectified   cv::remap(img, M1, M2, INTER_LINEAR) before tracking
+ *                                   orb_slam3/src/System.cc:233-240, maps from orb_slam3/src/Settings.cc:506-509   ("next" row)
+ *   orbb_undistort_points           Frame::UndistortKeyPoints (cv::undistortPoints)   orb_slam3/src/Frame.cc:747-780   ("next" row)
  *
  * Threading: one thread per handle at a time; distinct handles are independent (own stream, own workspace).
  * Errors: every function returns ORBB_OK (0) or a negative code; orbb_last_error() gives the text.
@@ -226,6 +229,29 @@ long long orbb_vocab_launch_count(const orbb_vocab* v);
  *   counts[3s+2]       features with a positive word weight ("not stopped") */
 int orbb_bow_transform(orbb_vocab* v, const uint8_t* desc, const int32_t* rowptr, int nsets, int levelsup, int norm, int32_t* bow_id,
                        double* bow_val, int32_t* fv_node, int32_t* fv_start, int32_t* fv_feat, int32_t* counts);
+
+/* ---- stereo rectification ("next" row) ---------------------------------------------------------------------------- */
+/* cv::remap(src, dst, map_x, map_y, cv::INTER_LINEAR) for 8-bit single-channel images with CV_32FC1 maps (what
+ * cv::initUndistortRectifyMap(..., CV_32F, M1, M2) returns, Settings.cc:506-509) and the default constant (0) border.  The
+ * maps are converted to OpenCV's fixed-point form once, at creation.  map_stride is in floats. */
+typedef struct orbb_rectifier orbb_rectifier;
+int orbb_rectifier_create(int device, const float* map_x, const float* map_y, size_t map_stride, int dst_width, int dst_height,
+                          int src_width, int src_height, orbb_rectifier** out);
+void orbb_rectifier_destroy(orbb_rectifier* r);
+/* one host frame in, the rectified host frame out (System.cc:239) */
+int orbb_remap(orbb_rectifier* r, const uint8_t* src, size_t src_stride, uint8_t* dst, size_t dst_stride);
+/* rectification + extraction without the rectified image leaving the device: batch of device-resident raw frames
+ * (asynchronous, results via orbb_batch_fetch) / one host frame (synchronous) */
+int orbb_extract_batch_rectified(orbb_extractor* h, orbb_rectifier* r, const uint8_t* dev_imgs, int nframes, size_t row_stride,
+                                 size_t frame_stride, int lap0, int lap1);
+int orbb_extract_rectified(orbb_extractor* h, orbb_rectifier* r, const uint8_t* img, size_t stride, int lap0, int lap1, orbb_keypoint* kps,
+                           uint8_t* desc, int capacity, int* n_out, int* mono_index);
+
+/* ---- Frame::UndistortKeyPoints ("next" row) ------------------------------------------------------------------------- */
+/* cv::undistortPoints(xy, out, K, dist, noArray(), newK) for n points (Frame.cc:766: newK = K).  K4 / newK4 = {fx, fy, cx, cy};
+ * dist = ndist (0..12) coefficients k1 k2 p1 p2 [k3 [k4 k5 k6 [s1 s2 s3 s4]]].  dist[0] == 0 copies the input (Frame.cc:749). */
+int orbb_undistort_points(orbb_matcher* m, const float* xy, int n, const float* K4, const float* dist, int ndist, const float* newK4,
+                          float* out_xy);
 
 /* pinned host memory helpers (so callers without a CUDA runtime can stage asynchronously) */
 void* orbb_host_alloc(size_t bytes);

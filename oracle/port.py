@@ -334,3 +334,61 @@ def stereo(ext_l, ext_r, kps_l, desc_l, kps_r, desc_r, bf, b):
     kept = lib().port_stereo(ext_l._h, ext_r._h, _ptr(kl), _ptr(dl), n, _ptr(kr), _ptr(dr), len(kr), bf, b, _ptr(ur),
                              _ptr(dp), _ptr(br), _ptr(sad))
     return ur, dp, br, sad, kept
+
+
+# ---- input side ("next" rows): stereo rectification and keypoint undistortion -------------------------------------------
+def remap_linear(src, map_x, map_y):
+    """cv::remap(src, dst, map_x, map_y, cv::INTER_LINEAR) for uint8 single-channel images, CV_32FC1 maps, constant (0)
+    border (reference System.cc:239-240).  Restatement of OpenCV's RemapInvoker + remapBilinear (imgproc/imgwarp.cpp):
+    maps to fixed point with cvRound(m * 32); weights BilinearTab_i (shorts, (0,0) entry = {32767,0,0,1} after the
+    table's saturation + sum fix-up); (sum + 2^14) >> 15.  Pinned to cv2.remap by tests/test_oracle_primitives.py."""
+    src = np.ascontiguousarray(src, np.uint8)
+    H, W = src.shape
+    sx = np.rint(np.asarray(map_x, np.float32) * np.float32(32)).astype(np.int64)
+    sy = np.rint(np.asarray(map_y, np.float32) * np.float32(32)).astype(np.int64)
+    ix, iy = np.clip(sx >> 5, -32768, 32767), np.clip(sy >> 5, -32768, 32767)
+    fx, fy = sx & 31, sy & 31
+    w = [(32 - fy) * (32 - fx) * 32, (32 - fy) * fx * 32, fy * (32 - fx) * 32, fy * fx * 32]
+    zero = (fx == 0) & (fy == 0)
+    w[0] = np.where(zero, 32767, w[0])
+    w[3] = np.where(zero, 1, w[3])
+
+    def tap(y, x):
+        ok = (x >= 0) & (x < W) & (y >= 0) & (y < H)
+        return np.where(ok, src[np.clip(y, 0, H - 1), np.clip(x, 0, W - 1)].astype(np.int64), 0)
+
+    acc = tap(iy, ix) * w[0] + tap(iy, ix + 1) * w[1] + tap(iy + 1, ix) * w[2] + tap(iy + 1, ix + 1) * w[3]
+    return ((acc + (1 << 14)) >> 15).astype(np.uint8)
+
+
+def undistort_points(xy, K4, dist, new_K4=None):
+    """cv::undistortPoints(xy, out, K, dist, noArray(), newK) as Frame::UndistortKeyPoints calls it (Frame.cc:747-780):
+    cvUndistortPointsInternal with the default criteria (5 iterations), double precision, un-fused; float32 result.
+    K4 = (fx, fy, cx, cy); dist = k1 k2 p1 p2 [k3 ...].  Pinned to cv2.undistortPoints by tests/test_oracle_primitives.py."""
+    xy = np.asarray(xy, np.float32).reshape(-1, 2)
+    dist = np.asarray(dist, np.float32).ravel()
+    if len(dist) == 0 or dist[0] == 0.0:                      # Frame.cc:749-753
+        return xy.copy()
+    new_K4 = K4 if new_K4 is None else new_K4
+    fx, fy, cx, cy = [np.float64(np.float32(v)) for v in K4]
+    nfx, nfy, ncx, ncy = [np.float64(np.float32(v)) for v in new_K4]
+    k = np.zeros(12, np.float64)
+    k[:len(dist)] = dist.astype(np.float64)
+    u, v = xy[:, 0].astype(np.float64), xy[:, 1].astype(np.float64)
+    ifx, ify = np.float64(1.) / fx, np.float64(1.) / fy
+    x, y = (u - cx) * ifx, (v - cy) * ify
+    x0, y0 = x.copy(), y.copy()
+    live = np.ones(len(x), bool)
+    for _ in range(5):
+        r2 = x * x + y * y
+        icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2)
+        neg = live & (icdist < 0)
+        dx = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2
+        dy = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2
+        nx, ny = (x0 - dx) * icdist, (y0 - dy) * icdist
+        upd = live & ~neg
+        x, y = np.where(upd, nx, x), np.where(upd, ny, y)
+        x, y = np.where(neg, (u - cx) * ifx, x), np.where(neg, (v - cy) * ify, y)
+        live &= ~neg
+    xx, yy, ww = nfx * x + 0. * y + ncx, 0. * x + nfy * y + ncy, 1. / (0. * x + 0. * y + 1.)
+    return np.stack([(xx * ww).astype(np.float32), (yy * ww).astype(np.float32)], 1)

@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(256) k_pyr_apron(const Plan* __restrict__ P, B
 }
 
 #include "orbb_pyr.cuh"
+#include "orbb_rectify.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // K5a: GaussianBlur 7x7 sigma 2, OpenCV's 8.8 fixed-point path: taps {18,34,48,56,48,34,18}/256, horizontal pass
@@ -1967,5 +1968,113 @@ void* orbb_host_alloc(size_t bytes) {
     return p;
 }
 void orbb_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ---- rectification ("next" row): cv::remap with the maps of cv::initUndistortRectifyMap, then extraction -------------
+struct orbb_rectifier {
+    int device = 0;
+    int dw = 0, dh = 0, sw = 0, sh = 0;
+    uint2* map = nullptr;                 // [dh][dw] {sx | sy << 16, a}
+    uint8_t* dSrc = nullptr; size_t srcBytes = 0;      // staging of one host source frame
+    uint8_t* dDst = nullptr; size_t dstBytes = 0;
+    cudaStream_t stream = nullptr;
+};
+
+int orbb_rectifier_create(int device, const float* map_x, const float* map_y, size_t map_stride, int dst_width, int dst_height,
+                          int src_width, int src_height, orbb_rectifier** out) {
+    if (!out || !map_x || !map_y || dst_width <= 0 || dst_height <= 0 || src_width <= 0 || src_height <= 0 || map_stride < (size_t)dst_width)
+        return set_err(nullptr, ORBB_ERR_ARG, "bad rectifier arguments");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return set_err(nullptr, ORBB_ERR_CUDA, "no CUDA device (%s): liborbb200 has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return set_err(nullptr, ORBB_ERR_ARG, "device %d out of range", device);
+    // RemapInvoker's float -> fixed-point map conversion (imgwarp.cpp), done once
+    std::vector<uint2> fixed((size_t)dst_width * dst_height);
+    for (int y = 0; y < dst_height; y++)
+        for (int x = 0; x < dst_width; x++) {
+            const int sx = cv_round_f(map_x[(size_t)y * map_stride + x] * 32.f), sy = cv_round_f(map_y[(size_t)y * map_stride + x] * 32.f);
+            const int ix = std::min(std::max(sx >> 5, -32768), 32767), iy = std::min(std::max(sy >> 5, -32768), 32767);      // saturate_cast<short>
+            fixed[(size_t)y * dst_width + x] = make_uint2((unsigned)(ix & 0xffff) | ((unsigned)(iy & 0xffff) << 16), (unsigned)((sy & 31) * 32 + (sx & 31)));
+        }
+    orbb_rectifier* r = new orbb_rectifier();
+    r->device = device; r->dw = dst_width; r->dh = dst_height; r->sw = src_width; r->sh = src_height;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc((void**)&r->map, fixed.size() * sizeof(uint2)) != cudaSuccess ||
+        cudaMemcpy(r->map, fixed.data(), fixed.size() * sizeof(uint2), cudaMemcpyHostToDevice) != cudaSuccess) {
+        const cudaError_t le = cudaGetLastError();
+        orbb_rectifier_destroy(r);
+        return set_err(nullptr, ORBB_ERR_CUDA, "rectifier setup failed: %s", cudaGetErrorString(le));
+    }
+    *out = r;
+    return ORBB_OK;
+}
+
+void orbb_rectifier_destroy(orbb_rectifier* r) {
+    if (!r) return;
+    cudaSetDevice(r->device);
+    if (r->stream) { cudaStreamSynchronize(r->stream); cudaStreamDestroy(r->stream); }
+    cudaFree(r->map); cudaFree(r->dSrc); cudaFree(r->dDst);
+    delete r;
+}
+
+static void launch_remap(const orbb_rectifier* r, const uint8_t* dSrc, size_t srcStride, size_t srcFrameStride, uint8_t* dDst, size_t dstStride,
+                         size_t dstFrameStride, int nframes, cudaStream_t st) {
+    dim3 grid(((r->dw + 3) / 4 + 31) / 32, (r->dh + 7) / 8, nframes);
+    k_remap<<<grid, 256, 0, st>>>(r->map, dSrc, srcStride, srcFrameStride, r->sw, r->sh, dDst, dstStride, dstFrameStride, r->dw, r->dh);
+}
+
+int orbb_remap(orbb_rectifier* r, const uint8_t* src, size_t src_stride, uint8_t* dst, size_t dst_stride) {
+    if (!r || !src || !dst || src_stride < (size_t)r->sw || dst_stride < (size_t)r->dw) return set_err(nullptr, ORBB_ERR_ARG, "bad remap arguments");
+    if (cudaSetDevice(r->device) != cudaSuccess) return set_err(nullptr, ORBB_ERR_CUDA, "cudaSetDevice failed");
+    const size_t sb = (size_t)r->sw * r->sh, db = (size_t)r->dw * r->dh;
+    if (r->srcBytes < sb) { cudaFree(r->dSrc); r->dSrc = nullptr; r->srcBytes = 0; if (cudaMalloc((void**)&r->dSrc, sb) != cudaSuccess) return set_err(nullptr, ORBB_ERR_CUDA, "out of device memory"); r->srcBytes = sb; }
+    if (r->dstBytes < db) { cudaFree(r->dDst); r->dDst = nullptr; r->dstBytes = 0; if (cudaMalloc((void**)&r->dDst, db) != cudaSuccess) return set_err(nullptr, ORBB_ERR_CUDA, "out of device memory"); r->dstBytes = db; }
+    cudaError_t e = cudaMemcpy2DAsync(r->dSrc, r->sw, src, src_stride, r->sw, r->sh, cudaMemcpyHostToDevice, r->stream);
+    if (e == cudaSuccess) {
+        launch_remap(r, r->dSrc, r->sw, sb, r->dDst, r->dw, db, 1, r->stream);
+        e = cudaMemcpy2DAsync(dst, dst_stride, r->dDst, r->dw, r->dw, r->dh, cudaMemcpyDeviceToHost, r->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(r->stream);
+    if (e != cudaSuccess) return set_err(nullptr, ORBB_ERR_CUDA, "remap failed: %s", cudaGetErrorString(e));
+    return ORBB_OK;
+}
+
+int orbb_extract_batch_rectified(orbb_extractor* h, orbb_rectifier* r, const uint8_t* dev_imgs, int nframes, size_t row_stride,
+                                 size_t frame_stride, int lap0, int lap1) {
+    if (!h || !r) return ORBB_ERR_ARG;
+    if (!dev_imgs || nframes <= 0) return set_err(h, ORBB_ERR_EMPTY, "empty image");
+    if (r->device != h->device) return set_err(h, ORBB_ERR_ARG, "rectifier and extractor live on different devices");
+    ORBB_CUDA(h, cudaSetDevice(h->device));
+    int rc = ensure_plan(h, r->dw, r->dh, nframes);
+    if (rc) return rc;
+    if ((rc = ensure_staging(h, (size_t)nframes * r->dw * r->dh))) return rc;
+    launch_remap(r, dev_imgs, row_stride, frame_stride, h->hImg, (size_t)r->dw, (size_t)r->dw * r->dh, nframes, h->stream);
+    h->launches++;
+    return run_batch(h, h->hImg, nframes, (size_t)r->dw, (size_t)r->dw * r->dh, lap0, lap1);
+}
+
+int orbb_extract_rectified(orbb_extractor* h, orbb_rectifier* r, const uint8_t* img, size_t stride, int lap0, int lap1, orbb_keypoint* kps,
+                           uint8_t* desc, int capacity, int* n_out, int* mono_index) {
+    if (!h || !r) return ORBB_ERR_ARG;
+    if (n_out) *n_out = 0;
+    if (mono_index) *mono_index = 0;
+    if (!img) return set_err(h, ORBB_ERR_EMPTY, "empty image");
+    ORBB_CUDA(h, cudaSetDevice(h->device));
+    const size_t sb = (size_t)r->sw * r->sh;
+    if (h->colorBytes < sb) {                              // (the raw-input staging buffer is shared with the colour path)
+        if (h->dColor) cudaFree(h->dColor);
+        h->dColor = nullptr; h->colorBytes = 0;
+        ORBB_CUDA(h, cudaMalloc((void**)&h->dColor, sb));
+        h->colorBytes = sb;
+    }
+    ORBB_CUDA(h, cudaMemcpy2DAsync(h->dColor, r->sw, img, stride, r->sw, r->sh, cudaMemcpyHostToDevice, h->stream));
+    int rc = orbb_extract_batch_rectified(h, r, h->dColor, 1, (size_t)r->sw, sb, lap0, lap1);
+    if (rc) return rc;
+    int32_t counts[2] = {0, 0};
+    rc = orbb_batch_fetch(h, 1, kps, desc, capacity, counts);
+    if (n_out) *n_out = counts[0];
+    if (mono_index) *mono_index = counts[1];
+    return rc;
+}
 
 }  // extern "C"

@@ -397,6 +397,36 @@ __device__ __forceinline__ int warp_sum_i(int v) {
     return v;
 }
 
+// "Next" row: Frame::UndistortKeyPoints (reference orb_slam3/src/Frame.cc:747-780) = cv::undistortPoints(pts, pts, K, D,
+// noArray(), K) over the N keypoints: OpenCV's cvUndistortPointsInternal with its default criteria (5 fixed-point
+// iterations, no epsilon test), in double precision without fused multiply-adds (this file is built with -fmad=false),
+// result rounded to float.  k[0..13] = distortion coefficients (k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4 taux tauy), zero-filled;
+// the tilt terms must be zero (ORB-SLAM3's pinhole model has 4 or 5 coefficients).
+struct UndistortParams { double fx, fy, cx, cy, nfx, nfy, ncx, ncy, k[12]; };
+
+__global__ void __launch_bounds__(256) k_undistort(const float2* __restrict__ in, float2* __restrict__ out, int n, const UndistortParams p) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float2 pt = in[i];
+    const double u = (double)pt.x, v = (double)pt.y;
+    const double ifx = 1. / p.fx, ify = 1. / p.fy;
+    double x = (u - p.cx) * ifx, y = (v - p.cy) * ify;
+    const double x0 = x, y0 = y;
+    const double* k = p.k;
+    for (int j = 0; j < 5; j++) {
+        const double r2 = x * x + y * y;
+        const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+        if (icdist < 0) { x = (u - p.cx) * ifx; y = (v - p.cy) * ify; break; }
+        const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+        const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+        x = (x0 - deltaX) * icdist;
+        y = (y0 - deltaY) * icdist;
+    }
+    // RR = P (new camera matrix), R = identity: xx = fx'*x + 0*y + cx', ww = 1 / (0*x + 0*y + 1)
+    const double xx = p.nfx * x + 0. * y + p.ncx, yy = 0. * x + p.nfy * y + p.ncy, ww = 1. / (0. * x + 0. * y + 1.);
+    out[i] = make_float2((float)(xx * ww), (float)(yy * ww));
+}
+
 // Right-image keypoints bucketed by row (counting sort on (int)y, one CTA per frame): the reference's vRowIndices table
 // (Frame.cc:824-838) lists for every row the right keypoints whose band [y - r, y + r] covers it; here a left keypoint
 // scans the buckets of the rows within the largest band radius of its own row and applies the exact band test per
@@ -868,6 +898,33 @@ int orbb_distinctive_csr(orbb_matcher* m, const uint8_t* desc, int ntotal, const
     m->launches++;
     ORBM_CUDA(m, cudaGetLastError());
     ORBM_CUDA(m, cudaMemcpyAsync(best, m->scratch[3], bo, cudaMemcpyDeviceToHost, m->stream));
+    ORBM_CUDA(m, cudaStreamSynchronize(m->stream));
+    return ORBB_OK;
+}
+
+// ---- Frame::UndistortKeyPoints ("next" row) -----------------------------------------------------------------------
+int orbb_undistort_points(orbb_matcher* m, const float* xy, int n, const float* K4, const float* dist, int ndist, const float* newK4,
+                          float* out_xy) {
+    if (!m || n < 0 || !K4 || !newK4 || (n > 0 && (!xy || !out_xy)) || ndist < 0 || ndist > 12 || (ndist > 0 && !dist))
+        return m_err(m, ORBB_ERR_ARG, "bad argument");
+    if (n == 0) return ORBB_OK;
+    if (ndist == 0 || dist[0] == 0.0f) {                   // Frame.cc:749-753: mDistCoef.at<float>(0) == 0 -> mvKeysUn = mvKeys
+        memcpy(out_xy, xy, sizeof(float) * 2 * (size_t)n);
+        return ORBB_OK;
+    }
+    ORBM_CUDA(m, cudaSetDevice(m->device));
+    UndistortParams p;
+    p.fx = K4[0]; p.fy = K4[1]; p.cx = K4[2]; p.cy = K4[3];
+    p.nfx = newK4[0]; p.nfy = newK4[1]; p.ncx = newK4[2]; p.ncy = newK4[3];
+    for (int i = 0; i < 12; i++) p.k[i] = i < ndist ? (double)dist[i] : 0.0;
+    int rc;
+    const size_t bytes = sizeof(float) * 2 * (size_t)n;
+    if ((rc = ensure_scratch(m, 0, bytes)) || (rc = ensure_scratch(m, 1, bytes))) return rc;
+    ORBM_CUDA(m, cudaMemcpyAsync(m->scratch[0], xy, bytes, cudaMemcpyHostToDevice, m->stream));
+    k_undistort<<<(n + 255) / 256, 256, 0, m->stream>>>((const float2*)m->scratch[0], (float2*)m->scratch[1], n, p);
+    m->launches++;
+    ORBM_CUDA(m, cudaGetLastError());
+    ORBM_CUDA(m, cudaMemcpyAsync(out_xy, m->scratch[1], bytes, cudaMemcpyDeviceToHost, m->stream));
     ORBM_CUDA(m, cudaStreamSynchronize(m->stream));
     return ORBB_OK;
 }

@@ -46,6 +46,18 @@ class ORBmatcher:
         b = np.ascontiguousarray(b, np.uint8)
         return capi.load().orbb_hamming_distance(capi.ptr(a), capi.ptr(b))
 
+    # ---- Frame::UndistortKeyPoints (Frame.cc:747-780) ----
+    def undistort_points(self, xy, K4, dist, new_K4=None):
+        """cv::undistortPoints(xy, out, K, dist, noArray(), newK): xy float32 [n,2]; K4 = (fx, fy, cx, cy); dist = k1 k2 p1 p2 [k3..]"""
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        k = np.ascontiguousarray(K4, np.float32)
+        nk = k if new_K4 is None else np.ascontiguousarray(new_K4, np.float32)
+        d = np.ascontiguousarray(dist, np.float32).ravel()
+        out = np.zeros_like(xy)
+        capi.check(self._lib.orbb_undistort_points(self._m, capi.ptr(xy), len(xy), capi.ptr(k), capi.ptr(d), len(d), capi.ptr(nk), capi.ptr(out)),
+                   self._m, matcher=True)
+        return out
+
     # ---- brute-force 2-NN (Frame.cc:1144) ----
     def knn2(self, query, train):
         """host arrays [nq,32], [nd,32] uint8 -> idx[nq,2], dist[nq,2] (missing = -1 / INT_MAX)"""

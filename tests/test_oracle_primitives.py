@@ -206,3 +206,48 @@ def test_bow_oracle_against_plain_python():
     assert got[2].tolist() == sorted(fv)
     assert got[4].tolist() == [f for n in sorted(fv) for f in fv[n]]
     assert got[5] == sum(len(v) for v in fv.values())
+
+
+def _rectify_maps(h, w, seed=0):
+    """maps of a mild radial + rotational warp (the shape initUndistortRectifyMap produces), partly leaving the source"""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    cx, cy = np.float32(w / 2 + 3.3), np.float32(h / 2 - 2.1)
+    r2 = ((xx - cx) ** 2 + (yy - cy) ** 2) / np.float32(w * w)
+    th = np.float32(0.02)
+    mx = cx + (xx - cx) * (1 + np.float32(0.25) * r2) * np.cos(th) - (yy - cy) * np.sin(th) + np.float32(1.7)
+    my = cy + (xx - cx) * np.sin(th) + (yy - cy) * (1 + np.float32(0.25) * r2) * np.cos(th) - np.float32(0.9)
+    mx[::7, ::5] = np.round(mx[::7, ::5])                     # exact integer positions (the {32767,0,0,1} table entry)
+    my[::7, ::5] = np.round(my[::7, ::5])
+    mx[:3] -= w                                               # rows mapped far outside
+    my[:, -2:] += np.float32(0.5) + h
+    mx[5, :40] = np.linspace(-1.5, 0.5, 40, dtype=np.float32)     # straddling the left / top border
+    my[6, :40] = np.linspace(-1.5, 0.5, 40, dtype=np.float32)
+    return mx.astype(np.float32), my.astype(np.float32)
+
+
+def test_remap_oracle_matches_cv2():
+    """oracle/port.remap_linear (restatement of cv::remap INTER_LINEAR, System.cc:239) against the real cv2.remap"""
+    cv2 = pytest.importorskip("cv2")
+    for (h, w, seed) in ((120, 160, 0), (376, 1241, 1), (97, 131, 2)):
+        src = synth.frame(h + 16, w + 24, seed)
+        mx, my = _rectify_maps(h, w, seed)
+        want = cv2.remap(src, mx, my, cv2.INTER_LINEAR)
+        assert np.array_equal(port.remap_linear(src, mx, my), want), (h, w)
+
+
+def test_undistort_oracle_matches_cv2():
+    """oracle/port.undistort_points against cv2.undistortPoints (Frame::UndistortKeyPoints, Frame.cc:766), bit for bit"""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    xy = np.stack([rng.uniform(0, 752, 4000), rng.uniform(0, 480, 4000)], 1).astype(np.float32)
+    K4 = (458.654, 457.296, 367.215, 248.375)                                    # config/.../EuRoC.yaml
+    for dist in ([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05],         # EuRoC cam0
+                 [-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.011],   # with k3
+                 [0.35, -0.6, 0.01, -0.02, 0.4]):                                # strong, some points diverge
+        K = np.float32([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1]])
+        D = np.float32(dist).reshape(-1, 1)
+        want = cv2.undistortPoints(xy.reshape(-1, 1, 2).copy(), K, D, None, K).reshape(-1, 2)
+        got = port.undistort_points(xy, K4, dist)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), dist
+    assert np.array_equal(port.undistort_points(xy, K4, [0.0, 0.1, 0, 0]), xy)   # Frame.cc:749: k1 == 0 -> copy
