@@ -160,3 +160,71 @@ def test_distinctive_descriptors_match_oracle(matcher):
     np.bitwise_xor.at(bits, (np.repeat(np.arange(len(desc)), 12), flip.ravel()), 1)
     desc = np.packbits(bits, axis=1)
     assert np.array_equal(matcher.distinctive(desc, rowptr), port.distinctive(desc, rowptr))
+
+
+def test_knn2_full_size_properties(matcher):
+    """BASELINE config 4 at full size (200 000 queries x 2 000 000 database rows, one shard): size-independent properties
+    of the result plus an exact oracle scan of a sample of queries."""
+    import torch
+    nq, nd = 200_000, 2_000_000
+    db, q = synth.descriptor_db(nd, nq, seed=77)
+    d_db, d_q = torch.from_numpy(db).cuda(), torch.from_numpy(q).cuda()
+    idx = torch.empty((nq, 2), dtype=torch.int32, device="cuda")
+    dst = torch.empty((nq, 2), dtype=torch.int32, device="cuda")
+    matcher.knn2_device(d_q, nq, d_db, nd, idx, dst)
+    torch.cuda.synchronize()
+    idx, dst = idx.cpu().numpy(), dst.cpu().numpy()
+    assert (idx >= 0).all() and (idx < nd).all() and (idx[:, 0] != idx[:, 1]).all()
+    assert (dst[:, 0] <= dst[:, 1]).all() and (dst >= 0).all() and (dst <= 256).all()
+    # the reported distances are the distances of the reported rows
+    for col in (0, 1):
+        d = np.unpackbits(db[idx[::997, col]] ^ q[::997], axis=1).sum(1)
+        assert np.array_equal(d, dst[::997, col])
+    # planted queries (first half: a database row with <= 40 flipped bits) find a row at least that close; ties on
+    # duplicated rows go to the lower index
+    assert (dst[: nq // 2, 0] <= 40).all()
+    assert (dst[nq // 2:, 0] > 40).mean() > 0.99            # random queries have no close row (256-bit uniform: ~85 at best)
+    eq = dst[:, 0] == dst[:, 1]
+    assert (idx[eq, 0] < idx[eq, 1]).all()
+    # exact scan of a sample on the CPU oracle
+    pick = np.r_[np.arange(0, nq // 2, 12500), np.arange(nq // 2, nq, 25000)]
+    i0, d0 = port.knn2(q[pick], db, nthreads=8)
+    assert np.array_equal(idx[pick], i0) and np.array_equal(dst[pick], d0)
+
+
+def test_stereo_full_size_batch_properties():
+    """BASELINE config 2 shape (1241x376, 2000 features per eye) as a batch: determinism, value ranges, and the
+    sequential per-frame call gives the same numbers as the batch."""
+    import torch
+    B = 16
+    bf, b = float(np.float32(718.856 * 0.53716)), float(np.float32(0.53716))
+    pairs = [synth.stereo_pair(376, 1241, i) for i in range(B)]
+    L = torch.from_numpy(np.stack([p[0] for p in pairs])).cuda()
+    R = torch.from_numpy(np.stack([p[1] for p in pairs])).cuda()
+    gl, gr = ORBextractor(2000, max_batch=B), ORBextractor(2000, max_batch=B)
+    out = []
+    for _ in range(2):
+        gl.extract_batch_device(L, B, 1241, 376)
+        gr.extract_batch_device(R, B, 1241, 376)
+        stereo_match_batch(gl, gr, B, bf, b)
+        out.append(stereo_fetch(gl, B))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    ur, dp = out[0]
+    counts, kps, _ = gl.fetch(B)
+    matched = 0
+    for f in range(B):
+        n = counts[f, 0]
+        u, d, x = ur[f, :n], dp[f, :n], kps[f, :n]["x"]
+        ok = u >= 0
+        matched += ok.sum()
+        assert ((u == -1) == (d == -1)).all()
+        assert (d[ok] > 0).all() and (x[ok] - u[ok] >= 0).all() and (x[ok] - u[ok] < np.float32(bf / b)).all()     # disparity in [0, maxD)
+        assert np.allclose(d[ok], np.float32(bf) / np.maximum(x[ok] - u[ok], np.float32(0.01)), rtol=1e-6)
+    assert matched > 0.3 * counts[:, 0].sum()
+    f = 5                                                     # one pair against the oracle
+    pl, pr = port.PortExtractor(2000), port.PortExtractor(2000)
+    _, kl, dl, _ = pl.extract(pairs[f][0])
+    _, kr, dr, _ = pr.extract(pairs[f][1])
+    ur0, dp0, _, _, _ = port.stereo(pl, pr, kl, dl, kr, dr, np.float32(bf), np.float32(b))
+    n = counts[f, 0]
+    assert n == len(ur0) and np.array_equal(ur[f, :n], ur0) and np.array_equal(dp[f, :n], dp0)
