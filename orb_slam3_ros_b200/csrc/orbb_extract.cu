@@ -1296,6 +1296,12 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
         P.apronItems = items;
     }
     P.bandsTotal = (int)bands.size(); P.bandSmem = bandSmem;
+    {   // k_fast_cell: tile pitch 64 when every cell (+6 margin, +15 alignment) fits, else 96; smem for the tallest cell
+        int maxW = 0, maxH = 0;
+        for (int l = 0; l < nl; l++) { maxW = std::max(maxW, P.lv[l].wCell); maxH = std::max(maxH, P.lv[l].hCell); }
+        P.cellTp = maxW + 21 <= 64 ? 64 : 96;
+        P.cellSmem = (maxH + 6) * P.cellTp + (maxH + 2) * P.cellTp + FB_WARP_SMEM;
+    }
     P.cellsTotal = cells; P.blurTilesTotal = tiles; P.kpCap = kpCap; P.fsTotal = fsTiles;
     P.pyrStride = pyrBytes; P.blurStride = blurBytes;
     P.cellKeyStride = cellKeys; P.rawStride = raw; P.nodeStride = nodes; P.selStride = sel;
@@ -1346,6 +1352,8 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
     ORBB_CUDA(h, cudaMemcpyAsync(dCellDesc, cellDesc.data(), cellDesc.size() * sizeof(CellDesc), cudaMemcpyHostToDevice, h->stream));
     ORBB_CUDA(h, cudaMemcpyAsync(dBands, bands.data(), bands.size() * sizeof(BandDesc), cudaMemcpyHostToDevice, h->stream));
     ORBB_CUDA(h, cudaFuncSetAttribute(k_fast_band, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(bandSmem, 1024)));
+    ORBB_CUDA(h, cudaFuncSetAttribute(k_fast_cell<64>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    ORBB_CUDA(h, cudaFuncSetAttribute(k_fast_cell<96>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     ORBB_CUDA(h, cudaMemcpyAsync(h->dPlan, &P, sizeof P, cudaMemcpyHostToDevice, h->stream));
     ORBB_CUDA(h, cudaStreamSynchronize(h->stream));
     h->capacity = frames;
@@ -1427,7 +1435,13 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
     if (legacyFast) {
         mark(h, ST_FAST_CELLS);
         mark(h, ST_FAST_RETRY);
-    } else if (!fastMode || strcmp(fastMode, "split")) {
+    } else if (!fastMode || !strcmp(fastMode, "cellwarp")) {
+        if (P.cellTp == 64) k_fast_cell<64><<<dim3(P.cellsTotal, nframes), 32, P.cellSmem, st>>>(h->dPlan, B);
+        else k_fast_cell<96><<<dim3(P.cellsTotal, nframes), 32, P.cellSmem, st>>>(h->dPlan, B);
+        mark(h, ST_FAST_CELLS);
+        mark(h, ST_FAST_RETRY);
+        h->launches++;
+    } else if (!strcmp(fastMode, "band")) {
         k_fast_band<<<dim3(P.bandsTotal, nframes), FB_THREADS, P.bandSmem, st>>>(h->dPlan, B, B.bands);
         mark(h, ST_FAST_CELLS);
         mark(h, ST_FAST_RETRY);

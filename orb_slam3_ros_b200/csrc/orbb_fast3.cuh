@@ -1,4 +1,6 @@
-// K2, fused band formulation (production path).  (included INSIDE namespace orbb, after orbb_fast.cuh / orbb_fast2.cuh)
+// K2, fused formulations.  (included INSIDE namespace orbb, after orbb_fast.cuh / orbb_fast2.cuh)
+// Production: k_fast_cell (one warp = one CTA = one cell, at the end of this file).  k_fast_band (ORBB_FAST_MODE=band) is
+// the same per-cell state machine with the tile shared by up to 4 cells of a cell row:
 //
 // One CTA stages a BAND SEGMENT -- a run of up to 4 adjacent 35-px cells of one cell row of one level -- and then each
 // WARP finishes one cell on its own (reference ORBextractor.cc:805-872: cv::FAST on each cell at iniThFAST, again at
@@ -47,10 +49,11 @@ __device__ __forceinline__ unsigned quick_bytes4(unsigned wl, unsigned wc, unsig
 
 // One cell, one warp.  tile: row t = level row gy0 - 3 + t, column = level column - X0.  score: row s = interior row s - 1.
 // Returns the number of NMS survivors parked in `park`.
+template <int TP>
 __device__ __forceinline__ int cell_pass(const uint8_t* __restrict__ tile, uint8_t* __restrict__ score, unsigned short* candS,
                                          unsigned short* cornS, unsigned short* allS, unsigned* __restrict__ park, int cx0, int cx1,
                                          int ih, int th, int lane) {
-    constexpr int PS = FB_TP, TPW = FB_TP / 4;
+    constexpr int PS = TP, TPW = TP / 4;
     const int wa = cx0 >> 2, nwc = max(((cx1 + 3) >> 2) - wa, 2);        // (>= 2 keeps the reciprocal in 32 bits; extra words are masked)
     const unsigned mInv = 0xffffffffu / (unsigned)nwc + 1u;
     const int items = ((ih + 1) >> 1) * nwc;
@@ -141,7 +144,7 @@ __device__ __forceinline__ int cell_pass(const uint8_t* __restrict__ tile, uint8
                 cand = (quick_bytes4(q[-1], q[0], q[1], q[3 * TPW], q[-3 * TPW], K7, M) >> 7) & xm1;      // bit 8k: pixel k of row r0
                 if (r0 + 1 < ih)                                                                              // bit 8k + 1: row r0 + 1
                     cand |= ((quick_bytes4(q[TPW - 1], q[TPW], q[TPW + 1], q[4 * TPW], q[-2 * TPW], K7, M) >> 7) & xm1) << 1;
-                pos0 = (r0 + 3) * FB_TP + xb0;
+                pos0 = (r0 + 3) * TP + xb0;
             }
             const int cnt = __popc(cand);
             const int inc = warp_incl_scan(cnt, lane);
@@ -150,7 +153,7 @@ __device__ __forceinline__ int cell_pass(const uint8_t* __restrict__ tile, uint8
             while (cand) {
                 const int b = __ffs(cand) - 1;
                 cand &= cand - 1;
-                candS[o++] = (unsigned short)(pos0 + (b & 1) * FB_TP + (b >> 3));
+                candS[o++] = (unsigned short)(pos0 + (b & 1) * TP + (b >> 3));
             }
             base += 32;
             __syncwarp();
@@ -162,11 +165,11 @@ __device__ __forceinline__ int cell_pass(const uint8_t* __restrict__ tile, uint8
         bool keep = false;
         unsigned rec = 0;
         if (valid) {
-            const int r1 = sp / FB_TP, x = sp - r1 * FB_TP;
+            const int r1 = sp / TP, x = sp - r1 * TP;
             const uint8_t* q = score + sp;
-            int m = max((int)q[-FB_TP], (int)q[FB_TP]);
-            if (x > cx0) m = max(m, max3i((int)q[-FB_TP - 1], (int)q[-1], (int)q[FB_TP - 1]));
-            if (x + 1 < cx1) m = max(m, max3i((int)q[-FB_TP + 1], (int)q[1], (int)q[FB_TP + 1]));
+            int m = max((int)q[-TP], (int)q[TP]);
+            if (x > cx0) m = max(m, max3i((int)q[-TP - 1], (int)q[-1], (int)q[TP - 1]));
+            if (x + 1 < cx1) m = max(m, max3i((int)q[-TP + 1], (int)q[1], (int)q[TP + 1]));
             keep = sc > m;
             rec = ((unsigned)(r1 - 1) << 16) | ((unsigned)(x - cx0) << 8) | (unsigned)sc;
         }
@@ -185,7 +188,7 @@ __device__ __forceinline__ int cell_pass(const uint8_t* __restrict__ tile, uint8
         for (int b0 = 0; b0 < ih * wc; b0 += 32) {
             const int i = b0 + lane;
             const int r = i / wc, x = cx0 + i - r * wc;
-            const int sp = (r + 1) * FB_TP + x;
+            const int sp = (r + 1) * TP + x;
             const int sc = i < ih * wc ? score[sp] : 0;
             nms(sc > 0, sp, sc);
         }
@@ -237,9 +240,9 @@ __global__ void __launch_bounds__(FB_THREADS, 10) k_fast_band(const Plan* __rest
         unsigned short* candS = stacks;
         unsigned short* cornS = candS + FB_CANDS;
         unsigned short* allS = cornS + FB_CORNS;
-        nSurv = cell_pass(tile, score, candS, cornS, allS, park, cx0, cx1, ih, min(max(P->iniTh, 0), 255), lane);
+        nSurv = cell_pass<FB_TP>(tile, score, candS, cornS, allS, park, cx0, cx1, ih, min(max(P->iniTh, 0), 255), lane);
         if (nSurv == 0)                                           // :833-846 (scores do not depend on the threshold: the map stays valid)
-            nSurv = cell_pass(tile, score, candS, cornS, allS, park, cx0, cx1, ih, min(max(P->minTh, 0), 255), lane);
+            nSurv = cell_pass<FB_TP>(tile, score, candS, cornS, allS, park, cx0, cx1, ih, min(max(P->minTh, 0), 255), lane);
     }
     // ---- E: raster order by rank counting; keys are relative to the 16-px border (:865-866) ----
     __syncwarp();
@@ -253,4 +256,59 @@ __global__ void __launch_bounds__(FB_THREADS, 10) k_fast_band(const Plan* __rest
         keysOut[rank] = (u64)(unsigned)x | ((u64)(unsigned)y << 16) | ((u64)(rec & 0xffu) << 32);
     }
     if (lane == 0) cellCount[warp] = nSurv;
+}
+
+
+// One warp = one CTA = one cell with its own tile (pitch TP: 16-byte aligned window of the cell + its 3-px margin), so a
+// finished cell frees its resources at once and up to 32 cells are in flight per SM, none waiting for a slower neighbour
+// (in k_fast_band the CTA lives as long as its slowest cell, e.g. one that needs the minThFAST retry).
+template <int TP>
+__global__ void __launch_bounds__(32) k_fast_cell(const Plan* __restrict__ P, Bufs B) {
+    extern __shared__ __align__(128) uint8_t fcSmem[];
+    __shared__ __align__(8) unsigned long long sBar;
+    const int gcell = blockIdx.x, frame = blockIdx.y, lane = threadIdx.x;
+    const CellDesc cd = B.cellDesc[gcell];
+    int* cellCount = B.cellCount + (size_t)frame * P->cellsTotal + gcell;
+    const int ih = cd.gy1 - cd.gy0;
+    if (cd.gx1 <= cd.gx0 || ih <= 0) {                        // cell skipped by the reference (:810,:819) or smaller than 7 px
+        if (lane == 0) *cellCount = 0;
+        return;
+    }
+    const LevelPlan& L = P->lv[cd.level];
+    const int rowsT = ih + 6;
+    const int X0 = (cd.gx0 - 3) & ~15;
+    uint8_t* tile = fcSmem;
+    uint8_t* score = fcSmem + rowsT * TP;                     // TP is a multiple of 16
+    unsigned short* candS = reinterpret_cast<unsigned short*>(score + (ih + 2) * TP);
+    unsigned short* cornS = candS + FB_CANDS;
+    unsigned short* allS = cornS + FB_CORNS;
+    const uint8_t* roi = B.pyr + (size_t)frame * P->pyrStride + L.roiOff;
+    if (lane == 0) {
+        mbar_init(&sBar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&sBar, rowsT * TP);
+    }
+    __syncwarp();
+    for (int r = lane; r < rowsT; r += 32) tma_bulk_g2s(tile + r * TP, roi + (ptrdiff_t)(cd.gy0 - 3 + r) * L.pitch + X0, TP, &sBar);
+    for (int i = lane; i < (ih + 2) * (TP / 16); i += 32) reinterpret_cast<uint4*>(score)[i] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    mbar_wait(&sBar, 0);
+    const int cx0 = cd.gx0 - X0, cx1 = cd.gx1 - X0;
+    // survivors are parked (unordered) in the quadtree's second key buffer, which k_octree only uses later
+    unsigned* park = reinterpret_cast<unsigned*>(B.keys + ((size_t)frame * 2 + 1) * P->rawStride + cd.outOff);
+    int nSurv = cell_pass<TP>(tile, score, candS, cornS, allS, park, cx0, cx1, ih, min(max(P->iniTh, 0), 255), lane);
+    if (nSurv == 0)                                           // :833-846 (scores do not depend on the threshold: the map stays valid)
+        nSurv = cell_pass<TP>(tile, score, candS, cornS, allS, park, cx0, cx1, ih, min(max(P->minTh, 0), 255), lane);
+    // ---- E: raster order by rank counting; keys are relative to the 16-px border (:865-866) ----
+    __syncwarp();
+    u64* keysOut = B.cellKeys + (size_t)frame * P->cellKeyStride + cd.outOff;
+    for (int i = lane; i < nSurv; i += 32) {
+        const unsigned rec = __ldcg(park + i);
+        int rank = 0;
+        for (int k = 0; k < nSurv; k++) rank += __ldcg(park + k) < rec;
+        const int x = cd.gx0 + (int)((rec >> 8) & 0xffu) - kMinBorder;
+        const int y = cd.gy0 + (int)(rec >> 16) - kMinBorder;
+        keysOut[rank] = (u64)(unsigned)x | ((u64)(unsigned)y << 16) | ((u64)(rec & 0xffu) << 32);
+    }
+    if (lane == 0) *cellCount = nSurv;
 }

@@ -49,6 +49,7 @@ struct Plan {
     int nlevels, W, H;
     int cellsTotal, blurTilesTotal, fsTotal;
     int bandsTotal, bandSmem;      // k_fast_band: CTAs per frame, dynamic shared memory per CTA
+    int cellTp, cellSmem;          // k_fast_cell: tile pitch (64 / 96), dynamic shared memory per CTA
     int kpCap;
     int iniTh, minTh;
     u64 pyrStride, blurStride;                                  // bytes per frame
