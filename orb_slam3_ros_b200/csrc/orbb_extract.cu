@@ -181,9 +181,8 @@ __device__ __forceinline__ unsigned hsum7(unsigned a, unsigned b) {
     return __dp4a(a, 0x38302212u, __dp4a(b, 0x00122230u, 0u));
 }
 
-// horizontal sums of the 4 columns of one word for one input row
-__device__ __forceinline__ void blur_hrow(const unsigned* __restrict__ row, unsigned (&h)[4]) {
-    const unsigned w0 = __ldg(row - 1), w1 = __ldg(row), w2 = __ldg(row + 1);
+// horizontal sums of the 4 columns of one word (w1) of one input row; w0 / w2 = the words left / right of it
+__device__ __forceinline__ void blur_hwords(unsigned w0, unsigned w1, unsigned w2, unsigned (&h)[4]) {
     h[0] = hsum7(__funnelshift_r(w0, w1, 8), __funnelshift_r(w1, w2, 8));
     h[1] = hsum7(__funnelshift_r(w0, w1, 16), __funnelshift_r(w1, w2, 16));
     h[2] = hsum7(__funnelshift_r(w0, w1, 24), __funnelshift_r(w1, w2, 24));
@@ -211,20 +210,29 @@ __global__ void __launch_bounds__(BLUR_THREADS) k_blur(const Plan* __restrict__ 
     const uint8_t* src = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + 4 * wc + (ptrdiff_t)(y0 - 3) * pitch;
     uint8_t* out = B.blur + (size_t)frame * P->blurStride + L.blurOff + 4 * wc + (size_t)y0 * bpitch;
     unsigned pk[4][4];                                       // 4 row pairs x 4 columns
-    auto load_pair = [&](unsigned (&dst)[4]) {
-        unsigned h0[4], h1[4];
-        blur_hrow(reinterpret_cast<const unsigned*>(src), h0);
-        blur_hrow(reinterpret_cast<const unsigned*>(src + pitch), h1);
+    unsigned raw[6];                                         // the next row pair's words, loaded one iteration ahead
+    auto fetch = [&]() {
+        const unsigned* r0 = reinterpret_cast<const unsigned*>(src);
+        const unsigned* r1 = reinterpret_cast<const unsigned*>(src + pitch);
+        raw[0] = __ldg(r0 - 1); raw[1] = __ldg(r0); raw[2] = __ldg(r0 + 1);
+        raw[3] = __ldg(r1 - 1); raw[4] = __ldg(r1); raw[5] = __ldg(r1 + 1);
         src += 2 * pitch;
+    };
+    auto pack = [&](unsigned (&dst)[4]) {
+        unsigned h0[4], h1[4];
+        blur_hwords(raw[0], raw[1], raw[2], h0);
+        blur_hwords(raw[3], raw[4], raw[5], h1);
 #pragma unroll
         for (int k = 0; k < 4; k++) dst[k] = h0[k] | (h1[k] << 16);
     };
 #pragma unroll
-    for (int j = 0; j < 3; j++) load_pair(pk[j]);
+    for (int j = 0; j < 3; j++) { fetch(); pack(pk[j]); }
+    fetch();
 #pragma unroll
     for (int m = 0; m < BLUR_STRIP / 2; m++) {
         if (2 * m < rows) {                                  // (input rows up to rows + 6 lie inside the 19-px apron)
-            load_pair(pk[(m + 3) & 3]);
+            pack(pk[(m + 3) & 3]);
+            if (2 * (m + 1) < rows) fetch();                 // in flight while this iteration's vertical pass runs
             unsigned e[4], o[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
