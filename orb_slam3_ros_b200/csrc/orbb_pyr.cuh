@@ -1,6 +1,7 @@
 // K1, production pyramid kernels (ComputePyramid, reference ORBextractor.cc:1170-1195).  (included INSIDE namespace orbb)
 //
 //   k_pyr_level0     copy of the source into its bordered slab, 16 bytes per thread.
+//   k_pyr_resize_t   (production) = k_pyr_resize_s with the CTA's source rows staged in shared memory by TMA bulk copies
 //   k_pyr_resize_s   cv::resize INTER_LINEAR for scale steps up to ~1.3 (the reference's 1.2): a thread owns FOUR destination columns and walks
 //                    down PR_ROWS destination rows.  cv::resize's horizontal pass (HResizeLinear) of a source row is
 //                    computed once and reused by the next destination row (consecutive destination rows share a source
@@ -46,7 +47,16 @@ __device__ __forceinline__ void hresize4(const unsigned* __restrict__ rp, const 
     }
 }
 
-__global__ void __launch_bounds__(PR_THREADS) k_pyr_resize_s(const Plan* __restrict__ P, Bufs B, int level) {
+__device__ __forceinline__ void hresize4s(const unsigned* rp, const ResizeCol (&c)[4], int (&h)[4]) {      // rp: shared memory
+    const unsigned wa = rp[0], wb = rp[1], wc = rp[2];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const unsigned lo = (wa & ~c[k].m) | (wb & c[k].m), hi = (wb & ~c[k].m) | (wc & c[k].m);
+        h[k] = (int)(__dp2a_lo(c[k].coef, __funnelshift_r(lo, hi, c[k].sh), 0u) >> 4);
+    }
+}
+
+__global__ void __launch_bounds__(PR_THREADS, 16) k_pyr_resize_s(const Plan* __restrict__ P, Bufs B, int level) {
     const LevelPlan& L = P->lv[level];
     const LevelPlan& S = P->lv[level - 1];
     const int word = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -99,6 +109,88 @@ __global__ void __launch_bounds__(PR_THREADS) k_pyr_resize_s(const Plan* __restr
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int v = (__mulhi(b0, h0[k]) + __mulhi(b1, hc[k]) + 2) >> 2;      // 0 .. 255 (coefficients sum to 2048)
+                out |= (unsigned)v << (8 * k);
+            }
+            *reinterpret_cast<unsigned*>(d + (size_t)r * Lpitch) = out;
+        }
+    }
+}
+
+// The same kernel with the source rows of the CTA (32 destination rows x 128 destination columns -> about 40 rows x 176 bytes)
+// staged in shared memory by one TMA bulk copy per source row: the three words per source row then come from shared
+// memory (short scoreboard) instead of L1/L2 (long scoreboard, which is what the kernel above waits on most).
+constexpr int PR_SROWS = 48, PR_SPITCH = 208;
+
+__global__ void __launch_bounds__(PR_THREADS, 12) k_pyr_resize_t(const Plan* __restrict__ P, Bufs B, int level) {
+    __shared__ __align__(128) uint8_t sSrc[PR_SROWS * PR_SPITCH];
+    __shared__ __align__(8) unsigned long long sBar;
+    const LevelPlan& L = P->lv[level];
+    const LevelPlan& S = P->lv[level - 1];
+    const int tid = threadIdx.x;
+    const int word = blockIdx.x * 32 + (tid & 31);
+    const int dyc = blockIdx.y * (PR_THREADS / 32) * PR_ROWS;             // first destination row of the CTA
+    const int dy0 = dyc + (tid >> 5) * PR_ROWS;
+    const int frame = blockIdx.z;
+    const int Lw = L.w, Lh = L.h, Lpitch = L.pitch, Sh1 = S.h - 1, Spitch = S.pitch;
+    // ---- stage: source rows rs0..rs1, bytes [xs0, xs0 + PR_SPITCH) ----
+    const int2* tyc = B.tab + L.tabY;
+    const int rs0 = min(max(__ldg(tyc + dyc).x, 0), Sh1);
+    const int rs1 = min(max(__ldg(tyc + min(dyc + (PR_THREADS / 32) * PR_ROWS, Lh) - 1).x + 1, 0), Sh1);
+    const int xs0 = __ldg(B.tab + L.tabX + blockIdx.x * 128).x & ~15;
+    const uint8_t* sbase = B.pyr + (size_t)frame * P->pyrStride + S.roiOff + xs0;
+    if (tid == 0) {
+        mbar_init(&sBar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&sBar, (rs1 - rs0 + 1) * PR_SPITCH);
+    }
+    __syncthreads();
+    if (tid <= rs1 - rs0) tma_bulk_g2s(sSrc + tid * PR_SPITCH, sbase + (size_t)(rs0 + tid) * Spitch, PR_SPITCH, &sBar);
+    if (word * 4 >= Lw || dy0 >= Lh) return;
+    const int4* tx = reinterpret_cast<const int4*>(B.tab + L.tabX + word * 4);      // 4 entries (sx, a0 | a1 << 16), padded
+    const int4 t01 = __ldg(tx), t23 = __ldg(tx + 1);
+    const int wbase = t01.x >> 2;
+    ResizeCol c[4];
+    {
+        const int sx[4] = {t01.x, t01.z, t23.x, t23.z};
+        const int cf[4] = {t01.y, t01.w, t23.y, t23.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int o = sx[k] - 4 * wbase;
+            c[k].coef = (unsigned)cf[k];
+            c[k].sh = 8u * (o & 3);
+            c[k].m = o >= 4 ? 0xffffffffu : 0u;
+            asm volatile("" : "+r"(c[k].sh), "+r"(c[k].m));
+        }
+    }
+    const uint8_t* srows = sSrc + (4 * wbase - xs0) - rs0 * PR_SPITCH;
+    uint8_t* d = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + (size_t)dy0 * Lpitch + 4 * word;
+    const int2* ty = tyc + dy0;
+    const int rows = min(PR_ROWS, Lh - dy0);
+    int cached = -1, hc[4] = {0, 0, 0, 0};
+    mbar_wait(&sBar, 0);
+#pragma unroll
+    for (int r = 0; r < PR_ROWS; r++) {
+        if (r < rows) {
+            const int2 t = __ldg(ty + r);
+            const int r0 = min(max(t.x, 0), Sh1), r1 = min(max(t.x + 1, 0), Sh1);
+            const int b0 = (int)(t.y << 16), b1 = (int)(t.y & 0xffff0000);
+            int h0[4];
+            if (r0 == cached) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) h0[k] = hc[k];
+            } else {
+                hresize4s(reinterpret_cast<const unsigned*>(srows + r0 * PR_SPITCH), c, h0);
+            }
+            if (r1 != r0) hresize4s(reinterpret_cast<const unsigned*>(srows + r1 * PR_SPITCH), c, hc);
+            else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) hc[k] = h0[k];
+            }
+            cached = r1;
+            unsigned out = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int v = (__mulhi(b0, h0[k]) + __mulhi(b1, hc[k]) + 2) >> 2;
                 out |= (unsigned)v << (8 * k);
             }
             *reinterpret_cast<unsigned*>(d + (size_t)r * Lpitch) = out;
