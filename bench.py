@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--knn-steps", type=int, default=3)
     ap.add_argument("--no-knn", action="store_true")
     ap.add_argument("--no-stereo", action="store_true")
+    ap.add_argument("--no-shapes", action="store_true")
     ap.add_argument("--stereo-pairs", type=int, default=256)
     ap.add_argument("--stereo-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -414,6 +415,36 @@ def run_ours(a):
                 port.stereo(pl, pr, kl, dl, kr, dr, np.float32(bf), np.float32(bl))
             stereo["cpu_single_thread_pairs_per_s"] = npairs / (time.perf_counter() - t0)
         del eL, eR, dL, dR
+
+    # ---- the other BASELINE shapes, resident, a few steps each (configs 3 and 5: TUM 640x480 / 4K 12 levels 8000 features) ----
+    shapes = []
+    if not a.no_shapes:
+        for (sw, sh, nf, nl, bt) in ((640, 480, 1000, 8, 256), (3840, 2160, 8000, 12, 8)):
+            if sw <= 1024:
+                fr = torch.from_numpy(synth.sequence(sh, sw, min(bt, 16), base_seed=synth.BASE_SEED + 31 * rank)).to(dev)
+            else:
+                fr = torch.from_numpy(np.stack([synth.frame(sh, sw, 100 + 4 * rank + k) for k in range(2)])).to(dev)
+            fr = fr.repeat((bt + fr.shape[0] - 1) // fr.shape[0], 1, 1)[:bt].contiguous()
+            ex = ORBextractor(nf, SCALE, nl, INI_TH, MIN_TH, device=local, max_batch=bt)
+            est = torch.cuda.ExternalStream(ex.stream, device=dev)
+            for _ in range(2):
+                ex.extract_batch_device(fr, bt, sw, sh)
+            ex.sync()
+            l0 = ex.launch_count
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(est):
+                e0.record()
+            for _ in range(5):
+                ex.extract_batch_device(fr, bt, sw, sh)
+            with torch.cuda.stream(est):
+                e1.record()
+            ex.sync()
+            ms = max_over_ranks(e0.elapsed_time(e1)) / 5
+            cnt, _, _ = ex.fetch(bt, with_data=False)
+            shapes.append({"shape": f"{sw}x{sh}", "nfeatures": nf, "nlevels": nl, "batch": bt, "value": world * bt / (ms * 1e-3),
+                           "unit": "frames/s", "ms_per_step": ms, "keypoints_per_frame": float(cnt[:, 0].mean())})
+            launches += ex.launch_count - l0
+            del ex, fr
     clk = clocks.stop()
 
     # ---- CPU baseline on the box's host cores (rank 0, N=1 only), bounded sample of the same workload ----
@@ -443,7 +474,7 @@ def run_ours(a):
                     "api": "orbb_extract_batch_host_submit/_wait on two alternating handles (pinned host frames -> keypoints+descriptors)",
                     "single_sync_call_frames_per_s": world * B * a.steps / e2e_sync_s},
             "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "knn": knn, "stereo": stereo, "clocks": clk,
+            "roofline": roofline, "cpu_baseline": cpu, "knn": knn, "stereo": stereo, "other_shapes": shapes, "clocks": clk,
         }
         _emit(line)
     if world > 1:
