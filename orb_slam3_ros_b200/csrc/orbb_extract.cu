@@ -389,8 +389,9 @@ __global__ void __launch_bounds__(256) k_fast_v0(const Plan* __restrict__ P, Buf
 // ------------------------------------------------------------------------------------------------
 // K3: DistributeOctTree, one CTA per (frame, level).
 // ------------------------------------------------------------------------------------------------
-constexpr int OT_THREADS = 128;
-constexpr int OT_WARPS = OT_THREADS / 32;
+constexpr int OT_THREADS = 128;          // CTA size of the quadtree kernel for ordinary levels ...
+constexpr int OT_THREADS_BIG = 512;      // ... and for levels with many cells (4K-class images): more warps split nodes at once
+constexpr int OT_BIG_CELLS = 1000;
 constexpr int OT_SORT_SMEM = 1024;
 
 __device__ __forceinline__ int node_count(const QNode& n) { return n.cntbuf & 0x7fffffff; }
@@ -478,7 +479,7 @@ __device__ __forceinline__ int multi4(const int4 c) { return (c.x > 1) + (c.y > 
 // host restatement, checked against the real std::sort).  Warp 0 runs the partition steps -- the positions l_k / r_k that
 // the sequential two-pointer loop would stop at are listed with ballots, the K swaps happen at once -- and collects the
 // leaf ranges; then one thread per leaf range does its insertion sort.  Lp, Rp: int[n]; leaf: unsigned[n]; stk: int[192].
-__device__ void sort_emul_cta(u64* a, int n, int* Lp, int* Rp, unsigned* leaf, int* stk, int* sNLeaf, int tid) {
+__device__ void sort_emul_cta(u64* a, int n, int* Lp, int* Rp, unsigned* leaf, int* stk, int* sNLeaf, int tid, int nthreads) {
     if (n <= 1) return;                                     // (uniform)
     const int lane = tid & 31;
     if (tid < 32) {
@@ -551,13 +552,15 @@ __device__ void sort_emul_cta(u64* a, int n, int* Lp, int* Rp, unsigned* leaf, i
     }
     __syncthreads();
     const int nLeaf = *sNLeaf;
-    for (int s = tid; s < nLeaf; s += OT_THREADS) insertion_sort(a, (int)(leaf[s] & 0xffffu), (int)(leaf[s] >> 16));
+    for (int s = tid; s < nLeaf; s += nthreads) insertion_sort(a, (int)(leaf[s] & 0xffffu), (int)(leaf[s] >> 16));
 }
 
-__global__ void __launch_bounds__(OT_THREADS) k_octree(const Plan* __restrict__ P, Bufs B) {
+template <int OT_T>
+__global__ void __launch_bounds__(OT_T) k_octree(const Plan* __restrict__ P, Bufs B, int level0) {
+    constexpr int OT_W = OT_T / 32;
     // grid = (frames, levels): CTAs are dispatched x-fastest, so the long-running low levels of ALL frames start first and
     // the short high levels fill the tail
-    const int level = blockIdx.y, frame = blockIdx.x;
+    const int level = level0 + blockIdx.y, frame = blockIdx.x;
     const LevelPlan& L = P->lv[level];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = L.nFeat;
@@ -578,30 +581,34 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const Plan* __restrict__ 
 
     __shared__ int sN, sNodes, sPend, sM, sFinish, sPhase2, sCur, sPcur;
     __shared__ int sSlotCnt[kMaxIni], sSlotStart[kMaxIni];
-    __shared__ int sWarpSlot[OT_WARPS][kMaxIni];
+    __shared__ int sWarpSlot[OT_W][kMaxIni];
     __shared__ u64 sRec[OT_SORT_SMEM];
     __shared__ int sSortL[OT_SORT_SMEM], sSortR[OT_SORT_SMEM], sSortStk[192], sSortLeaves;
     __shared__ unsigned sSortLeaf[OT_SORT_SMEM];
 
     // ---- 1. gather vToDistributeKeys in the reference's order: cell-row-major, raster inside the cell ----
     const int nCells = L.nCols * L.nRows;
-    if (warp == 0) {
-        int run = 0;
-        for (int base = 0; base < nCells; base += 32) {
-            const int c = base + lane;
-            const int v = c < nCells ? cellCount[c] : 0;
-            const int inc = warp_incl_scan(v, lane);
-            if (c < nCells) cellOff[c] = run + inc - v;
-            run += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        if (lane == 0) sN = run;
+    {   // exclusive prefix of the cell counts by the whole CTA: every thread owns a contiguous run of cells (independent
+        // loads), the runs' sums are scanned through shared memory
+        const int chunk = (nCells + OT_T - 1) / OT_T, c0 = min(tid * chunk, nCells), c1 = min(c0 + chunk, nCells);
+        int sum = 0;
+        for (int c = c0; c < c1; c++) sum += __ldg(cellCount + c);
+        const int inc = warp_incl_scan(sum, lane);
+        if (lane == 31) sWarpSlot[warp][0] = inc;
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < OT_W; w++) { const int v = sWarpSlot[w][0]; total += v; if (w < warp) before += v; }
+        int run = before + inc - sum;
+        for (int c = c0; c < c1; c++) { cellOff[c] = run; run += __ldg(cellCount + c); }
+        if (tid == 0) sN = total;
+        __syncthreads();                                    // sWarpSlot is reused below
     }
     if (tid < kMaxIni) sSlotCnt[tid] = 0;
     __syncthreads();
     const int n = sN;
     // one thread per cell: the loads of a cell's keys are independent (read-only path), so their latencies overlap instead
     // of adding up cell after cell
-    for (int c = tid; c < nCells; c += OT_THREADS) {
+    for (int c = tid; c < nCells; c += OT_T) {
         const int cnt = __ldg(cellCount + c), off = cellOff[c];
         const u64* src = cellKeys + (size_t)c * L.cellCap;
 #pragma unroll 4
@@ -616,7 +623,7 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const Plan* __restrict__ 
     if (nIni > 1) {
         rootBuf = 1;
         // each warp owns a contiguous quarter of the keys: count per root, then write in order behind the warps before it
-        const int seg = (n + OT_WARPS - 1) / OT_WARPS, s0 = min(warp * seg, n), s1 = min(s0 + seg, n);
+        const int seg = (n + OT_W - 1) / OT_W, s0 = min(warp * seg, n), s1 = min(s0 + seg, n);
         int cntS[kMaxIni];
 #pragma unroll
         for (int s = 0; s < kMaxIni; s++) cntS[s] = 0;
@@ -639,7 +646,7 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const Plan* __restrict__ 
                 dstS[s] = 0;
                 if (s < nIni) {
                     int tot = 0, before = 0;
-                    for (int w = 0; w < OT_WARPS; w++) { const int v = sWarpSlot[w][s]; tot += v; if (w < warp) before += v; }
+                    for (int w = 0; w < OT_W; w++) { const int v = sWarpSlot[w][s]; tot += v; if (w < warp) before += v; }
                     dstS[s] = acc + before;
                     if (tid == 0) { sSlotStart[s] = acc; sSlotCnt[s] = tot; }
                     acc += tot;
@@ -710,7 +717,7 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const Plan* __restrict__ 
             __syncthreads();
             const int m = sM;
             if (m == 0) break;                                      // size == prevSize (:685)
-            for (int e = warp; e < m; e += OT_WARPS) split_node_warp(nodes[elist[e]], k0, k1, &cnt4[elist[e]], lane);
+            for (int e = warp; e < m; e += OT_W) split_node_warp(nodes[elist[e]], k0, k1, &cnt4[elist[e]], lane);
             __syncthreads();
             if (warp == 0) {
                 int T = 0, X = 0;
@@ -757,8 +764,8 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const Plan* __restrict__ 
             // ---------- phase 2: sort the pending nodes, split from the back until N nodes exist (:692-753) ----------
             const int len = sPend;
             u64* srt = len <= OT_SORT_SMEM ? sRec : rec;
-            for (int i = tid; i < nNodes; i += OT_THREADS) erased[i] = 0;
-            for (int e = warp; e < len; e += OT_WARPS) {
+            for (int i = tid; i < nNodes; i += OT_T) erased[i] = 0;
+            for (int e = warp; e < len; e += OT_W) {
                 const int idx = pendCur[e];
                 const QNode nd = nodes[idx];
                 split_node_warp(nd, k0, k1, &cnt4[idx], lane);
@@ -767,10 +774,10 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const Plan* __restrict__ 
             }
             __syncthreads();
             // std::sort(..., compareNodes) :700
-            if (len <= OT_SORT_SMEM) sort_emul_cta(srt, len, sSortL, sSortR, sSortLeaf, sSortStk, &sSortLeaves, tid);
+            if (len <= OT_SORT_SMEM) sort_emul_cta(srt, len, sSortL, sSortR, sSortLeaf, sSortStk, &sSortLeaves, tid, OT_T);
             else {
                 int* tmp = B.sortTmp + (size_t)frame * 3 * P->nodeStride + 3 * (size_t)L.nodeBase;
-                sort_emul_cta(srt, len, tmp, tmp + L.maxNodes, reinterpret_cast<unsigned*>(tmp + 2 * L.maxNodes), sSortStk, &sSortLeaves, tid);
+                sort_emul_cta(srt, len, tmp, tmp + L.maxNodes, reinterpret_cast<unsigned*>(tmp + 2 * L.maxNodes), sSortStk, &sSortLeaves, tid, OT_T);
             }
             __syncthreads();
             if (warp == 0) {
@@ -833,7 +840,7 @@ __global__ void __launch_bounds__(OT_THREADS) k_octree(const Plan* __restrict__ 
     const QNode* fin = nodesAB[sCur];
     const int nOut = sNodes;
     u64* sel = B.sel + (size_t)frame * P->selStride + L.selBase;
-    for (int i = tid; i < nOut && i < L.selCap; i += OT_THREADS) {
+    for (int i = tid; i < nOut && i < L.selCap; i += OT_T) {
         const QNode nd = fin[i];
         const u64* src = (node_buf(nd) ? k1 : k0) + nd.start;
         u64 best = src[0];
@@ -1481,7 +1488,9 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
     // fork: the blur only needs the pyramid; on its own stream it fills the SMs that the latency-bound quadtree leaves idle.
     // With stage profiling on, everything stays on one stream so that the stage events mean what they say.
     if (fork) ORBB_CUDA(h, cudaEventRecord(ln.evFork, st));
-    k_octree<<<dim3(nframes, P.nlevels), OT_THREADS, 0, st>>>(h->dPlan, B);
+    // images whose first level has many cells (4K class) get the large CTA on every level: more warps split nodes at once
+    if (P.lv[0].nCols * P.lv[0].nRows >= OT_BIG_CELLS) k_octree<OT_THREADS_BIG><<<dim3(nframes, P.nlevels), OT_THREADS_BIG, 0, st>>>(h->dPlan, B, 0);
+    else k_octree<OT_THREADS><<<dim3(nframes, P.nlevels), OT_THREADS, 0, st>>>(h->dPlan, B, 0);
     if (fork) {
         ORBB_CUDA(h, cudaStreamWaitEvent(ln.blurSt, ln.evFork, 0));
         k_blur<<<dim3(P.blurTilesTotal, nframes), BLUR_THREADS, 0, ln.blurSt>>>(h->dPlan, B);
