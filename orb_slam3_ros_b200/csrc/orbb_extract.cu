@@ -441,6 +441,62 @@ __device__ void split_node_warp(const QNode nd, u64* k0, u64* k1, int4* out, int
     if (lane == 0) *out = make_int4(c0, c1, c2, c3);
 }
 
+// The same by the whole CTA for a node with many keys (the first passes over a large level have fewer nodes than warps):
+// every warp takes a contiguous part of the keys -- four keys per lane are loaded before they are used, so four loads are
+// in flight -- and the parts' counts give each warp its output offsets.  sPart: int[warps][4].
+constexpr int OT_BIG_NODE = 4096, OT_BIG_LIST = 16;
+__device__ void split_node_cta(const QNode nd, u64* k0, u64* k1, int4* out, int (*sPart)[4], int tid, int nw) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int cnt = node_count(nd);
+    const u64* src = (node_buf(nd) ? k1 : k0) + nd.start;
+    u64* dst = (node_buf(nd) ? k0 : k1) + nd.start;
+    const int mx = nd.x0 + ((nd.x1 - nd.x0 + 1) >> 1), my = nd.y0 + ((nd.y1 - nd.y0 + 1) >> 1);
+    const int part = ((cnt + nw - 1) / nw + 127) & ~127;
+    const int i0 = min(warp * part, cnt), i1 = min(i0 + part, cnt);
+    const unsigned lt = (1u << lane) - 1;
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    for (int base = i0; base < i1; base += 128) {
+        u64 k[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { const int i = base + 32 * j + lane; k[j] = i < i1 ? src[i] : 0; }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int q = base + 32 * j + lane < i1 ? key_quadrant(k[j], mx, my) : 4;
+            c0 += __popc(__ballot_sync(0xffffffffu, q == 0));
+            c1 += __popc(__ballot_sync(0xffffffffu, q == 1));
+            c2 += __popc(__ballot_sync(0xffffffffu, q == 2));
+            c3 += __popc(__ballot_sync(0xffffffffu, q == 3));
+        }
+    }
+    if (lane == 0) { sPart[warp][0] = c0; sPart[warp][1] = c1; sPart[warp][2] = c2; sPart[warp][3] = c3; }
+    __syncthreads();
+    int t[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};                   // totals, and what the warps before this one hold
+    for (int w = 0; w < nw; w++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const int v = sPart[w][q]; t[q] += v; if (w < warp) b[q] += v; }
+    int o0 = b[0], o1 = t[0] + b[1], o2 = t[0] + t[1] + b[2], o3 = t[0] + t[1] + t[2] + b[3];
+    for (int base = i0; base < i1; base += 128) {
+        u64 k[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { const int i = base + 32 * j + lane; k[j] = i < i1 ? src[i] : 0; }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const bool valid = base + 32 * j + lane < i1;
+            const int q = valid ? key_quadrant(k[j], mx, my) : 4;
+            const unsigned b0 = __ballot_sync(0xffffffffu, q == 0), b1 = __ballot_sync(0xffffffffu, q == 1);
+            const unsigned b2 = __ballot_sync(0xffffffffu, q == 2), b3 = __ballot_sync(0xffffffffu, q == 3);
+            if (valid) {
+                const unsigned bm = q == 0 ? b0 : q == 1 ? b1 : q == 2 ? b2 : b3;
+                const int off = q == 0 ? o0 : q == 1 ? o1 : q == 2 ? o2 : o3;
+                dst[off + __popc(bm & lt)] = k[j];
+            }
+            o0 += __popc(b0); o1 += __popc(b1); o2 += __popc(b2); o3 += __popc(b3);
+        }
+    }
+    if (tid == 0) *out = make_int4(t[0], t[1], t[2], t[3]);
+    __syncthreads();
+}
+
 // child q (0..3 = n1..n4, :486-507) of parent p given the four child sizes
 __device__ __forceinline__ QNode make_child(const QNode& p, const int4 c, int q) {
     const int mx = p.x0 + ((p.x1 - p.x0 + 1) >> 1), my = p.y0 + ((p.y1 - p.y0 + 1) >> 1);
@@ -583,6 +639,8 @@ __global__ void __launch_bounds__(OT_T) k_octree(const Plan* __restrict__ P, Buf
     __shared__ int sSlotCnt[kMaxIni], sSlotStart[kMaxIni];
     __shared__ int sWarpSlot[OT_W][kMaxIni];
     __shared__ u64 sRec[OT_SORT_SMEM];
+    __shared__ int sSplitPart[OT_W][4];
+    __shared__ int sBigList[OT_BIG_LIST], sNBig;
     __shared__ int sSortL[OT_SORT_SMEM], sSortR[OT_SORT_SMEM], sSortStk[192], sSortLeaves;
     __shared__ unsigned sSortLeaf[OT_SORT_SMEM];
 
@@ -705,19 +763,36 @@ __global__ void __launch_bounds__(OT_T) k_octree(const Plan* __restrict__ P, Buf
             // ---------- phase 1: split every node that holds more than one key, in list order (:622-681) ----------
             if (warp == 0) {
                 int run = 0;
+                int nBig = 0;
                 for (int base = 0; base < nNodes; base += 32) {
                     const int i = base + lane;
-                    const bool ex = i < nNodes && node_count(nodes[i]) > 1;
+                    const int cnt = i < nNodes ? node_count(nodes[i]) : 0;
+                    const bool ex = cnt > 1;
                     const unsigned bal = __ballot_sync(0xffffffffu, ex);
                     if (ex) elist[run + __popc(bal & ((1u << lane) - 1))] = i;
+                    if (OT_T > 128) {                               // large levels: nodes with many keys are split by the whole CTA
+                        const unsigned big = __ballot_sync(0xffffffffu, cnt >= OT_BIG_NODE);
+                        const int slot = nBig + __popc(big & ((1u << lane) - 1));
+                        if (cnt >= OT_BIG_NODE && slot < OT_BIG_LIST) sBigList[slot] = run + __popc(bal & ((1u << lane) - 1));
+                        nBig += __popc(big);
+                    }
                     run += __popc(bal);
                 }
-                if (lane == 0) sM = run;
+                if (lane == 0) { sM = run; sNBig = min(nBig, OT_BIG_LIST); }
             }
             __syncthreads();
             const int m = sM;
             if (m == 0) break;                                      // size == prevSize (:685)
-            for (int e = warp; e < m; e += OT_W) split_node_warp(nodes[elist[e]], k0, k1, &cnt4[elist[e]], lane);
+            const int nBig = OT_T > 128 ? sNBig : 0;
+            for (int b = 0; b < nBig; b++) {                        // (uniform)
+                const int e = sBigList[b];
+                split_node_cta(nodes[elist[e]], k0, k1, &cnt4[elist[e]], sSplitPart, tid, OT_W);
+            }
+            for (int e = warp; e < m; e += OT_W) {
+                bool done = false;
+                for (int b = 0; b < nBig; b++) done |= sBigList[b] == e;
+                if (!done) split_node_warp(nodes[elist[e]], k0, k1, &cnt4[elist[e]], lane);
+            }
             __syncthreads();
             if (warp == 0) {
                 int T = 0, X = 0;
