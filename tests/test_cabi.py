@@ -44,8 +44,17 @@ def test_no_cpu_fallback_without_gpu(lib):
     assert e.value.code == capi.ORBB_ERR_CUDA and "no CPU fallback" in str(e.value)
     with pytest.raises(capi.OrbbError):
         ORBmatcher()
-    # the single-pair distance is host code by design (ORBmatcher::DescriptorDistance)
+    # the "next"-row handles fail the same way: vocabulary (ComputeBoW) and rectifier (cv::remap)
+    from orb_slam3_ros_b200.bow import Vocabulary, synthetic_vocabulary
+    from orb_slam3_ros_b200.rectify import Rectifier
     import numpy as np
+    with pytest.raises(capi.OrbbError) as e:
+        Vocabulary(synthetic_vocabulary(3, 2))
+    assert e.value.code == capi.ORBB_ERR_CUDA
+    with pytest.raises(capi.OrbbError) as e:
+        Rectifier(np.zeros((8, 8), np.float32), np.zeros((8, 8), np.float32), (8, 8))
+    assert e.value.code == capi.ORBB_ERR_CUDA
+    # the single-pair distance is host code by design (ORBmatcher::DescriptorDistance)
     assert ORBmatcher.DescriptorDistance(np.zeros(32, np.uint8), np.full(32, 255, np.uint8)) == 256
 
 
@@ -55,3 +64,21 @@ def test_product_never_imports_oracle():
         assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S).replace("# oracle", ""), f"{py} references the oracle"
     for cu in (ROOT / "orb_slam3_ros_b200" / "csrc").iterdir():
         assert "orb_port" not in cu.read_text()
+
+
+def test_argument_errors_are_reported_before_any_device_work(lib):
+    """bad arguments come back as ORBB_ERR_ARG (with text) whether or not a GPU is present"""
+    import ctypes as C
+    import numpy as np
+    from orb_slam3_ros_b200 import capi
+    out = C.c_void_p()
+    m = np.zeros((4, 4), np.float32)
+    assert lib.orbb_rectifier_create(0, capi.ptr(m), capi.ptr(m), 4, 0, 4, 4, 4, C.byref(out)) == capi.ORBB_ERR_ARG      # dst width 0
+    assert lib.orbb_rectifier_create(0, capi.ptr(m), capi.ptr(m), 2, 4, 4, 4, 4, C.byref(out)) == capi.ORBB_ERR_ARG      # stride < width
+    assert lib.orbb_rectifier_create(0, None, capi.ptr(m), 4, 4, 4, 4, 4, C.byref(out)) == capi.ORBB_ERR_ARG
+    assert b"rectifier" in lib.orbb_last_error(None)
+    cb = np.zeros(1, np.int32)
+    assert lib.orbb_vocab_create(0, 0, capi.ptr(cb), capi.ptr(cb), capi.ptr(cb), 0, capi.ptr(cb), capi.ptr(cb), capi.ptr(cb), 1, C.byref(out)) == capi.ORBB_ERR_ARG
+    assert lib.orbb_create(None, C.byref(out)) == capi.ORBB_ERR_ARG
+    assert lib.orbb_extract(None, None, 0, 0, 0, 0, 0, None, None, 0, None, None) == capi.ORBB_ERR_ARG
+    assert lib.orbb_undistort_points(None, None, 0, None, None, 0, None, None) == capi.ORBB_ERR_ARG
