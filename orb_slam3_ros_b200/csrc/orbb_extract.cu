@@ -2,13 +2,15 @@
 //
 // Replaces ORB_SLAM3::ORBextractor (reference orb_slam3/src/ORBextractor.cc) behind the C ABI of
 // include/orbb200.h.  Stages (one launch each per BATCH of frames, all on the handle's stream):
-//   k_pyr_level0 / k_pyr_resize   ComputePyramid            :1170-1195  (cv::resize fixed point + reflect-101 apron)
-//   k_fast                        per-cell cv::FAST + ini/min threshold fallback   :787-872
+//   k_pyr_level0_v / k_pyr_resize_t x (levels-1) / k_pyr_apron16   ComputePyramid   :1170-1195  (orbb_pyr.cuh: cv::resize fixed
+//                                 point + reflect-101 apron)
+//   k_fast_cell                   per-cell cv::FAST + ini/min threshold fallback   :787-872   (orbb_fast3.cuh)
 //   k_octree                      DistributeOctTree         :555-779    (array-rebuild formulation, see
 //                                                                         tests/models/octree_array_model.cpp)
-//   k_blur                        cv::GaussianBlur 7x7 s=2  :1133       (8.8 fixed point)
+//   k_blur                        cv::GaussianBlur 7x7 s=2  :1133       (8.8 fixed point; on a side stream beside k_octree)
 //   k_assemble                    output ordering / scaling / lapping split   :1105-1167
-//   k_orient_desc                 IC_Angle + fastAtan2 + computeOrbDescriptor :76-146
+//   k_orient_desc32               IC_Angle + fastAtan2 + computeOrbDescriptor :76-146
+// plus the input-side rows: k_gray (cvtColor) and k_remap (cv::remap rectification, orbb_rectify.cuh).
 //
 // Compiled with -fmad=false: the un-fused float32 result is the specification.
 #include <limits.h>
@@ -86,26 +88,6 @@ __global__ void __launch_bounds__(256) k_gray(const uint8_t* __restrict__ src, s
 // cv::resize of level l-1 (image pixels only, 4 per thread), then ONE launch that fills the 19-px reflect-101 apron
 // of every level from the level's own pixels (copyMakeBorder BORDER_REFLECT_101 [| BORDER_ISOLATED]).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_pyr_level0(const Plan* __restrict__ P, Bufs B, const uint8_t* __restrict__ src,
-                                                    size_t rowStride, size_t frameStride) {
-    const LevelPlan& L = P->lv[0];
-    const int word = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    const int frame = blockIdx.z;
-    if (word * 4 >= L.w || y >= L.h) return;
-    const uint8_t* s = src + (size_t)frame * frameStride + (size_t)y * rowStride + word * 4;
-    unsigned v;
-    if ((((uintptr_t)s) & 3) == 0 && word * 4 + 3 < L.w) {
-        v = __ldg(reinterpret_cast<const unsigned*>(s));
-    } else {
-        const int n = min(4, L.w - word * 4);
-        v = 0;
-        for (int k = 0; k < n; k++) v |= (unsigned)__ldg(s + k) << (8 * k);
-    }
-    uint8_t* d = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + (size_t)y * L.pitch;
-    reinterpret_cast<unsigned*>(d)[word] = v;
-}
-
 // cv::resize INTER_LINEAR 8UC1 (imgproc/resize.cpp, HResizeLinear/VResizeLinear fixed point): tables hold (source
 // index, packed int16 coefficient pair) per destination column / row, computed on the host exactly as OpenCV does
 // (build_plan).  horizontal: S[sx]*a0 + S[sx+1]*a1 (x2048); vertical: (((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2) >> 2.
@@ -136,31 +118,6 @@ __global__ void __launch_bounds__(256) k_pyr_resize(const Plan* __restrict__ P, 
     }
     uint8_t* d = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + (size_t)dy * L.pitch;
     reinterpret_cast<unsigned*>(d)[word] = packed;
-}
-
-// apron of all levels in one launch: one warp per bordered row (8 rows per CTA).  Rows above / below the image copy
-// the reflected image row word by word; every row then fixes the (at most 12) words at its two ends byte by byte.
-// |offset| <= 19 < image size, so reflect-101 is a single fold.
-__global__ void __launch_bounds__(256) k_pyr_apron(const Plan* __restrict__ P, Bufs B, int totalRows) {
-    int by = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (by >= totalRows) return;
-    const int lane = threadIdx.x & 31, frame = blockIdx.y;
-    int level = 0;
-    while (by >= P->lv[level].h + 2 * kEdge) { by -= P->lv[level].h + 2 * kEdge; level++; }
-    const LevelPlan& L = P->lv[level];
-    const int iy = by - kEdge;
-    const int sy = iy < 0 ? -iy : (iy >= L.h ? 2 * L.h - 2 - iy : iy);
-    uint8_t* roi = B.pyr + (size_t)frame * P->pyrStride + L.roiOff;
-    const uint8_t* srow = roi + (ptrdiff_t)sy * L.pitch;
-    uint8_t* drow = roi + (ptrdiff_t)iy * L.pitch;
-    if (sy != iy) {
-        const int nfull = L.w >> 2;          // image words copied whole (source row is final: written by an earlier kernel)
-        for (int w = lane; w < nfull; w += 32) reinterpret_cast<unsigned*>(drow)[w] = reinterpret_cast<const unsigned*>(srow)[w];
-    }
-    // columns [-19, 0) and [w & ~3, w + 19): lanes 0..18 left, lanes 0..21 right (one byte each)
-    if (lane < kEdge) drow[-1 - lane] = srow[1 + lane];
-    const int x = (L.w & ~3) + lane;
-    if (lane < kEdge + 3 && x < L.w + kEdge && (sy != iy || x >= L.w)) drow[x] = srow[x >= L.w ? 2 * L.w - 2 - x : x];
 }
 
 #include "orbb_pyr.cuh"
@@ -262,124 +219,6 @@ __device__ __forceinline__ bool has_arc9(unsigned m16) {
     t &= t >> 4;          // bit i: 8 consecutive ring pixels starting at i
     t &= m >> 8;          // ... and the 9th
     return (t & 0xffffu) != 0;
-}
-
-// returns max-arc-minimum - 1 (cv::FAST response) if the pixel is a corner at threshold th, else 0
-__device__ __forceinline__ int fast_score(const uint8_t* c, int th) {
-    constexpr int PS = kCellPix;
-    const int v = c[0];
-    int d[16];
-    d[0] = v - c[3 * PS];
-    d[8] = v - c[-3 * PS];
-    bool pos = (d[0] > th) | (d[8] > th), neg = (d[0] < -th) | (d[8] < -th);
-    if (!(pos | neg)) return 0;
-    d[4] = v - c[3];
-    d[12] = v - c[-3];
-    pos &= (d[4] > th) | (d[12] > th);
-    neg &= (d[4] < -th) | (d[12] < -th);
-    if (!(pos | neg)) return 0;
-    d[1] = v - c[3 * PS + 1];   d[2] = v - c[2 * PS + 2];   d[3] = v - c[PS + 3];
-    d[5] = v - c[-PS + 3];      d[6] = v - c[-2 * PS + 2];  d[7] = v - c[-3 * PS + 1];
-    d[9] = v - c[-3 * PS - 1];  d[10] = v - c[-2 * PS - 2]; d[11] = v - c[-PS - 3];
-    d[13] = v - c[PS - 3];      d[14] = v - c[2 * PS - 2];  d[15] = v - c[3 * PS - 1];
-    unsigned mp = 0, mn = 0;
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        mp |= (unsigned)(d[k] > th) << k;
-        mn |= (unsigned)(d[k] < -th) << k;
-    }
-    const bool cp = pos && has_arc9(mp), cn = neg && has_arc9(mn);
-    if (!(cp | cn)) return 0;
-    if (cn) {
-#pragma unroll
-        for (int k = 0; k < 16; k++) d[k] = -d[k];
-    }
-    int a[16], b[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) a[k] = min(d[k], d[(k + 1) & 15]);
-#pragma unroll
-    for (int k = 0; k < 16; k++) b[k] = min(a[k], a[(k + 2) & 15]);
-#pragma unroll
-    for (int k = 0; k < 16; k++) a[k] = min(b[k], b[(k + 4) & 15]);
-    int M = -256;
-#pragma unroll
-    for (int k = 0; k < 16; k++) M = max(M, min(a[k], d[(k + 8) & 15]));
-    return M - 1;
-}
-
-// Straightforward formulation (one thread per pixel, full test in place).  Kept as the readable specification of
-// the per-cell semantics and selectable with ORBB_FAST_V0=1 for A/B debugging; production is k_fast in orbb_fast.cuh.
-__global__ void __launch_bounds__(256) k_fast_v0(const Plan* __restrict__ P, Bufs B) {
-    __shared__ uint8_t sPix[kCellPix * kCellPix];
-    __shared__ uint8_t sScore[kCellPix * kCellPix];
-    __shared__ int sWarpCnt[8];
-    const int frame = blockIdx.y;
-    const int gcell = blockIdx.x;
-    int level = 0;
-    while (level + 1 < P->nlevels && gcell >= P->lv[level + 1].cellBase) level++;
-    const LevelPlan& L = P->lv[level];
-    const int c = gcell - L.cellBase;
-    const int ci = c / L.nCols, cj = c - ci * L.nCols;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int* cellCount = B.cellCount + (size_t)frame * P->cellsTotal + gcell;
-    const int iniX = kMinBorder + cj * L.wCell, iniY = kMinBorder + ci * L.hCell;
-    const int maxX = min(iniX + L.wCell + 6, L.maxBX), maxY = min(iniY + L.hCell + 6, L.maxBY);
-    const int rw = maxX - iniX, rh = maxY - iniY;
-    if (iniY >= L.maxBY - 3 || iniX >= L.maxBX - 6 || rw < 7 || rh < 7) {     // :810,:819 and FAST_t on a <7-px ROI
-        if (tid == 0) *cellCount = 0;
-        return;
-    }
-    const uint8_t* roi = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + (size_t)iniY * L.pitch + iniX;
-    for (int r = warp; r < rh; r += 8)
-        for (int x = lane; x < rw; x += 32) sPix[r * kCellPix + x] = roi[(size_t)r * L.pitch + x];
-    const int iw = rw - 6, ih = rh - 6, npix = iw * ih;
-    const unsigned mdiv = ((1u << 20) + iw - 1) / iw;        // p / iw == (p * mdiv) >> 20 for p < 8192
-    u64* out = B.cellKeys + (size_t)frame * P->cellKeyStride + L.cellKeyBase + (size_t)c * L.cellCap;
-    const int kx = cj * L.wCell, ky = ci * L.hCell;          // :865-866
-    int total = 0;
-    for (int pass = 0; pass < 2 && total == 0; pass++) {
-        const int th = min(max(pass == 0 ? P->iniTh : P->minTh, 0), 255);
-        __syncthreads();
-        for (int i = tid; i < rh * kCellPix; i += 256) sScore[i] = 0;
-        __syncthreads();
-        for (int p = tid; p < npix; p += 256) {
-            const int y = (int)(((unsigned)p * mdiv) >> 20), x = p - y * iw;
-            const int s = fast_score(&sPix[(y + 3) * kCellPix + x + 3], th);
-            sScore[(y + 3) * kCellPix + x + 3] = (uint8_t)s;
-        }
-        __syncthreads();
-        for (int base = 0; base < npix; base += 256) {
-            const int p = base + tid;
-            bool keep = false;
-            int x = 0, y = 0, s = 0;
-            if (p < npix) {
-                y = (int)(((unsigned)p * mdiv) >> 20);
-                x = p - y * iw + 3;
-                y += 3;
-                const uint8_t* q = &sScore[y * kCellPix + x];
-                s = q[0];
-                keep = s > 0 && s > q[-1] && s > q[1] && s > q[-kCellPix - 1] && s > q[-kCellPix] && s > q[-kCellPix + 1] &&
-                       s > q[kCellPix - 1] && s > q[kCellPix] && s > q[kCellPix + 1];
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0) sWarpCnt[warp] = __popc(bal);
-            __syncthreads();
-            int woff = 0, tot = 0;
-#pragma unroll
-            for (int w = 0; w < 8; w++) {
-                const int cnt = sWarpCnt[w];
-                woff += w < warp ? cnt : 0;
-                tot += cnt;
-            }
-            if (keep) {
-                const int pos = total + woff + __popc(bal & ((1u << lane) - 1));
-                out[pos] = (u64)(unsigned)(x + kx) | ((u64)(unsigned)(y + ky) << 16) | ((u64)(unsigned)s << 32);
-            }
-            total += tot;
-            __syncthreads();
-        }
-    }
-    if (tid == 0) *cellCount = total;
 }
 
 #include "orbb_fast.cuh"
@@ -1032,53 +871,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
-__global__ void __launch_bounds__(256) k_orient_desc(const Plan* __restrict__ P, Bufs B) {
-    const int frame = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = B.outCount[frame * 2];
-    const int g = blockIdx.x * 8 + warp;
-    if (g >= n) return;
-    const WorkItem wi = B.work[(size_t)frame * P->kpCap + g];
-    const LevelPlan& L = P->lv[wi.level];
-    // ---- IC_Angle: lane u-15 covers column u of every row of the disc; umax (:453-468) for HALF_PATCH_SIZE 15 ----
-    constexpr int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-    const int u = lane - 15, au = u < 0 ? -u : u;
-    const uint8_t* center = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + (size_t)wi.y * L.pitch + wi.x + u;
-    int m10 = 0, m01 = 0;
-#pragma unroll
-    for (int v = -15; v <= 15; v++) {
-        if (au <= kUmax[v < 0 ? -v : v]) {          // lane 31 (u = 16) is never inside the disc
-            const int val = center[v * L.pitch];
-            m10 += val;
-            m01 += v * val;
-        }
-    }
-    m10 = warp_sum(m10 * u);
-    m01 = warp_sum(m01);
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
-    orbb_keypoint* kp = B.kps + (size_t)frame * P->kpCap + wi.pos;
-    if (lane == 0) kp->angle = angle;
-    // ---- steered BRIEF on the blurred level ----
-    const float factorPI = (float)(3.141592653589793238462643383279502884197 / 180.f);     // :106
-    const float rad = __fmul_rn(angle, factorPI);
-    const float a = (float)cos((double)rad), b = (float)sin((double)rad);                  // :112 (correctly rounded)
-    const uint8_t* bc = B.blur + (size_t)frame * P->blurStride + L.blurOff + (size_t)wi.y * L.bpitch + wi.x;
-    const int step = L.bpitch;
-    unsigned val = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const float4 pt = __ldg(&gPatF[j * 32 + lane]);
-        const int r0 = round_rne(__fadd_rn(__fmul_rn(pt.x, b), __fmul_rn(pt.y, a)));      // :118
-        const int c0 = round_rne(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, b)));      // :119
-        const int r1 = round_rne(__fadd_rn(__fmul_rn(pt.z, b), __fmul_rn(pt.w, a)));
-        const int c1 = round_rne(__fsub_rn(__fmul_rn(pt.z, a), __fmul_rn(pt.w, b)));
-        const int t0 = bc[r0 * step + c0], t1 = bc[r1 * step + c1];
-        val |= (unsigned)(t0 < t1) << j;
-    }
-    B.desc[((size_t)frame * P->kpCap + wi.pos) * 32 + lane] = (uint8_t)val;
-}
-
-// Production version: one warp takes OD_KPW keypoints of a frame through three phases, so that the per-keypoint scalar
+// One warp takes OD_KPW keypoints of a frame through three phases, so that the per-keypoint scalar
 // work (fastAtan2, the double-precision cos / sin) runs once per LANE instead of once per warp:
 //   1. moments: the 31 x 31 window around the keypoint is read as 31 rows x 9 aligned words, consecutive lanes taking
 //      consecutive words (coalesced); each word is dotted (IDP.4A) with two weight words from a table indexed by the
@@ -1500,29 +1293,22 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
     mark(h, ST_PYRAMID);
     ORBB_CUDA(h, cudaMemsetAsync(B.status, 0, sizeof(int) * nframes, st));
     ORBB_CUDA(h, cudaMemsetAsync(B.fbCount, 0, sizeof(int) * nframes, st));
-    static const bool legacyPyr = getenv("ORBB_PYR_LEGACY") != nullptr;      // debugging: the first (generic) formulation
-    int borderedRows = 0;
     for (int l = 0; l < P.nlevels; l++) {
         const LevelPlan& L = P.lv[l];
         dim3 grid(((L.w + 3) / 4 + 31) / 32, (L.h + 7) / 8, nframes);
         if (l == 0) {
-            if (legacyPyr) k_pyr_level0<<<grid, 256, 0, st>>>(h->dPlan, B, dImgs, rowStride, frameStride);
-            else {
-                const int aligned16 = ((uintptr_t)dImgs % 16 == 0) && rowStride % 16 == 0 && frameStride % 16 == 0;
-                k_pyr_level0_v<<<dim3(((L.w + 15) / 16 + 31) / 32, (L.h + 7) / 8, nframes), 256, 0, st>>>(h->dPlan, B, dImgs, rowStride,
-                                                                                                      frameStride, aligned16);
-            }
-        } else if (L.fastResize && !legacyPyr) {
+            const int aligned16 = ((uintptr_t)dImgs % 16 == 0) && rowStride % 16 == 0 && frameStride % 16 == 0;
+            k_pyr_level0_v<<<dim3(((L.w + 15) / 16 + 31) / 32, (L.h + 7) / 8, nframes), 256, 0, st>>>(h->dPlan, B, dImgs, rowStride, frameStride,
+                                                                                                  aligned16);
+        } else if (L.fastResize) {
             constexpr int rowsPerCta = PR_ROWS * (PR_THREADS / 32);
             static const bool tmaResize = getenv("ORBB_RESIZE_NO_TMA") == nullptr;      // (A/B switch; TMA staging measured 3 % faster)
             if (tmaResize && L.fastResize == 2) k_pyr_resize_t<<<dim3(grid.x, (L.h + rowsPerCta - 1) / rowsPerCta, nframes), PR_THREADS, 0, st>>>(h->dPlan, B, l);
             else k_pyr_resize_s<<<dim3(grid.x, (L.h + rowsPerCta - 1) / rowsPerCta, nframes), PR_THREADS, 0, st>>>(h->dPlan, B, l);
         } else k_pyr_resize<<<grid, 256, 0, st>>>(h->dPlan, B, l);
         h->launches++;
-        borderedRows += L.h + 2 * kEdge;
     }
-    if (legacyPyr) k_pyr_apron<<<dim3((borderedRows + 7) / 8, nframes), 256, 0, st>>>(h->dPlan, B, borderedRows);
-    else {
+    {
         ApronTable T;
         for (int l = 0; l <= ORBB_MAX_LEVELS; l++) T.base[l] = l < P.nlevels ? P.apron[l].itemBase : P.apronItems;
         k_pyr_apron16<<<dim3((P.apronItems + 255) / 256, nframes), 256, 0, st>>>(h->dPlan, B, T, P.nlevels);
@@ -1530,17 +1316,9 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
     h->launches++;
     const bool fork = !h->profiling;
     mark(h, ST_FAST);
-    static const char* fastMode = getenv("ORBB_FAST_MODE");      // debugging: "v0" / "cell" select the older formulations
-    if (fastMode && !strcmp(fastMode, "v0")) {
-        k_fast_v0<<<dim3(P.cellsTotal, nframes), 256, 0, st>>>(h->dPlan, B);
-    } else if (fastMode && !strcmp(fastMode, "cell")) {
-        k_fast<<<dim3(P.cellsTotal, nframes), FAST_THREADS, 0, st>>>(h->dPlan, B, 0);
-    }
-    const bool legacyFast = fastMode && (!strcmp(fastMode, "v0") || !strcmp(fastMode, "cell"));
-    if (legacyFast) {
-        mark(h, ST_FAST_CELLS);
-        mark(h, ST_FAST_RETRY);
-    } else if (!fastMode || !strcmp(fastMode, "cellwarp")) {
+    // ORBB_FAST_MODE = "band" / "split" select the two earlier formulations for A/B runs (same results)
+    static const char* fastMode = getenv("ORBB_FAST_MODE");
+    if (!fastMode || (strcmp(fastMode, "band") && strcmp(fastMode, "split"))) {
         if (P.cellTp == 64) k_fast_cell<64><<<dim3(P.cellsTotal, nframes), 32, P.cellSmem, st>>>(h->dPlan, B);
         else k_fast_cell<96><<<dim3(P.cellsTotal, nframes), 32, P.cellSmem, st>>>(h->dPlan, B);
         mark(h, ST_FAST_CELLS);
@@ -1557,7 +1335,7 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
         k_fast_cells<<<dim3(P.cellsTotal, nframes), FC_THREADS, 0, st>>>(B, P.cellsTotal, P.blurStride, P.cellKeyStride);
         mark(h, ST_FAST_RETRY);
         k_fast<<<dim3(std::min(P.cellsTotal, 48), nframes), FAST_THREADS, 0, st>>>(h->dPlan, B, 1);
-        h->launches += 2;
+        h->launches += 3;
     }
     mark(h, ST_OCTREE);
     // fork: the blur only needs the pyramid; on its own stream it fills the SMs that the latency-bound quadtree leaves idle.
@@ -1577,9 +1355,7 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
     mark(h, ST_ASSEMBLE);
     k_assemble<<<nframes, 256, 0, st>>>(h->dPlan, B, lap0, lap1);
     mark(h, ST_ORIENT_DESC);
-    static const bool legacyDesc = getenv("ORBB_DESC_LEGACY") != nullptr;
-    if (legacyDesc) k_orient_desc<<<dim3((P.kpCap + 7) / 8, nframes), 256, 0, st>>>(h->dPlan, B);
-    else k_orient_desc32<<<dim3((P.kpCap + OD_THREADS / 32 * OD_KPW - 1) / (OD_THREADS / 32 * OD_KPW), nframes), OD_THREADS, 0, st>>>(h->dPlan, B);
+    k_orient_desc32<<<dim3((P.kpCap + OD_THREADS / 32 * OD_KPW - 1) / (OD_THREADS / 32 * OD_KPW), nframes), OD_THREADS, 0, st>>>(h->dPlan, B);
     mark(h, ST_D2H);
     h->launches += 5;
     ORBB_CUDA(h, cudaGetLastError());
