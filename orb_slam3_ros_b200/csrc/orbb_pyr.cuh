@@ -121,27 +121,43 @@ __global__ void __launch_bounds__(PR_THREADS, 16) k_pyr_resize_s(const Plan* __r
 // memory (short scoreboard) instead of L1/L2 (long scoreboard, which is what the kernel above waits on most).
 constexpr int PR_SROWS = 48, PR_SPITCH = 208;
 
+__device__ __forceinline__ unsigned vresize4(const int (&h0)[4], const int (&h1)[4], int b0, int b1) {
+    unsigned out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int v = (__mulhi(b0, h0[k]) + __mulhi(b1, h1[k]) + 2) >> 2;      // 0 .. 255 (coefficients sum to 2048)
+        out |= (unsigned)v << (8 * k);
+    }
+    return out;
+}
+
 __global__ void __launch_bounds__(PR_THREADS, 12) k_pyr_resize_t(const Plan* __restrict__ P, Bufs B, int level) {
     __shared__ __align__(128) uint8_t sSrc[PR_SROWS * PR_SPITCH];
+    __shared__ __align__(16) int4 sRow[(PR_THREADS / 32) * PR_ROWS];      // per destination row of the CTA: {r0, r1, b0 << 16, b1 << 16}
     __shared__ __align__(8) unsigned long long sBar;
     const LevelPlan& L = P->lv[level];
     const LevelPlan& S = P->lv[level - 1];
     const int tid = threadIdx.x;
     const int word = blockIdx.x * 32 + (tid & 31);
-    const int dyc = blockIdx.y * (PR_THREADS / 32) * PR_ROWS;             // first destination row of the CTA
+    constexpr int rowsPerCta = (PR_THREADS / 32) * PR_ROWS;
+    const int dyc = blockIdx.y * rowsPerCta;                              // first destination row of the CTA
     const int dy0 = dyc + (tid >> 5) * PR_ROWS;
     const int frame = blockIdx.z;
     const int Lw = L.w, Lh = L.h, Lpitch = L.pitch, Sh1 = S.h - 1, Spitch = S.pitch;
-    // ---- stage: source rows rs0..rs1, bytes [xs0, xs0 + PR_SPITCH) ----
+    // ---- stage: source rows rs0..rs1, bytes [xs0, xs0 + PR_SPITCH); the row table of the CTA ----
     const int2* tyc = B.tab + L.tabY;
     const int rs0 = min(max(__ldg(tyc + dyc).x, 0), Sh1);
-    const int rs1 = min(max(__ldg(tyc + min(dyc + (PR_THREADS / 32) * PR_ROWS, Lh) - 1).x + 1, 0), Sh1);
+    const int rs1 = min(max(__ldg(tyc + min(dyc + rowsPerCta, Lh) - 1).x + 1, 0), Sh1);
     const int xs0 = __ldg(B.tab + L.tabX + blockIdx.x * 128).x & ~15;
     const uint8_t* sbase = B.pyr + (size_t)frame * P->pyrStride + S.roiOff + xs0;
     if (tid == 0) {
         mbar_init(&sBar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(&sBar, (rs1 - rs0 + 1) * PR_SPITCH);
+    }
+    if (tid < rowsPerCta && dyc + tid < Lh) {
+        const int2 t = __ldg(tyc + dyc + tid);
+        sRow[tid] = make_int4(min(max(t.x, 0), Sh1) - rs0, min(max(t.x + 1, 0), Sh1) - rs0, (int)(t.y << 16), (int)(t.y & 0xffff0000));
     }
     __syncthreads();
     if (tid <= rs1 - rs0) tma_bulk_g2s(sSrc + tid * PR_SPITCH, sbase + (size_t)(rs0 + tid) * Spitch, PR_SPITCH, &sBar);
@@ -162,40 +178,36 @@ __global__ void __launch_bounds__(PR_THREADS, 12) k_pyr_resize_t(const Plan* __r
             asm volatile("" : "+r"(c[k].sh), "+r"(c[k].m));
         }
     }
-    const uint8_t* srows = sSrc + (4 * wbase - xs0) - rs0 * PR_SPITCH;
     uint8_t* d = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + (size_t)dy0 * Lpitch + 4 * word;
-    const int2* ty = tyc + dy0;
+    const int4* rowt = sRow + (tid >> 5) * PR_ROWS;
     const int rows = min(PR_ROWS, Lh - dy0);
-    int cached = -1, hc[4] = {0, 0, 0, 0};
     mbar_wait(&sBar, 0);
-#pragma unroll
-    for (int r = 0; r < PR_ROWS; r++) {
-        if (r < rows) {
-            const int2 t = __ldg(ty + r);
-            const int r0 = min(max(t.x, 0), Sh1), r1 = min(max(t.x + 1, 0), Sh1);
-            const int b0 = (int)(t.y << 16), b1 = (int)(t.y & 0xffff0000);
-            int h0[4];
-            if (r0 == cached) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) h0[k] = hc[k];
-            } else {
-                hresize4s(reinterpret_cast<const unsigned*>(srows + r0 * PR_SPITCH), c, h0);
-            }
-            if (r1 != r0) hresize4s(reinterpret_cast<const unsigned*>(srows + r1 * PR_SPITCH), c, hc);
-            else {
-#pragma unroll
-                for (int k = 0; k < 4; k++) hc[k] = h0[k];
-            }
-            cached = r1;
-            unsigned out = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int v = (__mulhi(b0, h0[k]) + __mulhi(b1, hc[k]) + 2) >> 2;
-                out |= (unsigned)v << (8 * k);
-            }
-            *reinterpret_cast<unsigned*>(d + (size_t)r * Lpitch) = out;
-        }
+    // Walk down the SOURCE rows of the strip: every source row gets its horizontal pass exactly once (into ha / hb in turn),
+    // and the destination row whose lower source row it is gets emitted right after (the source row index grows with every
+    // destination row, so that is at most one).  All branches are warp-uniform.
+    int r = 0;
+    int4 cur = rowt[0];                                       // {r0, r1, b0, b1} of the next destination row to emit
+    int s = cur.x;                                            // newest source row computed
+    const uint8_t* sp = sSrc + (4 * wbase - xs0) + s * PR_SPITCH;
+    int ha[4], hb[4];
+    hresize4s(reinterpret_cast<const unsigned*>(sp), c, ha);
+    // emit every destination row whose lower source row is the newest one (`nw`; `pv` = the row before it)
+#define PR_EMIT(nw, pv)                                                                                         \
+    while (cur.y == s) {                                                                                        \
+        *reinterpret_cast<unsigned*>(d) = cur.x == s ? vresize4(nw, nw, cur.z, cur.w) : vresize4(pv, nw, cur.z, cur.w); \
+        d += Lpitch;                                                                                            \
+        if (++r == rows) return;                                                                                \
+        cur = rowt[r];                                                                                          \
     }
+    while (true) {
+        PR_EMIT(ha, hb)
+        sp += PR_SPITCH; s++;
+        hresize4s(reinterpret_cast<const unsigned*>(sp), c, hb);
+        PR_EMIT(hb, ha)
+        sp += PR_SPITCH; s++;
+        hresize4s(reinterpret_cast<const unsigned*>(sp), c, ha);
+    }
+#undef PR_EMIT
 }
 
 // Apron of every level in one launch.  Work item = one 16-byte chunk of a bordered row that contains apron bytes: all
