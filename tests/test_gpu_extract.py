@@ -271,3 +271,34 @@ def test_color_input_matches_cvtcolor_then_extract():
             m1, k1, d1 = ge.extract_color(img, rgb, (0, 1000))
             assert np.array_equal(ge.debug_level(0, 0), g), (channels, rgb)
             assert_same_features(k0, d0, m0, k1, d1, m1, f"channels={channels} rgb={rgb}")
+
+
+def test_random_geometries_match_oracle():
+    """seeded sweep over odd image sizes / level counts / budgets: every stage (bordered pyramid, raw FAST keys, quadtree
+    selection, blur) and the final features against the oracle -- exercises the alignment-dependent paths (TMA row staging,
+    16-byte apron chunks, word-wise resize) on widths that are not multiples of 4 or 16"""
+    rng = np.random.default_rng(2024)
+    sizes = [(131, 257), (203, 333), (97, 401), (311, 190), (480, 641), (255, 1000), (150, 150), (402, 599)]
+    for i, (h, w) in enumerate(sizes):
+        nl = int(rng.integers(2, 9))
+        while min(h, w) / 1.2 ** (nl - 1) < 80:            # every level must hold at least one 35-px cell row and column
+            nl -= 1
+        nf = int(rng.integers(150, 1600))
+        lap = (0, 0) if i % 2 else (int(w * 0.3), int(w * 0.6))
+        check_against_port(synth.frame(h, w, 40 + i), nf, nl, lap=lap)
+
+
+def test_single_frame_graph_is_rebuilt_when_the_call_changes():
+    """the single-frame path replays a captured CUDA graph; changing the lapping area, the image size or toggling the stage
+    profiling on one handle must give the same results as a fresh handle"""
+    ge = ORBextractor(500, 1.2, 5)
+    img_a, img_b = synth.frame(240, 320, 7), synth.frame(200, 400, 8)
+    seq = [(img_a, (0, 0)), (img_a, (100, 220)), (img_a, (100, 220)), (img_b, (0, 0)), (img_a, (0, 0))]
+    for step, (img, lap) in enumerate(seq):
+        if step == 2:
+            ge.set_profiling(True)
+        if step == 3:
+            ge.set_profiling(False)
+        m1, k1, d1 = ge(img, None, lap)
+        rc, k0, d0, m0 = port.PortExtractor(500, 1.2, 5).extract(img, lap)
+        assert_same_features(k0, d0, m0, k1, d1, m1, f"step {step}")
