@@ -1196,7 +1196,7 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
         int maxW = 0, maxH = 0;
         for (int l = 0; l < nl; l++) { maxW = std::max(maxW, P.lv[l].wCell); maxH = std::max(maxH, P.lv[l].hCell); }
         P.cellTp = maxW + 21 <= 64 ? 64 : 96;
-        P.cellSmem = (maxH + 6) * P.cellTp + (maxH + 2) * P.cellTp + FB_WARP_SMEM;
+        P.cellSmem = (maxH + 6) * P.cellTp + (maxH + 2) * (P.cellTp == 64 ? 48 : 80) + FB_WARP_SMEM;
     }
     P.cellsTotal = cells; P.blurTilesTotal = tiles; P.kpCap = kpCap; P.fsTotal = fsTiles;
     P.pyrStride = pyrBytes; P.blurStride = blurBytes;

@@ -28,7 +28,7 @@ constexpr int FB_MAXW = FB_TP - 36;        // max interior width of a segment (+
 constexpr int FB_MAXCELLS = FB_WARPS;
 constexpr int FB_CANDS = 32 + 256;         // candidate stack: < 32 left over + one round of phase A (32 lanes x 8 px)
 constexpr int FB_CORNS = 64;               // corner stack: < 32 left over + one round of phase B
-constexpr int FB_NC = 256;                 // corners of one cell kept for the list-driven NMS (more: NMS scans the score map)
+constexpr int FB_NC = 128;                 // corners of one cell kept for the list-driven NMS (more: NMS scans the score map)
 constexpr int FB_WARP_SMEM = 2 * (FB_CANDS + FB_CORNS + FB_NC);      // bytes of stacks per warp
 
 // Quick reject of 4 pixels (one word) as a byte mask: bit 7 of byte k is set when pixel k can still be a corner, i.e.
@@ -49,10 +49,12 @@ __device__ __forceinline__ unsigned quick_bytes4(unsigned wl, unsigned wc, unsig
 
 // One cell, one warp.  tile: row t = level row gy0 - 3 + t, column = level column - X0.  score: row s = interior row s - 1.
 // Returns the number of NMS survivors parked in `park`.
-template <int TP>
+// The score map has its own pitch SP and column origin: score column = tile column - sxo (k_fast_cell keeps only the cell's
+// columns plus a zero column on each side, which is what lets 32 cells fit an SM).
+template <int TP, int SP>
 __device__ __forceinline__ int cell_pass(const uint8_t* __restrict__ tile, uint8_t* __restrict__ score, unsigned short* candS,
                                          unsigned short* cornS, unsigned short* allS, unsigned* __restrict__ park, int cx0, int cx1,
-                                         int ih, int th, int lane) {
+                                         int ih, int th, int lane, int sxo) {
     constexpr int PS = TP, TPW = TP / 4;
     const int wa = cx0 >> 2, nwc = max(((cx1 + 3) >> 2) - wa, 2);        // (>= 2 keeps the reciprocal in 32 bits; extra words are masked)
     const unsigned mInv = 0xffffffffu / (unsigned)nwc + 1u;
@@ -88,8 +90,10 @@ __device__ __forceinline__ int cell_pass(const uint8_t* __restrict__ tile, uint8
                     const int e1 = min3i(m3[k + 1], m3[(k + 4) & 15], m3[(k + 7) & 15]);
                     M = max3i(M, e0, e1);
                 }
-                score[pos - 2 * PS] = (uint8_t)(M - 1);          // tile row = interior row + 3, score row = interior row + 1
-                if (nAll + lane < FB_NC) allS[nAll + lane] = (unsigned short)(pos - 2 * PS);
+                const int t = pos / TP;                              // tile row = interior row + 3, score row = interior row + 1
+                const int sp = (t - 2) * SP + (pos - t * TP) - sxo;
+                score[sp] = (uint8_t)(M - 1);
+                if (nAll + lane < FB_NC) allS[nAll + lane] = (unsigned short)sp;
             }
             nAll += n;
             __syncwarp();
@@ -165,11 +169,11 @@ __device__ __forceinline__ int cell_pass(const uint8_t* __restrict__ tile, uint8
         bool keep = false;
         unsigned rec = 0;
         if (valid) {
-            const int r1 = sp / TP, x = sp - r1 * TP;
+            const int r1 = sp / SP, x = sp - r1 * SP + sxo;
             const uint8_t* q = score + sp;
-            int m = max((int)q[-TP], (int)q[TP]);
-            if (x > cx0) m = max(m, max3i((int)q[-TP - 1], (int)q[-1], (int)q[TP - 1]));
-            if (x + 1 < cx1) m = max(m, max3i((int)q[-TP + 1], (int)q[1], (int)q[TP + 1]));
+            int m = max((int)q[-SP], (int)q[SP]);
+            if (x > cx0) m = max(m, max3i((int)q[-SP - 1], (int)q[-1], (int)q[SP - 1]));
+            if (x + 1 < cx1) m = max(m, max3i((int)q[-SP + 1], (int)q[1], (int)q[SP + 1]));
             keep = sc > m;
             rec = ((unsigned)(r1 - 1) << 16) | ((unsigned)(x - cx0) << 8) | (unsigned)sc;
         }
@@ -188,7 +192,7 @@ __device__ __forceinline__ int cell_pass(const uint8_t* __restrict__ tile, uint8
         for (int b0 = 0; b0 < ih * wc; b0 += 32) {
             const int i = b0 + lane;
             const int r = i / wc, x = cx0 + i - r * wc;
-            const int sp = (r + 1) * TP + x;
+            const int sp = (r + 1) * SP + x - sxo;
             const int sc = i < ih * wc ? score[sp] : 0;
             nms(sc > 0, sp, sc);
         }
@@ -240,9 +244,9 @@ __global__ void __launch_bounds__(FB_THREADS, 10) k_fast_band(const Plan* __rest
         unsigned short* candS = stacks;
         unsigned short* cornS = candS + FB_CANDS;
         unsigned short* allS = cornS + FB_CORNS;
-        nSurv = cell_pass<FB_TP>(tile, score, candS, cornS, allS, park, cx0, cx1, ih, min(max(P->iniTh, 0), 255), lane);
+        nSurv = cell_pass<FB_TP, FB_TP>(tile, score, candS, cornS, allS, park, cx0, cx1, ih, min(max(P->iniTh, 0), 255), lane, 0);
         if (nSurv == 0)                                           // :833-846 (scores do not depend on the threshold: the map stays valid)
-            nSurv = cell_pass<FB_TP>(tile, score, candS, cornS, allS, park, cx0, cx1, ih, min(max(P->minTh, 0), 255), lane);
+            nSurv = cell_pass<FB_TP, FB_TP>(tile, score, candS, cornS, allS, park, cx0, cx1, ih, min(max(P->minTh, 0), 255), lane, 0);
     }
     // ---- E: raster order by rank counting; keys are relative to the 16-px border (:865-866) ----
     __syncwarp();
@@ -263,7 +267,8 @@ __global__ void __launch_bounds__(FB_THREADS, 10) k_fast_band(const Plan* __rest
 // finished cell frees its resources at once and up to 32 cells are in flight per SM, none waiting for a slower neighbour
 // (in k_fast_band the CTA lives as long as its slowest cell, e.g. one that needs the minThFAST retry).
 template <int TP>
-__global__ void __launch_bounds__(32) k_fast_cell(const Plan* __restrict__ P, Bufs B) {
+__global__ void __launch_bounds__(32, 32) k_fast_cell(const Plan* __restrict__ P, Bufs B) {
+    constexpr int SP = TP == 64 ? 48 : 80;                    // score pitch: cell width (<= 43 / 71) + a zero column on each side
     extern __shared__ __align__(128) uint8_t fcSmem[];
     __shared__ __align__(8) unsigned long long sBar;
     const int gcell = blockIdx.x, frame = blockIdx.y, lane = threadIdx.x;
@@ -279,7 +284,7 @@ __global__ void __launch_bounds__(32) k_fast_cell(const Plan* __restrict__ P, Bu
     const int X0 = (cd.gx0 - 3) & ~15;
     uint8_t* tile = fcSmem;
     uint8_t* score = fcSmem + rowsT * TP;                     // TP is a multiple of 16
-    unsigned short* candS = reinterpret_cast<unsigned short*>(score + (ih + 2) * TP);
+    unsigned short* candS = reinterpret_cast<unsigned short*>(score + (ih + 2) * SP);
     unsigned short* cornS = candS + FB_CANDS;
     unsigned short* allS = cornS + FB_CORNS;
     const uint8_t* roi = B.pyr + (size_t)frame * P->pyrStride + L.roiOff;
@@ -290,15 +295,16 @@ __global__ void __launch_bounds__(32) k_fast_cell(const Plan* __restrict__ P, Bu
     }
     __syncwarp();
     for (int r = lane; r < rowsT; r += 32) tma_bulk_g2s(tile + r * TP, roi + (ptrdiff_t)(cd.gy0 - 3 + r) * L.pitch + X0, TP, &sBar);
-    for (int i = lane; i < (ih + 2) * (TP / 16); i += 32) reinterpret_cast<uint4*>(score)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = lane; i < (ih + 2) * (SP / 16); i += 32) reinterpret_cast<uint4*>(score)[i] = make_uint4(0, 0, 0, 0);
     __syncwarp();
     mbar_wait(&sBar, 0);
     const int cx0 = cd.gx0 - X0, cx1 = cd.gx1 - X0;
+    const int sxo = cx0 - 1;                                  // score column 0 = the zero column left of the cell
     // survivors are parked (unordered) in the quadtree's second key buffer, which k_octree only uses later
     unsigned* park = reinterpret_cast<unsigned*>(B.keys + ((size_t)frame * 2 + 1) * P->rawStride + cd.outOff);
-    int nSurv = cell_pass<TP>(tile, score, candS, cornS, allS, park, cx0, cx1, ih, min(max(P->iniTh, 0), 255), lane);
+    int nSurv = cell_pass<TP, SP>(tile, score, candS, cornS, allS, park, cx0, cx1, ih, min(max(P->iniTh, 0), 255), lane, sxo);
     if (nSurv == 0)                                           // :833-846 (scores do not depend on the threshold: the map stays valid)
-        nSurv = cell_pass<TP>(tile, score, candS, cornS, allS, park, cx0, cx1, ih, min(max(P->minTh, 0), 255), lane);
+        nSurv = cell_pass<TP, SP>(tile, score, candS, cornS, allS, park, cx0, cx1, ih, min(max(P->minTh, 0), 255), lane, sxo);
     // ---- E: raster order by rank counting; keys are relative to the 16-px border (:865-866) ----
     __syncwarp();
     u64* keysOut = B.cellKeys + (size_t)frame * P->cellKeyStride + cd.outOff;
