@@ -36,22 +36,18 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
 
 ORBextractor::~ORBextractor() { orbb_destroy(mpHandle); }
 
-int ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*_mask*/, std::vector<cv::KeyPoint>& _keypoints,
-                             cv::OutputArray _descriptors, std::vector<int>& vLappingArea) {
-    if (_image.empty()) return -1;
-    cv::Mat image = _image.getMat();
-    assert(image.type() == CV_8UC1);
-
-    const int cap = orbb_max_keypoints(mpHandle);
+void* ORBextractor::Staging(int& cap) {
+    cap = orbb_max_keypoints(mpHandle);
     mvKeypointStaging.resize((size_t)cap * sizeof(orbb_keypoint));
     mvDescStaging.resize((size_t)cap * 32);
-    orbb_keypoint* kps = reinterpret_cast<orbb_keypoint*>(mvKeypointStaging.data());
-    int n = 0, monoIndex = 0;
-    const int rc = orbb_extract(mpHandle, image.data, image.cols, image.rows, (size_t)image.step, vLappingArea[0], vLappingArea[1],
-                                kps, mvDescStaging.data(), cap, &n, &monoIndex);
-    if (rc == ORBB_ERR_EMPTY) return -1;
-    if (rc != ORBB_OK) throw std::runtime_error(std::string("orbb_extract failed: ") + orbb_last_error(mpHandle));
+    return mvKeypointStaging.data();
+}
 
+// common tail of the extraction entry points: error mapping, output containers, pyramid views
+int ORBextractor::Deliver(int rc, int n, int monoIndex, std::vector<cv::KeyPoint>& _keypoints, cv::OutputArray _descriptors) {
+    if (rc == ORBB_ERR_EMPTY) return -1;
+    if (rc != ORBB_OK) throw std::runtime_error(std::string("liborbb200 extraction failed: ") + orbb_last_error(mpHandle));
+    const orbb_keypoint* kps = reinterpret_cast<const orbb_keypoint*>(mvKeypointStaging.data());
     if (n == 0) {
         _descriptors.release();
     } else {
@@ -81,6 +77,50 @@ int ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*_mask*/, st
         }
     }
     return monoIndex;
+}
+
+int ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*_mask*/, std::vector<cv::KeyPoint>& _keypoints,
+                             cv::OutputArray _descriptors, std::vector<int>& vLappingArea) {
+    if (_image.empty()) return -1;
+    cv::Mat image = _image.getMat();
+    assert(image.type() == CV_8UC1);
+    int cap = 0, n = 0, monoIndex = 0;
+    orbb_keypoint* kps = static_cast<orbb_keypoint*>(Staging(cap));
+    const int rc = orbb_extract(mpHandle, image.data, image.cols, image.rows, (size_t)image.step, vLappingArea[0], vLappingArea[1],
+                                kps, mvDescStaging.data(), cap, &n, &monoIndex);
+    return Deliver(rc, n, monoIndex, _keypoints, _descriptors);
+}
+
+int ORBextractor::ExtractColor(const unsigned char* data, int cols, int rows, size_t step, int channels, bool bRGB,
+                               std::vector<cv::KeyPoint>& _keypoints, cv::OutputArray _descriptors, std::vector<int>& vLappingArea) {
+    if (!data || cols <= 0 || rows <= 0) return -1;
+    int cap = 0, n = 0, monoIndex = 0;
+    orbb_keypoint* kps = static_cast<orbb_keypoint*>(Staging(cap));
+    int rc = orbb_extract_color(mpHandle, data, cols, rows, step, channels, bRGB ? 1 : 0, vLappingArea[0], vLappingArea[1], kps,
+                                mvDescStaging.data(), cap, &n, &monoIndex);
+    if (rc == ORBB_ERR_CAPACITY) {                          // first frame of this size: the plan allows more keypoints than the estimate
+        kps = static_cast<orbb_keypoint*>(Staging(cap));
+        rc = orbb_extract_color(mpHandle, data, cols, rows, step, channels, bRGB ? 1 : 0, vLappingArea[0], vLappingArea[1], kps,
+                                mvDescStaging.data(), cap, &n, &monoIndex);
+    }
+    return Deliver(rc, n, monoIndex, _keypoints, _descriptors);
+}
+
+int ORBextractor::ExtractRectified(orbb_rectifier* rect, cv::InputArray _rawImage, std::vector<cv::KeyPoint>& _keypoints,
+                                   cv::OutputArray _descriptors, std::vector<int>& vLappingArea) {
+    if (_rawImage.empty()) return -1;
+    cv::Mat image = _rawImage.getMat();
+    assert(image.type() == CV_8UC1);
+    int cap = 0, n = 0, monoIndex = 0;
+    orbb_keypoint* kps = static_cast<orbb_keypoint*>(Staging(cap));
+    int rc = orbb_extract_rectified(mpHandle, rect, image.data, (size_t)image.step, vLappingArea[0], vLappingArea[1], kps,
+                                    mvDescStaging.data(), cap, &n, &monoIndex);
+    if (rc == ORBB_ERR_CAPACITY) {
+        kps = static_cast<orbb_keypoint*>(Staging(cap));
+        rc = orbb_extract_rectified(mpHandle, rect, image.data, (size_t)image.step, vLappingArea[0], vLappingArea[1], kps,
+                                    mvDescStaging.data(), cap, &n, &monoIndex);
+    }
+    return Deliver(rc, n, monoIndex, _keypoints, _descriptors);
 }
 
 }  // namespace ORB_SLAM3

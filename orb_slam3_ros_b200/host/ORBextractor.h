@@ -11,6 +11,7 @@
 #include <opencv2/opencv.hpp>
 
 struct orbb_extractor;
+struct orbb_rectifier;
 
 namespace ORB_SLAM3 {
 
@@ -42,6 +43,14 @@ public:
     // ---- extensions (not in the reference) ----
     void SetPyramidDownload(bool enabled) { mbDownloadPyramid = enabled; }
     orbb_extractor* Handle() { return mpHandle; }          // for orbb_stereo_match(hL, hR, ...)
+    // Colour frame (CV_8UC3 / CV_8UC4 data, `channels` bytes per pixel): the cvtColor(.., COLOR_*2GRAY) that Tracking applies
+    // before building the Frame (Tracking.cc:1498-1525) runs on the device; bRGB = Tracking's mbRGB.
+    int ExtractColor(const unsigned char* data, int cols, int rows, size_t step, int channels, bool bRGB,
+                     std::vector<cv::KeyPoint>& _keypoints, cv::OutputArray _descriptors, std::vector<int>& vLappingArea);
+    // Raw (unrectified) stereo frame: the cv::remap of System::TrackStereo (System.cc:233-240) runs on the device, the
+    // rectified image never comes back to the host.  `rect` from orbb_rectifier_create (maps of Settings.cc:506-509).
+    int ExtractRectified(orbb_rectifier* rect, cv::InputArray _rawImage, std::vector<cv::KeyPoint>& _keypoints,
+                         cv::OutputArray _descriptors, std::vector<int>& vLappingArea);
 
 protected:
     int nfeatures;
@@ -54,6 +63,9 @@ protected:
     std::vector<float> mvInvScaleFactor;
     std::vector<float> mvLevelSigma2;
     std::vector<float> mvInvLevelSigma2;
+
+    int Deliver(int rc, int n, int monoIndex, std::vector<cv::KeyPoint>& _keypoints, cv::OutputArray _descriptors);
+    void* Staging(int& cap);
 
     orbb_extractor* mpHandle;
     bool mbDownloadPyramid;

@@ -57,6 +57,20 @@ public:
         if (rc != ORBB_OK) throw std::runtime_error(std::string("orbb_knn2 failed: ") + orbb_matcher_last_error(mpMatcher));
     }
 
+    // Frame::UndistortKeyPoints (Frame.cc:747-780): cv::undistortPoints(mat, mat, K, mDistCoef, cv::Mat(), mK) over the keypoints.
+    // K = (fx, fy, cx, cy); dist = mDistCoef.ptr<float>(), ndist = mDistCoef.rows (4 or 5); dist[0] == 0 copies the keys (:749).
+    void UndistortKeyPoints(const std::vector<cv::KeyPoint>& keys, float fx, float fy, float cx, float cy, const float* dist, int ndist,
+                            std::vector<cv::KeyPoint>& keysUn) {
+        keysUn = keys;
+        if (keys.empty()) return;
+        std::vector<float> xy(keys.size() * 2), out(keys.size() * 2);
+        for (size_t i = 0; i < keys.size(); i++) { xy[2 * i] = keys[i].pt.x; xy[2 * i + 1] = keys[i].pt.y; }
+        const float K4[4] = {fx, fy, cx, cy};
+        const int rc = orbb_undistort_points(mpMatcher, xy.data(), (int)keys.size(), K4, dist, ndist, K4, out.data());
+        if (rc != ORBB_OK) throw std::runtime_error(std::string("orbb_undistort_points failed: ") + orbb_matcher_last_error(mpMatcher));
+        for (size_t i = 0; i < keys.size(); i++) { keysUn[i].pt.x = out[2 * i]; keysUn[i].pt.y = out[2 * i + 1]; }
+    }
+
 private:
     orbb_matcher* mpMatcher;
 };

@@ -6,6 +6,7 @@
 // argv[1] = raw 8-bit gray file, argv[2] = width, argv[3] = height.  Prints a checksum the python test compares.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "ORBextractor.h"
@@ -53,6 +54,44 @@ int main(int argc, char** argv) {
     const int d01 = mvKeys.size() > 1 ? ORBmatcherGPU::DescriptorDistance(mDescriptors.row(0), mDescriptors.row(1)) : -1;
     printf("n=%zu mono=%d desc=%dx%d sum=%llu pyr1=%dx%d psum=%llu d01=%d\n", mvKeys.size(), monoIdx, mDescriptors.rows, mDescriptors.cols, sum,
            p1.cols, p1.rows, psum, d01);
+
+    // ---- the input-side extensions: colour frame, raw stereo frame + rectifier, keypoint undistortion ----
+    unsigned long long sumC = 0, sumR = 0, sumU = 0;
+    {
+        std::vector<unsigned char> bgr((size_t)w * h * 3);
+        for (size_t i = 0; i < (size_t)w * h; i++) { bgr[3 * i] = buf[i]; bgr[3 * i + 1] = (unsigned char)(255 - buf[i]); bgr[3 * i + 2] = (unsigned char)(buf[i] / 2); }
+        std::vector<cv::KeyPoint> kc;
+        cv::Mat dc;
+        std::vector<int> lap0 = {0, 0};
+        mpORBextractorLeft->ExtractColor(bgr.data(), w, h, (size_t)w * 3, 3, false, kc, dc, lap0);
+        for (size_t i = 0; i < kc.size(); i++) {
+            sumC = sumC * 1000003ull + (unsigned)(kc[i].pt.x * 16) + 7ull * (unsigned)(kc[i].pt.y * 16) + 13ull * kc[i].octave;
+            for (int b = 0; b < 32; b++) sumC = sumC * 31ull + dc.ptr<uchar>((int)i)[b];
+        }
+        // rectifier: a shift by (2.25, -1.5) px with constant-zero border
+        std::vector<float> mx((size_t)w * h), my((size_t)w * h);
+        for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) { mx[(size_t)y * w + x] = x + 2.25f; my[(size_t)y * w + x] = y - 1.5f; }
+        orbb_rectifier* rect = nullptr;
+        if (orbb_rectifier_create(0, mx.data(), my.data(), (size_t)w, w, h, w, h, &rect) != ORBB_OK) return 7;
+        std::vector<cv::KeyPoint> kr;
+        cv::Mat dr;
+        mpORBextractorLeft->ExtractRectified(rect, im, kr, dr, lap0);
+        orbb_rectifier_destroy(rect);
+        for (size_t i = 0; i < kr.size(); i++) {
+            sumR = sumR * 1000003ull + (unsigned)(kr[i].pt.x * 16) + 7ull * (unsigned)(kr[i].pt.y * 16) + 13ull * kr[i].octave;
+            for (int b = 0; b < 32; b++) sumR = sumR * 31ull + dr.ptr<uchar>((int)i)[b];
+        }
+        ORBmatcherGPU gpu;
+        const float dist[4] = {-0.28340811f, 0.07395907f, 0.00019359f, 1.76187114e-05f};
+        std::vector<cv::KeyPoint> ku;
+        gpu.UndistortKeyPoints(mvKeys, 458.654f, 457.296f, 367.215f, 248.375f, dist, 4, ku);
+        for (size_t i = 0; i < ku.size(); i++) {
+            unsigned a, b2;
+            memcpy(&a, &ku[i].pt.x, 4); memcpy(&b2, &ku[i].pt.y, 4);
+            sumU = sumU * 1000003ull + a + 7ull * b2;
+        }
+        printf("sumC=%llu nC=%zu sumR=%llu nR=%zu sumU=%llu\n", sumC, kc.size(), sumR, kr.size(), sumU);
+    }
     delete mpORBextractorLeft;
     return 0;
 }

@@ -56,3 +56,26 @@ def test_adapter_matches_c_abi(tmp_path):
     assert int(got["sum"]) == s
     assert got["pyr1"] == f"{p1.shape[1]}x{p1.shape[0]}" and int(got["psum"]) == psum
     assert int(got["d01"]) == ORBmatcher.DescriptorDistance(d[0], d[1])
+    # the extensions: colour input, rectified extraction, keypoint undistortion -- against the python binding of the same C ABI
+    from orb_slam3_ros_b200.rectify import Rectifier
+
+    def ksum(k, d):
+        s = 0
+        for i in range(len(k)):
+            s = (s * 1000003 + int(np.float32(k["x"][i]) * np.float32(16)) + 7 * int(np.float32(k["y"][i]) * np.float32(16)) + 13 * int(k["octave"][i])) & M
+            for b in d[i]:
+                s = (s * 31 + int(b)) & M
+        return s
+    bgr = np.stack([img, 255 - img, img // 2], 2)
+    _, kc, dc = ge.extract_color(bgr, rgb=False)
+    assert int(got["nC"]) == len(kc) and int(got["sumC"]) == ksum(kc, dc)
+    yy, xx = np.mgrid[0:240, 0:320].astype(np.float32)
+    r = Rectifier(xx + np.float32(2.25), yy - np.float32(1.5), img.shape)
+    _, kr, dr = r.extract(ge, img)
+    assert int(got["nR"]) == len(kr) and int(got["sumR"]) == ksum(kr, dr)
+    un = ORBmatcher().undistort_points(np.stack([k["x"], k["y"]], 1), (458.654, 457.296, 367.215, 248.375),
+                                       [-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05])
+    s = 0
+    for a, b in un.view(np.uint32):
+        s = (s * 1000003 + int(a) + 7 * int(b)) & M
+    assert int(got["sumU"]) == s
