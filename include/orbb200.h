@@ -17,6 +17,7 @@
  *   orbb_hamming_distance           ORBmatcher::DescriptorDistance        orb_slam3/src/ORBmatcher.cc:2058-2074
  *   orbb_best2_csr                  best / second-best candidate scans    orb_slam3/src/ORBmatcher.cc:77-120 (and :273-325,
  *                                                                         :1743-1768 ...: same loop shape)
+ *   orbb_rotation_check_csr         rotation histogram + ComputeThreeMaxima   orb_slam3/src/ORBmatcher.cc:345-352, :405-423, :2012-2053
  *   orbb_knn2 / orbb_knn2_partial   cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, 2)   orb_slam3/src/Frame.cc:1144
  *   orbb_knn2_merge                 (top-2 merge of database shards after an all-gather; no reference counterpart)
  *   orbb_vocab_create / orbb_bow_transform   DBoW2 TemplatedVocabulary::transform via Frame::ComputeBoW   orb_slam3/src/Frame.cc:738-745,
@@ -246,6 +247,13 @@ int orbb_extract_batch_rectified(orbb_extractor* h, orbb_rectifier* r, const uin
                                  size_t frame_stride, int lap0, int lap1);
 int orbb_extract_rectified(orbb_extractor* h, orbb_rectifier* r, const uint8_t* img, size_t stride, int lap0, int lap1, orbb_keypoint* kps,
                            uint8_t* desc, int capacity, int* n_out, int* mono_index);
+
+/* ---- rotation-consistency filter of the match scans ---------------------------------------------------------------- */
+/* ORBmatcher.cc:345-352 (votes), :405-423 (discard), ComputeThreeMaxima :2012-2053, for nsets independent match sets at once
+ * (set s = matches rowptr[s] .. rowptr[s+1]): angle_a / angle_b = the keypoint angles of the two sides of every match;
+ * keep[i] = 1 when match i falls into one of the three fullest rotation bins of its set; ind3[3s..3s+2] = those bins (-1 = none). */
+int orbb_rotation_check_csr(orbb_matcher* m, const float* angle_a, const float* angle_b, int total, const int32_t* rowptr, int nsets,
+                            uint8_t* keep, int32_t* ind3);
 
 /* ---- Frame::UndistortKeyPoints ("next" row) ------------------------------------------------------------------------- */
 /* cv::undistortPoints(xy, out, K, dist, noArray(), newK) for n points (Frame.cc:766: newK = K).  K4 / newK4 = {fx, fy, cx, cy};

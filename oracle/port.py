@@ -392,3 +392,35 @@ def undistort_points(xy, K4, dist, new_K4=None):
         live &= ~neg
     xx, yy, ww = nfx * x + 0. * y + ncx, 0. * x + nfy * y + ncy, 1. / (0. * x + 0. * y + 1.)
     return np.stack([(xx * ww).astype(np.float32), (yy * ww).astype(np.float32)], 1)
+
+
+def rotation_check(angle_a, angle_b):
+    """the rotation-consistency filter of the match scans (reference ORBmatcher.cc:236, :345-352, :405-423 and
+    ComputeThreeMaxima :2012-2053) for one set of matches -> (keep[n] bool, (ind1, ind2, ind3))"""
+    a = np.asarray(angle_a, np.float32)
+    b = np.asarray(angle_b, np.float32)
+    factor = np.float32(1.0) / np.float32(30)
+    rot = a - b
+    rot = np.where(rot < 0, rot + np.float32(360.0), rot).astype(np.float32)
+    x = (rot * factor).astype(np.float32)
+    bins = np.floor(x.astype(np.float64) + 0.5).astype(np.int64)      # round(): half away from zero, x >= 0 here
+    bins[bins == 30] = 0
+    hist = np.bincount(bins, minlength=30)
+    max1 = max2 = max3 = 0
+    ind1 = ind2 = ind3 = -1
+    for i in range(30):
+        s = int(hist[i])
+        if s > max1:
+            max3, max2, max1 = max2, max1, s
+            ind3, ind2, ind1 = ind2, ind1, i
+        elif s > max2:
+            max3, max2 = max2, s
+            ind3, ind2 = ind2, i
+        elif s > max3:
+            max3, ind3 = s, i
+    if np.float32(max2) < np.float32(0.1) * np.float32(max1):
+        ind2 = ind3 = -1
+    elif np.float32(max3) < np.float32(0.1) * np.float32(max1):
+        ind3 = -1
+    keep = (bins == ind1) | (bins == ind2) | (bins == ind3)
+    return keep, (ind1, ind2, ind3)

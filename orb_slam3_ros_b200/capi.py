@@ -86,6 +86,7 @@ SYMBOLS = [
     ("orbb_remap", _I, [_VP, _VP, _SZ, _VP, _SZ]),
     ("orbb_extract_batch_rectified", _I, [_VP, _VP, _VP, _I, _SZ, _SZ, _I, _I]),
     ("orbb_extract_rectified", _I, [_VP, _VP, _VP, _SZ, _I, _I, _VP, _VP, _I, _VP, _VP]),
+    ("orbb_rotation_check_csr", _I, [_VP, _VP, _VP, _I, _VP, _I, _VP, _VP]),
     ("orbb_undistort_points", _I, [_VP, _VP, _I, _VP, _VP, _I, _VP, _VP]),
     ("orbb_host_alloc", _VP, [_SZ]),
     ("orbb_host_free", None, [_VP]),

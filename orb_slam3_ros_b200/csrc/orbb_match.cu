@@ -397,6 +397,49 @@ __device__ __forceinline__ int warp_sum_i(int v) {
     return v;
 }
 
+// Rotation-consistency filter of the match scans (reference ORBmatcher.cc:345-352 and siblings + ComputeThreeMaxima,
+// :2012-2053): every match votes for the bin round((angle_a - angle_b [+360]) * (1/HISTO_LENGTH)) of a 30-bin histogram, the three
+// fullest bins are found by the reference's single pass (later bins do not displace earlier equal ones; second / third are
+// dropped when below 10 % of the first) and the matches of all other bins are discarded.  One CTA per match set.
+__global__ void __launch_bounds__(256) k_rotation_check(const float* __restrict__ angA, const float* __restrict__ angB,
+                                                        const int* __restrict__ rowptr, uint8_t* __restrict__ keep, int* __restrict__ ind3) {
+    __shared__ int sHist[30];
+    __shared__ int sInd[3];
+    const int set = blockIdx.x, tid = threadIdx.x;
+    const int beg = rowptr[set], end = rowptr[set + 1];
+    if (tid < 30) sHist[tid] = 0;
+    __syncthreads();
+    const float factor = 1.0f / 30;                              // :236
+    auto bin_of = [&](int i) {
+        float rot = __fsub_rn(angA[i], angB[i]);
+        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+        int bin = (int)roundf(__fmul_rn(rot, factor));
+        if (bin == 30) bin = 0;
+        return min(max(bin, 0), 29);                             // (the reference asserts the range)
+    };
+    for (int i = beg + tid; i < end; i += 256) atomicAdd(&sHist[bin_of(i)], 1);
+    __syncthreads();
+    if (tid == 0) {
+        int max1 = 0, max2 = 0, max3 = 0, i1 = -1, i2 = -1, i3 = -1;
+        for (int i = 0; i < 30; i++) {
+            const int sz = sHist[i];
+            if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; i3 = i2; i2 = i1; i1 = i; }
+            else if (sz > max2) { max3 = max2; max2 = sz; i3 = i2; i2 = i; }
+            else if (sz > max3) { max3 = sz; i3 = i; }
+        }
+        if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { i2 = -1; i3 = -1; }
+        else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) i3 = -1;
+        sInd[0] = i1; sInd[1] = i2; sInd[2] = i3;
+        ind3[3 * set] = i1; ind3[3 * set + 1] = i2; ind3[3 * set + 2] = i3;
+    }
+    __syncthreads();
+    const int i1 = sInd[0], i2 = sInd[1], i3 = sInd[2];
+    for (int i = beg + tid; i < end; i += 256) {
+        const int b = bin_of(i);
+        keep[i] = b == i1 || b == i2 || b == i3;
+    }
+}
+
 // "Next" row: Frame::UndistortKeyPoints (reference orb_slam3/src/Frame.cc:747-780) = cv::undistortPoints(pts, pts, K, D,
 // noArray(), K) over the N keypoints: OpenCV's cvUndistortPointsInternal with its default criteria (5 fixed-point
 // iterations, no epsilon test), in double precision without fused multiply-adds (this file is built with -fmad=false),
@@ -898,6 +941,36 @@ int orbb_distinctive_csr(orbb_matcher* m, const uint8_t* desc, int ntotal, const
     m->launches++;
     ORBM_CUDA(m, cudaGetLastError());
     ORBM_CUDA(m, cudaMemcpyAsync(best, m->scratch[3], bo, cudaMemcpyDeviceToHost, m->stream));
+    ORBM_CUDA(m, cudaStreamSynchronize(m->stream));
+    return ORBB_OK;
+}
+
+// ---- rotation-consistency filter of the match scans (ORBmatcher.cc:345-352, :405-423, ComputeThreeMaxima :2012-2053) -------
+int orbb_rotation_check_csr(orbb_matcher* m, const float* angle_a, const float* angle_b, int total, const int32_t* rowptr, int nsets,
+                            uint8_t* keep, int32_t* ind3) {
+    if (!m || total < 0 || nsets < 0 || !rowptr || (total > 0 && (!angle_a || !angle_b || !keep)) || (nsets > 0 && !ind3))
+        return m_err(m, ORBB_ERR_ARG, "bad argument");
+    if (nsets == 0) return ORBB_OK;
+    for (int s = 0; s < nsets; s++)
+        if (rowptr[s + 1] < rowptr[s] || rowptr[s + 1] > total) return m_err(m, ORBB_ERR_ARG, "bad rowptr at set %d", s);
+    ORBM_CUDA(m, cudaSetDevice(m->device));
+    const size_t ba = std::max<size_t>(sizeof(float) * (size_t)total, 4), br = sizeof(int) * (size_t)(nsets + 1);
+    int rc;
+    if ((rc = ensure_scratch(m, 0, 2 * ba)) || (rc = ensure_scratch(m, 1, br)) || (rc = ensure_scratch(m, 2, std::max<size_t>(total, 1))) ||
+        (rc = ensure_scratch(m, 3, sizeof(int) * 3 * (size_t)nsets)))
+        return rc;
+    float* dA = (float*)m->scratch[0];
+    float* dB = dA + std::max(total, 1);
+    if (total > 0) {
+        ORBM_CUDA(m, cudaMemcpyAsync(dA, angle_a, sizeof(float) * total, cudaMemcpyHostToDevice, m->stream));
+        ORBM_CUDA(m, cudaMemcpyAsync(dB, angle_b, sizeof(float) * total, cudaMemcpyHostToDevice, m->stream));
+    }
+    ORBM_CUDA(m, cudaMemcpyAsync(m->scratch[1], rowptr, br, cudaMemcpyHostToDevice, m->stream));
+    k_rotation_check<<<nsets, 256, 0, m->stream>>>(dA, dB, (const int*)m->scratch[1], (uint8_t*)m->scratch[2], (int*)m->scratch[3]);
+    m->launches++;
+    ORBM_CUDA(m, cudaGetLastError());
+    if (total > 0) ORBM_CUDA(m, cudaMemcpyAsync(keep, m->scratch[2], total, cudaMemcpyDeviceToHost, m->stream));
+    ORBM_CUDA(m, cudaMemcpyAsync(ind3, m->scratch[3], sizeof(int) * 3 * (size_t)nsets, cudaMemcpyDeviceToHost, m->stream));
     ORBM_CUDA(m, cudaStreamSynchronize(m->stream));
     return ORBB_OK;
 }

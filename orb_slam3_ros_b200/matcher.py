@@ -128,6 +128,20 @@ class ORBmatcher:
                    self._m, matcher=True)
         return best
 
+    # ---- rotation-consistency filter (ORBmatcher.cc:345-352, :405-423) ----
+    def rotation_check(self, angle_sets):
+        """angle_sets: list of (angle_a[n], angle_b[n]) float32 pairs, one per match set -> list of (keep[n] bool, (ind1, ind2, ind3))"""
+        sizes = [len(a) for a, _ in angle_sets]
+        rowptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+        total = int(rowptr[-1])
+        A = np.ascontiguousarray(np.concatenate([np.asarray(a, np.float32) for a, _ in angle_sets]) if total else np.zeros(0, np.float32))
+        Bn = np.ascontiguousarray(np.concatenate([np.asarray(b, np.float32) for _, b in angle_sets]) if total else np.zeros(0, np.float32))
+        keep = np.zeros(max(total, 1), np.uint8)
+        ind3 = np.zeros((max(len(sizes), 1), 3), np.int32)
+        capi.check(self._lib.orbb_rotation_check_csr(self._m, capi.ptr(A), capi.ptr(Bn), total, capi.ptr(rowptr), len(sizes), capi.ptr(keep),
+                                                     capi.ptr(ind3)), self._m, matcher=True)
+        return [(keep[lo:hi].astype(bool), tuple(int(v) for v in ind3[s])) for s, (lo, hi) in enumerate(zip(rowptr[:-1], rowptr[1:]))]
+
     # ---- ComputeThreeMaxima (ORBmatcher.cc:2012-2053), host ----
     @staticmethod
     def ComputeThreeMaxima(histo_sizes):

@@ -228,3 +228,22 @@ def test_stereo_full_size_batch_properties():
     ur0, dp0, _, _, _ = port.stereo(pl, pr, kl, dl, kr, dr, np.float32(bf), np.float32(b))
     n = counts[f, 0]
     assert n == len(ur0) and np.array_equal(ur[f, :n], ur0) and np.array_equal(dp[f, :n], dp0)
+
+
+def test_rotation_check_matches_oracle(matcher):
+    """rotation histogram + ComputeThreeMaxima (ORBmatcher.cc:345-352, :405-423, :2012-2053), several match sets per call"""
+    rng = np.random.default_rng(12)
+    sets = []
+    for n, spread in ((900, 8.0), (300, 60.0), (57, 200.0), (1, 1.0), (0, 1.0), (2000, 0.5)):
+        base = rng.uniform(0, 360, n).astype(np.float32)
+        delta = rng.normal(rng.uniform(0, 360), spread, n)
+        other = np.mod(base - delta, 360).astype(np.float32)
+        sets.append((base, other))
+    # exact bin boundaries (multiples of 15 and 30 degrees), equal angles, and a tie between the fullest bins
+    a = np.float32(np.arange(0, 360, 7.5))
+    sets.append((a, np.zeros_like(a)))
+    sets.append((np.float32([10, 10, 50, 50, 200, 200, 200, 200]), np.float32([10, 10, 10, 10, 10, 10, 50, 50])))
+    got = matcher.rotation_check(sets)
+    for (a, b), (keep, ind) in zip(sets, got):
+        want_keep, want_ind = port.rotation_check(a, b)
+        assert ind == want_ind and np.array_equal(keep, want_keep)
