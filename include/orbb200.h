@@ -17,6 +17,7 @@
  *   orbb_hamming_distance           ORBmatcher::DescriptorDistance        orb_slam3/src/ORBmatcher.cc:2058-2074
  *   orbb_best2_csr                  best / second-best candidate scans    orb_slam3/src/ORBmatcher.cc:77-120 (and :273-325,
  *                                                                         :1743-1768 ...: same loop shape)
+ *   orbb_rgbd_stereo_batch          Frame::ComputeStereoFromRGBD   orb_slam3/src/Frame.cc:984-1005   ("next" row)
  *   orbb_rotation_check_csr         rotation histogram + ComputeThreeMaxima   orb_slam3/src/ORBmatcher.cc:345-352, :405-423, :2012-2053
  *   orbb_knn2 / orbb_knn2_partial   cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, 2)   orb_slam3/src/Frame.cc:1144
  *   orbb_knn2_merge                 (top-2 merge of database shards after an all-gather; no reference counterpart)
@@ -157,6 +158,13 @@ int orbb_stereo_match(orbb_extractor* hL, orbb_extractor* hR, int frame, float b
 /* batched: all frames [0,nframes) of the last batch; results stay on the device (see orbb_stereo_fetch) */
 int orbb_stereo_match_batch(orbb_extractor* hL, orbb_extractor* hR, int nframes, float bf, float b);
 int orbb_stereo_fetch(orbb_extractor* hL, int nframes, float* u_right, float* depth, int capacity);
+/* RGB-D counterpart ("next" row): Frame::ComputeStereoFromRGBD (orb_slam3/src/Frame.cc:984-1005) over the keypoints of the
+ * extractor's last batch.  dev_depth: device-resident depth maps of the frames (float32, or uint16 scaled by depth_factor like
+ * Tracking::GrabImageRGBD's convertTo, Tracking.cc:1576-1577); strides in bytes.  K4 = {fx, fy, cx, cy}, dist = the ndist
+ * coefficients of mDistCoef (the undistorted x of Frame::UndistortKeyPoints enters mvuRight); bf = mbf.  Asynchronous on the
+ * handle's stream; results via orbb_stereo_fetch. */
+int orbb_rgbd_stereo_batch(orbb_extractor* h, const void* dev_depth, int depth_is_u16, float depth_factor, size_t row_stride,
+                           size_t frame_stride, int nframes, const float* K4, const float* dist, int ndist, float bf);
 
 /* ---- Hamming matching ----------------------------------------------------------------------------------------- */
 /* host-side 256-bit Hamming distance (a single pair never goes to the GPU) */

@@ -424,3 +424,20 @@ def rotation_check(angle_a, angle_b):
         ind3 = -1
     keep = (bins == ind1) | (bins == ind2) | (bins == ind3)
     return keep, (ind1, ind2, ind3)
+
+
+def rgbd_stereo(kps_xy, depth, K4, dist, bf):
+    """Frame::ComputeStereoFromRGBD (reference Frame.cc:984-1005): depth = float32 [h, w]; kps_xy = the (distorted) keypoints;
+    the undistorted x comes from undistort_points (Frame::UndistortKeyPoints) -> (uRight[n], depth[n]) float32, -1 = none"""
+    xy = np.asarray(kps_xy, np.float32).reshape(-1, 2)
+    depth = np.asarray(depth, np.float32)
+    xu = undistort_points(xy, K4, dist)[:, 0]
+    d = depth[xy[:, 1].astype(np.int64), xy[:, 0].astype(np.int64)]       # Mat::at<float>(v, u) with float arguments: int conversion
+    ok = d > 0
+    ur = np.full(len(xy), -1, np.float32)
+    dp = np.full(len(xy), -1, np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        q = (np.float32(bf) / d).astype(np.float32)
+    ur[ok] = (xu[ok] - q[ok]).astype(np.float32)
+    dp[ok] = d[ok]
+    return ur, dp

@@ -63,6 +63,7 @@ SYMBOLS = [
     ("orbb_stereo_match", _I, [_VP, _VP, _I, _F, _F, _VP, _VP, _VP, _VP, _I, _PI]),
     ("orbb_stereo_match_batch", _I, [_VP, _VP, _I, _F, _F]),
     ("orbb_stereo_fetch", _I, [_VP, _I, _VP, _VP, _I]),
+    ("orbb_rgbd_stereo_batch", _I, [_VP, _VP, _I, _F, _SZ, _SZ, _I, _VP, _VP, _I, _F]),
     ("orbb_hamming_distance", _I, [_VP, _VP]),
     ("orbb_matcher_create", _I, [_I, C.POINTER(_VP)]),
     ("orbb_matcher_destroy", None, [_VP]),

@@ -447,11 +447,8 @@ __global__ void __launch_bounds__(256) k_rotation_check(const float* __restrict_
 // the tilt terms must be zero (ORB-SLAM3's pinhole model has 4 or 5 coefficients).
 struct UndistortParams { double fx, fy, cx, cy, nfx, nfy, ncx, ncy, k[12]; };
 
-__global__ void __launch_bounds__(256) k_undistort(const float2* __restrict__ in, float2* __restrict__ out, int n, const UndistortParams p) {
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    const float2 pt = in[i];
-    const double u = (double)pt.x, v = (double)pt.y;
+__device__ __forceinline__ float2 undistort_point(float px, float py, const UndistortParams& p) {
+    const double u = (double)px, v = (double)py;
     const double ifx = 1. / p.fx, ify = 1. / p.fy;
     double x = (u - p.cx) * ifx, y = (v - p.cy) * ify;
     const double x0 = x, y0 = y;
@@ -467,7 +464,41 @@ __global__ void __launch_bounds__(256) k_undistort(const float2* __restrict__ in
     }
     // RR = P (new camera matrix), R = identity: xx = fx'*x + 0*y + cx', ww = 1 / (0*x + 0*y + 1)
     const double xx = p.nfx * x + 0. * y + p.ncx, yy = 0. * x + p.nfy * y + p.ncy, ww = 1. / (0. * x + 0. * y + 1.);
-    out[i] = make_float2((float)(xx * ww), (float)(yy * ww));
+    return make_float2((float)(xx * ww), (float)(yy * ww));
+}
+
+__global__ void __launch_bounds__(256) k_undistort(const float2* __restrict__ in, float2* __restrict__ out, int n, const UndistortParams p) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float2 pt = in[i];
+    out[i] = undistort_point(pt.x, pt.y, p);
+}
+
+// "Next" row (RGB-D counterpart of S1): Frame::ComputeStereoFromRGBD (reference orb_slam3/src/Frame.cc:984-1005) over the
+// keypoints of the extractor's last batch: d = imDepth.at<float>(v, u) at the (distorted) keypoint, mvDepth = d and
+// mvuRight = kpU.x - mbf / d when d > 0, else -1 / -1; kpU = the undistorted keypoint (Frame::UndistortKeyPoints, :747-780;
+// dist[0] == 0: kpU = kp).  A 16-bit depth map is scaled on the fly like Tracking::GrabImageRGBD does with
+// imDepth.convertTo(imDepth, CV_32F, mDepthMapFactor) (Tracking.cc:1576-1577: float(src) * float(alpha), one rounding).
+__global__ void __launch_bounds__(256) k_rgbd_stereo(const Plan* __restrict__ P, Bufs B, const uint8_t* __restrict__ depth, int isU16,
+                                                     float factor, size_t rowStride, size_t frameStride, const UndistortParams p,
+                                                     int undist, float mbf) {
+    const int frame = blockIdx.y;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int n = B.outCount[frame * 2];
+    if (i >= n) return;
+    const size_t fo = (size_t)frame * P->kpCap;
+    const orbb_keypoint kp = B.kps[fo + i];
+    const int u = (int)kp.x, v = (int)kp.y;                  // Mat::at<float>(float, float): the indices convert to int
+    const uint8_t* row = depth + (size_t)frame * frameStride + (size_t)v * rowStride;
+    const float d = isU16 ? __fmul_rn((float)reinterpret_cast<const unsigned short*>(row)[u], factor) : reinterpret_cast<const float*>(row)[u];
+    float ur = -1.f, dp = -1.f;
+    if (d > 0) {
+        const float xu = undist ? undistort_point(kp.x, kp.y, p).x : kp.x;
+        dp = d;
+        ur = __fsub_rn(xu, __fdiv_rn(mbf, d));
+    }
+    B.uRight[fo + i] = ur;
+    B.depth[fo + i] = dp;
 }
 
 // Right-image keypoints bucketed by row (counting sort on (int)y, one CTA per frame): the reference's vRowIndices table
@@ -1029,6 +1060,27 @@ int orbb_stereo_match_batch(orbb_extractor* hL, orbb_extractor* hR, int nframes,
     k_stereo_cut<<<nframes, 256, 0, hL->stream>>>(hL->dPlan, hL->b);
     hL->launches += 2;
     ORBB_CUDA(hL, cudaGetLastError());
+    return ORBB_OK;
+}
+
+int orbb_rgbd_stereo_batch(orbb_extractor* h, const void* dev_depth, int depth_is_u16, float depth_factor, size_t row_stride,
+                           size_t frame_stride, int nframes, const float* K4, const float* dist, int ndist, float bf) {
+    if (!h) return ORBB_ERR_ARG;
+    if (!h->planValid || nframes < 1 || nframes > h->lastFrames) return set_err(h, ORBB_ERR_ARG, "rgbd: the extractor must hold a batch of >= %d frames", nframes);
+    if (!dev_depth || !K4 || ndist < 0 || ndist > 12 || (ndist > 0 && !dist)) return set_err(h, ORBB_ERR_ARG, "rgbd: bad argument");
+    const Plan& P = h->plan;
+    const size_t px = depth_is_u16 ? 2 : 4;
+    if (row_stride < (size_t)P.W * px || frame_stride < row_stride * (size_t)P.H) return set_err(h, ORBB_ERR_ARG, "rgbd: depth strides smaller than the image");
+    ORBB_CUDA(h, cudaSetDevice(h->device));
+    UndistortParams p;
+    p.fx = K4[0]; p.fy = K4[1]; p.cx = K4[2]; p.cy = K4[3];
+    p.nfx = K4[0]; p.nfy = K4[1]; p.ncx = K4[2]; p.ncy = K4[3];          // Frame.cc:766: P = mK
+    for (int i = 0; i < 12; i++) p.k[i] = i < ndist ? (double)dist[i] : 0.0;
+    const int undist = ndist > 0 && dist[0] != 0.0f;                      // Frame.cc:749
+    k_rgbd_stereo<<<dim3((P.kpCap + 255) / 256, nframes), 256, 0, h->stream>>>(h->dPlan, h->b, (const uint8_t*)dev_depth, depth_is_u16, depth_factor,
+                                                                         row_stride, frame_stride, p, undist, bf);
+    h->launches++;
+    ORBB_CUDA(h, cudaGetLastError());
     return ORBB_OK;
 }
 

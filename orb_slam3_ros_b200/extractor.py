@@ -222,6 +222,19 @@ def stereo_match_batch(ext_left, ext_right, nframes, bf, b):
     capi.check(capi.load().orbb_stereo_match_batch(ext_left._h, ext_right._h, nframes, bf, b), ext_left._h)
 
 
+def rgbd_stereo_batch(ext, depth_dev, nframes, width, height, K4, dist, bf, depth_is_u16=False, depth_factor=1.0, row_stride=None,
+                      frame_stride=None):
+    """Frame::ComputeStereoFromRGBD (Frame.cc:984-1005) for the extractor's last batch; depth maps resident on the device
+    (torch CUDA tensor / address, float32 or uint16); results via stereo_fetch(ext, nframes)"""
+    px = 2 if depth_is_u16 else 4
+    row_stride = row_stride or width * px
+    frame_stride = frame_stride or row_stride * height
+    k = np.ascontiguousarray(K4, np.float32)
+    d = np.ascontiguousarray(dist, np.float32).ravel()
+    capi.check(capi.load().orbb_rgbd_stereo_batch(ext._h, capi.ptr(depth_dev), int(depth_is_u16), float(depth_factor), row_stride, frame_stride,
+                                                  nframes, capi.ptr(k), capi.ptr(d), len(d), float(bf)), ext._h)
+
+
 def stereo_fetch(ext_left, nframes):
     cap = ext_left.max_keypoints
     ur = np.zeros((nframes, cap), np.float32)

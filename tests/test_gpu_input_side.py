@@ -65,3 +65,32 @@ def test_undistort_points_matches_oracle_bit_for_bit():
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), dist
     assert np.array_equal(m.undistort_points(xy, K4, [0.0, 0.1, 0.0, 0.0]), xy)       # Frame.cc:749
     assert m.undistort_points(np.zeros((0, 2), np.float32), K4, [0.1, 0, 0, 0]).shape == (0, 2)
+
+
+def test_rgbd_stereo_matches_oracle():
+    """Frame::ComputeStereoFromRGBD (Frame.cc:984-1005) for a TUM-shape batch: float32 depth maps and 16-bit ones with the
+    depth-map factor, with and without lens distortion"""
+    from orb_slam3_ros_b200.extractor import rgbd_stereo_batch, stereo_fetch
+    B, H, W = 3, 480, 640
+    frames = synth.sequence(H, W, B)
+    ge = ORBextractor(1000, max_batch=B)
+    ge.extract_batch_device(torch.from_numpy(frames).cuda(), B, W, H)
+    counts, kps, _ = ge.fetch(B)
+    rng = np.random.default_rng(9)
+    raw = rng.integers(0, 40000, (B, H, W)).astype(np.uint16)
+    raw[rng.random((B, H, W)) < 0.2] = 0                                   # holes in the depth map
+    factor = np.float32(1.0) / np.float32(5000.0)                          # TUM: DepthMapFactor 5000 (Tracking.cc:617)
+    depth_f = (raw.astype(np.float32) * factor).astype(np.float32)
+    K4 = (517.306408, 516.469215, 318.643040, 255.313989)                  # TUM1.yaml
+    bf = np.float32(40.0)
+    for dist in ([0.262383, -0.953104, -0.005358, 0.002628, 1.163314], [0.0, 0.0, 0.0, 0.0]):
+        for as_u16 in (False, True):
+            dev = torch.from_numpy(raw.view(np.int16) if as_u16 else depth_f).cuda()
+            rgbd_stereo_batch(ge, dev, B, W, H, K4, dist, float(bf), depth_is_u16=as_u16, depth_factor=float(factor))
+            ur, dp = stereo_fetch(ge, B)
+            for f in range(B):
+                n = counts[f, 0]
+                xy = np.stack([kps[f, :n]["x"], kps[f, :n]["y"]], 1)
+                ur0, dp0 = port.rgbd_stereo(xy, depth_f[f], K4, dist, bf)
+                assert np.array_equal(dp[f, :n], dp0) and np.array_equal(ur[f, :n].view(np.uint32), ur0.view(np.uint32)), (dist[0], as_u16, f)
+            assert 0.1 < (dp[0, :counts[0, 0]] < 0).mean() < 0.3
