@@ -302,3 +302,30 @@ def test_single_frame_graph_is_rebuilt_when_the_call_changes():
         m1, k1, d1 = ge(img, None, lap)
         rc, k0, d0, m0 = port.PortExtractor(500, 1.2, 5).extract(img, lap)
         assert_same_features(k0, d0, m0, k1, d1, m1, f"step {step}")
+
+
+def test_two_extractors_on_two_threads():
+    """the reference runs the left and the right extractor on two std::threads (Frame.cc:122-125): two handles used
+    concurrently from two host threads (graph capture, plan building and result copies included) give the serial results"""
+    import threading
+    imgs = [synth.frame(240, 320, 30 + i) for i in range(4)]
+    want = [port.PortExtractor(400, 1.2, 5).extract(im, (0, 0)) for im in imgs]
+    errors = []
+
+    def worker(offset):
+        try:
+            ge = ORBextractor(400, 1.2, 5)
+            for rep in range(6):
+                i = (offset + rep) % len(imgs)
+                m1, k1, d1 = ge(imgs[i], None, (0, 0))
+                rc, k0, d0, m0 = want[i]
+                assert_same_features(k0, d0, m0, k1, d1, m1, f"thread {offset} rep {rep}")
+        except Exception as e:                                 # noqa: BLE001 -- reported below, in the main thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in (0, 2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
