@@ -26,6 +26,7 @@
  *   orbb_search_area_best2          Frame::GetFeaturesInArea + SearchByProjection scan   orb_slam3/src/Frame.cc:657-723, ORBmatcher.cc:71-120 ("next" row)
  *   orbb_distinctive_csr            MapPoint::ComputeDistinctiveDescriptors   orb_slam3/src/MapPoint.cc:329-403   ("next" row)
  *   orbb_extract_color / _batch_color   cv::cvtColor(..., COLOR_*2GRAY) + extraction   orb_slam3/src/Tracking.cc:1498-1525, :1605-1618 ("next" row)
+ *   orbb_extract_resized / _batch_resized   cv::resize(im, imToFeed, newImSize) before tracking   orb_slam3/src/System.cc:241-244 ("next" row)
  *   orbb_rectifier_* / orbb_remap / orbb_extract_rectified / _batch_rectified   cv::remap(img, M1, M2, INTER_LINEAR) before tracking
  *                                   orb_slam3/src/System.cc:233-240, maps from orb_slam3/src/Settings.cc:506-509   ("next" row)
  *   orbb_undistort_points           Frame::UndistortKeyPoints (cv::undistortPoints)   orb_slam3/src/Frame.cc:747-780   ("next" row)
@@ -238,6 +239,15 @@ long long orbb_vocab_launch_count(const orbb_vocab* v);
  *   counts[3s+2]       features with a positive word weight ("not stopped") */
 int orbb_bow_transform(orbb_vocab* v, const uint8_t* desc, const int32_t* rowptr, int nsets, int levelsup, int norm, int32_t* bow_id,
                        double* bow_val, int32_t* fv_node, int32_t* fv_start, int32_t* fv_feat, int32_t* counts);
+
+/* ---- input-side resize ("next" row) -------------------------------------------------------------------------------- */
+/* cv::resize(im, imToFeed, newImSize) [INTER_LINEAR] that System::TrackStereo / TrackRGBD / TrackMonocular apply when the settings
+ * request another image size (orb_slam3/src/System.cc:241-244, :312-318, :383-388), on the device, followed by the extraction
+ * of the resized frame(s).  Batch: device-resident raw frames, asynchronous (results via orbb_batch_fetch); single: host frame. */
+int orbb_extract_batch_resized(orbb_extractor* h, const uint8_t* dev_imgs, int nframes, int width, int height, size_t row_stride,
+                               size_t frame_stride, int new_width, int new_height, int lap0, int lap1);
+int orbb_extract_resized(orbb_extractor* h, const uint8_t* img, int width, int height, size_t stride, int new_width, int new_height, int lap0,
+                         int lap1, orbb_keypoint* kps, uint8_t* desc, int capacity, int* n_out, int* mono_index);
 
 /* ---- stereo rectification ("next" row) ---------------------------------------------------------------------------- */
 /* cv::remap(src, dst, map_x, map_y, cv::INTER_LINEAR) for 8-bit single-channel images with CV_32FC1 maps (what

@@ -82,6 +82,8 @@ SYMBOLS = [
     ("orbb_vocab_last_error", C.c_char_p, [_VP]),
     ("orbb_vocab_launch_count", _LL, [_VP]),
     ("orbb_bow_transform", _I, [_VP, _VP, _VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
+    ("orbb_extract_batch_resized", _I, [_VP, _VP, _I, _I, _I, _SZ, _SZ, _I, _I, _I, _I]),
+    ("orbb_extract_resized", _I, [_VP, _VP, _I, _I, _SZ, _I, _I, _I, _I, _VP, _VP, _I, _VP, _VP]),
     ("orbb_rectifier_create", _I, [_I, _VP, _VP, _SZ, _I, _I, _I, _I, C.POINTER(_VP)]),
     ("orbb_rectifier_destroy", None, [_VP]),
     ("orbb_remap", _I, [_VP, _VP, _SZ, _VP, _SZ]),

@@ -120,6 +120,38 @@ __global__ void __launch_bounds__(256) k_pyr_resize(const Plan* __restrict__ P, 
     reinterpret_cast<unsigned*>(d)[word] = packed;
 }
 
+// The same arithmetic for a free-standing image pair ("next" row, input side): the cv::resize(im, imToFeed, newImSize) that
+// System::TrackStereo / TrackRGBD / TrackMonocular apply when the settings ask for another image size (reference
+// orb_slam3/src/System.cc:241-244, :312-318, :383-388).  tab = [dw (padded to 4)] column entries, then [dh] row entries.
+__global__ void __launch_bounds__(256) k_resize_image(const int2* __restrict__ tab, int tabY, const uint8_t* __restrict__ src, size_t srcStride,
+                                                      size_t srcFrameStride, int sw, int sh, uint8_t* __restrict__ dst, int dw, int dh) {
+    const int word = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int dy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int frame = blockIdx.z;
+    if (word * 4 >= dw || dy >= dh) return;
+    const uint8_t* s = src + (size_t)frame * srcFrameStride;
+    const int2 ty = __ldg(tab + tabY + dy);
+    const int sy0 = min(max(ty.x, 0), sh - 1), sy1 = min(max(ty.x + 1, 0), sh - 1);
+    const int b0 = (short)(ty.y & 0xffff), b1 = ty.y >> 16;
+    const uint8_t* r0 = s + (size_t)sy0 * srcStride;
+    const uint8_t* r1 = s + (size_t)sy1 * srcStride;
+    const int2* tx = tab + word * 4;
+    uint8_t* d = dst + ((size_t)frame * dh + dy) * dw + word * 4;     // tightly packed destination frames
+    const int n = min(4, dw - word * 4);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (k < n) {
+            const int2 t = __ldg(tx + k);
+            const int sx = t.x, sx1 = min(sx + 1, sw - 1);
+            const int a0 = (short)(t.y & 0xffff), a1 = t.y >> 16;
+            const int h0 = __ldg(r0 + sx) * a0 + __ldg(r0 + sx1) * a1;
+            const int h1 = __ldg(r1 + sx) * a0 + __ldg(r1 + sx1) * a1;
+            const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            d[k] = (uint8_t)min(max(v, 0), 255);
+        }
+    }
+}
+
 #include "orbb_pyr.cuh"
 #include "orbb_rectify.cuh"
 
@@ -1041,6 +1073,35 @@ static int dev_alloc(orbb_extractor* h, T** p, size_t count) {
     return ORBB_OK;
 }
 
+// cv::resize INTER_LINEAR tables (imgproc/resize.cpp: resizeGeneric_ with HResizeLinear / VResizeLinear) for sw x sh -> dw x dh,
+// appended to `tab`: dw column entries (source index, a0 | a1 << 16) padded to a multiple of 4, then dh row entries
+// (source row, b0 | b1 << 16) padded likewise.  Returns the index of the first row entry.
+static int append_resize_tables(std::vector<int2>& tab, int sw, int sh, int dw, int dh) {
+    const double inv_sx = (double)dw / sw, inv_sy = (double)dh / sh;
+    const double scale_x = 1. / inv_sx, scale_y = 1. / inv_sy;
+    const size_t x0 = tab.size();
+    for (int dx = 0; dx < dw; dx++) {
+        float fx = (float)((dx + 0.5) * scale_x - 0.5);
+        int sx = cv_floor_f(fx);
+        fx -= sx;
+        if (sx < 0) { fx = 0; sx = 0; }
+        if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+        const short a0 = (short)cv_round_f((1.f - fx) * 2048.f), a1 = (short)cv_round_f(fx * 2048.f);
+        tab.push_back(make_int2(sx, (int)((unsigned short)a0 | ((unsigned)(unsigned short)a1 << 16))));
+    }
+    while ((tab.size() - x0) % 4) tab.push_back(tab.back());     // the kernels read 4 column entries per thread
+    const int tabY = (int)tab.size();
+    for (int dy = 0; dy < dh; dy++) {
+        float fy = (float)((dy + 0.5) * scale_y - 0.5);
+        int sy = cv_floor_f(fy);
+        fy -= sy;
+        const short b0 = (short)cv_round_f((1.f - fy) * 2048.f), b1 = (short)cv_round_f(fy * 2048.f);
+        tab.push_back(make_int2(sy, (int)((unsigned short)b0 | ((unsigned)(unsigned short)b1 << 16))));
+    }
+    while (tab.size() % 4) tab.push_back(tab.back());
+    return tabY;
+}
+
 // Geometry of every level for a WxH input + the cv::resize coefficient tables (imgproc/resize.cpp).
 static int build_plan(orbb_extractor* h, int W, int H, int frames) {
     free_bufs(h);
@@ -1135,31 +1196,11 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
         // cv::resize tables for level l from level l-1
         if (l > 0) {
             const LevelPlan& S = P.lv[l - 1];
-            const double inv_sx = (double)L.w / S.w, inv_sy = (double)L.h / S.h;
-            const double scale_x = 1. / inv_sx, scale_y = 1. / inv_sy;
             L.tabX = (int)tab.size();
-            for (int dx = 0; dx < L.w; dx++) {
-                float fx = (float)((dx + 0.5) * scale_x - 0.5);
-                int sx = cv_floor_f(fx);
-                fx -= sx;
-                if (sx < 0) { fx = 0; sx = 0; }
-                if (sx >= S.w - 1) { fx = 0; sx = S.w - 1; }
-                const short a0 = (short)cv_round_f((1.f - fx) * 2048.f), a1 = (short)cv_round_f(fx * 2048.f);
-                tab.push_back(make_int2(sx, (int)((unsigned short)a0 | ((unsigned)(unsigned short)a1 << 16))));
-            }
-            while ((tab.size() - (size_t)L.tabX) % 4) tab.push_back(tab.back());     // k_pyr_resize reads 4 entries per thread
+            L.tabY = append_resize_tables(tab, S.w, S.h, L.w, L.h);
             L.fastResize = 1;
-            for (size_t g = (size_t)L.tabX; g < tab.size(); g += 4)
+            for (size_t g = (size_t)L.tabX; g < (size_t)L.tabY; g += 4)
                 if (tab[g + 3].x - 4 * (tab[g].x >> 2) > 7 || tab[g + 3].x < tab[g].x) L.fastResize = 0;      // taps must lie in bytes 0..8
-            L.tabY = (int)tab.size();
-            for (int dy = 0; dy < L.h; dy++) {
-                float fy = (float)((dy + 0.5) * scale_y - 0.5);
-                int sy = cv_floor_f(fy);
-                fy -= sy;
-                const short b0 = (short)cv_round_f((1.f - fy) * 2048.f), b1 = (short)cv_round_f(fy * 2048.f);
-                tab.push_back(make_int2(sy, (int)((unsigned short)b0 | ((unsigned)(unsigned short)b1 << 16))));
-            }
-            while (tab.size() % 4) tab.push_back(tab.back());
             if (L.fastResize) {   // k_pyr_resize_t: the source window of every 128-column x 32-row CTA must fit its shared-memory tile
                 bool fits = true;
                 for (int g = 0; g * 128 < L.w; g++) {
@@ -1454,6 +1495,7 @@ void orbb_destroy(orbb_extractor* h) {
     free_bufs(h);
     if (h->hImg) cudaFree(h->hImg);
     if (h->dColor) cudaFree(h->dColor);
+    if (h->rsTab) cudaFree(h->rsTab);
     if (h->hPyr) cudaFreeHost(h->hPyr);
     if (h->hCounts) cudaFreeHost(h->hCounts);
     for (int i = 0; i <= ST_COUNT; i++) cudaEventDestroy(h->ev[i]);
@@ -1966,6 +2008,59 @@ int orbb_extract_rectified(orbb_extractor* h, orbb_rectifier* r, const uint8_t* 
     }
     ORBB_CUDA(h, cudaMemcpy2DAsync(h->dColor, r->sw, img, stride, r->sw, r->sh, cudaMemcpyHostToDevice, h->stream));
     int rc = orbb_extract_batch_rectified(h, r, h->dColor, 1, (size_t)r->sw, sb, lap0, lap1);
+    if (rc) return rc;
+    int32_t counts[2] = {0, 0};
+    rc = orbb_batch_fetch(h, 1, kps, desc, capacity, counts);
+    if (n_out) *n_out = counts[0];
+    if (mono_index) *mono_index = counts[1];
+    return rc;
+}
+
+// ---- input-side resize ("next" row): cv::resize(im, imToFeed, newImSize) of System::Track* (System.cc:241-244), then extraction --
+static int ensure_resize_tables(orbb_extractor* h, int sw, int sh, int dw, int dh) {
+    if (h->rsTab && h->rsSw == sw && h->rsSh == sh && h->rsDw == dw && h->rsDh == dh) return ORBB_OK;
+    std::vector<int2> tab;
+    const int tabY = append_resize_tables(tab, sw, sh, dw, dh);
+    if (h->rsTab) cudaFree(h->rsTab);
+    h->rsTab = nullptr;
+    ORBB_CUDA(h, cudaMalloc((void**)&h->rsTab, tab.size() * sizeof(int2)));
+    ORBB_CUDA(h, cudaMemcpyAsync(h->rsTab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+    ORBB_CUDA(h, cudaStreamSynchronize(h->stream));          // `tab` is a local
+    h->rsTabY = tabY; h->rsSw = sw; h->rsSh = sh; h->rsDw = dw; h->rsDh = dh;
+    return ORBB_OK;
+}
+
+int orbb_extract_batch_resized(orbb_extractor* h, const uint8_t* dev_imgs, int nframes, int width, int height, size_t row_stride,
+                               size_t frame_stride, int new_width, int new_height, int lap0, int lap1) {
+    if (!h) return ORBB_ERR_ARG;
+    if (!dev_imgs || nframes <= 0 || width <= 0 || height <= 0 || new_width <= 0 || new_height <= 0) return set_err(h, ORBB_ERR_EMPTY, "empty image");
+    ORBB_CUDA(h, cudaSetDevice(h->device));
+    int rc = ensure_plan(h, new_width, new_height, nframes);
+    if (rc) return rc;
+    if ((rc = ensure_staging(h, (size_t)nframes * new_width * new_height))) return rc;
+    if ((rc = ensure_resize_tables(h, width, height, new_width, new_height))) return rc;
+    dim3 grid(((new_width + 3) / 4 + 31) / 32, (new_height + 7) / 8, nframes);
+    k_resize_image<<<grid, 256, 0, h->stream>>>(h->rsTab, h->rsTabY, dev_imgs, row_stride, frame_stride, width, height, h->hImg, new_width, new_height);
+    h->launches++;
+    return run_batch(h, h->hImg, nframes, (size_t)new_width, (size_t)new_width * new_height, lap0, lap1);
+}
+
+int orbb_extract_resized(orbb_extractor* h, const uint8_t* img, int width, int height, size_t stride, int new_width, int new_height, int lap0,
+                         int lap1, orbb_keypoint* kps, uint8_t* desc, int capacity, int* n_out, int* mono_index) {
+    if (!h) return ORBB_ERR_ARG;
+    if (n_out) *n_out = 0;
+    if (mono_index) *mono_index = 0;
+    if (!img || width <= 0 || height <= 0) return set_err(h, ORBB_ERR_EMPTY, "empty image");
+    ORBB_CUDA(h, cudaSetDevice(h->device));
+    const size_t sb = (size_t)width * height;
+    if (h->colorBytes < sb) {                              // (the raw-input staging buffer is shared with the colour / rectify paths)
+        if (h->dColor) cudaFree(h->dColor);
+        h->dColor = nullptr; h->colorBytes = 0;
+        ORBB_CUDA(h, cudaMalloc((void**)&h->dColor, sb));
+        h->colorBytes = sb;
+    }
+    ORBB_CUDA(h, cudaMemcpy2DAsync(h->dColor, width, img, stride, width, height, cudaMemcpyHostToDevice, h->stream));
+    int rc = orbb_extract_batch_resized(h, h->dColor, 1, width, height, (size_t)width, sb, new_width, new_height, lap0, lap1);
     if (rc) return rc;
     int32_t counts[2] = {0, 0};
     rc = orbb_batch_fetch(h, 1, kps, desc, capacity, counts);

@@ -185,7 +185,8 @@ struct orbb_extractor {
     bool stageRan[orbb::ST_COUNT]{};
     // staging: hImg is a DEVICE buffer for frames uploaded from the host; hPyr/hCounts are pinned host memory
     uint8_t* hImg = nullptr; size_t hImgBytes = 0;
-    uint8_t* dColor = nullptr; size_t colorBytes = 0;      // device copy of a colour frame (orbb_extract_color)
+    uint8_t* dColor = nullptr; size_t colorBytes = 0;      // device copy of a raw input frame (orbb_extract_color / _rectified / _resized)
+    int2* rsTab = nullptr; int rsTabY = 0, rsSw = 0, rsSh = 0, rsDw = 0, rsDh = 0;      // cv::resize tables of orbb_extract_resized
     uint8_t* hPyr = nullptr; size_t hPyrBytes = 0; bool hPyrFresh = false;
     int32_t* hCounts = nullptr; int hCountsCap = 0;
     std::string err;

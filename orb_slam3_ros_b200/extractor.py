@@ -102,6 +102,28 @@ class ORBextractor:
                                                 int(lapping[1]), capi.ptr(kps), capi.ptr(desc), cap, C.byref(n), C.byref(mono)), self._h)
         return mono.value, kps[:n.value].copy(), desc[:n.value].copy()
 
+    def extract_resized(self, image, new_size, lapping=(0, 0)):
+        """cv::resize(image, new_size=(width, height)) on the device (System.cc:241-244), then operator()"""
+        image = np.ascontiguousarray(image, np.uint8)
+        h, w = image.shape
+        n, mono = C.c_int(0), C.c_int(0)
+        for _ in range(2):                      # a second pass if the plan for this size allows more keypoints than the estimate
+            cap = self.max_keypoints
+            kps = np.zeros(cap, KP_DTYPE)
+            desc = np.zeros((cap, 32), np.uint8)
+            rc = self._lib.orbb_extract_resized(self._h, capi.ptr(image), w, h, image.strides[0], int(new_size[0]), int(new_size[1]),
+                                                int(lapping[0]), int(lapping[1]), capi.ptr(kps), capi.ptr(desc), cap, C.byref(n), C.byref(mono))
+            if rc != capi.ORBB_ERR_CAPACITY:
+                break
+        capi.check(rc, self._h)
+        return mono.value, kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch_resized_device(self, dev_ptr, nframes, width, height, new_size, row_stride=None, frame_stride=None, lapping=(0, 0)):
+        row_stride = row_stride or width
+        frame_stride = frame_stride or row_stride * height
+        capi.check(self._lib.orbb_extract_batch_resized(self._h, capi.ptr(dev_ptr), nframes, width, height, row_stride, frame_stride,
+                                                        int(new_size[0]), int(new_size[1]), int(lapping[0]), int(lapping[1])), self._h)
+
     def image_pyramid(self, level, with_border=False):
         """mvImagePyramid[level] of the last frame (ORBextractor.h:84), as a numpy copy."""
         p, w, h, s = C.c_void_p(), C.c_int(), C.c_int(), C.c_size_t()

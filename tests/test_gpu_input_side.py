@@ -94,3 +94,29 @@ def test_rgbd_stereo_matches_oracle():
                 ur0, dp0 = port.rgbd_stereo(xy, depth_f[f], K4, dist, bf)
                 assert np.array_equal(dp[f, :n], dp0) and np.array_equal(ur[f, :n].view(np.uint32), ur0.view(np.uint32)), (dist[0], as_u16, f)
             assert 0.1 < (dp[0, :counts[0, 0]] < 0).mean() < 0.3
+
+
+@pytest.mark.parametrize("src_shape,new_size", [((480, 752), (600, 350)), ((376, 1241), (621, 188)), ((240, 320), (500, 400)), ((300, 401), (333, 257))])
+def test_resized_extraction_equals_resize_then_extract(src_shape, new_size):
+    """cv::resize(im, imToFeed, newImSize) of System::Track* (System.cc:241-244) on the device: the pyramid's level 0 must
+    be the oracle's resize (pinned to cv2.resize, incl. up-scaling and the exact-2x case), the features those of
+    resize-then-extract; single host frame and a batch of device-resident frames"""
+    h, w = src_shape
+    raw = [synth.frame(h, w, 60 + i) for i in range(2)]
+    ge = ORBextractor(800, 1.2, 6)
+    want_img = [port.resize_linear(f, new_size[0], new_size[1]) for f in raw]
+    want = [port.PortExtractor(800, 1.2, 6).extract(im, (0, 0)) for im in want_img]
+    m1, k1, d1 = ge.extract_resized(raw[0], new_size)
+    assert np.array_equal(ge.debug_level(0, 0), want_img[0])
+    rc, k0, d0, m0 = want[0]
+    assert rc == 0 and m1 == m0 and len(k1) == len(k0)
+    for f in ("x", "y", "size", "response", "octave"):
+        assert np.array_equal(k0[f], k1[f]), f
+    assert np.unpackbits(d0 ^ d1).sum() <= 1e-4 * d0.size * 8
+    ge.extract_batch_resized_device(torch.from_numpy(np.stack(raw)).cuda(), 2, w, h, new_size)
+    counts, kps, desc = ge.fetch(2)
+    for i, (rc, k0, d0, m0) in enumerate(want):
+        n = counts[i, 0]
+        assert n == len(k0)
+        for f in ("x", "y", "size", "response", "octave"):
+            assert np.array_equal(k0[f], kps[i, :n][f]), (i, f)
