@@ -8,7 +8,7 @@ extraction path ("weak" scaling).  A second timed region measures the brute-forc
 database sharded over the ranks, per-shard top-2 all-gathered over NCCL and merged on the device).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          # our arm
-  python bench.py --impl reference ...                         # the reference's CPU path (oracle port) on the host cores
+  python bench.py --impl reference ...                         # the reference's CPU path (oracle/_ref, else the oracle port) on the host cores
 
 Prints ONE JSON line on rank 0.
 """
@@ -110,12 +110,20 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# reference arm: the reference's CPU implementation of the path (oracle port; the reference itself does not build here)
+# reference arm: the reference's CPU implementation of the path.  oracle/_ref/liborbref.so is the reference's own
+# ORBextractor.cc compiled unmodified (OpenCV primitives = the scalar stand-ins of oracle/cvshim); the oracle port is the
+# fallback when that library was not built.
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_extract_rate(frames, threads):
-    from oracle import port          # checker / CPU baseline only
+def have_reference_build():
+    from oracle import ref
+    return ref.available()
+
+
+def cpu_extract_rate(frames, threads, impl="port"):
+    from oracle import port, ref          # checker / CPU baseline only
+    mod = ref if impl == "reference" else port
     t0 = time.perf_counter()
-    port.extract_batch(frames, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, LAPPING, nthreads=threads, with_data=False)
+    mod.extract_batch(frames, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, LAPPING, nthreads=threads, with_data=False)
     return len(frames) / (time.perf_counter() - t0)
 
 
@@ -126,13 +134,15 @@ def run_reference(a):
     cores = os.cpu_count() or 1
     sample = min(a.cpu_sample * max(1, cores // 8), a.batch)
     frames = make_frames(sample)
+    kind = "reference" if have_reference_build() else "port"
     for _ in range(a.warmup):
-        cpu_extract_rate(frames[: max(4, sample // 4)], cores)
+        cpu_extract_rate(frames[: max(4, sample // 4)], cores, kind)
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        cpu_extract_rate(frames, cores)
+        cpu_extract_rate(frames, cores, kind)
     dt = time.perf_counter() - t0
     value = sample * a.steps / dt
+    port_value = cpu_extract_rate(frames, cores, "port") if kind == "reference" else value
     knn = None
     if not a.no_knn:
         from oracle import port
@@ -148,9 +158,12 @@ def run_reference(a):
         "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": f"euroc_mono_{W_}x{H_}_nf{NFEAT}_nl{NLEVELS}_fast{INI_TH}/{MIN_TH}", "batch": sample,
-                   "note": "reference .cc files need OpenCV C++/Eigen/Sophus (absent): timed the oracle port, g++ -O3, all host threads"},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} frames per step x {a.steps} steps, {cores} host threads"},
+                   "note": ("the reference's own ORBextractor.cc (unmodified, g++ -O3) with OpenCV's primitives replaced by the scalar stand-ins "
+                            "of oracle/cvshim, one extractor per host thread" if kind == "reference" else
+                            "oracle/_ref was not built: timed the oracle port, g++ -O3, all host threads")},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind,
+                         "sample": f"{sample} frames per step x {a.steps} steps, {cores} host threads",
+                         "oracle_port_frames_per_s": port_value},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "knn": knn,
     }
@@ -457,6 +470,8 @@ def run_ours(a):
         cpu = {"value": cpu_extract_rate(fr, cores), "unit": "frames/s", "cores": cores, "kind": "port",
                "sample": f"first {sample} frames of batch 0, {cores} host threads, oracle port (g++ -O3)"}
         cpu["single_thread_ms_per_frame"] = 1e3 / cpu_extract_rate(fr[:8], 1)
+        if have_reference_build():      # the reference's own ORBextractor.cc on the same sample (slower than the port: std::list, cv::KeyPoint vectors)
+            cpu["reference_source_frames_per_s"] = cpu_extract_rate(fr, cores, "reference")
 
     if rank == 0:
         line = {

@@ -5,12 +5,16 @@
 // cpu_baseline / --impl reference legs may load this library.  The product (liborbb200.so) never
 // links, loads or calls it.
 //
-// PARITY PINNING: the reference has no tests or golden vectors for this path,
-// and its .cc files cannot be compiled in this image (no OpenCV C++/Eigen/Sophus).  The arithmetic
-// that lives in un-vendored OpenCV (resize, FAST, GaussianBlur, fastAtan2, BFMatcher) is restated
-// here as closed integer / float32 formulas; oracle/orb_ref.py runs the SAME control flow through the
-// real OpenCV primitives (python cv2) and tests/test_oracle_*.py require the two to agree bit-for-bit.
-// Against the reference repository itself parity is therefore "unpinned" (no reference-held vectors).
+// PARITY PINNING: the reference has no tests or golden vectors for this path.
+// The arithmetic that lives in un-vendored OpenCV (resize, FAST, GaussianBlur, fastAtan2, BFMatcher) is
+// restated here as closed integer / float32 formulas; oracle/orb_ref.py runs the SAME control flow through
+// the real OpenCV primitives (python cv2) and tests/test_oracle_*.py require the two to agree bit-for-bit.
+// EXTRACTOR rows: pinned to the reference itself -- oracle/_ref/liborbref.so is the reference's own
+// ORBextractor.cc compiled unmodified (`make ref`, OpenCV declarations from cvshim/, primitives from this
+// file) and tests/test_reference_source.py requires this port to reproduce it bit for bit.
+// MATCHER / STEREO / BoW rows: "parity unpinned" against the reference repository (ORBmatcher.cc, Frame.cc,
+// DBoW2 need Eigen/Sophus/boost and cannot be compiled here; no reference-held vectors); pinned to cv2 where
+// OpenCV defines the result.
 //
 // Build: g++ -O3 -march=native -ffp-contract=off -shared -fPIC (see oracle/Makefile).
 // -ffp-contract=off makes the un-fused float32 result the truth ("sin/cos and FMA").

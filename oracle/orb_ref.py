@@ -11,8 +11,10 @@ Follows /root/reference/orb_slam3/src/ORBextractor.cc line by line:
                                           computeOrbDescriptor via port_descriptors (glibc cosf/sinf, un-fused)
 and Frame.cc:1126-1151 (BFMatcher kNN-2) for the brute-force matcher.
 
-"parity unpinned" with respect to the reference repository: it holds no golden vectors for this path.
-Pinned against the OpenCV build behind python cv2 only; cv2.__version__ is recorded in every golden file.
+The reference repository holds no golden vectors for this path; this module pins the OpenCV side (the build behind
+python cv2, cv2.__version__ is recorded in every golden file), oracle/ref.py (the reference's own ORBextractor.cc,
+compiled unmodified) pins the ORB-SLAM3 side of the extractor.  The matcher rows stay "parity unpinned" against the
+reference repository (its matcher sources cannot be compiled here).
 """
 import math
 

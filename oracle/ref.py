@@ -1,0 +1,118 @@
+"""ORACLE (test infrastructure, NOT product code): ctypes binding of oracle/_ref/liborbref.so -- the reference's OWN
+ORB_SLAM3::ORBextractor (orb_slam3/src/ORBextractor.cc, compiled unmodified from /root/reference by `make -C oracle ref`
+against the OpenCV stand-in of oracle/cvshim/).
+
+Only tests/, __graft_entry__ and bench.py's cpu_baseline / --impl reference legs may import this module.  The library is
+built in the development container (where /root/reference exists) and travels to the GPU box as a built file; when it
+is absent `available()` is False and the callers fall back to the port (tests skip).
+"""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from .port import KP_DTYPE
+
+_HERE = Path(__file__).resolve().parent
+_SO = _HERE / "_ref" / "liborbref.so"
+REFERENCE_SRC = Path("/root/reference/orb_slam3")
+_lib = None
+
+
+def build(force=False):
+    """Compile the reference extractor when its sources are present (never on the GPU box); returns the .so path or None."""
+    if (REFERENCE_SRC / "src" / "ORBextractor.cc").exists():
+        subprocess.check_call(["make", "-s", "-C", str(_HERE), "ref"] + (["-B"] if force else []))
+    return _SO if _SO.exists() else None
+
+
+def available():
+    return _SO.exists() or build() is not None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError("oracle/_ref/liborbref.so is missing and /root/reference is not here to build it")
+        l = C.CDLL(str(_SO))
+        l.ref_create.restype = C.c_void_p
+        l.ref_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        l.ref_destroy.argtypes = [C.c_void_p]
+        l.ref_tables.argtypes = [C.c_void_p] * 7
+        l.ref_extract.restype = C.c_int
+        l.ref_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        l.ref_level.restype = C.c_int
+        l.ref_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                C.POINTER(C.c_size_t)]
+        l.ref_extract_batch.restype = C.c_int
+        l.ref_extract_batch.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t,
+                                        C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        _lib = l
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class RefExtractor:
+    """ORB_SLAM3::ORBextractor itself (ORBextractor.h:43-109); same Python surface as oracle.port.PortExtractor."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self._l = lib()
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+        self._h = self._l.ref_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        sc = [np.zeros(nlevels, np.float32) for _ in range(4)]
+        nf = np.zeros(nlevels, np.int32)
+        um = np.zeros(16, np.int32)
+        self._l.ref_tables(self._h, _ptr(sc[0]), _ptr(sc[1]), _ptr(sc[2]), _ptr(sc[3]), _ptr(nf), _ptr(um))
+        self.scale_factors, self.inv_scale_factors, self.level_sigma2, self.inv_level_sigma2 = sc
+        self.features_per_level, self.umax = nf, um
+
+    def __del__(self):
+        try:
+            self._l.ref_destroy(self._h)
+        except Exception:
+            pass
+
+    def extract(self, img, lapping=(0, 0)):
+        """-> (rc, keypoints[KP_DTYPE], descriptors[n,32] u8, mono_index); rc=-1 on an empty image (ORBextractor.cc:1090)."""
+        if img is None or img.size == 0:
+            return -1, np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8), 0
+        assert img.dtype == np.uint8 and img.ndim == 2 and img.strides[1] == 1
+        h, w = img.shape
+        cap = self.nfeatures + 8 * self.nlevels + 64
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n, mono = C.c_int(0), C.c_int(0)
+        rc = self._l.ref_extract(self._h, _ptr(img), w, h, img.strides[0], int(lapping[0]), int(lapping[1]), _ptr(kps), _ptr(desc), cap,
+                                 C.byref(n), C.byref(mono))
+        return rc, kps[:n.value].copy(), desc[:n.value].copy(), mono.value
+
+    def level(self, level, bordered=False):
+        """mvImagePyramid[level] (bordered: with its 19-pixel apron)."""
+        p, w, h, s = C.c_void_p(), C.c_int(), C.c_int(), C.c_size_t()
+        if self._l.ref_level(self._h, level, int(bordered), C.byref(p), C.byref(w), C.byref(h), C.byref(s)):
+            return None
+        ww, hh = (w.value + 38, h.value + 38) if bordered else (w.value, h.value)
+        buf = (C.c_uint8 * (s.value * hh)).from_address(p.value)
+        return np.frombuffer(buf, np.uint8).reshape(hh, s.value)[:, :ww].copy()
+
+
+def extract_batch(images, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, lapping=(0, 0), nthreads=1, with_data=True):
+    """All-core run of the reference extractor over a [n,h,w] uint8 stack -> counts[n,2], kps[n,cap], desc[n,cap,32]."""
+    images = np.ascontiguousarray(images, np.uint8)
+    n, h, w = images.shape
+    cap = nfeatures + 8 * nlevels + 64
+    counts = np.zeros((n, 2), np.int32)
+    kps = np.zeros((n, cap), KP_DTYPE) if with_data else None
+    desc = np.zeros((n, cap, 32), np.uint8) if with_data else None
+    rc = lib().ref_extract_batch(nfeatures, scale_factor, nlevels, ini_th, min_th, _ptr(images), n, w, h, images.strides[1], images.strides[0],
+                                 int(lapping[0]), int(lapping[1]), _ptr(kps) if with_data else None, _ptr(desc) if with_data else None, cap,
+                                 _ptr(counts), nthreads)
+    if rc:
+        raise RuntimeError(f"ref_extract_batch rc={rc}")
+    return counts, kps, desc

@@ -1,6 +1,8 @@
 """GPU parity tests of the CUDA ORB extractor, through the C ABI (orbb_* via ctypes), against
   (a) the oracle port (oracle/orb_port.cpp, pinned to python-cv2 by tests/test_oracle_*.py) on seeded inputs, and
-  (b) the committed golden fixtures produced with the cv2-backed oracle (tools/make_golden.py).
+  (b) the committed golden fixtures produced with the cv2-backed oracle (tools/make_golden.py), and
+  (c) the reference's own ORBextractor.cc compiled unmodified (oracle/_ref/liborbref.so, see oracle/cvshim/cvshim.hpp) whenever that
+      library is present (it is built in the development container and travels to the GPU box with the other built files).
 Bar (BASELINE.json north_star): pyramid pixels, keypoints (pt, octave, size, response), their order and the mono index
 bit-exact; angles within 1e-3 deg; descriptor bit disagreement <= 1e-4.
 """
@@ -10,7 +12,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from oracle import port
+from oracle import port, ref
 from orb_slam3_ros_b200 import capi, synth
 from orb_slam3_ros_b200.extractor import ORBextractor
 
@@ -46,6 +48,10 @@ def check_against_port(img, nf, nl, ini=20, mn=7, lap=(0, 0), stages=True):
             if len(s):
                 assert np.array_equal(pe.level(l, blurred=True), ge.debug_level(0, l, blurred=True)), f"blur level {l}"
     assert_same_features(k0, d0, m0, k1, d1, m1)
+    if ref.available():      # the reference's object code on the same input
+        rc, kr, dr, mr = ref.RefExtractor(nf, 1.2, nl, ini, mn).extract(img, lap)
+        assert rc == 0
+        assert_same_features(kr, dr, mr, k1, d1, m1, "vs the reference's ORBextractor.cc")
     return ge, k1, d1
 
 

@@ -1,0 +1,88 @@
+"""CPU: the reference's OWN extractor -- orb_slam3/src/ORBextractor.cc compiled unmodified into oracle/_ref/liborbref.so
+(OpenCV replaced by the pinned stand-in of oracle/cvshim/) -- against the oracle port, the cv2-backed restatement and the
+committed golden fixtures.  This pins the restated ORB-SLAM3 control flow (cell loop + threshold fallback,
+DistributeOctTree, IC_Angle, steered BRIEF, lapping assembly, constructor tables) to the reference's object code; the
+OpenCV primitives are pinned separately against python-cv2 (test_oracle_primitives.py)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import port, ref
+from orb_slam3_ros_b200 import synth
+
+pytestmark = pytest.mark.skipif(not ref.available(), reason="oracle/_ref/liborbref.so not built (needs /root/reference)")
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def _same(k0, d0, m0, k1, d1, m1):
+    assert len(k0) == len(k1) and m0 == m1
+    for f in ("x", "y", "size", "angle", "response", "octave"):
+        assert np.array_equal(k0[f], k1[f]), f
+    assert np.array_equal(d0, d1)
+
+
+@pytest.mark.parametrize("nf,sf,nl,ini,mn", [(1000, 1.2, 8, 20, 7), (2000, 1.2, 8, 20, 7), (1250, 1.2, 8, 12, 7), (500, 1.5, 4, 20, 7),
+                                             (300, 2.0, 3, 30, 10), (1500, 1.1, 10, 20, 7), (1, 1.2, 8, 20, 7)])
+def test_constructor_tables_match_reference(nf, sf, nl, ini, mn):
+    a, b = port.PortExtractor(nf, sf, nl, ini, mn), ref.RefExtractor(nf, sf, nl, ini, mn)
+    for f in ("scale_factors", "inv_scale_factors", "level_sigma2", "inv_level_sigma2", "features_per_level", "umax"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+
+
+@pytest.mark.parametrize("shape,nf,nl,lap,seed", [((480, 752), 1000, 8, (0, 1000), 1), ((480, 752), 1000, 8, (0, 0), 5),
+                                                  ((376, 1241), 2000, 8, (0, 0), 2), ((240, 320), 300, 4, (100, 200), 3),
+                                                  ((480, 640), 1000, 8, (250, 400), 4), ((200, 260), 5000, 4, (0, 0), 6)])
+def test_port_equals_reference_source(shape, nf, nl, lap, seed):
+    img = synth.frame(shape[0], shape[1], seed)
+    pe, re_ = port.PortExtractor(nf, 1.2, nl), ref.RefExtractor(nf, 1.2, nl)
+    rc, k0, d0, m0 = pe.extract(img, lap)
+    rc2, k1, d1, m1 = re_.extract(img, lap)
+    assert rc == 0 and rc2 == 0 and len(k1) > 0
+    for l in range(nl):
+        assert np.array_equal(pe.level(l, bordered=True), re_.level(l, bordered=True)), l
+    _same(k0, d0, m0, k1, d1, m1)
+
+
+@pytest.mark.parametrize("sf,nl,ini,mn", [(1.5, 4, 20, 7), (2.0, 3, 20, 7), (1.1, 6, 20, 7), (1.2, 8, 40, 5), (1.2, 8, 7, 7)])
+def test_port_equals_reference_source_other_settings(sf, nl, ini, mn):
+    img = synth.frame(480, 640, 1)
+    rc, k0, d0, m0 = port.PortExtractor(500, sf, nl, ini, mn).extract(img)
+    rc2, k1, d1, m1 = ref.RefExtractor(500, sf, nl, ini, mn).extract(img)
+    assert rc == 0 and rc2 == 0
+    _same(k0, d0, m0, k1, d1, m1)
+
+
+def test_reference_source_on_noise_flat_and_strided_images():
+    rng = np.random.default_rng(11)
+    noise = rng.integers(0, 256, (300, 420), dtype=np.uint8)                      # far more corners than wanted: deep quadtree, sort ties
+    flat = np.full((240, 320), 127, np.uint8)                                     # no corner anywhere: empty output, descriptors released
+    wide = synth.frame(300, 500, 9)
+    view = np.ascontiguousarray(np.pad(wide, ((0, 0), (0, 37))))[:, :500]         # row stride != width
+    for img, nf in ((noise, 1000), (flat, 500), (view, 700)):
+        rc, k0, d0, m0 = port.PortExtractor(nf, 1.2, 8).extract(img, (50, 120))
+        rc2, k1, d1, m1 = ref.RefExtractor(nf, 1.2, 8).extract(img, (50, 120))
+        assert rc == rc2 == 0
+        _same(k0, d0, m0, k1, d1, m1)
+    assert len(port.PortExtractor(500, 1.2, 8).extract(flat)[1]) == 0
+    assert ref.RefExtractor().extract(np.zeros((0, 0), np.uint8))[0] == -1        # ORBextractor.cc:1090
+
+
+@pytest.mark.parametrize("name", ["mono_320x240", "wide_400x200", "noise_176x144", "fallback_260x200"])
+def test_reference_source_reproduces_golden(name):
+    """the fixtures were generated through python-cv2 (tools/make_golden.py): reference object code + stand-in == real OpenCV run"""
+    g = np.load(GOLD / f"{name}.npz")
+    nf, nl, ini, mn, l0, l1 = [int(v) for v in g["params"]]
+    rc, k, d, m = ref.RefExtractor(nf, 1.2, nl, ini, mn).extract(g["image"], (l0, l1))
+    assert rc == 0
+    _same(g["kps"].view(port.KP_DTYPE).reshape(-1), g["desc"], int(g["mono"]), k, d, m)
+
+
+def test_reference_source_batch_matches_single_calls():
+    imgs = np.stack([synth.frame(240, 320, s) for s in range(5)])
+    counts, kps, desc = ref.extract_batch(imgs, 400, 1.2, 6, lapping=(0, 100), nthreads=3)
+    e = ref.RefExtractor(400, 1.2, 6)
+    for f in range(5):
+        rc, k, d, m = e.extract(imgs[f], (0, 100))
+        assert counts[f, 0] == len(k) and counts[f, 1] == m
+        assert np.array_equal(kps[f, :len(k)], k) and np.array_equal(desc[f, :len(k)], d)
