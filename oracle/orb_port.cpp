@@ -502,7 +502,14 @@ struct Extractor {
             toDist.clear();
             const float width = (float)(maxBX - minBX), height = (float)(maxBY - minBY);
             const int nCols = (int)(width / W), nRows = (int)(height / W);
-            if (nCols <= 0 || nRows <= 0) return -2;          // reference divides by zero here
+            if (nCols <= 0 || nRows <= 0) {
+                // the reference's loops below do not execute (wCell / hCell = ceil(x / 0) are never used) and DistributeOctTree
+                // of no keys returns nothing: the level has no keypoints.  With a non-positive span :559 yields a negative or
+                // undefined root count (vector::resize throws); level 0 is kept out as well (an image without one cell).
+                if (level == 0 || width <= 0 || height <= 0) return -2;
+                sel[level].clear();
+                continue;
+            }
             const int wCell = (int)std::ceil(width / nCols), hCell = (int)std::ceil(height / nRows);
             std::vector<RawKey> cell;
             for (int i = 0; i < nRows; i++) {

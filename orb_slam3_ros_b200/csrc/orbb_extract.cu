@@ -1134,9 +1134,15 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
         L.maxBX = L.w - kEdge + 3; L.maxBY = L.h - kEdge + 3;
         const float width = (float)(L.maxBX - kMinBorder), height = (float)(L.maxBY - kMinBorder);
         L.nCols = (int)(width / 35.f); L.nRows = (int)(height / 35.f);
-        if (L.nCols <= 0 || L.nRows <= 0)
-            return set_err(h, ORBB_ERR_UNSUPPORTED, "level %d (%dx%d) is smaller than one 35-px FAST cell: the reference divides by zero here", l, L.w, L.h);
-        L.wCell = (int)ceilf(width / L.nCols); L.hCell = (int)ceilf(height / L.nRows);
+        // A level smaller than one 35-px cell: the reference's cell loops (:805-822) do not execute -- its wCell / hCell =
+        // ceil(x / 0) are never used -- and DistributeOctTree of no keys returns nothing, so the level simply contributes no
+        // keypoints (its image is still built: the next level is resized from it, Frame.cc reads mvImagePyramid).  That holds
+        // while both spans are positive; otherwise :559 gives a negative or undefined root count and vector::resize throws.
+        const bool emptyLevel = L.nCols <= 0 || L.nRows <= 0;
+        if (emptyLevel && (l == 0 || width <= 0.f || height <= 0.f))
+            return set_err(h, ORBB_ERR_UNSUPPORTED, "level %d (%dx%d) is smaller than the FAST border / one 35-px cell: the reference has undefined behaviour here", l, L.w, L.h);
+        if (emptyLevel) { L.nCols = L.nRows = 0; L.wCell = L.hCell = 1; }
+        else { L.wCell = (int)ceilf(width / L.nCols); L.hCell = (int)ceilf(height / L.nRows); }
         if (L.wCell + 9 > kCellPix || L.hCell + 6 > kCellPix - 1) return set_err(h, ORBB_ERR_UNSUPPORTED, "cell %dx%d exceeds the kernel's tile", L.wCell, L.hCell);
         L.cellBase = cells;
         L.cellCap = ((L.wCell + 1) / 2) * ((L.hCell + 1) / 2);      // NMS survivors are never 8-adjacent
@@ -1177,7 +1183,7 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
         cellKeys += (unsigned)(L.nCols * L.nRows * L.cellCap);
         // quadtree (:559-561)
         L.nFeat = h->featPerLevel[l];
-        L.nIni = (int)roundf((float)(L.maxBX - kMinBorder) / (L.maxBY - kMinBorder));
+        L.nIni = emptyLevel ? 1 : (int)roundf((float)(L.maxBX - kMinBorder) / (L.maxBY - kMinBorder));      // (no keys: the root count is immaterial)
         if (L.nIni <= 0 || L.nIni > kMaxIni)
             return set_err(h, ORBB_ERR_UNSUPPORTED, "level %d aspect ratio gives %d root nodes (reference: undefined behaviour for 0)", l, L.nIni);
         L.hX = (float)(L.maxBX - kMinBorder) / L.nIni;
@@ -1191,7 +1197,7 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
         L.blurTilesX = (L.w + 3) / 4; L.blurTilesY = (L.h + BLUR_STRIP - 1) / BLUR_STRIP;     // word columns x 32-row strips
         L.blurTileBase = tiles; tiles += (L.blurTilesX * L.blurTilesY + BLUR_THREADS - 1) / BLUR_THREADS;
         L.fsTilesX = ((L.w + 3) / 4 + 31) / 32;
-        L.fsGroups = ((L.h - 2 * kEdge + FS_R - 1) / FS_R + 3) / 4;
+        L.fsGroups = std::max(0, ((L.h - 2 * kEdge + FS_R - 1) / FS_R + 3) / 4);
         L.fsBase = fsTiles; fsTiles += L.fsTilesX * L.fsGroups;
         // cv::resize tables for level l from level l-1
         if (l > 0) {

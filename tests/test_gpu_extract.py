@@ -133,8 +133,16 @@ def test_thresholds_and_small_feature_budget():
 def test_too_small_level_is_rejected():
     ge = ORBextractor(100, 1.2, 8)
     with pytest.raises(capi.OrbbError) as e:
-        ge(synth.frame(90, 120, 0))                 # level 7 would be 33x25: the reference divides by zero (nCols = 0)
+        ge(synth.frame(90, 120, 0))                 # level 7 would be 33x25: a negative row span, the reference's root count (:559) is undefined
     assert e.value.code == capi.ORBB_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("shape,nf,nl", [((200, 260), 500, 8), ((150, 400), 300, 8), ((120, 160), 200, 6)])
+def test_levels_smaller_than_one_cell_contribute_nothing(shape, nf, nl):
+    """nCols or nRows == 0 on the top levels: the reference's cell loops do not run and the level stays empty (its image is
+    still built); checked against the port and the reference's own object code."""
+    ge, k, d = check_against_port(synth.frame(shape[0], shape[1], 3), nf, nl, lap=(0, 100))
+    assert len(k) > 0 and k["octave"].max() < nl - 1
 
 
 def test_pyramid_accessor_matches_mvImagePyramid():

@@ -32,7 +32,8 @@ def test_constructor_tables_match_reference(nf, sf, nl, ini, mn):
 
 @pytest.mark.parametrize("shape,nf,nl,lap,seed", [((480, 752), 1000, 8, (0, 1000), 1), ((480, 752), 1000, 8, (0, 0), 5),
                                                   ((376, 1241), 2000, 8, (0, 0), 2), ((240, 320), 300, 4, (100, 200), 3),
-                                                  ((480, 640), 1000, 8, (250, 400), 4), ((200, 260), 5000, 4, (0, 0), 6)])
+                                                  ((480, 640), 1000, 8, (250, 400), 4), ((200, 260), 5000, 4, (0, 0), 6),
+                                                  ((200, 260), 500, 8, (0, 100), 3), ((150, 400), 300, 8, (0, 0), 3)])      # top levels without a cell
 def test_port_equals_reference_source(shape, nf, nl, lap, seed):
     img = synth.frame(shape[0], shape[1], seed)
     pe, re_ = port.PortExtractor(nf, 1.2, nl), ref.RefExtractor(nf, 1.2, nl)
