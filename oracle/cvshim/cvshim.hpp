@@ -7,7 +7,11 @@
 // sampling, the lapping-area assembly -- is then the reference's own object code.  The OpenCV primitives it calls
 // (cv::resize INTER_LINEAR, copyMakeBorder REFLECT_101, cv::FAST with NMS, GaussianBlur 7x7 s=2, fastAtan2, cvRound)
 // are implemented in cvshim.cpp by the restatements of orb_port.cpp, which the CPU tests pin bit for bit against the real
-// OpenCV (python cv2) -- see tests/test_oracle_primitives.py.  Only 8-bit single-channel matrices exist here.
+// OpenCV (python cv2) -- see tests/test_oracle_primitives.py.  Matrices are single-channel, 8-bit (32-bit float storage exists
+// only so that the vendored DBoW2's FORB::toMat32F compiles).  `make ref` also compiles the vendored Thirdparty/DBoW2
+// (FORB.cpp, BowVector.cpp, FeatureVector.cpp, ScoringObject.cpp, TemplatedVocabulary.h) against this header; its YAML
+// persistence (cv::FileStorage) and boost::serialization hooks are inert stubs -- vocabularies are loaded with DBoW2's own
+// loadFromTextFile, as ORB-SLAM3 does (System.cc:116).
 #pragma once
 #include <algorithm>      // OpenCV's own headers pull these in; the reference relies on that (std::sort, assert)
 #include <cassert>
@@ -15,13 +19,17 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <iostream>
 #include <memory>
+#include <sstream>
+#include <string>
 #include <vector>
 
 typedef unsigned char uchar;
 
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_32F 5
 #define CV_PI 3.1415926535897932384626433832795
 
 inline int cvRound(double v) { return (int)std::lrint(v); }        // round-half-even, as OpenCV's SSE2 / lrint paths
@@ -76,15 +84,17 @@ public:
     Mat(Size sz, int type) : Mat() { create(sz.height, sz.width, type); }
     Mat(int r, int c, int, void* ext, size_t step_ = 0) : rows(r), cols(c), data((uchar*)ext), step(step_ ? step_ : (size_t)c) {}
 
-    void create(int r, int c, int /*type*/) {                    // keeps the buffer (and a ROI view) when the size already fits
-        if (data && r == rows && c == cols) return;
-        rows = r; cols = c; step = (size_t)c;
-        buf_ = allocate((size_t)r * c);
+    void create(int r, int c, int type) {                        // keeps the buffer (and a ROI view) when the size already fits
+        if (data && r == rows && c == cols && type == type_) return;
+        rows = r; cols = c; type_ = type; step = (size_t)c * elemSize();
+        buf_ = allocate((size_t)r * step);
         data = buf_.get();
     }
-    static Mat zeros(int r, int c, int type) { Mat m(r, c, type); if (m.data) std::memset(m.data, 0, (size_t)r * c); return m; }
+    void release() { *this = Mat(); }
+    static Mat zeros(int r, int c, int type) { Mat m(r, c, type); if (m.data) std::memset(m.data, 0, (size_t)r * m.step); return m; }
 
-    int type() const { return CV_8UC1; }
+    int type() const { return type_; }
+    size_t elemSize() const { return type_ == CV_32F ? 4 : 1; }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
     size_t step1() const { return step; }
     template <typename T> T& at(int r, int c) { return *(T*)(data + (size_t)r * step + c); }
@@ -110,6 +120,7 @@ private:
     // munmap per level, which serialises the worker threads of the throughput baseline on the process's memory map.
     static std::shared_ptr<uchar> allocate(size_t n);
     std::shared_ptr<uchar> buf_;
+    int type_ = CV_8UC1;
 };
 
 class _InputArray {
@@ -150,6 +161,26 @@ void resize(InputArray src, OutputArray dst, Size dsize, double fx = 0, double f
 void copyMakeBorder(InputArray src, OutputArray dst, int top, int bottom, int left, int right, int borderType);
 void GaussianBlur(InputArray src, OutputArray dst, Size ksize, double sigmaX, double sigmaY = 0, int borderType = BORDER_REFLECT_101);
 void FAST(InputArray image, std::vector<KeyPoint>& keypoints, int threshold, bool nonmaxSuppression = true);
+
+// YAML persistence used by DBoW2's save()/load(): never opens here (DBoW2 then throws, nothing calls it)
+class FileNode {
+public:
+    FileNode operator[](const std::string&) const { return FileNode(); }
+    FileNode operator[](const char*) const { return FileNode(); }
+    FileNode operator[](int) const { return FileNode(); }
+    size_t size() const { return 0; }
+    operator int() const { return 0; }
+    operator double() const { return 0; }
+    operator std::string() const { return std::string(); }
+};
+class FileStorage {
+public:
+    enum { READ = 0, WRITE = 1 };
+    FileStorage(const char*, int) {}
+    bool isOpened() const { return false; }
+    FileNode operator[](const std::string&) const { return FileNode(); }
+    template <typename T> FileStorage& operator<<(const T&) { return *this; }
+};
 
 struct KeyPointsFilter {       // only ORBextractor::ComputeKeyPointsOld (dead code in the reference, :1101) calls this
     static void retainBest(std::vector<KeyPoint>& keypoints, int npoints);

@@ -1,6 +1,6 @@
 """ORACLE (test infrastructure, NOT product code): ctypes binding of oracle/_ref/liborbref.so -- the reference's OWN
-ORB_SLAM3::ORBextractor (orb_slam3/src/ORBextractor.cc, compiled unmodified from /root/reference by `make -C oracle ref`
-against the OpenCV stand-in of oracle/cvshim/).
+ORB_SLAM3::ORBextractor (orb_slam3/src/ORBextractor.cc) and its vendored DBoW2 vocabulary (orb_slam3/Thirdparty/DBoW2),
+compiled unmodified from /root/reference by `make -C oracle ref` against the OpenCV stand-in of oracle/cvshim/.
 
 Only tests/, __graft_entry__ and bench.py's cpu_baseline / --impl reference legs may import this module.  The library is
 built in the development container (where /root/reference exists) and travels to the GPU box as a built file; when it
@@ -50,6 +50,15 @@ def lib():
         l.ref_extract_batch.restype = C.c_int
         l.ref_extract_batch.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t,
                                         C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        l.refbow_load_text.restype = C.c_void_p
+        l.refbow_load_text.argtypes = [C.c_char_p]
+        l.refbow_destroy.argtypes = [C.c_void_p]
+        l.refbow_size.restype = C.c_int
+        l.refbow_size.argtypes = [C.c_void_p]
+        l.refbow_distance.restype = C.c_int
+        l.refbow_distance.argtypes = [C.c_void_p, C.c_void_p]
+        l.refbow_transform.restype = C.c_int
+        l.refbow_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
         _lib = l
     return _lib
 
@@ -116,3 +125,57 @@ def extract_batch(images, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20
     if rc:
         raise RuntimeError(f"ref_extract_batch rc={rc}")
     return counts, kps, desc
+
+
+def write_vocabulary_text(vocab, path):
+    """A flat vocabulary (orb_slam3_ros_b200.bow.synthetic_vocabulary layout, children numbered after their parents) in the text
+    format of ORBvoc.txt that DBoW2's loadFromTextFile reads (TemplatedVocabulary.h:1350-1434): header `k L scoring weighting`
+    (L1_NORM = 0, TF_IDF = 0), then one line per node in id order: `parent isLeaf d0 .. d31 weight`."""
+    cb, cc, cl = vocab["child_begin"], vocab["child_count"], vocab["child_list"]
+    n = len(cb)
+    parent = np.zeros(n, np.int64)
+    for p in range(n):
+        for c in cl[cb[p]:cb[p] + cc[p]]:
+            assert c > p
+            parent[c] = p
+    lines = [f"{int(cc.max())} {int(vocab['depth'])} 0 0"]
+    for i in range(1, n):
+        leaf = int(cc[i] == 0)
+        lines.append(f"{parent[i]} {leaf} " + " ".join(str(int(b)) for b in vocab["node_desc"][i]) + f" {float(vocab['node_weight'][i])!r}")
+    with open(path, "w") as f:
+        f.write("\n".join(lines))      # no trailing newline: the loader's `while(!f.eof())` would read one more, empty, node line
+
+
+class RefVocabulary:
+    """The reference's ORBVocabulary (vendored DBoW2 TemplatedVocabulary<FORB::TDescriptor, FORB>), loaded from a text file."""
+
+    def __init__(self, path):
+        self._l = lib()
+        self._v = self._l.refbow_load_text(str(path).encode())
+        if not self._v:
+            raise RuntimeError(f"DBoW2 loadFromTextFile failed on {path}")
+        self.words = self._l.refbow_size(self._v)
+
+    def __del__(self):
+        try:
+            self._l.refbow_destroy(self._v)
+        except Exception:
+            pass
+
+    def transform(self, desc, levelsup=4):
+        """Frame::ComputeBoW (Frame.cc:738-745) -> (bow_id, bow_val, fv_node, fv_start, fv_feat, n_valid), all in std::map order"""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        bow_id, bow_val = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.float64)
+        fv_node, fv_start, fv_feat = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32)
+        counts = np.zeros(3, np.int32)
+        self._l.refbow_transform(self._v, _ptr(desc), n, levelsup, _ptr(bow_id), _ptr(bow_val), _ptr(fv_node), _ptr(fv_start), _ptr(fv_feat),
+                                 _ptr(counts))
+        return bow_id[:counts[0]], bow_val[:counts[0]], fv_node[:counts[1]], fv_start[:counts[1]], fv_feat[:counts[2]], int(counts[2])
+
+
+def descriptor_distance(a, b):
+    """DBoW2::FORB::distance (FORB.cpp:79-97) -- the same bit trick as ORBmatcher::DescriptorDistance (ORBmatcher.cc:2058-2074)"""
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    return lib().refbow_distance(_ptr(a), _ptr(b))

@@ -1,10 +1,14 @@
 """GPU parity of the bag-of-words transform ("next" row: Frame::ComputeBoW, Frame.cc:738-745 ->
-DBoW2 TemplatedVocabulary::transform, TemplatedVocabulary.h:1139-1275) against the std::map-based oracle, on seeded
+DBoW2 TemplatedVocabulary::transform, TemplatedVocabulary.h:1139-1275) against the std::map-based oracle and -- when
+oracle/_ref/liborbref.so is present -- against the reference's vendored DBoW2 itself (loadFromTextFile + transform), on seeded
 synthetic vocabulary trees (ORBvoc.txt.bin is not available offline)."""
+import tempfile
+from pathlib import Path
+
 import numpy as np
 import pytest
 
-from oracle import port
+from oracle import port, ref
 from orb_slam3_ros_b200.bow import Vocabulary, synthetic_vocabulary
 
 pytestmark = pytest.mark.gpu
@@ -23,9 +27,30 @@ def _descriptors(vocab, n, rng, near=0.7):
     return d
 
 
+_dbow2 = {}
+
+
+def _vendored_dbow2(vocab):
+    """the same tree loaded by the reference's DBoW2 (its text loader accepts k <= 20, L <= 10); None when not available"""
+    if not ref.available() or int(vocab["child_count"].max()) > 20 or vocab["depth"] > 10:
+        return None
+    key = (id(vocab), vocab["node_desc"].tobytes(), vocab["node_weight"].tobytes())
+    if key not in _dbow2:
+        with tempfile.TemporaryDirectory() as d:
+            ref.write_vocabulary_text(vocab, Path(d) / "voc.txt")
+            _dbow2.clear()
+            _dbow2[key] = ref.RefVocabulary(Path(d) / "voc.txt")
+    return _dbow2[key]
+
+
 def _check(vocab, sets, levelsup, norm):
     v = Vocabulary(vocab)
     got = v.transform(sets, levelsup, norm)
+    rv = _vendored_dbow2(vocab) if norm == 1 else None      # ORBvoc uses L1 scoring (header `.. 0 0`)
+    if rv is not None:
+        for s, g in zip(sets, got):
+            w = rv.transform(s, levelsup)
+            assert all(np.array_equal(a, b) for a, b in zip(w[:5], g[:5])) and w[5] == g[5], "vs the vendored DBoW2"
     for s, g in zip(sets, got):
         w = port.bow_transform(vocab, s, levelsup, norm)
         assert np.array_equal(w[0], g[0])

@@ -87,3 +87,34 @@ def test_reference_source_batch_matches_single_calls():
         rc, k, d, m = e.extract(imgs[f], (0, 100))
         assert counts[f, 0] == len(k) and counts[f, 1] == m
         assert np.array_equal(kps[f, :len(k)], k) and np.array_equal(desc[f, :len(k)], d)
+
+
+@pytest.mark.parametrize("k,depth,ragged,levelsup,n", [(10, 3, False, 2, 700), (10, 4, False, 4, 1500), (6, 5, True, 4, 900), (8, 3, True, 1, 300),
+                                                       (10, 2, False, 4, 50), (5, 3, False, 3, 0)])
+def test_bow_port_equals_vendored_dbow2(tmp_path, k, depth, ragged, levelsup, n):
+    """Frame::ComputeBoW: the port's restatement against the reference's vendored DBoW2 (loadFromTextFile + transform), on a seeded
+    vocabulary written in the ORBvoc.txt format; word ids, L1-normalised tf-idf values (bit-exact doubles), feature-vector nodes and
+    their feature lists, all in std::map order."""
+    from orb_slam3_ros_b200.bow import synthetic_vocabulary
+    vocab = synthetic_vocabulary(k, depth, seed=k * 10 + depth, stop_fraction=0.1, ragged=ragged)
+    ref.write_vocabulary_text(vocab, tmp_path / "voc.txt")
+    rv = ref.RefVocabulary(tmp_path / "voc.txt")
+    assert rv.words == int((vocab["node_word"] >= 0).sum())
+    rng = np.random.default_rng(n + depth)
+    desc = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    if n > 10:                                                     # some descriptors equal to node descriptors: distance ties, exact hits
+        desc[:10] = vocab["node_desc"][rng.integers(1, len(vocab["node_desc"]), 10)]
+    got = port.bow_transform(vocab, desc, levelsup, 1)
+    want = rv.transform(desc, levelsup)
+    for g, w in zip(got[:5], want[:5]):
+        assert np.array_equal(g, w)
+    assert got[5] == want[5]
+
+
+def test_descriptor_distance_equals_forb_distance():
+    rng = np.random.default_rng(3)
+    a, b = rng.integers(0, 256, (200, 32), dtype=np.uint8), rng.integers(0, 256, (200, 32), dtype=np.uint8)
+    b[:5] = a[:5]
+    a[5], b[5] = 0, 255
+    for x, y in zip(a, b):
+        assert port.hamming(x, y) == ref.descriptor_distance(x, y) == int(np.unpackbits(x ^ y).sum())
