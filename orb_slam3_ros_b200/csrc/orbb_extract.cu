@@ -1225,18 +1225,25 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
     }
     {
         int items = 0;
-        for (int l = 0; l < nl; l++) {
-            const LevelPlan& L = P.lv[l];
-            ApronLevel& A = P.apron[l];
-            A.itemBase = items;
-            A.rightChunk0 = (kRoiX + L.w) / 16;                                   // first chunk with a column >= w
-            A.nRight = (kRoiX + L.w + kEdge - 1) / 16 - A.rightChunk0 + 1;
-            A.interiorChunks = std::max(A.rightChunk0 - 2, 1);                    // chunks 2 .. rightChunk0-1 lie inside the image
-            A.invIC = A.interiorChunks > 1 ? 0xffffffffu / (unsigned)A.interiorChunks + 1u : 0u;
-            A.invNR = A.nRight > 1 ? 0xffffffffu / (unsigned)A.nRight + 1u : 0u;
-            items += 2 * kEdge * A.interiorChunks + (L.h + 2 * kEdge) * (2 + A.nRight);
+        for (int thin = 0; thin < 2; thin++) {
+            items = 0;
+            for (int l = 0; l < nl; l++) {
+                const LevelPlan& L = P.lv[l];
+                ApronLevel& A = thin ? P.apronThin[l] : P.apron[l];
+                const int depth = thin ? kThinApron : kEdge;
+                A.itemBase = items;
+                A.rows = depth;
+                A.leftChunk0 = (kRoiX - depth) / 16;                                  // chunks that hold the columns -depth .. -1
+                A.nLeft = 2 - A.leftChunk0;                                           // (kRoiX = 32: chunks 0,1 / chunk 1)
+                A.rightChunk0 = (kRoiX + L.w) / 16;                                   // first chunk with a column >= w
+                A.nRight = (kRoiX + L.w + depth - 1) / 16 - A.rightChunk0 + 1;
+                A.interiorChunks = std::max(A.rightChunk0 - 2, 1);                    // chunks 2 .. rightChunk0-1 lie inside the image
+                A.invIC = A.interiorChunks > 1 ? 0xffffffffu / (unsigned)A.interiorChunks + 1u : 0u;
+                A.invNR = A.nRight > 1 ? 0xffffffffu / (unsigned)A.nRight + 1u : 0u;
+                items += 2 * depth * A.interiorChunks + (L.h + 2 * depth) * (A.nLeft + A.nRight);
+            }
+            (thin ? P.apronThinItems : P.apronItems) = items;
         }
-        P.apronItems = items;
     }
     P.bandsTotal = (int)bands.size(); P.bandSmem = bandSmem;
     {   // k_fast_cell: tile pitch 64 when every cell (+6 margin, +15 alignment) fits, else 96; smem for the tallest cell
@@ -1355,10 +1362,12 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
         } else k_pyr_resize<<<grid, 256, 0, st>>>(h->dPlan, B, l);
         h->launches++;
     }
-    {
+    {   // only the blur reads beyond the image edge, 3 pixels: the 19-px apron is built when somebody asks for it (ensure_full_apron)
+        static const bool fullApron = getenv("ORBB_FULL_APRON") != nullptr;      // (A/B switch)
         ApronTable T;
-        for (int l = 0; l <= ORBB_MAX_LEVELS; l++) T.base[l] = l < P.nlevels ? P.apron[l].itemBase : P.apronItems;
-        k_pyr_apron16<<<dim3((P.apronItems + 255) / 256, nframes), 256, 0, st>>>(h->dPlan, B, T, P.nlevels);
+        for (int l = 0; l <= ORBB_MAX_LEVELS; l++)
+            T.base[l] = fullApron ? (l < P.nlevels ? P.apron[l].itemBase : P.apronItems) : (l < P.nlevels ? P.apronThin[l].itemBase : P.apronThinItems);
+        k_pyr_apron16<<<dim3((T.base[P.nlevels] + 255) / 256, nframes), 256, 0, st>>>(h->dPlan, B, T, P.nlevels, fullApron ? 0 : 1);
     }
     h->launches++;
     const bool fork = !h->profiling;
@@ -1429,6 +1438,7 @@ static int run_batch(orbb_extractor* h, const uint8_t* dImgs, int nframes, size_
     }
     h->lastFrames = f0 + nframes;
     h->hPyrFresh = false;
+    h->apronFull = false;
     return ORBB_OK;
 }
 
@@ -1731,6 +1741,7 @@ int orbb_extract_batch_host_submit(orbb_extractor* h, const uint8_t* host_imgs, 
         h->launches += h->g1Launches;
         h->lastFrames = 1;
         h->hPyrFresh = false;
+        h->apronFull = false;
         const int ncopy1 = std::min(capacity, P.kpCap);
         ORBB_CUDA(h, cudaMemcpyAsync(h->hCounts, h->b.outCount, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
         ORBB_CUDA(h, cudaMemcpyAsync(h->hCounts + 2, h->b.status, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1821,6 +1832,21 @@ int orbb_extract(orbb_extractor* h, const uint8_t* img, int width, int height, s
     return rc;
 }
 
+// The 19-px reflect-101 apron around every level (ComputePyramid's copyMakeBorder, :1185-1191) of the frames of the last
+// extraction.  Nothing in the pipeline reads it beyond the 3 pixels the blur needs, so it is built here, when the pyramid is
+// handed out (mvImagePyramid views, stage taps), instead of with every frame.
+static int ensure_full_apron(orbb_extractor* h) {
+    if (h->apronFull || h->lastFrames <= 0) return ORBB_OK;
+    const Plan& P = h->plan;
+    ApronTable T;
+    for (int l = 0; l <= ORBB_MAX_LEVELS; l++) T.base[l] = l < P.nlevels ? P.apron[l].itemBase : P.apronItems;
+    k_pyr_apron16<<<dim3((P.apronItems + 255) / 256, h->lastFrames), 256, 0, h->stream>>>(h->dPlan, h->b, T, P.nlevels, 0);
+    ORBB_CUDA(h, cudaGetLastError());
+    h->launches++;
+    h->apronFull = true;
+    return ORBB_OK;
+}
+
 int orbb_pyramid_level(orbb_extractor* h, int level, const uint8_t** ptr, int* width, int* height, size_t* stride) {
     if (!h || !ptr) return ORBB_ERR_ARG;
     if (!h->planValid || h->lastFrames == 0) return set_err(h, ORBB_ERR_ARG, "no frame has been extracted yet");
@@ -1828,6 +1854,8 @@ int orbb_pyramid_level(orbb_extractor* h, int level, const uint8_t** ptr, int* w
     ORBB_CUDA(h, cudaSetDevice(h->device));
     const Plan& P = h->plan;
     if (!h->hPyrFresh) {      // lazy D2H of frame 0's whole pyramid slab
+        const int arc = ensure_full_apron(h);
+        if (arc) return arc;
         if (h->hPyrBytes < P.pyrStride) {
             if (h->hPyr) cudaFreeHost(h->hPyr);
             h->hPyr = nullptr; h->hPyrBytes = 0;
@@ -1856,7 +1884,7 @@ int orbb_debug_level(orbb_extractor* h, int frame, int level, int blurred, int b
     const uint8_t* src;
     size_t pitch;
     if (blurred) { src = h->b.blur + (size_t)frame * P.blurStride + L.blurOff; pitch = L.bpitch; }
-    else if (bordered) { src = h->b.pyr + (size_t)frame * P.pyrStride + L.pyrOff + (kRoiX - kEdge); pitch = L.pitch; w += 2 * kEdge; hh += 2 * kEdge; }
+    else if (bordered) { const int arc = ensure_full_apron(h); if (arc) return arc; src = h->b.pyr + (size_t)frame * P.pyrStride + L.pyrOff + (kRoiX - kEdge); pitch = L.pitch; w += 2 * kEdge; hh += 2 * kEdge; }
     else { src = h->b.pyr + (size_t)frame * P.pyrStride + L.roiOff; pitch = L.pitch; }
     if (width) *width = w;
     if (height) *height = hh;

@@ -42,8 +42,10 @@ struct LevelPlan {
     int fastResize;                    // 1: the 4 source taps of every column group fit 3 aligned words (k_pyr_resize_s)
 };
 
-// k_pyr_apron16 work decomposition of one level (16-byte chunks that contain apron bytes)
-struct ApronLevel { int itemBase, interiorChunks, rightChunk0, nRight; unsigned invIC, invNR; };     // inv* = 2^32 / n + 1
+// k_pyr_apron16 work decomposition of one level (16-byte chunks that contain apron bytes): `rows` apron rows above and below
+// the image, `nLeft` chunks from chunk `leftChunk0` at the left end of every bordered row, `nRight` from `rightChunk0` at the right
+struct ApronLevel { int itemBase, interiorChunks, rightChunk0, nRight, rows, leftChunk0, nLeft; unsigned invIC, invNR; };     // inv* = 2^32 / n + 1
+constexpr int kThinApron = 3;      // what the 7x7 blur reads around the image (the only in-pipeline reader of the apron)
 
 struct Plan {
     int nlevels, W, H;
@@ -56,8 +58,9 @@ struct Plan {
     unsigned cellKeyStride, rawStride, nodeStride, selStride;   // entries per frame
     int umax[16];
     LevelPlan lv[ORBB_MAX_LEVELS];
-    ApronLevel apron[ORBB_MAX_LEVELS];
-    int apronItems;
+    ApronLevel apron[ORBB_MAX_LEVELS];      // the full 19-px apron of mvImagePyramid (built on demand: nothing in the pipeline reads it)
+    ApronLevel apronThin[ORBB_MAX_LEVELS];  // the 3-px ring the blur needs (built with every frame)
+    int apronItems, apronThinItems;
 };
 
 struct QNode {                     // quadtree node: UL=(x0,y0) BR=(x1,y1); keys = segment of a ping-pong buffer
@@ -188,6 +191,7 @@ struct orbb_extractor {
     uint8_t* dColor = nullptr; size_t colorBytes = 0;      // device copy of a raw input frame (orbb_extract_color / _rectified / _resized)
     int2* rsTab = nullptr; int rsTabY = 0, rsSw = 0, rsSh = 0, rsDw = 0, rsDh = 0;      // cv::resize tables of orbb_extract_resized
     uint8_t* hPyr = nullptr; size_t hPyrBytes = 0; bool hPyrFresh = false;
+    bool apronFull = false;          // the 19-px apron of the last extraction has been built (ensure_full_apron)
     int32_t* hCounts = nullptr; int hCountsCap = 0;
     std::string err;
 };

@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(PR_THREADS, 12) k_pyr_resize_t(const Plan* __r
 // image words (one PRMT); words inside the image are copied; only the words that straddle the right edge go byte by byte.
 struct ApronTable { int base[ORBB_MAX_LEVELS + 1]; };        // first item of every level (kernel parameter: constant bank)
 
-__global__ void __launch_bounds__(256) k_pyr_apron16(const Plan* __restrict__ P, Bufs B, const ApronTable T, int nlevels) {
+__global__ void __launch_bounds__(256) k_pyr_apron16(const Plan* __restrict__ P, Bufs B, const ApronTable T, int nlevels, int thin) {
     int item = blockIdx.x * 256 + threadIdx.x;
     if (item >= T.base[nlevels]) return;
     const int frame = blockIdx.y;
@@ -226,28 +226,28 @@ __global__ void __launch_bounds__(256) k_pyr_apron16(const Plan* __restrict__ P,
 #pragma unroll
     for (int l = 1; l < ORBB_MAX_LEVELS; l++) level += (l < nlevels && item >= T.base[l]);
     const LevelPlan& L = P->lv[level];
-    const ApronLevel A = P->apron[level];
+    const ApronLevel A = thin ? P->apronThin[level] : P->apron[level];
     const int w = L.w, h = L.h, pitch = L.pitch;
     item -= A.itemBase;
     // three item classes per level, each row-major (coalesced) and each taking ONE path below in all lanes of a warp:
-    // chunks inside the image of the 38 apron rows (copy), the two left chunks of every bordered row (reflection by PRMT),
+    // chunks inside the image of the 2 x A.rows apron rows (copy), the left chunks of every bordered row (reflection by PRMT),
     // the right-edge chunks of every bordered row (bytes)
     int by, chunk;                                          // bordered row (0 = top apron row), chunk within the row
-    const int nI = 2 * kEdge * A.interiorChunks, nL = 2 * (h + 2 * kEdge);
+    const int nI = 2 * A.rows * A.interiorChunks, nL = A.nLeft * (h + 2 * A.rows);
     if (item < nI) {
         by = A.interiorChunks == 1 ? item : (int)__umulhi((unsigned)item, A.invIC);
         chunk = 2 + item - by * A.interiorChunks;
-        if (by >= kEdge) by += h;
+        if (by >= A.rows) by += h;
     } else if (item < nI + nL) {
         item -= nI;
-        by = item >> 1;
-        chunk = item & 1;
+        by = A.nLeft == 2 ? item >> 1 : item;
+        chunk = A.nLeft == 2 ? item & 1 : A.leftChunk0;
     } else {
         item -= nI + nL;
         by = A.nRight == 1 ? item : (int)__umulhi((unsigned)item, A.invNR);
         chunk = A.rightChunk0 + item - by * A.nRight;
     }
-    const int iy = by - kEdge;
+    const int iy = by - A.rows;
     const int sy = iy < 0 ? -iy : (iy >= h ? 2 * h - 2 - iy : iy);
     uint8_t* roi = B.pyr + (size_t)frame * P->pyrStride + L.roiOff;
     const uint8_t* srow = roi + (ptrdiff_t)sy * pitch;
