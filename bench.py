@@ -290,6 +290,20 @@ def run_ours(a):
     for _ in range(50):
         ext1(one, None, LAPPING)
     single_ms = (time.perf_counter() - t0) / 50 * 1e3
+    # the same call without the Python mirror's per-call work (result slicing / copies): orbb_extract straight on the handle's
+    # pinned staging, which is what the C++ adapter does
+    import ctypes as _C
+    from orb_slam3_ros_b200 import capi as _capi
+    _cap, _k, _d = ext1._staging()
+    _n, _m = _C.c_int(0), _C.c_int(0)
+    _args = (ext1._h, _capi.ptr(one), W_, H_, one.strides[0], int(LAPPING[0]), int(LAPPING[1]), _capi.ptr(_k), _capi.ptr(_d), _cap,
+             _C.byref(_n), _C.byref(_m))
+    for _ in range(5):
+        _capi.check(ext1._lib.orbb_extract(*_args), ext1._h)
+    t0 = time.perf_counter()
+    for _ in range(100):
+        ext1._lib.orbb_extract(*_args)
+    single_c_ms = (time.perf_counter() - t0) / 100 * 1e3
     del ext1
 
     # ---- roofline of the dominant kernel (and of the whole path) ----
@@ -484,6 +498,7 @@ def run_ours(a):
                        "parallelism": f"frames partitioned over {world} GPU(s), no collective"},
             "keypoints_per_frame": n_kp / B,
             "single_frame_latency_ms": single_ms,
+            "single_frame_c_abi_ms": single_c_ms,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / a.steps,
                     "api": "orbb_extract_batch_host_submit/_wait on two alternating handles (pinned host frames -> keypoints+descriptors)",

@@ -315,7 +315,7 @@ __device__ void split_node_warp(const QNode nd, u64* k0, u64* k1, int4* out, int
 // The same by the whole CTA for a node with many keys (the first passes over a large level have fewer nodes than warps):
 // every warp takes a contiguous part of the keys -- four keys per lane are loaded before they are used, so four loads are
 // in flight -- and the parts' counts give each warp its output offsets.  sPart: int[warps][4].
-constexpr int OT_BIG_NODE = 4096, OT_BIG_LIST = 16;
+constexpr int OT_BIG_NODE = 4096, OT_BIG_NODE_LATENCY = 512, OT_BIG_LIST = 16;
 __device__ void split_node_cta(const QNode nd, u64* k0, u64* k1, int4* out, int (*sPart)[4], int tid, int nw) {
     const int lane = tid & 31, warp = tid >> 5;
     const int cnt = node_count(nd);
@@ -483,7 +483,7 @@ __device__ void sort_emul_cta(u64* a, int n, int* Lp, int* Rp, unsigned* leaf, i
 }
 
 template <int OT_T>
-__global__ void __launch_bounds__(OT_T) k_octree(const Plan* __restrict__ P, Bufs B, int level0) {
+__global__ void __launch_bounds__(OT_T) k_octree(const Plan* __restrict__ P, Bufs B, int level0, int bigNode) {
     constexpr int OT_W = OT_T / 32;
     // grid = (frames, levels): CTAs are dispatched x-fastest, so the long-running low levels of ALL frames start first and
     // the short high levels fill the tail
@@ -642,9 +642,9 @@ __global__ void __launch_bounds__(OT_T) k_octree(const Plan* __restrict__ P, Buf
                     const unsigned bal = __ballot_sync(0xffffffffu, ex);
                     if (ex) elist[run + __popc(bal & ((1u << lane) - 1))] = i;
                     if (OT_T > 128) {                               // large levels: nodes with many keys are split by the whole CTA
-                        const unsigned big = __ballot_sync(0xffffffffu, cnt >= OT_BIG_NODE);
+                        const unsigned big = __ballot_sync(0xffffffffu, cnt >= bigNode);
                         const int slot = nBig + __popc(big & ((1u << lane) - 1));
-                        if (cnt >= OT_BIG_NODE && slot < OT_BIG_LIST) sBigList[slot] = run + __popc(bal & ((1u << lane) - 1));
+                        if (cnt >= bigNode && slot < OT_BIG_LIST) sBigList[slot] = run + __popc(bal & ((1u << lane) - 1));
                         nBig += __popc(big);
                     }
                     run += __popc(bal);
@@ -1357,7 +1357,11 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
         } else if (L.fastResize) {
             constexpr int rowsPerCta = PR_ROWS * (PR_THREADS / 32);
             static const bool tmaResize = getenv("ORBB_RESIZE_NO_TMA") == nullptr;      // (A/B switch; TMA staging measured 3 % faster)
-            if (tmaResize && L.fastResize == 2) k_pyr_resize_t<<<dim3(grid.x, (L.h + rowsPerCta - 1) / rowsPerCta, nframes), PR_THREADS, 0, st>>>(h->dPlan, B, l);
+            constexpr int rowsPerCtaLat = PR_ROWS_LATENCY * (PR_THREADS / 32);
+            static const int pyrLatencyFrames = getenv("ORBB_PYR_LATENCY_FRAMES") ? atoi(getenv("ORBB_PYR_LATENCY_FRAMES")) : 4;
+            if (tmaResize && L.fastResize == 2 && nframes <= pyrLatencyFrames)
+                k_pyr_resize_t<PR_ROWS_LATENCY><<<dim3(grid.x, (L.h + rowsPerCtaLat - 1) / rowsPerCtaLat, nframes), PR_THREADS, 0, st>>>(h->dPlan, B, l);
+            else if (tmaResize && L.fastResize == 2) k_pyr_resize_t<PR_ROWS><<<dim3(grid.x, (L.h + rowsPerCta - 1) / rowsPerCta, nframes), PR_THREADS, 0, st>>>(h->dPlan, B, l);
             else k_pyr_resize_s<<<dim3(grid.x, (L.h + rowsPerCta - 1) / rowsPerCta, nframes), PR_THREADS, 0, st>>>(h->dPlan, B, l);
         } else k_pyr_resize<<<grid, 256, 0, st>>>(h->dPlan, B, l);
         h->launches++;
@@ -1398,8 +1402,13 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
     // With stage profiling on, everything stays on one stream so that the stage events mean what they say.
     if (fork) ORBB_CUDA(h, cudaEventRecord(ln.evFork, st));
     // images whose first level has many cells (4K class) get the large CTA on every level: more warps split nodes at once
-    if (P.lv[0].nCols * P.lv[0].nRows >= OT_BIG_CELLS) k_octree<OT_THREADS_BIG><<<dim3(nframes, P.nlevels), OT_THREADS_BIG, 0, st>>>(h->dPlan, B, 0);
-    else k_octree<OT_THREADS><<<dim3(nframes, P.nlevels), OT_THREADS, 0, st>>>(h->dPlan, B, 0);
+    // 512 threads per (frame, level) for levels with many cells -- and for a call with a few frames, where the quadtree of
+    // level 0 is one CTA on the critical path and a warp issues one dependent instruction every few cycles: more warps split
+    // more nodes at once, and nodes with many keys are split by the whole CTA
+    static const int otLatencyFrames = getenv("ORBB_OCTREE_LATENCY_FRAMES") ? atoi(getenv("ORBB_OCTREE_LATENCY_FRAMES")) : 4;
+    if (P.lv[0].nCols * P.lv[0].nRows >= OT_BIG_CELLS) k_octree<OT_THREADS_BIG><<<dim3(nframes, P.nlevels), OT_THREADS_BIG, 0, st>>>(h->dPlan, B, 0, OT_BIG_NODE);
+    else if (nframes <= otLatencyFrames) k_octree<OT_THREADS_BIG><<<dim3(nframes, P.nlevels), OT_THREADS_BIG, 0, st>>>(h->dPlan, B, 0, OT_BIG_NODE_LATENCY);
+    else k_octree<OT_THREADS><<<dim3(nframes, P.nlevels), OT_THREADS, 0, st>>>(h->dPlan, B, 0, OT_BIG_NODE);
     if (fork) {
         ORBB_CUDA(h, cudaStreamWaitEvent(ln.blurSt, ln.evFork, 0));
         k_blur<<<dim3(P.blurTilesTotal, nframes), BLUR_THREADS, 0, ln.blurSt>>>(h->dPlan, B);

@@ -14,6 +14,7 @@
 #pragma once
 
 constexpr int PR_ROWS = 8;            // destination rows per thread
+constexpr int PR_ROWS_LATENCY = 2;    // ... in calls with a few frames (k_pyr_resize_t only)
 constexpr int PR_THREADS = 128;       // 32 word-columns x 4 row strips
 
 __global__ void __launch_bounds__(256) k_pyr_level0_v(const Plan* __restrict__ P, Bufs B, const uint8_t* __restrict__ src,
@@ -131,17 +132,20 @@ __device__ __forceinline__ unsigned vresize4(const int (&h0)[4], const int (&h1)
     return out;
 }
 
+// ROWS = destination rows per thread: PR_ROWS for batches; PR_ROWS_LATENCY for a call with a few frames, where a level is one
+// short dependent kernel on the critical path and more, shorter threads finish it sooner.
+template <int ROWS>
 __global__ void __launch_bounds__(PR_THREADS, 12) k_pyr_resize_t(const Plan* __restrict__ P, Bufs B, int level) {
     __shared__ __align__(128) uint8_t sSrc[PR_SROWS * PR_SPITCH];
-    __shared__ __align__(16) int4 sRow[(PR_THREADS / 32) * PR_ROWS];      // per destination row of the CTA: {r0, r1, b0 << 16, b1 << 16}
+    __shared__ __align__(16) int4 sRow[(PR_THREADS / 32) * ROWS];      // per destination row of the CTA: {r0, r1, b0 << 16, b1 << 16}
     __shared__ __align__(8) unsigned long long sBar;
     const LevelPlan& L = P->lv[level];
     const LevelPlan& S = P->lv[level - 1];
     const int tid = threadIdx.x;
     const int word = blockIdx.x * 32 + (tid & 31);
-    constexpr int rowsPerCta = (PR_THREADS / 32) * PR_ROWS;
+    constexpr int rowsPerCta = (PR_THREADS / 32) * ROWS;
     const int dyc = blockIdx.y * rowsPerCta;                              // first destination row of the CTA
-    const int dy0 = dyc + (tid >> 5) * PR_ROWS;
+    const int dy0 = dyc + (tid >> 5) * ROWS;
     const int frame = blockIdx.z;
     const int Lw = L.w, Lh = L.h, Lpitch = L.pitch, Sh1 = S.h - 1, Spitch = S.pitch;
     // ---- stage: source rows rs0..rs1, bytes [xs0, xs0 + PR_SPITCH); the row table of the CTA ----
@@ -179,8 +183,8 @@ __global__ void __launch_bounds__(PR_THREADS, 12) k_pyr_resize_t(const Plan* __r
         }
     }
     uint8_t* d = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + (size_t)dy0 * Lpitch + 4 * word;
-    const int4* rowt = sRow + (tid >> 5) * PR_ROWS;
-    const int rows = min(PR_ROWS, Lh - dy0);
+    const int4* rowt = sRow + (tid >> 5) * ROWS;
+    const int rows = min(ROWS, Lh - dy0);
     mbar_wait(&sBar, 0);
     // Walk down the SOURCE rows of the strip: every source row gets its horizontal pass exactly once (into ha / hb in turn),
     // and the destination row whose lower source row it is gets emitted right after (the source row index grows with every

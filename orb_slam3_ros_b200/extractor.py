@@ -30,6 +30,7 @@ class ORBextractor:
 
     def close(self):
         if getattr(self, "_h", None):
+            self._free_staging()
             self._lib.orbb_destroy(self._h)
             self._h = None
 
@@ -73,20 +74,37 @@ class ORBextractor:
         if image.strides[1] != 1:
             image = np.ascontiguousarray(image)
         h, w = image.shape
-        cap = self.max_keypoints
-        kps = np.zeros(cap, KP_DTYPE)
-        desc = np.zeros((cap, 32), np.uint8)
+        cap, kps, desc = self._staging()
         n, mono = C.c_int(0), C.c_int(0)
         rc = self._lib.orbb_extract(self._h, capi.ptr(image), w, h, image.strides[0], int(lapping[0]), int(lapping[1]),
                                     capi.ptr(kps), capi.ptr(desc), cap, C.byref(n), C.byref(mono))
         if rc == capi.ORBB_ERR_CAPACITY:      # the plan for this image size allows more keypoints than the estimate
-            cap = self.max_keypoints
-            kps = np.zeros(cap, KP_DTYPE)
-            desc = np.zeros((cap, 32), np.uint8)
+            cap, kps, desc = self._staging()
             rc = self._lib.orbb_extract(self._h, capi.ptr(image), w, h, image.strides[0], int(lapping[0]), int(lapping[1]),
                                         capi.ptr(kps), capi.ptr(desc), cap, C.byref(n), C.byref(mono))
         capi.check(rc, self._h)
         return mono.value, kps[:n.value].copy(), desc[:n.value].copy()
+
+    def _staging(self):
+        """result staging in pinned host memory (orbb_host_alloc), as the C++ adapter keeps it: the call's device-to-host copies
+        are then asynchronous instead of going through the driver's pageable path"""
+        cap = self.max_keypoints
+        if cap > getattr(self, "_stage_cap", 0):
+            self._free_staging()
+            self._stage_ptrs = [self._lib.orbb_host_alloc(cap * KP_DTYPE.itemsize), self._lib.orbb_host_alloc(cap * 32)]
+            if not all(self._stage_ptrs):
+                raise MemoryError("orbb_host_alloc failed")
+            self._stage_kps = np.frombuffer((C.c_uint8 * (cap * KP_DTYPE.itemsize)).from_address(self._stage_ptrs[0]), KP_DTYPE)
+            self._stage_desc = np.frombuffer((C.c_uint8 * (cap * 32)).from_address(self._stage_ptrs[1]), np.uint8).reshape(cap, 32)
+            self._stage_cap = cap
+        return self._stage_cap, self._stage_kps, self._stage_desc
+
+    def _free_staging(self):
+        for p in getattr(self, "_stage_ptrs", []):
+            if p:
+                self._lib.orbb_host_free(p)
+        self._stage_ptrs, self._stage_cap = [], 0
+        self._stage_kps = self._stage_desc = None
 
     def extract_color(self, image, rgb=True, lapping=(0, 0)):
         """colour frame [h,w,3|4] uint8: cv::cvtColor(..2GRAY) on the device (Tracking.cc:1498-1525), then operator()"""

@@ -34,26 +34,36 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
     mvImagePyramid.resize(nlevels);
 }
 
-ORBextractor::~ORBextractor() { orbb_destroy(mpHandle); }
+ORBextractor::~ORBextractor() {
+    orbb_host_free(mpKeypointStaging);
+    orbb_host_free(mpDescStaging);
+    orbb_destroy(mpHandle);
+}
 
 void* ORBextractor::Staging(int& cap) {
     cap = orbb_max_keypoints(mpHandle);
-    mvKeypointStaging.resize((size_t)cap * sizeof(orbb_keypoint));
-    mvDescStaging.resize((size_t)cap * 32);
-    return mvKeypointStaging.data();
+    if (cap > mnStagingCap) {
+        orbb_host_free(mpKeypointStaging);
+        orbb_host_free(mpDescStaging);
+        mpKeypointStaging = static_cast<unsigned char*>(orbb_host_alloc((size_t)cap * sizeof(orbb_keypoint)));
+        mpDescStaging = static_cast<unsigned char*>(orbb_host_alloc((size_t)cap * 32));
+        mnStagingCap = (mpKeypointStaging && mpDescStaging) ? cap : 0;
+        if (!mnStagingCap) throw std::runtime_error("liborbb200: pinned staging allocation failed");
+    }
+    return mpKeypointStaging;
 }
 
 // common tail of the extraction entry points: error mapping, output containers, pyramid views
 int ORBextractor::Deliver(int rc, int n, int monoIndex, std::vector<cv::KeyPoint>& _keypoints, cv::OutputArray _descriptors) {
     if (rc == ORBB_ERR_EMPTY) return -1;
     if (rc != ORBB_OK) throw std::runtime_error(std::string("liborbb200 extraction failed: ") + orbb_last_error(mpHandle));
-    const orbb_keypoint* kps = reinterpret_cast<const orbb_keypoint*>(mvKeypointStaging.data());
+    const orbb_keypoint* kps = reinterpret_cast<const orbb_keypoint*>(mpKeypointStaging);
     if (n == 0) {
         _descriptors.release();
     } else {
         _descriptors.create(n, 32, CV_8U);
         cv::Mat descriptors = _descriptors.getMat();
-        for (int i = 0; i < n; i++) memcpy(descriptors.ptr(i), mvDescStaging.data() + (size_t)i * 32, 32);
+        for (int i = 0; i < n; i++) memcpy(descriptors.ptr(i), mpDescStaging + (size_t)i * 32, 32);
     }
     _keypoints = std::vector<cv::KeyPoint>(n);
     for (int i = 0; i < n; i++) {
@@ -87,7 +97,7 @@ int ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*_mask*/, st
     int cap = 0, n = 0, monoIndex = 0;
     orbb_keypoint* kps = static_cast<orbb_keypoint*>(Staging(cap));
     const int rc = orbb_extract(mpHandle, image.data, image.cols, image.rows, (size_t)image.step, vLappingArea[0], vLappingArea[1],
-                                kps, mvDescStaging.data(), cap, &n, &monoIndex);
+                                kps, mpDescStaging, cap, &n, &monoIndex);
     return Deliver(rc, n, monoIndex, _keypoints, _descriptors);
 }
 
@@ -97,11 +107,11 @@ int ORBextractor::ExtractColor(const unsigned char* data, int cols, int rows, si
     int cap = 0, n = 0, monoIndex = 0;
     orbb_keypoint* kps = static_cast<orbb_keypoint*>(Staging(cap));
     int rc = orbb_extract_color(mpHandle, data, cols, rows, step, channels, bRGB ? 1 : 0, vLappingArea[0], vLappingArea[1], kps,
-                                mvDescStaging.data(), cap, &n, &monoIndex);
+                                mpDescStaging, cap, &n, &monoIndex);
     if (rc == ORBB_ERR_CAPACITY) {                          // first frame of this size: the plan allows more keypoints than the estimate
         kps = static_cast<orbb_keypoint*>(Staging(cap));
         rc = orbb_extract_color(mpHandle, data, cols, rows, step, channels, bRGB ? 1 : 0, vLappingArea[0], vLappingArea[1], kps,
-                                mvDescStaging.data(), cap, &n, &monoIndex);
+                                mpDescStaging, cap, &n, &monoIndex);
     }
     return Deliver(rc, n, monoIndex, _keypoints, _descriptors);
 }
@@ -114,11 +124,11 @@ int ORBextractor::ExtractRectified(orbb_rectifier* rect, cv::InputArray _rawImag
     int cap = 0, n = 0, monoIndex = 0;
     orbb_keypoint* kps = static_cast<orbb_keypoint*>(Staging(cap));
     int rc = orbb_extract_rectified(mpHandle, rect, image.data, (size_t)image.step, vLappingArea[0], vLappingArea[1], kps,
-                                    mvDescStaging.data(), cap, &n, &monoIndex);
+                                    mpDescStaging, cap, &n, &monoIndex);
     if (rc == ORBB_ERR_CAPACITY) {
         kps = static_cast<orbb_keypoint*>(Staging(cap));
         rc = orbb_extract_rectified(mpHandle, rect, image.data, (size_t)image.step, vLappingArea[0], vLappingArea[1], kps,
-                                    mvDescStaging.data(), cap, &n, &monoIndex);
+                                    mpDescStaging, cap, &n, &monoIndex);
     }
     return Deliver(rc, n, monoIndex, _keypoints, _descriptors);
 }
