@@ -807,15 +807,18 @@ __global__ void __launch_bounds__(OT_T) k_octree(const Plan* __restrict__ P, Buf
 // K6: output assembly (:1105-1167): level-major order, pt *= scale for level > 0, keypoints inside the lapping
 // area are written from the back, the others from the front.  One CTA per frame.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_assemble(const Plan* __restrict__ P, Bufs B, int lap0, int lap1) {
+__global__ void __launch_bounds__(1024) k_assemble(const Plan* __restrict__ P, Bufs B, int lap0, int lap1) {
     const int frame = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ int sOff[ORBB_MAX_LEVELS + 1];
-    __shared__ int sWarp[8];
-    if (tid == 0) {
-        int acc = 0;
-        for (int l = 0; l < P->nlevels; l++) { sOff[l] = acc; acc += B.selCount[frame * ORBB_MAX_LEVELS + l]; }
-        sOff[P->nlevels] = acc;
+    __shared__ int sWarp[32];
+    const int nthreads = blockDim.x, nwarps = nthreads >> 5;
+    if (warp == 0) {                                        // exclusive prefix of the per-level counts: one load per lane, one warp scan
+        const int nl = P->nlevels;                          // (ORBB_MAX_LEVELS <= 32)
+        const int c = lane < nl ? B.selCount[frame * ORBB_MAX_LEVELS + lane] : 0;
+        const int inc = warp_incl_scan(c, lane);
+        if (lane < nl) sOff[lane] = inc - c;
+        if (lane == nl - 1) sOff[nl] = inc;
     }
     __syncthreads();
     const int n = min(sOff[P->nlevels], P->kpCap);
@@ -823,7 +826,7 @@ __global__ void __launch_bounds__(256) k_assemble(const Plan* __restrict__ P, Bu
     WorkItem* work = B.work + (size_t)frame * P->kpCap;
     const float fl0 = (float)lap0, fl1 = (float)lap1;
     int stereoRun = 0;
-    for (int base = 0; base < n; base += 256) {
+    for (int base = 0; base < n; base += nthreads) {
         const int g = base + tid;
         bool valid = g < n, st = false;
         int level = 0, x = 0, y = 0;
@@ -841,8 +844,7 @@ __global__ void __launch_bounds__(256) k_assemble(const Plan* __restrict__ P, Bu
         if (lane == 0) sWarp[warp] = __popc(bal);
         __syncthreads();
         int woff = 0, tot = 0;
-#pragma unroll
-        for (int w = 0; w < 8; w++) { woff += w < warp ? sWarp[w] : 0; tot += sWarp[w]; }
+        for (int w = 0; w < nwarps; w++) { woff += w < warp ? sWarp[w] : 0; tot += sWarp[w]; }
         if (valid) {
             const int stBefore = stereoRun + woff + __popc(bal & ((1u << lane) - 1));
             const int pos = st ? n - 1 - stBefore : g - stBefore;
