@@ -1,6 +1,11 @@
+#!/bin/bash
+# One round's measurement set on a GPU box (run under gpurun, one GPU):  bash tools/profile_round.sh <tag>
+#   bench line, reference arm, the ncu launch list of the bench command and one `ncu --set full` capture of a 256-frame batch.
+# Outputs land in gpurun_out/; summarise them here with  python tools/summarize_profiles.py <tag> --rep ... --launches ...
+TAG=${1:-r1}
 set -x
-python bench.py > gpurun_out/bench_r1_k.json 2> gpurun_out/bench_r1_k.err
-python bench.py --impl reference > gpurun_out/bench_r1_k_ref.json 2> gpurun_out/bench_r1_k_ref.err
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r1_k.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --knn-steps 1 > gpurun_out/ncu_l_k.log 2>&1
-ncu --set full --clock-control none --import-source on -f -o gpurun_out/prof_r1_k python tools/prof_extract.py --batch 256 --iters 1 > gpurun_out/ncu_k.log 2>&1
+python bench.py > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err
+python bench.py --impl reference > gpurun_out/bench_${TAG}_ref.json 2> gpurun_out/bench_${TAG}_ref.err
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --knn-steps 1 > gpurun_out/ncu_l_${TAG}.log 2>&1
+ncu --set full --clock-control none --import-source on -f -o gpurun_out/prof_${TAG} python tools/prof_extract.py --batch 256 --iters 1 > gpurun_out/ncu_${TAG}.log 2>&1
 ls -la gpurun_out | tail -8
