@@ -553,6 +553,11 @@ struct Extractor {
                 int* nOut, int* monoOut) {
         *nOut = 0; *monoOut = 0;
         if (!img || w <= 0 || h <= 0) return -1;                                                                   // :1090
+        for (int l = 0; l < nlevels; l++) {          // geometry the reference cannot handle, rejected before any work: a level without
+            const int lw = cv_round((float)w * invScale[l]), lh = cv_round((float)h * invScale[l]);      // pixels (cv::resize asserts
+            if (lw < 1 || lh < 1) return -2;                                                              // dsize.area() > 0, :1183) ...
+            if (lw - 2 * (kEdge - 3) <= 0 || lh - 2 * (kEdge - 3) <= 0) return -2;                        // ... or inside the FAST border (:559)
+        }
         compute_pyramid(img, w, h, stride);
         int rc = compute_keypoints();
         if (rc) return rc;

@@ -135,6 +135,9 @@ def test_too_small_level_is_rejected():
     with pytest.raises(capi.OrbbError) as e:
         ge(synth.frame(90, 120, 0))                 # level 7 would be 33x25: a negative row span, the reference's root count (:559) is undefined
     assert e.value.code == capi.ORBB_ERR_UNSUPPORTED
+    with pytest.raises(capi.OrbbError) as e:
+        ORBextractor(90, 2.0, 10, 17, 16)(synth.frame(236, 192, 1))      # levels shrink to 1x1 and 0x0: cv::resize asserts in the reference
+    assert e.value.code == capi.ORBB_ERR_UNSUPPORTED
 
 
 @pytest.mark.parametrize("shape,nf,nl", [((200, 260), 500, 8), ((150, 400), 300, 8), ((120, 160), 200, 6)])

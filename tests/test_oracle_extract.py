@@ -97,3 +97,10 @@ def test_port_equals_cv2_reference_other_scale_factors(sf, nl):
     for l in range(nl):
         assert np.array_equal(pe.level(l, bordered=True), re_.pyramid[l])
     _same(k0, d0, m0, k1, d1, m1)
+
+
+def test_port_rejects_degenerate_pyramids_without_work():
+    """levels that shrink to nothing (scale 2.0 x 10 levels on a 236x192 frame: level 8 would be 1x1, level 9 0x0) -- cv::resize
+    asserts dsize.area() > 0 in the reference; the port must say "unsupported" at once, not loop"""
+    assert port.PortExtractor(90, 2.0, 10, 17, 16).extract(synth.frame(236, 192, 1))[0] == -2
+    assert port.PortExtractor(100, 1.2, 8).extract(synth.frame(90, 120, 0))[0] == -2          # level 7 = 33x25: inside the FAST border
