@@ -118,3 +118,31 @@ def test_descriptor_distance_equals_forb_distance():
     a[5], b[5] = 0, 255
     for x, y in zip(a, b):
         assert port.hamming(x, y) == ref.descriptor_distance(x, y) == int(np.unpackbits(x ^ y).sum())
+
+
+def test_random_settings_sweep_port_equals_reference_source():
+    """seeded sweep over image sizes, level counts, scale factors, thresholds, budgets, lapping areas and image statistics (natural-like,
+    low contrast = threshold-fallback cells, pure noise = deep tie-heavy quadtrees); geometry the reference cannot handle is skipped
+    when the port says so (the reference itself would assert or throw there)"""
+    rng = np.random.default_rng(20241018)
+    checked = 0
+    for it in range(60):
+        h, w = int(rng.integers(70, 420)), int(rng.integers(70, 640))
+        nl = int(rng.integers(1, 10))
+        sf = float(rng.choice([1.2, 1.2, 1.1, 1.3, 1.5, 2.0, 1.25]))
+        nf = int(rng.integers(1, 2500))
+        ini = int(rng.integers(5, 70))
+        mn = int(rng.integers(1, ini + 1))
+        lap = (int(rng.integers(0, w)), int(rng.integers(0, w)))
+        kind = int(rng.integers(0, 3))
+        img = (rng.integers(0, 256, (h, w), dtype=np.uint8) if kind == 0 else
+               np.clip(synth.frame(h, w, it).astype(np.int32) // 4 + 100, 0, 255).astype(np.uint8) if kind == 1 else synth.frame(h, w, 500 + it))
+        rc, k0, d0, m0 = port.PortExtractor(nf, sf, nl, ini, mn).extract(img, lap)
+        if rc == -2:
+            continue
+        assert rc == 0
+        rc2, k1, d1, m1 = ref.RefExtractor(nf, sf, nl, ini, mn).extract(img, lap)
+        assert rc2 == 0, (h, w, nl, sf, nf, ini, mn)
+        _same(k0, d0, m0, k1, d1, m1)
+        checked += 1
+    assert checked >= 30
