@@ -1207,8 +1207,14 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
             L.tabX = (int)tab.size();
             L.tabY = append_resize_tables(tab, S.w, S.h, L.w, L.h);
             L.fastResize = 1;
-            for (size_t g = (size_t)L.tabX; g < (size_t)L.tabY; g += 4)
+            L.prmtTaps = 1;
+            for (size_t g = (size_t)L.tabX; g < (size_t)L.tabY; g += 4) {
                 if (tab[g + 3].x - 4 * (tab[g].x >> 2) > 7 || tab[g + 3].x < tab[g].x) L.fastResize = 0;      // taps must lie in bytes 0..8
+                for (int k = 0; k < 3; k++) {
+                    const int o = tab[g + k].x - 4 * (tab[g].x >> 2);
+                    if (o < 0 || o + 1 > 7) L.prmtTaps = 0;                                                   // columns 0..2: both taps in bytes 0..7
+                }
+            }
             if (L.fastResize) {   // k_pyr_resize_t: the source window of every 128-column x 32-row CTA must fit its shared-memory tile
                 bool fits = true;
                 for (int g = 0; g * 128 < L.w; g++) {
@@ -1361,9 +1367,16 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
             static const bool tmaResize = getenv("ORBB_RESIZE_NO_TMA") == nullptr;      // (A/B switch; TMA staging measured 3 % faster)
             constexpr int rowsPerCtaLat = PR_ROWS_LATENCY * (PR_THREADS / 32);
             static const int pyrLatencyFrames = getenv("ORBB_PYR_LATENCY_FRAMES") ? atoi(getenv("ORBB_PYR_LATENCY_FRAMES")) : 4;
-            if (tmaResize && L.fastResize == 2 && nframes <= pyrLatencyFrames)
-                k_pyr_resize_t<PR_ROWS_LATENCY><<<dim3(grid.x, (L.h + rowsPerCtaLat - 1) / rowsPerCtaLat, nframes), PR_THREADS, 0, st>>>(h->dPlan, B, l);
-            else if (tmaResize && L.fastResize == 2) k_pyr_resize_t<PR_ROWS><<<dim3(grid.x, (L.h + rowsPerCta - 1) / rowsPerCta, nframes), PR_THREADS, 0, st>>>(h->dPlan, B, l);
+            static const bool noPrmt = getenv("ORBB_RESIZE_NO_PRMT") != nullptr;      // (A/B switch)
+            const bool prmt = L.prmtTaps && !noPrmt;
+            const dim3 gLat(grid.x, (L.h + rowsPerCtaLat - 1) / rowsPerCtaLat, nframes), gBat(grid.x, (L.h + rowsPerCta - 1) / rowsPerCta, nframes);
+            if (tmaResize && L.fastResize == 2 && nframes <= pyrLatencyFrames) {
+                if (prmt) k_pyr_resize_t<PR_ROWS_LATENCY, true><<<gLat, PR_THREADS, 0, st>>>(h->dPlan, B, l);
+                else k_pyr_resize_t<PR_ROWS_LATENCY, false><<<gLat, PR_THREADS, 0, st>>>(h->dPlan, B, l);
+            } else if (tmaResize && L.fastResize == 2) {
+                if (prmt) k_pyr_resize_t<PR_ROWS, true><<<gBat, PR_THREADS, 0, st>>>(h->dPlan, B, l);
+                else k_pyr_resize_t<PR_ROWS, false><<<gBat, PR_THREADS, 0, st>>>(h->dPlan, B, l);
+            }
             else k_pyr_resize_s<<<dim3(grid.x, (L.h + rowsPerCta - 1) / rowsPerCta, nframes), PR_THREADS, 0, st>>>(h->dPlan, B, l);
         } else k_pyr_resize<<<grid, 256, 0, st>>>(h->dPlan, B, l);
         h->launches++;

@@ -40,6 +40,7 @@ struct LevelPlan {
     int blurTileBase, blurTilesX, blurTilesY;
     int fsBase, fsTilesX, fsGroups;    // k_fast_score tiling: 32 word-columns x (4 strips of 8 rows) per CTA
     int fastResize;                    // 1: the 4 source taps of every column group fit 3 aligned words (k_pyr_resize_s)
+    int prmtTaps;                      // 1: the taps of the first three columns of every group lie in the first two of those words
 };
 
 // k_pyr_apron16 work decomposition of one level (16-byte chunks that contain apron bytes): `rows` apron rows above and below

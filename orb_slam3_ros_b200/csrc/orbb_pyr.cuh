@@ -48,12 +48,22 @@ __device__ __forceinline__ void hresize4(const unsigned* __restrict__ rp, const 
     }
 }
 
+// PRMT = the taps of the first three columns lie in the first two words for every thread of the level (LevelPlan::prmtTaps,
+// true at the reference's scale 1.2): one byte permute with a per-thread selector (held in ResizeCol::sh) picks both taps
+// instead of two mask-selects and a funnel shift.
+template <bool PRMT>
 __device__ __forceinline__ void hresize4s(const unsigned* rp, const ResizeCol (&c)[4], int (&h)[4]) {      // rp: shared memory
     const unsigned wa = rp[0], wb = rp[1], wc = rp[2];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const unsigned lo = (wa & ~c[k].m) | (wb & c[k].m), hi = (wb & ~c[k].m) | (wc & c[k].m);
-        h[k] = (int)(__dp2a_lo(c[k].coef, __funnelshift_r(lo, hi, c[k].sh), 0u) >> 4);
+        unsigned taps;
+        if (PRMT && k < 3) {
+            taps = __byte_perm(wa, wb, c[k].sh);
+        } else {
+            const unsigned lo = (wa & ~c[k].m) | (wb & c[k].m), hi = (wb & ~c[k].m) | (wc & c[k].m);
+            taps = __funnelshift_r(lo, hi, c[k].sh);
+        }
+        h[k] = (int)(__dp2a_lo(c[k].coef, taps, 0u) >> 4);
     }
 }
 
@@ -134,7 +144,7 @@ __device__ __forceinline__ unsigned vresize4(const int (&h0)[4], const int (&h1)
 
 // ROWS = destination rows per thread: PR_ROWS for batches; PR_ROWS_LATENCY for a call with a few frames, where a level is one
 // short dependent kernel on the critical path and more, shorter threads finish it sooner.
-template <int ROWS>
+template <int ROWS, bool PRMT>
 __global__ void __launch_bounds__(PR_THREADS, 12) k_pyr_resize_t(const Plan* __restrict__ P, Bufs B, int level) {
     __shared__ __align__(128) uint8_t sSrc[PR_SROWS * PR_SPITCH];
     __shared__ __align__(16) int4 sRow[(PR_THREADS / 32) * ROWS];      // per destination row of the CTA: {r0, r1, b0 << 16, b1 << 16}
@@ -177,9 +187,15 @@ __global__ void __launch_bounds__(PR_THREADS, 12) k_pyr_resize_t(const Plan* __r
         for (int k = 0; k < 4; k++) {
             const int o = sx[k] - 4 * wbase;
             c[k].coef = (unsigned)cf[k];
-            c[k].sh = 8u * (o & 3);
-            c[k].m = o >= 4 ? 0xffffffffu : 0u;
-            asm volatile("" : "+r"(c[k].sh), "+r"(c[k].m));
+            if (PRMT && k < 3) {
+                c[k].sh = (unsigned)o | ((unsigned)(o + 1) << 4);      // byte-permute selector: bytes o, o + 1 of {wa, wb}
+                c[k].m = 0u;
+                asm volatile("" : "+r"(c[k].sh));
+            } else {
+                c[k].sh = 8u * (o & 3);
+                c[k].m = o >= 4 ? 0xffffffffu : 0u;
+                asm volatile("" : "+r"(c[k].sh), "+r"(c[k].m));
+            }
         }
     }
     uint8_t* d = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + (size_t)dy0 * Lpitch + 4 * word;
@@ -194,7 +210,7 @@ __global__ void __launch_bounds__(PR_THREADS, 12) k_pyr_resize_t(const Plan* __r
     int s = cur.x;                                            // newest source row computed
     const uint8_t* sp = sSrc + (4 * wbase - xs0) + s * PR_SPITCH;
     int ha[4], hb[4];
-    hresize4s(reinterpret_cast<const unsigned*>(sp), c, ha);
+    hresize4s<PRMT>(reinterpret_cast<const unsigned*>(sp), c, ha);
     // emit every destination row whose lower source row is the newest one (`nw`; `pv` = the row before it)
 #define PR_EMIT(nw, pv)                                                                                         \
     while (cur.y == s) {                                                                                        \
@@ -206,10 +222,10 @@ __global__ void __launch_bounds__(PR_THREADS, 12) k_pyr_resize_t(const Plan* __r
     while (true) {
         PR_EMIT(ha, hb)
         sp += PR_SPITCH; s++;
-        hresize4s(reinterpret_cast<const unsigned*>(sp), c, hb);
+        hresize4s<PRMT>(reinterpret_cast<const unsigned*>(sp), c, hb);
         PR_EMIT(hb, ha)
         sp += PR_SPITCH; s++;
-        hresize4s(reinterpret_cast<const unsigned*>(sp), c, ha);
+        hresize4s<PRMT>(reinterpret_cast<const unsigned*>(sp), c, ha);
     }
 #undef PR_EMIT
 }
