@@ -34,6 +34,16 @@ std::shared_ptr<uchar> Mat::allocate(size_t n) {
 
 float fastAtan2(float y, float x) { return port_fast_atan2(y, x); }
 
+double norm(InputArray a_, InputArray b_, int) {        // cv::norm(.., NORM_L1) on CV_8U: exact integer sum of |a - b|, returned as double
+    const Mat a = a_.getMat(), b = b_.getMat();
+    long long s = 0;
+    for (int y = 0; y < a.rows; y++) {
+        const uchar *pa = a.ptr(y), *pb = b.ptr(y);
+        for (int x = 0; x < a.cols; x++) s += pa[x] > pb[x] ? pa[x] - pb[x] : pb[x] - pa[x];
+    }
+    return (double)s;
+}
+
 void resize(InputArray src_, OutputArray dst_, Size dsize, double, double, int) {
     const Mat src = src_.getMat();
     dst_.create(dsize, CV_8UC1);                   // a correctly sized ROI view stays where it is (ComputePyramid relies on it)

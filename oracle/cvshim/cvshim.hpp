@@ -82,7 +82,7 @@ public:
     Mat() : rows(0), cols(0), data(nullptr), step(0) {}
     Mat(int r, int c, int type) : Mat() { create(r, c, type); }
     Mat(Size sz, int type) : Mat() { create(sz.height, sz.width, type); }
-    Mat(int r, int c, int, void* ext, size_t step_ = 0) : rows(r), cols(c), data((uchar*)ext), step(step_ ? step_ : (size_t)c) {}
+    Mat(int r, int c, int type, void* ext, size_t step_ = 0) : rows(r), cols(c), data((uchar*)ext), step(step_ ? step_ : (size_t)c * (type == CV_32F ? 4 : 1)), type_(type) {}
 
     void create(int r, int c, int type) {                        // keeps the buffer (and a ROI view) when the size already fits
         if (data && r == rows && c == cols && type == type_) return;
@@ -97,8 +97,8 @@ public:
     size_t elemSize() const { return type_ == CV_32F ? 4 : 1; }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
     size_t step1() const { return step; }
-    template <typename T> T& at(int r, int c) { return *(T*)(data + (size_t)r * step + c); }
-    template <typename T> const T& at(int r, int c) const { return *(const T*)(data + (size_t)r * step + c); }
+    template <typename T> T& at(int r, int c) { return *(T*)(data + (size_t)r * step + (size_t)c * sizeof(T)); }
+    template <typename T> const T& at(int r, int c) const { return *(const T*)(data + (size_t)r * step + (size_t)c * sizeof(T)); }
     uchar* ptr(int r = 0) { return data + (size_t)r * step; }
     const uchar* ptr(int r = 0) const { return data + (size_t)r * step; }
     template <typename T> T* ptr(int r = 0) { return (T*)(data + (size_t)r * step); }
@@ -155,8 +155,10 @@ inline void Mat::copyTo(const _OutputArray& dst) const {
 
 enum { BORDER_REFLECT_101 = 4, BORDER_ISOLATED = 16 };
 enum { INTER_LINEAR = 1 };
+enum { NORM_L1 = 2 };
 
 float fastAtan2(float y, float x);
+double norm(InputArray a, InputArray b, int normType);      // NORM_L1 of two 8-bit matrices of one size (Frame.cc:930)
 void resize(InputArray src, OutputArray dst, Size dsize, double fx = 0, double fy = 0, int interpolation = INTER_LINEAR);
 void copyMakeBorder(InputArray src, OutputArray dst, int top, int bottom, int left, int right, int borderType);
 void GaussianBlur(InputArray src, OutputArray dst, Size ksize, double sigmaX, double sigmaY = 0, int borderType = BORDER_REFLECT_101);

@@ -12,9 +12,11 @@
 // EXTRACTOR rows: pinned to the reference itself -- oracle/_ref/liborbref.so is the reference's own
 // ORBextractor.cc compiled unmodified (`make ref`, OpenCV declarations from cvshim/, primitives from this
 // file) and tests/test_reference_source.py requires this port to reproduce it bit for bit.
-// MATCHER / STEREO / BoW rows: "parity unpinned" against the reference repository (ORBmatcher.cc, Frame.cc,
-// DBoW2 need Eigen/Sophus/boost and cannot be compiled here; no reference-held vectors); pinned to cv2 where
-// OpenCV defines the result.
+// STEREO / GRID / DISTANCE / BoW rows: pinned the same way -- the vendored DBoW2 is compiled unmodified, and the
+// definitions of Frame::ComputeStereoMatches, ComputeStereoFromRGBD, AssignFeaturesToGrid, PosInGrid,
+// GetFeaturesInArea, ORBmatcher::DescriptorDistance and ComputeThreeMaxima are cut out of Frame.cc / ORBmatcher.cc
+// at build time and compiled inside stand-in classes (ref_cut_tu.cpp).  The Search* loops around the scans and
+// ComputeDistinctiveDescriptors stay line-cited restatements; OpenCV-defined results are pinned to cv2.
 //
 // Build: g++ -O3 -march=native -ffp-contract=off -shared -fPIC (see oracle/Makefile).
 // -ffp-contract=off makes the un-fused float32 result the truth ("sin/cos and FMA").

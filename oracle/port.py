@@ -394,21 +394,11 @@ def undistort_points(xy, K4, dist, new_K4=None):
     return np.stack([(xx * ww).astype(np.float32), (yy * ww).astype(np.float32)], 1)
 
 
-def rotation_check(angle_a, angle_b):
-    """the rotation-consistency filter of the match scans (reference ORBmatcher.cc:236, :345-352, :405-423 and
-    ComputeThreeMaxima :2012-2053) for one set of matches -> (keep[n] bool, (ind1, ind2, ind3))"""
-    a = np.asarray(angle_a, np.float32)
-    b = np.asarray(angle_b, np.float32)
-    factor = np.float32(1.0) / np.float32(30)
-    rot = a - b
-    rot = np.where(rot < 0, rot + np.float32(360.0), rot).astype(np.float32)
-    x = (rot * factor).astype(np.float32)
-    bins = np.floor(x.astype(np.float64) + 0.5).astype(np.int64)      # round(): half away from zero, x >= 0 here
-    bins[bins == 30] = 0
-    hist = np.bincount(bins, minlength=30)
+def three_maxima(hist):
+    """ORBmatcher::ComputeThreeMaxima (reference ORBmatcher.cc:2012-2053) on the bin sizes of a rotation histogram"""
     max1 = max2 = max3 = 0
     ind1 = ind2 = ind3 = -1
-    for i in range(30):
+    for i in range(len(hist)):
         s = int(hist[i])
         if s > max1:
             max3, max2, max1 = max2, max1, s
@@ -422,6 +412,22 @@ def rotation_check(angle_a, angle_b):
         ind2 = ind3 = -1
     elif np.float32(max3) < np.float32(0.1) * np.float32(max1):
         ind3 = -1
+    return ind1, ind2, ind3
+
+
+def rotation_check(angle_a, angle_b):
+    """the rotation-consistency filter of the match scans (reference ORBmatcher.cc:236, :345-352, :405-423 and
+    ComputeThreeMaxima :2012-2053) for one set of matches -> (keep[n] bool, (ind1, ind2, ind3))"""
+    a = np.asarray(angle_a, np.float32)
+    b = np.asarray(angle_b, np.float32)
+    factor = np.float32(1.0) / np.float32(30)
+    rot = a - b
+    rot = np.where(rot < 0, rot + np.float32(360.0), rot).astype(np.float32)
+    x = (rot * factor).astype(np.float32)
+    bins = np.floor(x.astype(np.float64) + 0.5).astype(np.int64)      # round(): half away from zero, x >= 0 here
+    bins[bins == 30] = 0
+    hist = np.bincount(bins, minlength=30)
+    ind1, ind2, ind3 = three_maxima(hist)
     keep = (bins == ind1) | (bins == ind2) | (bins == ind3)
     return keep, (ind1, ind2, ind3)
 

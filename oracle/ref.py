@@ -1,6 +1,8 @@
 """ORACLE (test infrastructure, NOT product code): ctypes binding of oracle/_ref/liborbref.so -- the reference's OWN
 ORB_SLAM3::ORBextractor (orb_slam3/src/ORBextractor.cc) and its vendored DBoW2 vocabulary (orb_slam3/Thirdparty/DBoW2),
-compiled unmodified from /root/reference by `make -C oracle ref` against the OpenCV stand-in of oracle/cvshim/.
+compiled unmodified from /root/reference by `make -C oracle ref` against the OpenCV stand-in of oracle/cvshim/, plus the
+reference's own definitions of the stereo / matcher / grid functions of Frame.cc and ORBmatcher.cc (cut out at build time and
+compiled inside stand-in classes, oracle/ref_cut_tu.cpp).
 
 Only tests/, __graft_entry__ and bench.py's cpu_baseline / --impl reference legs may import this module.  The library is
 built in the development container (where /root/reference exists) and travels to the GPU box as a built file; when it
@@ -59,6 +61,17 @@ def lib():
         l.refbow_distance.argtypes = [C.c_void_p, C.c_void_p]
         l.refbow_transform.restype = C.c_int
         l.refbow_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
+        l.refcut_constants.argtypes = [C.POINTER(C.c_int)] * 3
+        l.refcut_descriptor_distance.restype = C.c_int
+        l.refcut_descriptor_distance.argtypes = [C.c_void_p, C.c_void_p]
+        l.refcut_three_maxima.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        l.refcut_stereo.restype = C.c_int
+        l.refcut_stereo.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float,
+                                    C.c_void_p, C.c_void_p]
+        l.refcut_rgbd.restype = C.c_int
+        l.refcut_rgbd.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_float, C.c_void_p, C.c_void_p]
+        l.refcut_search_area_best2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                               C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib = l
     return _lib
 
@@ -179,3 +192,65 @@ def descriptor_distance(a, b):
     a = np.ascontiguousarray(a, np.uint8)
     b = np.ascontiguousarray(b, np.uint8)
     return lib().refbow_distance(_ptr(a), _ptr(b))
+
+
+# ---- the reference's own matcher / stereo / grid functions (oracle/ref_cut_tu.cpp: definitions cut out of Frame.cc and ORBmatcher.cc
+# ---- at build time and compiled inside stand-in classes) ---------------------------------------------------------------------
+def matcher_constants():
+    """(TH_LOW, TH_HIGH, HISTO_LENGTH) as ORBmatcher.cc:35-37 defines them"""
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    lib().refcut_constants(C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value
+
+
+def matcher_descriptor_distance(a, b):
+    """ORBmatcher::DescriptorDistance (ORBmatcher.cc:2058-2074)"""
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    return lib().refcut_descriptor_distance(_ptr(a), _ptr(b))
+
+
+def three_maxima(counts):
+    """ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:2012-2053) on a histogram given by its bin sizes -> (ind1, ind2, ind3)"""
+    counts = np.ascontiguousarray(counts, np.int32)
+    out = np.zeros(3, np.int32)
+    lib().refcut_three_maxima(_ptr(counts), len(counts), _ptr(out))
+    return tuple(int(v) for v in out)
+
+
+def stereo(ext_l, ext_r, kps_l, desc_l, kps_r, desc_r, bf, b):
+    """Frame::ComputeStereoMatches (Frame.cc:811-981) on two RefExtractors that have just extracted the two eyes -> (mvuRight, mvDepth)"""
+    kl = np.ascontiguousarray(kps_l, KP_DTYPE)
+    kr = np.ascontiguousarray(kps_r, KP_DTYPE)
+    dl, dr = np.ascontiguousarray(desc_l, np.uint8), np.ascontiguousarray(desc_r, np.uint8)
+    ur, dp = np.zeros(len(kl), np.float32), np.zeros(len(kl), np.float32)
+    lib().refcut_stereo(ext_l._h, ext_r._h, _ptr(kl), _ptr(dl), len(kl), _ptr(kr), _ptr(dr), len(kr), bf, b, _ptr(ur), _ptr(dp))
+    return ur, dp
+
+
+def rgbd_stereo(kps_xy, x_undistorted, depth, bf):
+    """Frame::ComputeStereoFromRGBD (Frame.cc:984-1005) -> (mvuRight, mvDepth)"""
+    xy = np.ascontiguousarray(kps_xy, np.float32).reshape(-1, 2)
+    xu = np.ascontiguousarray(x_undistorted, np.float32)
+    depth = np.ascontiguousarray(depth, np.float32)
+    ur, dp = np.zeros(len(xy), np.float32), np.zeros(len(xy), np.float32)
+    lib().refcut_rgbd(_ptr(xy), _ptr(xu), len(xy), _ptr(depth), depth.shape[1], depth.shape[0], depth.strides[0] // 4, bf, _ptr(ur), _ptr(dp))
+    return ur, dp
+
+
+def search_area_best2(kps_xy, octaves, train, grid4, queries, qlev, qdesc, skip=None, u_right=None, init=256):
+    """Frame::AssignFeaturesToGrid + GetFeaturesInArea (reference text) followed by the best / second scan; same arguments and
+    result as oracle.port.search_area_best2"""
+    kps_xy = np.ascontiguousarray(kps_xy, np.float32).reshape(-1, 2)
+    octaves = np.ascontiguousarray(octaves, np.int32)
+    train = np.ascontiguousarray(train, np.uint8)
+    grid4 = np.ascontiguousarray(grid4, np.float32)
+    queries = np.ascontiguousarray(queries, np.float32).reshape(-1, 4)
+    qlev = np.ascontiguousarray(qlev, np.int32).reshape(-1, 2)
+    qdesc = np.ascontiguousarray(qdesc, np.uint8)
+    out = np.zeros((len(queries), 4), np.int32)
+    sk = None if skip is None else np.ascontiguousarray(skip, np.uint8)
+    ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+    lib().refcut_search_area_best2(_ptr(kps_xy), _ptr(octaves), _ptr(train), len(kps_xy), _ptr(grid4), _ptr(queries), _ptr(qlev), _ptr(qdesc),
+                                   len(queries), None if sk is None else _ptr(sk), None if ur is None else _ptr(ur), init, _ptr(out))
+    return out

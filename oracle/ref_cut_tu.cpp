@@ -1,0 +1,184 @@
+// ORACLE (test infrastructure, NOT product code): the reference's OWN text of the matcher / stereo / grid functions,
+// compiled inside minimal stand-in classes.
+//
+// Frame.cc and ORBmatcher.cc cannot be compiled as a whole in this image (their headers pull in Eigen, Sophus, boost,
+// Pangolin, g2o).  `make ref` therefore cuts the DEFINITIONS of the functions below out of those files at build time
+// (oracle/cut_reference.py -> oracle/_ref/cut/*.inc, a git-ignored build directory; no reference text lives in the repository)
+// and this file #includes them between declarations of `class Frame` / `class ORBmatcher` that carry exactly the members
+// those bodies touch, with the reference's names and types (Frame.h:44-45, :214-360; ORBmatcher.h:38-106).  The bodies are
+// compiled unmodified; OpenCV comes from cvshim/ as for the extractor.
+//
+//   ORBmatcher::TH_HIGH / TH_LOW / HISTO_LENGTH   ORBmatcher.cc:35-37
+//   ORBmatcher::DescriptorDistance                ORBmatcher.cc:2058-2074
+//   ORBmatcher::ComputeThreeMaxima                ORBmatcher.cc:2012-2053
+//   Frame::ComputeStereoMatches                   Frame.cc:811-981
+//   Frame::ComputeStereoFromRGBD                  Frame.cc:984-1005
+//   Frame::AssignFeaturesToGrid / PosInGrid       Frame.cc:385-416, :725-735
+//   Frame::GetFeaturesInArea                      Frame.cc:657-723
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "ORBextractor.h"
+
+#define FRAME_GRID_ROWS 48      // Frame.h:44
+#define FRAME_GRID_COLS 64      // Frame.h:45
+
+using namespace std;            // as Frame.cc / ORBmatcher.cc do
+
+namespace ORB_SLAM3 {
+
+class ORBmatcher {
+public:
+    static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
+    void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);
+    static const int TH_LOW;
+    static const int TH_HIGH;
+    static const int HISTO_LENGTH;
+};
+
+#include "cut/ORBmatcher_TH_HIGH.inc"
+#include "cut/ORBmatcher_TH_LOW.inc"
+#include "cut/ORBmatcher_HISTO_LENGTH.inc"
+#include "cut/ORBmatcher_ComputeThreeMaxima.inc"
+#include "cut/ORBmatcher_DescriptorDistance.inc"
+
+class Frame {
+public:
+    void ComputeStereoMatches();
+    void ComputeStereoFromRGBD(const cv::Mat& imDepth);
+    void AssignFeaturesToGrid();
+    bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);
+    vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1, const int maxLevel = -1,
+                                     const bool bRight = false) const;
+
+    ORBextractor *mpORBextractorLeft = nullptr, *mpORBextractorRight = nullptr;
+    float mbf = 0, mb = 0;
+    int N = 0;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysRight, mvKeysUn;
+    std::vector<float> mvuRight, mvDepth;
+    cv::Mat mDescriptors, mDescriptorsRight;
+    static float mfGridElementWidthInv, mfGridElementHeightInv;
+    std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+    std::vector<float> mvScaleFactors, mvInvScaleFactors;
+    static float mnMinX, mnMaxX, mnMinY, mnMaxY;
+    int Nleft = -1, Nright = -1;
+    std::vector<std::size_t> mGridRight[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+};
+float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
+
+}  // namespace ORB_SLAM3
+
+namespace ORB_SLAM3 {      // Frame.cc defines its functions at namespace scope
+#include "cut/Frame_AssignFeaturesToGrid.inc"
+#include "cut/Frame_PosInGrid.inc"
+#include "cut/Frame_GetFeaturesInArea.inc"
+#include "cut/Frame_ComputeStereoMatches.inc"
+#include "cut/Frame_ComputeStereoFromRGBD.inc"
+}  // namespace ORB_SLAM3
+
+namespace {
+struct PortKP { float x, y, size, angle, response; int octave; };
+
+std::vector<cv::KeyPoint> to_keypoints(const PortKP* k, int n) {
+    std::vector<cv::KeyPoint> v(n);
+    for (int i = 0; i < n; i++) v[i] = cv::KeyPoint(k[i].x, k[i].y, k[i].size, k[i].angle, k[i].response, k[i].octave);
+    return v;
+}
+cv::Mat to_descriptors(const uint8_t* d, int n) {
+    cv::Mat m(std::max(n, 1), 32, CV_8U);
+    if (n) memcpy(m.data, d, (size_t)n * 32);
+    return m;
+}
+}  // namespace
+
+extern "C" {
+
+int refcut_constants(int* th_low, int* th_high, int* histo_length) {
+    *th_low = ORB_SLAM3::ORBmatcher::TH_LOW; *th_high = ORB_SLAM3::ORBmatcher::TH_HIGH; *histo_length = ORB_SLAM3::ORBmatcher::HISTO_LENGTH;
+    return 0;
+}
+
+int refcut_descriptor_distance(const uint8_t* a, const uint8_t* b) {
+    return ORB_SLAM3::ORBmatcher::DescriptorDistance(to_descriptors(a, 1), to_descriptors(b, 1));
+}
+
+// histo: counts per bin -> lists of that length (the function only looks at histo[i].size())
+void refcut_three_maxima(const int32_t* counts, int L, int32_t* ind3) {
+    std::vector<std::vector<int>> histo(L);
+    for (int i = 0; i < L; i++) histo[i].resize(counts[i]);
+    int i1 = -1, i2 = -1, i3 = -1;                                         // ORBmatcher.cc:347-349
+    ORB_SLAM3::ORBmatcher().ComputeThreeMaxima(histo.data(), L, i1, i2, i3);
+    ind3[0] = i1; ind3[1] = i2; ind3[2] = i3;
+}
+
+// Frame::ComputeStereoMatches on the key points / descriptors of the two eyes; extL / extR = ref_create handles that have just
+// extracted the two images (their mvImagePyramid is what the function reads).  Outputs mvuRight / mvDepth (nL floats each).
+int refcut_stereo(void* extL, void* extR, const PortKP* kL, const uint8_t* dL, int nL, const PortKP* kR, const uint8_t* dR, int nR, float bf,
+                  float b, float* uRight, float* depth) {
+    ORB_SLAM3::Frame F;
+    F.mpORBextractorLeft = (ORB_SLAM3::ORBextractor*)extL;
+    F.mpORBextractorRight = (ORB_SLAM3::ORBextractor*)extR;
+    F.mvScaleFactors = F.mpORBextractorLeft->GetScaleFactors();            // Frame.cc:110-116
+    F.mvInvScaleFactors = F.mpORBextractorLeft->GetInverseScaleFactors();
+    F.mvKeys = to_keypoints(kL, nL);
+    F.mvKeysRight = to_keypoints(kR, nR);
+    F.mDescriptors = to_descriptors(dL, nL);
+    F.mDescriptorsRight = to_descriptors(dR, nR);
+    F.N = nL; F.mbf = bf; F.mb = b;
+    F.ComputeStereoMatches();
+    for (int i = 0; i < nL; i++) { uRight[i] = F.mvuRight[i]; depth[i] = F.mvDepth[i]; }
+    return 0;
+}
+
+// Frame::ComputeStereoFromRGBD: keys (x, y), undistorted x, float depth map
+int refcut_rgbd(const float* xy, const float* xUn, int n, const float* depthMap, int w, int h, size_t strideFloats, float bf, float* uRight,
+                float* depth) {
+    ORB_SLAM3::Frame F;
+    F.N = n; F.mbf = bf;
+    F.mvKeys.resize(n); F.mvKeysUn.resize(n);
+    for (int i = 0; i < n; i++) { F.mvKeys[i].pt.x = xy[2 * i]; F.mvKeys[i].pt.y = xy[2 * i + 1]; F.mvKeysUn[i].pt.x = xUn[i]; F.mvKeysUn[i].pt.y = xy[2 * i + 1]; }
+    cv::Mat im(h, w, CV_32F, const_cast<float*>(depthMap), strideFloats * sizeof(float));
+    F.ComputeStereoFromRGBD(im);
+    for (int i = 0; i < n; i++) { uRight[i] = F.mvuRight[i]; depth[i] = F.mvDepth[i]; }
+    return 0;
+}
+
+// AssignFeaturesToGrid + GetFeaturesInArea for every query, followed by the best / second scan of
+// ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&) (ORBmatcher.cc:77-120, restated here: that function needs MapPoint)
+// with the reference's DescriptorDistance.  Same arguments and output as port_search_area_best2.
+void refcut_search_area_best2(const float* kps, const int32_t* oct, const uint8_t* train, int n, const float* grid4, const float* queries,
+                              const int32_t* qlev, const uint8_t* qdesc, int nq, const uint8_t* skip, const float* uRight, int init,
+                              int32_t* out4) {
+    using ORB_SLAM3::Frame;
+    Frame* F = new Frame();                                                // (the two grids make the object large)
+    Frame::mnMinX = grid4[0]; Frame::mnMinY = grid4[1]; Frame::mfGridElementWidthInv = grid4[2]; Frame::mfGridElementHeightInv = grid4[3];
+    F->N = n; F->Nleft = -1;
+    F->mvKeysUn.resize(n);
+    for (int i = 0; i < n; i++) { F->mvKeysUn[i].pt.x = kps[2 * i]; F->mvKeysUn[i].pt.y = kps[2 * i + 1]; F->mvKeysUn[i].octave = oct[i]; }
+    F->AssignFeaturesToGrid();
+    const cv::Mat tr = to_descriptors(train, n);
+    for (int q = 0; q < nq; q++) {
+        const float x = queries[4 * q], y = queries[4 * q + 1], r = queries[4 * q + 2], xr = queries[4 * q + 3];
+        const std::vector<size_t> idxs = F->GetFeaturesInArea(x, y, r, qlev[2 * q], qlev[2 * q + 1]);
+        const cv::Mat dq = to_descriptors(qdesc + (size_t)q * 32, 1);
+        int bestDist = init, bestDist2 = init, bestIdx = -1, bestIdx2 = -1;
+        for (size_t idx : idxs) {
+            if (skip && skip[idx]) continue;
+            if (uRight && uRight[idx] > 0) {
+                const float er = std::fabs(xr - uRight[idx]);
+                if (er > r) continue;
+            }
+            const int dist = ORB_SLAM3::ORBmatcher::DescriptorDistance(dq, tr.row((int)idx));
+            if (dist < bestDist) { bestDist2 = bestDist; bestIdx2 = bestIdx; bestDist = dist; bestIdx = (int)idx; }
+            else if (dist < bestDist2) { bestDist2 = dist; bestIdx2 = (int)idx; }
+        }
+        out4[4 * q] = bestDist; out4[4 * q + 1] = bestIdx; out4[4 * q + 2] = bestDist2; out4[4 * q + 3] = bestIdx2;
+    }
+    delete F;
+}
+
+}  // extern "C"

@@ -146,3 +146,98 @@ def test_random_settings_sweep_port_equals_reference_source():
         _same(k0, d0, m0, k1, d1, m1)
         checked += 1
     assert checked >= 30
+
+
+# ---- matcher / stereo / grid rows: the reference's own definitions, cut out of Frame.cc / ORBmatcher.cc at build time and compiled
+# ---- inside stand-in classes (oracle/ref_cut_tu.cpp) ------------------------------------------------------------------------------
+def test_matcher_constants_and_descriptor_distance_are_the_reference_ones():
+    assert ref.matcher_constants() == (50, 100, 30)                       # TH_LOW, TH_HIGH, HISTO_LENGTH (ORBmatcher.cc:35-37)
+    rng = np.random.default_rng(4)
+    a, b = rng.integers(0, 256, (300, 32), dtype=np.uint8), rng.integers(0, 256, (300, 32), dtype=np.uint8)
+    b[:4] = a[:4]
+    a[4], b[4] = 0, 255
+    for x, y in zip(a, b):
+        assert ref.matcher_descriptor_distance(x, y) == port.hamming(x, y) == int(np.unpackbits(x ^ y).sum())
+
+
+@pytest.mark.parametrize("shape,nf,dmax,bf,b", [((376, 1241), 2000, 60, 386.1448, 0.53716), ((480, 752), 1200, 40, 47.9, 0.11),
+                                                ((240, 400), 600, 30, 380.0, 0.5)])
+def test_stereo_port_equals_reference_compute_stereo_matches(shape, nf, dmax, bf, b):
+    """Frame::ComputeStereoMatches (Frame.cc:811-981): row table, descriptor search, 11x11 SAD sliding window on the two extractors'
+    pyramids, parabola refinement, median cut -- the reference's text on the reference extractor's pyramids vs the port"""
+    left, right = synth.stereo_pair(shape[0], shape[1], nf % 7, dmax=dmax)
+    pl, pr = port.PortExtractor(nf, 1.2, 8), port.PortExtractor(nf, 1.2, 8)
+    _, kl, dl, _ = pl.extract(left)
+    _, kr, dr, _ = pr.extract(right)
+    rl, rr = ref.RefExtractor(nf, 1.2, 8), ref.RefExtractor(nf, 1.2, 8)
+    assert np.array_equal(rl.extract(left)[1], kl) and np.array_equal(rr.extract(right)[1], kr)
+    ur, dp, _, _, kept = port.stereo(pl, pr, kl, dl, kr, dr, np.float32(bf), np.float32(b))
+    ur2, dp2 = ref.stereo(rl, rr, kl, dl, kr, dr, bf, b)
+    assert kept == int((ur2 >= 0).sum()) and kept > 0.2 * len(kl)
+    assert np.array_equal(ur.view(np.uint32), ur2.view(np.uint32)) and np.array_equal(dp.view(np.uint32), dp2.view(np.uint32))
+
+
+def test_rotation_histogram_maxima_equal_reference_compute_three_maxima():
+    rng = np.random.default_rng(6)
+    cases = [rng.integers(0, 40, 30) for _ in range(40)]
+    cases += [np.zeros(30, np.int64), np.full(30, 7), np.eye(30, dtype=np.int64)[3] * 9, np.r_[np.full(15, 10), np.zeros(15, np.int64)],
+              np.r_[100, 9, 10, np.zeros(27, np.int64)], np.r_[100, 10, 9, 11, np.zeros(26, np.int64)]]       # ties, 10 % rule edges
+    for counts in cases:
+        counts = np.asarray(counts, np.int64)
+        assert ref.three_maxima(counts) == port.three_maxima(counts), counts.tolist()
+    # through the whole filter: the bins of real angle differences (round(rot / 30), ORBmatcher.cc:236,:345-352) and their maxima
+    for seed in range(5):
+        r = np.random.default_rng(seed)
+        a, b = r.uniform(0, 360, 500).astype(np.float32), r.uniform(0, 360, 500).astype(np.float32)
+        b[:300] = (a[:300] + r.normal(25, 6, 300)).astype(np.float32) % np.float32(360)
+        keep, inds = port.rotation_check(a, b)
+        rot = np.where(a - b < 0, a - b + np.float32(360), a - b).astype(np.float32)
+        bins = np.floor((rot * (np.float32(1) / np.float32(30))).astype(np.float64) + 0.5).astype(np.int64) % 30
+        assert ref.three_maxima(np.bincount(bins, minlength=30)) == tuple(int(v) for v in inds)
+
+
+def test_rgbd_port_equals_reference_compute_stereo_from_rgbd():
+    rng = np.random.default_rng(12)
+    h, w, n = 480, 640, 900
+    depth = (rng.integers(0, 40000, (h, w)).astype(np.float32) * (np.float32(1) / np.float32(5000))).astype(np.float32)
+    depth[rng.random((h, w)) < 0.2] = 0
+    xy = np.stack([rng.uniform(16, w - 17, n), rng.uniform(16, h - 17, n)], 1).astype(np.float32)
+    K4 = (517.306408, 516.469215, 318.643040, 255.313989)
+    for dist in ([0.262383, -0.953104, -0.005358, 0.002628, 1.163314], [0.0, 0.0, 0.0, 0.0]):
+        ur, dp = port.rgbd_stereo(xy, depth, K4, dist, np.float32(40.0))
+        xu = port.undistort_points(xy, K4, dist)[:, 0] if dist[0] else xy[:, 0]
+        ur2, dp2 = ref.rgbd_stereo(xy, xu, depth, 40.0)
+        assert np.array_equal(dp, dp2) and np.array_equal(ur.view(np.uint32), ur2.view(np.uint32))
+
+
+@pytest.mark.parametrize("with_stereo", [False, True])
+def test_search_area_port_equals_reference_grid_functions(with_stereo):
+    """Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea (reference text) + best/second scan vs the port, on projected points
+    near key points, outside the image and exactly on cell borders"""
+    h, w = 480, 752
+    _, k, d, _ = port.PortExtractor(1000, 1.2, 8).extract(synth.frame(h, w, 3))
+    n = len(k)
+    rng = np.random.default_rng(5)
+    kps_xy = np.stack([k["x"], k["y"]], 1)
+    grid4 = np.float32([0.0, 0.0, np.float32(64) / np.float32(w), np.float32(48) / np.float32(h)])      # Frame.cc:251-252
+    nq = 1200
+    src = rng.integers(0, n, nq)
+    qx = k["x"][src] + rng.normal(0, 3, nq).astype(np.float32)
+    qy = k["y"][src] + rng.normal(0, 3, nq).astype(np.float32)
+    qx[::50] = rng.choice([-40.0, w + 60.0, 0.0, w / 64 * 7], len(qx[::50])).astype(np.float32)
+    qy[::70] = rng.choice([-30.0, h + 50.0, 0.0, h / 48 * 5], len(qy[::70])).astype(np.float32)
+    r = (rng.choice([2.5, 4.0], nq) * rng.choice([1.0, 1.2, 1.44, 3.0, 15.0], nq)).astype(np.float32)
+    lvl = k["octave"][src]
+    qlev = np.stack([lvl - 1, lvl], 1).astype(np.int32)
+    qlev[::9] = (-1, -1)
+    qlev[5::9, 1] = -1
+    qdesc = d[src].copy()
+    qdesc[:, :3] ^= rng.integers(0, 256, (nq, 3), dtype=np.uint8)
+    skip = (rng.random(n) < 0.2).astype(np.uint8)
+    u_right = np.where(rng.random(n) < 0.5, k["x"] - rng.uniform(1, 40, n), -1).astype(np.float32) if with_stereo else None
+    queries = np.stack([qx, qy, r, qx - rng.uniform(0, 45, nq).astype(np.float32)], 1).astype(np.float32)
+    for init in (256, 100):
+        want = ref.search_area_best2(kps_xy, k["octave"], d, grid4, queries, qlev, qdesc, skip, u_right, init)
+        got = port.search_area_best2(kps_xy, k["octave"], d, grid4, queries, qlev, qdesc, skip, u_right, init)
+        assert np.array_equal(want, got), init
+    assert (want[:, 1] >= 0).mean() > 0.5
