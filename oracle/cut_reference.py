@@ -22,6 +22,7 @@ PIECES = [
     ("Frame_AssignFeaturesToGrid", "src/Frame.cc", r"^void Frame::AssignFeaturesToGrid\(\)", "function"),
     ("Frame_PosInGrid", "src/Frame.cc", r"^bool Frame::PosInGrid\(", "function"),
     ("Frame_GetFeaturesInArea", "src/Frame.cc", r"^vector<size_t> Frame::GetFeaturesInArea\(", "function"),
+    ("MapPoint_ComputeDistinctiveDescriptors", "src/MapPoint.cc", r"^void MapPoint::ComputeDistinctiveDescriptors\(\)", "function"),
 ]
 
 

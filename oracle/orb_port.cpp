@@ -14,9 +14,9 @@
 // file) and tests/test_reference_source.py requires this port to reproduce it bit for bit.
 // STEREO / GRID / DISTANCE / BoW rows: pinned the same way -- the vendored DBoW2 is compiled unmodified, and the
 // definitions of Frame::ComputeStereoMatches, ComputeStereoFromRGBD, AssignFeaturesToGrid, PosInGrid,
-// GetFeaturesInArea, ORBmatcher::DescriptorDistance and ComputeThreeMaxima are cut out of Frame.cc / ORBmatcher.cc
-// at build time and compiled inside stand-in classes (ref_cut_tu.cpp).  The Search* loops around the scans and
-// ComputeDistinctiveDescriptors stay line-cited restatements; OpenCV-defined results are pinned to cv2.
+// GetFeaturesInArea, ORBmatcher::DescriptorDistance, ComputeThreeMaxima and MapPoint::ComputeDistinctiveDescriptors
+// are cut out of Frame.cc / ORBmatcher.cc / MapPoint.cc at build time and compiled inside stand-in classes
+// (ref_cut_tu.cpp).  The Search* loops around the scans stay line-cited restatements; OpenCV-defined results are pinned to cv2.
 //
 // Build: g++ -O3 -march=native -ffp-contract=off -shared -fPIC (see oracle/Makefile).
 // -ffp-contract=off makes the un-fused float32 result the truth ("sin/cos and FMA").

@@ -72,6 +72,8 @@ def lib():
         l.refcut_rgbd.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_float, C.c_void_p, C.c_void_p]
         l.refcut_search_area_best2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                                C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        l.refcut_distinctive.restype = C.c_int
+        l.refcut_distinctive.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib = l
     return _lib
 
@@ -254,3 +256,15 @@ def search_area_best2(kps_xy, octaves, train, grid4, queries, qlev, qdesc, skip=
     lib().refcut_search_area_best2(_ptr(kps_xy), _ptr(octaves), _ptr(train), len(kps_xy), _ptr(grid4), _ptr(queries), _ptr(qlev), _ptr(qdesc),
                                    len(queries), None if sk is None else _ptr(sk), None if ur is None else _ptr(ur), init, _ptr(out))
     return out
+
+
+def distinctive(kf_desc, left_right, bad=None):
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:329-403) for one map point: kf_desc [nkf, 2, 32] = two descriptor rows per
+    observing key frame, left_right [nkf, 2] = the observation's (left, right) row indices (0 / 1, -1 = none), bad [nkf] = key frames
+    flagged bad -> the chosen descriptor [32] or None (early return)"""
+    kf_desc = np.ascontiguousarray(kf_desc, np.uint8).reshape(-1, 2, 32)
+    lr = np.ascontiguousarray(left_right, np.int32).reshape(-1, 2)
+    b = None if bad is None else np.ascontiguousarray(bad, np.uint8)
+    out = np.zeros(32, np.uint8)
+    ok = lib().refcut_distinctive(_ptr(kf_desc), _ptr(lr), None if b is None else _ptr(b), len(kf_desc), _ptr(out))
+    return out if ok else None

@@ -15,11 +15,15 @@
 //   Frame::ComputeStereoFromRGBD                  Frame.cc:984-1005
 //   Frame::AssignFeaturesToGrid / PosInGrid       Frame.cc:385-416, :725-735
 //   Frame::GetFeaturesInArea                      Frame.cc:657-723
+//   MapPoint::ComputeDistinctiveDescriptors       MapPoint.cc:329-403
 #include <algorithm>
 #include <climits>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <vector>
 
 #include "ORBextractor.h"
@@ -78,6 +82,24 @@ namespace ORB_SLAM3 {      // Frame.cc defines its functions at namespace scope
 #include "cut/Frame_GetFeaturesInArea.inc"
 #include "cut/Frame_ComputeStereoMatches.inc"
 #include "cut/Frame_ComputeStereoFromRGBD.inc"
+}  // namespace ORB_SLAM3
+
+namespace ORB_SLAM3 {
+class KeyFrame {                // KeyFrame.h: the two members the function reads
+public:
+    bool isBad() { return mbBad; }
+    cv::Mat mDescriptors;
+    bool mbBad = false;
+};
+class MapPoint {                // MapPoint.h:175-207
+public:
+    void ComputeDistinctiveDescriptors();
+    std::map<KeyFrame*, std::tuple<int, int>> mObservations;
+    cv::Mat mDescriptor;
+    bool mbBad = false;
+    std::mutex mMutexFeatures;
+};
+#include "cut/MapPoint_ComputeDistinctiveDescriptors.inc"
 }  // namespace ORB_SLAM3
 
 namespace {
@@ -179,6 +201,24 @@ void refcut_search_area_best2(const float* kps, const int32_t* oct, const uint8_
         out4[4 * q] = bestDist; out4[4 * q + 1] = bestIdx; out4[4 * q + 2] = bestDist2; out4[4 * q + 3] = bestIdx2;
     }
     delete F;
+}
+
+// MapPoint::ComputeDistinctiveDescriptors for one map point observed in nkf key frames (left and right index each, -1 = none;
+// desc = the key frames' descriptor matrices, 2 rows per key frame).  The observations map is ordered by KeyFrame address: the
+// stand-in key frames live in one array, so that order is the index order.  -> 1 and out[32] = mDescriptor, or 0 when the
+// function returned early (no usable observation).
+int refcut_distinctive(const uint8_t* desc, const int32_t* leftRight, const uint8_t* bad, int nkf, uint8_t* out) {
+    std::vector<ORB_SLAM3::KeyFrame> kfs(nkf);
+    ORB_SLAM3::MapPoint mp;
+    for (int i = 0; i < nkf; i++) {
+        kfs[i].mDescriptors = to_descriptors(desc + (size_t)i * 64, 2);
+        kfs[i].mbBad = bad && bad[i];
+        mp.mObservations[&kfs[i]] = std::make_tuple((int)leftRight[2 * i], (int)leftRight[2 * i + 1]);
+    }
+    mp.ComputeDistinctiveDescriptors();
+    if (mp.mDescriptor.empty()) return 0;
+    memcpy(out, mp.mDescriptor.data, 32);
+    return 1;
 }
 
 }  // extern "C"

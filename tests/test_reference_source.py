@@ -241,3 +241,27 @@ def test_search_area_port_equals_reference_grid_functions(with_stereo):
         got = port.search_area_best2(kps_xy, k["octave"], d, grid4, queries, qlev, qdesc, skip, u_right, init)
         assert np.array_equal(want, got), init
     assert (want[:, 1] >= 0).mean() > 0.5
+
+
+def test_distinctive_port_equals_reference_compute_distinctive_descriptors():
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:329-403, reference text): observations with a left and/or right index,
+    bad key frames skipped, least median distance incl. the self distance, first minimum on ties"""
+    rng = np.random.default_rng(21)
+    for case in range(60):
+        nkf = int(rng.integers(1, 40))
+        base = rng.integers(0, 256, 32, dtype=np.uint8)
+        kf_desc = np.repeat(base[None, None, :], nkf * 2, 0).reshape(nkf, 2, 32).copy()
+        flips = rng.integers(0, 256, (nkf, 2, 32), dtype=np.uint8) & rng.integers(0, 256, (nkf, 2, 32), dtype=np.uint8) & rng.integers(0, 256, (nkf, 2, 32), dtype=np.uint8)
+        kf_desc ^= flips                                                   # observations of one point: close to a common descriptor
+        if case % 5 == 0:
+            kf_desc[:, 0] = kf_desc[0, 0]                                  # many identical descriptors: ties
+        lr = np.stack([rng.choice([0, -1], nkf, p=[0.8, 0.2]), rng.choice([1, -1], nkf, p=[0.3, 0.7])], 1).astype(np.int32)
+        bad = (rng.random(nkf) < 0.15).astype(np.uint8)
+        rows = [kf_desc[i, j] for i in range(nkf) if not bad[i] for j in (0, 1) if lr[i, j] != -1]      # order of vDescriptors (:347-361)
+        got = ref.distinctive(kf_desc, lr, bad)
+        if not rows:
+            assert got is None
+            continue
+        group = np.stack(rows)
+        best = port.distinctive(group, np.int32([0, len(group)]))[0]
+        assert np.array_equal(got, group[best]), case
