@@ -22,6 +22,10 @@ PIECES = [
     ("Frame_AssignFeaturesToGrid", "src/Frame.cc", r"^void Frame::AssignFeaturesToGrid\(\)", "function"),
     ("Frame_PosInGrid", "src/Frame.cc", r"^bool Frame::PosInGrid\(", "function"),
     ("Frame_GetFeaturesInArea", "src/Frame.cc", r"^vector<size_t> Frame::GetFeaturesInArea\(", "function"),
+    ("ORBmatcher_ctor", "src/ORBmatcher.cc", r"^\s*ORBmatcher::ORBmatcher\(float nnratio, bool checkOri\)", "function"),
+    ("ORBmatcher_RadiusByViewingCos", "src/ORBmatcher.cc", r"^\s*float ORBmatcher::RadiusByViewingCos\(", "function"),
+    ("ORBmatcher_SearchByProjection_local", "src/ORBmatcher.cc",
+     r"^\s*int ORBmatcher::SearchByProjection\(Frame &F, const vector<MapPoint\*> &vpMapPoints, const float th, const bool bFarPoints", "function"),
     ("MapPoint_ComputeDistinctiveDescriptors", "src/MapPoint.cc", r"^void MapPoint::ComputeDistinctiveDescriptors\(\)", "function"),
 ]
 

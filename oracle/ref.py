@@ -72,6 +72,9 @@ def lib():
         l.refcut_rgbd.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_float, C.c_void_p, C.c_void_p]
         l.refcut_search_area_best2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                                C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        l.refcut_search_by_projection.restype = C.c_int
+        l.refcut_search_by_projection.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]
         l.refcut_distinctive.restype = C.c_int
         l.refcut_distinctive.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib = l
@@ -268,3 +271,27 @@ def distinctive(kf_desc, left_right, bad=None):
     out = np.zeros(32, np.uint8)
     ok = lib().refcut_distinctive(_ptr(kf_desc), _ptr(lr), None if b is None else _ptr(b), len(kf_desc), _ptr(out))
     return out if ok else None
+
+
+def search_by_projection(kps_xy, octaves, train, grid4, scale_factors, proj, level, mp_desc, in_view=None, u_right=None, has_point=None,
+                         nnratio=0.8, th=1.0):
+    """ORBmatcher(nnratio).SearchByProjection(F, vpMapPoints, th) (ORBmatcher.cc:43-213, reference text) on a frame with Nleft == -1:
+    proj [nmp, 4] = {mTrackProjX, mTrackProjY, mTrackProjXR, mTrackViewCos}, level = mnTrackScaleLevel, has_point = key points that
+    already hold a map point with observations -> (nmatches, match_of[n]: map point assigned to each key point by this call, -1 none)"""
+    kps_xy = np.ascontiguousarray(kps_xy, np.float32).reshape(-1, 2)
+    octaves = np.ascontiguousarray(octaves, np.int32)
+    train = np.ascontiguousarray(train, np.uint8)
+    grid4 = np.ascontiguousarray(grid4, np.float32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    proj = np.ascontiguousarray(proj, np.float32).reshape(-1, 4)
+    level = np.ascontiguousarray(level, np.int32)
+    mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+    n, nmp = len(kps_xy), len(proj)
+    iv = np.ones(nmp, np.uint8) if in_view is None else np.ascontiguousarray(in_view, np.uint8)
+    ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+    hp = None if has_point is None else np.ascontiguousarray(has_point, np.uint8)
+    match_of = np.full(n, -1, np.int32)
+    nm = lib().refcut_search_by_projection(_ptr(kps_xy), _ptr(octaves), _ptr(train), n, _ptr(grid4), None if ur is None else _ptr(ur),
+                                           None if hp is None else _ptr(hp), _ptr(sf), len(sf), _ptr(proj), _ptr(level), _ptr(mp_desc), _ptr(iv),
+                                           nmp, nnratio, th, _ptr(match_of))
+    return nm, match_of

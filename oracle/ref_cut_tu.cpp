@@ -16,6 +16,8 @@
 //   Frame::AssignFeaturesToGrid / PosInGrid       Frame.cc:385-416, :725-735
 //   Frame::GetFeaturesInArea                      Frame.cc:657-723
 //   MapPoint::ComputeDistinctiveDescriptors       MapPoint.cc:329-403
+//   ORBmatcher::ORBmatcher, RadiusByViewingCos    ORBmatcher.cc:39-41, :215-221
+//   ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints)   ORBmatcher.cc:43-213
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -35,22 +37,50 @@ using namespace std;            // as Frame.cc / ORBmatcher.cc do
 
 namespace ORB_SLAM3 {
 
-class ORBmatcher {
+class Frame;
+class KeyFrame;
+class MapPoint;
+
+class ORBmatcher {              // ORBmatcher.h:38-106
 public:
+    ORBmatcher(float nnratio = 0.6, bool checkOri = true);
     static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
-    void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);
+    int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3, const bool bFarPoints = false,
+                           const float thFarPoints = 50.0f);
     static const int TH_LOW;
     static const int TH_HIGH;
     static const int HISTO_LENGTH;
+    float RadiusByViewingCos(const float& viewCos);
+    void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);
+    float mfNNratio;
+    bool mbCheckOrientation;
 };
 
-#include "cut/ORBmatcher_TH_HIGH.inc"
-#include "cut/ORBmatcher_TH_LOW.inc"
-#include "cut/ORBmatcher_HISTO_LENGTH.inc"
-#include "cut/ORBmatcher_ComputeThreeMaxima.inc"
-#include "cut/ORBmatcher_DescriptorDistance.inc"
+class KeyFrame {                // KeyFrame.h: the members ComputeDistinctiveDescriptors reads
+public:
+    bool isBad() { return mbBad; }
+    cv::Mat mDescriptors;
+    bool mbBad = false;
+};
 
-class Frame {
+class MapPoint {                // MapPoint.h:114-207: the members the cut functions touch; the three accessors are plain stand-ins
+public:
+    void ComputeDistinctiveDescriptors();
+    int Observations() { return nObs; }
+    bool isBad() { return mbBad; }
+    cv::Mat GetDescriptor() { return mDescriptor.clone(); }
+    float mTrackProjX = 0, mTrackProjY = 0, mTrackDepth = 0, mTrackDepthR = 0, mTrackProjXR = 0, mTrackProjYR = 0;
+    bool mbTrackInView = false, mbTrackInViewR = false;
+    int mnTrackScaleLevel = 0, mnTrackScaleLevelR = -1;
+    float mTrackViewCos = 1, mTrackViewCosR = 1;
+    std::map<KeyFrame*, std::tuple<int, int>> mObservations;
+    cv::Mat mDescriptor;
+    int nObs = 0;
+    bool mbBad = false;
+    std::mutex mMutexFeatures;
+};
+
+class Frame {                   // Frame.h:214-360
 public:
     void ComputeStereoMatches();
     void ComputeStereoFromRGBD(const cv::Mat& imDepth);
@@ -63,6 +93,7 @@ public:
     float mbf = 0, mb = 0;
     int N = 0;
     std::vector<cv::KeyPoint> mvKeys, mvKeysRight, mvKeysUn;
+    std::vector<MapPoint*> mvpMapPoints;
     std::vector<float> mvuRight, mvDepth;
     cv::Mat mDescriptors, mDescriptorsRight;
     static float mfGridElementWidthInv, mfGridElementHeightInv;
@@ -70,36 +101,27 @@ public:
     std::vector<float> mvScaleFactors, mvInvScaleFactors;
     static float mnMinX, mnMaxX, mnMinY, mnMaxY;
     int Nleft = -1, Nright = -1;
+    std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;
     std::vector<std::size_t> mGridRight[FRAME_GRID_COLS][FRAME_GRID_ROWS];
 };
 float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
 
-}  // namespace ORB_SLAM3
-
-namespace ORB_SLAM3 {      // Frame.cc defines its functions at namespace scope
+// ---- the reference's own definitions (build-time cuts) ----
+#include "cut/ORBmatcher_TH_HIGH.inc"
+#include "cut/ORBmatcher_TH_LOW.inc"
+#include "cut/ORBmatcher_HISTO_LENGTH.inc"
+#include "cut/ORBmatcher_ctor.inc"
+#include "cut/ORBmatcher_SearchByProjection_local.inc"
+#include "cut/ORBmatcher_RadiusByViewingCos.inc"
+#include "cut/ORBmatcher_ComputeThreeMaxima.inc"
+#include "cut/ORBmatcher_DescriptorDistance.inc"
 #include "cut/Frame_AssignFeaturesToGrid.inc"
 #include "cut/Frame_PosInGrid.inc"
 #include "cut/Frame_GetFeaturesInArea.inc"
 #include "cut/Frame_ComputeStereoMatches.inc"
 #include "cut/Frame_ComputeStereoFromRGBD.inc"
-}  // namespace ORB_SLAM3
-
-namespace ORB_SLAM3 {
-class KeyFrame {                // KeyFrame.h: the two members the function reads
-public:
-    bool isBad() { return mbBad; }
-    cv::Mat mDescriptors;
-    bool mbBad = false;
-};
-class MapPoint {                // MapPoint.h:175-207
-public:
-    void ComputeDistinctiveDescriptors();
-    std::map<KeyFrame*, std::tuple<int, int>> mObservations;
-    cv::Mat mDescriptor;
-    bool mbBad = false;
-    std::mutex mMutexFeatures;
-};
 #include "cut/MapPoint_ComputeDistinctiveDescriptors.inc"
+
 }  // namespace ORB_SLAM3
 
 namespace {
@@ -219,6 +241,50 @@ int refcut_distinctive(const uint8_t* desc, const int32_t* leftRight, const uint
     if (mp.mDescriptor.empty()) return 0;
     memcpy(out, mp.mDescriptor.data, 32);
     return 1;
+}
+
+// Tracking::SearchLocalPoints' call: ORBmatcher(nnratio).SearchByProjection(F, vpMapPoints, th) on a monocular / rectified-stereo
+// frame (Nleft == -1).  Key points (undistorted x, y, octave), descriptors, mvuRight (or null) and the frame's current matches
+// (hasPoint[i] != 0: key point i already holds a map point with observations).  Map points: proj = {x, y, xR, viewCos} floats,
+// level, descriptor, inView flag.  -> matchOf[n] = index of the map point assigned to key point i by this call (-1 none);
+// returns nmatches.
+int refcut_search_by_projection(const float* kps, const int32_t* oct, const uint8_t* train, int n, const float* grid4, const float* uRight,
+                                const uint8_t* hasPoint, const float* scaleFactors, int nlevels, const float* proj, const int32_t* level,
+                                const uint8_t* mpDesc, const uint8_t* inView, int nmp, float nnratio, float th, int32_t* matchOf) {
+    using namespace ORB_SLAM3;
+    Frame* F = new Frame();
+    Frame::mnMinX = grid4[0]; Frame::mnMinY = grid4[1]; Frame::mfGridElementWidthInv = grid4[2]; Frame::mfGridElementHeightInv = grid4[3];
+    F->N = n; F->Nleft = -1;
+    F->mvKeysUn.resize(n);
+    for (int i = 0; i < n; i++) { F->mvKeysUn[i].pt.x = kps[2 * i]; F->mvKeysUn[i].pt.y = kps[2 * i + 1]; F->mvKeysUn[i].octave = oct[i]; }
+    F->AssignFeaturesToGrid();
+    F->mDescriptors = to_descriptors(train, n);
+    F->mvuRight.assign(n, -1.0f);
+    if (uRight) for (int i = 0; i < n; i++) F->mvuRight[i] = uRight[i];
+    F->mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    MapPoint old;                                                      // what the key points matched earlier hold
+    old.nObs = 1;
+    F->mvpMapPoints.assign(n, nullptr);
+    for (int i = 0; i < n; i++) if (hasPoint && hasPoint[i]) F->mvpMapPoints[i] = &old;
+    std::vector<MapPoint> mps(nmp);
+    std::vector<MapPoint*> vp(nmp);
+    for (int j = 0; j < nmp; j++) {
+        MapPoint& m = mps[j];
+        m.mTrackProjX = proj[4 * j]; m.mTrackProjY = proj[4 * j + 1]; m.mTrackProjXR = proj[4 * j + 2]; m.mTrackViewCos = proj[4 * j + 3];
+        m.mnTrackScaleLevel = level[j];
+        m.mbTrackInView = inView[j] != 0;
+        m.mDescriptor = to_descriptors(mpDesc + (size_t)32 * j, 1);
+        m.nObs = 1;                                                    // local map points have observations
+        vp[j] = &m;
+    }
+    ORBmatcher matcher(nnratio);
+    const int nmatches = matcher.SearchByProjection(*F, vp, th);
+    for (int i = 0; i < n; i++) {
+        MapPoint* p = F->mvpMapPoints[i];
+        matchOf[i] = (p && p != &old) ? (int)(p - mps.data()) : -1;
+    }
+    delete F;
+    return nmatches;
 }
 
 }  // extern "C"

@@ -265,3 +265,67 @@ def test_distinctive_port_equals_reference_compute_distinctive_descriptors():
         group = np.stack(rows)
         best = port.distinctive(group, np.int32([0, len(group)]))[0]
         assert np.array_equal(got, group[best]), case
+
+
+def _batched_search_local_points(k, d, grid4, sf, proj, level, mp_desc, in_view, u_right, has_point, nnratio, th, scan):
+    """one batched grid lookup + best/second scan for all map points of the call (`scan` = the oracle's or the
+    library's search_area_best2), then the reference's per-point decision in list order.  The reference updates F.mvpMapPoints while it
+    walks the list, and a key point that got a map point is skipped by the later ones (ORBmatcher.cc:88-90); the batched scan saw
+    the key points as they were BEFORE the call, so a point whose best or second candidate was taken meanwhile is scanned again with
+    the current mask (excluding any other candidate cannot change its best two)."""
+    kps_xy = np.stack([k["x"], k["y"]], 1)
+    oct_ = k["octave"].astype(np.int32)
+    r = np.where(proj[:, 3] > np.float32(0.998), np.float32(2.5), np.float32(4.0)).astype(np.float32)      # RadiusByViewingCos :215-221
+    if th != 1.0:
+        r = (r * np.float32(th)).astype(np.float32)
+    rq = (r * sf[level]).astype(np.float32)
+    queries = np.stack([proj[:, 0], proj[:, 1], rq, proj[:, 2]], 1).astype(np.float32)
+    qlev = np.stack([level - 1, level], 1).astype(np.int32)
+    skip = np.zeros(len(k), np.uint8) if has_point is None else has_point.astype(np.uint8).copy()
+    out = scan(kps_xy, oct_, d, grid4, queries, qlev, mp_desc, skip, u_right, 256)
+    match_of = np.full(len(k), -1, np.int32)
+    nmatches = rescans = 0
+    for j in range(len(proj)):
+        if not in_view[j]:
+            continue
+        d1, i1, d2, i2 = (int(v) for v in out[j])
+        if (i1 >= 0 and skip[i1]) or (i2 >= 0 and skip[i2]):
+            d1, i1, d2, i2 = (int(v) for v in scan(kps_xy, oct_, d, grid4, queries[j:j + 1], qlev[j:j + 1], mp_desc[j:j + 1], skip, u_right, 256)[0])
+            rescans += 1
+        if i1 < 0 or d1 > 100:                                             # TH_HIGH :122
+            continue
+        l1, l2 = int(oct_[i1]), (int(oct_[i2]) if i2 >= 0 else -1)
+        if l1 == l2 and np.float32(d1) > np.float32(nnratio) * np.float32(d2):      # :124-125
+            continue
+        match_of[i1] = j                                                   # :127-128
+        skip[i1] = 1
+        nmatches += 1
+    return nmatches, match_of, rescans
+
+
+@pytest.mark.parametrize("with_stereo,th", [(False, 1.0), (True, 1.0), (False, 3.0)])
+def test_batched_search_local_points_equals_reference_search_by_projection(with_stereo, th):
+    """the reference's own SearchByProjection(F, vpMapPoints, th) (Tracking::SearchLocalPoints) against the batched formulation of the
+    integration notes, on a scene where many map points compete for the same key points"""
+    h, w = 480, 752
+    pe = port.PortExtractor(1000, 1.2, 8)
+    _, k, d, _ = pe.extract(synth.frame(h, w, 8))
+    n = len(k)
+    rng = np.random.default_rng(31)
+    grid4 = np.float32([0.0, 0.0, np.float32(64) / np.float32(w), np.float32(48) / np.float32(h)])
+    nmp = 1600                                                             # more map points than key points: collisions guaranteed
+    src = rng.integers(0, n, nmp)
+    proj = np.stack([k["x"][src] + rng.normal(0, 2.5, nmp), k["y"][src] + rng.normal(0, 2.5, nmp),
+                     k["x"][src] - rng.uniform(0, 40, nmp), rng.choice([0.9, 0.999, 0.9985], nmp)], 1).astype(np.float32)
+    level = np.clip(k["octave"][src] + rng.integers(-1, 2, nmp), 0, 7).astype(np.int32)
+    mp_desc = d[src].copy()
+    mp_desc[:, :4] ^= rng.integers(0, 256, (nmp, 4), dtype=np.uint8) & rng.integers(0, 256, (nmp, 4), dtype=np.uint8)
+    in_view = (rng.random(nmp) < 0.9).astype(np.uint8)
+    has_point = (rng.random(n) < 0.25).astype(np.uint8)
+    u_right = np.where(rng.random(n) < 0.5, k["x"] - rng.uniform(1, 40, n), -1).astype(np.float32) if with_stereo else None
+    nm_ref, match_ref = ref.search_by_projection(np.stack([k["x"], k["y"]], 1), k["octave"], d, grid4, pe.scale_factors, proj, level, mp_desc,
+                                                 in_view, u_right, has_point, nnratio=0.8, th=th)
+    nm, match, rescans = _batched_search_local_points(k, d, grid4, pe.scale_factors, proj, level, mp_desc, in_view, u_right, has_point, 0.8, th,
+                                                      port.search_area_best2)
+    assert nm == nm_ref and np.array_equal(match, match_ref)
+    assert nm > 300 and rescans > 0                                       # collisions really happened (extreme here: 1600 points for ~1000 key points)
