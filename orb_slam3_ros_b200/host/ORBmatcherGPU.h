@@ -48,6 +48,32 @@ public:
         return out;
     }
 
+    // The decision loop of ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, ..) (ORBmatcher.cc:77-141) over the
+    // results of ONE batched scan of all map points of the call, in list order.  The reference updates F.mvpMapPoints while it
+    // walks the list and later map points skip a key point that has just been matched (:88-90); the batched scan saw the key
+    // points as they were before the call, so a query whose best or second candidate has been taken meanwhile is scanned again
+    // -- `rescan(j, taken)` must return the best two of query j among its candidates with taken[idx] == 0 (excluding any other
+    // candidate cannot change the best two).  `octave[idx]` = octave of key point idx (F.mvKeysUn[idx].octave); `taken` (one byte
+    // per key point) starts as "holds a map point with observations" and is updated here.  Returns the number of matches;
+    // matchOf[idx] = query assigned to key point idx by this call, -1 otherwise.  Pure host code.
+    template <class Rescan>
+    static int ResolveInOrder(std::vector<BestTwo> best, const std::vector<int>& octave, std::vector<unsigned char>& taken, float nnratio,
+                              Rescan rescan, std::vector<int>& matchOf) {
+        matchOf.assign(octave.size(), -1);
+        int nmatches = 0;
+        for (size_t j = 0; j < best.size(); j++) {
+            BestTwo b = best[j];
+            if ((b.bestIdx >= 0 && taken[b.bestIdx]) || (b.secondIdx >= 0 && taken[b.secondIdx])) b = rescan((int)j, taken);
+            if (b.bestIdx < 0 || b.bestDist > TH_HIGH) continue;                                        // :122
+            const int bestLevel = octave[b.bestIdx], bestLevel2 = b.secondIdx >= 0 ? octave[b.secondIdx] : -1;
+            if (bestLevel == bestLevel2 && b.bestDist > nnratio * b.secondDist) continue;               // :124-125
+            matchOf[b.bestIdx] = (int)j;                                                                // :127-128
+            taken[b.bestIdx] = 1;
+            nmatches++;
+        }
+        return nmatches;
+    }
+
     // cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, matches, 2): idx/dist are nq x 2, missing = (-1, INT_MAX)
     void KnnMatch2(const cv::Mat& query, const cv::Mat& train, std::vector<int>& idx, std::vector<int>& dist) {
         idx.assign((size_t)query.rows * 2, -1);

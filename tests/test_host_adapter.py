@@ -28,6 +28,21 @@ def test_adapter_compiles_and_links_as_cxx14():
     assert EXE.exists()
 
 
+def test_resolve_in_order_equals_the_sequential_reference_loop():
+    """ORBmatcherGPU::ResolveInOrder (pure host code): one batched best-two scan + the in-order decision loop must give what the
+    reference's scan-decide-update loop (ORBmatcher.cc:77-141) gives, on random candidate lists competing for the same key points"""
+    from orb_slam3_ros_b200 import build
+    build.build_library()
+    exe = EXE.parent / "resolve_check"
+    exe.parent.mkdir(exist_ok=True)
+    pkg = ROOT / "orb_slam3_ros_b200"
+    subprocess.check_call(["g++", "-std=c++14", "-O2", f"-I{ROOT / 'tests' / 'cvstub'}", f"-I{ROOT / 'include'}", f"-I{pkg / 'host'}",
+                           str(ROOT / "tests" / "host" / "resolve_check.cpp"), f"-L{pkg}", "-lorbb200", f"-Wl,-rpath,{pkg}",
+                           "-L/usr/local/cuda/lib64", "-lcudart", "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "resolve_check OK" in out.stdout, out.stdout + out.stderr
+
+
 @pytest.mark.gpu
 def test_adapter_matches_c_abi(tmp_path):
     from orb_slam3_ros_b200 import synth
