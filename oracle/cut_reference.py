@@ -26,6 +26,8 @@ PIECES = [
     ("ORBmatcher_RadiusByViewingCos", "src/ORBmatcher.cc", r"^\s*float ORBmatcher::RadiusByViewingCos\(", "function"),
     ("ORBmatcher_SearchByProjection_local", "src/ORBmatcher.cc",
      r"^\s*int ORBmatcher::SearchByProjection\(Frame &F, const vector<MapPoint\*> &vpMapPoints, const float th, const bool bFarPoints", "function"),
+    ("ORBmatcher_SearchByBoW_KF_F", "src/ORBmatcher.cc",
+     r"^\s*int ORBmatcher::SearchByBoW\(KeyFrame\* pKF,Frame &F, vector<MapPoint\*> &vpMapPointMatches\)", "function"),
     ("MapPoint_ComputeDistinctiveDescriptors", "src/MapPoint.cc", r"^void MapPoint::ComputeDistinctiveDescriptors\(\)", "function"),
 ]
 

@@ -16,7 +16,8 @@
 // definitions of Frame::ComputeStereoMatches, ComputeStereoFromRGBD, AssignFeaturesToGrid, PosInGrid,
 // GetFeaturesInArea, ORBmatcher::DescriptorDistance, ComputeThreeMaxima and MapPoint::ComputeDistinctiveDescriptors
 // are cut out of Frame.cc / ORBmatcher.cc / MapPoint.cc at build time and compiled inside stand-in classes
-// (ref_cut_tu.cpp).  The Search* loops around the scans stay line-cited restatements; OpenCV-defined results are pinned to cv2.
+// (ref_cut_tu.cpp), as are SearchByProjection(Frame&, vector<MapPoint*>&, ..) and SearchByBoW(KeyFrame*, Frame&, ..)
+// for end-to-end checks of the batched scans.  The other Search* loops stay line-cited restatements; OpenCV-defined results are pinned to cv2.
 //
 // Build: g++ -O3 -march=native -ffp-contract=off -shared -fPIC (see oracle/Makefile).
 // -ffp-contract=off makes the un-fused float32 result the truth ("sin/cos and FMA").

@@ -75,6 +75,9 @@ def lib():
         l.refcut_search_by_projection.restype = C.c_int
         l.refcut_search_by_projection.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]
+        l.refcut_search_by_bow.restype = C.c_int
+        l.refcut_search_by_bow.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_int] + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 3 + \
+            [C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]
         l.refcut_distinctive.restype = C.c_int
         l.refcut_distinctive.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib = l
@@ -294,4 +297,19 @@ def search_by_projection(kps_xy, octaves, train, grid4, scale_factors, proj, lev
     nm = lib().refcut_search_by_projection(_ptr(kps_xy), _ptr(octaves), _ptr(train), n, _ptr(grid4), None if ur is None else _ptr(ur),
                                            None if hp is None else _ptr(hp), _ptr(sf), len(sf), _ptr(proj), _ptr(level), _ptr(mp_desc), _ptr(iv),
                                            nmp, nnratio, th, _ptr(match_of))
+    return nm, match_of
+
+
+def search_by_bow(kf_angle, kf_desc, kf_has_point, kf_fv, f_angle, f_desc, f_fv, nnratio=0.7, check_orientation=True):
+    """ORBmatcher(nnratio, checkOri).SearchByBoW(pKF, F, vpMapPointMatches) (ORBmatcher.cc:223-421, reference text) for a monocular
+    pair; kf_fv / f_fv = (node, start, feat) arrays of the two feature vectors (RefVocabulary.transform()[2:5] or the port's)
+    -> (nmatches, match_of[nF]: key-frame feature whose map point was matched to each frame feature, -1 none)"""
+    ka, fa = np.ascontiguousarray(kf_angle, np.float32), np.ascontiguousarray(f_angle, np.float32)
+    kd, fd = np.ascontiguousarray(kf_desc, np.uint8), np.ascontiguousarray(f_desc, np.uint8)
+    hp = np.ascontiguousarray(kf_has_point, np.uint8)
+    kn, ks, kf_ = (np.ascontiguousarray(a, np.int32) for a in kf_fv)
+    fn, fs, ff = (np.ascontiguousarray(a, np.int32) for a in f_fv)
+    match_of = np.full(len(fa), -1, np.int32)
+    nm = lib().refcut_search_by_bow(_ptr(ka), _ptr(kd), _ptr(hp), len(ka), _ptr(kn), _ptr(ks), _ptr(kf_), len(kn), len(kf_), _ptr(fa), _ptr(fd), len(fa),
+                                    _ptr(fn), _ptr(fs), _ptr(ff), len(fn), len(ff), nnratio, int(check_orientation), _ptr(match_of))
     return nm, match_of

@@ -18,6 +18,7 @@
 //   MapPoint::ComputeDistinctiveDescriptors       MapPoint.cc:329-403
 //   ORBmatcher::ORBmatcher, RadiusByViewingCos    ORBmatcher.cc:39-41, :215-221
 //   ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints)   ORBmatcher.cc:43-213
+//   ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)   ORBmatcher.cc:223-421 (over the vendored DBoW2::FeatureVector)
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -28,6 +29,8 @@
 #include <tuple>
 #include <vector>
 
+#include "DBoW2/BowVector.h"
+#include "DBoW2/FeatureVector.h"
 #include "ORBextractor.h"
 
 #define FRAME_GRID_ROWS 48      // Frame.h:44
@@ -40,11 +43,13 @@ namespace ORB_SLAM3 {
 class Frame;
 class KeyFrame;
 class MapPoint;
+class GeometricCamera;
 
 class ORBmatcher {              // ORBmatcher.h:38-106
 public:
     ORBmatcher(float nnratio = 0.6, bool checkOri = true);
     static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
+    int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
     int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3, const bool bFarPoints = false,
                            const float thFarPoints = 50.0f);
     static const int TH_LOW;
@@ -56,10 +61,16 @@ public:
     bool mbCheckOrientation;
 };
 
-class KeyFrame {                // KeyFrame.h: the members ComputeDistinctiveDescriptors reads
+class KeyFrame {                // KeyFrame.h:256, :380-522: the members the cut functions read
 public:
     bool isBad() { return mbBad; }
+    std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+    std::vector<cv::KeyPoint> mvKeys, mvKeysUn, mvKeysRight;
     cv::Mat mDescriptors;
+    DBoW2::FeatureVector mFeatVec;
+    std::vector<MapPoint*> mvpMapPoints;
+    GeometricCamera *mpCamera = nullptr, *mpCamera2 = nullptr;
+    int NLeft = -1, NRight = -1;
     bool mbBad = false;
 };
 
@@ -95,7 +106,10 @@ public:
     std::vector<cv::KeyPoint> mvKeys, mvKeysRight, mvKeysUn;
     std::vector<MapPoint*> mvpMapPoints;
     std::vector<float> mvuRight, mvDepth;
+    DBoW2::BowVector mBowVec;
+    DBoW2::FeatureVector mFeatVec;
     cv::Mat mDescriptors, mDescriptorsRight;
+    GeometricCamera *mpCamera = nullptr, *mpCamera2 = nullptr;
     static float mfGridElementWidthInv, mfGridElementHeightInv;
     std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
     std::vector<float> mvScaleFactors, mvInvScaleFactors;
@@ -113,6 +127,7 @@ float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX
 #include "cut/ORBmatcher_ctor.inc"
 #include "cut/ORBmatcher_SearchByProjection_local.inc"
 #include "cut/ORBmatcher_RadiusByViewingCos.inc"
+#include "cut/ORBmatcher_SearchByBoW_KF_F.inc"
 #include "cut/ORBmatcher_ComputeThreeMaxima.inc"
 #include "cut/ORBmatcher_DescriptorDistance.inc"
 #include "cut/Frame_AssignFeaturesToGrid.inc"
@@ -285,6 +300,37 @@ int refcut_search_by_projection(const float* kps, const int32_t* oct, const uint
     }
     delete F;
     return nmatches;
+}
+
+// ORBmatcher(nnratio, checkOri).SearchByBoW(pKF, F, vpMapPointMatches) (Tracking::TrackReferenceKeyFrame / Relocalization) on a
+// monocular key frame / frame pair.  Feature vectors as (node, start, feature list) triples in ascending node order (what
+// refbow_transform returns); kfHasPoint[i] != 0: key-frame feature i holds a (good) map point.  -> matchOf[nF] = key-frame feature
+// whose map point was matched to frame feature i (-1 none); returns nmatches.
+int refcut_search_by_bow(const float* kfAngle, const uint8_t* kfDesc, const uint8_t* kfHasPoint, int nK, const int32_t* kfNode,
+                         const int32_t* kfStart, const int32_t* kfFeat, int kfNodes, int kfFeats, const float* fAngle, const uint8_t* fDesc, int nF,
+                         const int32_t* fNode, const int32_t* fStart, const int32_t* fFeat, int fNodes, int fFeats, float nnratio, int checkOri,
+                         int32_t* matchOf) {
+    using namespace ORB_SLAM3;
+    KeyFrame kf;
+    Frame* F = new Frame();
+    std::vector<MapPoint> mps(nK);
+    kf.mvKeysUn.resize(nK); kf.mvpMapPoints.assign(nK, nullptr);
+    for (int i = 0; i < nK; i++) { kf.mvKeysUn[i].angle = kfAngle[i]; if (kfHasPoint[i]) kf.mvpMapPoints[i] = &mps[i]; }
+    kf.mDescriptors = to_descriptors(kfDesc, nK);
+    for (int g = 0; g < kfNodes; g++)
+        for (int f = kfStart[g]; f < (g + 1 < kfNodes ? kfStart[g + 1] : kfFeats); f++) kf.mFeatVec.addFeature(kfNode[g], kfFeat[f]);
+    F->N = nF; F->Nleft = -1;
+    F->mvKeys.resize(nF);
+    for (int i = 0; i < nF; i++) F->mvKeys[i].angle = fAngle[i];
+    F->mDescriptors = to_descriptors(fDesc, nF);
+    for (int g = 0; g < fNodes; g++)
+        for (int f = fStart[g]; f < (g + 1 < fNodes ? fStart[g + 1] : fFeats); f++) F->mFeatVec.addFeature(fNode[g], fFeat[f]);
+    std::vector<MapPoint*> matches;
+    ORBmatcher matcher(nnratio, checkOri != 0);
+    const int nm = matcher.SearchByBoW(&kf, *F, matches);
+    for (int i = 0; i < nF; i++) matchOf[i] = matches[i] ? (int)(matches[i] - mps.data()) : -1;
+    delete F;
+    return nm;
 }
 
 }  // extern "C"

@@ -329,3 +329,62 @@ def test_batched_search_local_points_equals_reference_search_by_projection(with_
                                                       port.search_area_best2)
     assert nm == nm_ref and np.array_equal(match, match_ref)
     assert nm > 300 and rescans > 0                                       # collisions really happened (extreme here: 1600 points for ~1000 key points)
+
+
+def test_batched_search_by_bow_equals_reference_search_by_bow():
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ..) (TrackReferenceKeyFrame; reference text over the vendored DBoW2::FeatureVector)
+    against the batched formulation: feature vectors from the BoW transform, one best-two scan over the candidate lists of all
+    key-frame features (init 256), the in-order decision (frame features matched earlier in the call are skipped, :276-277; TH_LOW
+    and the strict float ratio test, :322-324) and the rotation-histogram filter (:329-341, :396-415)"""
+    from orb_slam3_ros_b200.bow import synthetic_vocabulary
+    vocab = synthetic_vocabulary(8, 4, seed=5, stop_fraction=0.0)
+    left, right = synth.stereo_pair(376, 620, 4, dmax=25)
+    _, kk, dk, _ = port.PortExtractor(900, 1.2, 8).extract(left)
+    _, kf, df, _ = port.PortExtractor(900, 1.2, 8).extract(right)
+    rng = np.random.default_rng(17)
+    ang_k = kk["angle"].copy()
+    turn = rng.random(len(kk)) < 0.25
+    ang_k[turn] = (ang_k[turn] + rng.uniform(40, 320, int(turn.sum())).astype(np.float32)) % np.float32(360)      # inconsistent rotations
+    has_point = (rng.random(len(kk)) < 0.85).astype(np.uint8)
+    levelsup = 2
+    fv_k = port.bow_transform(vocab, dk, levelsup, 1)[2:5]
+    fv_f = port.bow_transform(vocab, df, levelsup, 1)[2:5]
+    nnratio = 0.7
+    nm_ref, match_ref = ref.search_by_bow(ang_k, dk, has_point, fv_k, kf["angle"], df, fv_f, nnratio, True)
+
+    def groups(fv, n):
+        node, start, feat = fv
+        ends = list(start[1:]) + [len(feat)]
+        return {int(nd): feat[s:e] for nd, s, e in zip(node, start, ends)}
+    gk, gf = groups(fv_k, len(kk)), groups(fv_f, len(kf))
+    queries, cand, rowptr = [], [], [0]
+    for nd in sorted(set(gk) & set(gf)):                                  # the merge loop :243-394 visits common nodes in ascending order
+        for q in gk[nd]:
+            if has_point[q]:
+                queries.append(int(q))
+                cand.extend(int(c) for c in gf[nd])
+                rowptr.append(len(cand))
+    cand, rowptr = np.int32(cand), np.int32(rowptr)
+    best = port.best2_csr(dk[queries], df, cand, rowptr, 256)
+    taken = np.zeros(len(kf), bool)
+    match = np.full(len(kf), -1, np.int32)
+    pairs, rescans = [], 0
+    for j, q in enumerate(queries):
+        d1, i1, d2, i2 = (int(v) for v in best[j])
+        if (i1 >= 0 and taken[i1]) or (i2 >= 0 and taken[i2]):
+            c = np.int32([x for x in cand[rowptr[j]:rowptr[j + 1]] if not taken[x]])
+            d1, i1, d2, i2 = (int(v) for v in port.best2_csr(dk[q:q + 1], df, c, np.int32([0, len(c)]), 256)[0])
+            rescans += 1
+        if i1 < 0 or d1 > 50:                                              # TH_LOW :320
+            continue
+        if not (np.float32(d1) < np.float32(nnratio) * np.float32(d2)):    # :322
+            continue
+        match[i1] = q
+        taken[i1] = True
+        pairs.append((q, i1))
+    keep, _ = port.rotation_check(ang_k[[p[0] for p in pairs]], kf["angle"][[p[1] for p in pairs]])
+    for (q, i1), kp in zip(pairs, keep):
+        if not kp:
+            match[i1] = -1
+    assert int((match >= 0).sum()) == nm_ref and np.array_equal(match, match_ref)
+    assert nm_ref > 100 and rescans > 0 and (~keep).sum() > 0              # matches, collisions and rotation rejects all occurred
