@@ -3,8 +3,8 @@
 compiled as a whole here (Frame.cc and ORBmatcher.cc need Eigen / Sophus / boost / Pangolin through their headers), so that
 oracle/ref_cut_tu.cpp can compile the reference's OWN text of those functions inside minimal stand-in classes.
 
-The pieces are written to oracle/_ref/cut/*.inc -- a git-ignored build directory; nothing of the reference is stored in the
-repository.  A piece is located by the start of its definition and ends where its braces balance; the script fails loudly when
+The pieces are written to oracle/_ref/cut/*.inc -- a git-ignored build directory that the Makefile removes again once the
+library is linked; nothing of the reference is stored in the repository.  A piece is located by the start of its definition and ends where its braces balance; the script fails loudly when
 a definition is not found exactly once.   usage: cut_reference.py <reference orb_slam3 dir> <output dir>"""
 import re
 import sys
