@@ -3,7 +3,8 @@
 //
 // Frame.cc and ORBmatcher.cc cannot be compiled as a whole in this image (their headers pull in Eigen, Sophus, boost,
 // Pangolin, g2o).  `make ref` therefore cuts the DEFINITIONS of the functions below out of those files at build time
-// (oracle/cut_reference.py -> oracle/_ref/cut/*.inc, a git-ignored build directory; no reference text lives in the repository)
+// (oracle/cut_reference.py -> oracle/_ref/cut/*.inc, a git-ignored build directory removed again after linking; no reference text
+// lives in the repository)
 // and this file #includes them between declarations of `class Frame` / `class ORBmatcher` that carry exactly the members
 // those bodies touch, with the reference's names and types (Frame.h:44-45, :214-360; ORBmatcher.h:38-106).  The bodies are
 // compiled unmodified; OpenCV comes from cvshim/ as for the extractor.
