@@ -21,6 +21,7 @@
  *   orbb_rotation_check_csr         rotation histogram + ComputeThreeMaxima   orb_slam3/src/ORBmatcher.cc:345-352, :405-423, :2012-2053
  *   orbb_knn2 / orbb_knn2_partial   cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, 2)   orb_slam3/src/Frame.cc:1144
  *   orbb_knn2_merge                 (top-2 merge of database shards after an all-gather; no reference counterpart)
+ *   orbb_knn2_sharded               the same knnMatch against a database sharded over an NCCL communicator (BASELINE config 4)
  *   orbb_vocab_create / orbb_bow_transform   DBoW2 TemplatedVocabulary::transform via Frame::ComputeBoW   orb_slam3/src/Frame.cc:738-745,
  *                                   orb_slam3/Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1139-1275 ("next" row)
  *   orbb_search_area_best2          Frame::GetFeaturesInArea + SearchByProjection scan   orb_slam3/src/Frame.cc:657-723, ORBmatcher.cc:71-120 ("next" row)
@@ -190,6 +191,22 @@ int orbb_knn2_dev(orbb_matcher* m, const uint8_t* q_dev, int nq, const uint8_t* 
  * by lexicographic (distance, index); output nq x 2 */
 int orbb_knn2_merge_dev(orbb_matcher* m, const int32_t* idx_sh_dev, const int32_t* dist_sh_dev, int nshards, int nq,
                         int32_t* idx2_dev, int32_t* dist2_dev);
+/* The same 2-NN against a database SHARDED over the ranks of an NCCL communicator (BASELINE config 4; no reference call site at
+ * that size -- the semantics are those of knnMatch at Frame.cc:1144-1151).  Every rank passes all nq queries (replicated) and ITS
+ * contiguous shard of the database (nd_shard rows whose first row has the global index index_base); the per-shard top-2 of all
+ * ranks travel in ONE ncclAllGather (idx and dist packed, 16 bytes per query and rank) and are merged on the device by
+ * lexicographic (distance, index), which with contiguous shards is BFMatcher's lowest-index tie rule.  idx2_dev / dist2_dev
+ * (nq x 2, device) hold the global result on every rank.  nccl_comm is the caller's ncclComm_t; asynchronous on the matcher's
+ * stream.  NCCL is bound at run time to the libnccl.so.2 already loaded in the process (else the system one);
+ * ORBB_ERR_UNSUPPORTED when there is none. */
+int orbb_knn2_sharded(orbb_matcher* m, void* nccl_comm, const uint8_t* q_dev, int nq, const uint8_t* db_shard_dev, int64_t nd_shard,
+                      int32_t index_base, int32_t* idx2_dev, int32_t* dist2_dev);
+/* For hosts that do not link NCCL themselves: ncclGetUniqueId (id128 = 128 bytes, made on one rank and handed to the others by
+ * any means), ncclCommInitRank on `device`, ncclCommDestroy; orbb_nccl_version() = ncclGetVersion() of the bound library, 0 = none. */
+int orbb_nccl_version(void);
+int orbb_nccl_unique_id(void* id128);
+int orbb_nccl_comm_create(int device, int nranks, int rank, const void* id128, void** comm_out);
+void orbb_nccl_comm_destroy(void* comm);
 /* Lowe ratio test of Frame.cc:1151 on device results: keep[i] = (second exists) && dist0 < dist1 * ratio (double) */
 int orbb_ratio_test_dev(orbb_matcher* m, const int32_t* idx2_dev, const int32_t* dist2_dev, int nq, double ratio,
                         uint8_t* keep_dev);

@@ -701,6 +701,10 @@ void port_sort_nodes(const int* sizes, const int* x0s, int n, int* perm) {
 float port_ic_angle(const uint8_t* img, size_t stride, int x, int y, const int* umax) {
     return ic_angle(img + (size_t)y * stride + x, (ptrdiff_t)stride, umax);
 }
+// IC_Angle for n key points at once (xy = n x {x, y} level coordinates, cvRound'ed like :80); used by oracle/cv2_baseline.py
+void port_ic_angles(const uint8_t* img, size_t stride, const float* xy, int n, const int* umax, float* out) {
+    for (int i = 0; i < n; i++) out[i] = ic_angle(img + (size_t)cv_round(xy[2 * i + 1]) * stride + cv_round(xy[2 * i]), (ptrdiff_t)stride, umax);
+}
 void port_descriptors(const uint8_t* blurred, size_t stride, const float* xya, int n, uint8_t* desc) {
     for (int i = 0; i < n; i++)
         orb_descriptor(blurred + (size_t)cv_round(xya[3 * i + 1]) * stride + cv_round(xya[3 * i]), (ptrdiff_t)stride, xya[3 * i + 2],

@@ -67,6 +67,7 @@ def _sig(lib):
     lib.port_sort_nodes.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.port_ic_angle.restype = C.c_float
     lib.port_ic_angle.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+    lib.port_ic_angles.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.port_descriptors.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
     lib.port_hamming.restype = C.c_int
     lib.port_hamming.argtypes = [C.c_void_p, C.c_void_p]
@@ -234,6 +235,15 @@ def ic_angle(img, x, y, umax):
     img = _u8c(img)
     um = np.ascontiguousarray(umax, np.int32)
     return float(lib().port_ic_angle(_ptr(img), img.strides[0], int(x), int(y), _ptr(um)))
+
+
+def ic_angles(img, xy, umax):
+    """IC_Angle of n key points of one level: img = the level (its parent buffer must extend 15 px beyond every key point), xy float32 [n,2]"""
+    um = np.ascontiguousarray(umax, np.int32)
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    out = np.zeros(len(xy), np.float32)
+    lib().port_ic_angles(C.c_void_p(img.ctypes.data), img.strides[0], _ptr(xy), len(xy), _ptr(um), _ptr(out))
+    return out
 
 
 def descriptors(blurred, xya, fma=False):

@@ -12,7 +12,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "liborbb200.so"
-SOURCES = ["orbb_extract.cu", "orbb_match.cu", "orbb_bow.cu"]
+SOURCES = ["orbb_extract.cu", "orbb_match.cu", "orbb_bow.cu", "orbb_nccl.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2", "--shared", "-cudart", "shared",
@@ -34,7 +34,7 @@ def is_stale():
 def build_library(force=False, verbose=False):
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [str(CSRC / s) for s in SOURCES] + ["-o", str(LIB)]
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [str(CSRC / s) for s in SOURCES] + ["-o", str(LIB), "-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

@@ -73,6 +73,11 @@ SYMBOLS = [
     ("orbb_knn2", _I, [_VP, _VP, _I, _VP, C.c_int64, _VP, _VP]),
     ("orbb_knn2_dev", _I, [_VP, _VP, _I, _VP, C.c_int64, C.c_int32, _VP, _VP]),
     ("orbb_knn2_merge_dev", _I, [_VP, _VP, _VP, _I, _I, _VP, _VP]),
+    ("orbb_knn2_sharded", _I, [_VP, _VP, _VP, _I, _VP, C.c_int64, C.c_int32, _VP, _VP]),
+    ("orbb_nccl_version", _I, []),
+    ("orbb_nccl_unique_id", _I, [_VP]),
+    ("orbb_nccl_comm_create", _I, [_I, _I, _I, _VP, C.POINTER(_VP)]),
+    ("orbb_nccl_comm_destroy", None, [_VP]),
     ("orbb_ratio_test_dev", _I, [_VP, _VP, _VP, _I, _D, _VP]),
     ("orbb_best2_csr", _I, [_VP, _VP, _I, _VP, _I, _VP, _VP, _I, _VP]),
     ("orbb_search_area_best2", _I, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _VP]),

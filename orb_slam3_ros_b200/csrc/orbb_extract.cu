@@ -4,7 +4,7 @@
 // include/orbb200.h.  Stages (one launch each per BATCH of frames, all on the handle's stream):
 //   k_pyr_level0_v / k_pyr_resize_t x (levels-1) / k_pyr_apron16   ComputePyramid   :1170-1195  (orbb_pyr.cuh: cv::resize fixed
 //                                 point + reflect-101 apron)
-//   k_fast_cell                   per-cell cv::FAST + ini/min threshold fallback   :787-872   (orbb_fast3.cuh)
+//   k_fast_cell                   per-cell cv::FAST + ini/min threshold fallback   :787-872   (orbb_fast.cuh)
 //   k_octree                      DistributeOctTree         :555-779    (array-rebuild formulation, see
 //                                                                         tests/models/octree_array_model.cpp)
 //   k_blur                        cv::GaussianBlur 7x7 s=2  :1133       (8.8 fixed point; on a side stream beside k_octree)
@@ -161,9 +161,12 @@ __global__ void __launch_bounds__(256) k_resize_image(const int2* __restrict__ t
 // (the reference blurs a clone of the level, so the pyramid apron is not used) (:1132-1133).
 // ------------------------------------------------------------------------------------------------
 // No shared memory: 3 aligned word loads per row (served by L1; neighbouring lanes share two of them), the 7-tap
-// horizontal sums as two IDP.4A each.  The pyramid's own 19-px apron IS the reflect-101 extension of the level, so edge
-// pixels need no special case.
-constexpr int BLUR_THREADS = 128, BLUR_STRIP = 32;
+// horizontal sums as two IDP.4A each.  The kernel does its own reflect-101 at the image edge, so the pyramid needs no apron
+// while a frame is processed (nothing else in the pipeline reads beyond the image; the reference's 19-px apron is built when
+// the pyramid is handed out, ensure_full_apron): rows outside the image are read through reflected row pointers (first / last
+// strip only), the word left of the image and the bytes right of it are byte permutes of the two nearest image words (first /
+// last two word columns only).
+constexpr int BLUR_THREADS = 128, BLUR_STRIP = 32, BLUR_STRIP_EDGE = 8;
 
 __device__ __forceinline__ unsigned hsum7(unsigned a, unsigned b) {
     // a = bytes x-3..x (taps 18,34,48,56), b = bytes x+1..x+4 (taps 48,34,18,0); result <= 255 * 256 fits 16 bits
@@ -178,34 +181,107 @@ __device__ __forceinline__ void blur_hwords(unsigned w0, unsigned w1, unsigned w
     h[3] = hsum7(w1, w2);
 }
 
-// One thread owns 4 adjacent columns (one word) of a 32-row strip.  The horizontal sums of two consecutive input rows are
+// One thread owns 4 adjacent columns (one word) of a strip of rows.  The horizontal sums of two consecutive input rows are
 // kept PACKED in one register (u16 | u16 << 16), so the vertical 7-tap pass of one pixel is four IDP.2A (u16 x u8 dot
 // products with the tap pairs) over the four row pairs that cover its window -- for even and for odd output rows with
 // different tap constants -- instead of 4 multiplies + 3 adds on unpacked sums.
-__global__ void __launch_bounds__(BLUR_THREADS) k_blur(const Plan* __restrict__ P, Bufs B) {
+//
+// Two launches, side by side on two streams:
+//   EDGE = false  the interior: output rows 3 .. h-4 of the word columns 1 .. nwords-3 in 32-row strips.  Their 7 x 7 windows stay
+//                 inside the image (the bytes of the last word beyond the image width are never read): no reflection code at all.
+//   EDGE = true   the frame around it, where BORDER_REFLECT_101 applies, in short strips (a few hundred threads per frame):
+//                 the word columns 0, nwords-2, nwords-1 over all rows (8-row strips; reflected bytes come from byte permutes of the
+//                 two nearest image words), and output rows 0..2 / h-3..h-1 of the interior columns (reflected row pointers).
+constexpr int BLUR_BAND = 3;                                 // output rows at the top / bottom whose windows leave the image
+
+
+template <bool EDGE>
+__global__ void __launch_bounds__(BLUR_THREADS, EDGE ? 8 : 12) k_blur(const Plan* __restrict__ P, Bufs B) {
+    constexpr int STRIP = EDGE ? BLUR_STRIP_EDGE : BLUR_STRIP;
     const int frame = blockIdx.y;
     int level = 0;
-    while (level + 1 < P->nlevels && (int)blockIdx.x >= P->lv[level + 1].blurTileBase) level++;
+    while (level + 1 < P->nlevels && (int)blockIdx.x >= (EDGE ? P->lv[level + 1].blurEdgeBase : P->lv[level + 1].blurTileBase)) level++;
     const LevelPlan& L = P->lv[level];
     // (the reference skips levels without keypoints, :1128; here the blur runs beside the detector, before that is known)
-    const int nwords = L.blurTilesX, nstrips = L.blurTilesY;
-    const int item = (blockIdx.x - L.blurTileBase) * BLUR_THREADS + threadIdx.x;
-    if (item >= nwords * nstrips) return;
-    const int strip = item / nwords, wc = item - strip * nwords;
-    const int y0 = strip * BLUR_STRIP;
-    const int rows = min(BLUR_STRIP, L.h - y0);
+    const int nwords = L.blurTilesX, h = L.h;                // (nwords >= 17, h >= 67: a level holds at least one 35-px cell + borders)
+    const int item = (blockIdx.x - (EDGE ? L.blurEdgeBase : L.blurTileBase)) * BLUR_THREADS + threadIdx.x;
+    int wc, y0, rows, colFix = 3;                            // colFix: 0 / 1 / 2 = first / last-but-one / last word column, 3 = none
+    if (!EDGE) {
+        const int ncols = nwords - 3;
+        if (item >= ncols * L.blurTilesY) return;
+        const int strip = item / ncols;
+        wc = item - strip * ncols + 1;
+        y0 = BLUR_BAND + strip * STRIP;
+        rows = min(STRIP, h - BLUR_BAND - y0);
+    } else {
+        const int nstrips = (h + STRIP - 1) / STRIP, nColItems = 3 * nstrips;
+        if (item >= nColItems + 2 * (nwords - 3)) return;
+        if (item < nColItems) {
+            const int strip = item / 3;
+            colFix = item - 3 * strip;
+            wc = colFix == 0 ? 0 : nwords - 3 + colFix;
+            y0 = strip * STRIP;
+            rows = min(STRIP, h - y0);
+        } else {
+            const int j = item - nColItems, band = j >= nwords - 3;
+            wc = 1 + j - band * (nwords - 3);
+            y0 = band ? h - BLUR_BAND : 0;
+            rows = BLUR_BAND;
+        }
+    }
     const int pitch = L.pitch, bpitch = L.bpitch;
     // input row i of the strip = level row y0 - 3 + i; output row i uses input rows i .. i + 6
-    const uint8_t* src = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + 4 * wc + (ptrdiff_t)(y0 - 3) * pitch;
-    uint8_t* out = B.blur + (size_t)frame * P->blurStride + L.blurOff + 4 * wc + (size_t)y0 * bpitch;
+    const uint8_t* col = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + 4 * wc;
+    const uint8_t* src = col + (ptrdiff_t)(y0 - 3) * pitch;  // (interior: walked two rows at a time)
+    int yin = y0 - 3;                                        // (edge: next input row, reflected into the image)
+    // column fix-ups (BORDER_REFLECT_101: column -k = column k, column w-1+k = column w-1-k).  r = valid bytes of the last word.
+    //   colFix 0: the word left of the first word column = bytes {c4, c3, c2, c1} of the words {c0..c3}, {c4..c7}
+    //   colFix 2: last word column, window {w0, w1}: byte j >= r of w1 = window byte 2r+2-j; byte j of the word right of it = 2r-2-j
+    //   colFix 1: the one before it, window {w1, w2}: byte j >= r of w2 = window byte 2r+2-j
+    unsigned selA = 0x7654u, selB = 0x7654u;
+    if (EDGE && (colFix == 1 || colFix == 2)) {
+        const int r = L.w - 4 * (nwords - 1);
+        selA = selB = 0;
+        for (int j = 0; j < 4; j++) {
+            const unsigned keep = (unsigned)(j < r ? 4 + j : 2 * r + 2 - j);
+            if (colFix == 2) {
+                selA |= keep << (4 * j);
+                selB |= (unsigned)max(2 * r - 2 - j, 0) << (4 * j);
+            } else {
+                selB |= keep << (4 * j);
+            }
+        }
+    }
     unsigned pk[4][4];                                       // 4 row pairs x 4 columns
     unsigned raw[6];                                         // the next row pair's words, loaded one iteration ahead
     auto fetch = [&]() {
-        const unsigned* r0 = reinterpret_cast<const unsigned*>(src);
-        const unsigned* r1 = reinterpret_cast<const unsigned*>(src + pitch);
+        const unsigned *r0, *r1;
+        if (EDGE) {
+            int ya = yin, yb = yin + 1;
+            ya = ya < 0 ? -ya : (ya >= h ? 2 * h - 2 - ya : ya);
+            yb = yb < 0 ? -yb : (yb >= h ? 2 * h - 2 - yb : yb);
+            r0 = reinterpret_cast<const unsigned*>(col + (ptrdiff_t)ya * pitch);
+            r1 = reinterpret_cast<const unsigned*>(col + (ptrdiff_t)yb * pitch);
+            yin += 2;
+        } else {
+            r0 = reinterpret_cast<const unsigned*>(src);
+            r1 = reinterpret_cast<const unsigned*>(src + pitch);
+            src += 2 * pitch;
+        }
         raw[0] = __ldg(r0 - 1); raw[1] = __ldg(r0); raw[2] = __ldg(r0 + 1);
         raw[3] = __ldg(r1 - 1); raw[4] = __ldg(r1); raw[5] = __ldg(r1 + 1);
-        src += 2 * pitch;
+        if (EDGE) {
+            if (colFix == 0) {
+                raw[0] = __byte_perm(raw[1], raw[2], 0x1234);
+                raw[3] = __byte_perm(raw[4], raw[5], 0x1234);
+            } else if (colFix == 2) {
+                raw[2] = __byte_perm(raw[0], raw[1], selB); raw[1] = __byte_perm(raw[0], raw[1], selA);
+                raw[5] = __byte_perm(raw[3], raw[4], selB); raw[4] = __byte_perm(raw[3], raw[4], selA);
+            } else if (colFix == 1) {
+                raw[2] = __byte_perm(raw[1], raw[2], selB);
+                raw[5] = __byte_perm(raw[4], raw[5], selB);
+            }
+        }
     };
     auto pack = [&](unsigned (&dst)[4]) {
         unsigned h0[4], h1[4];
@@ -214,48 +290,42 @@ __global__ void __launch_bounds__(BLUR_THREADS) k_blur(const Plan* __restrict__ 
 #pragma unroll
         for (int k = 0; k < 4; k++) dst[k] = h0[k] | (h1[k] << 16);
     };
+    uint8_t* out = B.blur + (size_t)frame * P->blurStride + L.blurOff + 4 * wc + (size_t)y0 * bpitch;
 #pragma unroll
     for (int j = 0; j < 3; j++) { fetch(); pack(pk[j]); }
     fetch();
+#pragma unroll 1
+    for (int mo = 0; mo < STRIP / 2; mo += 4) {               // (4 = the period of the row-pair ring pk[])
+        if (2 * mo >= rows) break;
 #pragma unroll
-    for (int m = 0; m < BLUR_STRIP / 2; m++) {
-        if (2 * m < rows) {                                  // (input rows up to rows + 6 lie inside the 19-px apron)
-            pack(pk[(m + 3) & 3]);
-            if (2 * (m + 1) < rows) fetch();                 // in flight while this iteration's vertical pass runs
-            unsigned e[4], o[4];
+        for (int mi = 0; mi < 4; mi++) {
+            const int m = mo + mi;
+            if (2 * m < rows) {                               // (the interior reads rows up to y0 + rows + 3 <= h: inside the image or its first apron row)
+                pack(pk[(mi + 3) & 3]);
+                if (2 * (m + 1) < rows) fetch();              // in flight while this iteration's vertical pass runs
+                unsigned e[4], o[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const unsigned p0 = pk[m & 3][k], p1 = pk[(m + 1) & 3][k], p2 = pk[(m + 2) & 3][k], p3 = pk[(m + 3) & 3][k];
-                // even output row 2m: rows 2m..2m+6 = (18,34) (48,56) (48,34) (18,-)
-                e[k] = __dp2a_lo(p0, 0x2212u, __dp2a_lo(p1, 0x3830u, __dp2a_lo(p2, 0x2230u, __dp2a_lo(p3, 0x0012u, 32768u))));
-                // odd output row 2m+1: rows 2m+1..2m+7 = (-,18) (34,48) (56,48) (34,18)
-                o[k] = __dp2a_lo(p0, 0x1200u, __dp2a_lo(p1, 0x3022u, __dp2a_lo(p2, 0x3038u, __dp2a_lo(p3, 0x1222u, 32768u))));
+                for (int k = 0; k < 4; k++) {
+                    const unsigned p0 = pk[mi & 3][k], p1 = pk[(mi + 1) & 3][k], p2 = pk[(mi + 2) & 3][k], p3 = pk[(mi + 3) & 3][k];
+                    // even output row 2m: rows 2m..2m+6 = (18,34) (48,56) (48,34) (18,-)
+                    e[k] = __dp2a_lo(p0, 0x2212u, __dp2a_lo(p1, 0x3830u, __dp2a_lo(p2, 0x2230u, __dp2a_lo(p3, 0x0012u, 32768u))));
+                    // odd output row 2m+1: rows 2m+1..2m+7 = (-,18) (34,48) (56,48) (34,18)
+                    o[k] = __dp2a_lo(p0, 0x1200u, __dp2a_lo(p1, 0x3022u, __dp2a_lo(p2, 0x3038u, __dp2a_lo(p3, 0x1222u, 32768u))));
+                }
+                // byte 2 of every accumulator = (acc + 2^15) >> 16
+                *reinterpret_cast<unsigned*>(out) = __byte_perm(__byte_perm(e[0], e[1], 0x0062), __byte_perm(e[2], e[3], 0x0062), 0x5410);
+                if (2 * m + 1 < rows)
+                    *reinterpret_cast<unsigned*>(out + bpitch) = __byte_perm(__byte_perm(o[0], o[1], 0x0062), __byte_perm(o[2], o[3], 0x0062), 0x5410);
+                out += 2 * bpitch;
             }
-            // byte 2 of every accumulator = (acc + 2^15) >> 16
-            *reinterpret_cast<unsigned*>(out) = __byte_perm(__byte_perm(e[0], e[1], 0x0062), __byte_perm(e[2], e[3], 0x0062), 0x5410);
-            if (2 * m + 1 < rows)
-                *reinterpret_cast<unsigned*>(out + bpitch) = __byte_perm(__byte_perm(o[0], o[1], 0x0062), __byte_perm(o[2], o[3], 0x0062), 0x5410);
-            out += 2 * bpitch;
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: FAST-9/16 per 35-px cell with NMS and the iniTh -> minTh fallback (:805-872; cv::FAST == FAST_t<16>).
-// One CTA per cell.  Cell interiors tile the level exactly, NMS never looks across a cell border.
+// K2: FAST-9/16 per 35-px cell with NMS and the iniTh -> minTh fallback (:805-872; cv::FAST == FAST_t<16>): orbb_fast.cuh
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool has_arc9(unsigned m16) {
-    unsigned m = m16 | (m16 << 16);
-    unsigned t = m & (m >> 1);
-    t &= t >> 2;
-    t &= t >> 4;          // bit i: 8 consecutive ring pixels starting at i
-    t &= m >> 8;          // ... and the 9th
-    return (t & 0xffffu) != 0;
-}
-
 #include "orbb_fast.cuh"
-#include "orbb_fast2.cuh"
-#include "orbb_fast3.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // K3: DistributeOctTree, one CTA per (frame, level).
@@ -943,7 +1013,19 @@ __device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) {         // un
     return d;
 }
 
+// STAGE: the 37 x 37 window of the blurred level that the rotated pattern can reach (|coordinate| <= 13 -> radius < 18.4) is first
+// copied into shared memory -- 37 rows x 10 aligned words, lane t of round q moves word 32q + t with a 4-byte cp.async, the copy of
+// keypoint k+1 running while keypoint k is sampled -- and the 512 samples are LDS.U8 with a few bank conflicts instead of global
+// gathers that cost ~12 L1 data-pipe wavefronts each (the L1 data pipe, at 83 % of its peak, bounded the un-staged kernel).
+constexpr int OD_PROWS = 37, OD_PWORDS = 10, OD_PATCH_WORDS = OD_PROWS * OD_PWORDS, OD_PROUNDS = (OD_PATCH_WORDS + 31) / 32;
+
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+
+template <bool STAGE>
 __global__ void __launch_bounds__(OD_THREADS, 4) k_orient_desc32(const Plan* __restrict__ P, Bufs B) {
+    __shared__ __align__(16) unsigned sPatch[STAGE ? OD_THREADS / 32 : 1][2][STAGE ? OD_PATCH_WORDS + 2 : 1];
     const int frame = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = B.outCount[frame * 2];
@@ -988,10 +1070,56 @@ __global__ void __launch_bounds__(OD_THREADS, 4) k_orient_desc32(const Plan* __r
         ca = (float)cos((double)rad); sa = (float)sin((double)rad);                            // :112 (correctly rounded)
     }
     // ---- 3. steered BRIEF on the blurred level (:107-146) ----
-    // (staging the 37 x 37 patch in shared memory first was measured slower than gathering through L1: 0.29 vs 0.25 ms)
     float4 pat[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) pat[j] = __ldg(&gPatF[j * 32 + lane]);
+    if constexpr (STAGE) {
+        unsigned (*patch)[OD_PATCH_WORDS + 2] = sPatch[warp];
+        auto stage = [&](int k) {                              // window of keypoint k -> patch[k & 1]
+            const WorkItem wi = work[k];
+            const LevelPlan& L = P->lv[wi.level];
+            const uint8_t* src = B.blur + (size_t)frame * P->blurStride + L.blurOff + (ptrdiff_t)(wi.y - 18) * L.bpitch + ((wi.x - 18) & ~3);
+            unsigned* dst = patch[k & 1];
+#pragma unroll
+            for (int q = 0; q < OD_PROUNDS; q++) {
+                const int t = q * 32 + lane;
+                if (q < OD_PROUNDS - 1 || t < OD_PATCH_WORDS) {
+                    const int row = (t * 205) >> 11;           // t / 10 for t < 1029
+                    cp_async4(dst + t, src + (ptrdiff_t)row * L.bpitch + 4 * (t - row * OD_PWORDS));
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        stage(0);
+        for (int k = 0; k < cnt; k++) {
+            if (k + 1 < cnt) {
+                stage(k + 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            __syncwarp();
+            const WorkItem wi = work[k];
+            const float a = __shfl_sync(0xffffffffu, ca, k), b = __shfl_sync(0xffffffffu, sa, k);
+            // byte (r, c) of the window lies at (r + 18) * 40 + c + (x - xstart); r and c come out of the rounding trick biased by
+            // 0x4B400000 each (see round_rne): everything constant goes into the base
+            const uint8_t* pb = reinterpret_cast<const uint8_t*>(patch[k & 1]) +
+                                (18 * 4 * OD_PWORDS + 18 + ((wi.x - 18) & 3) - (ptrdiff_t)0x4B400000 * (4 * OD_PWORDS + 1));
+            unsigned val = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float4 pt = pat[j];
+                const int r0 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(pt.x, b), __fmul_rn(pt.y, a)), 12582912.f));      // :118
+                const int c0 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, b)), 12582912.f));      // :119
+                const int r1 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(pt.z, b), __fmul_rn(pt.w, a)), 12582912.f));
+                const int c1 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(pt.z, a), __fmul_rn(pt.w, b)), 12582912.f));
+                const int t0 = pb[(ptrdiff_t)r0 * (4 * OD_PWORDS) + c0], t1 = pb[(ptrdiff_t)r1 * (4 * OD_PWORDS) + c1];
+                val |= (unsigned)(t0 < t1) << j;
+            }
+            B.desc[((size_t)frame * P->kpCap + wi.pos) * 32 + lane] = (uint8_t)val;
+            __syncwarp();                                      // everyone is done with patch[k & 1] before keypoint k + 2 overwrites it
+        }
+    } else
     for (int k = 0; k < cnt; k++) {
         const WorkItem wi = work[k];
         const LevelPlan& L = P->lv[wi.level];
@@ -1064,6 +1192,7 @@ static void free_bufs(orbb_extractor* h) {
     if (h->g1Exec) cudaGraphExecDestroy(h->g1Exec);
     h->g1Exec = nullptr;
     h->g1Valid = false;
+    h->tmapsValid = false;
 }
 
 template <typename T>
@@ -1104,6 +1233,36 @@ static int append_resize_tables(std::vector<int2>& tab, int sw, int sh, int dw, 
     return tabY;
 }
 
+// One 3-D tensor map per level over the handle's pyramid slab: x = byte within the bordered row (pitch bytes), y = bordered row
+// (h + 38), z = frame (stride = one frame's slab); box = one FAST cell tile (cellTp bytes x cellRows rows x 1 frame).  Rows or
+// frames outside the tensor are zero-filled by the copy engine (only the don't-care rows below a short bottom cell can be).
+// cuTensorMapEncodeTiled comes from the driver through the runtime (no link against libcuda).
+static bool build_tensor_maps(orbb_extractor* h, int frames) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+        cudaGetLastError();
+        return (EncodeFn)fn;
+    }();
+    if (!encode) return false;
+    const Plan& P = h->plan;
+    if (P.pyrStride % 16) return false;
+    for (int l = 0; l < P.nlevels; l++) {
+        const LevelPlan& L = P.lv[l];
+        const cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)(L.h + 2 * kEdge), (cuuint64_t)frames};
+        const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)P.pyrStride};
+        const cuuint32_t box[3] = {(cuuint32_t)P.cellTp, (cuuint32_t)P.cellRows, 1u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        if (encode(&h->tmaps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, h->b.pyr + L.pyrOff, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    return true;
+}
+
 // Geometry of every level for a WxH input + the cv::resize coefficient tables (imgproc/resize.cpp).
 static int build_plan(orbb_extractor* h, int W, int H, int frames) {
     free_bufs(h);
@@ -1111,15 +1270,14 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
     memset(&P, 0, sizeof P);
     const int nl = h->prm.nlevels;
     P.nlevels = nl; P.W = W; P.H = H;
-    P.iniTh = h->prm.ini_th_fast; P.minTh = h->prm.min_th_fast;
+    P.iniTh = std::min(std::max(h->prm.ini_th_fast, 0), 255); P.minTh = std::min(std::max(h->prm.min_th_fast, 0), 255);
+    P.k7Ini = (unsigned)(0x7f - (P.iniTh & 0x7f)) * 0x01010101u; P.k7Min = (unsigned)(0x7f - (P.minTh & 0x7f)) * 0x01010101u;
     for (int i = 0; i < 16; i++) P.umax[i] = h->umax[i];
     std::vector<int2> tab;
     std::vector<CellDesc> cellDesc;
-    std::vector<BandDesc> bands;
-    int bandSmem = 0;
     size_t pyrBytes = 0, blurBytes = 0;
     unsigned cellKeys = 0, raw = 0, nodes = 0, sel = 0;
-    int cells = 0, tiles = 0, kpCap = 0, fsTiles = 0;
+    int cells = 0, tiles = 0, edgeTiles = 0, kpCap = 0;
     for (int l = 0; l < nl; l++) {
         LevelPlan& L = P.lv[l];
         L.w = cv_round_f((float)W * h->invScale[l]);                 // :1175
@@ -1159,28 +1317,20 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
                 d.gy0 = (short)(iniY + 3); d.gy1 = (short)(skip ? iniY + 3 : maxY - 3);
                 d.level = l;
                 d.outOff = L.cellKeyBase + (unsigned)((ci * L.nCols + cj) * L.cellCap);
-                d.scoreOff = L.blurOff;
-                d.bpitch = L.bpitch;
+                {   // phase-A constants of k_fast_cell (orbb_fast.cuh)
+                    const int X0 = (d.gx0 - 3) & ~15, ih = d.gy1 - d.gy0;
+                    d.cx0 = (short)(d.gx0 - X0); d.cx1 = (short)(d.gx1 - X0);
+                    d.wa = (short)(d.cx0 >> 2);
+                    d.wLast = (short)(skip ? 0 : ((d.cx1 - 1) >> 2) - d.wa);
+                    d.nwc = std::max(d.wLast + 1, 2);                                // (>= 2 keeps the reciprocal in 32 bits; extra words are masked)
+                    d.items = std::max((ih + 1) >> 1, 0) * d.nwc;
+                    d.mInv = 0xffffffffu / (unsigned)d.nwc + 1u;
+                    d.mF7 = 0x80808080u << (8 * (d.cx0 & 3));                        // first word: bytes of columns >= cx0
+                    d.mL7 = skip ? 0u : 0x80808080u >> (8 * (3 - ((d.cx1 - 1) & 3)));   // last word: bytes of columns < cx1
+                    d.pad = 0;
+                }
                 cellDesc.push_back(d);
             }
-        {   // k_fast_band work items: per cell row, runs of cells whose pixels fit one FB_TP-wide tile
-            const int maxCells = std::max(1, std::min(FB_MAXCELLS, FB_MAXW / L.wCell));
-            const int nSeg = (L.nCols + maxCells - 1) / maxCells, per = (L.nCols + nSeg - 1) / nSeg;
-            for (int ci = 0; ci < L.nRows; ci++) {
-                const int iniY = kMinBorder + ci * L.hCell, maxY = std::min(iniY + L.hCell + 6, L.maxBY);
-                const bool skipRow = iniY >= L.maxBY - 3 || maxY - iniY < 7;
-                for (int c0 = 0; c0 < L.nCols; c0 += per) {
-                    BandDesc bd;
-                    bd.level = l; bd.ci = (short)ci; bd.c0 = (short)c0; bd.c1 = (short)std::min(c0 + per, L.nCols);
-                    bd.gy0 = (short)(iniY + 3); bd.ih = (short)(skipRow ? 0 : maxY - 3 - (iniY + 3));
-                    bd.X0 = (short)((kMinBorder + c0 * L.wCell) & ~15);
-                    bands.push_back(bd);
-                    if (bd.ih > 0)
-                        bandSmem = std::max(bandSmem, (int)(align_up((size_t)(bd.ih + 6) * FB_TP, 128) + align_up((size_t)(bd.ih + 2) * FB_TP, 128)) +
-                                                          FB_WARPS * FB_WARP_SMEM);
-                }
-            }
-        }
         cells += L.nCols * L.nRows;
         cellKeys += (unsigned)(L.nCols * L.nRows * L.cellCap);
         // quadtree (:559-561)
@@ -1196,11 +1346,11 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
         kpCap += L.selCap;
         L.scale = h->scale[l];
         L.kpSize = (float)(int)(31 * h->scale[l]);                   // :880 (PATCH_SIZE*mvScaleFactor -> int)
-        L.blurTilesX = (L.w + 3) / 4; L.blurTilesY = (L.h + BLUR_STRIP - 1) / BLUR_STRIP;     // word columns x 32-row strips
-        L.blurTileBase = tiles; tiles += (L.blurTilesX * L.blurTilesY + BLUR_THREADS - 1) / BLUR_THREADS;
-        L.fsTilesX = ((L.w + 3) / 4 + 31) / 32;
-        L.fsGroups = std::max(0, ((L.h - 2 * kEdge + FS_R - 1) / FS_R + 3) / 4);
-        L.fsBase = fsTiles; fsTiles += L.fsTilesX * L.fsGroups;
+        L.blurTilesX = (L.w + 3) / 4; L.blurTilesY = (L.h - 2 * BLUR_BAND + BLUR_STRIP - 1) / BLUR_STRIP;     // word columns; 32-row strips of the rows 3 .. h-4
+        if (L.blurTilesX < 4 || L.h < 2 * BLUR_BAND + 1) return set_err(h, ORBB_ERR_UNSUPPORTED, "level %d is too small for the blur kernel", l);
+        L.blurTileBase = tiles; tiles += ((L.blurTilesX - 3) * L.blurTilesY + BLUR_THREADS - 1) / BLUR_THREADS;      // interior: word columns 1 .. nwords-3
+        L.blurEdgeBase = edgeTiles;                                                                                  // the frame around it (k_blur<true>)
+        edgeTiles += (3 * ((L.h + BLUR_STRIP_EDGE - 1) / BLUR_STRIP_EDGE) + 2 * (L.blurTilesX - 3) + BLUR_THREADS - 1) / BLUR_THREADS;
         // cv::resize tables for level l from level l-1
         if (l > 0) {
             const LevelPlan& S = P.lv[l - 1];
@@ -1231,36 +1381,32 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
 
         }
     }
-    {
+    {   // k_pyr_apron16 work items of the 19-px apron (built on demand, ensure_full_apron)
         int items = 0;
-        for (int thin = 0; thin < 2; thin++) {
-            items = 0;
-            for (int l = 0; l < nl; l++) {
-                const LevelPlan& L = P.lv[l];
-                ApronLevel& A = thin ? P.apronThin[l] : P.apron[l];
-                const int depth = thin ? kThinApron : kEdge;
-                A.itemBase = items;
-                A.rows = depth;
-                A.leftChunk0 = (kRoiX - depth) / 16;                                  // chunks that hold the columns -depth .. -1
-                A.nLeft = 2 - A.leftChunk0;                                           // (kRoiX = 32: chunks 0,1 / chunk 1)
-                A.rightChunk0 = (kRoiX + L.w) / 16;                                   // first chunk with a column >= w
-                A.nRight = (kRoiX + L.w + depth - 1) / 16 - A.rightChunk0 + 1;
-                A.interiorChunks = std::max(A.rightChunk0 - 2, 1);                    // chunks 2 .. rightChunk0-1 lie inside the image
-                A.invIC = A.interiorChunks > 1 ? 0xffffffffu / (unsigned)A.interiorChunks + 1u : 0u;
-                A.invNR = A.nRight > 1 ? 0xffffffffu / (unsigned)A.nRight + 1u : 0u;
-                items += 2 * depth * A.interiorChunks + (L.h + 2 * depth) * (A.nLeft + A.nRight);
-            }
-            (thin ? P.apronThinItems : P.apronItems) = items;
+        for (int l = 0; l < nl; l++) {
+            const LevelPlan& L = P.lv[l];
+            ApronLevel& A = P.apron[l];
+            A.itemBase = items;
+            A.rows = kEdge;
+            A.leftChunk0 = (kRoiX - kEdge) / 16;                                  // chunks that hold the columns -19 .. -1
+            A.nLeft = 2 - A.leftChunk0;                                           // (kRoiX = 32: chunks 0,1)
+            A.rightChunk0 = (kRoiX + L.w) / 16;                                   // first chunk with a column >= w
+            A.nRight = (kRoiX + L.w + kEdge - 1) / 16 - A.rightChunk0 + 1;
+            A.interiorChunks = std::max(A.rightChunk0 - 2, 1);                    // chunks 2 .. rightChunk0-1 lie inside the image
+            A.invIC = A.interiorChunks > 1 ? 0xffffffffu / (unsigned)A.interiorChunks + 1u : 0u;
+            A.invNR = A.nRight > 1 ? 0xffffffffu / (unsigned)A.nRight + 1u : 0u;
+            items += 2 * kEdge * A.interiorChunks + (L.h + 2 * kEdge) * (A.nLeft + A.nRight);
         }
+        P.apronItems = items;
     }
-    P.bandsTotal = (int)bands.size(); P.bandSmem = bandSmem;
     {   // k_fast_cell: tile pitch 64 when every cell (+6 margin, +15 alignment) fits, else 96; smem for the tallest cell
         int maxW = 0, maxH = 0;
         for (int l = 0; l < nl; l++) { maxW = std::max(maxW, P.lv[l].wCell); maxH = std::max(maxH, P.lv[l].hCell); }
         P.cellTp = maxW + 21 <= 64 ? 64 : 96;
-        P.cellSmem = (maxH + 6) * P.cellTp + (maxH + 2) * (P.cellTp == 64 ? 48 : 80) + FB_WARP_SMEM;
+        P.cellRows = maxH + 6;
+        P.cellSmem = P.cellRows * P.cellTp + (maxH + 2) * (P.cellTp == 64 ? 48 : 80) + FC_STACK_BYTES;
     }
-    P.cellsTotal = cells; P.blurTilesTotal = tiles; P.kpCap = kpCap; P.fsTotal = fsTiles;
+    P.cellsTotal = cells; P.blurTilesTotal = tiles; P.blurEdgeTotal = edgeTiles; P.kpCap = kpCap;
     P.pyrStride = pyrBytes; P.blurStride = blurBytes;
     P.cellKeyStride = cellKeys; P.rawStride = raw; P.nodeStride = nodes; P.selStride = sel;
 
@@ -1270,17 +1416,11 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
 #define A(ptr, count) if ((rc = dev_alloc(h, &ptr, (count))) != ORBB_OK) return rc
     A(b.pyr, F * pyrBytes + 512);          // slack: tile rows of the last level may be read a few bytes past their pitch
     A(b.blur, F * blurBytes + 256);        // slack: descriptor patch rows are read as whole words
-    A(b.score, F * blurBytes);
     A(b.tab, tab.size());
     CellDesc* dCellDesc = nullptr;
     A(dCellDesc, cellDesc.size());
     b.cellDesc = dCellDesc;
-    BandDesc* dBands = nullptr;
-    A(dBands, bands.size());
-    b.bands = dBands;
     A(b.cellCount, F * cells);
-    A(b.fbList, F * cells);
-    A(b.fbCount, F);
     A(b.cellOff, F * cells);
     A(b.cellKeys, F * cellKeys);
     A(b.keys, F * 2 * raw);
@@ -1308,10 +1448,11 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
 #undef A
     if (!tab.empty()) ORBB_CUDA(h, cudaMemcpyAsync(b.tab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
     ORBB_CUDA(h, cudaMemcpyAsync(dCellDesc, cellDesc.data(), cellDesc.size() * sizeof(CellDesc), cudaMemcpyHostToDevice, h->stream));
-    ORBB_CUDA(h, cudaMemcpyAsync(dBands, bands.data(), bands.size() * sizeof(BandDesc), cudaMemcpyHostToDevice, h->stream));
-    ORBB_CUDA(h, cudaFuncSetAttribute(k_fast_band, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(bandSmem, 1024)));
-    ORBB_CUDA(h, cudaFuncSetAttribute(k_fast_cell<64>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    ORBB_CUDA(h, cudaFuncSetAttribute(k_fast_cell<96>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    ORBB_CUDA(h, (cudaFuncSetAttribute(k_fast_cell<64, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)));
+    ORBB_CUDA(h, (cudaFuncSetAttribute(k_fast_cell<96, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)));
+    ORBB_CUDA(h, (cudaFuncSetAttribute(k_fast_cell<64, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)));
+    ORBB_CUDA(h, (cudaFuncSetAttribute(k_fast_cell<96, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)));
+    h->tmapsValid = build_tensor_maps(h, frames);
     ORBB_CUDA(h, cudaMemcpyAsync(h->dPlan, &P, sizeof P, cudaMemcpyHostToDevice, h->stream));
     ORBB_CUDA(h, cudaStreamSynchronize(h->stream));
     h->capacity = frames;
@@ -1334,8 +1475,8 @@ static void mark(orbb_extractor* h, int stage) {
 static Bufs shift_bufs(const Bufs& b, const Plan& P, int f0) {
     Bufs s = b;
     const size_t f = (size_t)f0;
-    s.pyr += f * P.pyrStride; s.blur += f * P.blurStride; s.score += f * P.blurStride;
-    s.cellCount += f * P.cellsTotal; s.cellOff += f * P.cellsTotal; s.fbList += f * P.cellsTotal; s.fbCount += f;
+    s.pyr += f * P.pyrStride; s.blur += f * P.blurStride;
+    s.cellCount += f * P.cellsTotal; s.cellOff += f * P.cellsTotal;
     s.cellKeys += f * P.cellKeyStride; s.keys += f * 2 * P.rawStride; s.nodes += f * 2 * P.nodeStride;
     s.rec += f * P.nodeStride; s.cnt4 += f * P.nodeStride; s.pend += f * 2 * P.nodeStride; s.elist += f * P.nodeStride;
     s.erased += f * P.nodeStride; s.sortTmp += f * 3 * P.nodeStride; s.sel += f * P.selStride; s.selCount += f * ORBB_MAX_LEVELS;
@@ -1354,7 +1495,6 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
     cudaStream_t st = ln.st;
     mark(h, ST_PYRAMID);
     ORBB_CUDA(h, cudaMemsetAsync(B.status, 0, sizeof(int) * nframes, st));
-    ORBB_CUDA(h, cudaMemsetAsync(B.fbCount, 0, sizeof(int) * nframes, st));
     for (int l = 0; l < P.nlevels; l++) {
         const LevelPlan& L = P.lv[l];
         dim3 grid(((L.w + 3) / 4 + 31) / 32, (L.h + 7) / 8, nframes);
@@ -1381,36 +1521,20 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
         } else k_pyr_resize<<<grid, 256, 0, st>>>(h->dPlan, B, l);
         h->launches++;
     }
-    {   // only the blur reads beyond the image edge, 3 pixels: the 19-px apron is built when somebody asks for it (ensure_full_apron)
-        static const bool fullApron = getenv("ORBB_FULL_APRON") != nullptr;      // (A/B switch)
-        ApronTable T;
-        for (int l = 0; l <= ORBB_MAX_LEVELS; l++)
-            T.base[l] = fullApron ? (l < P.nlevels ? P.apron[l].itemBase : P.apronItems) : (l < P.nlevels ? P.apronThin[l].itemBase : P.apronThinItems);
-        k_pyr_apron16<<<dim3((T.base[P.nlevels] + 255) / 256, nframes), 256, 0, st>>>(h->dPlan, B, T, P.nlevels, fullApron ? 0 : 1);
-    }
-    h->launches++;
     const bool fork = !h->profiling;
     mark(h, ST_FAST);
-    // ORBB_FAST_MODE = "band" / "split" select the two earlier formulations for A/B runs (same results)
-    static const char* fastMode = getenv("ORBB_FAST_MODE");
-    if (!fastMode || (strcmp(fastMode, "band") && strcmp(fastMode, "split"))) {
-        if (P.cellTp == 64) k_fast_cell<64><<<dim3(P.cellsTotal, nframes), 32, P.cellSmem, st>>>(h->dPlan, B);
-        else k_fast_cell<96><<<dim3(P.cellsTotal, nframes), 32, P.cellSmem, st>>>(h->dPlan, B);
-        mark(h, ST_FAST_CELLS);
-        mark(h, ST_FAST_RETRY);
+    {   // ORBB_FAST_NO_TMAP=1: stage the cell tiles with one bulk copy per row instead of one tensor-map copy (A/B switch; also the
+        // path taken when the driver cannot encode the tensor maps)
+        static const bool noTmap = getenv("ORBB_FAST_NO_TMAP") != nullptr;
+        const dim3 grid(P.cellsTotal, nframes);
+        if (h->tmapsValid && !noTmap) {
+            if (P.cellTp == 64) k_fast_cell<64, true><<<grid, 32, P.cellSmem, st>>>(h->dPlan, B, h->tmaps, f0);
+            else k_fast_cell<96, true><<<grid, 32, P.cellSmem, st>>>(h->dPlan, B, h->tmaps, f0);
+        } else {
+            if (P.cellTp == 64) k_fast_cell<64, false><<<grid, 32, P.cellSmem, st>>>(h->dPlan, B, h->tmaps, f0);
+            else k_fast_cell<96, false><<<grid, 32, P.cellSmem, st>>>(h->dPlan, B, h->tmaps, f0);
+        }
         h->launches++;
-    } else if (!strcmp(fastMode, "band")) {
-        k_fast_band<<<dim3(P.bandsTotal, nframes), FB_THREADS, P.bandSmem, st>>>(h->dPlan, B, B.bands);
-        mark(h, ST_FAST_CELLS);
-        mark(h, ST_FAST_RETRY);
-        h->launches++;
-    } else {
-        k_fast_score<<<dim3(P.fsTotal, nframes), FS_THREADS, 0, st>>>(h->dPlan, B);
-        mark(h, ST_FAST_CELLS);
-        k_fast_cells<<<dim3(P.cellsTotal, nframes), FC_THREADS, 0, st>>>(B, P.cellsTotal, P.blurStride, P.cellKeyStride);
-        mark(h, ST_FAST_RETRY);
-        k_fast<<<dim3(std::min(P.cellsTotal, 48), nframes), FAST_THREADS, 0, st>>>(h->dPlan, B, 1);
-        h->launches += 3;
     }
     mark(h, ST_OCTREE);
     // fork: the blur only needs the pyramid; on its own stream it fills the SMs that the latency-bound quadtree leaves idle.
@@ -1426,18 +1550,31 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
     else k_octree<OT_THREADS><<<dim3(nframes, P.nlevels), OT_THREADS, 0, st>>>(h->dPlan, B, 0, OT_BIG_NODE);
     if (fork) {
         ORBB_CUDA(h, cudaStreamWaitEvent(ln.blurSt, ln.evFork, 0));
-        k_blur<<<dim3(P.blurTilesTotal, nframes), BLUR_THREADS, 0, ln.blurSt>>>(h->dPlan, B);
+        ORBB_CUDA(h, cudaStreamWaitEvent(ln.blurEdgeSt, ln.evFork, 0));
+        k_blur<true><<<dim3(P.blurEdgeTotal, nframes), BLUR_THREADS, 0, ln.blurEdgeSt>>>(h->dPlan, B);
+        k_blur<false><<<dim3(P.blurTilesTotal, nframes), BLUR_THREADS, 0, ln.blurSt>>>(h->dPlan, B);
         ORBB_CUDA(h, cudaEventRecord(ln.evJoin, ln.blurSt));
+        ORBB_CUDA(h, cudaEventRecord(ln.evJoinEdge, ln.blurEdgeSt));
     }
     mark(h, ST_BLUR);
-    if (fork) ORBB_CUDA(h, cudaStreamWaitEvent(st, ln.evJoin, 0));
-    else k_blur<<<dim3(P.blurTilesTotal, nframes), BLUR_THREADS, 0, st>>>(h->dPlan, B);
+    if (fork) {
+        ORBB_CUDA(h, cudaStreamWaitEvent(st, ln.evJoin, 0));
+        ORBB_CUDA(h, cudaStreamWaitEvent(st, ln.evJoinEdge, 0));
+    } else {
+        k_blur<false><<<dim3(P.blurTilesTotal, nframes), BLUR_THREADS, 0, st>>>(h->dPlan, B);
+        k_blur<true><<<dim3(P.blurEdgeTotal, nframes), BLUR_THREADS, 0, st>>>(h->dPlan, B);
+    }
     mark(h, ST_ASSEMBLE);
     k_assemble<<<nframes, 256, 0, st>>>(h->dPlan, B, lap0, lap1);
     mark(h, ST_ORIENT_DESC);
-    k_orient_desc32<<<dim3((P.kpCap + OD_THREADS / 32 * OD_KPW - 1) / (OD_THREADS / 32 * OD_KPW), nframes), OD_THREADS, 0, st>>>(h->dPlan, B);
+    {   // ORBB_DESC_NO_STAGE=1: sample the blurred level through L1 instead of a shared-memory copy of the window (A/B switch)
+        static const bool noStage = getenv("ORBB_DESC_NO_STAGE") != nullptr;
+        const dim3 grid((P.kpCap + OD_THREADS / 32 * OD_KPW - 1) / (OD_THREADS / 32 * OD_KPW), nframes);
+        if (noStage) k_orient_desc32<false><<<grid, OD_THREADS, 0, st>>>(h->dPlan, B);
+        else k_orient_desc32<true><<<grid, OD_THREADS, 0, st>>>(h->dPlan, B);
+    }
     mark(h, ST_D2H);
-    h->launches += 5;
+    h->launches += 6;
     ORBB_CUDA(h, cudaGetLastError());
     return ORBB_OK;
 }
@@ -1508,8 +1645,10 @@ int orbb_create(const orbb_params* prm, orbb_extractor** out) {
         if (l == 0) ln.st = h->stream;
         else cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking);
         cudaStreamCreateWithFlags(&ln.blurSt, cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&ln.blurEdgeSt, cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&ln.evFork, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ln.evJoin, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ln.evJoinEdge, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ln.evStart, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ln.evDone, cudaEventDisableTiming);
     }
@@ -1546,8 +1685,10 @@ void orbb_destroy(orbb_extractor* h) {
         orbb_extractor::Lane& ln = h->lanes[l];
         if (l > 0 && ln.st) { cudaStreamSynchronize(ln.st); cudaStreamDestroy(ln.st); }
         if (ln.blurSt) { cudaStreamSynchronize(ln.blurSt); cudaStreamDestroy(ln.blurSt); }
+        if (ln.blurEdgeSt) { cudaStreamSynchronize(ln.blurEdgeSt); cudaStreamDestroy(ln.blurEdgeSt); }
         if (ln.evFork) cudaEventDestroy(ln.evFork);
         if (ln.evJoin) cudaEventDestroy(ln.evJoin);
+        if (ln.evJoinEdge) cudaEventDestroy(ln.evJoinEdge);
         if (ln.evStart) cudaEventDestroy(ln.evStart);
         if (ln.evDone) cudaEventDestroy(ln.evDone);
     }
@@ -1585,7 +1726,7 @@ int orbb_set_profiling(orbb_extractor* h, int enabled) {
 }
 
 const char* orbb_stage_name(int i) {
-    static const char* names[ST_COUNT] = {"h2d", "pyramid", "fast", "fast_cells", "fast_retry", "octree", "blur", "assemble", "orient_desc", "d2h"};
+    static const char* names[ST_COUNT] = {"h2d", "pyramid", "fast", "octree", "blur", "assemble", "orient_desc", "d2h"};
     return (i >= 0 && i < ST_COUNT) ? names[i] : "";
 }
 
@@ -1612,9 +1753,13 @@ int orbb_extract_batch(orbb_extractor* h, const uint8_t* dev_imgs, int nframes, 
     return run_batch(h, dev_imgs, nframes, row_stride, frame_stride, lap0, lap1);
 }
 
+// device staging area for frames that arrive from the host / from an input-side kernel.  The single-frame CUDA graph captured
+// the old pointer (its level-0 kernel reads hImg): a reallocation invalidates it.
 static int ensure_staging(orbb_extractor* h, size_t need) {
     if (h->hImgBytes >= need) return ORBB_OK;
-    if (h->hImg) cudaFree(h->hImg);
+    if (h->g1Exec) { cudaGraphExecDestroy(h->g1Exec); h->g1Exec = nullptr; }
+    h->g1Valid = false;
+    if (h->hImg) { cudaStreamSynchronize(h->stream); cudaFree(h->hImg); }
     h->hImg = nullptr; h->hImgBytes = 0;
     ORBB_CUDA(h, cudaMalloc((void**)&h->hImg, need));
     h->hImgBytes = need;
@@ -1733,12 +1878,7 @@ int orbb_extract_batch_host_submit(orbb_extractor* h, const uint8_t* host_imgs, 
     const Plan& P = h->plan;
     // device staging area for the raw frames: tightly packed WxH
     const size_t fbytes = (size_t)width * height, need = (size_t)nframes * fbytes;
-    if (h->hImgBytes < need) {
-        if (h->hImg) cudaFree(h->hImg);
-        h->hImg = nullptr; h->hImgBytes = 0;
-        ORBB_CUDA(h, cudaMalloc((void**)&h->hImg, need));
-        h->hImgBytes = need;
-    }
+    if ((rc = ensure_staging(h, need))) return rc;
     static const bool noGraph = getenv("ORBB_NO_GRAPH") != nullptr;
     if (nframes == 1 && !h->profiling && !noGraph) {
         // ---- latency path: one stream, the kernels of the frame replayed as a CUDA graph ----
@@ -1857,14 +1997,14 @@ int orbb_extract(orbb_extractor* h, const uint8_t* img, int width, int height, s
 }
 
 // The 19-px reflect-101 apron around every level (ComputePyramid's copyMakeBorder, :1185-1191) of the frames of the last
-// extraction.  Nothing in the pipeline reads it beyond the 3 pixels the blur needs, so it is built here, when the pyramid is
+// extraction.  Nothing in the pipeline reads it (the blur reflects at the image edge itself), so it is built here, when the pyramid is
 // handed out (mvImagePyramid views, stage taps), instead of with every frame.
 static int ensure_full_apron(orbb_extractor* h) {
     if (h->apronFull || h->lastFrames <= 0) return ORBB_OK;
     const Plan& P = h->plan;
     ApronTable T;
     for (int l = 0; l <= ORBB_MAX_LEVELS; l++) T.base[l] = l < P.nlevels ? P.apron[l].itemBase : P.apronItems;
-    k_pyr_apron16<<<dim3((P.apronItems + 255) / 256, h->lastFrames), 256, 0, h->stream>>>(h->dPlan, h->b, T, P.nlevels, 0);
+    k_pyr_apron16<<<dim3((P.apronItems + 255) / 256, h->lastFrames), 256, 0, h->stream>>>(h->dPlan, h->b, T, P.nlevels);
     ORBB_CUDA(h, cudaGetLastError());
     h->launches++;
     h->apronFull = true;

@@ -1,233 +1,244 @@
-// K2 (production version): per-cell FAST-9/16 + NMS + iniTh->minTh fallback, restructured so that the work is
-// proportional to what survives each test instead of paying the full ring test in every warp:
+// K2: per-cell FAST-9/16 + non-maximum suppression + the iniThFAST -> minThFAST fallback (reference ORBextractor.cc:805-872:
+// cv::FAST on each 35-px cell at iniThFAST, again at minThFAST when the cell stays empty).   (included INSIDE namespace orbb)
 //
-//   A. quick reject for ALL interior pixels, 4 pixels per thread with byte-SIMD: a 9-long arc always contains ring
-//      pixel 0 or 8 and ring pixel 4 or 12 (cv::FAST's high-speed test), so a pixel can only be a corner if
-//      min(max(|v-p0|,|v-p8|), max(|v-p4|,|v-p12|)) > t.  VABSDIFF4 + VIMNMX.U16x2, survivors -> candidate list.
-//   B. candidates (typically 10-20 % of the pixels): 16-pixel bright/dark masks + 9-arc test -> corner list.
-//   C. corners (2-4 %): exact score  max over arcs of the arc minimum, minus 1  (3-input min network) -> score map.
-//   D. NMS on the corners only (strict '>' against the 8 neighbours, non-corners count as 0).
-//   E. survivors are few; each finds its raster rank by counting (the reference's output order, fast.cpp row scan).
+// One warp = one CTA = one cell with its own tile, so a finished cell frees its resources at once and up to 32 cells are in
+// flight per SM.  The cell interiors tile the level and cv::FAST's NMS never looks across a cell border, so after the tile is in
+// shared memory the warp needs nobody else:
 //
-// Included by orbb_extract.cu (needs Plan/Bufs and warp_incl_scan).  Reference: ORBextractor.cc:805-872, cv::FAST.
+//   stage   the cell's pixels (+3 px ring margin, 16-byte aligned window) by ONE tensor-map TMA copy (cp.async.bulk.tensor.3d:
+//           x, y, frame of the level's bordered slab; SASS UTMALDG) -- or one bulk copy per row when no tensor map is available
+//   per cell, a small state machine over one stack in shared memory keeps the expensive step at 32 busy lanes:
+//     A     quick reject, 4 px x 2 rows per lane, byte-SIMD: a 9-arc always contains ring pixel 0 or 8 AND 4 or 12, so a
+//           corner needs (|v-p0| > t or |v-p8| > t) and (|v-p4| > t or |v-p12| > t).  Per word: 4 VABSDIFF4, 4 adds, 4 LOP3.
+//           The test may pass a non-corner (it is a filter; step S is exact), it never rejects a corner.  -> candidate stack
+//     S     pops 32 candidates: EXACT score of both polarities at once.  Ring pixel p_k becomes ONE multiply-add
+//               R_k = p_k * (1 - 2^16) + v * (2^16 - 1)   =   (p_k - v)  in the low 16 bits,  (v - p_k) - [p_k < v]  in the high 16
+//           and the 9-arc minimum / maximum-over-arcs network runs on both halves with VIMNMX3.S16x2 (40 instructions):
+//           low half = max over arcs of min(p_k - v) (bright), high half = the same for v - p_k, one short where positive --
+//           the map d -> d - [d > 0] is monotone, so it commutes with min / max and is undone at the end.  score = max - 1
+//           (cv::FAST: largest threshold for which the pixel is still a corner), corner <=> max > t.  -> score byte map + the
+//           cell's corner list
+//     D     NMS over the corner list inside the cell (strict '>' against the 8 neighbours; outside the cell counts as 0)
+//     retry a cell without survivors runs A-D again at minThFAST on the pixels that are still in shared memory
+//     E     raster order by rank counting -> cellKeys / cellCount  (= vToDistributeKeys, in the reference's order)
 #pragma once
-// (included INSIDE namespace orbb)
 
-constexpr int FAST_THREADS = 256;
-constexpr int FAST_LIST = 74 * 74;      // max interior pixels of one cell
+constexpr int FC_CANDS = 32 + 256;         // candidate stack: < 32 left over + one round of phase A (32 lanes x 8 px)
+constexpr int FC_NC = 128;                 // corners of one cell kept for the list-driven NMS (more: NMS scans the score map)
+constexpr int FC_STACK_BYTES = 2 * (FC_CANDS + FC_NC);
 
-__device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel) {
-    unsigned r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
-    return r;
-}
-__device__ __forceinline__ unsigned umax16x2(unsigned a, unsigned b) { return __vmaxu2(a, b); }
-__device__ __forceinline__ unsigned umin16x2(unsigned a, unsigned b) { return __vminu2(a, b); }
-
-__device__ __forceinline__ bool arc9(unsigned m16) {
-    const unsigned m = m16 | (m16 << 16);
-    unsigned t = m & (m >> 1);
-    t &= t >> 2;
-    t &= t >> 4;
-    t &= m >> 8;
-    return (t & 0xffffu) != 0;
-}
-
-__device__ __forceinline__ int min3i(int a, int b, int c) { return min(min(a, b), c); }
 __device__ __forceinline__ int max3i(int a, int b, int c) { return max(max(a, b), c); }
 
-// mode 0: both thresholds (iniTh, then minTh if the cell stays empty).  mode 1: only cells that k_fast_cells marked -1
-// (no corner at iniTh), minTh only.
-__global__ void __launch_bounds__(FAST_THREADS) k_fast(const Plan* __restrict__ P, Bufs B, int mode) {
-    constexpr int PS = kCellPix;
-    __shared__ __align__(16) uint8_t sPix[PS * PS];
-    __shared__ __align__(16) uint8_t sScore[PS * PS];
-    __shared__ unsigned short sCand[FAST_LIST];      // phase A -> B; reused for the survivors (as 32-bit) in D/E
-    __shared__ unsigned short sCorner[FAST_LIST];    // phase B -> C/D: position | polarity << 15
-    __shared__ int sCnt[3];
+// Quick reject of 4 pixels (one word): bit 7 of byte k is set when pixel k can still be a corner.
+//   EXACT = false (both thresholds < 128, every real configuration): per byte x = |v - p|:  x > t  <=>  bit 7 of
+//     ((x + (127 - t)) | x).  The adds run on whole words; a carry out of one byte can only turn the byte above it into a false
+//     POSITIVE (x' + K + 1 reaches bit 7 for x' == t; if it wraps, x' >= 128 and the OR keeps bit 7), which step S sorts out.
+//   EXACT = true (any threshold): s = (x & 0x7f) + (0x7f - (t & 0x7f)) carries into bit 7 iff low7(x) > low7(t); for t < 128 the
+//     answer is s | x, for t >= 128 it is s & x.  M = t >= 128 ? ~0u : 0.
+template <bool EXACT>
+__device__ __forceinline__ unsigned gt_bytes(unsigned x, unsigned K7, unsigned M) {
+    if (!EXACT) return (x + K7) | x;
+    const unsigned s = (x & 0x7f7f7f7fu) + K7;
+    return (M & s & x) | (~M & (s | x));
+}
+template <bool EXACT>
+__device__ __forceinline__ unsigned quick_bytes4(unsigned wl, unsigned wc, unsigned wr, unsigned wt, unsigned wb, unsigned K7, unsigned M) {
+    const unsigned pl = __funnelshift_r(wl, wc, 8);      // bytes x-3 .. x
+    const unsigned pr = __funnelshift_r(wc, wr, 24);     // bytes x+3 .. x+6
+    const unsigned v = gt_bytes<EXACT>(__vabsdiffu4(wc, wt), K7, M) | gt_bytes<EXACT>(__vabsdiffu4(wc, wb), K7, M);
+    const unsigned h = gt_bytes<EXACT>(__vabsdiffu4(wc, pr), K7, M) | gt_bytes<EXACT>(__vabsdiffu4(wc, pl), K7, M);
+    return v & h;
+}
 
-    const int frame = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31;
-    // mode 1: persistent CTAs walk the frame's list of cells that stayed empty at iniThFAST
-    const int nWork = mode == 1 ? B.fbCount[frame] : P->cellsTotal;
-    for (int work = blockIdx.x; work < nWork; work += gridDim.x) {
-    const int gcell = mode == 1 ? B.fbList[(size_t)frame * P->cellsTotal + work] : work;
-    const CellDesc cd = B.cellDesc[gcell];
-    const LevelPlan& L = P->lv[cd.level];
-    int* cellCount = B.cellCount + (size_t)frame * P->cellsTotal + gcell;
-    const int iniX = cd.gx0 - 3, iniY = cd.gy0 - 3;
-    const int rw = cd.gx1 - cd.gx0 + 6, rh = cd.gy1 - cd.gy0 + 6;
-    if (cd.gx1 <= cd.gx0) {                        // cell skipped by the reference (:810,:819) or smaller than 7 px
-        if (tid == 0) *cellCount = 0;
-        continue;
-    }
-    __syncthreads();                               // previous work item is done with the shared tiles
-    // ---- stage the ROI with aligned 32-bit loads: tile column 0 = level column (iniX & ~3) ----
-    const int sh = iniX & 3;                       // ROI column x lives at tile column x + sh
-    const int nw = (rw + sh + 3) >> 2;             // words per tile row (<= 20)
-    const unsigned mw = (65536u + nw - 1) / nw;    // i / nw == (i * mw) >> 16 for i < 3276 (rh * nw <= 1600)
-    {
-        const uint8_t* g = B.pyr + (size_t)frame * P->pyrStride + L.roiOff + (size_t)iniY * L.pitch + (iniX - sh);
-        for (int i = tid; i < rh * nw; i += FAST_THREADS) {
-            const int r = (int)(((unsigned)i * mw) >> 16), w = i - r * nw;
-            reinterpret_cast<unsigned*>(sPix)[r * (PS / 4) + w] = __ldg(reinterpret_cast<const unsigned*>(g + (size_t)r * L.pitch) + w);
+// One cell, one warp.  tile: row t = level row gy0 - 3 + t, column = level column - X0 (pitch TP).  score: row s = interior
+// row s - 1, column = tile column - sxo (pitch SP: the cell's columns plus a zero column on each side).
+// Returns the number of NMS survivors parked in `park`.
+template <int TP, int SP, bool EXACT>
+__device__ __forceinline__ int cell_pass(const uint8_t* __restrict__ tile, uint8_t* __restrict__ score, unsigned short* candS,
+                                         unsigned short* allS, unsigned* __restrict__ park, const CellDesc& cd, int ih, int th, unsigned K7,
+                                         int lane) {
+    constexpr int PS = TP, TPW = TP / 4;
+    const int cx0 = cd.cx0, cx1 = cd.cx1, sxo = cx0 - 1;                 // score column 0 = the zero column left of the cell
+    const int wa = cd.wa, wLast = cd.wLast, nwc = cd.nwc, items = cd.items;
+    const unsigned mInv = cd.mInv, mF7 = cd.mF7, mL7 = cd.mL7;
+    const unsigned M = th >= 128 ? 0xffffffffu : 0u;
+    const unsigned* tileW = reinterpret_cast<const unsigned*>(tile) + wa;
+    const unsigned lt = (1u << lane) - 1;
+    int nCand = 0, nAll = 0, base = 0;
+    for (;;) {
+        const bool aDone = base >= items;
+        if (nCand >= 32 || (aDone && nCand > 0)) {
+            // ---- S: exact score of up to 32 candidates ----
+            const int n = min(nCand, 32);
+            nCand -= n;
+            bool isCorner = false;
+            int sp = 0;
+            if (lane < n) {
+                const unsigned rec = candS[nCand + lane];                // row << 8 | column (tile coordinates)
+                const int row = rec >> 8, col = rec & 0xff;
+                const uint8_t* q = tile + row * PS + col;
+                const unsigned C = (unsigned)q[0] * 65535u;
+#define ORBB_RING(off) ((unsigned)q[off] * 0xFFFF0001u + C)
+                unsigned d[16];
+                d[0] = ORBB_RING(3 * PS);       d[1] = ORBB_RING(3 * PS + 1);   d[2] = ORBB_RING(2 * PS + 2);   d[3] = ORBB_RING(PS + 3);
+                d[4] = ORBB_RING(3);            d[5] = ORBB_RING(-PS + 3);      d[6] = ORBB_RING(-2 * PS + 2);  d[7] = ORBB_RING(-3 * PS + 1);
+                d[8] = ORBB_RING(-3 * PS);      d[9] = ORBB_RING(-3 * PS - 1);  d[10] = ORBB_RING(-2 * PS - 2); d[11] = ORBB_RING(-PS - 3);
+                d[12] = ORBB_RING(-3);          d[13] = ORBB_RING(PS - 3);      d[14] = ORBB_RING(2 * PS - 2);  d[15] = ORBB_RING(3 * PS - 1);
+#undef ORBB_RING
+                unsigned m3[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) m3[k] = __vimin3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+                unsigned e[16];                                          // e[k] = min over the arc k .. k+8
+#pragma unroll
+                for (int k = 0; k < 16; k++) e[k] = __vimin3_s16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+                const unsigned t0 = __vimax3_s16x2(e[0], e[1], e[2]), t1 = __vimax3_s16x2(e[3], e[4], e[5]), t2 = __vimax3_s16x2(e[6], e[7], e[8]);
+                const unsigned t3 = __vimax3_s16x2(e[9], e[10], e[11]), t4 = __vimax3_s16x2(e[12], e[13], e[14]);
+                const unsigned u0 = __vimax3_s16x2(t0, t1, t2), u1 = __vimax3_s16x2(t3, t4, e[15]);
+                const unsigned X = __vimax3_s16x2(u0, u1, u1);
+                const int bright = (int)(short)(X & 0xffffu);
+                int dark = (int)X >> 16;
+                dark += dark > 0;                                        // undo d -> d - [d > 0]
+                const int M = max(bright, dark);
+                isCorner = M > th;
+                sp = (row - 2) * SP + col - sxo;                         // tile row = interior row + 3, score row = interior row + 1
+                if (isCorner) score[sp] = (uint8_t)(M - 1);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, isCorner);
+            const int slot = nAll + __popc(bal & lt);
+            if (isCorner && slot < FC_NC) allS[slot] = (unsigned short)sp;
+            nAll += __popc(bal);
+            __syncwarp();
+            continue;
         }
-    }
-    const int ih = rh - 6;
-    const int x0 = 3 + sh, x1 = rw - 3 + sh;       // interior tile columns [x0, x1)
-    const int items = ih * nw;
-    u64* out = B.cellKeys + (size_t)frame * P->cellKeyStride + cd.outOff;
-    const int kx = iniX - kMinBorder - sh, ky = iniY - kMinBorder;          // :865-866 (tile column -> ROI column)
-    unsigned* sSurv = reinterpret_cast<unsigned*>(sCand);
-    int total = 0;
-
-    for (int pass = mode; pass < 2 && total == 0; pass++) {
-        const int th = min(max(pass == 0 ? P->iniTh : P->minTh, 0), 255);
-        __syncthreads();
-        if (tid < 3) sCnt[tid] = 0;
-        for (int i = tid; i < rh * (PS / 16); i += FAST_THREADS) reinterpret_cast<uint4*>(sScore)[i] = make_uint4(0, 0, 0, 0);
-        __syncthreads();
-
-        // ---- A: quick reject, 4 pixels per thread ----
-        const unsigned K = (unsigned)(0x7fff - th) * 0x00010001u;
-        for (int base = 0; base < items; base += FAST_THREADS) {
-            const int i = base + tid;
-            unsigned cand = 0;
-            int pos0 = 0;
+        if (aDone) break;
+        // ---- A: quick reject, one word column x 2 rows per lane ----
+        {
+            const int i = base + lane;
+            unsigned cand = 0, basev = 0;
             if (i < items) {
-                const int r = (int)(((unsigned)i * mw) >> 16), w = i - r * nw;
-                const int y = r + 3;
-                const unsigned* row = reinterpret_cast<const unsigned*>(sPix) + y * (PS / 4) + w;
-                const unsigned wc = row[0];
-                const unsigned wl = w > 0 ? row[-1] : 0u, wr = row[1];
-                const unsigned wt = row[3 * (PS / 4)], wb = row[-3 * (PS / 4)];
-                const unsigned pl = __funnelshift_r(wl, wc, 8);     // bytes x-3 .. x
-                const unsigned pr = __funnelshift_r(wc, wr, 24);    // bytes x+3 .. x+6
-                const unsigned a0 = __vabsdiffu4(wc, wt), a8 = __vabsdiffu4(wc, wb);
-                const unsigned a4 = __vabsdiffu4(wc, pr), a12 = __vabsdiffu4(wc, pl);
-                const unsigned me = umin16x2(umax16x2(prmt(a0, 0, 0x4240), prmt(a8, 0, 0x4240)),
-                                             umax16x2(prmt(a4, 0, 0x4240), prmt(a12, 0, 0x4240)));
-                const unsigned mo = umin16x2(umax16x2(prmt(a0, 0, 0x4341), prmt(a8, 0, 0x4341)),
-                                             umax16x2(prmt(a4, 0, 0x4341), prmt(a12, 0, 0x4341)));
-                const unsigned te = me + K, to = mo + K;            // bit 15 / 31 set  <=>  lane value > th
-                cand = ((te >> 15) & 1u) | ((to >> 14) & 2u) | ((te >> 29) & 4u) | ((to >> 28) & 8u);
-                const int xb = 4 * w;
-                const int lo = max(x0 - xb, 0), hi = min(x1 - xb, 4);
-                cand &= hi > lo ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
-                pos0 = y * PS + xb;
+                const int s = (int)__umulhi((unsigned)i, mInv);
+                const int w = i - s * nwc;
+                const int r0 = 2 * s;
+                unsigned m7 = w == 0 ? mF7 : 0x80808080u;
+                if (w == wLast) m7 &= mL7;
+                if (w > wLast) m7 = 0u;
+                const unsigned m7b = r0 + 1 < ih ? m7 : 0u;              // (the row below the cell is readable: it is masked, not skipped)
+                const unsigned* q = tileW + (r0 + 3) * TPW + w;
+                const unsigned q0 = quick_bytes4<EXACT>(q[-1], q[0], q[1], q[3 * TPW], q[-3 * TPW], K7, M);
+                const unsigned q1 = quick_bytes4<EXACT>(q[TPW - 1], q[TPW], q[TPW + 1], q[4 * TPW], q[-2 * TPW], K7, M);
+                cand = (q0 & m7) | ((q1 & m7b) >> 1);                    // bit 8k+7: pixel k of row r0; bit 8k+6: row r0 + 1
+                basev = ((unsigned)(r0 + 3) << 8) | (unsigned)(4 * (wa + w));
             }
             const int cnt = __popc(cand);
             const int inc = warp_incl_scan(cnt, lane);
-            const int wtot = __shfl_sync(0xffffffffu, inc, 31);
-            int wbase = 0;
-            if (lane == 31 && wtot) wbase = atomicAdd(&sCnt[0], wtot);
-            wbase = __shfl_sync(0xffffffffu, wbase, 31);
-            int o = wbase + inc - cnt;
-            while (cand) {
-                const int k = __ffs(cand) - 1;
-                cand &= cand - 1;
-                sCand[o++] = (unsigned short)(pos0 + k);
-            }
-        }
-        __syncthreads();
-
-        // ---- B: full 16-pixel ring test on the candidates ----
-        const int nCand = sCnt[0];
-        for (int base = 0; base < nCand; base += FAST_THREADS) {
-            const int i = base + tid;
-            bool corner = false;
-            unsigned rec = 0;
-            if (i < nCand) {
-                const int pos = sCand[i];
-                const uint8_t* q = &sPix[pos];
-                const int v = q[0], hi = v + th, lo = v - th;
-                unsigned mb = 0, md = 0;        // ring pixel darker than v-th ("bright centre") / brighter than v+th
-#define ORBB_RING(off)                                                     \
-    {                                                                      \
-        const int p = q[off];                                              \
-        mb = __funnelshift_l((unsigned)(p - lo), mb, 1);  /* p < lo */     \
-        md = __funnelshift_l((unsigned)(hi - p), md, 1);  /* p > hi */     \
-    }
-                ORBB_RING(3 * PS) ORBB_RING(3 * PS + 1) ORBB_RING(2 * PS + 2) ORBB_RING(PS + 3)
-                ORBB_RING(3) ORBB_RING(-PS + 3) ORBB_RING(-2 * PS + 2) ORBB_RING(-3 * PS + 1)
-                ORBB_RING(-3 * PS) ORBB_RING(-3 * PS - 1) ORBB_RING(-2 * PS - 2) ORBB_RING(-PS - 3)
-                ORBB_RING(-3) ORBB_RING(PS - 3) ORBB_RING(2 * PS - 2) ORBB_RING(3 * PS - 1)
-#undef ORBB_RING
-                const bool cb = arc9(mb & 0xffffu), cd = arc9(md & 0xffffu);
-                corner = cb | cd;
-                rec = (unsigned)pos | (cd ? 0x8000u : 0u);
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, corner);
-            int wbase = 0;
-            if (lane == 0 && bal) wbase = atomicAdd(&sCnt[1], __popc(bal));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (corner) sCorner[wbase + __popc(bal & ((1u << lane) - 1))] = (unsigned short)rec;
-        }
-        __syncthreads();
-
-        // ---- C: exact score of the corners ----
-        const int nCorner = sCnt[1];
-        for (int i = tid; i < nCorner; i += FAST_THREADS) {
-            const unsigned rec = sCorner[i];
-            const int pos = rec & 0x7fff;
-            const uint8_t* q = &sPix[pos];
-            const int v = q[0];
-            const int sgn = (rec & 0x8000u) ? -1 : 1;
-            int d[16];
-            d[0] = sgn * (v - q[3 * PS]);       d[1] = sgn * (v - q[3 * PS + 1]);   d[2] = sgn * (v - q[2 * PS + 2]);
-            d[3] = sgn * (v - q[PS + 3]);       d[4] = sgn * (v - q[3]);            d[5] = sgn * (v - q[-PS + 3]);
-            d[6] = sgn * (v - q[-2 * PS + 2]);  d[7] = sgn * (v - q[-3 * PS + 1]);  d[8] = sgn * (v - q[-3 * PS]);
-            d[9] = sgn * (v - q[-3 * PS - 1]);  d[10] = sgn * (v - q[-2 * PS - 2]); d[11] = sgn * (v - q[-PS - 3]);
-            d[12] = sgn * (v - q[-3]);          d[13] = sgn * (v - q[PS - 3]);      d[14] = sgn * (v - q[2 * PS - 2]);
-            d[15] = sgn * (v - q[3 * PS - 1]);
-            int m3[16];
+            unsigned short* o = candS + (nCand + inc - cnt);
+            nCand += __shfl_sync(0xffffffffu, inc, 31);
 #pragma unroll
-            for (int k = 0; k < 16; k++) m3[k] = min3i(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-            int M = -256;
-#pragma unroll
-            for (int k = 0; k < 16; k += 2) {
-                const int e0 = min3i(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
-                const int e1 = min3i(m3[k + 1], m3[(k + 4) & 15], m3[(k + 7) & 15]);
-                M = max3i(M, e0, e1);
+            for (int k = 0; k < 4; k++) {                                // fixed predicated sequence (the order on the stack is irrelevant)
+                if (cand & (0x80u << (8 * k))) *o++ = (unsigned short)(basev + k);
+                if (cand & (0x40u << (8 * k))) *o++ = (unsigned short)(basev + 256 + k);
             }
-            sScore[pos] = (uint8_t)(M - 1);          // response = M - 1 (M > th >= 0)
+            base += 32;
+            __syncwarp();
         }
-        __syncthreads();
-
-        // ---- D: non-maximum suppression on the corners ----
-        for (int base = 0; base < nCorner; base += FAST_THREADS) {
-            const int i = base + tid;
-            bool keep = false;
-            unsigned rec = 0;
-            if (i < nCorner) {
-                const int pos = sCorner[i] & 0x7fff;
-                const uint8_t* q = &sScore[pos];
-                const int s = q[0];
-                keep = s > 0 && s > q[-1] && s > q[1] && s > q[-PS - 1] && s > q[-PS] && s > q[-PS + 1] && s > q[PS - 1] &&
-                       s > q[PS] && s > q[PS + 1];
-                rec = ((unsigned)pos << 8) | (unsigned)s;
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            int wbase = 0;
-            if (lane == 0 && bal) wbase = atomicAdd(&sCnt[2], __popc(bal));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (keep) sSurv[wbase + __popc(bal & ((1u << lane) - 1))] = rec;     // sCand is dead after phase B
-        }
-        __syncthreads();
-
-        // ---- E: raster order by rank counting (pos = y*PS + x is the raster key) ----
-        const int nSurv = sCnt[2];
-        for (int i = tid; i < nSurv; i += FAST_THREADS) {
-            const unsigned rec = sSurv[i];
-            int rank = 0;
-            for (int j = 0; j < nSurv; j++) rank += sSurv[j] < rec;
-            const int pos = (int)(rec >> 8);
-            const int y = pos / PS, x = pos - y * PS;
-            out[rank] = (u64)(unsigned)(x + kx) | ((u64)(unsigned)(y + ky) << 16) | ((u64)(rec & 0xffu) << 32);
-        }
-        total = nSurv;
     }
-    if (tid == 0) *cellCount = total;
+    // ---- D: NMS inside the cell (strict '>' against the 8 neighbours; outside the cell counts as 0) ----
+    int nSurv = 0;
+    auto nms = [&](bool valid, int sp, int sc) {                      // sp = score-map position
+        bool keep = false;
+        unsigned rec = 0;
+        if (valid) {
+            const int r1 = sp / SP, x = sp - r1 * SP + sxo;
+            const uint8_t* q = score + sp;
+            int m = max((int)q[-SP], (int)q[SP]);
+            if (x > cx0) m = max(m, max3i((int)q[-SP - 1], (int)q[-1], (int)q[SP - 1]));
+            if (x + 1 < cx1) m = max(m, max3i((int)q[-SP + 1], (int)q[1], (int)q[SP + 1]));
+            keep = sc > m;
+            rec = ((unsigned)(r1 - 1) << 16) | ((unsigned)(x - cx0) << 8) | (unsigned)sc;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) park[nSurv + __popc(bal & lt)] = rec;
+        nSurv += __popc(bal);
+    };
+    if (nAll <= FC_NC) {
+        for (int b0 = 0; b0 < nAll; b0 += 32) {
+            const bool valid = b0 + lane < nAll;
+            const int sp = valid ? allS[b0 + lane] : 0;
+            nms(valid, sp, valid ? score[sp] : 0);
+        }
+    } else {                                                          // very dense cell: walk its score map
+        const int wc = cx1 - cx0;
+        for (int b0 = 0; b0 < ih * wc; b0 += 32) {
+            const int i = b0 + lane;
+            const int r = i / wc, x = cx0 + i - r * wc;
+            const int sp = (r + 1) * SP + x - sxo;
+            const int sc = i < ih * wc ? score[sp] : 0;
+            nms(sc > 0, sp, sc);
+        }
     }
+    return nSurv;
 }
 
+// TP: tile pitch in bytes (64 when every cell + 6 px margin + 15 px alignment slop fits, else 96).  TMAP: the tile comes in by
+// one tensor-map TMA copy (tmaps = one CUtensorMap per level, a kernel parameter: dims {pitch, rows, frames} of the level's bordered
+// slab; frame0 = index of this launch's first frame within the slab) instead of one bulk copy per row.
+template <int TP, bool TMAP>
+__global__ void __launch_bounds__(32, 32) k_fast_cell(const Plan* __restrict__ P, Bufs B, const __grid_constant__ TmapTable tmaps, int frame0) {
+    constexpr int SP = TP == 64 ? 48 : 80;                    // score pitch: cell width (<= 43 / 71) + a zero column on each side
+    extern __shared__ __align__(128) uint8_t fcSmem[];
+    __shared__ __align__(8) unsigned long long sBar;
+    const int gcell = blockIdx.x, frame = blockIdx.y, lane = threadIdx.x;
+    const CellDesc cd = B.cellDesc[gcell];
+    int* cellCount = B.cellCount + (size_t)frame * P->cellsTotal + gcell;
+    const int ih = cd.gy1 - cd.gy0;
+    if (cd.gx1 <= cd.gx0 || ih <= 0) {                        // cell skipped by the reference (:810,:819) or smaller than 7 px
+        if (lane == 0) *cellCount = 0;
+        return;
+    }
+    const LevelPlan& L = P->lv[cd.level];
+    const int rowsT = ih + 6;
+    const int X0 = (cd.gx0 - 3) & ~15;
+    uint8_t* tile = fcSmem;
+    const int tileRows = TMAP ? P->cellRows : rowsT;          // (the tensor-map box has a fixed height: the tallest cell's)
+    uint8_t* score = fcSmem + tileRows * TP;                  // TP is a multiple of 16
+    unsigned short* candS = reinterpret_cast<unsigned short*>(score + (ih + 2) * SP);
+    unsigned short* allS = candS + FC_CANDS;
+    if (lane == 0) {
+        mbar_init(&sBar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&sBar, tileRows * TP);
+        if (TMAP) tma_tensor3d_g2s(tile, &tmaps.m[cd.level], kRoiX + X0, kEdge + cd.gy0 - 3, frame0 + frame, &sBar);
+    }
+    __syncwarp();
+    if (!TMAP) {
+        const uint8_t* roi = B.pyr + (size_t)frame * P->pyrStride + L.roiOff;
+        for (int r = lane; r < rowsT; r += 32) tma_bulk_g2s(tile + r * TP, roi + (ptrdiff_t)(cd.gy0 - 3 + r) * L.pitch + X0, TP, &sBar);
+    }
+    for (int i = lane; i < (ih + 2) * (SP / 16); i += 32) reinterpret_cast<uint4*>(score)[i] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    mbar_wait(&sBar, 0);
+    // survivors are parked (unordered) in the quadtree's second key buffer, which k_octree only uses later
+    unsigned* park = reinterpret_cast<unsigned*>(B.keys + ((size_t)frame * 2 + 1) * P->rawStride + cd.outOff);
+    const int iniTh = P->iniTh, minTh = P->minTh;
+    int nSurv;
+    if (iniTh < 128 && minTh < 128) {
+        nSurv = cell_pass<TP, SP, false>(tile, score, candS, allS, park, cd, ih, iniTh, P->k7Ini, lane);
+        if (nSurv == 0)                                       // :833-846 (scores do not depend on the threshold: the map stays valid)
+            nSurv = cell_pass<TP, SP, false>(tile, score, candS, allS, park, cd, ih, minTh, P->k7Min, lane);
+    } else {                                                  // thresholds >= 128: exact byte compare in the quick reject
+        nSurv = cell_pass<TP, SP, true>(tile, score, candS, allS, park, cd, ih, iniTh, P->k7Ini, lane);
+        if (nSurv == 0) nSurv = cell_pass<TP, SP, true>(tile, score, candS, allS, park, cd, ih, minTh, P->k7Min, lane);
+    }
+    // ---- E: raster order by rank counting; keys are relative to the 16-px border (:865-866) ----
+    __syncwarp();
+    u64* keysOut = B.cellKeys + (size_t)frame * P->cellKeyStride + cd.outOff;
+    for (int i = lane; i < nSurv; i += 32) {
+        const unsigned rec = __ldcg(park + i);
+        int rank = 0;
+        for (int k = 0; k < nSurv; k++) rank += __ldcg(park + k) < rec;
+        const int x = cd.gx0 + (int)((rec >> 8) & 0xffu) - kMinBorder;
+        const int y = cd.gy0 + (int)(rec >> 16) - kMinBorder;
+        keysOut[rank] = (u64)(unsigned)x | ((u64)(unsigned)y << 16) | ((u64)(rec & 0xffu) << 32);
+    }
+    if (lane == 0) *cellCount = nSurv;
+}

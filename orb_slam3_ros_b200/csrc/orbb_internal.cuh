@@ -1,5 +1,6 @@
 // Internal declarations shared by the extractor and matcher translation units of liborbb200.so.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -15,7 +16,7 @@ typedef unsigned long long u64;
 constexpr int kEdge = 19;          // EDGE_THRESHOLD        (reference ORBextractor.cc:73)
 constexpr int kRoiX = 32;          // column of the first image pixel inside a bordered row (>= kEdge, 16B aligned)
 constexpr int kMinBorder = 16;     // EDGE_THRESHOLD - 3    (:789)
-constexpr int kCellPix = 80;       // shared-memory pitch / max side of one FAST cell incl. its 6-px apron
+constexpr int kCellPix = 80;       // max side of one FAST cell incl. its 6-px apron
 constexpr int kMaxIni = 16;        // max root nodes of the quadtree (image aspect ratio <= 16.5)
 
 // One pyramid level: geometry + where its data lives inside the per-frame slabs.
@@ -37,8 +38,7 @@ struct LevelPlan {
     unsigned selBase;
     int selCap;
     float scale, kpSize;
-    int blurTileBase, blurTilesX, blurTilesY;
-    int fsBase, fsTilesX, fsGroups;    // k_fast_score tiling: 32 word-columns x (4 strips of 8 rows) per CTA
+    int blurTileBase, blurEdgeBase, blurTilesX, blurTilesY;      // k_blur: first CTA of the level in the interior / edge-column launch; word columns, 32-row strips
     int fastResize;                    // 1: the 4 source taps of every column group fit 3 aligned words (k_pyr_resize_s)
     int prmtTaps;                      // 1: the taps of the first three columns of every group lie in the first two of those words
 };
@@ -46,22 +46,20 @@ struct LevelPlan {
 // k_pyr_apron16 work decomposition of one level (16-byte chunks that contain apron bytes): `rows` apron rows above and below
 // the image, `nLeft` chunks from chunk `leftChunk0` at the left end of every bordered row, `nRight` from `rightChunk0` at the right
 struct ApronLevel { int itemBase, interiorChunks, rightChunk0, nRight, rows, leftChunk0, nLeft; unsigned invIC, invNR; };     // inv* = 2^32 / n + 1
-constexpr int kThinApron = 3;      // what the 7x7 blur reads around the image (the only in-pipeline reader of the apron)
 
 struct Plan {
     int nlevels, W, H;
-    int cellsTotal, blurTilesTotal, fsTotal;
-    int bandsTotal, bandSmem;      // k_fast_band: CTAs per frame, dynamic shared memory per CTA
-    int cellTp, cellSmem;          // k_fast_cell: tile pitch (64 / 96), dynamic shared memory per CTA
+    int cellsTotal, blurTilesTotal, blurEdgeTotal;
+    int cellTp, cellSmem, cellRows;   // k_fast_cell: tile pitch (64 / 96), dynamic shared memory per CTA, tile rows of the tallest cell
     int kpCap;
-    int iniTh, minTh;
+    int iniTh, minTh;              // clamped to 0..255
+    unsigned k7Ini, k7Min;         // (0x7f - (th & 0x7f)) * 0x01010101: the byte-wise compare constant of the quick reject
     u64 pyrStride, blurStride;                                  // bytes per frame
     unsigned cellKeyStride, rawStride, nodeStride, selStride;   // entries per frame
     int umax[16];
     LevelPlan lv[ORBB_MAX_LEVELS];
-    ApronLevel apron[ORBB_MAX_LEVELS];      // the full 19-px apron of mvImagePyramid (built on demand: nothing in the pipeline reads it)
-    ApronLevel apronThin[ORBB_MAX_LEVELS];  // the 3-px ring the blur needs (built with every frame)
-    int apronItems, apronThinItems;
+    ApronLevel apron[ORBB_MAX_LEVELS];      // the 19-px apron of mvImagePyramid (built on demand: nothing in the pipeline reads it)
+    int apronItems;
 };
 
 struct QNode {                     // quadtree node: UL=(x0,y0) BR=(x1,y1); keys = segment of a ping-pong buffer
@@ -74,27 +72,25 @@ struct WorkItem { int level, x, y, pos; };
 
 // FAST cell (host-built, shared by all frames): interior [gx0,gx1) x [gy0,gy1) in level coordinates (empty when the
 // reference skips the cell, ORBextractor.cc:810,:819), first key slot of the cell inside the frame's cellKeys.
-struct CellDesc { short gx0, gx1, gy0, gy1; int level; unsigned outOff; unsigned scoreOff; int bpitch; };
-
-// k_fast_band work item (host-built, one per CTA, shared by all frames): a run of adjacent cells of one cell row
-struct BandDesc {
-    int level;
-    short ci, c0, c1;              // cell row; cells [c0, c1) of that row
-    short gy0, ih;                 // interior rows [gy0, gy0 + ih) in level coordinates (ih <= 0: skipped cell row)
-    short X0;                      // level column of tile byte 0 (multiple of 16)
+// The second half holds what the detector's state machine needs in every round, precomputed here because ptxas otherwise
+// re-derives these loop invariants (as uniform-datapath instructions, but issue slots all the same) in every round: tile columns
+// [cx0, cx1) of the interior (tile column 0 = level column (gx0 - 3) & ~15), first word `wa`, last word offset `wLast`, words per
+// row pair `nwc` (>= 2) with its reciprocal, work items of phase A, byte masks of the first / last word.
+struct __align__(16) CellDesc {
+    short gx0, gx1, gy0, gy1; int level; unsigned outOff;
+    short cx0, cx1, wa, wLast; int nwc, items; unsigned mInv, mF7, mL7, pad;
 };
+
+// One tensor map per pyramid level (k_fast_cell's tile loads): dims {pitch, bordered rows, frames} of the level's slab
+struct TmapTable { CUtensorMap m[ORBB_MAX_LEVELS]; };
 
 // Device buffers of one extractor handle, sized for `capacity` frames.
 struct Bufs {
     uint8_t* pyr;
     uint8_t* blur;
-    uint8_t* score;                // FAST response map per level (same layout as blur)
     int2* tab;                     // resize tables (shared by all frames)
     const CellDesc* cellDesc;      // [cellsTotal]
-    const BandDesc* bands;         // [bandsTotal]
     int* cellCount;
-    int* fbList;                   // [frame][cellsTotal] cells that need the minThFAST retry
-    int* fbCount;                  // [frame]
     int* cellOff;
     u64* cellKeys;                 // key = x | y<<16 | score<<32 (x,y relative to the 16-px border)
     u64* keys;                     // [frame][2][rawStride]
@@ -148,10 +144,17 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigne
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// one tile of a 3-D tensor map (x = byte within the bordered row, y = bordered row, z = frame) -> shared memory; SASS: UTMALDG.3D
+__device__ __forceinline__ void tma_tensor3d_g2s(void* dst, const CUtensorMap* tmap, int x, int y, int z, void* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 #endif
 
-enum Stage { ST_H2D = 0, ST_PYRAMID, ST_FAST, ST_FAST_CELLS, ST_FAST_RETRY, ST_OCTREE, ST_BLUR, ST_ASSEMBLE, ST_ORIENT_DESC, ST_D2H, ST_COUNT };
+enum Stage { ST_H2D = 0, ST_PYRAMID, ST_FAST, ST_OCTREE, ST_BLUR, ST_ASSEMBLE, ST_ORIENT_DESC, ST_D2H, ST_COUNT };
 
 }  // namespace orbb
 
@@ -167,12 +170,14 @@ struct orbb_extractor {
     // execution lanes of the resident batch path: the frames of a batch are split over ORBB_LANES streams so that the
     // latency-bound kernels of one part (quadtree, descriptors) share the SMs with the issue-bound ones of another; inside a
     // lane the blur runs on a side stream beside the quadtree (both only read the pyramid).  Lane 0 uses `stream`.
-    struct Lane { cudaStream_t st = nullptr, blurSt = nullptr; cudaEvent_t evFork = nullptr, evJoin = nullptr, evStart = nullptr, evDone = nullptr; };
+    struct Lane { cudaStream_t st = nullptr, blurSt = nullptr, blurEdgeSt = nullptr; cudaEvent_t evFork = nullptr, evJoin = nullptr, evJoinEdge = nullptr, evStart = nullptr, evDone = nullptr; };
     Lane lanes[4];
     int nLanes = 1;                // measured on B200: 2 lanes +1.7 % resident, -11 % end to end -> off by default (ORBB_LANES)
     // plan for the current image size
     orbb::Plan plan;
     orbb::Plan* dPlan = nullptr;
+    orbb::TmapTable tmaps{};       // per-level tensor maps over b.pyr (valid with the plan)
+    bool tmapsValid = false;
     bool planValid = false;
     int capacity = 0;              // frames the buffers are sized for
     orbb::Bufs b{};

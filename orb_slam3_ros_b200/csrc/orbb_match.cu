@@ -215,7 +215,9 @@ __global__ void k_knn2_merge_chunks(const unsigned* __restrict__ partial, int nc
 }
 
 // merge across database shards: input [shard][nq][2] (idx, dist), lexicographic (dist, idx) order
-__global__ void k_knn2_merge_shards(const int* __restrict__ idxSh, const int* __restrict__ distSh, int nshards, int nq,
+// (shardStride = ints between the blocks of consecutive shards: 2 * nq for separate idx / dist arrays, 4 * nq for the packed
+// [idx][dist] blocks that orbb_knn2_sharded all-gathers)
+__global__ void k_knn2_merge_shards(const int* __restrict__ idxSh, const int* __restrict__ distSh, size_t shardStride, int nshards, int nq,
                                     int* __restrict__ idx2, int* __restrict__ dist2) {
     const int qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
@@ -223,8 +225,8 @@ __global__ void k_knn2_merge_shards(const int* __restrict__ idxSh, const int* __
     for (int s = 0; s < nshards; s++) {
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            const int i = idxSh[((size_t)s * nq + qi) * 2 + k];
-            const int d = distSh[((size_t)s * nq + qi) * 2 + k];
+            const int i = idxSh[(size_t)s * shardStride + (size_t)qi * 2 + k];
+            const int d = distSh[(size_t)s * shardStride + (size_t)qi * 2 + k];
             if (i < 0) continue;
             if (d < d1 || (d == d1 && i < i1)) { d2 = d1; i2 = i1; d1 = d; i1 = i; }
             else if (d < d2 || (d == d2 && i < i2)) { d2 = d; i2 = i; }
@@ -748,6 +750,23 @@ static int ensure_scratch(orbb_matcher* m, int slot, size_t bytes) {
     return ORBB_OK;
 }
 
+// ---- what orbb_nccl.cu (the sharded 2-NN) needs from this translation unit ----
+int matcher_device(const orbb_matcher* m) { return m->device; }
+cudaStream_t matcher_stream(const orbb_matcher* m) { return m->stream; }
+int matcher_scratch(orbb_matcher* m, int slot, size_t bytes, void** out) {
+    const int rc = ensure_scratch(m, slot, bytes);
+    *out = rc ? nullptr : m->scratch[slot];
+    return rc;
+}
+int matcher_error(orbb_matcher* m, int code, const char* msg) { return m_err(m, code, "%s", msg); }
+int launch_merge_shards(orbb_matcher* m, const int32_t* idx_sh, const int32_t* dist_sh, size_t shard_stride, int nshards, int nq, int32_t* idx2,
+                        int32_t* dist2) {
+    k_knn2_merge_shards<<<(nq + 255) / 256, 256, 0, m->stream>>>(idx_sh, dist_sh, shard_stride, nshards, nq, idx2, dist2);
+    m->launches++;
+    ORBM_CUDA(m, cudaGetLastError());
+    return ORBB_OK;
+}
+
 }  // namespace orbb
 
 using namespace orbb;
@@ -832,21 +851,10 @@ int orbb_knn2_dev(orbb_matcher* m, const uint8_t* q_dev, int nq, const uint8_t* 
 #define ORBB_KNN_LAUNCH_M(C, S, M)                                                                                                \
     k_knn2_partial<C, S, M, 0><<<dim3(qtiles, nchunks), KNN_THREADS, 0, m->stream>>>((const uint4*)q_dev, nq, (const uint4*)db_dev, \
                                                                                     nd, (int)rowsPer, m->partial)
-        if (mixM == 2 && mixC == 2 && mixS == 1) ORBB_KNN_LAUNCH_M(2, 1, 2);
-        else if (mixM == 2 && mixC == 3 && mixS == 1) ORBB_KNN_LAUNCH_M(3, 1, 2);
-        else if (mixM == 2 && mixC == 5 && mixS == 2) ORBB_KNN_LAUNCH_M(5, 2, 2);
-        else if (mixM == 2 && mixC == 3 && mixS == 0) ORBB_KNN_LAUNCH_M(3, 0, 2);
-        else if (mixM == 3 && mixC == 3 && mixS == 0) ORBB_KNN_LAUNCH_M(3, 0, 3);
-        else if (mixM == 3 && mixC == 4 && mixS == 0) ORBB_KNN_LAUNCH_M(4, 0, 3);
-        else if (mixM == 3 && mixC == 5 && mixS == 0) ORBB_KNN_LAUNCH_M(5, 0, 3);
-        else if (mixM == 3 && mixC == 4 && mixS == 1) ORBB_KNN_LAUNCH_M(4, 1, 3);
-        else if (mixC == 0 && mixS == 4) ORBB_KNN_LAUNCH(0, 4);
-        else if (mixC == 2 && mixS == 1) ORBB_KNN_LAUNCH(2, 1);
-        else if (mixC == 3 && mixS == 1) ORBB_KNN_LAUNCH(3, 1);
+        if (mixM == 3 && mixC == 3 && mixS == 0) ORBB_KNN_LAUNCH_M(3, 0, 3);          // production
+        else if (mixM == 3 && mixC == 4 && mixS == 0) ORBB_KNN_LAUNCH_M(4, 0, 3);     // A/B variants, each covered by tests/test_gpu_extract.py::test_every_shipped_switch_keeps_parity
+        else if (mixC == 0 && mixS == 4) ORBB_KNN_LAUNCH(0, 4);                        // no carry-save compression: 8 POPC per pair
         else if (mixC == 2 && mixS == 2) ORBB_KNN_LAUNCH(2, 2);
-        else if (mixC == 4 && mixS == 2) ORBB_KNN_LAUNCH(4, 2);
-        else if (mixC == 3 && mixS == 0) ORBB_KNN_LAUNCH(3, 0);
-        else if (mixC == 4 && mixS == 0) ORBB_KNN_LAUNCH(4, 0);
         else return m_err(m, ORBB_ERR_ARG, "unsupported ORBB_KNN_MIX=%d,%d", mixC, mixS);
 #undef ORBB_KNN_LAUNCH
 #undef ORBB_KNN_LAUNCH_M
@@ -884,10 +892,7 @@ int orbb_knn2_merge_dev(orbb_matcher* m, const int32_t* idx_sh_dev, const int32_
     if (!m || !idx_sh_dev || !dist_sh_dev || !idx2_dev || !dist2_dev || nshards < 1 || nq < 0) return m_err(m, ORBB_ERR_ARG, "bad argument");
     if (nq == 0) return ORBB_OK;
     ORBM_CUDA(m, cudaSetDevice(m->device));
-    k_knn2_merge_shards<<<(nq + 255) / 256, 256, 0, m->stream>>>(idx_sh_dev, dist_sh_dev, nshards, nq, idx2_dev, dist2_dev);
-    m->launches++;
-    ORBM_CUDA(m, cudaGetLastError());
-    return ORBB_OK;
+    return launch_merge_shards(m, idx_sh_dev, dist_sh_dev, (size_t)nq * 2, nshards, nq, idx2_dev, dist2_dev);
 }
 
 int orbb_ratio_test_dev(orbb_matcher* m, const int32_t* idx2_dev, const int32_t* dist2_dev, int nq, double ratio, uint8_t* keep_dev) {
@@ -902,10 +907,17 @@ int orbb_ratio_test_dev(orbb_matcher* m, const int32_t* idx2_dev, const int32_t*
 
 int orbb_best2_csr(orbb_matcher* m, const uint8_t* q, int nq, const uint8_t* train, int ntrain, const int32_t* cand,
                    const int32_t* rowptr, int init, int32_t* out4) {
-    if (!m || !rowptr || !out4 || nq < 0 || ntrain < 0) return m_err(m, ORBB_ERR_ARG, "bad argument");
+    if (!m || !rowptr || !out4 || nq < 0 || ntrain < 0 || (nq > 0 && !q)) return m_err(m, ORBB_ERR_ARG, "bad argument");
     if (nq == 0) return ORBB_OK;
-    ORBM_CUDA(m, cudaSetDevice(m->device));
+    // the arrays are host-resident: a bad candidate index would become an out-of-bounds device read that poisons the CUDA context
+    if (rowptr[0] != 0) return m_err(m, ORBB_ERR_ARG, "rowptr[0] must be 0");
+    for (int i = 0; i < nq; i++)
+        if (rowptr[i + 1] < rowptr[i]) return m_err(m, ORBB_ERR_ARG, "rowptr decreases at query %d", i);
     const int ncand = rowptr[nq];
+    if (ncand > 0 && (!cand || !train)) return m_err(m, ORBB_ERR_ARG, "candidate lists without cand / train arrays");
+    for (int i = 0; i < ncand; i++)
+        if (cand[i] < 0 || cand[i] >= ntrain) return m_err(m, ORBB_ERR_ARG, "candidate %d = %d outside [0, %d)", i, cand[i], ntrain);
+    ORBM_CUDA(m, cudaSetDevice(m->device));
     const size_t bq = (size_t)nq * 32, bt = std::max<size_t>((size_t)ntrain * 32, 32), bc = std::max<size_t>((size_t)ncand * 4, 4);
     const size_t br = (size_t)(nq + 1) * 4, bo = (size_t)nq * 16;
     int rc;
@@ -929,7 +941,8 @@ int orbb_best2_csr(orbb_matcher* m, const uint8_t* q, int nq, const uint8_t* tra
 int orbb_search_area_best2(orbb_matcher* m, const float* kps_xy, const int32_t* octaves, const uint8_t* train, int n, const float* grid4,
                            const float* queries, const int32_t* qlev, const uint8_t* qdesc, int nq, const uint8_t* skip, const float* u_right,
                            int init, int32_t* out4) {
-    if (!m || !grid4 || !out4 || n < 0 || nq < 0) return m_err(m, ORBB_ERR_ARG, "bad argument");
+    if (!m || !grid4 || !out4 || n < 0 || nq < 0 || (n > 0 && (!kps_xy || !octaves || !train)) || (nq > 0 && (!queries || !qlev || !qdesc)))
+        return m_err(m, ORBB_ERR_ARG, "bad argument");
     if (nq == 0) return ORBB_OK;
     if (n >= (1 << 20)) return m_err(m, ORBB_ERR_UNSUPPORTED, "more than 2^20 keypoints per frame");
     ORBM_CUDA(m, cudaSetDevice(m->device));
@@ -1060,6 +1073,13 @@ int orbb_stereo_match_batch(orbb_extractor* hL, orbb_extractor* hR, int nframes,
     k_stereo_cut<<<nframes, 256, 0, hL->stream>>>(hL->dPlan, hL->b);
     hL->launches += 2;
     ORBB_CUDA(hL, cudaGetLastError());
+    // ... and the right extractor's next batch waits for the stereo kernels, which read ITS pyramid, key points, descriptors and
+    // row buckets on the left stream (orbb_extract_batch is asynchronous: without this the next right-image extraction could
+    // overwrite them under the running stereo kernels)
+    ORBB_CUDA(hL, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    ORBB_CUDA(hL, cudaEventRecord(ev, hL->stream));
+    ORBB_CUDA(hL, cudaStreamWaitEvent(hR->stream, ev, 0));
+    ORBB_CUDA(hL, cudaEventDestroy(ev));
     return ORBB_OK;
 }
 

@@ -8,7 +8,8 @@
 //                    row at scale 1.2): three aligned word loads cover the <= 9 source bytes of the four columns, the two
 //                    taps of a column come out of them with one funnel shift, the tap sum is one IDP.2A
 //                    (u16 coefficients x u8 pixels).  The vertical pass is two IMAD.HI per pixel.
-//   k_pyr_apron16    reflect-101 apron of every level: one thread per 16-byte chunk that touches the apron.
+//   k_pyr_apron16    reflect-101 apron of every level: one thread per 16-byte chunk that touches the apron (on demand only: when
+//                    the pyramid is handed out as mvImagePyramid; no kernel of the pipeline reads the apron).
 //
 // The generic k_pyr_resize (orbb_extract.cu) stays as the fallback for larger scale steps.
 #pragma once
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(PR_THREADS, 12) k_pyr_resize_t(const Plan* __r
 // image words (one PRMT); words inside the image are copied; only the words that straddle the right edge go byte by byte.
 struct ApronTable { int base[ORBB_MAX_LEVELS + 1]; };        // first item of every level (kernel parameter: constant bank)
 
-__global__ void __launch_bounds__(256) k_pyr_apron16(const Plan* __restrict__ P, Bufs B, const ApronTable T, int nlevels, int thin) {
+__global__ void __launch_bounds__(256) k_pyr_apron16(const Plan* __restrict__ P, Bufs B, const ApronTable T, int nlevels) {
     int item = blockIdx.x * 256 + threadIdx.x;
     if (item >= T.base[nlevels]) return;
     const int frame = blockIdx.y;
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(256) k_pyr_apron16(const Plan* __restrict__ P,
 #pragma unroll
     for (int l = 1; l < ORBB_MAX_LEVELS; l++) level += (l < nlevels && item >= T.base[l]);
     const LevelPlan& L = P->lv[level];
-    const ApronLevel A = thin ? P->apronThin[level] : P->apron[level];
+    const ApronLevel A = P->apron[level];
     const int w = L.w, h = L.h, pitch = L.pitch;
     item -= A.itemBase;
     // three item classes per level, each row-major (coalesced) and each taking ONE path below in all lanes of a warp:

@@ -74,6 +74,30 @@ class ORBmatcher:
         capi.check(self._lib.orbb_knn2_dev(self._m, capi.ptr(q_dev), nq, capi.ptr(db_dev), nd, index_base, capi.ptr(idx_dev),
                                            capi.ptr(dist_dev)), self._m, matcher=True)
 
+    # ---- the same against a database sharded over the ranks of an NCCL communicator (BASELINE config 4) ----
+    def nccl_comm_create(self, nranks, rank, unique_id):
+        """ncclCommInitRank through the library (it binds the process's libnccl at run time); unique_id = 128 bytes from
+        nccl_unique_id() on one rank, handed to the others by any means (torch.distributed broadcast, a file, MPI ...)"""
+        comm = C.c_void_p()
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        capi.check(self._lib.orbb_nccl_comm_create(self.device, nranks, rank, buf, C.byref(comm)))
+        return comm
+
+    @staticmethod
+    def nccl_unique_id():
+        buf = (C.c_char * 128)()
+        capi.check(capi.load().orbb_nccl_unique_id(buf))
+        return bytes(buf)
+
+    def nccl_comm_destroy(self, comm):
+        self._lib.orbb_nccl_comm_destroy(comm)
+
+    def knn2_sharded_device(self, comm, q_dev, nq, db_shard_dev, nd_shard, index_base, idx_dev, dist_dev):
+        """every rank: all queries x its database shard -> ONE packed all-gather of the per-shard top-2 -> device merge;
+        idx_dev / dist_dev [nq,2] hold the global result on every rank (asynchronous on the matcher's stream)"""
+        capi.check(self._lib.orbb_knn2_sharded(self._m, comm, capi.ptr(q_dev), nq, capi.ptr(db_shard_dev), nd_shard, index_base,
+                                               capi.ptr(idx_dev), capi.ptr(dist_dev)), self._m, matcher=True)
+
     def merge_shards_device(self, idx_sh_dev, dist_sh_dev, nshards, nq, idx_dev, dist_dev):
         capi.check(self._lib.orbb_knn2_merge_dev(self._m, capi.ptr(idx_sh_dev), capi.ptr(dist_sh_dev), nshards, nq,
                                                  capi.ptr(idx_dev), capi.ptr(dist_dev)), self._m, matcher=True)

@@ -80,16 +80,18 @@ def frame(h, w, index=0, base_seed=BASE_SEED):
     return np.clip(np.rint(texture(h, w, base_seed + index)), 0, 255).astype(np.uint8)
 
 
-def sequence(h, w, n, base_seed=BASE_SEED, canvas=2048):
-    """n frames produced as a slowly translating crop of one big texture (TUM-like sequence)."""
+def sequence(h, w, n, base_seed=BASE_SEED, canvas=2048, start=0, stop=None):
+    """n frames produced as a slowly translating crop of one big texture (TUM-like sequence); start / stop select the frames
+    [start, stop) of that n-frame sequence (a rank's contiguous block of a frame-partitioned sequence)."""
     big = np.clip(np.rint(texture(canvas, canvas, base_seed)), 0, 255).astype(np.uint8)
-    out = np.empty((n, h, w), np.uint8)
+    stop = n if stop is None else stop
+    out = np.empty((stop - start, h, w), np.uint8)
     span_x, span_y = canvas - w, canvas - h
-    for i in range(n):
+    for i in range(start, stop):
         t = i / max(n - 1, 1)
         ox = int(round((0.5 + 0.5 * np.sin(2 * np.pi * t)) * span_x))
         oy = int(round((0.5 + 0.5 * np.cos(2 * np.pi * 0.5 * t)) * span_y))
-        out[i] = big[oy:oy + h, ox:ox + w]
+        out[i - start] = big[oy:oy + h, ox:ox + w]
     return out
 
 

@@ -186,7 +186,7 @@ def test_batch_equals_single_and_host_equals_device_path():
 
 
 def test_full_size_batch_properties():
-    """BASELINE-size batch (256 x 752x480): size-independent properties + spot checks against the oracle."""
+    """BASELINE-size batch (256 x 752x480): size-independent properties, and ALL 256 frames against the oracle."""
     import torch
     B = 256
     frames = synth.sequence(480, 752, B)
@@ -207,10 +207,13 @@ def test_full_size_batch_properties():
         per =np.bincount(k["octave"], minlength=8)
         assert (per <= npl + 2).all()
         assert ((k["angle"] >= 0) & (k["angle"] < 360)).all()
-    for f in (0, 97, 255):
-        rc, k0, d0, m0 = port.PortExtractor().extract(frames[f], (0, 1000))
+    # every frame of the batch against the oracle port (all host threads)
+    import os
+    c0, k0, d0 = port.extract_batch(frames, lapping=(0, 1000), nthreads=max(1, os.cpu_count() or 1))
+    assert np.array_equal(c0, c1)
+    for f in range(B):
         n = c1[f, 0]
-        assert_same_features(k0, d0, m0, k1[f, :n], d1[f, :n], int(c1[f, 1]), f"frame {f}")
+        assert_same_features(k0[f, :n], d0[f, :n], int(c0[f, 1]), k1[f, :n], d1[f, :n], int(c1[f, 1]), f"frame {f}")
 
 
 def test_submit_wait_on_two_handles_equals_sync_call():
@@ -346,3 +349,93 @@ def test_two_extractors_on_two_threads():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_single_and_batch_calls_mixed_on_one_handle():
+    """the single-frame CUDA graph captures the staging pointer; a batch call that regrows the staging area must invalidate it:
+    single -> batch of 8 -> single on one handle, each checked against a fresh handle"""
+    NF = 8
+    frames = synth.sequence(240, 320, NF, canvas=512, base_seed=300)
+    img = synth.frame(240, 320, 77)
+    ge = ORBextractor(300, 1.2, 4, max_batch=NF)
+    want1 = ORBextractor(300, 1.2, 4)(img, None, (0, 0))
+    wantB = ORBextractor(300, 1.2, 4, max_batch=NF).extract_batch_host(frames, (0, 0))
+    for step in range(2):
+        m1, k1, d1 = ge(img, None, (0, 0))
+        assert m1 == want1[0] and np.array_equal(k1, want1[1]) and np.array_equal(d1, want1[2]), f"single, round {step}"
+        c, k, d = ge.extract_batch_host(frames, (0, 0))
+        assert np.array_equal(c, wantB[0])
+        for f in range(NF):
+            n = c[f, 0]
+            assert np.array_equal(k[f, :n], wantB[1][f, :n]) and np.array_equal(d[f, :n], wantB[2][f, :n]), f"batch frame {f}, round {step}"
+    m1, k1, d1 = ge(img, None, (0, 0))
+    assert m1 == want1[0] and np.array_equal(k1, want1[1]) and np.array_equal(d1, want1[2])
+
+
+@pytest.mark.parametrize("ini,mn", [(140, 130), (200, 128), (130, 20), (20, 1), (3, 0)])
+def test_extreme_fast_thresholds(ini, mn):
+    """thresholds >= 128 take the exact byte compare of the quick reject; minThFAST 0/1 exercise the dark-polarity bookkeeping of
+    the packed score network (a corner whose best arc minimum is 1 has response 0 and can never survive NMS)"""
+    rng = np.random.default_rng(ini * 7 + mn)
+    img = rng.integers(0, 256, (160, 224), dtype=np.uint8)
+    img[40:90, 60:140] = 0
+    img[100:130, 30:200] = 255
+    check_against_port(img, 300, 3, ini=ini, mn=mn)
+
+
+_SWITCH_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, {root!r})
+from oracle import port
+from orb_slam3_ros_b200 import synth
+from orb_slam3_ros_b200.extractor import ORBextractor
+import torch
+def same(a, b):
+    return len(a[1]) == len(b[1]) and all(np.array_equal(a[1][f], b[1][f]) for f in ("x", "y", "size", "response", "octave")) and \
+        np.abs(a[1]["angle"] - b[1]["angle"]).max() <= 1e-3 and np.unpackbits(a[2] ^ b[2]).sum() <= 1e-4 * a[2].size * 8
+img = synth.frame(300, 417, 3)
+ge = ORBextractor(600, 1.2, 6)
+m1, k1, d1 = ge(img, None, (0, 1000))
+rc, k0, d0, m0 = port.PortExtractor(600, 1.2, 6).extract(img, (0, 1000))
+assert m0 == m1 and same((m0, k0, d0), (m1, k1, d1)), "single frame"
+pe = port.PortExtractor(600, 1.2, 6); pe.extract(img, (0, 1000))
+for l in range(6):
+    assert np.array_equal(pe.level(l, bordered=True), ge.debug_level(0, l, bordered=True)), l
+    assert np.array_equal(pe.raw_keys(l), ge.debug_raw_keys(0, l)), l
+NF = 40
+frames = synth.sequence(240, 320, NF, canvas=512, base_seed=11)
+gb = ORBextractor(300, 1.2, 4, max_batch=NF)
+c, k, d = gb.extract_batch_host(frames, (0, 0))
+c0, k0, d0 = port.extract_batch(frames, 300, 1.2, 4, lapping=(0, 0), nthreads=4)
+assert np.array_equal(c, c0)
+for f in range(NF):
+    n = c[f, 0]
+    assert same((0, k0[f, :n], d0[f, :n]), (0, k[f, :n], d[f, :n])), f
+gb.extract_batch_device(torch.from_numpy(frames).cuda(), NF, 320, 240)
+c2, k2, d2 = gb.fetch(NF)
+assert np.array_equal(c2, c) and all(np.array_equal(k2[f, :c[f, 0]], k[f, :c[f, 0]]) for f in range(NF))
+from orb_slam3_ros_b200.matcher import ORBmatcher
+db, q = synth.descriptor_db(6000, 700, seed=3)
+i1, dd1 = ORBmatcher().knn2(q, db)
+i0, dd0 = port.knn2(q, db)
+assert np.array_equal(i1, i0) and np.array_equal(dd1, dd0)
+print("SWITCH-OK")
+"""
+
+
+@pytest.mark.parametrize("env", [
+    {"ORBB_FAST_NO_TMAP": "1"}, {"ORBB_RESIZE_NO_TMA": "1"}, {"ORBB_RESIZE_NO_PRMT": "1"}, {"ORBB_NO_GRAPH": "1"},
+    {"ORBB_LANES": "2"}, {"ORBB_CHUNKS": "4"}, {"ORBB_PYR_LATENCY_FRAMES": "0", "ORBB_OCTREE_LATENCY_FRAMES": "0"},
+    {"ORBB_KNN_MIX": "2,2"}, {"ORBB_KNN_MIX": "4,0,3"}, {"ORBB_KNN_MIX": "0,4"},
+], ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
+def test_every_shipped_switch_keeps_parity(env):
+    """the A/B environment switches of DESIGN.md section 5 select alternative kernels / launch shapes; they are read once per
+    process, so each setting runs the same parity script (single frame incl. pyramid and raw FAST keys, a 40-frame host batch, the
+    device batch, a 2-NN scan -- all against the oracle) in its own interpreter"""
+    import os
+    import subprocess
+    import sys
+    root = str(Path(__file__).resolve().parent.parent)
+    r = subprocess.run([sys.executable, "-c", _SWITCH_SCRIPT.format(root=root)], env={**os.environ, **env}, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "SWITCH-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

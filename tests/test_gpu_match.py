@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import port
-from orb_slam3_ros_b200 import synth
+from orb_slam3_ros_b200 import capi, synth
 from orb_slam3_ros_b200.extractor import ORBextractor, compute_stereo_matches, stereo_fetch, stereo_match_batch
 from orb_slam3_ros_b200.matcher import INT_MAX, ORBmatcher
 
@@ -187,8 +187,9 @@ def test_knn2_full_size_properties(matcher):
     eq = dst[:, 0] == dst[:, 1]
     assert (idx[eq, 0] < idx[eq, 1]).all()
     # exact scan of a sample on the CPU oracle
-    pick = np.r_[np.arange(0, nq // 2, 12500), np.arange(nq // 2, nq, 25000)]
-    i0, d0 = port.knn2(q[pick], db, nthreads=8)
+    import os
+    pick = np.r_[np.arange(0, nq // 2, 80), np.arange(nq // 2, nq, 100)]          # 2 250 queries: planted and random halves
+    i0, d0 = port.knn2(q[pick], db, nthreads=max(1, os.cpu_count() or 1))
     assert np.array_equal(idx[pick], i0) and np.array_equal(dst[pick], d0)
 
 
@@ -247,3 +248,25 @@ def test_rotation_check_matches_oracle(matcher):
     for (a, b), (keep, ind) in zip(sets, got):
         want_keep, want_ind = port.rotation_check(a, b)
         assert ind == want_ind and np.array_equal(keep, want_keep)
+
+
+def test_best2_csr_rejects_bad_candidate_lists():
+    """host-side validation (the arrays are host-resident): a candidate index outside the train set or a non-monotonic rowptr is
+    an argument error, not an out-of-bounds device read"""
+    import ctypes as C
+    lib = capi.load()
+    m = ORBmatcher()
+    rng = np.random.default_rng(0)
+    q = rng.integers(0, 256, (4, 32), dtype=np.uint8)
+    tr = rng.integers(0, 256, (10, 32), dtype=np.uint8)
+    out = np.zeros((4, 4), np.int32)
+    good_row = np.array([0, 2, 2, 5, 6], np.int32)
+    for cand, rowptr in [(np.array([0, 1, 2, 3, 10, 5], np.int32), good_row),        # 10 >= ntrain
+                         (np.array([0, 1, -1, 3, 4, 5], np.int32), good_row),
+                         (np.array([0, 1, 2, 3, 4, 5], np.int32), np.array([0, 3, 2, 5, 6], np.int32)),
+                         (np.array([0, 1, 2, 3, 4, 5], np.int32), np.array([1, 2, 2, 5, 6], np.int32))]:
+        rc = lib.orbb_best2_csr(m._m, capi.ptr(q), 4, capi.ptr(tr), 10, capi.ptr(cand), capi.ptr(rowptr), 256, capi.ptr(out))
+        assert rc == capi.ORBB_ERR_ARG
+    cand = np.array([0, 1, 2, 3, 9, 5], np.int32)
+    assert lib.orbb_best2_csr(m._m, capi.ptr(q), 4, capi.ptr(tr), 10, capi.ptr(cand), capi.ptr(good_row), 256, capi.ptr(out)) == 0
+    assert np.array_equal(out, port.best2_csr(q, tr, cand, good_row, 256))

@@ -104,3 +104,19 @@ def test_port_rejects_degenerate_pyramids_without_work():
     asserts dsize.area() > 0 in the reference; the port must say "unsupported" at once, not loop"""
     assert port.PortExtractor(90, 2.0, 10, 17, 16).extract(synth.frame(236, 192, 1))[0] == -2
     assert port.PortExtractor(100, 1.2, 8).extract(synth.frame(90, 120, 0))[0] == -2          # level 7 = 33x25: inside the FAST border
+
+
+def test_cv2_baseline_equals_port():
+    """oracle/cv2_baseline.py (bench.py's honest CPU baseline: the extractor's control flow over python-cv2's SIMD resize /
+    FAST / GaussianBlur + the port's C++ glue) gives bit for bit the port's result, so the two CPU arms time the same work"""
+    from oracle import cv2_baseline
+    for (h, w, nf, nl, lap, seed) in [(240, 320, 300, 4, (0, 1000), 1), (200, 333, 500, 5, (100, 220), 2), (480, 752, 1000, 8, (0, 0), 3)]:
+        img = synth.frame(h, w, seed)
+        rc0, k0, d0, m0 = port.PortExtractor(nf, 1.2, nl).extract(img, lap)
+        rc1, k1, d1, m1 = cv2_baseline.Cv2Extractor(nf, 1.2, nl).extract(img, lap)
+        assert rc0 == rc1 == 0 and m0 == m1 and len(k0) == len(k1)
+        for f in k0.dtype.names:
+            assert np.array_equal(k0[f], k1[f]), f
+        assert np.array_equal(d0, d1)
+    a, b = cv2_baseline.rates(synth.sequence(240, 320, 4, canvas=512), (300, 1.2, 4, 20, 7), processes=2)
+    assert a > 0 and b >= a * 0.5
