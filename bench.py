@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--stereo-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=32, help="frames in the bounded CPU sample")
+    ap.add_argument("--no-matcher-rows", action="store_true")
     ap.add_argument("--no-config3", action="store_true")
     ap.add_argument("--config3-frames", type=int, default=4096)
     ap.add_argument("--sustain-s", type=float, default=2.0, help="seconds of back-to-back resident extraction for the sustained figure")
@@ -230,6 +231,128 @@ def run_reference(a):
         "knn": knn,
     }
     _emit(line)
+
+
+def measure_matcher_rows(local, with_cpu):
+    """Per-call latency of the matcher rows through the C ABI (host arguments unless stated, copies inside the call) and the CPU time
+    of the same work.  One 752x480 frame with ~1000 key points is the frame side everywhere, as in the SLAM threads."""
+    import ctypes as C
+    import torch
+    from orb_slam3_ros_b200 import capi, synth
+    from orb_slam3_ros_b200.bow import Vocabulary, synthetic_vocabulary
+    from orb_slam3_ros_b200.extractor import ORBextractor
+    from orb_slam3_ros_b200.matcher import ORBmatcher
+    from orb_slam3_ros_b200.rectify import Rectifier
+    lib = capi.load()
+    rows = []
+    rng = np.random.default_rng(7)
+
+    def timeit(fn, reps=30, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps * 1e3
+
+    def cpu_time(fn, reps=3):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) / reps * 1e3
+
+    _p = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)
+    img = synth.frame(H_, W_, 8)
+    ext = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local)
+    _, k, d = ext(img, None, (0, 0))
+    n = len(k)
+    m = ORBmatcher(device=local)
+    kxy = np.ascontiguousarray(np.stack([k["x"], k["y"]], 1), np.float32)
+    octs = np.ascontiguousarray(k["octave"], np.int32)
+    grid4 = np.float32([0, 0, 64 / W_, 48 / H_])
+    # (1) Tracking::SearchLocalPoints: 1600 projected map points against the frame, grid lookup + best-4 scan in one launch
+    nmp = 1600
+    src = rng.integers(0, n, nmp)
+    lev = np.clip(k["octave"][src] + rng.integers(-1, 2, nmp), 0, NLEVELS - 1).astype(np.int32)
+    sf = ext.GetScaleFactors()
+    proj = np.stack([k["x"][src] + rng.normal(0, 2.5, nmp), k["y"][src] + rng.normal(0, 2.5, nmp), k["x"][src] - 20, np.full(nmp, 0.9)], 1).astype(np.float32)
+    queries = np.stack([proj[:, 0], proj[:, 1], np.float32(4.0) * sf[lev], proj[:, 2]], 1).astype(np.float32)
+    qlev = np.stack([lev - 1, lev], 1).astype(np.int32)
+    qdesc = d[src].copy()
+    skip = (rng.random(n) < 0.25).astype(np.uint8)
+    out = np.zeros((nmp, 4, 2), np.int32)
+    hv = capi.FrameView()
+    hv.kps_xy, hv.kps_stride, hv.octaves, hv.oct_stride, hv.desc, hv.u_right, hv.n, hv.on_device = kxy.ctypes.data, 8, octs.ctypes.data, 4, d.ctypes.data, None, n, 0
+    kp_dev, desc_dev, cnt_dev = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    capi.check(lib.orbb_batch_device_ptrs(ext._h, C.byref(kp_dev), C.byref(desc_dev), C.byref(cnt_dev)), ext._h)
+    ev = capi.FrameView()
+    ev.kps_xy, ev.kps_stride, ev.octaves, ev.oct_stride, ev.desc, ev.u_right, ev.n, ev.on_device = kp_dev.value, 24, kp_dev.value + 20, 24, desc_dev.value, None, n, 1
+
+    def scan(view):
+        capi.check(lib.orbb_search_area_topk(m._m, C.byref(view), _p(grid4), _p(queries), _p(qlev), _p(qdesc), nmp, _p(skip), 256, 4, _p(out)), m._m, matcher=True)
+    row = {"row": "SearchByProjection scan (Frame::GetFeaturesInArea + best/second scan, ORBmatcher.cc:77-120), 1600 map points x 1 frame",
+           "api": "orbb_search_area_topk k=4", "ms_host_frame": timeit(lambda: scan(hv)),
+           "ms_device_resident_frame": timeit(lambda: scan(ev)),
+           "frame_bytes_not_moved": int(n * (24 + 32)), "note": "device-resident = the extractor's own key point / descriptor buffers (orbb_batch_device_ptrs): "
+           "zero descriptor D2H / H2D; the query side (map-point descriptors + projections, 83 KB) goes up, 51 KB of candidates come back"}
+    if with_cpu:
+        from oracle import port, ref
+        if ref.available():
+            row["cpu_ms"] = cpu_time(lambda: ref.search_by_projection(kxy, octs, d, grid4, sf, proj, lev, qdesc, None, None, skip, 0.8, 1.0))
+            row["cpu_kind"] = "reference (ORBmatcher::SearchByProjection cut out of ORBmatcher.cc, one thread, incl. AssignFeaturesToGrid)"
+        else:
+            row["cpu_ms"] = cpu_time(lambda: port.search_area_best2(kxy, octs, d, grid4, queries, qlev, qdesc, skip, None, 256))
+            row["cpu_kind"] = "port"
+    rows.append(row)
+    # (2) best / second-best over candidate lists (SearchByBoW-shaped: 1000 queries x 30 candidates)
+    nq = 1000
+    q = d[rng.integers(0, n, nq)].copy()
+    rowptr = (np.arange(nq + 1) * 30).astype(np.int32)
+    cand = rng.integers(0, n, rowptr[-1]).astype(np.int32)
+    out4 = np.zeros((nq, 4), np.int32)
+    row = {"row": "best / second-best over candidate lists (ORBmatcher.cc:273-325), 1000 queries x 30 candidates", "api": "orbb_best2_csr / _dev",
+           "ms_host_frame": timeit(lambda: capi.check(lib.orbb_best2_csr(m._m, _p(q), nq, _p(d), n, _p(cand), _p(rowptr), 256, _p(out4)), m._m, matcher=True)),
+           "ms_device_resident_frame": timeit(lambda: capi.check(lib.orbb_best2_csr_dev(m._m, _p(q), nq, desc_dev, n, _p(cand), _p(rowptr), 256, _p(out4)), m._m, matcher=True)),
+           "hamming_pairs": int(rowptr[-1])}
+    if with_cpu:
+        row["cpu_ms"] = cpu_time(lambda: port.best2_csr(q, d, cand, rowptr, 256))
+        row["cpu_kind"] = "port (the reference's loop shape, one thread)"
+    rows.append(row)
+    # (3) Frame::ComputeBoW: k = 10, L = 5 synthetic vocabulary (the ORBvoc blob is not available offline), one frame's descriptors
+    vocab = synthetic_vocabulary(10, 5, seed=3)
+    V = Vocabulary(vocab, device=local)
+    row = {"row": "Frame::ComputeBoW (DBoW2 transform, Frame.cc:738-745), 10^5-word tree, ~1000 descriptors", "api": "orbb_bow_transform",
+           "ms_host_frame": timeit(lambda: V.transform([d], 4, 1)), "hamming_pairs": int(n * 10 * 5)}
+    if with_cpu:
+        row["cpu_ms"] = cpu_time(lambda: port.bow_transform(vocab, d, 4, 1))
+        row["cpu_kind"] = "port (std::map restatement of TemplatedVocabulary::transform)"
+    rows.append(row)
+    # (4) MapPoint::ComputeDistinctiveDescriptors for 2000 map points with 8 observations each
+    ng = 2000
+    gd = d[rng.integers(0, n, ng * 8)].copy()
+    grp = (np.arange(ng + 1) * 8).astype(np.int32)
+    row = {"row": "MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:329-403), 2000 points x 8 observations", "api": "orbb_distinctive_csr",
+           "ms_host_frame": timeit(lambda: m.distinctive(gd, grp)), "hamming_pairs": int(ng * 64)}
+    if with_cpu:
+        row["cpu_ms"] = cpu_time(lambda: port.distinctive(gd, grp))
+        row["cpu_kind"] = "port"
+    rows.append(row)
+    # (5) stereo rectification: cv::remap of one 752x480 frame (System.cc:233-240)
+    yy, xx = np.mgrid[0:H_, 0:W_].astype(np.float32)
+    mx = (xx + 3.0 * np.sin(yy / 57.0)).astype(np.float32)
+    my = (yy + 2.0 * np.cos(xx / 91.0)).astype(np.float32)
+    R = Rectifier(mx, my, (H_, W_), device=local)
+    row = {"row": "cv::remap rectification of one 752x480 frame (System.cc:233-240)", "api": "orbb_remap (host image in, host image out)",
+           "ms_host_frame": timeit(lambda: R.remap(img)), "bytes": int(2 * W_ * H_ + 8 * W_ * H_)}
+    if with_cpu:
+        import cv2
+        row["cpu_ms"] = cpu_time(lambda: cv2.remap(img, mx, my, cv2.INTER_LINEAR))
+        row["cpu_kind"] = "cv2.remap (OpenCV SIMD)"
+    rows.append(row)
+    return rows
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -656,6 +779,12 @@ def run_ours(a):
                    "keypoints_per_frame_rank0": nkp3 / max(n3, 1),
                    "parallelism": f"contiguous blocks of {n3} frames per rank, no collective"}
         del ex3, d_seq, h_seq
+    # ---- the matcher / "next" rows (M2, f1-f4): per-call latency through the C ABI with the CPU figure of the same
+    # work beside it (the reference's own cut-out functions where they exist in oracle/_ref, else the oracle port; one thread, as the
+    # reference runs them) ----
+    matcher_rows = None
+    if rank == 0 and world == 1 and not a.no_matcher_rows:
+        matcher_rows = measure_matcher_rows(local, not a.no_cpu_baseline)
     clk = clocks.stop()
 
     # ---- CPU baseline on the box's host cores (rank 0, N=1 only), bounded sample of the same workload ----
@@ -702,7 +831,7 @@ def run_ours(a):
                     "api": "orbb_extract_batch_host_submit/_wait on two alternating handles (pinned host frames -> keypoints+descriptors)",
                     "single_sync_call_frames_per_s": world * B * a.steps / e2e_sync_s},
             "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "knn": knn, "stereo": stereo, "config3": config3, "other_shapes": shapes, "clocks": clk,
+            "roofline": roofline, "cpu_baseline": cpu, "knn": knn, "stereo": stereo, "config3": config3, "matcher_rows": matcher_rows, "other_shapes": shapes, "clocks": clk,
         }
         _emit(line)
     if world > 1:

@@ -231,6 +231,36 @@ int orbb_search_area_best2(orbb_matcher* m, const float* kps_xy, const int32_t* 
                            const float* queries, const int32_t* qlev, const uint8_t* qdesc, int nq, const uint8_t* skip,
                            const float* u_right, int init, int32_t* out4);
 
+/* ---- the same scans with the FRAME side resident on the device ----------------------------------------------------------------
+ * A tracked frame's key points and descriptors are produced on the GPU by the extractor and read by every Search* call made on
+ * that frame; with a frame view they are uploaded at most once (orbb_frame_upload) or not at all (on_device = 1 with the
+ * extractor's own buffers from orbb_batch_device_ptrs: x, y at offset 0 and octave at offset 20 of the 24-byte orbb_keypoint
+ * records -- valid for frames without lens distortion, where Frame::mvKeysUn == mvKeys, Frame.cc:749-753).  The query side
+ * (map-point descriptors and projections: host state of the SLAM threads) goes up per call, the per-query result comes back. */
+#define ORBB_FRAME_SLOTS 4
+typedef struct orbb_frame_view {
+    const void* kps_xy;      /* key point i: float x, y at kps_xy + i * kps_stride      (Frame::mvKeysUn[i].pt) */
+    size_t kps_stride;       /* bytes, >= 8 */
+    const void* octaves;     /* key point i: int32 octave at octaves + i * oct_stride    (Frame::mvKeysUn[i].octave) */
+    size_t oct_stride;       /* bytes, >= 4 */
+    const uint8_t* desc;     /* n x 32                                                   (Frame::mDescriptors) */
+    const float* u_right;    /* n floats or NULL                                         (Frame::mvuRight) */
+    int32_t n;
+    int32_t on_device;       /* 1: the pointers above are device pointers; 0: host pointers (uploaded by the call) */
+} orbb_frame_view;
+/* copies a host-resident frame to the device once (slot 0 .. ORBB_FRAME_SLOTS-1 of the matcher; a slot is overwritten by the next
+ * upload into it) and returns the device view to pass to the scans below; asynchronous on the matcher's stream */
+int orbb_frame_upload(orbb_matcher* m, int slot, const orbb_frame_view* host, orbb_frame_view* dev);
+/* orbb_search_area_best2 generalised: the k (1, 2, 4 or 8) best candidates of every query in the reference's scan order (distance,
+ * then cell column, cell row, key point index), out = nq x k x {dist, idx} (missing entries = {init, -1}).  k = 4 lets the host apply
+ * the reference's in-order decisions (a key point matched by an earlier map point of the call is skipped by the later ones,
+ * ORBmatcher.cc:88-90, :1749-1751) without another scan: dropping taken candidates from the sorted list leaves the same first two. */
+int orbb_search_area_topk(orbb_matcher* m, const orbb_frame_view* frame, const float* grid4, const float* queries, const int32_t* qlev,
+                          const uint8_t* qdesc, int nq, const uint8_t* skip, int init, int k, int32_t* out);
+/* orbb_best2_csr with the train descriptors (Frame::mDescriptors) already on the device */
+int orbb_best2_csr_dev(orbb_matcher* m, const uint8_t* q, int nq, const uint8_t* train_dev, int ntrain, const int32_t* cand,
+                       const int32_t* rowptr, int init, int32_t* out4);
+
 /* MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:329-403) for many map points at once: group g holds the
  * descriptors desc[rowptr[g] .. rowptr[g+1]) (32 bytes each, host memory); best[g] = index within the group of the
  * descriptor with the least median Hamming distance to the others (first minimum), -1 for an empty group. */

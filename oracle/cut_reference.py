@@ -28,6 +28,8 @@ PIECES = [
      r"^\s*int ORBmatcher::SearchByProjection\(Frame &F, const vector<MapPoint\*> &vpMapPoints, const float th, const bool bFarPoints", "function"),
     ("ORBmatcher_SearchByBoW_KF_F", "src/ORBmatcher.cc",
      r"^\s*int ORBmatcher::SearchByBoW\(KeyFrame\* pKF,Frame &F, vector<MapPoint\*> &vpMapPointMatches\)", "function"),
+    ("ORBmatcher_SearchByProjection_motion", "src/ORBmatcher.cc",
+     r"^\s*int ORBmatcher::SearchByProjection\(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono\)", "function"),
     ("MapPoint_ComputeDistinctiveDescriptors", "src/MapPoint.cc", r"^void MapPoint::ComputeDistinctiveDescriptors\(\)", "function"),
 ]
 

@@ -1,0 +1,57 @@
+// ORACLE / TEST INFRASTRUCTURE (not product code): the handful of Eigen / Sophus declarations that the motion-model
+// ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) (reference orb_slam3/src/ORBmatcher.cc:1676-1887) touches --
+// Eigen::Vector2f / Vector3f with operator()(int), Sophus::SE3f with inverse(), translation() and operator*(Vector3f).  Neither
+// library exists in this image.  The geometry is host code on both sides of the comparison (the reference's cut-out body in
+// oracle/_ref and the GPU-backed replacement in tests/host/ are compiled against THIS header with the same flags), so the floats
+// they feed into the candidate scan are identical; what is compared is the scan and its decisions.
+#pragma once
+
+namespace Eigen {
+struct Vector2f {
+    float v[2] = {0, 0};
+    Vector2f() {}
+    Vector2f(float a, float b) { v[0] = a; v[1] = b; }
+    float& operator()(int i) { return v[i]; }
+    float operator()(int i) const { return v[i]; }
+};
+struct Vector3f {
+    float v[3] = {0, 0, 0};
+    Vector3f() {}
+    Vector3f(float a, float b, float c) { v[0] = a; v[1] = b; v[2] = c; }
+    float& operator()(int i) { return v[i]; }
+    float operator()(int i) const { return v[i]; }
+};
+}  // namespace Eigen
+
+namespace Sophus {
+template <class T>
+class SE3 {                     // rotation matrix (row major) + translation: x -> R x + t
+public:
+    T R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    T t[3] = {0, 0, 0};
+    SE3() {}
+    SE3(const T* r9, const T* t3) { for (int i = 0; i < 9; i++) R[i] = r9[i]; for (int i = 0; i < 3; i++) t[i] = t3[i]; }
+    SE3 inverse() const {       // (R^T, -R^T t)
+        SE3 o;
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) o.R[3 * i + j] = R[3 * j + i];
+        for (int i = 0; i < 3; i++) o.t[i] = -(o.R[3 * i] * t[0] + o.R[3 * i + 1] * t[1] + o.R[3 * i + 2] * t[2]);
+        return o;
+    }
+    Eigen::Vector3f translation() const { return Eigen::Vector3f(t[0], t[1], t[2]); }
+    Eigen::Vector3f operator*(const Eigen::Vector3f& p) const {
+        return Eigen::Vector3f(R[0] * p(0) + R[1] * p(1) + R[2] * p(2) + t[0], R[3] * p(0) + R[4] * p(1) + R[5] * p(2) + t[1],
+                               R[6] * p(0) + R[7] * p(1) + R[8] * p(2) + t[2]);
+    }
+};
+typedef SE3<float> SE3f;
+}  // namespace Sophus
+
+namespace ORB_SLAM3 {
+class GeometricCamera {         // CameraModels/GeometricCamera.h:61-63: the one overload the cut function calls; pinhole (Pinhole.cpp:40-47)
+public:
+    float fx = 1, fy = 1, cx = 0, cy = 0;
+    virtual ~GeometricCamera() {}
+    virtual Eigen::Vector2f project(const Eigen::Vector3f& v3D) { return Eigen::Vector2f(fx * v3D(0) / v3D(2) + cx, fy * v3D(1) / v3D(2) + cy); }
+};
+}  // namespace ORB_SLAM3

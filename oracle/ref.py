@@ -300,6 +300,34 @@ def search_by_projection(kps_xy, octaves, train, grid4, scale_factors, proj, lev
     return nm, match_of
 
 
+def search_by_projection_motion(cur, last, th, mono, nnratio=0.9, check_orientation=True):
+    """ORBmatcher(nnratio, checkOri).SearchByProjection(CurrentFrame, LastFrame, th, bMono) (ORBmatcher.cc:1676-1887, reference text;
+    the call of Tracking::TrackWithMotionModel) for frames with Nleft == -1.
+      cur:  dict(kps_xy [n,2], octaves, angles, desc [n,32], u_right (or None), state [n] (0 no map point / 1 one with observations /
+            2 one without), fp = (mnMinX, mnMaxX, mnMinY, mnMaxY, gridWInv, gridHInv, mbf, mb), scale_factors, Tcw [12] = R row-major + t,
+            cam4 = (fx, fy, cx, cy))
+      last: dict(octaves, angles, state [m] (0 / 1 / 2 as above), outlier [m], pos [m,3], desc [m,32], Tlw [12])
+    -> (nmatches, match_of[n]: last-frame feature whose map point the key point received in this call, -1 otherwise)"""
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    k, o, a, d = f32(cur["kps_xy"]).reshape(-1, 2), i32(cur["octaves"]), f32(cur["angles"]), u8(cur["desc"])
+    n = len(k)
+    ur = None if cur.get("u_right") is None else f32(cur["u_right"])
+    cs, fp, sf, tcw, cam = u8(cur["state"]), f32(cur["fp"]), f32(cur["scale_factors"]), f32(cur["Tcw"]), f32(cur["cam4"])
+    lo, la, ls, lout = i32(last["octaves"]), f32(last["angles"]), u8(last["state"]), u8(last["outlier"])
+    lp, ld, tlw = f32(last["pos"]).reshape(-1, 3), u8(last["desc"]), f32(last["Tlw"])
+    match_of = np.full(n, -1, np.int32)
+    fn = lib().refcut_search_by_projection_motion
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 7 + \
+                  [C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    nm = fn(_ptr(k), _ptr(o), _ptr(a), _ptr(d), n, _ptr(fp), None if ur is None else _ptr(ur), _ptr(cs), _ptr(sf), len(sf), _ptr(tcw), _ptr(cam),
+            len(lo), _ptr(lo), _ptr(la), _ptr(ls), _ptr(lout), _ptr(lp), _ptr(ld), _ptr(tlw), th, int(mono), nnratio, int(check_orientation),
+            _ptr(match_of))
+    return nm, match_of
+
+
 def search_by_bow(kf_angle, kf_desc, kf_has_point, kf_fv, f_angle, f_desc, f_fv, nnratio=0.7, check_orientation=True):
     """ORBmatcher(nnratio, checkOri).SearchByBoW(pKF, F, vpMapPointMatches) (ORBmatcher.cc:223-421, reference text) for a monocular
     pair; kf_fv / f_fv = (node, start, feat) arrays of the two feature vectors (RefVocabulary.transform()[2:5] or the port's)

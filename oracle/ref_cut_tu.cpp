@@ -20,6 +20,8 @@
 //   ORBmatcher::ORBmatcher, RadiusByViewingCos    ORBmatcher.cc:39-41, :215-221
 //   ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints)   ORBmatcher.cc:43-213
 //   ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)   ORBmatcher.cc:223-421 (over the vendored DBoW2::FeatureVector)
+//   ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono)   ORBmatcher.cc:1676-1887 (the
+//       motion-model call of Tracking::TrackWithMotionModel, Tracking.cc:2925/:2933; Eigen / Sophus from cvshim/mini_geom.hpp)
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -33,6 +35,7 @@
 #include "DBoW2/BowVector.h"
 #include "DBoW2/FeatureVector.h"
 #include "ORBextractor.h"
+#include "mini_geom.hpp"
 
 #define FRAME_GRID_ROWS 48      // Frame.h:44
 #define FRAME_GRID_COLS 64      // Frame.h:45
@@ -44,7 +47,6 @@ namespace ORB_SLAM3 {
 class Frame;
 class KeyFrame;
 class MapPoint;
-class GeometricCamera;
 
 class ORBmatcher {              // ORBmatcher.h:38-106
 public:
@@ -53,6 +55,7 @@ public:
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
     int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3, const bool bFarPoints = false,
                            const float thFarPoints = 50.0f);
+    int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
     static const int TH_LOW;
     static const int TH_HIGH;
     static const int HISTO_LENGTH;
@@ -81,6 +84,8 @@ public:
     int Observations() { return nObs; }
     bool isBad() { return mbBad; }
     cv::Mat GetDescriptor() { return mDescriptor.clone(); }
+    Eigen::Vector3f GetWorldPos() { return mWorldPos; }
+    Eigen::Vector3f mWorldPos;
     float mTrackProjX = 0, mTrackProjY = 0, mTrackDepth = 0, mTrackDepthR = 0, mTrackProjXR = 0, mTrackProjYR = 0;
     bool mbTrackInView = false, mbTrackInViewR = false;
     int mnTrackScaleLevel = 0, mnTrackScaleLevelR = -1;
@@ -100,6 +105,11 @@ public:
     bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);
     vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1, const int maxLevel = -1,
                                      const bool bRight = false) const;
+
+    Sophus::SE3<float> GetPose() const { return mTcw; }            // Frame.h:144-147
+    Sophus::SE3f GetRelativePoseTrl() { return mTrl; }              // Frame.cc:1054
+    Sophus::SE3<float> mTcw, mTrl;
+    std::vector<bool> mvbOutlier;
 
     ORBextractor *mpORBextractorLeft = nullptr, *mpORBextractorRight = nullptr;
     float mbf = 0, mb = 0;
@@ -129,6 +139,7 @@ float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX
 #include "cut/ORBmatcher_SearchByProjection_local.inc"
 #include "cut/ORBmatcher_RadiusByViewingCos.inc"
 #include "cut/ORBmatcher_SearchByBoW_KF_F.inc"
+#include "cut/ORBmatcher_SearchByProjection_motion.inc"
 #include "cut/ORBmatcher_ComputeThreeMaxima.inc"
 #include "cut/ORBmatcher_DescriptorDistance.inc"
 #include "cut/Frame_AssignFeaturesToGrid.inc"
@@ -300,6 +311,70 @@ int refcut_search_by_projection(const float* kps, const int32_t* oct, const uint
         matchOf[i] = (p && p != &old) ? (int)(p - mps.data()) : -1;
     }
     delete F;
+    return nmatches;
+}
+
+// Tracking::TrackWithMotionModel's call: ORBmatcher(nnratio, checkOri).SearchByProjection(CurrentFrame, LastFrame, th, bMono) on
+// monocular / rectified-stereo / RGB-D frames (Nleft == -1).
+//   current frame: undistorted key points (x, y), octaves, angles, descriptors, mvuRight (or null), curState[i] = 0 no map point /
+//     1 a map point with observations / 2 a map point without (e.g. a temporal stereo point); fp = {mnMinX, mnMaxX, mnMinY, mnMaxY,
+//     mfGridElementWidthInv, mfGridElementHeightInv, mbf, mb}; pose Tcw = {R (9, row major), t (3)}; pinhole cam4 = {fx, fy, cx, cy}
+//   last frame: per feature its octave, angle, whether it holds a map point (lastState: 0 none / 1 with / 2 without observations),
+//     the outlier flag, the map point's world position and descriptor; pose Tlw
+// -> matchOf[i] = last-frame feature whose map point key point i holds after the call and did not hold before (-1 otherwise);
+//    returns nmatches.
+int refcut_search_by_projection_motion(const float* kps, const int32_t* oct, const float* angle, const uint8_t* desc, int n, const float* fp,
+                                       const float* uRight, const uint8_t* curState, const float* scaleFactors, int nlevels, const float* Tcw,
+                                       const float* cam4, int nLast, const int32_t* lastOct, const float* lastAngle, const uint8_t* lastState,
+                                       const uint8_t* lastOutlier, const float* lastPos, const uint8_t* lastDesc, const float* Tlw, float th,
+                                       int bMono, float nnratio, int checkOri, int32_t* matchOf) {
+    using namespace ORB_SLAM3;
+    Frame* C = new Frame();
+    Frame* L = new Frame();
+    Frame::mnMinX = fp[0]; Frame::mnMaxX = fp[1]; Frame::mnMinY = fp[2]; Frame::mnMaxY = fp[3];
+    Frame::mfGridElementWidthInv = fp[4]; Frame::mfGridElementHeightInv = fp[5];
+    GeometricCamera cam;
+    cam.fx = cam4[0]; cam.fy = cam4[1]; cam.cx = cam4[2]; cam.cy = cam4[3];
+    C->N = n; C->Nleft = -1; C->mbf = fp[6]; C->mb = fp[7]; C->mpCamera = &cam;
+    C->mTcw = Sophus::SE3f(Tcw, Tcw + 9);
+    C->mvKeysUn.resize(n);
+    for (int i = 0; i < n; i++) {
+        C->mvKeysUn[i].pt.x = kps[2 * i]; C->mvKeysUn[i].pt.y = kps[2 * i + 1]; C->mvKeysUn[i].octave = oct[i]; C->mvKeysUn[i].angle = angle[i];
+    }
+    C->mvKeys = C->mvKeysUn;
+    C->AssignFeaturesToGrid();
+    C->mDescriptors = to_descriptors(desc, n);
+    C->mvuRight.assign(n, -1.0f);
+    if (uRight) for (int i = 0; i < n; i++) C->mvuRight[i] = uRight[i];
+    C->mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    MapPoint oldObs, oldNoObs;                                         // what the current frame's key points hold before the call
+    oldObs.nObs = 1; oldNoObs.nObs = 0;
+    C->mvpMapPoints.assign(n, nullptr);
+    for (int i = 0; i < n; i++) if (curState && curState[i]) C->mvpMapPoints[i] = curState[i] == 1 ? &oldObs : &oldNoObs;
+    L->N = nLast; L->Nleft = -1; L->mTcw = Sophus::SE3f(Tlw, Tlw + 9);
+    L->mvKeysUn.resize(nLast);
+    std::vector<MapPoint> mps(nLast);
+    L->mvpMapPoints.assign(nLast, nullptr);
+    L->mvbOutlier.assign(nLast, false);
+    for (int j = 0; j < nLast; j++) {
+        L->mvKeysUn[j].octave = lastOct[j]; L->mvKeysUn[j].angle = lastAngle[j];
+        L->mvbOutlier[j] = lastOutlier[j] != 0;
+        if (lastState[j]) {
+            mps[j].nObs = lastState[j] == 1 ? 1 : 0;
+            mps[j].mWorldPos = Eigen::Vector3f(lastPos[3 * j], lastPos[3 * j + 1], lastPos[3 * j + 2]);
+            mps[j].mDescriptor = to_descriptors(lastDesc + (size_t)32 * j, 1);
+            L->mvpMapPoints[j] = &mps[j];
+        }
+    }
+    L->mvKeys = L->mvKeysUn;
+    ORBmatcher matcher(nnratio, checkOri != 0);
+    const int nmatches = matcher.SearchByProjection(*C, *L, th, bMono != 0);
+    for (int i = 0; i < n; i++) {
+        MapPoint* p = C->mvpMapPoints[i];
+        matchOf[i] = (p && p != &oldObs && p != &oldNoObs) ? (int)(p - mps.data()) : -1;
+    }
+    delete C;
+    delete L;
     return nmatches;
 }
 

@@ -31,6 +31,12 @@ class Params(C.Structure):
                 ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32), ("device", C.c_int32), ("max_batch", C.c_int32)]
 
 
+class FrameView(C.Structure):
+    """orbb_frame_view (include/orbb200.h): the frame side of the matcher scans, host- or device-resident"""
+    _fields_ = [("kps_xy", C.c_void_p), ("kps_stride", C.c_size_t), ("octaves", C.c_void_p), ("oct_stride", C.c_size_t),
+                ("desc", C.c_void_p), ("u_right", C.c_void_p), ("n", C.c_int32), ("on_device", C.c_int32)]
+
+
 # every symbol include/orbb200.h declares: (name, restype, argtypes)
 _VP, _I, _F, _SZ, _LL, _D = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong, C.c_double
 _PI = C.POINTER(C.c_int)
@@ -81,6 +87,9 @@ SYMBOLS = [
     ("orbb_ratio_test_dev", _I, [_VP, _VP, _VP, _I, _D, _VP]),
     ("orbb_best2_csr", _I, [_VP, _VP, _I, _VP, _I, _VP, _VP, _I, _VP]),
     ("orbb_search_area_best2", _I, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _VP]),
+    ("orbb_frame_upload", _I, [_VP, _I, _VP, _VP]),
+    ("orbb_search_area_topk", _I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _VP, _I, _I, _VP]),
+    ("orbb_best2_csr_dev", _I, [_VP, _VP, _I, _VP, _I, _VP, _VP, _I, _VP]),
     ("orbb_distinctive_csr", _I, [_VP, _VP, _I, _VP, _I, _VP]),
     ("orbb_vocab_create", _I, [_I, _I, _VP, _VP, _VP, _I, _VP, _VP, _VP, _I, C.POINTER(_VP)]),
     ("orbb_vocab_destroy", None, [_VP]),

@@ -97,6 +97,8 @@ __global__ void __launch_bounds__(256) k_pyr_resize(const Plan* __restrict__ P, 
     const int word = blockIdx.x * 32 + (threadIdx.x & 31);
     const int dy = blockIdx.y * 8 + (threadIdx.x >> 5);
     const int frame = blockIdx.z;
+    pdl_launch_dependents();
+    pdl_wait();
     if (word * 4 >= L.w || dy >= L.h) return;
     const uint8_t* sroi = B.pyr + (size_t)frame * P->pyrStride + S.roiOff;
     const int2 ty = __ldg(B.tab + L.tabY + dy);
@@ -561,6 +563,8 @@ __global__ void __launch_bounds__(OT_T) k_octree(const Plan* __restrict__ P, Buf
     const LevelPlan& L = P->lv[level];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = L.nFeat;
+    pdl_launch_dependents();
+    pdl_wait();
 
     const int* cellCount = B.cellCount + (size_t)frame * P->cellsTotal + L.cellBase;
     int* cellOff = B.cellOff + (size_t)frame * P->cellsTotal + L.cellBase;
@@ -1028,6 +1032,8 @@ __global__ void __launch_bounds__(OD_THREADS, 4) k_orient_desc32(const Plan* __r
     __shared__ __align__(16) unsigned sPatch[STAGE ? OD_THREADS / 32 : 1][2][STAGE ? OD_PATCH_WORDS + 2 : 1];
     const int frame = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_launch_dependents();
+    pdl_wait();
     const int n = B.outCount[frame * 2];
     const int g0 = (blockIdx.x * (OD_THREADS / 32) + warp) * OD_KPW;
     if (g0 >= n) return;
@@ -1486,6 +1492,18 @@ static Bufs shift_bufs(const Bufs& b, const Plan& P, int f0) {
     return s;
 }
 
+// kernel launch, optionally as a programmatic dependent of the previous kernel of the stream (see pdl_wait in orbb_internal.cuh)
+template <typename... KArgs, typename... Args>
+static void launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // the launch sequence for `nframes` device-resident frames whose buffers start at frame f0
 static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nframes, size_t rowStride, size_t frameStride, int lap0, int lap1,
                     int f0) {
@@ -1493,6 +1511,13 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
     const Bufs B = f0 ? shift_bufs(h->b, P, f0) : h->b;
     const orbb_extractor::Lane& ln = h->lanes[lane];
     cudaStream_t st = ln.st;
+    // ORBB_NO_PDL=1: every kernel waits for the full completion of its predecessor before it is scheduled (A/B switch).  Stage
+    // profiling records events between the kernels, and a capturing stream (single-frame graph) keeps plain edges.
+    static const bool noPdl = getenv("ORBB_NO_PDL") != nullptr;
+    const bool pdl = !noPdl && !h->profiling && !h->capturing;
+    // ORBB_BLUR_EARLY=1: the blur forks right after the pyramid (beside the detector) instead of after the detector (beside the quadtree)
+    static const bool blurEarly = getenv("ORBB_BLUR_EARLY") != nullptr;
+    const bool fork = !h->profiling;
     mark(h, ST_PYRAMID);
     ORBB_CUDA(h, cudaMemsetAsync(B.status, 0, sizeof(int) * nframes, st));
     for (int l = 0; l < P.nlevels; l++) {
@@ -1511,43 +1536,45 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
             const bool prmt = L.prmtTaps && !noPrmt;
             const dim3 gLat(grid.x, (L.h + rowsPerCtaLat - 1) / rowsPerCtaLat, nframes), gBat(grid.x, (L.h + rowsPerCta - 1) / rowsPerCta, nframes);
             if (tmaResize && L.fastResize == 2 && nframes <= pyrLatencyFrames) {
-                if (prmt) k_pyr_resize_t<PR_ROWS_LATENCY, true><<<gLat, PR_THREADS, 0, st>>>(h->dPlan, B, l);
-                else k_pyr_resize_t<PR_ROWS_LATENCY, false><<<gLat, PR_THREADS, 0, st>>>(h->dPlan, B, l);
+                if (prmt) launch_k(pdl, k_pyr_resize_t<PR_ROWS_LATENCY, true>, gLat, PR_THREADS, 0, st, h->dPlan, B, l);
+                else launch_k(pdl, k_pyr_resize_t<PR_ROWS_LATENCY, false>, gLat, PR_THREADS, 0, st, h->dPlan, B, l);
             } else if (tmaResize && L.fastResize == 2) {
-                if (prmt) k_pyr_resize_t<PR_ROWS, true><<<gBat, PR_THREADS, 0, st>>>(h->dPlan, B, l);
-                else k_pyr_resize_t<PR_ROWS, false><<<gBat, PR_THREADS, 0, st>>>(h->dPlan, B, l);
+                if (prmt) launch_k(pdl, k_pyr_resize_t<PR_ROWS, true>, gBat, PR_THREADS, 0, st, h->dPlan, B, l);
+                else launch_k(pdl, k_pyr_resize_t<PR_ROWS, false>, gBat, PR_THREADS, 0, st, h->dPlan, B, l);
             }
-            else k_pyr_resize_s<<<dim3(grid.x, (L.h + rowsPerCta - 1) / rowsPerCta, nframes), PR_THREADS, 0, st>>>(h->dPlan, B, l);
-        } else k_pyr_resize<<<grid, 256, 0, st>>>(h->dPlan, B, l);
+            else launch_k(pdl, k_pyr_resize_s, dim3(grid.x, (L.h + rowsPerCta - 1) / rowsPerCta, nframes), PR_THREADS, 0, st, h->dPlan, B, l);
+        } else launch_k(pdl, k_pyr_resize, grid, 256, 0, st, h->dPlan, B, l);
         h->launches++;
     }
-    const bool fork = !h->profiling;
+    if (fork && blurEarly) ORBB_CUDA(h, cudaEventRecord(ln.evFork, st));
     mark(h, ST_FAST);
     {   // ORBB_FAST_NO_TMAP=1: stage the cell tiles with one bulk copy per row instead of one tensor-map copy (A/B switch; also the
         // path taken when the driver cannot encode the tensor maps)
         static const bool noTmap = getenv("ORBB_FAST_NO_TMAP") != nullptr;
         const dim3 grid(P.cellsTotal, nframes);
+        const bool pdlFast = pdl && !(fork && blurEarly);      // (an event record between two kernels makes the edge a full dependency)
         if (h->tmapsValid && !noTmap) {
-            if (P.cellTp == 64) k_fast_cell<64, true><<<grid, 32, P.cellSmem, st>>>(h->dPlan, B, h->tmaps, f0);
-            else k_fast_cell<96, true><<<grid, 32, P.cellSmem, st>>>(h->dPlan, B, h->tmaps, f0);
+            if (P.cellTp == 64) launch_k(pdlFast, k_fast_cell<64, true>, grid, 32, P.cellSmem, st, h->dPlan, B, h->tmaps, f0);
+            else launch_k(pdlFast, k_fast_cell<96, true>, grid, 32, P.cellSmem, st, h->dPlan, B, h->tmaps, f0);
         } else {
-            if (P.cellTp == 64) k_fast_cell<64, false><<<grid, 32, P.cellSmem, st>>>(h->dPlan, B, h->tmaps, f0);
-            else k_fast_cell<96, false><<<grid, 32, P.cellSmem, st>>>(h->dPlan, B, h->tmaps, f0);
+            if (P.cellTp == 64) launch_k(pdlFast, k_fast_cell<64, false>, grid, 32, P.cellSmem, st, h->dPlan, B, h->tmaps, f0);
+            else launch_k(pdlFast, k_fast_cell<96, false>, grid, 32, P.cellSmem, st, h->dPlan, B, h->tmaps, f0);
         }
         h->launches++;
     }
     mark(h, ST_OCTREE);
     // fork: the blur only needs the pyramid; on its own stream it fills the SMs that the latency-bound quadtree leaves idle.
     // With stage profiling on, everything stays on one stream so that the stage events mean what they say.
-    if (fork) ORBB_CUDA(h, cudaEventRecord(ln.evFork, st));
+    if (fork && !blurEarly) ORBB_CUDA(h, cudaEventRecord(ln.evFork, st));
+    const bool pdlTree = pdl && (!fork || blurEarly);
     // images whose first level has many cells (4K class) get the large CTA on every level: more warps split nodes at once
     // 512 threads per (frame, level) for levels with many cells -- and for a call with a few frames, where the quadtree of
     // level 0 is one CTA on the critical path and a warp issues one dependent instruction every few cycles: more warps split
     // more nodes at once, and nodes with many keys are split by the whole CTA
     static const int otLatencyFrames = getenv("ORBB_OCTREE_LATENCY_FRAMES") ? atoi(getenv("ORBB_OCTREE_LATENCY_FRAMES")) : 4;
-    if (P.lv[0].nCols * P.lv[0].nRows >= OT_BIG_CELLS) k_octree<OT_THREADS_BIG><<<dim3(nframes, P.nlevels), OT_THREADS_BIG, 0, st>>>(h->dPlan, B, 0, OT_BIG_NODE);
-    else if (nframes <= otLatencyFrames) k_octree<OT_THREADS_BIG><<<dim3(nframes, P.nlevels), OT_THREADS_BIG, 0, st>>>(h->dPlan, B, 0, OT_BIG_NODE_LATENCY);
-    else k_octree<OT_THREADS><<<dim3(nframes, P.nlevels), OT_THREADS, 0, st>>>(h->dPlan, B, 0, OT_BIG_NODE);
+    if (P.lv[0].nCols * P.lv[0].nRows >= OT_BIG_CELLS) launch_k(pdlTree, k_octree<OT_THREADS_BIG>, dim3(nframes, P.nlevels), OT_THREADS_BIG, 0, st, h->dPlan, B, 0, (int)OT_BIG_NODE);
+    else if (nframes <= otLatencyFrames) launch_k(pdlTree, k_octree<OT_THREADS_BIG>, dim3(nframes, P.nlevels), OT_THREADS_BIG, 0, st, h->dPlan, B, 0, (int)OT_BIG_NODE_LATENCY);
+    else launch_k(pdlTree, k_octree<OT_THREADS>, dim3(nframes, P.nlevels), OT_THREADS, 0, st, h->dPlan, B, 0, (int)OT_BIG_NODE);
     if (fork) {
         ORBB_CUDA(h, cudaStreamWaitEvent(ln.blurSt, ln.evFork, 0));
         ORBB_CUDA(h, cudaStreamWaitEvent(ln.blurEdgeSt, ln.evFork, 0));
@@ -1570,8 +1597,8 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
     {   // ORBB_DESC_NO_STAGE=1: sample the blurred level through L1 instead of a shared-memory copy of the window (A/B switch)
         static const bool noStage = getenv("ORBB_DESC_NO_STAGE") != nullptr;
         const dim3 grid((P.kpCap + OD_THREADS / 32 * OD_KPW - 1) / (OD_THREADS / 32 * OD_KPW), nframes);
-        if (noStage) k_orient_desc32<false><<<grid, OD_THREADS, 0, st>>>(h->dPlan, B);
-        else k_orient_desc32<true><<<grid, OD_THREADS, 0, st>>>(h->dPlan, B);
+        if (noStage) launch_k(pdl, k_orient_desc32<false>, grid, OD_THREADS, 0, st, h->dPlan, B);
+        else launch_k(pdl, k_orient_desc32<true>, grid, OD_THREADS, 0, st, h->dPlan, B);
     }
     mark(h, ST_D2H);
     h->launches += 6;
@@ -1582,8 +1609,13 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
 // the launch sequence for `nframes` device-resident frames whose buffers start at frame f0: contiguous parts of the batch
 // go to the handle's lanes (all ordered after what is already queued on h->stream, and joined back into it)
 static int run_batch(orbb_extractor* h, const uint8_t* dImgs, int nframes, size_t rowStride, size_t frameStride, int lap0, int lap1,
-                     int f0 = 0) {
-    const int lanes = (h->profiling || nframes < 16 * h->nLanes) ? 1 : h->nLanes;
+                     int f0 = 0, bool hostChunk = false) {
+    // lanes: a resident batch of >= 64 frames per lane is split over the handle's lanes (2 by default: 1.329 -> 1.277 ms per 256
+    // frames, the latency-bound quadtree / descriptor kernels of one half run under the issue-bound detector of the other); the
+    // chunks of the host pipeline are already interleaved with their copies and stay on one lane unless ORBB_LANES_HOST=1
+    static const bool lanesHost = getenv("ORBB_LANES_HOST") != nullptr;
+    static const int lanesMin = getenv("ORBB_LANES_MIN") ? std::max(1, atoi(getenv("ORBB_LANES_MIN"))) : 64;      // frames per lane below which a batch is not split
+    const int lanes = (h->profiling || h->capturing || (hostChunk && !lanesHost) || nframes < lanesMin * h->nLanes) ? 1 : h->nLanes;
     if (lanes > 1) ORBB_CUDA(h, cudaEventRecord(h->lanes[0].evStart, h->stream));
     int done = 0;
     for (int l = 0; l < lanes; l++) {
@@ -1890,7 +1922,9 @@ int orbb_extract_batch_host_submit(orbb_extractor* h, const uint8_t* host_imgs, 
             cudaGraph_t graph = nullptr;
             const long long before = h->launches;
             ORBB_CUDA(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            h->capturing = true;
             rc = run_batch(h, h->hImg, 1, (size_t)width, fbytes, lap0, lap1, 0);
+            h->capturing = false;
             const cudaError_t ce = cudaStreamEndCapture(st, &graph);
             if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
             if (ce != cudaSuccess) return set_err(h, ORBB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
@@ -1941,7 +1975,7 @@ int orbb_extract_batch_host_submit(orbb_extractor* h, const uint8_t* host_imgs, 
         const int f0 = c * per, n = std::min(per, nframes - f0);
         if (n <= 0) break;
         ORBB_CUDA(h, cudaStreamWaitEvent(h->stream, h->evH2D[c], 0));
-        if ((rc = run_batch(h, h->hImg + f0 * fbytes, n, (size_t)width, fbytes, lap0, lap1, f0))) return rc;
+        if ((rc = run_batch(h, h->hImg + f0 * fbytes, n, (size_t)width, fbytes, lap0, lap1, f0, true))) return rc;
         ORBB_CUDA(h, cudaEventRecord(h->evDone[c], h->stream));
         ORBB_CUDA(h, cudaStreamWaitEvent(h->d2hStream, h->evDone[c], 0));
         ORBB_CUDA(h, cudaMemcpyAsync(h->hCounts + 2 * f0, h->b.outCount + 2 * f0, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, h->d2hStream));

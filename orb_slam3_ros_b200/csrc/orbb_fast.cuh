@@ -188,10 +188,12 @@ __global__ void __launch_bounds__(32, 32) k_fast_cell(const Plan* __restrict__ P
     extern __shared__ __align__(128) uint8_t fcSmem[];
     __shared__ __align__(8) unsigned long long sBar;
     const int gcell = blockIdx.x, frame = blockIdx.y, lane = threadIdx.x;
-    const CellDesc cd = B.cellDesc[gcell];
+    pdl_launch_dependents();
+    const CellDesc cd = B.cellDesc[gcell];                    // (plan data, not a product of the previous kernel)
     int* cellCount = B.cellCount + (size_t)frame * P->cellsTotal + gcell;
     const int ih = cd.gy1 - cd.gy0;
     if (cd.gx1 <= cd.gx0 || ih <= 0) {                        // cell skipped by the reference (:810,:819) or smaller than 7 px
+        pdl_wait();                                           // (the quadtree of the previous batch read this count)
         if (lane == 0) *cellCount = 0;
         return;
     }
@@ -207,6 +209,9 @@ __global__ void __launch_bounds__(32, 32) k_fast_cell(const Plan* __restrict__ P
         mbar_init(&sBar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(&sBar, tileRows * TP);
+    }
+    pdl_wait();                                               // the pyramid is complete from here on
+    if (lane == 0) {
         if (TMAP) tma_tensor3d_g2s(tile, &tmaps.m[cd.level], kRoiX + X0, kEdge + cd.gy0 - 3, frame0 + frame, &sBar);
     }
     __syncwarp();

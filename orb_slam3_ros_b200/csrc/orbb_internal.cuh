@@ -144,6 +144,15 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigne
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// Programmatic dependent launch (PTX griddepcontrol, sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// may have its CTAs scheduled while the previous kernel of the stream is still draining its last wave.  pdl_launch_dependents() at the
+// top of a kernel lets the NEXT kernel be scheduled as soon as every CTA of this one has started; pdl_wait() blocks until the
+// PREVIOUS kernel has completed and its writes are visible -- it must come before the first read of anything that kernel produced.
+// Both are no-ops in a kernel launched the ordinary way.  What this hides is the launch latency and the tail between the ~14
+// dependent kernels of one batch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // one tile of a 3-D tensor map (x = byte within the bordered row, y = bordered row, z = frame) -> shared memory; SASS: UTMALDG.3D
 __device__ __forceinline__ void tma_tensor3d_g2s(void* dst, const CUtensorMap* tmap, int x, int y, int z, void* bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
@@ -172,7 +181,7 @@ struct orbb_extractor {
     // lane the blur runs on a side stream beside the quadtree (both only read the pyramid).  Lane 0 uses `stream`.
     struct Lane { cudaStream_t st = nullptr, blurSt = nullptr, blurEdgeSt = nullptr; cudaEvent_t evFork = nullptr, evJoin = nullptr, evJoinEdge = nullptr, evStart = nullptr, evDone = nullptr; };
     Lane lanes[4];
-    int nLanes = 1;                // measured on B200: 2 lanes +1.7 % resident, -11 % end to end -> off by default (ORBB_LANES)
+    int nLanes = 2;                // lanes of a resident batch (ORBB_LANES=1..4)
     // plan for the current image size
     orbb::Plan plan;
     orbb::Plan* dPlan = nullptr;
@@ -186,6 +195,7 @@ struct orbb_extractor {
     int pendingFrames = 0, pendingCapacity = 0;   // orbb_extract_batch_host_submit -> _wait
     long long launches = 0;
     bool profiling = false;
+    bool capturing = false;        // run_batch is being recorded into the single-frame CUDA graph
     // single-frame calls (the SLAM thread's operator()) replay the launch sequence as a CUDA graph: 14 launches + the blur
     // fork/join cost more host time than the kernels of one frame take
     cudaGraphExec_t g1Exec = nullptr; int g1Lap0 = 0, g1Lap1 = 0; long long g1Launches = 0; bool g1Valid = false;

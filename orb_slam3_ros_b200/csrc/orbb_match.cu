@@ -28,6 +28,8 @@ struct orbb_matcher {
     unsigned* partial = nullptr; size_t partialCap = 0;     // [chunk][nq][2] packed (dist<<22 | local index)
     void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t scratchCap[4] = {0, 0, 0, 0};
+    void* frame[ORBB_FRAME_SLOTS] = {};                     // orbb_frame_upload: frames kept on the device between scans
+    size_t frameCap[ORBB_FRAME_SLOTS] = {};
 };
 
 namespace orbb {
@@ -294,18 +296,27 @@ __global__ void __launch_bounds__(256) k_best2_csr(const uint4* __restrict__ q, 
 // and radius.  The reference visits candidates cell by cell (ix, then iy, then keypoint index) and keeps the FIRST minimum;
 // the same tie rule falls out of an unsigned min over  dist << 32 | ix << 26 | iy << 20 | index.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_search_area_best2(const float2* __restrict__ kps, const int* __restrict__ oct,
-                                                          const uint4* __restrict__ train, int n, float minX, float minY, float invW,
-                                                          float invH, const float4* __restrict__ queries, const int2* __restrict__ qlev,
-                                                          const uint4* __restrict__ qdesc, int nq, const uint8_t* __restrict__ skip,
-                                                          const float* __restrict__ uRight, int init, int* __restrict__ out4) {
+// K = candidates kept per query, in the order of the reference's scan (distance, then first seen): K = 2 is the best / second-best
+// pair of :77-120; K = 4 lets the host apply the reference's in-order decisions (a key point matched by an earlier map point of
+// the same call is skipped by the later ones, :88-90) without going back to the device -- dropping taken candidates from a longer
+// sorted list leaves the same first two.  Key point coordinates / octaves are read with byte strides, so the arrays may be the
+// extractor's own orbb_keypoint records (x, y at offset 0, octave at offset 20, stride 24).
+template <int K>
+__global__ void __launch_bounds__(256) k_search_area_topk(const uint8_t* __restrict__ kps, size_t kpsStride, const uint8_t* __restrict__ oct,
+                                                         size_t octStride, const uint4* __restrict__ train, int n, float minX, float minY,
+                                                         float invW, float invH, const float4* __restrict__ queries,
+                                                         const int2* __restrict__ qlev, const uint4* __restrict__ qdesc, int nq,
+                                                         const uint8_t* __restrict__ skip, const float* __restrict__ uRight, int init,
+                                                         int* __restrict__ out) {
     const int qi = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (qi >= nq) return;
     const float4 q = __ldg(queries + qi);                      // x, y, r, projXR
     const int2 lev = __ldg(qlev + qi);
     const float x = q.x, y = q.y, r = q.z;
-    unsigned long long k1 = ~0ull, k2 = ~0ull;
+    unsigned long long top[K];                                 // this lane's K smallest keys, ascending
+#pragma unroll
+    for (int k = 0; k < K; k++) top[k] = ~0ull;
     const int nMinCellX = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, minX), r), invW)));
     const int nMaxCellX = min(63, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, minX), r), invW)));
     const int nMinCellY = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, minY), r), invH)));
@@ -314,11 +325,11 @@ __global__ void __launch_bounds__(256) k_search_area_best2(const float2* __restr
         const bool bCheckLevels = lev.x > 0 || lev.y >= 0;
         const uint4 a0 = __ldg(qdesc + (size_t)qi * 2), a1 = __ldg(qdesc + (size_t)qi * 2 + 1);
         for (int j = lane; j < n; j += 32) {
-            const float2 kp = __ldg(kps + j);
+            const float2 kp = __ldg(reinterpret_cast<const float2*>(kps + (size_t)j * kpsStride));
             const int px = (int)roundf(__fmul_rn(__fsub_rn(kp.x, minX), invW)), py = (int)roundf(__fmul_rn(__fsub_rn(kp.y, minY), invH));
             if (px < nMinCellX || px > nMaxCellX || py < nMinCellY || py > nMaxCellY) continue;   // also drops cells outside the grid
             if (bCheckLevels) {
-                const int o = __ldg(oct + j);
+                const int o = __ldg(reinterpret_cast<const int*>(oct + (size_t)j * octStride));
                 if (o < lev.x || (lev.y >= 0 && o > lev.y)) continue;
             }
             if (!(fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r)) continue;
@@ -329,27 +340,33 @@ __global__ void __launch_bounds__(256) k_search_area_best2(const float2* __restr
             }
             const int d = hamming256(a0, a1, __ldg(train + (size_t)j * 2), __ldg(train + (size_t)j * 2 + 1));
             if (d < init) {
-                const unsigned long long k = ((unsigned long long)(unsigned)d << 32) | ((unsigned long long)px << 26) |
-                                             ((unsigned long long)py << 20) | (unsigned)j;
-                const unsigned long long hi = max(k1, k);
-                k1 = min(k1, k);
-                k2 = min(k2, hi);
+                unsigned long long k = ((unsigned long long)(unsigned)d << 32) | ((unsigned long long)px << 26) |
+                                       ((unsigned long long)py << 20) | (unsigned)j;
+#pragma unroll
+                for (int t = 0; t < K; t++) {                  // insertion into the sorted K
+                    const unsigned long long lo = min(top[t], k);
+                    k = max(top[t], k);
+                    top[t] = lo;
+                }
             }
         }
     }
+    // K rounds: the smallest head of all lanes is the next entry; its owner advances (keys are unique: they contain the index)
+    int* o = out + (size_t)qi * 2 * K;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, k1, off), o2 = __shfl_xor_sync(0xffffffffu, k2, off);
-        const unsigned long long lo = min(k1, o1), hi = max(k1, o1);
-        k2 = min(min(k2, o2), hi);
-        k1 = lo;
-    }
-    if (lane == 0) {
-        int* o = out4 + (size_t)qi * 4;
-        o[0] = k1 == ~0ull ? init : (int)(k1 >> 32);
-        o[1] = k1 == ~0ull ? -1 : (int)(k1 & 0xfffffu);
-        o[2] = k2 == ~0ull ? init : (int)(k2 >> 32);
-        o[3] = k2 == ~0ull ? -1 : (int)(k2 & 0xfffffu);
+    for (int round = 0; round < K; round++) {
+        unsigned long long m = top[0];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, off));
+        if (top[0] == m && m != ~0ull) {
+#pragma unroll
+            for (int t = 0; t + 1 < K; t++) top[t] = top[t + 1];
+            top[K - 1] = ~0ull;
+        }
+        if (lane == 0) {
+            o[2 * round] = m == ~0ull ? init : (int)(m >> 32);
+            o[2 * round + 1] = m == ~0ull ? -1 : (int)(m & 0xfffffu);
+        }
     }
 }
 
@@ -805,6 +822,7 @@ void orbb_matcher_destroy(orbb_matcher* m) {
     cudaStreamSynchronize(m->stream);
     if (m->partial) cudaFree(m->partial);
     for (int i = 0; i < 4; i++) if (m->scratch[i]) cudaFree(m->scratch[i]);
+    for (int i = 0; i < ORBB_FRAME_SLOTS; i++) if (m->frame[i]) cudaFree(m->frame[i]);
     cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -905,8 +923,8 @@ int orbb_ratio_test_dev(orbb_matcher* m, const int32_t* idx2_dev, const int32_t*
     return ORBB_OK;
 }
 
-int orbb_best2_csr(orbb_matcher* m, const uint8_t* q, int nq, const uint8_t* train, int ntrain, const int32_t* cand,
-                   const int32_t* rowptr, int init, int32_t* out4) {
+static int best2_csr_impl(orbb_matcher* m, const uint8_t* q, int nq, const uint8_t* train, int ntrain, bool trainOnDevice, const int32_t* cand,
+                          const int32_t* rowptr, int init, int32_t* out4) {
     if (!m || !rowptr || !out4 || nq < 0 || ntrain < 0 || (nq > 0 && !q)) return m_err(m, ORBB_ERR_ARG, "bad argument");
     if (nq == 0) return ORBB_OK;
     // the arrays are host-resident: a bad candidate index would become an out-of-bounds device read that poisons the CUDA context
@@ -927,10 +945,11 @@ int orbb_best2_csr(orbb_matcher* m, const uint8_t* q, int nq, const uint8_t* tra
     int* dCand = (int*)m->scratch[2];
     int* dRow = (int*)((char*)m->scratch[2] + (bc + 255) / 256 * 256);
     ORBM_CUDA(m, cudaMemcpyAsync(m->scratch[0], q, bq, cudaMemcpyHostToDevice, m->stream));
-    if (ntrain > 0) ORBM_CUDA(m, cudaMemcpyAsync(m->scratch[1], train, (size_t)ntrain * 32, cudaMemcpyHostToDevice, m->stream));
+    if (ntrain > 0 && !trainOnDevice) ORBM_CUDA(m, cudaMemcpyAsync(m->scratch[1], train, (size_t)ntrain * 32, cudaMemcpyHostToDevice, m->stream));
     if (ncand > 0) ORBM_CUDA(m, cudaMemcpyAsync(dCand, cand, (size_t)ncand * 4, cudaMemcpyHostToDevice, m->stream));
     ORBM_CUDA(m, cudaMemcpyAsync(dRow, rowptr, br, cudaMemcpyHostToDevice, m->stream));
-    k_best2_csr<<<(nq + 7) / 8, 256, 0, m->stream>>>((const uint4*)m->scratch[0], nq, (const uint4*)m->scratch[1], dCand, dRow, init, (int*)m->scratch[3]);
+    k_best2_csr<<<(nq + 7) / 8, 256, 0, m->stream>>>((const uint4*)m->scratch[0], nq, trainOnDevice ? (const uint4*)train : (const uint4*)m->scratch[1], dCand, dRow,
+                                                    init, (int*)m->scratch[3]);
     m->launches++;
     ORBM_CUDA(m, cudaGetLastError());
     ORBM_CUDA(m, cudaMemcpyAsync(out4, m->scratch[3], bo, cudaMemcpyDeviceToHost, m->stream));
@@ -938,35 +957,96 @@ int orbb_best2_csr(orbb_matcher* m, const uint8_t* q, int nq, const uint8_t* tra
     return ORBB_OK;
 }
 
-int orbb_search_area_best2(orbb_matcher* m, const float* kps_xy, const int32_t* octaves, const uint8_t* train, int n, const float* grid4,
-                           const float* queries, const int32_t* qlev, const uint8_t* qdesc, int nq, const uint8_t* skip, const float* u_right,
-                           int init, int32_t* out4) {
-    if (!m || !grid4 || !out4 || n < 0 || nq < 0 || (n > 0 && (!kps_xy || !octaves || !train)) || (nq > 0 && (!queries || !qlev || !qdesc)))
+// frame-side arrays resident on the device for the matcher scans (orbb_frame_upload): one slot = one frame
+int orbb_best2_csr(orbb_matcher* m, const uint8_t* q, int nq, const uint8_t* train, int ntrain, const int32_t* cand, const int32_t* rowptr,
+                   int init, int32_t* out4) {
+    return best2_csr_impl(m, q, nq, train, ntrain, false, cand, rowptr, init, out4);
+}
+int orbb_best2_csr_dev(orbb_matcher* m, const uint8_t* q, int nq, const uint8_t* train_dev, int ntrain, const int32_t* cand, const int32_t* rowptr,
+                       int init, int32_t* out4) {
+    return best2_csr_impl(m, q, nq, train_dev, ntrain, true, cand, rowptr, init, out4);
+}
+
+int orbb_search_area_topk(orbb_matcher* m, const orbb_frame_view* f, const float* grid4, const float* queries, const int32_t* qlev,
+                          const uint8_t* qdesc, int nq, const uint8_t* skip, int init, int k, int32_t* out) {
+    if (!m || !f || !grid4 || !out || f->n < 0 || nq < 0 || (k != 1 && k != 2 && k != 4 && k != 8) ||
+        (f->n > 0 && (!f->kps_xy || !f->octaves || !f->desc || f->kps_stride < 8 || f->oct_stride < 4)) || (nq > 0 && (!queries || !qlev || !qdesc)))
         return m_err(m, ORBB_ERR_ARG, "bad argument");
     if (nq == 0) return ORBB_OK;
+    const int n = f->n;
     if (n >= (1 << 20)) return m_err(m, ORBB_ERR_UNSUPPORTED, "more than 2^20 keypoints per frame");
     ORBM_CUDA(m, cudaSetDevice(m->device));
-    // one staging buffer: [kps n*8][oct n*4][train n*32][queries nq*16][qlev nq*8][qdesc nq*32][skip n][uRight n*4][out nq*16], 256-B aligned parts
+    // one staging buffer: [queries nq*16][qlev nq*8][qdesc nq*32][skip n][out nq*k*8] and, for a host-resident frame,
+    // [kps n*stride][oct n*stride][train n*32][uRight n*4]; 256-B aligned parts
+    const bool dev = f->on_device != 0;
+    const size_t kb = dev ? 0 : (size_t)n * f->kps_stride, ob = dev ? 0 : (size_t)n * f->oct_stride;
+    const bool sameArray = !dev && (const char*)f->octaves >= (const char*)f->kps_xy && (const char*)f->octaves < (const char*)f->kps_xy + f->kps_stride &&
+                           f->oct_stride == f->kps_stride;      // octaves live inside the key point records: upload them once
     size_t off[10], cur = 0;
-    const size_t sz[9] = {(size_t)n * 8, (size_t)n * 4, (size_t)n * 32, (size_t)nq * 16, (size_t)nq * 8, (size_t)nq * 32,
-                          skip ? (size_t)n : 0, u_right ? (size_t)n * 4 : 0, (size_t)nq * 16};
+    const size_t sz[9] = {(size_t)nq * 16, (size_t)nq * 8, (size_t)nq * 32, skip ? (size_t)n : 0, (size_t)nq * k * 8, kb, sameArray ? 0 : ob,
+                          dev ? 0 : (size_t)n * 32, (dev || !f->u_right) ? 0 : (size_t)n * 4};
     for (int i = 0; i < 9; i++) { off[i] = cur; cur += (sz[i] + 255) / 256 * 256; }
     int rc;
     if ((rc = ensure_scratch(m, 0, cur + 256))) return rc;
     char* base = (char*)m->scratch[0];
-    const void* src[8] = {kps_xy, octaves, train, queries, qlev, qdesc, skip, u_right};
-    for (int i = 0; i < 8; i++)
-        if (sz[i]) ORBM_CUDA(m, cudaMemcpyAsync(base + off[i], src[i], sz[i], cudaMemcpyHostToDevice, m->stream));
-    k_search_area_best2<<<(nq + 7) / 8, 256, 0, m->stream>>>((const float2*)(base + off[0]), (const int*)(base + off[1]), (const uint4*)(base + off[2]), n,
-                                                            grid4[0], grid4[1], grid4[2], grid4[3], (const float4*)(base + off[3]),
-                                                            (const int2*)(base + off[4]), (const uint4*)(base + off[5]), nq,
-                                                            skip ? (const uint8_t*)(base + off[6]) : nullptr,
-                                                            u_right ? (const float*)(base + off[7]) : nullptr, init, (int*)(base + off[8]));
+    const void* src[9] = {queries, qlev, qdesc, skip, nullptr, f->kps_xy, f->octaves, f->desc, f->u_right};
+    for (int i = 0; i < 9; i++)
+        if (sz[i] && src[i]) ORBM_CUDA(m, cudaMemcpyAsync(base + off[i], src[i], sz[i], cudaMemcpyHostToDevice, m->stream));
+    const uint8_t* dK = dev ? (const uint8_t*)f->kps_xy : (const uint8_t*)(base + off[5]);
+    const uint8_t* dO = dev ? (const uint8_t*)f->octaves : sameArray ? dK + ((const char*)f->octaves - (const char*)f->kps_xy) : (const uint8_t*)(base + off[6]);
+    const uint4* dT = dev ? (const uint4*)f->desc : (const uint4*)(base + off[7]);
+    const float* dU = !f->u_right ? nullptr : dev ? f->u_right : (const float*)(base + off[8]);
+#define ORBB_TOPK(KK)                                                                                                                       \
+    k_search_area_topk<KK><<<(nq + 7) / 8, 256, 0, m->stream>>>(dK, f->kps_stride, dO, f->oct_stride, dT, n, grid4[0], grid4[1], grid4[2], grid4[3], \
+                                                               (const float4*)(base + off[0]), (const int2*)(base + off[1]),                   \
+                                                               (const uint4*)(base + off[2]), nq, skip ? (const uint8_t*)(base + off[3]) : nullptr, \
+                                                               dU, init, (int*)(base + off[4]))
+    if (k == 1) ORBB_TOPK(1);
+    else if (k == 2) ORBB_TOPK(2);
+    else if (k == 4) ORBB_TOPK(4);
+    else ORBB_TOPK(8);
+#undef ORBB_TOPK
     m->launches++;
     ORBM_CUDA(m, cudaGetLastError());
-    ORBM_CUDA(m, cudaMemcpyAsync(out4, base + off[8], sz[8], cudaMemcpyDeviceToHost, m->stream));
+    ORBM_CUDA(m, cudaMemcpyAsync(out, base + off[4], sz[4], cudaMemcpyDeviceToHost, m->stream));
     ORBM_CUDA(m, cudaStreamSynchronize(m->stream));
     return ORBB_OK;
+}
+
+int orbb_search_area_best2(orbb_matcher* m, const float* kps_xy, const int32_t* octaves, const uint8_t* train, int n, const float* grid4,
+                           const float* queries, const int32_t* qlev, const uint8_t* qdesc, int nq, const uint8_t* skip, const float* u_right,
+                           int init, int32_t* out4) {
+    orbb_frame_view f;
+    f.kps_xy = kps_xy; f.kps_stride = 8; f.octaves = octaves; f.oct_stride = 4; f.desc = train; f.u_right = u_right; f.n = n; f.on_device = 0;
+    return orbb_search_area_topk(m, &f, grid4, queries, qlev, qdesc, nq, skip, init, 2, out4);
+}
+
+int orbb_frame_upload(orbb_matcher* m, int slot, const orbb_frame_view* host, orbb_frame_view* dev) {
+    if (!m || !host || !dev || slot < 0 || slot >= ORBB_FRAME_SLOTS || host->n < 0 || host->on_device ||
+        (host->n > 0 && (!host->kps_xy || !host->octaves || !host->desc || host->kps_stride < 8 || host->oct_stride < 4)))
+        return m_err(m, ORBB_ERR_ARG, "bad argument");
+    ORBM_CUDA(m, cudaSetDevice(m->device));
+    const int n = host->n;
+    // packed on the device as {x, y} floats, int32 octaves, 32-byte descriptors, float u_right
+    const size_t bk = ((size_t)n * 8 + 255) / 256 * 256, bo = ((size_t)n * 4 + 255) / 256 * 256, bd = ((size_t)n * 32 + 255) / 256 * 256;
+    const size_t need = bk + bo + bd + bo + 256;
+    if (m->frameCap[slot] < need) {
+        if (m->frame[slot]) cudaFree(m->frame[slot]);
+        m->frame[slot] = nullptr; m->frameCap[slot] = 0;
+        ORBM_CUDA(m, cudaMalloc(&m->frame[slot], need));
+        m->frameCap[slot] = need;
+    }
+    char* base = (char*)m->frame[slot];
+    if (n > 0) {
+        ORBM_CUDA(m, cudaMemcpy2DAsync(base, 8, host->kps_xy, host->kps_stride, 8, n, cudaMemcpyHostToDevice, m->stream));
+        ORBM_CUDA(m, cudaMemcpy2DAsync(base + bk, 4, host->octaves, host->oct_stride, 4, n, cudaMemcpyHostToDevice, m->stream));
+        ORBM_CUDA(m, cudaMemcpyAsync(base + bk + bo, host->desc, (size_t)n * 32, cudaMemcpyHostToDevice, m->stream));
+        if (host->u_right) ORBM_CUDA(m, cudaMemcpyAsync(base + bk + bo + bd, host->u_right, (size_t)n * 4, cudaMemcpyHostToDevice, m->stream));
+    }
+    dev->kps_xy = base; dev->kps_stride = 8; dev->octaves = base + bk; dev->oct_stride = 4; dev->desc = (const uint8_t*)(base + bk + bo);
+    dev->u_right = host->u_right ? (const float*)(base + bk + bo + bd) : nullptr;
+    dev->n = n; dev->on_device = 1;
+    return ORBB_OK;                                        // (the copies are ordered before any later scan on the matcher's stream)
 }
 
 int orbb_distinctive_csr(orbb_matcher* m, const uint8_t* desc, int ntotal, const int32_t* rowptr, int ngroups, int32_t* best) {

@@ -75,6 +75,8 @@ __global__ void __launch_bounds__(PR_THREADS, 16) k_pyr_resize_s(const Plan* __r
     const int dy0 = (blockIdx.y * (PR_THREADS / 32) + (threadIdx.x >> 5)) * PR_ROWS;
     const int frame = blockIdx.z;
     const int Lw = L.w, Lh = L.h, Lpitch = L.pitch, Sh1 = S.h - 1, Spitch = S.pitch;
+    pdl_launch_dependents();
+    pdl_wait();
     if (word * 4 >= Lw || dy0 >= Lh) return;
     const int4* tx = reinterpret_cast<const int4*>(B.tab + L.tabX + word * 4);      // 4 entries (sx, a0 | a1 << 16), padded
     const int4 t01 = __ldg(tx), t23 = __ldg(tx + 1);
@@ -159,6 +161,7 @@ __global__ void __launch_bounds__(PR_THREADS, 12) k_pyr_resize_t(const Plan* __r
     const int dy0 = dyc + (tid >> 5) * ROWS;
     const int frame = blockIdx.z;
     const int Lw = L.w, Lh = L.h, Lpitch = L.pitch, Sh1 = S.h - 1, Spitch = S.pitch;
+    pdl_launch_dependents();
     // ---- stage: source rows rs0..rs1, bytes [xs0, xs0 + PR_SPITCH); the row table of the CTA ----
     const int2* tyc = B.tab + L.tabY;
     const int rs0 = min(max(__ldg(tyc + dyc).x, 0), Sh1);
@@ -175,6 +178,7 @@ __global__ void __launch_bounds__(PR_THREADS, 12) k_pyr_resize_t(const Plan* __r
         sRow[tid] = make_int4(min(max(t.x, 0), Sh1) - rs0, min(max(t.x + 1, 0), Sh1) - rs0, (int)(t.y << 16), (int)(t.y & 0xffff0000));
     }
     __syncthreads();
+    pdl_wait();                                                           // (everything above reads the plan's tables only)
     if (tid <= rs1 - rs0) tma_bulk_g2s(sSrc + tid * PR_SPITCH, sbase + (size_t)(rs0 + tid) * Spitch, PR_SPITCH, &sBar);
     if (word * 4 >= Lw || dy0 >= Lh) return;
     const int4* tx = reinterpret_cast<const int4*>(B.tab + L.tabX + word * 4);      // 4 entries (sx, a0 | a1 << 16), padded

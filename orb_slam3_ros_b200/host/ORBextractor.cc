@@ -4,12 +4,22 @@
 #include "ORBextractor.h"
 
 #include <cassert>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
 #include "orbb200.h"
 
 namespace ORB_SLAM3 {
+
+static int g_defaultDevice = -1;      // -1: not set -> ORBB_DEVICE or 0
+
+void ORBextractor::SetDefaultDevice(int device) { g_defaultDevice = device; }
+int ORBextractor::DefaultDevice() {
+    if (g_defaultDevice >= 0) return g_defaultDevice;
+    const char* e = getenv("ORBB_DEVICE");
+    return e ? atoi(e) : 0;
+}
 
 ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST)
     : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST), minThFAST(_minThFAST),
@@ -20,7 +30,7 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
     prm.nlevels = _nlevels;
     prm.ini_th_fast = _iniThFAST;
     prm.min_th_fast = _minThFAST;
-    prm.device = 0;
+    prm.device = DefaultDevice();
     prm.max_batch = 1;
     const int rc = orbb_create(&prm, &mpHandle);
     if (rc != ORBB_OK) throw std::runtime_error(std::string("orbb_create failed: ") + orbb_last_error(nullptr));

@@ -41,7 +41,15 @@ public:
     std::vector<cv::Mat> mvImagePyramid;
 
     // ---- extensions (not in the reference) ----
+    // mvImagePyramid is a public data member that Frame::ComputeStereoMatches reads right after the two extractions (Frame.cc:818-923),
+    // so by default every call ends with the hand-out of the pyramid (19-px apron built on the device, one 1.5 MB copy at 752x480:
+    // +0.05 ms, see bench.py single_frame_with_pyramid_ms).  Monocular / RGB-D callers never read it and can switch it off; stereo
+    // callers that use orbb_stereo_match (the pyramids stay on the device) can too.
     void SetPyramidDownload(bool enabled) { mbDownloadPyramid = enabled; }
+    // CUDA device of the extractors constructed after this call (default: environment variable ORBB_DEVICE, else 0).  The reference's
+    // constructor has no such argument and Tracking constructs the extractors itself, hence a process-wide setting.
+    static void SetDefaultDevice(int device);
+    static int DefaultDevice();
     orbb_extractor* Handle() { return mpHandle; }          // for orbb_stereo_match(hL, hR, ...)
     // Colour frame (CV_8UC3 / CV_8UC4 data, `channels` bytes per pixel): the cvtColor(.., COLOR_*2GRAY) that Tracking applies
     // before building the Frame (Tracking.cc:1498-1525) runs on the device; bRGB = Tracking's mbRGB.

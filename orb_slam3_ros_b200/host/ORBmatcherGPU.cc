@@ -1,0 +1,262 @@
+// GPU-backed replacements for the two ORBmatcher::SearchByProjection overloads that Tracking calls on every frame:
+//
+//   SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, th, bFarPoints, thFarPoints)     reference ORBmatcher.cc:43-213
+//       (Tracking::SearchLocalPoints, Tracking.cc:3216 ff.)
+//   SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono)                           reference ORBmatcher.cc:1676-1887
+//       (Tracking::TrackWithMotionModel, Tracking.cc:2925 / :2933)
+//
+// for monocular, rectified-stereo and RGB-D frames (Frame::Nleft == -1).  What stays on the host is what is host state in the
+// reference as well: the MapPoint / Frame objects, the projection of every point, the accept / reject decisions.  What moves to the
+// GPU is the part that costs: Frame::GetFeaturesInArea (Frame.cc:657-723) + the DescriptorDistance scan of every candidate
+// (orbb_search_area_topk: all points of the call in one launch, the frame's key points and descriptors uploaded once per frame).
+//
+// The reference walks its points in order and updates F.mvpMapPoints as it goes; a key point that has just received a map point with
+// observations is skipped by every later point (:88-90, :1749-1751).  The batched scan sees the frame as it was BEFORE the call, so
+// it returns the FOUR best candidates of every point in the reference's scan order and the decision loop below drops the ones that
+// were taken meanwhile: what remains at the head of the list is what the reference's scan would have found.  Only when all four are
+// gone does a point go back to the device, alone, with the current mask.
+//
+// Integration: at the top of the two reference methods
+//     if (F.Nleft == -1) return ORBmatcherGPU::Instance().SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints, mfNNratio);
+// Compiled here against tests/host/slam_stub (this image has no Eigen / Sophus / OpenCV headers) and compared on the GPU with the
+// reference's own bodies (oracle/_ref, cut out of ORBmatcher.cc at build time): tests/test_gpu_matcher_host.py.
+#include "ORBmatcherGPU.h"
+
+#include <cmath>
+#include <cstring>
+
+#include "Frame.h"
+#include "MapPoint.h"
+
+namespace ORB_SLAM3 {
+
+namespace {
+const int kTopK = 4;
+
+struct Cand { int dist, idx; };
+
+// the frame side of the scans, uploaded once per (frame id, slot) and reused by later calls on the same frame
+struct FrameOnDevice {
+    unsigned long id = ~0ul;
+    int n = -1;
+    const void* descData = nullptr;
+    orbb_frame_view view;
+};
+}  // namespace
+
+struct ORBmatcherGPU::Impl {
+    FrameOnDevice slot[2];
+    std::vector<float> xy, q, ur;
+    std::vector<int32_t> oct, qlev, out;
+    std::vector<unsigned char> qdesc, skip;
+    std::vector<int> src;
+};
+
+ORBmatcherGPU::Impl& ORBmatcherGPU::Scratch() {
+    if (!mpImpl) {
+        mpImpl = new Impl();
+        mpImplFree = [](Impl* p) { delete p; };
+    }
+    return *mpImpl;
+}
+
+ORBmatcherGPU& ORBmatcherGPU::Instance(int device) {
+    static thread_local ORBmatcherGPU inst(device);      // one matcher (stream + scratch) per SLAM thread, like the stack objects of the reference
+    return inst;
+}
+
+// the frame's undistorted key points, octaves, descriptors and mvuRight on the device (slot 0: current frame, 1: any other)
+static const orbb_frame_view* FrameView(orbb_matcher* m, ORBmatcherGPU::Impl& s, const Frame& F, int slotIdx) {
+    FrameOnDevice& c = s.slot[slotIdx];
+    if (c.id == F.mnId && c.n == F.N && c.descData == (const void*)F.mDescriptors.data) return &c.view;
+    s.xy.resize((size_t)F.N * 2);
+    s.oct.resize(F.N);
+    for (int i = 0; i < F.N; i++) { s.xy[2 * i] = F.mvKeysUn[i].pt.x; s.xy[2 * i + 1] = F.mvKeysUn[i].pt.y; s.oct[i] = F.mvKeysUn[i].octave; }
+    orbb_frame_view h;
+    h.kps_xy = s.xy.data(); h.kps_stride = 8; h.octaves = s.oct.data(); h.oct_stride = 4;
+    h.desc = F.mDescriptors.ptr<uchar>(); h.u_right = (int)F.mvuRight.size() == F.N ? F.mvuRight.data() : nullptr;
+    h.n = F.N; h.on_device = 0;
+    if (!F.mDescriptors.isContinuous()) throw std::runtime_error("Frame::mDescriptors must be continuous");
+    if (orbb_frame_upload(m, slotIdx, &h, &c.view) != ORBB_OK)
+        throw std::runtime_error(std::string("orbb_frame_upload failed: ") + orbb_matcher_last_error(m));
+    c.id = F.mnId; c.n = F.N; c.descData = F.mDescriptors.data;
+    return &c.view;
+}
+
+static inline bool Taken(const Frame& F, int idx) {      // ORBmatcher.cc:88-90 / :1749-1751, evaluated on the live objects
+    MapPoint* p = F.mvpMapPoints[idx];
+    return p && p->Observations() > 0;
+}
+
+// first `want` candidates of query j that are still free; false when the list is exhausted although it was full (more candidates
+// may exist beyond the k returned: the caller scans that one query again)
+static bool LiveHead(const Frame& F, const int32_t* list, int k, int want, Cand* out, int& nout) {
+    nout = 0;
+    int valid = 0;
+    for (int t = 0; t < k; t++) {
+        const int idx = list[2 * t + 1];
+        if (idx < 0) break;
+        valid++;
+        if (Taken(F, idx)) continue;
+        if (nout < want) { out[nout].dist = list[2 * t]; out[nout].idx = idx; nout++; }
+    }
+    return nout >= want || valid < k;
+}
+
+void ORBmatcherGPU::RunScan(const Frame& F, int nq, int k, std::vector<int32_t>& out) {
+    Impl& s = Scratch();
+    const orbb_frame_view* fv = FrameView(mpMatcher, s, F, 0);
+    s.skip.assign(F.N, 0);
+    for (int i = 0; i < F.N; i++) s.skip[i] = Taken(F, i);
+    const float grid4[4] = {Frame::mnMinX, Frame::mnMinY, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv};
+    out.assign((size_t)nq * k * 2, -1);
+    if (nq == 0) return;
+    if (orbb_search_area_topk(mpMatcher, fv, grid4, s.q.data(), s.qlev.data(), s.qdesc.data(), nq, s.skip.data(), 256, k, out.data()) != ORBB_OK)
+        throw std::runtime_error(std::string("orbb_search_area_topk failed: ") + orbb_matcher_last_error(mpMatcher));
+}
+
+// one query again, with the frame as it is now
+void ORBmatcherGPU::Rescan(const Frame& F, int j, int want, void* candOut, int& nout) {
+    Impl& s = Scratch();
+    const orbb_frame_view* fv = FrameView(mpMatcher, s, F, 0);
+    for (int i = 0; i < F.N; i++) s.skip[i] = Taken(F, i);
+    const float grid4[4] = {Frame::mnMinX, Frame::mnMinY, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv};
+    int32_t o[4] = {256, -1, 256, -1};
+    if (orbb_search_area_topk(mpMatcher, fv, grid4, &s.q[4 * (size_t)j], &s.qlev[2 * (size_t)j], &s.qdesc[32 * (size_t)j], 1, s.skip.data(), 256, 2, o) != ORBB_OK)
+        throw std::runtime_error(std::string("orbb_search_area_topk failed: ") + orbb_matcher_last_error(mpMatcher));
+    Cand* c = (Cand*)candOut;
+    nout = 0;
+    for (int t = 0; t < 2 && t < want; t++)
+        if (o[2 * t + 1] >= 0) { c[nout].dist = o[2 * t]; c[nout].idx = o[2 * t + 1]; nout++; }
+    mnRescans++;
+}
+
+static inline float RadiusByViewingCos(float viewCos) { return viewCos > 0.998f ? 2.5f : 4.0f; }      // ORBmatcher.cc:215-221
+
+int ORBmatcherGPU::SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th, const bool bFarPoints,
+                                      const float thFarPoints, const float nnratio) {
+    if (F.Nleft != -1) throw std::logic_error("ORBmatcherGPU::SearchByProjection: fisheye-stereo frames (Nleft != -1) keep the reference's host path");
+    Impl& s = Scratch();
+    const bool bFactor = th != 1.0;
+    s.q.clear(); s.qlev.clear(); s.qdesc.clear(); s.src.clear();
+    for (size_t iMP = 0; iMP < vpMapPoints.size(); iMP++) {                       // :49-75
+        MapPoint* pMP = vpMapPoints[iMP];
+        if (!pMP->mbTrackInView && !pMP->mbTrackInViewR) continue;
+        if (bFarPoints && pMP->mTrackDepth > thFarPoints) continue;
+        if (pMP->isBad()) continue;
+        if (!pMP->mbTrackInView) continue;
+        const int nPredictedLevel = pMP->mnTrackScaleLevel;
+        float r = RadiusByViewingCos(pMP->mTrackViewCos);
+        if (bFactor) r *= th;
+        const float q4[4] = {pMP->mTrackProjX, pMP->mTrackProjY, r * F.mvScaleFactors[nPredictedLevel], pMP->mTrackProjXR};
+        s.q.insert(s.q.end(), q4, q4 + 4);
+        s.qlev.push_back(nPredictedLevel - 1); s.qlev.push_back(nPredictedLevel);
+        const cv::Mat d = pMP->GetDescriptor();
+        s.qdesc.insert(s.qdesc.end(), d.ptr<uchar>(), d.ptr<uchar>() + 32);
+        s.src.push_back((int)iMP);
+    }
+    const int nq = (int)s.src.size();
+    RunScan(F, nq, kTopK, s.out);
+    int nmatches = 0;
+    for (int j = 0; j < nq; j++) {                                                // :77-141, in list order
+        Cand c[2];
+        int nc = 0;
+        if (!LiveHead(F, &s.out[(size_t)j * kTopK * 2], kTopK, 2, c, nc)) Rescan(F, j, 2, c, nc);
+        if (nc == 0) continue;
+        const int bestDist = c[0].dist, bestIdx = c[0].idx, bestDist2 = nc > 1 ? c[1].dist : 256;
+        const int bestLevel = F.mvKeysUn[bestIdx].octave, bestLevel2 = nc > 1 ? F.mvKeysUn[c[1].idx].octave : -1;
+        if (bestDist <= TH_HIGH) {
+            if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+            if (bestLevel != bestLevel2 || bestDist <= nnratio * bestDist2) {
+                F.mvpMapPoints[bestIdx] = vpMapPoints[s.src[j]];
+                nmatches++;
+            }
+        }
+    }
+    return nmatches;
+}
+
+int ORBmatcherGPU::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono, const bool checkOrientation) {
+    if (CurrentFrame.Nleft != -1 || LastFrame.Nleft != -1)
+        throw std::logic_error("ORBmatcherGPU::SearchByProjection: fisheye-stereo frames (Nleft != -1) keep the reference's host path");
+    Impl& s = Scratch();
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    const Sophus::SE3f Tcw = CurrentFrame.GetPose();                              // :1686-1693
+    const Eigen::Vector3f twc = Tcw.inverse().translation();
+    const Sophus::SE3f Tlw = LastFrame.GetPose();
+    const Eigen::Vector3f tlc = Tlw * twc;
+    const bool bForward = tlc(2) > CurrentFrame.mb && !bMono;
+    const bool bBackward = -tlc(2) > CurrentFrame.mb && !bMono;
+    s.q.clear(); s.qlev.clear(); s.qdesc.clear(); s.src.clear();
+    for (int i = 0; i < LastFrame.N; i++) {                                       // :1695-1735: project, window, level range
+        MapPoint* pMP = LastFrame.mvpMapPoints[i];
+        if (!pMP || LastFrame.mvbOutlier[i]) continue;
+        Eigen::Vector3f x3Dw = pMP->GetWorldPos();
+        Eigen::Vector3f x3Dc = Tcw * x3Dw;
+        const float invzc = 1.0 / x3Dc(2);
+        if (invzc < 0) continue;
+        Eigen::Vector2f uv = CurrentFrame.mpCamera->project(x3Dc);
+        if (uv(0) < CurrentFrame.mnMinX || uv(0) > CurrentFrame.mnMaxX) continue;
+        if (uv(1) < CurrentFrame.mnMinY || uv(1) > CurrentFrame.mnMaxY) continue;
+        const int nLastOctave = LastFrame.mvKeys[i].octave;
+        const float radius = th * CurrentFrame.mvScaleFactors[nLastOctave];
+        const float q4[4] = {uv(0), uv(1), radius, uv(0) - CurrentFrame.mbf * invzc};      // (:1757: ur of the stereo check)
+        s.q.insert(s.q.end(), q4, q4 + 4);
+        if (bForward) { s.qlev.push_back(nLastOctave); s.qlev.push_back(-1); }
+        else if (bBackward) { s.qlev.push_back(0); s.qlev.push_back(nLastOctave); }
+        else { s.qlev.push_back(nLastOctave - 1); s.qlev.push_back(nLastOctave + 1); }
+        const cv::Mat d = pMP->GetDescriptor();
+        s.qdesc.insert(s.qdesc.end(), d.ptr<uchar>(), d.ptr<uchar>() + 32);
+        s.src.push_back(i);
+    }
+    const int nq = (int)s.src.size();
+    RunScan(CurrentFrame, nq, kTopK, s.out);
+    int nmatches = 0;
+    for (int j = 0; j < nq; j++) {                                                // :1737-1790: best candidate, TH_HIGH, rotation vote
+        Cand c[1];
+        int nc = 0;
+        if (!LiveHead(CurrentFrame, &s.out[(size_t)j * kTopK * 2], kTopK, 1, c, nc)) Rescan(CurrentFrame, j, 1, c, nc);
+        if (nc == 0) continue;
+        const int bestDist = c[0].dist, bestIdx2 = c[0].idx, i = s.src[j];
+        if (bestDist <= TH_HIGH) {
+            CurrentFrame.mvpMapPoints[bestIdx2] = LastFrame.mvpMapPoints[i];
+            nmatches++;
+            if (checkOrientation) {
+                float rot = LastFrame.mvKeysUn[i].angle - CurrentFrame.mvKeysUn[bestIdx2].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = round(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rotHist[bin].push_back(bestIdx2);
+            }
+        }
+    }
+    if (checkOrientation) {                                                       // :1866-1884
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i != ind1 && i != ind2 && i != ind3) {
+                for (size_t j = 0, jend = rotHist[i].size(); j < jend; j++) {
+                    CurrentFrame.mvpMapPoints[rotHist[i][j]] = static_cast<MapPoint*>(NULL);
+                    nmatches--;
+                }
+            }
+        }
+    }
+    return nmatches;
+}
+
+// ORBmatcher::ComputeThreeMaxima (ORBmatcher.cc:2012-2053): the three fullest bins; the second / third are dropped below 10 % of the first
+void ORBmatcherGPU::ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; i++) {
+        const int s = (int)histo[i].size();
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) ind3 = -1;
+}
+
+}  // namespace ORB_SLAM3

@@ -16,17 +16,36 @@
 
 namespace ORB_SLAM3 {
 
+class Frame;
+class MapPoint;
+
 class ORBmatcherGPU {
 public:
     static const int TH_LOW = 50;        // ORBmatcher.cc:36
     static const int TH_HIGH = 100;      // ORBmatcher.cc:35
     static const int HISTO_LENGTH = 30;  // ORBmatcher.cc:37
 
-    explicit ORBmatcherGPU(int device = 0) : mpMatcher(nullptr) {
+    struct Impl;                          // scratch of the compiled SearchByProjection replacements (ORBmatcherGPU.cc)
+
+    explicit ORBmatcherGPU(int device = 0) : mpMatcher(nullptr), mpImpl(nullptr), mpImplFree(nullptr), mnRescans(0) {
         if (orbb_matcher_create(device, &mpMatcher) != ORBB_OK)
             throw std::runtime_error(std::string("orbb_matcher_create failed: ") + orbb_matcher_last_error(nullptr));
     }
-    ~ORBmatcherGPU() { orbb_matcher_destroy(mpMatcher); }
+    ~ORBmatcherGPU() {
+        if (mpImpl && mpImplFree) mpImplFree(mpImpl);
+        orbb_matcher_destroy(mpMatcher);
+    }
+
+    // ---- compiled replacements of the two per-frame ORBmatcher::SearchByProjection overloads (ORBmatcherGPU.cc) ----------------
+    // one instance per calling thread (the reference constructs an ORBmatcher on the stack per call; this one owns a stream)
+    static ORBmatcherGPU& Instance(int device = 0);
+    // ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints)   ORBmatcher.cc:43-213; nnratio = mfNNratio
+    int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th, const bool bFarPoints, const float thFarPoints,
+                           const float nnratio);
+    // ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono)           ORBmatcher.cc:1676-1887; checkOrientation = mbCheckOrientation
+    int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono, const bool checkOrientation);
+    static void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);      // ORBmatcher.cc:2012-2053
+    long Rescans() const { return mnRescans; }      // points that had to be scanned a second time (all their 4 candidates were taken meanwhile)
     ORBmatcherGPU(const ORBmatcherGPU&) = delete;
     ORBmatcherGPU& operator=(const ORBmatcherGPU&) = delete;
 
@@ -98,7 +117,13 @@ public:
     }
 
 private:
+    void RunScan(const Frame& F, int nq, int k, std::vector<int32_t>& out);
+    void Rescan(const Frame& F, int j, int want, void* candOut, int& nout);
+    Impl& Scratch();
     orbb_matcher* mpMatcher;
+    Impl* mpImpl;
+    void (*mpImplFree)(Impl*);
+    long mnRescans;
 };
 
 }  // namespace ORB_SLAM3

@@ -7,6 +7,8 @@ import pytest
 ROOT = Path(__file__).resolve().parents[1]
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
+if str(ROOT / "tests") not in sys.path:      # tests/scenes.py: seeded scenes shared by the CPU pinning and the GPU parity tests
+    sys.path.insert(0, str(ROOT / "tests"))
 
 
 def pytest_configure(config):

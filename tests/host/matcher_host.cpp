@@ -1,0 +1,120 @@
+// TEST HARNESS: the compiled GPU matcher adapter (orb_slam3_ros_b200/host/ORBmatcherGPU.cc) behind the SAME flat C entry points as the
+// reference-cut glue of oracle/ref_cut_tu.cpp (refcut_search_by_projection, refcut_search_by_projection_motion), so that
+// tests/test_gpu_matcher_host.py can feed both sides identical arrays and compare what they leave in mvpMapPoints.  Built as a shared
+// library against tests/host/slam_stub + tests/cvstub (no Eigen / Sophus / OpenCV in this image).
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "Frame.h"
+#include "MapPoint.h"
+#include "ORBmatcherGPU.h"
+
+namespace ORB_SLAM3 {
+float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
+}
+
+using namespace ORB_SLAM3;
+
+static cv::Mat to_descriptors(const uint8_t* d, int n) {
+    cv::Mat m(n > 0 ? n : 1, 32, CV_8U);
+    if (n) memcpy(m.data, d, (size_t)n * 32);
+    return m;
+}
+
+static unsigned long g_frameId = 1;
+
+extern "C" {
+
+long gpuhost_rescans() { return ORBmatcherGPU::Instance().Rescans(); }
+
+// same arguments and result as refcut_search_by_projection (oracle/ref_cut_tu.cpp)
+int gpuhost_search_by_projection(const float* kps, const int32_t* oct, const uint8_t* train, int n, const float* grid4, const float* uRight,
+                                 const uint8_t* hasPoint, const float* scaleFactors, int nlevels, const float* proj, const int32_t* level,
+                                 const uint8_t* mpDesc, const uint8_t* inView, int nmp, float nnratio, float th, int32_t* matchOf) {
+    Frame F;
+    F.mnId = g_frameId++;
+    Frame::mnMinX = grid4[0]; Frame::mnMinY = grid4[1]; Frame::mfGridElementWidthInv = grid4[2]; Frame::mfGridElementHeightInv = grid4[3];
+    F.N = n; F.Nleft = -1;
+    F.mvKeysUn.resize(n);
+    for (int i = 0; i < n; i++) { F.mvKeysUn[i].pt.x = kps[2 * i]; F.mvKeysUn[i].pt.y = kps[2 * i + 1]; F.mvKeysUn[i].octave = oct[i]; }
+    F.mDescriptors = to_descriptors(train, n);
+    F.mvuRight.assign(n, -1.0f);
+    if (uRight) for (int i = 0; i < n; i++) F.mvuRight[i] = uRight[i];
+    F.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    MapPoint old;
+    old.nObs = 1;
+    F.mvpMapPoints.assign(n, nullptr);
+    for (int i = 0; i < n; i++) if (hasPoint && hasPoint[i]) F.mvpMapPoints[i] = &old;
+    std::vector<MapPoint> mps(nmp);
+    std::vector<MapPoint*> vp(nmp);
+    for (int j = 0; j < nmp; j++) {
+        MapPoint& m = mps[j];
+        m.mTrackProjX = proj[4 * j]; m.mTrackProjY = proj[4 * j + 1]; m.mTrackProjXR = proj[4 * j + 2]; m.mTrackViewCos = proj[4 * j + 3];
+        m.mnTrackScaleLevel = level[j];
+        m.mbTrackInView = inView[j] != 0;
+        m.mDescriptor = to_descriptors(mpDesc + (size_t)32 * j, 1);
+        m.nObs = 1;
+        vp[j] = &m;
+    }
+    const int nmatches = ORBmatcherGPU::Instance().SearchByProjection(F, vp, th, false, 50.0f, nnratio);
+    for (int i = 0; i < n; i++) {
+        MapPoint* p = F.mvpMapPoints[i];
+        matchOf[i] = (p && p != &old) ? (int)(p - mps.data()) : -1;
+    }
+    return nmatches;
+}
+
+// same arguments and result as refcut_search_by_projection_motion (oracle/ref_cut_tu.cpp)
+int gpuhost_search_by_projection_motion(const float* kps, const int32_t* oct, const float* angle, const uint8_t* desc, int n, const float* fp,
+                                        const float* uRight, const uint8_t* curState, const float* scaleFactors, int nlevels, const float* Tcw,
+                                        const float* cam4, int nLast, const int32_t* lastOct, const float* lastAngle, const uint8_t* lastState,
+                                        const uint8_t* lastOutlier, const float* lastPos, const uint8_t* lastDesc, const float* Tlw, float th,
+                                        int bMono, float nnratio, int checkOri, int32_t* matchOf) {
+    (void)nnratio;
+    Frame C, L;
+    C.mnId = g_frameId++; L.mnId = g_frameId++;
+    Frame::mnMinX = fp[0]; Frame::mnMaxX = fp[1]; Frame::mnMinY = fp[2]; Frame::mnMaxY = fp[3];
+    Frame::mfGridElementWidthInv = fp[4]; Frame::mfGridElementHeightInv = fp[5];
+    GeometricCamera cam;
+    cam.fx = cam4[0]; cam.fy = cam4[1]; cam.cx = cam4[2]; cam.cy = cam4[3];
+    C.N = n; C.Nleft = -1; C.mbf = fp[6]; C.mb = fp[7]; C.mpCamera = &cam;
+    C.mTcw = Sophus::SE3f(Tcw, Tcw + 9);
+    C.mvKeysUn.resize(n);
+    for (int i = 0; i < n; i++) {
+        C.mvKeysUn[i].pt.x = kps[2 * i]; C.mvKeysUn[i].pt.y = kps[2 * i + 1]; C.mvKeysUn[i].octave = oct[i]; C.mvKeysUn[i].angle = angle[i];
+    }
+    C.mvKeys = C.mvKeysUn;
+    C.mDescriptors = to_descriptors(desc, n);
+    C.mvuRight.assign(n, -1.0f);
+    if (uRight) for (int i = 0; i < n; i++) C.mvuRight[i] = uRight[i];
+    C.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    MapPoint oldObs, oldNoObs;
+    oldObs.nObs = 1; oldNoObs.nObs = 0;
+    C.mvpMapPoints.assign(n, nullptr);
+    for (int i = 0; i < n; i++) if (curState && curState[i]) C.mvpMapPoints[i] = curState[i] == 1 ? &oldObs : &oldNoObs;
+    L.N = nLast; L.Nleft = -1; L.mTcw = Sophus::SE3f(Tlw, Tlw + 9);
+    L.mvKeysUn.resize(nLast);
+    std::vector<MapPoint> mps(nLast);
+    L.mvpMapPoints.assign(nLast, nullptr);
+    L.mvbOutlier.assign(nLast, false);
+    for (int j = 0; j < nLast; j++) {
+        L.mvKeysUn[j].octave = lastOct[j]; L.mvKeysUn[j].angle = lastAngle[j];
+        L.mvbOutlier[j] = lastOutlier[j] != 0;
+        if (lastState[j]) {
+            mps[j].nObs = lastState[j] == 1 ? 1 : 0;
+            mps[j].mWorldPos = Eigen::Vector3f(lastPos[3 * j], lastPos[3 * j + 1], lastPos[3 * j + 2]);
+            mps[j].mDescriptor = to_descriptors(lastDesc + (size_t)32 * j, 1);
+            L.mvpMapPoints[j] = &mps[j];
+        }
+    }
+    L.mvKeys = L.mvKeysUn;
+    const int nmatches = ORBmatcherGPU::Instance().SearchByProjection(C, L, th, bMono != 0, checkOri != 0);
+    for (int i = 0; i < n; i++) {
+        MapPoint* p = C.mvpMapPoints[i];
+        matchOf[i] = (p && p != &oldObs && p != &oldNoObs) ? (int)(p - mps.data()) : -1;
+    }
+    return nmatches;
+}
+
+}  // extern "C"

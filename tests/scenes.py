@@ -1,0 +1,80 @@
+"""Seeded scenes for the matcher tests (shared by the CPU pinning tests and the GPU parity tests): the flat arrays that both the
+reference-cut glue (oracle/ref.py) and the GPU host adapter harness (tests/host/matcher_host.cpp) take."""
+import numpy as np
+
+from oracle import port
+from orb_slam3_ros_b200 import synth
+
+
+def local_points_scene(with_stereo, seed=31, nmp=1600):
+    """Tracking::SearchLocalPoints: more projected map points than key points, so that many compete for the same key point"""
+    h, w = 480, 752
+    pe = port.PortExtractor(1000, 1.2, 8)
+    _, k, d, _ = pe.extract(synth.frame(h, w, 8))
+    n = len(k)
+    rng = np.random.default_rng(seed)
+    grid4 = np.float32([0.0, 0.0, np.float32(64) / np.float32(w), np.float32(48) / np.float32(h)])
+    src = rng.integers(0, n, nmp)
+    proj = np.stack([k["x"][src] + rng.normal(0, 2.5, nmp), k["y"][src] + rng.normal(0, 2.5, nmp),
+                     k["x"][src] - rng.uniform(0, 40, nmp), rng.choice([0.9, 0.999, 0.9985], nmp)], 1).astype(np.float32)
+    level = np.clip(k["octave"][src] + rng.integers(-1, 2, nmp), 0, 7).astype(np.int32)
+    mp_desc = d[src].copy()
+    mp_desc[:, :4] ^= rng.integers(0, 256, (nmp, 4), dtype=np.uint8) & rng.integers(0, 256, (nmp, 4), dtype=np.uint8)
+    in_view = (rng.random(nmp) < 0.9).astype(np.uint8)
+    has_point = (rng.random(n) < 0.25).astype(np.uint8)
+    u_right = np.where(rng.random(n) < 0.5, k["x"] - rng.uniform(1, 40, n), -1).astype(np.float32) if with_stereo else None
+    return dict(k=k, d=d, grid4=grid4, sf=pe.scale_factors, proj=proj, level=level, mp_desc=mp_desc, in_view=in_view, has_point=has_point,
+                u_right=u_right)
+
+
+def motion_scene(stereo, direction=0, seed=5, dense=False):
+    """Tracking::TrackWithMotionModel: the last frame's map points projected into the current frame with the predicted pose.
+    direction: 0 = sideways motion (level window oct-1 .. oct+1), +1 / -1 = forward / backward by more than the baseline (stereo
+    only: levels >= oct / <= oct).  A fraction of the last frame's points are temporal stereo points (no observations) and some
+    current key points already hold points -- both kinds of in-loop state of ORBmatcher.cc:1749-1751.  dense: several last-frame
+    points land on the same key points (collisions)."""
+    h, w = 480, 752
+    rng = np.random.default_rng(seed)
+    seq = synth.sequence(h, w, 40, canvas=1024, base_seed=900 + seed)
+    pe = port.PortExtractor(1000, 1.2, 8)
+    _, kl, dl, _ = pe.extract(seq[10])
+    _, kc, dc, _ = pe.extract(seq[11])
+    # image motion between the two crops (see synth.sequence): the texture moves by (-dx, -dy)
+    n_seq, span_x, span_y = 40, 1024 - w, 1024 - h
+    off = lambda i: (int(round((0.5 + 0.5 * np.sin(2 * np.pi * i / (n_seq - 1))) * span_x)), int(round((0.5 + 0.5 * np.cos(np.pi * i / (n_seq - 1))) * span_y)))
+    (x0, y0), (x1, y1) = off(10), off(11)
+    dx, dy = float(x0 - x1), float(y0 - y1)
+    fx = fy = np.float32(458.0)
+    cx, cy = np.float32(w / 2), np.float32(h / 2)
+    m = len(kl)
+    depth = rng.uniform(4.0, 9.0, m).astype(np.float32)
+    # last frame at the origin: X = depth * K^-1 (u, v, 1)
+    pos = np.stack([(kl["x"] - cx) / fx * depth, (kl["y"] - cy) / fy * depth, depth], 1).astype(np.float32)
+    zmean = 6.5
+    tz = {0: 0.0, 1: -0.9, -1: 0.9}[direction]                    # camera moves forward: points come closer (z decreases in the camera frame)
+    t = np.float32([dx * zmean / float(fx), dy * zmean / float(fy), tz])
+    ang = 0.01
+    R = np.float32([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+    Tcw = np.concatenate([R.ravel(), t]).astype(np.float32)
+    Tlw = np.concatenate([np.eye(3, dtype=np.float32).ravel(), np.zeros(3, np.float32)])
+    last_state = rng.choice([0, 1, 2], m, p=[0.15, 0.7, 0.15]).astype(np.uint8)
+    last_desc = dl.copy()
+    last_desc[:, :3] ^= rng.integers(0, 256, (m, 3), dtype=np.uint8) & rng.integers(0, 256, (m, 3), dtype=np.uint8)
+    if dense:                                                     # duplicate points: several map points project onto the same place
+        dup = rng.integers(0, m, m // 2)
+        sel = np.arange(m // 2)
+        pos[sel] = pos[dup] + rng.normal(0, 0.01, (m // 2, 3)).astype(np.float32)
+        last_desc[sel] = last_desc[dup]
+        last_state[sel] = rng.choice([1, 2], m // 2, p=[0.8, 0.2])
+    n = len(kc)
+    cur = dict(kps_xy=np.stack([kc["x"], kc["y"]], 1), octaves=kc["octave"].astype(np.int32), angles=kc["angle"], desc=dc,
+               u_right=(np.where(rng.random(n) < 0.6, kc["x"] - rng.uniform(2, 60, n), -1).astype(np.float32) if stereo else None),
+               state=rng.choice([0, 1, 2], n, p=[0.8, 0.12, 0.08]).astype(np.uint8),
+               fp=np.float32([0, w, 0, h, np.float32(64) / np.float32(w), np.float32(48) / np.float32(h), 40.0 if stereo else 0.0, 0.11 if stereo else 0.0]),
+               scale_factors=pe.scale_factors, Tcw=Tcw, cam4=np.float32([fx, fy, cx, cy]))
+    last_angle = kl["angle"].copy()
+    turn = rng.random(m) < 0.2
+    last_angle[turn] = (last_angle[turn] + rng.uniform(40, 320, int(turn.sum())).astype(np.float32)) % np.float32(360)      # inconsistent rotations
+    last = dict(octaves=kl["octave"].astype(np.int32), angles=last_angle, state=last_state, outlier=(rng.random(m) < 0.05).astype(np.uint8),
+                pos=pos, desc=last_desc, Tlw=Tlw)
+    return cur, last

@@ -1,0 +1,161 @@
+"""GPU: the compiled matcher replacements of the host adapter (orb_slam3_ros_b200/host/ORBmatcherGPU.cc: the two per-frame
+ORBmatcher::SearchByProjection overloads on top of orbb_search_area_topk, frames uploaded once) against the REFERENCE's own function
+bodies (cut out of ORBmatcher.cc at build time and compiled into oracle/_ref, see oracle/ref_cut_tu.cpp) on identical inputs: what the
+two leave in Frame::mvpMapPoints and the match counts must be identical.  Plus the device-resident frame views of the C ABI against
+the oracle port."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import port, ref
+from orb_slam3_ros_b200 import capi, synth
+from orb_slam3_ros_b200.extractor import ORBextractor
+from orb_slam3_ros_b200.matcher import ORBmatcher
+from scenes import local_points_scene, motion_scene
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+SO = ROOT / "tests" / "models" / "_build" / "libmatcher_host.so"
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def host():
+    """the adapter + harness compiled as C++14 against the stand-in headers (tests/host/slam_stub, tests/cvstub, oracle/cvshim/mini_geom.hpp)"""
+    from orb_slam3_ros_b200 import build
+    build.build_library()
+    SO.parent.mkdir(exist_ok=True)
+    pkg = ROOT / "orb_slam3_ros_b200"
+    subprocess.check_call(["g++", "-std=c++14", "-O2", "-ffp-contract=off", "-fPIC", "-shared", f"-I{ROOT / 'tests' / 'cvstub'}",
+                           f"-I{ROOT / 'tests' / 'host' / 'slam_stub'}", f"-I{ROOT / 'oracle' / 'cvshim'}", f"-I{ROOT / 'include'}", f"-I{pkg / 'host'}",
+                           str(ROOT / "tests" / "host" / "matcher_host.cpp"), str(pkg / "host" / "ORBmatcherGPU.cc"), f"-L{pkg}", "-lorbb200",
+                           f"-Wl,-rpath,{pkg}", "-o", str(SO)])
+    lib = C.CDLL(str(SO))
+    lib.gpuhost_rescans.restype = C.c_long
+    lib.gpuhost_search_by_projection.restype = C.c_int
+    lib.gpuhost_search_by_projection.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]
+    lib.gpuhost_search_by_projection_motion.restype = C.c_int
+    lib.gpuhost_search_by_projection_motion.argtypes = [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int] + \
+        [C.c_void_p] * 7 + [C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    return lib
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref (the reference's own object code) is not built")
+@pytest.mark.parametrize("with_stereo,th", [(False, 1.0), (True, 1.0), (False, 3.0)])
+def test_search_local_points_equals_reference(host, with_stereo, th):
+    """ORBmatcher::SearchByProjection(F, vpMapPoints, th) (ORBmatcher.cc:43-213): 1600 projected map points compete for ~1000 key points"""
+    s = local_points_scene(with_stereo)
+    k, d = s["k"], s["d"]
+    kxy = np.ascontiguousarray(np.stack([k["x"], k["y"]], 1), np.float32)
+    octs = np.ascontiguousarray(k["octave"], np.int32)
+    nm_ref, match_ref = ref.search_by_projection(kxy, octs, d, s["grid4"], s["sf"], s["proj"], s["level"], s["mp_desc"], s["in_view"], s["u_right"],
+                                                 s["has_point"], nnratio=0.8, th=th)
+    match = np.full(len(k), -1, np.int32)
+    sf = np.ascontiguousarray(s["sf"], np.float32)
+    r0 = host.gpuhost_rescans()
+    nm = host.gpuhost_search_by_projection(_p(kxy), _p(octs), _p(d), len(k), _p(s["grid4"]), _p(s["u_right"]), _p(s["has_point"]), _p(sf), len(sf),
+                                           _p(s["proj"]), _p(s["level"]), _p(s["mp_desc"]), _p(s["in_view"]), len(s["proj"]), 0.8, th, _p(match))
+    assert nm == nm_ref and np.array_equal(match, match_ref)
+    assert nm > 300
+    assert host.gpuhost_rescans() - r0 < 0.2 * len(s["proj"])      # the four-candidate lists resolve most collisions on the host
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref (the reference's own object code) is not built")
+@pytest.mark.parametrize("stereo,direction,dense", [(False, 0, False), (True, 0, False), (True, 1, False), (True, -1, True), (False, 0, True)])
+def test_motion_model_search_equals_reference(host, stereo, direction, dense):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (ORBmatcher.cc:1676-1887, Tracking::TrackWithMotionModel)"""
+    cur, last = motion_scene(stereo, direction, dense=dense)
+    th = 7 if stereo else 15
+    nm_ref, match_ref = ref.search_by_projection_motion(cur, last, th, mono=not stereo)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    a = [f32(cur["kps_xy"]), i32(cur["octaves"]), f32(cur["angles"]), u8(cur["desc"])]
+    n = len(a[1])
+    ur = None if cur["u_right"] is None else f32(cur["u_right"])
+    b = [f32(cur["fp"]), ur, u8(cur["state"]), f32(cur["scale_factors"])]
+    c = [f32(cur["Tcw"]), f32(cur["cam4"])]
+    l = [i32(last["octaves"]), f32(last["angles"]), u8(last["state"]), u8(last["outlier"]), f32(last["pos"]), u8(last["desc"]), f32(last["Tlw"])]
+    match = np.full(n, -1, np.int32)
+    nm = host.gpuhost_search_by_projection_motion(*[_p(x) for x in a], n, *[_p(x) for x in b], len(b[3]), *[_p(x) for x in c], len(l[0]),
+                                                  *[_p(x) for x in l], th, int(not stereo), 0.9, 1, _p(match))
+    assert nm == nm_ref and np.array_equal(match, match_ref)
+    assert nm_ref > 30
+
+
+def _frame_view(kxy, kstride, octs, ostride, desc, ur, n, on_device):
+    v = capi.FrameView()
+    v.kps_xy, v.kps_stride, v.octaves, v.oct_stride, v.desc, v.u_right, v.n, v.on_device = kxy, kstride, octs, ostride, desc, ur, n, on_device
+    return v
+
+
+def test_topk_scan_host_uploaded_and_extractor_resident_frames_agree_with_the_oracle():
+    """orbb_search_area_topk: (a) a host frame view, (b) the same frame uploaded once with orbb_frame_upload, (c) the extractor's own
+    device buffers (orbb_batch_device_ptrs: 24-byte key point records, the descriptors never leave the GPU) give the same lists; their
+    first two entries are the oracle's best / second best; the lists are sorted by (distance, scan order) and hold no duplicates"""
+    lib = capi.load()
+    img = synth.frame(480, 752, 12)
+    ge = ORBextractor(1000, 1.2, 8)
+    mono, k, d = ge(img, None, (0, 0))
+    n = len(k)
+    rng = np.random.default_rng(3)
+    nq = 700
+    src = rng.integers(0, n, nq)
+    queries = np.stack([k["x"][src] + rng.normal(0, 3, nq), k["y"][src] + rng.normal(0, 3, nq), rng.uniform(4, 30, nq), k["x"][src] - 10], 1).astype(np.float32)
+    qlev = np.stack([np.maximum(k["octave"][src] - 1, 0), k["octave"][src] + 1], 1).astype(np.int32)
+    qdesc = d[src].copy()
+    qdesc[:, 5] ^= 0x3c
+    skip = (rng.random(n) < 0.2).astype(np.uint8)
+    grid4 = np.float32([0, 0, 64 / 752, 48 / 480])
+    kxy = np.ascontiguousarray(np.stack([k["x"], k["y"]], 1), np.float32)
+    octs = np.ascontiguousarray(k["octave"], np.int32)
+    want = port.search_area_best2(kxy, octs, d, grid4, queries, qlev, qdesc, skip, None, 256)
+    m = ORBmatcher()
+    outs = []
+    hv = _frame_view(kxy.ctypes.data, 8, octs.ctypes.data, 4, d.ctypes.data, None, n, 0)
+    dv = capi.FrameView()
+    capi.check(lib.orbb_frame_upload(m._m, 1, C.byref(hv), C.byref(dv)), m._m, matcher=True)
+    kp_dev, desc_dev, cnt_dev = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    capi.check(lib.orbb_batch_device_ptrs(ge._h, C.byref(kp_dev), C.byref(desc_dev), C.byref(cnt_dev)), ge._h)
+    ev = _frame_view(kp_dev.value, 24, kp_dev.value + 20, 24, desc_dev.value, None, n, 1)      # (no distortion: mvKeysUn == mvKeys)
+    for view in (hv, dv, ev):
+        for kk in (2, 4, 8):
+            out = np.zeros((nq, kk, 2), np.int32)
+            capi.check(lib.orbb_search_area_topk(m._m, C.byref(view), _p(grid4), _p(queries), _p(qlev), _p(qdesc), nq, _p(skip), 256, kk, _p(out)),
+                       m._m, matcher=True)
+            assert np.array_equal(out[:, :2].reshape(nq, 4), want), kk
+            valid = out[:, :, 1] >= 0
+            assert (np.diff(np.where(valid, out[:, :, 0], 256), axis=1) >= 0).all()          # ascending distances
+            for q in range(0, nq, 37):
+                ids = out[q, valid[q], 1]
+                assert len(set(ids.tolist())) == len(ids) and not skip[ids].any()
+            outs.append(out)
+    assert all(np.array_equal(outs[i], outs[i % 3]) for i in range(len(outs)))               # the three views agree for every k
+    assert (outs[2][:, :, 1] >= 0).sum() > (outs[0][:, :, 1] >= 0).sum()                     # k = 8 really returns more
+
+
+def test_best2_csr_with_device_resident_train_descriptors():
+    lib = capi.load()
+    ge = ORBextractor(600, 1.2, 6)
+    mono, k, d = ge(synth.frame(300, 400, 5), None, (0, 0))
+    n = len(k)
+    rng = np.random.default_rng(1)
+    nq = 200
+    q = d[rng.integers(0, n, nq)].copy()
+    q[:, 0] ^= 0x81
+    rowptr = np.concatenate([[0], np.cumsum(rng.integers(0, 40, nq))]).astype(np.int32)
+    cand = rng.integers(0, n, rowptr[-1]).astype(np.int32)
+    want = port.best2_csr(q, d, cand, rowptr, 256)
+    kp_dev, desc_dev, cnt_dev = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    capi.check(lib.orbb_batch_device_ptrs(ge._h, C.byref(kp_dev), C.byref(desc_dev), C.byref(cnt_dev)), ge._h)
+    m = ORBmatcher()
+    out = np.zeros((nq, 4), np.int32)
+    capi.check(lib.orbb_best2_csr_dev(m._m, _p(q), nq, desc_dev, n, _p(cand), _p(rowptr), 256, _p(out)), m._m, matcher=True)
+    assert np.array_equal(out, want)

@@ -94,3 +94,24 @@ def test_adapter_matches_c_abi(tmp_path):
     for a, b in un.view(np.uint32):
         s = (s * 1000003 + int(a) + 7 * int(b)) & M
     assert int(got["sumU"]) == s
+
+
+def test_reference_call_site_text_compiles_against_the_adapter_header(tmp_path):
+    """Frame::ExtractORB (Frame.cc:418-425) and Frame::ComputeStereoMatches (Frame.cc:811-981), the reference's own text cut out at test
+    time, compile against orb_slam3_ros_b200/host/ORBextractor.h (with the OpenCV stand-in of oracle/cvshim, which carries cv::norm and
+    the Mat views ComputeStereoMatches needs).  Only where /root/reference exists (the development container)."""
+    import sys
+    ref_root = Path("/root/reference/orb_slam3")
+    if not (ref_root / "src" / "Frame.cc").exists():
+        pytest.skip("the reference sources are not present on this machine")
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import cut_reference
+    cut = tmp_path / "cut"
+    cut.mkdir()
+    lines = (ref_root / "src" / "Frame.cc").read_text(errors="replace").splitlines(keepends=True)
+    (cut / "Frame_ExtractORB.inc").write_text(cut_reference.cut(lines, r"^void Frame::ExtractORB\(int flag, const cv::Mat &im", "function", "Frame::ExtractORB"))
+    (cut / "Frame_ComputeStereoMatches.inc").write_text(cut_reference.cut(lines, r"^void Frame::ComputeStereoMatches\(\)", "function", "Frame::ComputeStereoMatches"))
+    pkg = ROOT / "orb_slam3_ros_b200"
+    r = subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-w", f"-I{ROOT / 'oracle' / 'cvshim'}", f"-I{pkg / 'host'}", f"-I{ROOT / 'include'}", f"-I{tmp_path}",
+                        str(ROOT / "tests" / "host" / "callsite_check.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]

@@ -388,3 +388,89 @@ def test_batched_search_by_bow_equals_reference_search_by_bow():
             match[i1] = -1
     assert int((match >= 0).sum()) == nm_ref and np.array_equal(match, match_ref)
     assert nm_ref > 100 and rescans > 0 and (~keep).sum() > 0              # matches, collisions and rotation rejects all occurred
+
+
+def _batched_motion_model(cur, last, th, mono, scan, check_orientation=True):
+    """ORBmatcherGPU::SearchByProjection(CurrentFrame, LastFrame, th, bMono) restated in numpy (orb_slam3_ros_b200/host/ORBmatcherGPU.cc):
+    all projections first, ONE batched grid lookup + best scan (`scan` = the oracle's search_area_best2), then the reference's
+    per-point decisions in order on the live state -- a key point that received a point WITH observations is skipped by later
+    points (ORBmatcher.cc:1749-1751), one that received a temporal point is not and can be overwritten."""
+    f32 = np.float32
+    R, t = cur["Tcw"][:9].astype(f32), cur["Tcw"][9:].astype(f32)
+    Rl, tl = last["Tlw"][:9].astype(f32), last["Tlw"][9:].astype(f32)
+
+    def apply(Rm, tv, p):
+        return [f32(f32(f32(f32(Rm[3 * i] * p[0]) + f32(Rm[3 * i + 1] * p[1])) + f32(Rm[3 * i + 2] * p[2])) + tv[i]) for i in range(3)]
+    Ri = [R[3 * j + i] for i in range(3) for j in range(3)]                     # inverse: (R^T, -R^T t)
+    twc = [f32(-f32(f32(f32(Ri[3 * i] * t[0]) + f32(Ri[3 * i + 1] * t[1])) + f32(Ri[3 * i + 2] * t[2]))) for i in range(3)]
+    tlc = apply(Rl, tl, twc)
+    mb, mbf = f32(cur["fp"][7]), f32(cur["fp"][6])
+    forward, backward = (tlc[2] > mb and not mono), (-tlc[2] > mb and not mono)
+    fx, fy, cx, cy = (f32(v) for v in cur["cam4"])
+    sf = cur["scale_factors"]
+    queries, qlev, qdesc, src = [], [], [], []
+    for i in range(len(last["octaves"])):
+        if not last["state"][i] or last["outlier"][i]:
+            continue
+        x, y, z = apply(R, t, last["pos"][i].astype(f32))
+        invz = f32(1.0 / float(z))
+        if invz < 0:
+            continue
+        u, v = f32(f32(f32(fx * x) / z) + cx), f32(f32(f32(fy * y) / z) + cy)
+        if u < cur["fp"][0] or u > cur["fp"][1] or v < cur["fp"][2] or v > cur["fp"][3]:
+            continue
+        o = int(last["octaves"][i])
+        queries.append([u, v, f32(f32(th) * sf[o]), f32(u - f32(mbf * invz))])
+        qlev.append([o, -1] if forward else [0, o] if backward else [o - 1, o + 1])
+        qdesc.append(last["desc"][i])
+        src.append(i)
+    queries, qlev, qdesc = np.float32(queries).reshape(-1, 4), np.int32(qlev).reshape(-1, 2), np.uint8(qdesc).reshape(-1, 32)
+    grid4 = np.float32([cur["fp"][0], cur["fp"][2], cur["fp"][4], cur["fp"][5]])
+    holds = cur["state"].astype(np.int64).copy()                                 # 0 none, 1 with observations, 2 without
+    assigned = np.full(len(holds), -1, np.int32)
+    skip = (holds == 1).astype(np.uint8)
+    out = scan(cur["kps_xy"], cur["octaves"], cur["desc"], grid4, queries, qlev, qdesc, skip, cur["u_right"], 256)
+    nmatches, rescans, votes = 0, 0, []
+    for j, i in enumerate(src):
+        d1, i1 = int(out[j][0]), int(out[j][1])
+        if i1 >= 0 and holds[i1] == 1:                                           # its best candidate was taken meanwhile: scan this point again
+            skip = (holds == 1).astype(np.uint8)
+            d1, i1 = (int(v) for v in scan(cur["kps_xy"], cur["octaves"], cur["desc"], grid4, queries[j:j + 1], qlev[j:j + 1], qdesc[j:j + 1], skip,
+                                           cur["u_right"], 256)[0][:2])
+            rescans += 1
+        if i1 < 0 or d1 > 100:
+            continue
+        holds[i1] = last["state"][i]
+        assigned[i1] = i
+        nmatches += 1
+        if check_orientation:
+            rot = f32(last["angles"][i] - cur["angles"][i1])
+            if rot < 0:
+                rot = f32(rot + f32(360))
+            b = int(np.round(f32(rot * f32(1.0 / 30))))                          # round(): half away from zero; rot >= 0 here
+            b = int(np.floor(float(f32(rot * f32(1.0 / 30))) + 0.5))
+            votes.append((0 if b == 30 else b, i1))
+    if check_orientation:
+        hist = np.bincount([b for b, _ in votes], minlength=30)
+        keep3 = set(int(v) for v in port.three_maxima(hist) if v >= 0)
+        for b, i1 in votes:
+            if b not in keep3:
+                assigned[i1] = -1
+                nmatches -= 1
+    return nmatches, assigned, rescans
+
+
+@pytest.mark.parametrize("stereo,direction,dense", [(False, 0, False), (True, 0, False), (True, 1, False), (True, -1, True), (False, 0, True)])
+def test_batched_motion_model_search_equals_reference_search_by_projection(stereo, direction, dense):
+    """the reference's own SearchByProjection(CurrentFrame, LastFrame, th, bMono) (Tracking::TrackWithMotionModel; its definition cut out of
+    ORBmatcher.cc:1676-1887 and compiled against the Eigen / Sophus stand-ins of oracle/cvshim/mini_geom.hpp) against the batched
+    formulation that the GPU host adapter implements, with the oracle's scan in the place of the device scan"""
+    from scenes import motion_scene
+    cur, last = motion_scene(stereo, direction, dense=dense)
+    th = 7 if stereo else 15                                                     # Tracking.cc:2918-2923
+    nm_ref, match_ref = ref.search_by_projection_motion(cur, last, th, mono=not stereo)
+    nm, match, rescans = _batched_motion_model(cur, last, th, not stereo, port.search_area_best2)
+    assert nm == nm_ref and np.array_equal(match, match_ref)
+    assert nm_ref > 30
+    if dense:
+        assert rescans > 0
