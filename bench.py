@@ -307,6 +307,7 @@ def measure_matcher_rows(local, with_cpu):
             row["cpu_ms"] = cpu_time(lambda: port.search_area_best2(kxy, octs, d, grid4, queries, qlev, qdesc, skip, None, 256))
             row["cpu_kind"] = "port"
     rows.append(row)
+    print("matcher_rows: scan done", file=sys.stderr, flush=True)
     # (2) best / second-best over candidate lists (SearchByBoW-shaped: 1000 queries x 30 candidates)
     nq = 1000
     q = d[rng.integers(0, n, nq)].copy()
@@ -321,6 +322,7 @@ def measure_matcher_rows(local, with_cpu):
         row["cpu_ms"] = cpu_time(lambda: port.best2_csr(q, d, cand, rowptr, 256))
         row["cpu_kind"] = "port (the reference's loop shape, one thread)"
     rows.append(row)
+    print("matcher_rows: best2 done", file=sys.stderr, flush=True)
     # (3) Frame::ComputeBoW: k = 10, L = 5 synthetic vocabulary (the ORBvoc blob is not available offline), one frame's descriptors
     vocab = synthetic_vocabulary(10, 5, seed=3)
     V = Vocabulary(vocab, device=local)
@@ -330,6 +332,7 @@ def measure_matcher_rows(local, with_cpu):
         row["cpu_ms"] = cpu_time(lambda: port.bow_transform(vocab, d, 4, 1))
         row["cpu_kind"] = "port (std::map restatement of TemplatedVocabulary::transform)"
     rows.append(row)
+    print("matcher_rows: bow done", file=sys.stderr, flush=True)
     # (4) MapPoint::ComputeDistinctiveDescriptors for 2000 map points with 8 observations each
     ng = 2000
     gd = d[rng.integers(0, n, ng * 8)].copy()
@@ -340,6 +343,7 @@ def measure_matcher_rows(local, with_cpu):
         row["cpu_ms"] = cpu_time(lambda: port.distinctive(gd, grp))
         row["cpu_kind"] = "port"
     rows.append(row)
+    print("matcher_rows: distinctive done", file=sys.stderr, flush=True)
     # (5) stereo rectification: cv::remap of one 752x480 frame (System.cc:233-240)
     yy, xx = np.mgrid[0:H_, 0:W_].astype(np.float32)
     mx = (xx + 3.0 * np.sin(yy / 57.0)).astype(np.float32)
@@ -543,6 +547,20 @@ def run_ours(a):
     for _ in range(100):
         ext1._lib.orbb_extract(*_args)
     single_c_ms = (time.perf_counter() - t0) / 100 * 1e3
+    # ... and with the hand-out of the pyramid that the C++ adapter does by default after every call (mvImagePyramid is a public member
+    # that Frame::ComputeStereoMatches reads): 19-px apron on the device + one copy of the frame's pyramid slab
+    _pp, _pw, _ph, _ps = _C.c_void_p(), _C.c_int(), _C.c_int(), _C.c_size_t()
+
+    def _with_pyramid():
+        ext1._lib.orbb_extract(*_args)
+        for lv in range(NLEVELS):
+            ext1._lib.orbb_pyramid_level(ext1._h, lv, _C.byref(_pp), _C.byref(_pw), _C.byref(_ph), _C.byref(_ps))
+    for _ in range(5):
+        _with_pyramid()
+    t0 = time.perf_counter()
+    for _ in range(100):
+        _with_pyramid()
+    single_pyr_ms = (time.perf_counter() - t0) / 100 * 1e3
     del ext1
 
     # ---- roofline of the dominant kernel (and of the whole path) ----
@@ -820,6 +838,7 @@ def run_ours(a):
             "keypoints_per_frame": n_kp / B,
             "single_frame_latency_ms": single_ms,
             "single_frame_c_abi_ms": single_c_ms,
+            "single_frame_with_pyramid_ms": single_pyr_ms,
             "sustained": sustained,
             "host": host_info,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -844,6 +863,8 @@ def _emit(line):
 
 
 if __name__ == "__main__":
+    import faulthandler
+    faulthandler.dump_traceback_later(1500, exit=True)      # a hung leg must not hang the caller: dump the stacks and exit after 25 minutes
     # C-level writers (NCCL prints its version banner to stdout) must not pollute the single JSON line
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)

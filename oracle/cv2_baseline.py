@@ -142,17 +142,41 @@ def rate(frames, params=(1000, 1.2, 8, 20, 7), lapping=(0, 1000), processes=1):
 
 def rates(frames, params=(1000, 1.2, 8, 20, 7), lapping=(0, 1000), processes=1):
     """-> (frames/s as run, frames/s counting only the time inside the cv2 primitives and the C++ glue -- the rate a C++ build of
-    the same calls would reach with no Python between them; both over `processes` concurrent workers)"""
+    the same calls would reach with no Python between them; both over `processes` concurrent workers).  The workers are fresh
+    interpreters (subprocess, not fork: the caller may hold a CUDA context and helper threads); each times its own share after a
+    warm-up frame, so interpreter start-up is not part of the number."""
     if processes <= 1:
         dt, tp = _worker((frames, params, lapping))
         return len(frames) / dt, len(frames) / tp
-    import multiprocessing as mp
-    parts = [frames[i::processes] for i in range(processes)]
-    parts = [p for p in parts if len(p)]
-    ctx = mp.get_context("fork")
-    t0 = time.perf_counter()
-    with ctx.Pool(len(parts)) as pool:
-        res = pool.map(_worker, [(p, params, lapping) for p in parts])
-    wall = time.perf_counter() - t0
-    # the workers run concurrently: the primitive-only rate of the pool is the sum of the per-worker rates
-    return len(frames) / wall, sum(len(p) / max(tp, 1e-9) for p, (_, tp) in zip(parts, res))
+    import subprocess
+    import sys
+    import tempfile
+    frames = np.ascontiguousarray(frames)
+    processes = min(processes, len(frames))
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "frames.npy")
+        np.save(path, frames)
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        cmd = [sys.executable, "-m", "oracle.cv2_baseline", path, str(processes)] + [repr(p) for p in params] + [str(lapping[0]), str(lapping[1])]
+        procs = [subprocess.Popen(cmd + [str(i)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, cwd=root, text=True) for i in range(processes)]
+        res = []
+        for pr in procs:
+            out, _ = pr.communicate(timeout=600)
+            n, dt, tp = out.split()[-3:]
+            res.append((int(n), float(dt), float(tp)))
+    # the workers run concurrently: the pool's rate is the sum of the per-worker rates
+    return sum(n / max(dt, 1e-9) for n, dt, _ in res), sum(n / max(tp, 1e-9) for n, _, tp in res)
+
+
+if __name__ == "__main__":      # worker: frames.npy processes nfeatures scale nlevels ini min lap0 lap1 index
+    import sys
+    a = sys.argv[1:]
+    fr = np.load(a[0], mmap_mode="r")
+    nproc, idx = int(a[1]), int(a[9])
+    prm = (int(a[2]), float(a[3]), int(a[4]), int(a[5]), int(a[6]))
+    lap = (int(a[7]), int(a[8]))
+    mine = np.ascontiguousarray(fr[idx::nproc])
+    cv2.setNumThreads(1)
+    Cv2Extractor(*prm).extract(mine[0], lap)      # warm-up (library loading, first-call allocations)
+    dt, tp = _worker((mine, prm, lap))
+    print(len(mine), dt, tp)

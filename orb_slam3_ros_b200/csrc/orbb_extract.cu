@@ -1512,9 +1512,11 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
     const orbb_extractor::Lane& ln = h->lanes[lane];
     cudaStream_t st = ln.st;
     // ORBB_NO_PDL=1: every kernel waits for the full completion of its predecessor before it is scheduled (A/B switch).  Stage
-    // profiling records events between the kernels, and a capturing stream (single-frame graph) keeps plain edges.
+    // profiling records events between the kernels and keeps plain launches.
     static const bool noPdl = getenv("ORBB_NO_PDL") != nullptr;
-    const bool pdl = !noPdl && !h->profiling && !h->capturing;
+    // (the single-frame CUDA graph keeps the programmatic edges: 0.143 -> 0.135 ms per call; ORBB_GRAPH_NO_PDL=1 captures plain edges)
+    static const bool graphPdl = getenv("ORBB_GRAPH_NO_PDL") == nullptr;
+    const bool pdl = !noPdl && !h->profiling && (!h->capturing || graphPdl);
     // ORBB_BLUR_EARLY=1: the blur forks right after the pyramid (beside the detector) instead of after the detector (beside the quadtree)
     static const bool blurEarly = getenv("ORBB_BLUR_EARLY") != nullptr;
     const bool fork = !h->profiling;
@@ -1553,6 +1555,14 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
         static const bool noTmap = getenv("ORBB_FAST_NO_TMAP") != nullptr;
         const dim3 grid(P.cellsTotal, nframes);
         const bool pdlFast = pdl && !(fork && blurEarly);      // (an event record between two kernels makes the edge a full dependency)
+        // a call with a few frames: four warps per cell (the kernel lasts as long as its slowest cell)
+        static const int fastLatencyFrames = getenv("ORBB_FAST_LATENCY_FRAMES") ? atoi(getenv("ORBB_FAST_LATENCY_FRAMES")) : 4;
+        if (nframes <= fastLatencyFrames) {
+            const int smem = P.cellSmem + (FC_MW - 1) * 2 * FC_CANDS;
+            const bool tm = h->tmapsValid && !noTmap;
+            if (P.cellTp == 64) { if (tm) launch_k(pdlFast, k_fast_cell_mw<64, true>, grid, 32 * FC_MW, smem, st, h->dPlan, B, h->tmaps, f0); else launch_k(pdlFast, k_fast_cell_mw<64, false>, grid, 32 * FC_MW, smem, st, h->dPlan, B, h->tmaps, f0); }
+            else { if (tm) launch_k(pdlFast, k_fast_cell_mw<96, true>, grid, 32 * FC_MW, smem, st, h->dPlan, B, h->tmaps, f0); else launch_k(pdlFast, k_fast_cell_mw<96, false>, grid, 32 * FC_MW, smem, st, h->dPlan, B, h->tmaps, f0); }
+        } else
         if (h->tmapsValid && !noTmap) {
             if (P.cellTp == 64) launch_k(pdlFast, k_fast_cell<64, true>, grid, 32, P.cellSmem, st, h->dPlan, B, h->tmaps, f0);
             else launch_k(pdlFast, k_fast_cell<96, true>, grid, 32, P.cellSmem, st, h->dPlan, B, h->tmaps, f0);
@@ -1592,7 +1602,7 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
         k_blur<true><<<dim3(P.blurEdgeTotal, nframes), BLUR_THREADS, 0, st>>>(h->dPlan, B);
     }
     mark(h, ST_ASSEMBLE);
-    k_assemble<<<nframes, 256, 0, st>>>(h->dPlan, B, lap0, lap1);
+    k_assemble<<<nframes, nframes <= 4 ? 1024 : 256, 0, st>>>(h->dPlan, B, lap0, lap1);      // (a call with a few frames: one pass over the key points instead of four)
     mark(h, ST_ORIENT_DESC);
     {   // ORBB_DESC_NO_STAGE=1: sample the blurred level through L1 instead of a shared-memory copy of the window (A/B switch)
         static const bool noStage = getenv("ORBB_DESC_NO_STAGE") != nullptr;

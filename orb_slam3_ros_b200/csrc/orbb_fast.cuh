@@ -50,13 +50,16 @@ __device__ __forceinline__ unsigned quick_bytes4(unsigned wl, unsigned wc, unsig
     return v & h;
 }
 
-// One cell, one warp.  tile: row t = level row gy0 - 3 + t, column = level column - X0 (pitch TP).  score: row s = interior
-// row s - 1, column = tile column - sxo (pitch SP: the cell's columns plus a zero column on each side).
+// One cell, NW warps (1 in batches; 4 in a call with a few frames, where the detector's duration is that of its slowest cell and
+// the GPU is otherwise idle: the warps split the work items of phase A -- each with its own candidate stack -- and share the score
+// map, the corner list and the survivor list through two counters in shared memory, sCnt = {corners, survivors}, zeroed by the
+// caller).  tile: row t = level row gy0 - 3 + t, column = level column - X0 (pitch TP).  score: row s = interior row s - 1,
+// column = tile column - sxo (pitch SP: the cell's columns plus a zero column on each side).
 // Returns the number of NMS survivors parked in `park`.
-template <int TP, int SP, bool EXACT>
+template <int TP, int SP, bool EXACT, int NW>
 __device__ __forceinline__ int cell_pass(const uint8_t* __restrict__ tile, uint8_t* __restrict__ score, unsigned short* candS,
                                          unsigned short* allS, unsigned* __restrict__ park, const CellDesc& cd, int ih, int th, unsigned K7,
-                                         int lane) {
+                                         int lane, int warp = 0, int* sCnt = nullptr) {
     constexpr int PS = TP, TPW = TP / 4;
     const int cx0 = cd.cx0, cx1 = cd.cx1, sxo = cx0 - 1;                 // score column 0 = the zero column left of the cell
     const int wa = cd.wa, wLast = cd.wLast, nwc = cd.nwc, items = cd.items;
@@ -64,7 +67,8 @@ __device__ __forceinline__ int cell_pass(const uint8_t* __restrict__ tile, uint8
     const unsigned M = th >= 128 ? 0xffffffffu : 0u;
     const unsigned* tileW = reinterpret_cast<const unsigned*>(tile) + wa;
     const unsigned lt = (1u << lane) - 1;
-    int nCand = 0, nAll = 0, base = 0;
+    int nCand = 0, nAll = 0, base = 32 * warp;
+    if (NW > 1) candS += warp * FC_CANDS;
     for (;;) {
         const bool aDone = base >= items;
         if (nCand >= 32 || (aDone && nCand > 0)) {
@@ -104,6 +108,11 @@ __device__ __forceinline__ int cell_pass(const uint8_t* __restrict__ tile, uint8
                 if (isCorner) score[sp] = (uint8_t)(M - 1);
             }
             const unsigned bal = __ballot_sync(0xffffffffu, isCorner);
+            if (NW > 1) {                                            // (the corner list is shared by the warps of the cell)
+                int first = 0;
+                if (lane == 0 && bal) first = atomicAdd(&sCnt[0], __popc(bal));
+                nAll = __shfl_sync(0xffffffffu, first, 0);
+            }
             const int slot = nAll + __popc(bal & lt);
             if (isCorner && slot < FC_NC) allS[slot] = (unsigned short)sp;
             nAll += __popc(bal);
@@ -138,9 +147,13 @@ __device__ __forceinline__ int cell_pass(const uint8_t* __restrict__ tile, uint8
                 if (cand & (0x80u << (8 * k))) *o++ = (unsigned short)(basev + k);
                 if (cand & (0x40u << (8 * k))) *o++ = (unsigned short)(basev + 256 + k);
             }
-            base += 32;
+            base += 32 * NW;
             __syncwarp();
         }
+    }
+    if (NW > 1) {
+        __syncthreads();                                             // every warp's scores and corners are in
+        nAll = sCnt[0];
     }
     // ---- D: NMS inside the cell (strict '>' against the 8 neighbours; outside the cell counts as 0) ----
     int nSurv = 0;
@@ -157,24 +170,33 @@ __device__ __forceinline__ int cell_pass(const uint8_t* __restrict__ tile, uint8
             rec = ((unsigned)(r1 - 1) << 16) | ((unsigned)(x - cx0) << 8) | (unsigned)sc;
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (NW > 1) {
+            int first = 0;
+            if (lane == 0 && bal) first = atomicAdd(&sCnt[1], __popc(bal));
+            nSurv = __shfl_sync(0xffffffffu, first, 0);
+        }
         if (keep) park[nSurv + __popc(bal & lt)] = rec;
         nSurv += __popc(bal);
     };
     if (nAll <= FC_NC) {
-        for (int b0 = 0; b0 < nAll; b0 += 32) {
+        for (int b0 = 32 * warp; b0 < nAll; b0 += 32 * NW) {
             const bool valid = b0 + lane < nAll;
             const int sp = valid ? allS[b0 + lane] : 0;
             nms(valid, sp, valid ? score[sp] : 0);
         }
     } else {                                                          // very dense cell: walk its score map
         const int wc = cx1 - cx0;
-        for (int b0 = 0; b0 < ih * wc; b0 += 32) {
+        for (int b0 = 32 * warp; b0 < ih * wc; b0 += 32 * NW) {
             const int i = b0 + lane;
             const int r = i / wc, x = cx0 + i - r * wc;
             const int sp = (r + 1) * SP + x - sxo;
             const int sc = i < ih * wc ? score[sp] : 0;
             nms(sc > 0, sp, sc);
         }
+    }
+    if (NW > 1) {
+        __syncthreads();                                             // all survivors are parked (global memory, same CTA)
+        nSurv = sCnt[1];
     }
     return nSurv;
 }
@@ -227,12 +249,12 @@ __global__ void __launch_bounds__(32, 32) k_fast_cell(const Plan* __restrict__ P
     const int iniTh = P->iniTh, minTh = P->minTh;
     int nSurv;
     if (iniTh < 128 && minTh < 128) {
-        nSurv = cell_pass<TP, SP, false>(tile, score, candS, allS, park, cd, ih, iniTh, P->k7Ini, lane);
+        nSurv = cell_pass<TP, SP, false, 1>(tile, score, candS, allS, park, cd, ih, iniTh, P->k7Ini, lane);
         if (nSurv == 0)                                       // :833-846 (scores do not depend on the threshold: the map stays valid)
-            nSurv = cell_pass<TP, SP, false>(tile, score, candS, allS, park, cd, ih, minTh, P->k7Min, lane);
+            nSurv = cell_pass<TP, SP, false, 1>(tile, score, candS, allS, park, cd, ih, minTh, P->k7Min, lane);
     } else {                                                  // thresholds >= 128: exact byte compare in the quick reject
-        nSurv = cell_pass<TP, SP, true>(tile, score, candS, allS, park, cd, ih, iniTh, P->k7Ini, lane);
-        if (nSurv == 0) nSurv = cell_pass<TP, SP, true>(tile, score, candS, allS, park, cd, ih, minTh, P->k7Min, lane);
+        nSurv = cell_pass<TP, SP, true, 1>(tile, score, candS, allS, park, cd, ih, iniTh, P->k7Ini, lane);
+        if (nSurv == 0) nSurv = cell_pass<TP, SP, true, 1>(tile, score, candS, allS, park, cd, ih, minTh, P->k7Min, lane);
     }
     // ---- E: raster order by rank counting; keys are relative to the 16-px border (:865-866) ----
     __syncwarp();
@@ -246,4 +268,71 @@ __global__ void __launch_bounds__(32, 32) k_fast_cell(const Plan* __restrict__ P
         keysOut[rank] = (u64)(unsigned)x | ((u64)(unsigned)y << 16) | ((u64)(rec & 0xffu) << 32);
     }
     if (lane == 0) *cellCount = nSurv;
+}
+
+// The same cell with FC_MW warps (see cell_pass): for calls with a few frames.  Results are identical -- the order in which
+// candidates, corners and survivors are found does not matter (NMS reads the finished score map, phase E sorts by rank).
+constexpr int FC_MW = 4;
+template <int TP, bool TMAP>
+__global__ void __launch_bounds__(32 * FC_MW) k_fast_cell_mw(const Plan* __restrict__ P, Bufs B, const __grid_constant__ TmapTable tmaps, int frame0) {
+    constexpr int SP = TP == 64 ? 48 : 80;
+    extern __shared__ __align__(128) uint8_t fcSmem[];
+    __shared__ __align__(8) unsigned long long sBar;
+    __shared__ int sCnt[2];
+    const int gcell = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_launch_dependents();
+    const CellDesc cd = B.cellDesc[gcell];
+    int* cellCount = B.cellCount + (size_t)frame * P->cellsTotal + gcell;
+    const int ih = cd.gy1 - cd.gy0;
+    pdl_wait();                                               // the pyramid is complete from here on
+    if (cd.gx1 <= cd.gx0 || ih <= 0) {
+        if (tid == 0) *cellCount = 0;
+        return;
+    }
+    const LevelPlan& L = P->lv[cd.level];
+    const int rowsT = ih + 6;
+    const int X0 = (cd.gx0 - 3) & ~15;
+    uint8_t* tile = fcSmem;
+    const int tileRows = TMAP ? P->cellRows : rowsT;
+    uint8_t* score = fcSmem + tileRows * TP;
+    unsigned short* candS = reinterpret_cast<unsigned short*>(score + (ih + 2) * SP);
+    unsigned short* allS = candS + FC_MW * FC_CANDS;
+    if (tid == 0) {
+        mbar_init(&sBar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&sBar, tileRows * TP);
+        if (TMAP) tma_tensor3d_g2s(tile, &tmaps.m[cd.level], kRoiX + X0, kEdge + cd.gy0 - 3, frame0 + frame, &sBar);
+        sCnt[0] = sCnt[1] = 0;
+    }
+    __syncthreads();
+    if (!TMAP) {
+        const uint8_t* roi = B.pyr + (size_t)frame * P->pyrStride + L.roiOff;
+        for (int r = tid; r < rowsT; r += 32 * FC_MW) tma_bulk_g2s(tile + r * TP, roi + (ptrdiff_t)(cd.gy0 - 3 + r) * L.pitch + X0, TP, &sBar);
+    }
+    for (int i = tid; i < (ih + 2) * (SP / 16); i += 32 * FC_MW) reinterpret_cast<uint4*>(score)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    mbar_wait(&sBar, 0);
+    unsigned* park = reinterpret_cast<unsigned*>(B.keys + ((size_t)frame * 2 + 1) * P->rawStride + cd.outOff);
+    const int iniTh = P->iniTh, minTh = P->minTh;
+    const bool exact = iniTh >= 128 || minTh >= 128;
+    int nSurv = exact ? cell_pass<TP, SP, true, FC_MW>(tile, score, candS, allS, park, cd, ih, iniTh, P->k7Ini, lane, warp, sCnt)
+                      : cell_pass<TP, SP, false, FC_MW>(tile, score, candS, allS, park, cd, ih, iniTh, P->k7Ini, lane, warp, sCnt);
+    if (nSurv == 0) {                                         // :833-846 (uniform: nSurv comes out of shared memory behind a barrier)
+        __syncthreads();
+        if (tid == 0) sCnt[0] = sCnt[1] = 0;
+        __syncthreads();
+        nSurv = exact ? cell_pass<TP, SP, true, FC_MW>(tile, score, candS, allS, park, cd, ih, minTh, P->k7Min, lane, warp, sCnt)
+                      : cell_pass<TP, SP, false, FC_MW>(tile, score, candS, allS, park, cd, ih, minTh, P->k7Min, lane, warp, sCnt);
+    }
+    // ---- E: raster order by rank counting ----
+    u64* keysOut = B.cellKeys + (size_t)frame * P->cellKeyStride + cd.outOff;
+    for (int i = tid; i < nSurv; i += 32 * FC_MW) {
+        const unsigned rec = __ldcg(park + i);
+        int rank = 0;
+        for (int k = 0; k < nSurv; k++) rank += __ldcg(park + k) < rec;
+        const int x = cd.gx0 + (int)((rec >> 8) & 0xffu) - kMinBorder;
+        const int y = cd.gy0 + (int)(rec >> 16) - kMinBorder;
+        keysOut[rank] = (u64)(unsigned)x | ((u64)(unsigned)y << 16) | ((u64)(rec & 0xffu) << 32);
+    }
+    if (tid == 0) *cellCount = nSurv;
 }
