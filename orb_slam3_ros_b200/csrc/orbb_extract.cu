@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(BLUR_THREADS, EDGE ? 8 : 12) k_blur(const Plan
 #pragma unroll
     for (int j = 0; j < 3; j++) { fetch(); pack(pk[j]); }
     fetch();
-#pragma unroll 1
+#pragma unroll 1                                              // (fully unrolled: 2.3 x the code, no faster)
     for (int mo = 0; mo < STRIP / 2; mo += 4) {               // (4 = the period of the row-pair ring pk[])
         if (2 * mo >= rows) break;
 #pragma unroll
@@ -1018,18 +1018,20 @@ __device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) {         // un
 }
 
 // STAGE: the 37 x 37 window of the blurred level that the rotated pattern can reach (|coordinate| <= 13 -> radius < 18.4) is first
-// copied into shared memory -- 37 rows x 10 aligned words, lane t of round q moves word 32q + t with a 4-byte cp.async, the copy of
-// keypoint k+1 running while keypoint k is sampled -- and the 512 samples are LDS.U8 with a few bank conflicts instead of global
-// gathers that cost ~12 L1 data-pipe wavefronts each (the L1 data pipe, at 83 % of its peak, bounded the un-staged kernel).
-constexpr int OD_PROWS = 37, OD_PWORDS = 10, OD_PATCH_WORDS = OD_PROWS * OD_PWORDS, OD_PROUNDS = (OD_PATCH_WORDS + 31) / 32;
+// copied into shared memory -- 37 rows x four 16-byte chunks from the 16-byte aligned column left of the window, lane t of round q moves
+// chunk 32q + t with one cp.async (5 rounds), the copy of keypoint k+1 running while keypoint k is sampled -- and the 512 samples
+// are LDS.U8 with a few bank conflicts instead of global gathers that cost ~12 L1 data-pipe wavefronts each (the L1 data pipe, at
+// 83 % of its peak, bounded the un-staged kernel: 0.251 -> 0.217 ms per 256 frames with 4-byte copies, 12 rounds).
+constexpr int OD_PROWS = 37, OD_PPITCH = 64, OD_PCHUNKS = OD_PROWS * (OD_PPITCH / 16), OD_PROUNDS = (OD_PCHUNKS + 31) / 32;
+constexpr int OD_PATCH_WORDS = OD_PROWS * OD_PPITCH / 4;
 
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
 
 template <bool STAGE>
 __global__ void __launch_bounds__(OD_THREADS, 4) k_orient_desc32(const Plan* __restrict__ P, Bufs B) {
-    __shared__ __align__(16) unsigned sPatch[STAGE ? OD_THREADS / 32 : 1][2][STAGE ? OD_PATCH_WORDS + 2 : 1];
+    __shared__ __align__(16) unsigned sPatch[STAGE ? OD_THREADS / 32 : 1][2][STAGE ? OD_PATCH_WORDS : 4];
     const int frame = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_launch_dependents();
@@ -1080,19 +1082,18 @@ __global__ void __launch_bounds__(OD_THREADS, 4) k_orient_desc32(const Plan* __r
 #pragma unroll
     for (int j = 0; j < 8; j++) pat[j] = __ldg(&gPatF[j * 32 + lane]);
     if constexpr (STAGE) {
-        unsigned (*patch)[OD_PATCH_WORDS + 2] = sPatch[warp];
+        unsigned (*patch)[OD_PATCH_WORDS] = sPatch[warp];
         auto stage = [&](int k) {                              // window of keypoint k -> patch[k & 1]
             const WorkItem wi = work[k];
             const LevelPlan& L = P->lv[wi.level];
-            const uint8_t* src = B.blur + (size_t)frame * P->blurStride + L.blurOff + (ptrdiff_t)(wi.y - 18) * L.bpitch + ((wi.x - 18) & ~3);
-            unsigned* dst = patch[k & 1];
+            // lane t of round q: row (32q + t) / 4, chunk (32q + t) % 4 = rows 8q + t / 4: the lane's source pointer advances by 8 rows per round
+            const uint8_t* src = B.blur + (size_t)frame * P->blurStride + L.blurOff + (ptrdiff_t)(wi.y - 18 + (lane >> 2)) * L.bpitch +
+                                 ((wi.x - 18) & ~15) + 16 * (lane & 3);
+            uint8_t* dst = reinterpret_cast<uint8_t*>(patch[k & 1]) + 16 * lane;
+            const ptrdiff_t step = (ptrdiff_t)8 * L.bpitch;
 #pragma unroll
             for (int q = 0; q < OD_PROUNDS; q++) {
-                const int t = q * 32 + lane;
-                if (q < OD_PROUNDS - 1 || t < OD_PATCH_WORDS) {
-                    const int row = (t * 205) >> 11;           // t / 10 for t < 1029
-                    cp_async4(dst + t, src + (ptrdiff_t)row * L.bpitch + 4 * (t - row * OD_PWORDS));
-                }
+                if (q < OD_PROUNDS - 1 || q * 32 + lane < OD_PCHUNKS) cp_async16(dst + q * 512, src + q * step);
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
@@ -1107,10 +1108,10 @@ __global__ void __launch_bounds__(OD_THREADS, 4) k_orient_desc32(const Plan* __r
             __syncwarp();
             const WorkItem wi = work[k];
             const float a = __shfl_sync(0xffffffffu, ca, k), b = __shfl_sync(0xffffffffu, sa, k);
-            // byte (r, c) of the window lies at (r + 18) * 40 + c + (x - xstart); r and c come out of the rounding trick biased by
+            // byte (r, c) of the window lies at (r + 18) * 64 + c + 18 + (x - 18) % 16; r and c come out of the rounding trick biased by
             // 0x4B400000 each (see round_rne): everything constant goes into the base
             const uint8_t* pb = reinterpret_cast<const uint8_t*>(patch[k & 1]) +
-                                (18 * 4 * OD_PWORDS + 18 + ((wi.x - 18) & 3) - (ptrdiff_t)0x4B400000 * (4 * OD_PWORDS + 1));
+                                (18 * OD_PPITCH + 18 + ((wi.x - 18) & 15) - (ptrdiff_t)0x4B400000 * (OD_PPITCH + 1));
             unsigned val = 0;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
@@ -1119,7 +1120,7 @@ __global__ void __launch_bounds__(OD_THREADS, 4) k_orient_desc32(const Plan* __r
                 const int c0 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, b)), 12582912.f));      // :119
                 const int r1 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(pt.z, b), __fmul_rn(pt.w, a)), 12582912.f));
                 const int c1 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(pt.z, a), __fmul_rn(pt.w, b)), 12582912.f));
-                const int t0 = pb[(ptrdiff_t)r0 * (4 * OD_PWORDS) + c0], t1 = pb[(ptrdiff_t)r1 * (4 * OD_PWORDS) + c1];
+                const int t0 = pb[(ptrdiff_t)r0 * OD_PPITCH + c0], t1 = pb[(ptrdiff_t)r1 * OD_PPITCH + c1];
                 val |= (unsigned)(t0 < t1) << j;
             }
             B.desc[((size_t)frame * P->kpCap + wi.pos) * 32 + lane] = (uint8_t)val;
@@ -1410,7 +1411,7 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
         for (int l = 0; l < nl; l++) { maxW = std::max(maxW, P.lv[l].wCell); maxH = std::max(maxH, P.lv[l].hCell); }
         P.cellTp = maxW + 21 <= 64 ? 64 : 96;
         P.cellRows = maxH + 6;
-        P.cellSmem = P.cellRows * P.cellTp + (maxH + 2) * (P.cellTp == 64 ? 48 : 80) + FC_STACK_BYTES;
+        P.cellSmem = (int)align_up(P.cellRows * P.cellTp + (maxH + 2) * (P.cellTp == 64 ? 48 : 80) + FC_STACK_BYTES, 128);
     }
     P.cellsTotal = cells; P.blurTilesTotal = tiles; P.blurEdgeTotal = edgeTiles; P.kpCap = kpCap;
     P.pyrStride = pyrBytes; P.blurStride = blurBytes;

@@ -102,6 +102,23 @@ public:
         if (rc != ORBB_OK) throw std::runtime_error(std::string("orbb_knn2 failed: ") + orbb_matcher_last_error(mpMatcher));
     }
 
+    // Frame::ComputeStereoFishEyeMatches (Frame.cc:1126-1166), the descriptor part: the key points inside the lapping area sit at the
+    // tail of both descriptor matrices (rows monoLeft.. / monoRight.., ORBextractor.cc:1153-1162), knnMatch(.., 2) between the two
+    // tails, Lowe's test (*it)[0].distance < (*it)[1].distance * 0.7 (:1151).  matches: (index in the left tail, index in the right
+    // tail, distance) of the pairs that pass, in left order -- what the reference triangulates next (:1152 ff.).
+    struct StereoTailMatch { int queryIdx, trainIdx, distance; };
+    std::vector<StereoTailMatch> StereoFishEyeMatches(const cv::Mat& descLeft, int monoLeft, const cv::Mat& descRight, int monoRight) {
+        std::vector<StereoTailMatch> out;
+        if (descLeft.rows <= monoLeft || descRight.rows <= monoRight) return out;
+        const cv::Mat l = descLeft.rowRange(monoLeft, descLeft.rows), r = descRight.rowRange(monoRight, descRight.rows);
+        std::vector<int> idx, dist;
+        KnnMatch2(l, r, idx, dist);
+        for (int i = 0; i < l.rows; i++)
+            if (idx[2 * i + 1] >= 0 && (double)(float)dist[2 * i] < (double)(float)dist[2 * i + 1] * 0.7)      // size() >= 2 && ratio
+                out.push_back(StereoTailMatch{i, idx[2 * i], dist[2 * i]});
+        return out;
+    }
+
     // Frame::UndistortKeyPoints (Frame.cc:747-780): cv::undistortPoints(mat, mat, K, mDistCoef, cv::Mat(), mK) over the keypoints.
     // K = (fx, fy, cx, cy); dist = mDistCoef.ptr<float>(), ndist = mDistCoef.rows (4 or 5); dist[0] == 0 copies the keys (:749).
     void UndistortKeyPoints(const std::vector<cv::KeyPoint>& keys, float fx, float fy, float cx, float cy, const float* dist, int ndist,

@@ -270,3 +270,30 @@ def test_best2_csr_rejects_bad_candidate_lists():
     cand = np.array([0, 1, 2, 3, 9, 5], np.int32)
     assert lib.orbb_best2_csr(m._m, capi.ptr(q), 4, capi.ptr(tr), 10, capi.ptr(cand), capi.ptr(good_row), 256, capi.ptr(out)) == 0
     assert np.array_equal(out, port.best2_csr(q, tr, cand, good_row, 256))
+
+
+def test_fisheye_stereo_tail_matching_equals_bfmatcher_with_ratio(matcher):
+    """Frame::ComputeStereoFishEyeMatches (Frame.cc:1126-1166), descriptor part: both eyes extracted with their lapping areas (key
+    points inside it are written from the back, so rows monoIndex.. of each descriptor matrix are the overlap), brute-force 2-NN between
+    the two tails, Lowe's 0.7 test -- against cv2.BFMatcher(NORM_HAMMING).knnMatch + the same test on the oracle's extraction"""
+    import torch
+    from oracle import orb_ref
+    left, right = synth.stereo_pair(376, 620, 9, dmax=30)
+    lap_l, lap_r = (250, 619), (0, 370)                       # Frame.cc:1059-1060: the overlapping columns of the two cameras
+    gl, gr = ORBextractor(800, 1.2, 8), ORBextractor(800, 1.2, 8)
+    ml, kl, dl = gl(left, None, lap_l)
+    mr, kr, dr = gr(right, None, lap_r)
+    rc, k0, d0, m0 = port.PortExtractor(800, 1.2, 8).extract(left, lap_l)
+    rc, k1, d1, m1 = port.PortExtractor(800, 1.2, 8).extract(right, lap_r)
+    assert (ml, mr) == (m0, m1) and np.array_equal(dl, d0) and np.array_equal(dr, d1)
+    assert 0 < ml < len(kl) and 0 < mr < len(kr)
+    tl, tr = dl[ml:], dr[mr:]
+    idx, dist = matcher.knn2(tl, tr)
+    d_i, d_d = torch.from_numpy(idx).cuda(), torch.from_numpy(dist).cuda()
+    keep = torch.zeros(len(tl), dtype=torch.uint8, device="cuda")
+    matcher.ratio_test_device(d_i, d_d, len(tl), 0.7, keep)
+    torch.cuda.synchronize()
+    i0, dd0 = orb_ref.bf_knn2(tl, tr)                          # cv2.BFMatcher
+    want = (i0[:, 1] >= 0) & (dd0[:, 0].astype(np.float32).astype(np.float64) < dd0[:, 1].astype(np.float32).astype(np.float64) * 0.7)
+    assert np.array_equal(idx, i0) and np.array_equal(dist, dd0)
+    assert np.array_equal(keep.cpu().numpy().astype(bool), want) and 5 < want.sum() < len(tl)
