@@ -1343,8 +1343,10 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
         // quadtree (:559-561)
         L.nFeat = h->featPerLevel[l];
         L.nIni = emptyLevel ? 1 : (int)roundf((float)(L.maxBX - kMinBorder) / (L.maxBY - kMinBorder));      // (no keys: the root count is immaterial)
-        if (L.nIni <= 0 || L.nIni > kMaxIni)
-            return set_err(h, ORBB_ERR_UNSUPPORTED, "level %d aspect ratio gives %d root nodes (reference: undefined behaviour for 0)", l, L.nIni);
+        if (L.nIni <= 0)
+            return set_err(h, ORBB_ERR_UNSUPPORTED, "level %d aspect ratio gives %d root nodes: undefined behaviour in the reference (out-of-range write at ORBextractor.cc:585)", l, L.nIni);
+        if (L.nIni > kMaxIni)
+            return set_err(h, ORBB_ERR_UNSUPPORTED, "level %d is more than %d.5 times wider than high (%d root nodes): beyond this library's limit", l, kMaxIni, L.nIni);
         L.hX = (float)(L.maxBX - kMinBorder) / L.nIni;
         L.rawBase = raw; L.rawCap = L.nCols * L.nRows * L.cellCap; raw += (unsigned)L.rawCap;
         L.maxNodes = std::max(L.nFeat + 2, 4 * L.nIni) + 6;
