@@ -1,11 +1,12 @@
 """ctypes binding of liborbb200.so (include/orbb200.h).  No fallback: if the CUDA library is missing this raises."""
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "liborbb200.so"
+LIB_PATH = Path(os.environ["ORBB_LIB"]) if os.environ.get("ORBB_LIB") else PKG / "liborbb200.so"      # (ORBB_LIB: A/B runs against another build)
 
 ORBB_OK = 0
 ORBB_ERR_EMPTY = -1

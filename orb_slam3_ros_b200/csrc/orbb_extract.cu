@@ -8,7 +8,8 @@
 //   k_octree                      DistributeOctTree         :555-779    (array-rebuild formulation, see
 //                                                                         tests/models/octree_array_model.cpp)
 //   k_blur                        cv::GaussianBlur 7x7 s=2  :1133       (8.8 fixed point; on a side stream beside k_octree)
-//   k_assemble                    output ordering / scaling / lapping split   :1105-1167
+//   k_assemble                    output ordering / scaling / lapping split   :1105-1167 (batches; the prologue of the next kernel in
+//                                 a call with a few frames)
 //   k_orient_desc32               IC_Angle + fastAtan2 + computeOrbDescriptor :76-146
 // plus the input-side rows: k_gray (cvtColor) and k_remap (cv::remap rectification, orbb_rectify.cuh).
 //
@@ -879,7 +880,8 @@ __global__ void __launch_bounds__(OT_T) k_octree(const Plan* __restrict__ P, Buf
 
 // ------------------------------------------------------------------------------------------------
 // K6: output assembly (:1105-1167): level-major order, pt *= scale for level > 0, keypoints inside the lapping
-// area are written from the back, the others from the front.  One CTA per frame.
+// area are written from the back, the others from the front.  One CTA per frame.  (Batches; a call with a few frames does this in the
+// prologue of k_orient_desc32<.., true> instead.)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_assemble(const Plan* __restrict__ P, Bufs B, int lap0, int lap1) {
     const int frame = blockIdx.x;
@@ -1029,18 +1031,109 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
 
-template <bool STAGE>
-__global__ void __launch_bounds__(OD_THREADS, 4) k_orient_desc32(const Plan* __restrict__ P, Bufs B) {
+// The output assembly (K6, :1105-1167) is the kernel's prologue: a CTA derives the level, the level coordinates and the output position
+// of its 64 key points itself -- level offsets from the quadtree's per-level counts, and for the lapping split the number of key points
+// inside [lap0, lap1] BEFORE its first one, counted by the CTA over the selected keys (<= 1000 8-byte reads from L2).  That removes a
+// kernel of one CTA per frame from the critical path (15 us per 256 frames, 11 of the 135 us of the single-frame call).
+constexpr int OD_CTA_KPS = (OD_THREADS / 32) * OD_KPW;          // key points per CTA (64)
+
+template <bool STAGE, bool ASM>
+__global__ void __launch_bounds__(OD_THREADS, 4) k_orient_desc32(const Plan* __restrict__ P, Bufs B, int lap0, int lap1) {
     __shared__ __align__(16) unsigned sPatch[STAGE ? OD_THREADS / 32 : 1][2][STAGE ? OD_PATCH_WORDS : 4];
+    __shared__ int sOff[ASM ? ORBB_MAX_LEVELS + 1 : 1];
+    __shared__ int sRed[ASM ? OD_THREADS / 32 + 2 : 1];
+    __shared__ WorkItem sWork[ASM ? OD_CTA_KPS : 1];
     const int frame = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_launch_dependents();
     pdl_wait();
-    const int n = B.outCount[frame * 2];
-    const int g0 = (blockIdx.x * (OD_THREADS / 32) + warp) * OD_KPW;
+    int n, g0;
+    const WorkItem* work;
+    if constexpr (!ASM) {                                     // batches: k_assemble has run
+        n = B.outCount[frame * 2];
+        g0 = (blockIdx.x * (OD_THREADS / 32) + warp) * OD_KPW;
+        work = B.work + (size_t)frame * P->kpCap + g0;
+    } else {
+    // ---- 0. output assembly: level-major order, pt *= scale for level > 0, key points inside the lapping area from the back ----
+    const int nl = P->nlevels;
+    if (warp == 0) {                                          // exclusive prefix of the per-level counts (ORBB_MAX_LEVELS <= 32)
+        const int c = lane < nl ? B.selCount[frame * ORBB_MAX_LEVELS + lane] : 0;
+        const int inc = warp_incl_scan(c, lane);
+        if (lane < nl) sOff[lane] = inc - c;
+        if (lane == nl - 1) sOff[nl] = inc;
+    }
+    __syncthreads();
+    n = min(sOff[nl], P->kpCap);
+    const int G0 = blockIdx.x * OD_CTA_KPS;
+    if (blockIdx.x != 0 && G0 >= n) return;                   // (uniform; CTA 0 always runs: it writes the frame's counts)
+    const float fl0 = (float)lap0, fl1 = (float)lap1;
+    const u64* selF = B.sel + (size_t)frame * P->selStride;
+    auto key_of = [&](int g, int& level) {                    // selected key g of the frame in level-major order
+        level = 0;
+        while (g >= sOff[level + 1]) level++;
+        return selF[P->lv[level].selBase + (g - sOff[level])];
+    };
+    auto lapping = [&](u64 k, int level) {                    // :1149-1153
+        float xs = (float)(int)(k & 0xffff);
+        if (level != 0) xs = __fmul_rn(xs, P->lv[level].scale);
+        return xs >= fl0 && xs <= fl1;
+    };
+    // key points inside the lapping area before this CTA's first one (CTA 0 also counts the whole frame: monoIndex)
+    const int countTo = blockIdx.x == 0 ? n : min(G0, n);
+    int before = 0, total = 0;
+    for (int g = tid; g < countTo; g += OD_THREADS) {
+        int level;
+        const u64 k = key_of(g, level);
+        const int st = lapping(k, level);
+        total += st;
+        before += g < G0 ? st : 0;
+    }
+    before = warp_sum(before);
+    total = warp_sum(total);
+    if (lane == 0) sRed[warp] = blockIdx.x == 0 ? total : before;
+    __syncthreads();
+    int stBefore = 0;
+    for (int w = 0; w < OD_THREADS / 32; w++) stBefore += sRed[w];
+    if (blockIdx.x == 0) {
+        if (tid == 0) {
+            B.outCount[frame * 2] = n;
+            B.outCount[frame * 2 + 1] = n - stBefore;         // monoIndex: key points written at the front
+            if (sOff[nl] > P->kpCap) atomicOr(&B.status[frame], 2);
+        }
+        stBefore = 0;                                         // (CTA 0 starts at key point 0)
+    }
+    if (G0 >= n) return;                                      // (uniform)
+    __syncthreads();                                          // sRed is reused below
+    if (tid < OD_CTA_KPS) {                                   // warps 0 and 1: one key point per thread
+        const int g = G0 + tid;
+        bool st = false;
+        int level = 0, x = 0, y = 0;
+        float xs = 0, ys = 0, resp = 0;
+        if (g < n) {
+            const u64 k = key_of(g, level);
+            x = (int)(k & 0xffff); y = (int)((k >> 16) & 0xffff); resp = (float)(int)(k >> 32);
+            xs = (float)x; ys = (float)y;
+            if (level != 0) { xs = __fmul_rn(xs, P->lv[level].scale); ys = __fmul_rn(ys, P->lv[level].scale); }      // :1149-1151
+            st = xs >= fl0 && xs <= fl1;                                                                              // :1153
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, st);
+        if (lane == 0) sRed[OD_THREADS / 32 + warp] = __popc(bal);
+        asm volatile("bar.sync 1, 64;" ::: "memory");         // the two warps that hold key points
+        const int stHere = stBefore + (warp == 1 ? sRed[OD_THREADS / 32] : 0) + __popc(bal & ((1u << lane) - 1));
+        if (g < n) {
+            const int pos = st ? n - 1 - stHere : g - stHere;
+            orbb_keypoint kp;
+            kp.x = xs; kp.y = ys; kp.size = P->lv[level].kpSize; kp.angle = -1.f; kp.response = resp; kp.octave = level;
+            B.kps[(size_t)frame * P->kpCap + pos] = kp;
+            sWork[tid] = WorkItem{level, x, y, pos};
+        }
+    }
+    __syncthreads();
+    g0 = G0 + warp * OD_KPW;
+    work = sWork + warp * OD_KPW;
+    }
     if (g0 >= n) return;
     const int cnt = min(OD_KPW, n - g0);
-    const WorkItem* work = B.work + (size_t)frame * P->kpCap + g0;
     const uint8_t* pyr = B.pyr + (size_t)frame * P->pyrStride;
     // ---- 1. IC_Angle moments (:76-103) ----
     int M10 = 0, M01 = 0;
@@ -1604,17 +1697,27 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
         k_blur<false><<<dim3(P.blurTilesTotal, nframes), BLUR_THREADS, 0, st>>>(h->dPlan, B);
         k_blur<true><<<dim3(P.blurEdgeTotal, nframes), BLUR_THREADS, 0, st>>>(h->dPlan, B);
     }
+    // output assembly: its own kernel in batches (one CTA per frame, free beside the other lane); folded into the prologue of the
+    // next kernel in a call with a few frames, where it is 11 us on the critical path (measured: fused 1.289 vs 1.249 ms per 256
+    // frames, but 0.128 vs 0.135 ms for one frame)
+    static const int asmLatencyFrames = getenv("ORBB_ASM_LATENCY_FRAMES") ? atoi(getenv("ORBB_ASM_LATENCY_FRAMES")) : 4;
+    const bool fusedAsm = nframes <= asmLatencyFrames;
     mark(h, ST_ASSEMBLE);
-    k_assemble<<<nframes, nframes <= 4 ? 1024 : 256, 0, st>>>(h->dPlan, B, lap0, lap1);      // (a call with a few frames: one pass over the key points instead of four)
+    if (!fusedAsm) { k_assemble<<<nframes, 256, 0, st>>>(h->dPlan, B, lap0, lap1); h->launches++; }
     mark(h, ST_ORIENT_DESC);
     {   // ORBB_DESC_NO_STAGE=1: sample the blurred level through L1 instead of a shared-memory copy of the window (A/B switch)
         static const bool noStage = getenv("ORBB_DESC_NO_STAGE") != nullptr;
         const dim3 grid((P.kpCap + OD_THREADS / 32 * OD_KPW - 1) / (OD_THREADS / 32 * OD_KPW), nframes);
-        if (noStage) launch_k(pdl, k_orient_desc32<false>, grid, OD_THREADS, 0, st, h->dPlan, B);
-        else launch_k(pdl, k_orient_desc32<true>, grid, OD_THREADS, 0, st, h->dPlan, B);
+        if (fusedAsm) {                                        // (behind the joins of the blur streams the edge is a full dependency anyway)
+            if (noStage) launch_k(pdl && !fork, k_orient_desc32<false, true>, grid, OD_THREADS, 0, st, h->dPlan, B, lap0, lap1);
+            else launch_k(pdl && !fork, k_orient_desc32<true, true>, grid, OD_THREADS, 0, st, h->dPlan, B, lap0, lap1);
+        } else {
+            if (noStage) launch_k(pdl, k_orient_desc32<false, false>, grid, OD_THREADS, 0, st, h->dPlan, B, lap0, lap1);
+            else launch_k(pdl, k_orient_desc32<true, false>, grid, OD_THREADS, 0, st, h->dPlan, B, lap0, lap1);
+        }
     }
     mark(h, ST_D2H);
-    h->launches += 6;
+    h->launches += 5;
     ORBB_CUDA(h, cudaGetLastError());
     return ORBB_OK;
 }
