@@ -1616,6 +1616,43 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
     // ORBB_BLUR_EARLY=1: the blur forks right after the pyramid (beside the detector) instead of after the detector (beside the quadtree)
     static const bool blurEarly = getenv("ORBB_BLUR_EARLY") != nullptr;
     const bool fork = !h->profiling;
+    // a call with a few frames: every level gets its own branch (detector + quadtree of level l start as soon as level l of the pyramid
+    // exists, beside the resize chain of the smaller levels; the blur forks after the last resize).  The critical path is then the longest
+    // level branch instead of pyramid + slowest cell of any level + slowest quadtree of any level.  ORBB_BRANCH_FRAMES=0 keeps one chain.
+    static const int branchFrames = getenv("ORBB_BRANCH_FRAMES") ? atoi(getenv("ORBB_BRANCH_FRAMES")) : 4;
+    const bool perLevel = fork && !blurEarly && lane == 0 && nframes <= branchFrames;
+    // ORBB_FAST_NO_TMAP=1: stage the cell tiles with one bulk copy per row instead of one tensor-map copy (A/B switch; also the
+    // path taken when the driver cannot encode the tensor maps)
+    static const bool noTmap = getenv("ORBB_FAST_NO_TMAP") != nullptr;
+    // a call with a few frames: four warps per cell (the kernel lasts as long as its slowest cell)
+    static const int fastLatencyFrames = getenv("ORBB_FAST_LATENCY_FRAMES") ? atoi(getenv("ORBB_FAST_LATENCY_FRAMES")) : 4;
+    auto launchFast = [&](cudaStream_t s, bool pdlFast, int cell0, int ncells) {
+        const dim3 grid(ncells, nframes);
+        const bool tm = h->tmapsValid && !noTmap;
+        if (nframes <= fastLatencyFrames) {
+            const int smem = P.cellSmem + (FC_MW - 1) * 2 * FC_CANDS;
+            if (P.cellTp == 64) { if (tm) launch_k(pdlFast, k_fast_cell_mw<64, true>, grid, 32 * FC_MW, smem, s, h->dPlan, B, h->tmaps, f0, cell0); else launch_k(pdlFast, k_fast_cell_mw<64, false>, grid, 32 * FC_MW, smem, s, h->dPlan, B, h->tmaps, f0, cell0); }
+            else { if (tm) launch_k(pdlFast, k_fast_cell_mw<96, true>, grid, 32 * FC_MW, smem, s, h->dPlan, B, h->tmaps, f0, cell0); else launch_k(pdlFast, k_fast_cell_mw<96, false>, grid, 32 * FC_MW, smem, s, h->dPlan, B, h->tmaps, f0, cell0); }
+        } else if (tm) {
+            if (P.cellTp == 64) launch_k(pdlFast, k_fast_cell<64, true>, grid, 32, P.cellSmem, s, h->dPlan, B, h->tmaps, f0, cell0);
+            else launch_k(pdlFast, k_fast_cell<96, true>, grid, 32, P.cellSmem, s, h->dPlan, B, h->tmaps, f0, cell0);
+        } else {
+            if (P.cellTp == 64) launch_k(pdlFast, k_fast_cell<64, false>, grid, 32, P.cellSmem, s, h->dPlan, B, h->tmaps, f0, cell0);
+            else launch_k(pdlFast, k_fast_cell<96, false>, grid, 32, P.cellSmem, s, h->dPlan, B, h->tmaps, f0, cell0);
+        }
+        h->launches++;
+    };
+    // images whose first level has many cells (4K class) get the large CTA on every level: more warps split nodes at once
+    // 512 threads per (frame, level) for levels with many cells -- and for a call with a few frames, where the quadtree of
+    // level 0 is one CTA on the critical path and a warp issues one dependent instruction every few cycles: more warps split
+    // more nodes at once, and nodes with many keys are split by the whole CTA
+    static const int otLatencyFrames = getenv("ORBB_OCTREE_LATENCY_FRAMES") ? atoi(getenv("ORBB_OCTREE_LATENCY_FRAMES")) : 4;
+    auto launchTree = [&](cudaStream_t s, bool pdlTree, int level0, int nlev) {
+        if (P.lv[0].nCols * P.lv[0].nRows >= OT_BIG_CELLS) launch_k(pdlTree, k_octree<OT_THREADS_BIG>, dim3(nframes, nlev), OT_THREADS_BIG, 0, s, h->dPlan, B, level0, (int)OT_BIG_NODE);
+        else if (nframes <= otLatencyFrames) launch_k(pdlTree, k_octree<OT_THREADS_BIG>, dim3(nframes, nlev), OT_THREADS_BIG, 0, s, h->dPlan, B, level0, (int)OT_BIG_NODE_LATENCY);
+        else launch_k(pdlTree, k_octree<OT_THREADS>, dim3(nframes, nlev), OT_THREADS, 0, s, h->dPlan, B, level0, (int)OT_BIG_NODE);
+        h->launches++;
+    };
     mark(h, ST_PYRAMID);
     ORBB_CUDA(h, cudaMemsetAsync(B.status, 0, sizeof(int) * nframes, st));
     for (int l = 0; l < P.nlevels; l++) {
@@ -1643,44 +1680,24 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
             else launch_k(pdl, k_pyr_resize_s, dim3(grid.x, (L.h + rowsPerCta - 1) / rowsPerCta, nframes), PR_THREADS, 0, st, h->dPlan, B, l);
         } else launch_k(pdl, k_pyr_resize, grid, 256, 0, st, h->dPlan, B, l);
         h->launches++;
-    }
-    if (fork && blurEarly) ORBB_CUDA(h, cudaEventRecord(ln.evFork, st));
-    mark(h, ST_FAST);
-    {   // ORBB_FAST_NO_TMAP=1: stage the cell tiles with one bulk copy per row instead of one tensor-map copy (A/B switch; also the
-        // path taken when the driver cannot encode the tensor maps)
-        static const bool noTmap = getenv("ORBB_FAST_NO_TMAP") != nullptr;
-        const dim3 grid(P.cellsTotal, nframes);
-        const bool pdlFast = pdl && !(fork && blurEarly);      // (an event record between two kernels makes the edge a full dependency)
-        // a call with a few frames: four warps per cell (the kernel lasts as long as its slowest cell)
-        static const int fastLatencyFrames = getenv("ORBB_FAST_LATENCY_FRAMES") ? atoi(getenv("ORBB_FAST_LATENCY_FRAMES")) : 4;
-        if (nframes <= fastLatencyFrames) {
-            const int smem = P.cellSmem + (FC_MW - 1) * 2 * FC_CANDS;
-            const bool tm = h->tmapsValid && !noTmap;
-            if (P.cellTp == 64) { if (tm) launch_k(pdlFast, k_fast_cell_mw<64, true>, grid, 32 * FC_MW, smem, st, h->dPlan, B, h->tmaps, f0); else launch_k(pdlFast, k_fast_cell_mw<64, false>, grid, 32 * FC_MW, smem, st, h->dPlan, B, h->tmaps, f0); }
-            else { if (tm) launch_k(pdlFast, k_fast_cell_mw<96, true>, grid, 32 * FC_MW, smem, st, h->dPlan, B, h->tmaps, f0); else launch_k(pdlFast, k_fast_cell_mw<96, false>, grid, 32 * FC_MW, smem, st, h->dPlan, B, h->tmaps, f0); }
-        } else
-        if (h->tmapsValid && !noTmap) {
-            if (P.cellTp == 64) launch_k(pdlFast, k_fast_cell<64, true>, grid, 32, P.cellSmem, st, h->dPlan, B, h->tmaps, f0);
-            else launch_k(pdlFast, k_fast_cell<96, true>, grid, 32, P.cellSmem, st, h->dPlan, B, h->tmaps, f0);
-        } else {
-            if (P.cellTp == 64) launch_k(pdlFast, k_fast_cell<64, false>, grid, 32, P.cellSmem, st, h->dPlan, B, h->tmaps, f0);
-            else launch_k(pdlFast, k_fast_cell<96, false>, grid, 32, P.cellSmem, st, h->dPlan, B, h->tmaps, f0);
+        if (perLevel) {
+            cudaStream_t ls = h->lvlSt[l];
+            ORBB_CUDA(h, cudaEventRecord(h->evLvl[l], st));
+            ORBB_CUDA(h, cudaStreamWaitEvent(ls, h->evLvl[l], 0));
+            if (L.nCols * L.nRows > 0) launchFast(ls, false, L.cellBase, L.nCols * L.nRows);
+            launchTree(ls, pdl && L.nCols * L.nRows > 0, l, 1);
+            ORBB_CUDA(h, cudaEventRecord(h->evTree[l], ls));
         }
-        h->launches++;
     }
+    if (fork && (blurEarly || perLevel)) ORBB_CUDA(h, cudaEventRecord(ln.evFork, st));
+    mark(h, ST_FAST);
+    if (!perLevel) launchFast(st, pdl && !(fork && blurEarly), 0, P.cellsTotal);      // (an event record between two kernels makes the edge a full dependency)
     mark(h, ST_OCTREE);
     // fork: the blur only needs the pyramid; on its own stream it fills the SMs that the latency-bound quadtree leaves idle.
     // With stage profiling on, everything stays on one stream so that the stage events mean what they say.
-    if (fork && !blurEarly) ORBB_CUDA(h, cudaEventRecord(ln.evFork, st));
-    const bool pdlTree = pdl && (!fork || blurEarly);
-    // images whose first level has many cells (4K class) get the large CTA on every level: more warps split nodes at once
-    // 512 threads per (frame, level) for levels with many cells -- and for a call with a few frames, where the quadtree of
-    // level 0 is one CTA on the critical path and a warp issues one dependent instruction every few cycles: more warps split
-    // more nodes at once, and nodes with many keys are split by the whole CTA
-    static const int otLatencyFrames = getenv("ORBB_OCTREE_LATENCY_FRAMES") ? atoi(getenv("ORBB_OCTREE_LATENCY_FRAMES")) : 4;
-    if (P.lv[0].nCols * P.lv[0].nRows >= OT_BIG_CELLS) launch_k(pdlTree, k_octree<OT_THREADS_BIG>, dim3(nframes, P.nlevels), OT_THREADS_BIG, 0, st, h->dPlan, B, 0, (int)OT_BIG_NODE);
-    else if (nframes <= otLatencyFrames) launch_k(pdlTree, k_octree<OT_THREADS_BIG>, dim3(nframes, P.nlevels), OT_THREADS_BIG, 0, st, h->dPlan, B, 0, (int)OT_BIG_NODE_LATENCY);
-    else launch_k(pdlTree, k_octree<OT_THREADS>, dim3(nframes, P.nlevels), OT_THREADS, 0, st, h->dPlan, B, 0, (int)OT_BIG_NODE);
+    if (fork && !blurEarly && !perLevel) ORBB_CUDA(h, cudaEventRecord(ln.evFork, st));
+    if (!perLevel) launchTree(st, pdl && (!fork || blurEarly), 0, P.nlevels);
+    else for (int l = 0; l < P.nlevels; l++) ORBB_CUDA(h, cudaStreamWaitEvent(st, h->evTree[l], 0));
     if (fork) {
         ORBB_CUDA(h, cudaStreamWaitEvent(ln.blurSt, ln.evFork, 0));
         ORBB_CUDA(h, cudaStreamWaitEvent(ln.blurEdgeSt, ln.evFork, 0));
@@ -1717,7 +1734,7 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
         }
     }
     mark(h, ST_D2H);
-    h->launches += 5;
+    h->launches += 3;
     ORBB_CUDA(h, cudaGetLastError());
     return ORBB_OK;
 }
@@ -1800,6 +1817,11 @@ int orbb_create(const orbb_params* prm, orbb_extractor** out) {
         cudaEventCreateWithFlags(&ln.evStart, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ln.evDone, cudaEventDisableTiming);
     }
+    for (int l = 0; l < ORBB_MAX_LEVELS; l++) {
+        cudaStreamCreateWithFlags(&h->lvlSt[l], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&h->evLvl[l], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&h->evTree[l], cudaEventDisableTiming);
+    }
     for (int i = 0; i < 8; i++) {
         cudaEventCreateWithFlags(&h->evH2D[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&h->evDone[i], cudaEventDisableTiming);
@@ -1839,6 +1861,11 @@ void orbb_destroy(orbb_extractor* h) {
         if (ln.evJoinEdge) cudaEventDestroy(ln.evJoinEdge);
         if (ln.evStart) cudaEventDestroy(ln.evStart);
         if (ln.evDone) cudaEventDestroy(ln.evDone);
+    }
+    for (int l = 0; l < ORBB_MAX_LEVELS; l++) {
+        if (h->lvlSt[l]) { cudaStreamSynchronize(h->lvlSt[l]); cudaStreamDestroy(h->lvlSt[l]); }
+        if (h->evLvl[l]) cudaEventDestroy(h->evLvl[l]);
+        if (h->evTree[l]) cudaEventDestroy(h->evTree[l]);
     }
     cudaStreamDestroy(h->stream);
     delete h;

@@ -207,11 +207,11 @@ __device__ __forceinline__ int cell_pass(const uint8_t* __restrict__ tile, uint8
 // (Two independent cells per 64-thread CTA -- shared memory instead of the 32-CTA limit bounding the cells in flight, 39 instead of 32
 // per SM -- measured slower: 0.515 vs 0.477 ms per 256 frames.)
 template <int TP, bool TMAP>
-__global__ void __launch_bounds__(32, 32) k_fast_cell(const Plan* __restrict__ P, Bufs B, const __grid_constant__ TmapTable tmaps, int frame0) {
+__global__ void __launch_bounds__(32, 32) k_fast_cell(const Plan* __restrict__ P, Bufs B, const __grid_constant__ TmapTable tmaps, int frame0, int cell0) {
     constexpr int SP = TP == 64 ? 48 : 80;                    // score pitch: cell width (<= 43 / 71) + a zero column on each side
     extern __shared__ __align__(128) uint8_t fcSmem[];
     __shared__ __align__(8) unsigned long long sBar;
-    const int gcell = blockIdx.x, frame = blockIdx.y, lane = threadIdx.x;
+    const int gcell = blockIdx.x + cell0, frame = blockIdx.y, lane = threadIdx.x;
     pdl_launch_dependents();
     const CellDesc cd = B.cellDesc[gcell];                    // (plan data, not a product of the previous kernel)
     int* cellCount = B.cellCount + (size_t)frame * P->cellsTotal + gcell;
@@ -276,12 +276,12 @@ __global__ void __launch_bounds__(32, 32) k_fast_cell(const Plan* __restrict__ P
 // candidates, corners and survivors are found does not matter (NMS reads the finished score map, phase E sorts by rank).
 constexpr int FC_MW = 4;
 template <int TP, bool TMAP>
-__global__ void __launch_bounds__(32 * FC_MW) k_fast_cell_mw(const Plan* __restrict__ P, Bufs B, const __grid_constant__ TmapTable tmaps, int frame0) {
+__global__ void __launch_bounds__(32 * FC_MW) k_fast_cell_mw(const Plan* __restrict__ P, Bufs B, const __grid_constant__ TmapTable tmaps, int frame0, int cell0) {
     constexpr int SP = TP == 64 ? 48 : 80;
     extern __shared__ __align__(128) uint8_t fcSmem[];
     __shared__ __align__(8) unsigned long long sBar;
     __shared__ int sCnt[2];
-    const int gcell = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gcell = blockIdx.x + cell0, frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_launch_dependents();
     const CellDesc cd = B.cellDesc[gcell];
     int* cellCount = B.cellCount + (size_t)frame * P->cellsTotal + gcell;

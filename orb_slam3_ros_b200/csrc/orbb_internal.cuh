@@ -181,6 +181,9 @@ struct orbb_extractor {
     // lane the blur runs on a side stream beside the quadtree (both only read the pyramid).  Lane 0 uses `stream`.
     struct Lane { cudaStream_t st = nullptr, blurSt = nullptr, blurEdgeSt = nullptr; cudaEvent_t evFork = nullptr, evJoin = nullptr, evJoinEdge = nullptr, evStart = nullptr, evDone = nullptr; };
     Lane lanes[4];
+    // one branch per pyramid level in a call with a few frames (run_lane)
+    cudaStream_t lvlSt[ORBB_MAX_LEVELS] = {};
+    cudaEvent_t evLvl[ORBB_MAX_LEVELS] = {}, evTree[ORBB_MAX_LEVELS] = {};
     int nLanes = 2;                // lanes of a resident batch (ORBB_LANES=1..4)
     // plan for the current image size
     orbb::Plan plan;
