@@ -337,6 +337,9 @@ constexpr int OT_THREADS = 128;          // CTA size of the quadtree kernel for 
 constexpr int OT_THREADS_BIG = 512;      // ... and for levels with many cells (4K-class images): more warps split nodes at once
 constexpr int OT_BIG_CELLS = 1000;
 constexpr int OT_SORT_SMEM = 1024;
+constexpr int OT_SMEM_KEYS = 8192;        // keys per shared-memory buffer of the quadtree of a call with a few frames (2 x 64 KB)
+constexpr int OT_SMEM_NODES = 512;        // ... and nodes per shared-memory node array
+constexpr int OT_SMEM_BYTES = OT_SMEM_KEYS * 16 + OT_SMEM_NODES * (2 * 16 + 16 + 2 * 4 + 4 + 1);
 
 __device__ __forceinline__ int node_count(const QNode& n) { return n.cntbuf & 0x7fffffff; }
 __device__ __forceinline__ int node_buf(const QNode& n) { return (unsigned)n.cntbuf >> 31; }
@@ -555,7 +558,119 @@ __device__ void sort_emul_cta(u64* a, int n, int* Lp, int* Rp, unsigned* leaf, i
     for (int s = tid; s < nLeaf; s += nthreads) insertion_sort(a, (int)(leaf[s] & 0xffffu), (int)(leaf[s] >> 16));
 }
 
-template <int OT_T>
+#ifdef ORBB_OT_TIMING
+// debug build only (tools/ot_timing.py): clock64 at the phase boundaries of the level-0 quadtree of frame 0
+__device__ long long g_otT[64];
+__device__ int g_otN;
+#define OT_TS(tag) do { if (tid == 0 && level == 0 && frame == 0 && g_otN < 31) { g_otT[2 * g_otN] = clock64(); g_otT[2 * g_otN + 1] = (tag); g_otN++; } } while (0)
+#define OT_TS_RESET() do { if (tid == 0 && level == 0 && frame == 0) g_otN = 0; } while (0)
+extern "C" int orbb_debug_ot_timing(long long* out) {
+    int n = 0;
+    cudaMemcpyFromSymbol(&n, g_otN, sizeof(int));
+    cudaMemcpyFromSymbol(out, g_otT, sizeof(long long) * 64);
+    return n;
+}
+#else
+#define OT_TS(tag) do {} while (0)
+#define OT_TS_RESET() do {} while (0)
+#endif
+
+// The same arrangement for n <= OT_SORT_SMEM records in shared memory, breadth first: the ranges left by a partition step are disjoint
+// and may be partitioned in any order, so round r partitions ALL ranges of recursion depth r at once, one warp per range (the chain
+// of dependent steps is the depth of the recursion, ~log2(n / 16), instead of the number of ranges, ~n / 10).  One ascending pass
+// lists l_k and the r positions (ascending: r_k = Ra[nr - 1 - k]) in the range's own part of Lp / Ra; then one thread per RECORD
+// ranks it inside its leaf range (a stable insertion sort of <= 16 records = position by (key, original index)).
+// Lp, Ra: int[n]; leafOf: unsigned[n]; tmp: u64[n]; ranges: unsigned[2][OT_SORT_RANGES]; cnt: int[2].
+constexpr int OT_SORT_RANGES = 64;          // ranges of > 16 records are disjoint: <= n / 17 of them
+__device__ void sort_emul_bf(u64* a, int n, int* Lp, int* Ra, unsigned* leafOf, u64* tmp, unsigned (*ranges)[OT_SORT_RANGES], int* cnt, int tid,
+                             int nthreads) {
+    if (n <= 1) return;                                     // (uniform)
+    const int lane = tid & 31, warp = tid >> 5, nw = nthreads >> 5;
+    const unsigned lt = (1u << lane) - 1;
+    const int INF = 0x7fffffff;
+    int lg = 0;
+    for (int t = n; t > 1; t >>= 1) lg++;
+    if (n <= 16) {
+        if (tid < n) leafOf[tid] = (unsigned)n << 16;
+        if (tid == 0) cnt[0] = 0;
+    } else if (tid == 0) { ranges[0][0] = (unsigned)n << 16; cnt[0] = 1; }
+    if (tid == 0) cnt[1] = 0;
+    __syncthreads();
+    int cur = 0;
+    for (int depth = 2 * lg; ; depth--) {                   // (uniform: every range of a round has the same recursion depth)
+        const int nr_ = cnt[cur];
+        if (nr_ == 0) break;
+        for (int ri = warp; ri < nr_; ri += nw) {
+            const unsigned fl = ranges[cur][ri];
+            const int first = (int)(fl & 0xffffu), last = (int)(fl >> 16);
+            if (depth == 0) {                               // depth limit: heapsort of the range, serial (adversarial inputs only)
+                if (lane == 0) heap_sort_range(a, first, last);
+                for (int p = first + lane; p < last; p += 32) leafOf[p] = (unsigned)p | ((unsigned)(p + 1) << 16);
+                continue;
+            }
+            {                                               // std::__move_median_to_first(first, first+1, mid, last-1): every lane decides, lane 0 swaps
+                const int x = first + 1, y = first + (last - first) / 2, z = last - 1;
+                const u64 ax = a[x], ay = a[y], az = a[z];
+                int w;
+                if (rec_less(ax, ay)) w = rec_less(ay, az) ? y : rec_less(ax, az) ? z : x;
+                else w = rec_less(ax, az) ? x : rec_less(ay, az) ? z : y;
+                __syncwarp();
+                if (lane == 0) rec_swap(a, first, w);
+                __syncwarp();
+            }
+            const u64 pk = a[first] >> ORBB_SORT_PAYLOAD_BITS;
+            int nl = 0, nr = 0;
+            for (int base = first; base < last; base += 32) {
+                const int p = base + lane;
+                const u64 key = p < last ? a[p] >> ORBB_SORT_PAYLOAD_BITS : 0;
+                const bool fL = p > first && p < last && !(key < pk), fR = p < last && !(pk < key);
+                const unsigned bL = __ballot_sync(0xffffffffu, fL), bR = __ballot_sync(0xffffffffu, fR);
+                if (fL) Lp[first + nl + __popc(bL & lt)] = p;
+                if (fR) Ra[first + nr + __popc(bR & lt)] = p;
+                nl += __popc(bL);
+                nr += __popc(bR);
+            }
+            __syncwarp();
+            const int m = min(nl, nr);
+            int K = 0;
+            for (int base = 0; base < m; base += 32) {      // (l_k < r_k holds for a prefix of k)
+                const int k = base + lane;
+                const unsigned ok = __ballot_sync(0xffffffffu, k < m && Lp[first + min(k, m - 1)] < Ra[first + nr - 1 - min(k, m - 1)]);
+                K += __popc(ok);
+                if (ok != 0xffffffffu) break;
+            }
+            for (int k = lane; k < K; k += 32) rec_swap(a, Lp[first + k], Ra[first + nr - 1 - k]);
+            const int cut = min(K < nl ? Lp[first + K] : INF, K > 0 ? Ra[first + nr - K] : INF);
+            // children: [first, cut) and [cut, last); the ones that are still long go to the next round
+            if (cut - first > 16) { if (lane == 0) ranges[cur ^ 1][atomicAdd(&cnt[cur ^ 1], 1)] = (unsigned)first | ((unsigned)cut << 16); }
+            else if (lane < cut - first) leafOf[first + lane] = (unsigned)first | ((unsigned)cut << 16);
+            if (last - cut > 16) { if (lane == 0) ranges[cur ^ 1][atomicAdd(&cnt[cur ^ 1], 1)] = (unsigned)cut | ((unsigned)last << 16); }
+            else if (lane < last - cut) leafOf[cut + lane] = (unsigned)cut | ((unsigned)last << 16);
+        }
+        __syncthreads();
+        if (tid == 0) cnt[cur] = 0;
+        cur ^= 1;
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += nthreads) {
+        const unsigned fl = leafOf[i];
+        const int f = (int)(fl & 0xffffu), l = (int)(fl >> 16);
+        const u64 rec = a[i], key = rec >> ORBB_SORT_PAYLOAD_BITS;
+        int pos = f;
+        for (int j = f; j < l; j++) {
+            const u64 kj = a[j] >> ORBB_SORT_PAYLOAD_BITS;
+            pos += (kj < key) || (kj == key && j < i);
+        }
+        tmp[pos] = rec;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nthreads) a[i] = tmp[i];
+}
+
+// LAT (a call with a few frames, one CTA per SM): keys and node arrays live in dynamic shared memory when the level fits, and the
+// pending list is sorted breadth first -- every phase of the tree is a chain of dependent round trips, so their latency is the run time.
+// Batches keep global arrays (plain LDG/STG instead of generic accesses, ~10 CTAs per SM) and the one-warp sort.
+template <int OT_T, bool LAT>
 __global__ void __launch_bounds__(OT_T) k_octree(const Plan* __restrict__ P, Bufs B, int level0, int bigNode) {
     constexpr int OT_W = OT_T / 32;
     // grid = (frames, levels): CTAs are dispatched x-fastest, so the long-running low levels of ALL frames start first and
@@ -566,11 +681,13 @@ __global__ void __launch_bounds__(OT_T) k_octree(const Plan* __restrict__ P, Buf
     const int N = L.nFeat;
     pdl_launch_dependents();
     pdl_wait();
+    OT_TS_RESET();
+    OT_TS(0);
 
     const int* cellCount = B.cellCount + (size_t)frame * P->cellsTotal + L.cellBase;
     int* cellOff = B.cellOff + (size_t)frame * P->cellsTotal + L.cellBase;
     const u64* cellKeys = B.cellKeys + (size_t)frame * P->cellKeyStride + L.cellKeyBase;
-    u64* k0 = B.keys + ((size_t)frame * 2 + 0) * P->rawStride + L.rawBase;
+    u64* k0 = B.keys + ((size_t)frame * 2 + 0) * P->rawStride + L.rawBase;      // (not const: see sKeyBuf)
     u64* k1 = B.keys + ((size_t)frame * 2 + 1) * P->rawStride + L.rawBase;
     QNode* nodesAB[2] = {B.nodes + ((size_t)frame * 2 + 0) * P->nodeStride + L.nodeBase,
                          B.nodes + ((size_t)frame * 2 + 1) * P->nodeStride + L.nodeBase};
@@ -587,8 +704,9 @@ __global__ void __launch_bounds__(OT_T) k_octree(const Plan* __restrict__ P, Buf
     __shared__ u64 sRec[OT_SORT_SMEM];
     __shared__ int sSplitPart[OT_W][4];
     __shared__ int sBigList[OT_BIG_LIST], sNBig;
-    __shared__ int sSortL[OT_SORT_SMEM], sSortR[OT_SORT_SMEM], sSortStk[192], sSortLeaves;
-    __shared__ unsigned sSortLeaf[OT_SORT_SMEM];
+    __shared__ int sSortL[OT_SORT_SMEM], sSortR[OT_SORT_SMEM], sSortStk[192], sSortLeaves, sSortCnt[2];
+    __shared__ unsigned sSortLeaf[OT_SORT_SMEM], sSortRanges[2][OT_SORT_RANGES];
+    __shared__ u64 sSortTmp[LAT ? OT_SORT_SMEM : 1];
 
     // ---- 1. gather vToDistributeKeys in the reference's order: cell-row-major, raster inside the cell ----
     const int nCells = L.nCols * L.nRows;
@@ -609,7 +727,20 @@ __global__ void __launch_bounds__(OT_T) k_octree(const Plan* __restrict__ P, Buf
     }
     if (tid < kMaxIni) sSlotCnt[tid] = 0;
     __syncthreads();
+    OT_TS(1);
     const int n = sN;
+    if (LAT) {
+        extern __shared__ __align__(16) unsigned char sDyn[];
+        if (n <= OT_SMEM_KEYS) { k0 = reinterpret_cast<u64*>(sDyn); k1 = k0 + OT_SMEM_KEYS; }
+        if (L.maxNodes <= OT_SMEM_NODES) {
+            unsigned char* q = sDyn + (size_t)OT_SMEM_KEYS * 16;
+            nodesAB[0] = reinterpret_cast<QNode*>(q); nodesAB[1] = nodesAB[0] + OT_SMEM_NODES; q += 2 * OT_SMEM_NODES * sizeof(QNode);
+            cnt4 = reinterpret_cast<int4*>(q); q += OT_SMEM_NODES * sizeof(int4);
+            pendAB[0] = reinterpret_cast<int*>(q); pendAB[1] = pendAB[0] + OT_SMEM_NODES; q += 2 * OT_SMEM_NODES * sizeof(int);
+            elist = reinterpret_cast<int*>(q); q += OT_SMEM_NODES * sizeof(int);
+            erased = q;
+        }
+    }
     // one thread per cell: the loads of a cell's keys are independent (read-only path), so their latencies overlap instead
     // of adding up cell after cell
     for (int c = tid; c < nCells; c += OT_T) {
@@ -619,6 +750,7 @@ __global__ void __launch_bounds__(OT_T) k_octree(const Plan* __restrict__ P, Buf
         for (int i = 0; i < cnt; i++) k0[off + i] = __ldg(src + i);
     }
     __syncthreads();
+    OT_TS(2);
 
     // ---- 2. root nodes (:559-601): keys bucketed by (int)(x / hX), stable ----
     const int nIni = L.nIni;
@@ -692,6 +824,7 @@ __global__ void __launch_bounds__(OT_T) k_octree(const Plan* __restrict__ P, Buf
         sNodes = m; sCur = 0; sPcur = 0; sPend = 0; sFinish = 0; sPhase2 = 0;
     }
     __syncthreads();
+    OT_TS(3);
 
     // ---- 3. main loop (:610-755) ----
     while (true) {
@@ -728,6 +861,7 @@ __global__ void __launch_bounds__(OT_T) k_octree(const Plan* __restrict__ P, Buf
             }
             __syncthreads();
             const int m = sM;
+            OT_TS(10);
             if (m == 0) break;                                      // size == prevSize (:685)
             const int nBig = OT_T > 128 ? sNBig : 0;
             for (int b = 0; b < nBig; b++) {                        // (uniform)
@@ -740,6 +874,7 @@ __global__ void __launch_bounds__(OT_T) k_octree(const Plan* __restrict__ P, Buf
                 if (!done) split_node_warp(nodes[elist[e]], k0, k1, &cnt4[elist[e]], lane);
             }
             __syncthreads();
+            OT_TS(11);
             if (warp == 0) {
                 int T = 0, X = 0;
                 for (int base = 0; base < m; base += 32) {
@@ -781,6 +916,7 @@ __global__ void __launch_bounds__(OT_T) k_octree(const Plan* __restrict__ P, Buf
                 }
             }
             __syncthreads();
+            OT_TS(12);
         } else {
             // ---------- phase 2: sort the pending nodes, split from the back until N nodes exist (:692-753) ----------
             const int len = sPend;
@@ -794,13 +930,19 @@ __global__ void __launch_bounds__(OT_T) k_octree(const Plan* __restrict__ P, Buf
                     srt[e] = ((u64)(unsigned)node_count(nd) << 40) | ((u64)(unsigned short)nd.x0 << 24) | (u64)(unsigned)idx;
             }
             __syncthreads();
+            OT_TS(20);
+#ifdef ORBB_OT_TIMING
+            if (tid == 0 && level == 0 && frame == 0) { g_otT[61] = len; g_otT[62] = nNodes; g_otT[63] = n; }
+#endif
             // std::sort(..., compareNodes) :700
-            if (len <= OT_SORT_SMEM) sort_emul_cta(srt, len, sSortL, sSortR, sSortLeaf, sSortStk, &sSortLeaves, tid, OT_T);
+            if (LAT && len <= OT_SORT_SMEM) sort_emul_bf(srt, len, sSortL, sSortR, sSortLeaf, sSortTmp, sSortRanges, sSortCnt, tid, OT_T);
+            else if (len <= OT_SORT_SMEM) sort_emul_cta(srt, len, sSortL, sSortR, sSortLeaf, sSortStk, &sSortLeaves, tid, OT_T);
             else {
                 int* tmp = B.sortTmp + (size_t)frame * 3 * P->nodeStride + 3 * (size_t)L.nodeBase;
                 sort_emul_cta(srt, len, tmp, tmp + L.maxNodes, reinterpret_cast<unsigned*>(tmp + 2 * L.maxNodes), sSortStk, &sSortLeaves, tid, OT_T);
             }
             __syncthreads();
+            OT_TS(21);
             if (warp == 0) {
                 // processing order i = 0..len-1 is the sorted vector walked from the back (:701)
                 int kstar = len, run = 0;
@@ -853,6 +995,7 @@ __global__ void __launch_bounds__(OT_T) k_octree(const Plan* __restrict__ P, Buf
                 }
             }
             __syncthreads();
+            OT_TS(22);
         }
     }
     __syncthreads();
@@ -872,6 +1015,10 @@ __global__ void __launch_bounds__(OT_T) k_octree(const Plan* __restrict__ P, Buf
         }
         sel[i] = best + (u64)kMinBorder + ((u64)kMinBorder << 16);
     }
+#ifdef ORBB_OT_TIMING
+    __syncthreads();
+#endif
+    OT_TS(4);
     if (tid == 0) {
         B.selCount[frame * ORBB_MAX_LEVELS + level] = min(nOut, L.selCap);
         if (nOut > L.selCap) atomicOr(&B.status[frame], 1);
@@ -1538,8 +1685,8 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
     A(b.work, F * kpCap);
     A(b.kps, F * kpCap);
     A(b.desc, F * kpCap * 32);
-    A(b.outCount, F * 2);
-    A(b.status, F);
+    A(b.outCount, F * 3);                  // counts (2 per frame), then the status words: one copy brings both to the host
+    b.status = b.outCount + F * 2;
     A(b.uRight, F * kpCap);
     A(b.depth, F * kpCap);
     A(b.bestR, F * kpCap);
@@ -1550,6 +1697,7 @@ static int build_plan(orbb_extractor* h, int W, int H, int frames) {
 #undef A
     if (!tab.empty()) ORBB_CUDA(h, cudaMemcpyAsync(b.tab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
     ORBB_CUDA(h, cudaMemcpyAsync(dCellDesc, cellDesc.data(), cellDesc.size() * sizeof(CellDesc), cudaMemcpyHostToDevice, h->stream));
+    ORBB_CUDA(h, (cudaFuncSetAttribute(k_octree<OT_THREADS_BIG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, OT_SMEM_BYTES)));
     ORBB_CUDA(h, (cudaFuncSetAttribute(k_fast_cell<64, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)));
     ORBB_CUDA(h, (cudaFuncSetAttribute(k_fast_cell<96, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)));
     ORBB_CUDA(h, (cudaFuncSetAttribute(k_fast_cell<64, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)));
@@ -1647,10 +1795,13 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
     // level 0 is one CTA on the critical path and a warp issues one dependent instruction every few cycles: more warps split
     // more nodes at once, and nodes with many keys are split by the whole CTA
     static const int otLatencyFrames = getenv("ORBB_OCTREE_LATENCY_FRAMES") ? atoi(getenv("ORBB_OCTREE_LATENCY_FRAMES")) : 4;
+    // ORBB_OCTREE_NO_SMEM=1: the quadtree of a call with a few frames keeps keys and nodes in global memory and sorts with one warp (A/B switch)
+    static const bool otNoSmem = getenv("ORBB_OCTREE_NO_SMEM") != nullptr;
     auto launchTree = [&](cudaStream_t s, bool pdlTree, int level0, int nlev) {
-        if (P.lv[0].nCols * P.lv[0].nRows >= OT_BIG_CELLS) launch_k(pdlTree, k_octree<OT_THREADS_BIG>, dim3(nframes, nlev), OT_THREADS_BIG, 0, s, h->dPlan, B, level0, (int)OT_BIG_NODE);
-        else if (nframes <= otLatencyFrames) launch_k(pdlTree, k_octree<OT_THREADS_BIG>, dim3(nframes, nlev), OT_THREADS_BIG, 0, s, h->dPlan, B, level0, (int)OT_BIG_NODE_LATENCY);
-        else launch_k(pdlTree, k_octree<OT_THREADS>, dim3(nframes, nlev), OT_THREADS, 0, s, h->dPlan, B, level0, (int)OT_BIG_NODE);
+        if (P.lv[0].nCols * P.lv[0].nRows >= OT_BIG_CELLS) launch_k(pdlTree, k_octree<OT_THREADS_BIG, false>, dim3(nframes, nlev), OT_THREADS_BIG, 0, s, h->dPlan, B, level0, (int)OT_BIG_NODE);
+        else if (nframes <= otLatencyFrames && !otNoSmem) launch_k(pdlTree, k_octree<OT_THREADS_BIG, true>, dim3(nframes, nlev), OT_THREADS_BIG, OT_SMEM_BYTES, s, h->dPlan, B, level0, (int)OT_BIG_NODE_LATENCY);
+        else if (nframes <= otLatencyFrames) launch_k(pdlTree, k_octree<OT_THREADS_BIG, false>, dim3(nframes, nlev), OT_THREADS_BIG, 0, s, h->dPlan, B, level0, (int)OT_BIG_NODE_LATENCY);
+        else launch_k(pdlTree, k_octree<OT_THREADS, false>, dim3(nframes, nlev), OT_THREADS, 0, s, h->dPlan, B, level0, (int)OT_BIG_NODE);
         h->launches++;
     };
     mark(h, ST_PYRAMID);
@@ -2058,6 +2209,8 @@ int orbb_extract_batch_host_submit(orbb_extractor* h, const uint8_t* host_imgs, 
     if (nframes == 1 && !h->profiling && !noGraph) {
         // ---- latency path: one stream, the kernels of the frame replayed as a CUDA graph ----
         cudaStream_t st = h->stream;
+        // (uploading straight into the pitched level 0 of the pyramid instead -- no level-0 kernel -- was measured: the 2-D copy takes
+        // 44 us longer than this linear one)
         ORBB_CUDA(h, copy_rows(h->hImg, width, host_imgs, row_stride, width, height, cudaMemcpyHostToDevice, st));
         if (!h->g1Valid || h->g1Lap0 != lap0 || h->g1Lap1 != lap1) {
             if (h->g1Exec) { cudaGraphExecDestroy(h->g1Exec); h->g1Exec = nullptr; }
@@ -2084,8 +2237,12 @@ int orbb_extract_batch_host_submit(orbb_extractor* h, const uint8_t* host_imgs, 
         h->hPyrFresh = false;
         h->apronFull = false;
         const int ncopy1 = std::min(capacity, P.kpCap);
-        ORBB_CUDA(h, cudaMemcpyAsync(h->hCounts, h->b.outCount, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
-        ORBB_CUDA(h, cudaMemcpyAsync(h->hCounts + 2, h->b.status, sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (h->b.status == h->b.outCount + 2) {             // (a handle sized for one frame: counts, then status, in one copy)
+            ORBB_CUDA(h, cudaMemcpyAsync(h->hCounts, h->b.outCount, sizeof(int) * 3, cudaMemcpyDeviceToHost, st));
+        } else {
+            ORBB_CUDA(h, cudaMemcpyAsync(h->hCounts, h->b.outCount, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+            ORBB_CUDA(h, cudaMemcpyAsync(h->hCounts + 2, h->b.status, sizeof(int), cudaMemcpyDeviceToHost, st));
+        }
         if (kps && ncopy1 > 0) ORBB_CUDA(h, cudaMemcpyAsync(kps, h->b.kps, sizeof(orbb_keypoint) * ncopy1, cudaMemcpyDeviceToHost, st));
         if (desc && ncopy1 > 0) ORBB_CUDA(h, cudaMemcpyAsync(desc, h->b.desc, (size_t)32 * ncopy1, cudaMemcpyDeviceToHost, st));
         h->pendingFrames = 1;

@@ -426,7 +426,7 @@ print("SWITCH-OK")
 @pytest.mark.parametrize("env", [
     {"ORBB_FAST_NO_TMAP": "1"}, {"ORBB_RESIZE_NO_TMA": "1"}, {"ORBB_RESIZE_NO_PRMT": "1"}, {"ORBB_NO_GRAPH": "1"},
     {"ORBB_NO_PDL": "1"}, {"ORBB_BLUR_EARLY": "1"}, {"ORBB_DESC_NO_STAGE": "1"}, {"ORBB_GRAPH_NO_PDL": "1"},
-    {"ORBB_FAST_LATENCY_FRAMES": "0"}, {"ORBB_BRANCH_FRAMES": "0"}, {"ORBB_ASM_LATENCY_FRAMES": "0"}, {"ORBB_ASM_LATENCY_FRAMES": "1000"}, {"ORBB_FAST_LATENCY_FRAMES": "64", "ORBB_FAST_NO_TMAP": "1"},
+    {"ORBB_FAST_LATENCY_FRAMES": "0"}, {"ORBB_BRANCH_FRAMES": "0"}, {"ORBB_OCTREE_NO_SMEM": "1"}, {"ORBB_ASM_LATENCY_FRAMES": "0"}, {"ORBB_ASM_LATENCY_FRAMES": "1000"}, {"ORBB_FAST_LATENCY_FRAMES": "64", "ORBB_FAST_NO_TMAP": "1"},
     {"ORBB_LANES": "1"}, {"ORBB_LANES": "3", "ORBB_LANES_MIN": "8"}, {"ORBB_LANES_MIN": "8", "ORBB_LANES_HOST": "1"}, {"ORBB_CHUNKS": "4"}, {"ORBB_PYR_LATENCY_FRAMES": "0", "ORBB_OCTREE_LATENCY_FRAMES": "0"},
     {"ORBB_KNN_MIX": "2,2"}, {"ORBB_KNN_MIX": "4,0,3"}, {"ORBB_KNN_MIX": "0,4"},
 ], ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
