@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--no-matcher-rows", action="store_true")
     ap.add_argument("--no-config3", action="store_true")
     ap.add_argument("--config3-frames", type=int, default=4096)
+    ap.add_argument("--latency-reps", type=int, default=100, help="single-frame calls in the latency legs (the ncu launch-list pass uses 2)")
     ap.add_argument("--sustain-s", type=float, default=2.0, help="seconds of back-to-back resident extraction for the sustained figure")
     ap.add_argument("--no-bind", action="store_true", help="do not bind the rank to its GPU's local cores / NUMA node")
     return ap.parse_args()
@@ -527,12 +528,13 @@ def run_ours(a):
     # ---- BASELINE config 1: ONE 752x480 frame through the synchronous call the SLAM thread makes (latency, not throughput)
     ext1 = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=1)
     one = np.ascontiguousarray(host_np[0][0])
-    for _ in range(5):
+    LR, LW = max(1, a.latency_reps), min(5, max(1, a.latency_reps))
+    for _ in range(LW):
         ext1(one, None, LAPPING)
     t0 = time.perf_counter()
-    for _ in range(50):
+    for _ in range(max(1, LR // 2)):
         ext1(one, None, LAPPING)
-    single_ms = (time.perf_counter() - t0) / 50 * 1e3
+    single_ms = (time.perf_counter() - t0) / max(1, LR // 2) * 1e3
     # the same call without the Python mirror's per-call work (result slicing / copies): orbb_extract straight on the handle's
     # pinned staging, which is what the C++ adapter does
     import ctypes as _C
@@ -541,12 +543,12 @@ def run_ours(a):
     _n, _m = _C.c_int(0), _C.c_int(0)
     _args = (ext1._h, _capi.ptr(one), W_, H_, one.strides[0], int(LAPPING[0]), int(LAPPING[1]), _capi.ptr(_k), _capi.ptr(_d), _cap,
              _C.byref(_n), _C.byref(_m))
-    for _ in range(5):
+    for _ in range(LW):
         _capi.check(ext1._lib.orbb_extract(*_args), ext1._h)
     t0 = time.perf_counter()
-    for _ in range(100):
+    for _ in range(LR):
         ext1._lib.orbb_extract(*_args)
-    single_c_ms = (time.perf_counter() - t0) / 100 * 1e3
+    single_c_ms = (time.perf_counter() - t0) / LR * 1e3
     # ... and with the hand-out of the pyramid that the C++ adapter does by default after every call (mvImagePyramid is a public member
     # that Frame::ComputeStereoMatches reads): 19-px apron on the device + one copy of the frame's pyramid slab
     _pp, _pw, _ph, _ps = _C.c_void_p(), _C.c_int(), _C.c_int(), _C.c_size_t()
@@ -555,12 +557,12 @@ def run_ours(a):
         ext1._lib.orbb_extract(*_args)
         for lv in range(NLEVELS):
             ext1._lib.orbb_pyramid_level(ext1._h, lv, _C.byref(_pp), _C.byref(_pw), _C.byref(_ph), _C.byref(_ps))
-    for _ in range(5):
+    for _ in range(LW):
         _with_pyramid()
     t0 = time.perf_counter()
-    for _ in range(100):
+    for _ in range(LR):
         _with_pyramid()
-    single_pyr_ms = (time.perf_counter() - t0) / 100 * 1e3
+    single_pyr_ms = (time.perf_counter() - t0) / LR * 1e3
     del ext1
 
     # ---- roofline of the dominant kernel (and of the whole path) ----

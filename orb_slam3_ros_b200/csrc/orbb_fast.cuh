@@ -58,8 +58,8 @@ __device__ __forceinline__ unsigned quick_bytes4(unsigned wl, unsigned wc, unsig
 // Returns the number of NMS survivors parked in `park`.
 template <int TP, int SP, bool EXACT, int NW>
 __device__ __forceinline__ int cell_pass(const uint8_t* __restrict__ tile, uint8_t* __restrict__ score, unsigned short* candS,
-                                         unsigned short* allS, unsigned* __restrict__ park, const CellDesc& cd, int ih, int th, unsigned K7,
-                                         int lane, int warp = 0, int* sCnt = nullptr) {
+                                         unsigned short* allS, unsigned* park, const CellDesc& cd, int ih, int th, unsigned K7,
+                                         int lane, int warp = 0, int* sCnt = nullptr, const unsigned** parkUsed = nullptr) {
     constexpr int PS = TP, TPW = TP / 4;
     const int cx0 = cd.cx0, cx1 = cd.cx1, sxo = cx0 - 1;                 // score column 0 = the zero column left of the cell
     const int wa = cd.wa, wLast = cd.wLast, nwc = cd.nwc, items = cd.items;
@@ -138,10 +138,14 @@ __device__ __forceinline__ int cell_pass(const uint8_t* __restrict__ tile, uint8
                 cand = (q0 & m7) | ((q1 & m7b) >> 1);                    // bit 8k+7: pixel k of row r0; bit 8k+6: row r0 + 1
                 basev = ((unsigned)(r0 + 3) << 8) | (unsigned)(4 * (wa + w));
             }
+            // exclusive prefix of the per-lane candidate counts (0..8) from four ballots of the count's bits: independent votes
+            // instead of the five dependent shuffle steps of a scan (13 % of the kernel's stall samples sat on that chain)
             const int cnt = __popc(cand);
-            const int inc = warp_incl_scan(cnt, lane);
-            unsigned short* o = candS + (nCand + inc - cnt);
-            nCand += __shfl_sync(0xffffffffu, inc, 31);
+            const unsigned v0 = __ballot_sync(0xffffffffu, cnt & 1), v1 = __ballot_sync(0xffffffffu, cnt & 2);
+            const unsigned v2 = __ballot_sync(0xffffffffu, cnt & 4), v3 = __ballot_sync(0xffffffffu, cnt & 8);
+            const int excl = __popc(v0 & lt) + 2 * __popc(v1 & lt) + 4 * __popc(v2 & lt) + 8 * __popc(v3 & lt);
+            unsigned short* o = candS + (nCand + excl);
+            nCand += __popc(v0) + 2 * __popc(v1) + 4 * __popc(v2) + 8 * __popc(v3);
 #pragma unroll
             for (int k = 0; k < 4; k++) {                                // fixed predicated sequence (the order on the stack is irrelevant)
                 if (cand & (0x80u << (8 * k))) *o++ = (unsigned short)(basev + k);
@@ -156,6 +160,10 @@ __device__ __forceinline__ int cell_pass(const uint8_t* __restrict__ tile, uint8
         nAll = sCnt[0];
     }
     // ---- D: NMS inside the cell (strict '>' against the 8 neighbours; outside the cell counts as 0) ----
+    // one warp per cell: the survivors of an ordinary cell (<= FC_NC corners) are parked on the candidate stack, which is free by now
+    // (phase E reads every record nSurv times: shared memory instead of L2 round trips); dense cells use the global park
+    if (NW == 1 && nAll <= FC_NC) park = reinterpret_cast<unsigned*>(candS);
+    if (parkUsed) *parkUsed = park;
     int nSurv = 0;
     auto nms = [&](bool valid, int sp, int sc) {                      // sp = score-map position
         bool keep = false;
@@ -250,21 +258,24 @@ __global__ void __launch_bounds__(32, 32) k_fast_cell(const Plan* __restrict__ P
     unsigned* park = reinterpret_cast<unsigned*>(B.keys + ((size_t)frame * 2 + 1) * P->rawStride + cd.outOff);
     const int iniTh = P->iniTh, minTh = P->minTh;
     int nSurv;
+    const unsigned* parked = park;
     if (iniTh < 128 && minTh < 128) {
-        nSurv = cell_pass<TP, SP, false, 1>(tile, score, candS, allS, park, cd, ih, iniTh, P->k7Ini, lane);
+        nSurv = cell_pass<TP, SP, false, 1>(tile, score, candS, allS, park, cd, ih, iniTh, P->k7Ini, lane, 0, nullptr, &parked);
         if (nSurv == 0)                                       // :833-846 (scores do not depend on the threshold: the map stays valid)
-            nSurv = cell_pass<TP, SP, false, 1>(tile, score, candS, allS, park, cd, ih, minTh, P->k7Min, lane);
+            nSurv = cell_pass<TP, SP, false, 1>(tile, score, candS, allS, park, cd, ih, minTh, P->k7Min, lane, 0, nullptr, &parked);
     } else {                                                  // thresholds >= 128: exact byte compare in the quick reject
-        nSurv = cell_pass<TP, SP, true, 1>(tile, score, candS, allS, park, cd, ih, iniTh, P->k7Ini, lane);
-        if (nSurv == 0) nSurv = cell_pass<TP, SP, true, 1>(tile, score, candS, allS, park, cd, ih, minTh, P->k7Min, lane);
+        nSurv = cell_pass<TP, SP, true, 1>(tile, score, candS, allS, park, cd, ih, iniTh, P->k7Ini, lane, 0, nullptr, &parked);
+        if (nSurv == 0) nSurv = cell_pass<TP, SP, true, 1>(tile, score, candS, allS, park, cd, ih, minTh, P->k7Min, lane, 0, nullptr, &parked);
     }
     // ---- E: raster order by rank counting; keys are relative to the 16-px border (:865-866) ----
     __syncwarp();
     u64* keysOut = B.cellKeys + (size_t)frame * P->cellKeyStride + cd.outOff;
+    const bool parkedShared = parked != park;
     for (int i = lane; i < nSurv; i += 32) {
-        const unsigned rec = __ldcg(park + i);
+        const unsigned rec = parkedShared ? parked[i] : __ldcg(park + i);
         int rank = 0;
-        for (int k = 0; k < nSurv; k++) rank += __ldcg(park + k) < rec;
+        if (parkedShared) for (int k = 0; k < nSurv; k++) rank += parked[k] < rec;
+        else for (int k = 0; k < nSurv; k++) rank += __ldcg(park + k) < rec;
         const int x = cd.gx0 + (int)((rec >> 8) & 0xffu) - kMinBorder;
         const int y = cd.gy0 + (int)(rec >> 16) - kMinBorder;
         keysOut[rank] = (u64)(unsigned)x | ((u64)(unsigned)y << 16) | ((u64)(rec & 0xffu) << 32);

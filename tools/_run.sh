@@ -1,4 +1,3 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/r2m_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2m_pytest.log
-python tools/latency_probe.py 2>&1 | tail -6
-ORBB_OCTREE_NO_SMEM=1 python tools/latency_probe.py 2>&1 | tail -3
-python tools/batch_stages.py --tag default 2>&1 | tail -2
+python tools/batch_stages.py --tag default 2>&1 | tail -1
+python tools/batch_stages.py --tag tum --shape 480 640 2>&1 | tail -1
+python -m pytest tests/test_gpu_extract.py -m gpu -x -q > gpurun_out/r2n_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2n_pytest.log

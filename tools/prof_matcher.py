@@ -21,6 +21,7 @@ from orb_slam3_ros_b200.rectify import Rectifier                   # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--knn", action="store_true")
 ap.add_argument("--pairs", type=int, default=16)
+ap.add_argument("--knn-nq", type=int, default=200_000)
 a = ap.parse_args()
 lib = capi.load()
 _p = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)
@@ -65,7 +66,7 @@ m.rotation_check([(k["angle"][:500], k["angle"][500:1000])])
 yy, xx = np.mgrid[0:480, 0:752].astype(np.float32)
 Rectifier((xx + 3.0 * np.sin(yy / 57.0)).astype(np.float32), (yy + 2.0 * np.cos(xx / 91.0)).astype(np.float32), (480, 752)).remap(synth.frame(480, 752, 8))
 if a.knn:
-    db, qq = synth.descriptor_db(2_000_000, 200_000, seed=77)
+    db, qq = synth.descriptor_db(2_000_000, a.knn_nq, seed=77)
     d_db, d_q = torch.from_numpy(db).cuda(), torch.from_numpy(qq).cuda()
     idx = torch.empty((len(qq), 2), dtype=torch.int32, device="cuda")
     dst = torch.empty_like(idx)

@@ -10,7 +10,7 @@ TAG=${1:-r2}
 set -x
 python bench.py > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err
 python bench.py --impl reference > gpurun_out/bench_${TAG}_ref.json 2> gpurun_out/bench_${TAG}_ref.err
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --knn-steps 1 --sustain-s 0 --no-config3 --no-matcher-rows > gpurun_out/ncu_l_${TAG}.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --knn-steps 1 --sustain-s 0 --no-config3 --no-matcher-rows --latency-reps 2 --no-shapes --stereo-steps 1 > gpurun_out/ncu_l_${TAG}.log 2>&1
 ncu --set full --clock-control none --import-source on -f -o gpurun_out/prof_${TAG} python tools/prof_extract.py --batch 256 --iters 1 > gpurun_out/ncu_${TAG}.log 2>&1
-ncu --set full --clock-control none -f -o gpurun_out/prof_${TAG}_matcher python tools/prof_matcher.py --knn > gpurun_out/ncu_${TAG}_matcher.log 2>&1
+ncu --set full --clock-control none -k regex:'k_best2_csr|k_bow_|k_distinctive|k_knn2_|k_ratio_test|k_remap|k_rotation_check|k_search_area_topk|k_stereo_|k_undistort' -c 40 -f -o gpurun_out/prof_${TAG}_matcher python tools/prof_matcher.py --knn --knn-nq 50000 > gpurun_out/ncu_${TAG}_matcher.log 2>&1
 ls -la gpurun_out | tail -8
