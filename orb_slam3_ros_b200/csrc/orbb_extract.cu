@@ -1182,14 +1182,23 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 // of its 64 key points itself -- level offsets from the quadtree's per-level counts, and for the lapping split the number of key points
 // inside [lap0, lap1] BEFORE its first one, counted by the CTA over the selected keys (<= 1000 8-byte reads from L2).  That removes a
 // kernel of one CTA per frame from the critical path (15 us per 256 frames, 11 of the 135 us of the single-frame call).
-constexpr int OD_CTA_KPS = (OD_THREADS / 32) * OD_KPW;          // key points per CTA (64)
+// In that form (calls with a few frames) a warp takes OD_KPW_LAT key points instead of OD_KPW: 1000 key points are 16 CTAs at 8 per
+// warp -- a tenth of the machine, every warp walking through 8 moments and 8 descriptors one after the other -- and 126 CTAs at 1
+// (measured per frame: 0.109 ms at 8, 0.106 at 2, 0.100 at 1).
+#ifndef ORBB_OD_KPW_LAT
+#define ORBB_OD_KPW_LAT 1
+#endif
+constexpr int OD_KPW_LAT = ORBB_OD_KPW_LAT;
 
 template <bool STAGE, bool ASM>
 __global__ void __launch_bounds__(OD_THREADS, 4) k_orient_desc32(const Plan* __restrict__ P, Bufs B, int lap0, int lap1) {
     __shared__ __align__(16) unsigned sPatch[STAGE ? OD_THREADS / 32 : 1][2][STAGE ? OD_PATCH_WORDS : 4];
     __shared__ int sOff[ASM ? ORBB_MAX_LEVELS + 1 : 1];
     __shared__ int sRed[ASM ? OD_THREADS / 32 + 2 : 1];
-    __shared__ WorkItem sWork[ASM ? OD_CTA_KPS : 1];
+    constexpr int KPW = ASM ? OD_KPW_LAT : OD_KPW;           // key points per warp
+    constexpr int CTA_KPS = (OD_THREADS / 32) * KPW;          // key points per CTA
+    static_assert(CTA_KPS <= 64, "the assembly prologue holds one key point per thread of warps 0 and 1");
+    __shared__ WorkItem sWork[ASM ? CTA_KPS : 1];
     const int frame = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_launch_dependents();
@@ -1198,7 +1207,7 @@ __global__ void __launch_bounds__(OD_THREADS, 4) k_orient_desc32(const Plan* __r
     const WorkItem* work;
     if constexpr (!ASM) {                                     // batches: k_assemble has run
         n = B.outCount[frame * 2];
-        g0 = (blockIdx.x * (OD_THREADS / 32) + warp) * OD_KPW;
+        g0 = (blockIdx.x * (OD_THREADS / 32) + warp) * KPW;
         work = B.work + (size_t)frame * P->kpCap + g0;
     } else {
     // ---- 0. output assembly: level-major order, pt *= scale for level > 0, key points inside the lapping area from the back ----
@@ -1211,7 +1220,7 @@ __global__ void __launch_bounds__(OD_THREADS, 4) k_orient_desc32(const Plan* __r
     }
     __syncthreads();
     n = min(sOff[nl], P->kpCap);
-    const int G0 = blockIdx.x * OD_CTA_KPS;
+    const int G0 = blockIdx.x * CTA_KPS;
     if (blockIdx.x != 0 && G0 >= n) return;                   // (uniform; CTA 0 always runs: it writes the frame's counts)
     const float fl0 = (float)lap0, fl1 = (float)lap1;
     const u64* selF = B.sel + (size_t)frame * P->selStride;
@@ -1251,12 +1260,13 @@ __global__ void __launch_bounds__(OD_THREADS, 4) k_orient_desc32(const Plan* __r
     }
     if (G0 >= n) return;                                      // (uniform)
     __syncthreads();                                          // sRed is reused below
-    if (tid < OD_CTA_KPS) {                                   // warps 0 and 1: one key point per thread
+    if (tid < (CTA_KPS > 32 ? 64 : 32)) {                     // warp 0 (and warp 1 when a CTA holds more than 32): one key point per thread
         const int g = G0 + tid;
+        const bool mine = tid < CTA_KPS && g < n;
         bool st = false;
         int level = 0, x = 0, y = 0;
         float xs = 0, ys = 0, resp = 0;
-        if (g < n) {
+        if (mine) {
             const u64 k = key_of(g, level);
             x = (int)(k & 0xffff); y = (int)((k >> 16) & 0xffff); resp = (float)(int)(k >> 32);
             xs = (float)x; ys = (float)y;
@@ -1264,10 +1274,13 @@ __global__ void __launch_bounds__(OD_THREADS, 4) k_orient_desc32(const Plan* __r
             st = xs >= fl0 && xs <= fl1;                                                                              // :1153
         }
         const unsigned bal = __ballot_sync(0xffffffffu, st);
-        if (lane == 0) sRed[OD_THREADS / 32 + warp] = __popc(bal);
-        asm volatile("bar.sync 1, 64;" ::: "memory");         // the two warps that hold key points
-        const int stHere = stBefore + (warp == 1 ? sRed[OD_THREADS / 32] : 0) + __popc(bal & ((1u << lane) - 1));
-        if (g < n) {
+        int stHere = stBefore + __popc(bal & ((1u << lane) - 1));
+        if (CTA_KPS > 32) {
+            if (lane == 0) sRed[OD_THREADS / 32 + warp] = __popc(bal);
+            asm volatile("bar.sync 1, 64;" ::: "memory");     // the two warps that hold key points
+            if (warp == 1) stHere += sRed[OD_THREADS / 32];
+        }
+        if (mine) {
             const int pos = st ? n - 1 - stHere : g - stHere;
             orbb_keypoint kp;
             kp.x = xs; kp.y = ys; kp.size = P->lv[level].kpSize; kp.angle = -1.f; kp.response = resp; kp.octave = level;
@@ -1276,11 +1289,11 @@ __global__ void __launch_bounds__(OD_THREADS, 4) k_orient_desc32(const Plan* __r
         }
     }
     __syncthreads();
-    g0 = G0 + warp * OD_KPW;
-    work = sWork + warp * OD_KPW;
+    g0 = G0 + warp * KPW;
+    work = sWork + warp * KPW;
     }
     if (g0 >= n) return;
-    const int cnt = min(OD_KPW, n - g0);
+    const int cnt = min(KPW, n - g0);
     const uint8_t* pyr = B.pyr + (size_t)frame * P->pyrStride;
     // ---- 1. IC_Angle moments (:76-103) ----
     int M10 = 0, M01 = 0;
@@ -1875,7 +1888,8 @@ static int run_lane(orbb_extractor* h, int lane, const uint8_t* dImgs, int nfram
     mark(h, ST_ORIENT_DESC);
     {   // ORBB_DESC_NO_STAGE=1: sample the blurred level through L1 instead of a shared-memory copy of the window (A/B switch)
         static const bool noStage = getenv("ORBB_DESC_NO_STAGE") != nullptr;
-        const dim3 grid((P.kpCap + OD_THREADS / 32 * OD_KPW - 1) / (OD_THREADS / 32 * OD_KPW), nframes);
+        const int ctaKps = OD_THREADS / 32 * (fusedAsm ? OD_KPW_LAT : OD_KPW);
+        const dim3 grid((P.kpCap + ctaKps - 1) / ctaKps, nframes);
         if (fusedAsm) {                                        // (behind the joins of the blur streams the edge is a full dependency anyway)
             if (noStage) launch_k(pdl && !fork, k_orient_desc32<false, true>, grid, OD_THREADS, 0, st, h->dPlan, B, lap0, lap1);
             else launch_k(pdl && !fork, k_orient_desc32<true, true>, grid, OD_THREADS, 0, st, h->dPlan, B, lap0, lap1);
