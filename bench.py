@@ -158,6 +158,32 @@ def bind_to_gpu(local, enable=True):
     return info
 
 
+def cpp_adapter_latency(frame, reps):
+    """one frame through ORB_SLAM3::ORBextractor::operator() of the C++ adapter (host/ORBextractor.cc, compiled here with g++ against the
+    OpenCV stand-in of tests/cvstub): the call the reference's Frame constructor makes, pageable image in, vector<cv::KeyPoint> + cv::Mat out"""
+    import subprocess
+    import tempfile
+    pkg = ROOT / "orb_slam3_ros_b200"
+    exe = ROOT / "tests" / "models" / "_build" / "adapter_latency"
+    try:
+        exe.parent.mkdir(parents=True, exist_ok=True)
+        src = ROOT / "tests" / "host" / "adapter_latency.cpp"
+        deps = [src, pkg / "host" / "ORBextractor.cc", pkg / "host" / "ORBextractor.h", pkg / "liborbb200.so"]
+        if not exe.exists() or exe.stat().st_mtime < max(d.stat().st_mtime for d in deps):
+            subprocess.check_call(["g++", "-std=c++14", "-O2", f"-I{ROOT / 'tests' / 'cvstub'}", f"-I{ROOT / 'include'}", f"-I{pkg / 'host'}", str(src),
+                                   str(pkg / "host" / "ORBextractor.cc"), f"-L{pkg}", "-lorbb200", f"-Wl,-rpath,{pkg}", "-L/usr/local/cuda/lib64", "-lcudart",
+                                   "-o", str(exe)], timeout=300)
+        with tempfile.NamedTemporaryFile(suffix=".raw") as f:
+            frame.tofile(f.name)
+            out = subprocess.run([str(exe), f.name, str(frame.shape[1]), str(frame.shape[0]), str(NFEAT), str(NLEVELS), str(reps)], capture_output=True,
+                                 text=True, timeout=300)
+        if out.returncode != 0:
+            return {"error": f"adapter_latency rc={out.returncode}: {out.stderr[-200:]}"}
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as e:                      # (no g++ on the box, ...): the line says so instead of failing the bench
+        return {"error": repr(e)[:200]}
+
+
 def cv2_baseline_rates(frames, processes):
     """the honest CPU arm (oracle/cv2_baseline.py): OpenCV's own SIMD resize / FAST / GaussianBlur under the reference's control flow"""
     from oracle import cv2_baseline          # checker / CPU baseline only
@@ -564,6 +590,7 @@ def run_ours(a):
         _with_pyramid()
     single_pyr_ms = (time.perf_counter() - t0) / LR * 1e3
     del ext1
+    cpp_adapter = cpp_adapter_latency(one, max(2, 2 * LR)) if rank == 0 else None
 
     # ---- roofline of the dominant kernel (and of the whole path) ----
     # "pyramid" is a stage of 9 launches (level0, 7 resizes, apron); the other entries are single kernels
@@ -841,6 +868,7 @@ def run_ours(a):
             "single_frame_latency_ms": single_ms,
             "single_frame_c_abi_ms": single_c_ms,
             "single_frame_with_pyramid_ms": single_pyr_ms,
+            "single_frame_cpp_adapter": cpp_adapter,
             "sustained": sustained,
             "host": host_info,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -30,6 +30,8 @@ PIECES = [
      r"^\s*int ORBmatcher::SearchByBoW\(KeyFrame\* pKF,Frame &F, vector<MapPoint\*> &vpMapPointMatches\)", "function"),
     ("ORBmatcher_SearchByProjection_motion", "src/ORBmatcher.cc",
      r"^\s*int ORBmatcher::SearchByProjection\(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono\)", "function"),
+    ("ORBmatcher_SearchForInitialization", "src/ORBmatcher.cc",
+     r"^\s*int ORBmatcher::SearchForInitialization\(Frame &F1, Frame &F2, vector<cv::Point2f> &vbPrevMatched, vector<int> &vnMatches12, int windowSize\)", "function"),
     ("MapPoint_ComputeDistinctiveDescriptors", "src/MapPoint.cc", r"^void MapPoint::ComputeDistinctiveDescriptors\(\)", "function"),
 ]
 

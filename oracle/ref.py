@@ -328,6 +328,27 @@ def search_by_projection_motion(cur, last, th, mono, nnratio=0.9, check_orientat
     return nm, match_of
 
 
+def search_for_initialization(f1, f2, prev, window=100, nnratio=0.9, check_orientation=True):
+    """ORBmatcher(nnratio, checkOri).SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (ORBmatcher.cc:648-766,
+    reference text; the call of Tracking::MonocularInitialization, Tracking.cc:2527).
+      f1: dict(octaves, angles, desc [n1,32]);  f2: dict(kps_xy [n2,2], octaves, angles, desc [n2,32], fp = (mnMinX, mnMaxX, mnMinY, mnMaxY,
+      gridWInv, gridHInv));  prev [n1,2] = vbPrevMatched
+    -> (nmatches, matches12[n1], prev after the call [n1,2])"""
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    o1, a1, d1 = i32(f1["octaves"]), f32(f1["angles"]), u8(f1["desc"])
+    k2, o2, a2, d2, fp = f32(f2["kps_xy"]).reshape(-1, 2), i32(f2["octaves"]), f32(f2["angles"]), u8(f2["desc"]), f32(f2["fp"])
+    pv = f32(prev).reshape(-1, 2).copy()
+    m12 = np.full(len(o1), -1, np.int32)
+    fn = lib().refcut_search_for_initialization
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int, C.c_float, C.c_int, C.c_void_p]
+    nm = fn(_ptr(o1), _ptr(a1), _ptr(d1), len(o1), _ptr(k2), _ptr(o2), _ptr(a2), _ptr(d2), len(o2), _ptr(fp), _ptr(pv), int(window), nnratio,
+            int(check_orientation), _ptr(m12))
+    return nm, m12, pv
+
+
 def search_by_bow(kf_angle, kf_desc, kf_has_point, kf_fv, f_angle, f_desc, f_fv, nnratio=0.7, check_orientation=True):
     """ORBmatcher(nnratio, checkOri).SearchByBoW(pKF, F, vpMapPointMatches) (ORBmatcher.cc:223-421, reference text) for a monocular
     pair; kf_fv / f_fv = (node, start, feat) arrays of the two feature vectors (RefVocabulary.transform()[2:5] or the port's)

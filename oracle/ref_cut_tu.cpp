@@ -56,6 +56,7 @@ public:
     int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3, const bool bFarPoints = false,
                            const float thFarPoints = 50.0f);
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+    int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
     static const int TH_LOW;
     static const int TH_HIGH;
     static const int HISTO_LENGTH;
@@ -140,6 +141,7 @@ float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX
 #include "cut/ORBmatcher_RadiusByViewingCos.inc"
 #include "cut/ORBmatcher_SearchByBoW_KF_F.inc"
 #include "cut/ORBmatcher_SearchByProjection_motion.inc"
+#include "cut/ORBmatcher_SearchForInitialization.inc"
 #include "cut/ORBmatcher_ComputeThreeMaxima.inc"
 #include "cut/ORBmatcher_DescriptorDistance.inc"
 #include "cut/Frame_AssignFeaturesToGrid.inc"
@@ -375,6 +377,42 @@ int refcut_search_by_projection_motion(const float* kps, const int32_t* oct, con
     }
     delete C;
     delete L;
+    return nmatches;
+}
+
+// Tracking::MonocularInitialization's call (Tracking.cc:2396 ff.): ORBmatcher(0.9, true).SearchForInitialization(mInitialFrame, mCurrentFrame,
+// mvbPrevMatched, mvIniMatches, 100) (ORBmatcher.cc:648-766).  Frame 1: undistorted key points' octaves and angles + descriptors; frame 2: undistorted
+// key points (x, y), octaves, angles, descriptors; fp = {mnMinX, mnMaxX, mnMinY, mnMaxY, mfGridElementWidthInv, mfGridElementHeightInv}; prev = n1 x 2
+// search centres, updated in place as the reference does (:757-760).  -> matches12[n1]; returns nmatches.
+int refcut_search_for_initialization(const int32_t* oct1, const float* angle1, const uint8_t* desc1, int n1, const float* kps2, const int32_t* oct2,
+                                     const float* angle2, const uint8_t* desc2, int n2, const float* fp, float* prev, int windowSize, float nnratio,
+                                     int checkOri, int32_t* matches12) {
+    using namespace ORB_SLAM3;
+    Frame* F1 = new Frame();
+    Frame* F2 = new Frame();
+    Frame::mnMinX = fp[0]; Frame::mnMaxX = fp[1]; Frame::mnMinY = fp[2]; Frame::mnMaxY = fp[3];
+    Frame::mfGridElementWidthInv = fp[4]; Frame::mfGridElementHeightInv = fp[5];
+    F1->N = n1; F1->Nleft = -1;
+    F1->mvKeysUn.resize(n1);
+    for (int i = 0; i < n1; i++) { F1->mvKeysUn[i].octave = oct1[i]; F1->mvKeysUn[i].angle = angle1[i]; }
+    F1->mvKeys = F1->mvKeysUn;
+    F1->mDescriptors = to_descriptors(desc1, n1);
+    F2->N = n2; F2->Nleft = -1;
+    F2->mvKeysUn.resize(n2);
+    for (int i = 0; i < n2; i++) {
+        F2->mvKeysUn[i].pt.x = kps2[2 * i]; F2->mvKeysUn[i].pt.y = kps2[2 * i + 1]; F2->mvKeysUn[i].octave = oct2[i]; F2->mvKeysUn[i].angle = angle2[i];
+    }
+    F2->mvKeys = F2->mvKeysUn;
+    F2->AssignFeaturesToGrid();
+    F2->mDescriptors = to_descriptors(desc2, n2);
+    std::vector<cv::Point2f> vbPrevMatched(n1);
+    for (int i = 0; i < n1; i++) { vbPrevMatched[i].x = prev[2 * i]; vbPrevMatched[i].y = prev[2 * i + 1]; }
+    std::vector<int> vnMatches12;
+    ORBmatcher matcher(nnratio, checkOri != 0);
+    const int nmatches = matcher.SearchForInitialization(*F1, *F2, vbPrevMatched, vnMatches12, windowSize);
+    for (int i = 0; i < n1; i++) { matches12[i] = vnMatches12[i]; prev[2 * i] = vbPrevMatched[i].x; prev[2 * i + 1] = vbPrevMatched[i].y; }
+    delete F1;
+    delete F2;
     return nmatches;
 }
 

@@ -5,6 +5,11 @@
 //   SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono)                           reference ORBmatcher.cc:1676-1887
 //       (Tracking::TrackWithMotionModel, Tracking.cc:2925 / :2933)
 //
+// and for the matcher of the monocular initialisation, which Tracking calls on every frame until the map exists:
+//
+//   SearchForInitialization(Frame& F1, Frame& F2, vbPrevMatched, vnMatches12, windowSize)                reference ORBmatcher.cc:648-766
+//       (Tracking::MonocularInitialization, Tracking.cc:2527)
+//
 // for monocular, rectified-stereo and RGB-D frames (Frame::Nleft == -1).  What stays on the host is what is host state in the
 // reference as well: the MapPoint / Frame objects, the projection of every point, the accept / reject decisions.  What moves to the
 // GPU is the part that costs: Frame::GetFeaturesInArea (Frame.cc:657-723) + the DescriptorDistance scan of every candidate
@@ -103,15 +108,16 @@ static bool LiveHead(const Frame& F, const int32_t* list, int k, int want, Cand*
     return nout >= want || valid < k;
 }
 
-void ORBmatcherGPU::RunScan(const Frame& F, int nq, int k, std::vector<int32_t>& out) {
+void ORBmatcherGPU::RunScan(const Frame& F, int nq, int k, std::vector<int32_t>& out, bool maskTaken, bool rightCheck, int init) {
     Impl& s = Scratch();
-    const orbb_frame_view* fv = FrameView(mpMatcher, s, F, 0);
+    orbb_frame_view fv = *FrameView(mpMatcher, s, F, 0);
+    if (!rightCheck) fv.u_right = nullptr;                 // (a scan without the mvuRight test of ORBmatcher.cc:94-100 / :1755-1761)
     s.skip.assign(F.N, 0);
-    for (int i = 0; i < F.N; i++) s.skip[i] = Taken(F, i);
+    if (maskTaken) for (int i = 0; i < F.N; i++) s.skip[i] = Taken(F, i);
     const float grid4[4] = {Frame::mnMinX, Frame::mnMinY, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv};
     out.assign((size_t)nq * k * 2, -1);
     if (nq == 0) return;
-    if (orbb_search_area_topk(mpMatcher, fv, grid4, s.q.data(), s.qlev.data(), s.qdesc.data(), nq, s.skip.data(), 256, k, out.data()) != ORBB_OK)
+    if (orbb_search_area_topk(mpMatcher, &fv, grid4, s.q.data(), s.qlev.data(), s.qdesc.data(), nq, s.skip.data(), init, k, out.data()) != ORBB_OK)
         throw std::runtime_error(std::string("orbb_search_area_topk failed: ") + orbb_matcher_last_error(mpMatcher));
 }
 
@@ -243,6 +249,103 @@ int ORBmatcherGPU::SearchByProjection(Frame& CurrentFrame, const Frame& LastFram
             }
         }
     }
+    return nmatches;
+}
+
+// ORBmatcher::SearchForInitialization (ORBmatcher.cc:648-766; Tracking::MonocularInitialization, Tracking.cc:2527, windowSize 100): every
+// level-0 key point of F1 looks for its best / second-best descriptor among the level-0 key points of F2 inside a square window around
+// vbPrevMatched[i1].  Unlike the projection searches the scan of the reference is NOT masked by what is taken: a candidate i2 is left
+// out only when an earlier key point holds it with a distance <= this one (vMatchedDistance, :687), and a later, closer key point takes
+// it over (:706-710).  The batched scan returns the four best candidates of every key point in scan order; the loop below applies the
+// distance test on the live vMatchedDistance, and only a key point that loses more than two of its four candidates that way walks its
+// window on the host, exactly as the reference does.
+int ORBmatcherGPU::SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12,
+                                           int windowSize, const float nnratio, const bool checkOrientation) {
+    if (F1.Nleft != -1 || F2.Nleft != -1)
+        throw std::logic_error("ORBmatcherGPU::SearchForInitialization: fisheye-stereo frames (Nleft != -1) keep the reference's host path");
+    Impl& s = Scratch();
+    const int n1 = (int)F1.mvKeysUn.size(), n2 = (int)F2.mvKeysUn.size();
+    const int INF = 0x7fffffff;
+    int nmatches = 0;
+    vnMatches12 = std::vector<int>(n1, -1);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    for (int i = 0; i < HISTO_LENGTH; i++) rotHist[i].reserve(500);
+    const float factor = 1.0f / HISTO_LENGTH;
+    std::vector<int> vMatchedDistance(n2, INF), vnMatches21(n2, -1);
+    s.q.clear(); s.qlev.clear(); s.qdesc.clear(); s.src.clear();
+    for (int i1 = 0; i1 < n1; i1++) {                                             // :661-668
+        if (F1.mvKeysUn[i1].octave > 0) continue;
+        const float q4[4] = {vbPrevMatched[i1].x, vbPrevMatched[i1].y, (float)windowSize, -1.0f};
+        s.q.insert(s.q.end(), q4, q4 + 4);
+        s.qlev.push_back(0); s.qlev.push_back(0);                                 // GetFeaturesInArea(.., level1, level1) with level1 == 0
+        const uchar* d = F1.mDescriptors.ptr<uchar>(i1);
+        s.qdesc.insert(s.qdesc.end(), d, d + 32);
+        s.src.push_back(i1);
+    }
+    const int nq = (int)s.src.size();
+    RunScan(F2, nq, kTopK, s.out, false, false, 257);                             // (bestDist starts at INT_MAX: every distance 0..256 counts)
+    for (int j = 0; j < nq; j++) {
+        const int i1 = s.src[j];
+        const int32_t* list = &s.out[(size_t)j * kTopK * 2];
+        int bestDist = INF, bestDist2 = INF, bestIdx2 = -1, valid = 0, got = 0;
+        for (int t = 0; t < kTopK && got < 2; t++) {                              // :679-700 on the head of the list
+            const int idx = list[2 * t + 1];
+            if (idx < 0) break;
+            valid++;
+            const int dist = list[2 * t];
+            if (vMatchedDistance[idx] <= dist) continue;
+            if (got == 0) { bestDist = dist; bestIdx2 = idx; } else bestDist2 = dist;
+            got++;
+        }
+        if (got < 2 && valid == kTopK) {                                          // more candidates may follow the four: the reference's loop for this one
+            const std::vector<size_t> vIndices2 = F2.GetFeaturesInArea(vbPrevMatched[i1].x, vbPrevMatched[i1].y, windowSize, 0, 0);
+            bestDist = INF; bestDist2 = INF; bestIdx2 = -1;
+            const uchar* d1 = F1.mDescriptors.ptr<uchar>(i1);
+            for (size_t v = 0; v < vIndices2.size(); v++) {
+                const size_t i2 = vIndices2[v];
+                const int dist = orbb_hamming_distance(d1, F2.mDescriptors.ptr<uchar>((int)i2));
+                if (vMatchedDistance[i2] <= dist) continue;
+                if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = (int)i2; }
+                else if (dist < bestDist2) bestDist2 = dist;
+            }
+            mnRescans++;
+        }
+        if (bestDist <= TH_LOW) {                                                 // :702-728
+            if (bestDist < (float)bestDist2 * nnratio) {
+                if (vnMatches21[bestIdx2] >= 0) {
+                    vnMatches12[vnMatches21[bestIdx2]] = -1;
+                    nmatches--;
+                }
+                vnMatches12[i1] = bestIdx2;
+                vnMatches21[bestIdx2] = i1;
+                vMatchedDistance[bestIdx2] = bestDist;
+                nmatches++;
+                if (checkOrientation) {
+                    float rot = F1.mvKeysUn[i1].angle - F2.mvKeysUn[bestIdx2].angle;
+                    if (rot < 0.0) rot += 360.0f;
+                    int bin = round(rot * factor);
+                    if (bin == HISTO_LENGTH) bin = 0;
+                    rotHist[bin].push_back(i1);
+                }
+            }
+        }
+    }
+    if (checkOrientation) {                                                       // :732-755
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0, jend = rotHist[i].size(); j < jend; j++) {
+                const int idx1 = rotHist[i][j];
+                if (vnMatches12[idx1] >= 0) {
+                    vnMatches12[idx1] = -1;
+                    nmatches--;
+                }
+            }
+        }
+    }
+    for (int i1 = 0; i1 < n1; i1++)                                               // :757-760
+        if (vnMatches12[i1] >= 0) vbPrevMatched[i1] = F2.mvKeysUn[vnMatches12[i1]].pt;
     return nmatches;
 }
 

@@ -44,8 +44,11 @@ public:
                            const float nnratio);
     // ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono)           ORBmatcher.cc:1676-1887; checkOrientation = mbCheckOrientation
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono, const bool checkOrientation);
+    // ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vbPrevMatched, vnMatches12, windowSize)  ORBmatcher.cc:648-766; nnratio = mfNNratio
+    int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize,
+                                const float nnratio, const bool checkOrientation);
     static void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);      // ORBmatcher.cc:2012-2053
-    long Rescans() const { return mnRescans; }      // points that had to be scanned a second time (all their 4 candidates were taken meanwhile)
+    long Rescans() const { return mnRescans; }      // points that had to be scanned a second time (their 4 candidates did not survive the in-order decisions)
     ORBmatcherGPU(const ORBmatcherGPU&) = delete;
     ORBmatcherGPU& operator=(const ORBmatcherGPU&) = delete;
 
@@ -134,7 +137,7 @@ public:
     }
 
 private:
-    void RunScan(const Frame& F, int nq, int k, std::vector<int32_t>& out);
+    void RunScan(const Frame& F, int nq, int k, std::vector<int32_t>& out, bool maskTaken = true, bool rightCheck = true, int init = 256);
     void Rescan(const Frame& F, int j, int want, void* candOut, int& nout);
     Impl& Scratch();
     orbb_matcher* mpMatcher;

@@ -1,5 +1,5 @@
 // TEST HARNESS: the compiled GPU matcher adapter (orb_slam3_ros_b200/host/ORBmatcherGPU.cc) behind the SAME flat C entry points as the
-// reference-cut glue of oracle/ref_cut_tu.cpp (refcut_search_by_projection, refcut_search_by_projection_motion), so that
+// reference-cut glue of oracle/ref_cut_tu.cpp (refcut_search_by_projection, refcut_search_by_projection_motion, refcut_search_for_initialization), so that
 // tests/test_gpu_matcher_host.py can feed both sides identical arrays and compare what they leave in mvpMapPoints.  Built as a shared
 // library against tests/host/slam_stub + tests/cvstub (no Eigen / Sophus / OpenCV in this image).
 #include <cstdint>
@@ -114,6 +114,40 @@ int gpuhost_search_by_projection_motion(const float* kps, const int32_t* oct, co
         MapPoint* p = C.mvpMapPoints[i];
         matchOf[i] = (p && p != &oldObs && p != &oldNoObs) ? (int)(p - mps.data()) : -1;
     }
+    return nmatches;
+}
+
+// same arguments and result as refcut_search_for_initialization (oracle/ref_cut_tu.cpp)
+int gpuhost_search_for_initialization(const int32_t* oct1, const float* angle1, const uint8_t* desc1, int n1, const float* kps2, const int32_t* oct2,
+                                      const float* angle2, const uint8_t* desc2, int n2, const float* fp, float* prev, int windowSize, float nnratio,
+                                      int checkOri, int32_t* matches12) {
+    Frame* F1 = new Frame();      // (the grid makes a Frame too large for the stack)
+    Frame* F2 = new Frame();
+    F1->mnId = g_frameId++; F2->mnId = g_frameId++;
+    Frame::mnMinX = fp[0]; Frame::mnMaxX = fp[1]; Frame::mnMinY = fp[2]; Frame::mnMaxY = fp[3];
+    Frame::mfGridElementWidthInv = fp[4]; Frame::mfGridElementHeightInv = fp[5];
+    F1->N = n1; F1->Nleft = -1;
+    F1->mvKeysUn.resize(n1);
+    for (int i = 0; i < n1; i++) { F1->mvKeysUn[i].octave = oct1[i]; F1->mvKeysUn[i].angle = angle1[i]; }
+    F1->mvKeys = F1->mvKeysUn;
+    F1->mDescriptors = to_descriptors(desc1, n1);
+    F2->N = n2; F2->Nleft = -1;
+    F2->mvKeysUn.resize(n2);
+    for (int i = 0; i < n2; i++) {
+        F2->mvKeysUn[i].pt.x = kps2[2 * i]; F2->mvKeysUn[i].pt.y = kps2[2 * i + 1]; F2->mvKeysUn[i].octave = oct2[i]; F2->mvKeysUn[i].angle = angle2[i];
+    }
+    F2->mvKeys = F2->mvKeysUn;
+    F2->AssignFeaturesToGrid();
+    F2->mDescriptors = to_descriptors(desc2, n2);
+    F2->mvuRight.assign(n2, -1.0f);
+    F2->mvpMapPoints.assign(n2, nullptr);
+    std::vector<cv::Point2f> vbPrevMatched(n1);
+    for (int i = 0; i < n1; i++) { vbPrevMatched[i].x = prev[2 * i]; vbPrevMatched[i].y = prev[2 * i + 1]; }
+    std::vector<int> vnMatches12;
+    const int nmatches = ORBmatcherGPU::Instance().SearchForInitialization(*F1, *F2, vbPrevMatched, vnMatches12, windowSize, nnratio, checkOri != 0);
+    for (int i = 0; i < n1; i++) { matches12[i] = vnMatches12[i]; prev[2 * i] = vbPrevMatched[i].x; prev[2 * i + 1] = vbPrevMatched[i].y; }
+    delete F1;
+    delete F2;
     return nmatches;
 }
 

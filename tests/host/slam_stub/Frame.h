@@ -4,6 +4,7 @@
 // OpenCV.  The same members are declared by the stand-ins of oracle/ref_cut_tu.cpp, against which the REFERENCE's own function bodies
 // are compiled; the two sides are compared on identical flat inputs by tests/test_gpu_matcher_host.py.
 #pragma once
+#include <cmath>
 #include <mutex>
 #include <vector>
 
@@ -35,6 +36,35 @@ public:
 class Frame {
 public:
     Sophus::SE3<float> GetPose() const { return mTcw; }
+    // Test stand-ins for Frame::AssignFeaturesToGrid / GetFeaturesInArea (Frame.cc:385-416, :657-735; monocular branch): the key points of a
+    // 64 x 48 grid cell in index order, cells visited column by column.  (The compiled adapter calls GetFeaturesInArea only for the rare key
+    // point of SearchForInitialization whose candidate list is exhausted; in the reference's build it is the reference's own method.)
+    void AssignFeaturesToGrid() {
+        for (int i = 0; i < FRAME_GRID_COLS; i++) for (int j = 0; j < FRAME_GRID_ROWS; j++) mGrid[i][j].clear();
+        for (int i = 0; i < N; i++) {
+            const int gx = (int)std::round((mvKeysUn[i].pt.x - mnMinX) * mfGridElementWidthInv);
+            const int gy = (int)std::round((mvKeysUn[i].pt.y - mnMinY) * mfGridElementHeightInv);
+            if (gx >= 0 && gx < FRAME_GRID_COLS && gy >= 0 && gy < FRAME_GRID_ROWS) mGrid[gx][gy].push_back((std::size_t)i);
+        }
+    }
+    std::vector<std::size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1, const int maxLevel = -1) const {
+        std::vector<std::size_t> found;
+        const int cx0 = std::max(0, (int)std::floor((x - mnMinX - r) * mfGridElementWidthInv));
+        const int cx1 = std::min(FRAME_GRID_COLS - 1, (int)std::ceil((x - mnMinX + r) * mfGridElementWidthInv));
+        const int cy0 = std::max(0, (int)std::floor((y - mnMinY - r) * mfGridElementHeightInv));
+        const int cy1 = std::min(FRAME_GRID_ROWS - 1, (int)std::ceil((y - mnMinY + r) * mfGridElementHeightInv));
+        if (cx0 >= FRAME_GRID_COLS || cx1 < 0 || cy0 >= FRAME_GRID_ROWS || cy1 < 0) return found;
+        const bool levels = minLevel > 0 || maxLevel >= 0;
+        for (int ix = cx0; ix <= cx1; ix++)
+            for (int iy = cy0; iy <= cy1; iy++)
+                for (std::size_t idx : mGrid[ix][iy]) {
+                    const cv::KeyPoint& kp = mvKeysUn[idx];
+                    if (levels && (kp.octave < minLevel || (maxLevel >= 0 && kp.octave > maxLevel))) continue;
+                    if (std::fabs(kp.pt.x - x) < r && std::fabs(kp.pt.y - y) < r) found.push_back(idx);
+                }
+        return found;
+    }
+    std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
     long unsigned int mnId = 0;
     Sophus::SE3<float> mTcw;
     float mbf = 0, mb = 0;

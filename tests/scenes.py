@@ -78,3 +78,30 @@ def motion_scene(stereo, direction=0, seed=5, dense=False):
     last = dict(octaves=kl["octave"].astype(np.int32), angles=last_angle, state=last_state, outlier=(rng.random(m) < 0.05).astype(np.uint8),
                 pos=pos, desc=last_desc, Tlw=Tlw)
     return cur, last
+
+
+def init_scene(seed=3, crowd=False, jitter=0.0):
+    """Tracking::MonocularInitialization: two consecutive frames of a sequence; the search centres are the first frame's own key points
+    (Tracking.cc:2484-2486), optionally jittered.  crowd: groups of level-0 key points of the first frame share one descriptor, so that
+    several of them claim the same key point of the second frame -- the take-over / vMatchedDistance paths of ORBmatcher.cc:687, :706-710."""
+    h, w = 480, 752
+    rng = np.random.default_rng(seed)
+    seq = synth.sequence(h, w, 40, canvas=1024, base_seed=700 + seed)
+    pe = port.PortExtractor(1000, 1.2, 8)
+    _, k1, d1, _ = pe.extract(seq[20])
+    _, k2, d2, _ = pe.extract(seq[21])
+    d1 = d1.copy()
+    prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+    if jitter:
+        prev += rng.normal(0, jitter, prev.shape).astype(np.float32)
+    if crowd:
+        lvl0 = np.flatnonzero(k1["octave"] == 0)
+        for g in range(len(lvl0) // 4):                            # groups of four neighbours in index order
+            grp = lvl0[4 * g:4 * g + 4]
+            d1[grp] = d1[grp[0]]
+            d1[grp[1:], 0] ^= rng.integers(0, 4, 3, dtype=np.uint8)      # a bit or two apart: different distances to the same target
+            prev[grp] = prev[grp[0]]
+    f1 = dict(octaves=k1["octave"].astype(np.int32), angles=k1["angle"].copy(), desc=d1)
+    f2 = dict(kps_xy=np.stack([k2["x"], k2["y"]], 1).astype(np.float32), octaves=k2["octave"].astype(np.int32), angles=k2["angle"].copy(), desc=d2,
+              fp=np.float32([0, w, 0, h, np.float32(64) / np.float32(w), np.float32(48) / np.float32(h)]))
+    return f1, f2, prev

@@ -14,7 +14,7 @@ from oracle import port, ref
 from orb_slam3_ros_b200 import capi, synth
 from orb_slam3_ros_b200.extractor import ORBextractor
 from orb_slam3_ros_b200.matcher import ORBmatcher
-from scenes import local_points_scene, motion_scene
+from scenes import init_scene, local_points_scene, motion_scene
 
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
@@ -44,7 +44,36 @@ def host():
     lib.gpuhost_search_by_projection_motion.restype = C.c_int
     lib.gpuhost_search_by_projection_motion.argtypes = [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int] + \
         [C.c_void_p] * 7 + [C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    lib.gpuhost_search_for_initialization.restype = C.c_int
+    lib.gpuhost_search_for_initialization.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 2 + \
+        [C.c_int, C.c_float, C.c_int, C.c_void_p]
     return lib
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref (the reference's own object code) is not built")
+@pytest.mark.parametrize("crowd,jitter,window,check", [(False, 0.0, 100, True), (True, 0.0, 100, True), (False, 6.0, 40, True), (True, 3.0, 100, False)])
+def test_search_for_initialization_equals_reference(host, crowd, jitter, window, check):
+    """ORBmatcher::SearchForInitialization (ORBmatcher.cc:648-766, Tracking::MonocularInitialization): matches, match count and the updated
+    vbPrevMatched of the compiled GPU replacement against the reference's own body on the same two frames"""
+    f1, f2, prev = init_scene(crowd=crowd, jitter=jitter)
+    nm_ref, m_ref, prev_ref = ref.search_for_initialization(f1, f2, prev, window, 0.9, check)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    o1, a1, d1 = i32(f1["octaves"]), f32(f1["angles"]), u8(f1["desc"])
+    k2, o2, a2, d2, fp = f32(f2["kps_xy"]), i32(f2["octaves"]), f32(f2["angles"]), u8(f2["desc"]), f32(f2["fp"])
+    pv = f32(prev).copy()
+    m12 = np.full(len(o1), -1, np.int32)
+    nm = host.gpuhost_search_for_initialization(_p(o1), _p(a1), _p(d1), len(o1), _p(k2), _p(o2), _p(a2), _p(d2), len(o2), _p(fp), _p(pv), window, 0.9,
+                                                int(check), _p(m12))
+    assert nm == nm_ref and np.array_equal(m12, m_ref) and np.array_equal(pv, prev_ref)
+    assert nm_ref > 20
+    # a second round from the updated centres, as Tracking does frame after frame until the map is initialised (Tracking.cc:2527)
+    nm_ref2, m_ref2, prev_ref2 = ref.search_for_initialization(f1, f2, prev_ref, window, 0.9, check)
+    m12b = np.full(len(o1), -1, np.int32)
+    nm2 = host.gpuhost_search_for_initialization(_p(o1), _p(a1), _p(d1), len(o1), _p(k2), _p(o2), _p(a2), _p(d2), len(o2), _p(fp), _p(pv), window, 0.9,
+                                                 int(check), _p(m12b))
+    assert nm2 == nm_ref2 and np.array_equal(m12b, m_ref2) and np.array_equal(pv, prev_ref2)
 
 
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref (the reference's own object code) is not built")

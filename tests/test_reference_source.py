@@ -474,3 +474,96 @@ def test_batched_motion_model_search_equals_reference_search_by_projection(stere
     assert nm_ref > 30
     if dense:
         assert rescans > 0
+
+
+def _batched_search_for_initialization(f1, f2, prev, window, nnratio, check_orientation, scan, k=4):
+    """ORBmatcherGPU::SearchForInitialization restated in numpy (orb_slam3_ros_b200/host/ORBmatcherGPU.cc): ONE batched scan for the k best
+    candidates of every level-0 key point (`scan` = the oracle's best-two scan, applied twice with the first two masked to get four), then
+    the reference's decisions in order on the live vMatchedDistance; a key point that loses more than k - 2 of a full list walks its window
+    again with the reference's own loop."""
+    f32 = np.float32
+    n1, n2 = len(f1["octaves"]), len(f2["octaves"])
+    grid4 = f32([f2["fp"][0], f2["fp"][2], f2["fp"][4], f2["fp"][5]])
+    src = [i for i in range(n1) if f1["octaves"][i] == 0]
+    queries = f32([[prev[i][0], prev[i][1], window, -1] for i in src]).reshape(-1, 4)
+    qlev = np.zeros((len(src), 2), np.int32)
+    qdesc = f1["desc"][src]
+    args = (f2["kps_xy"], f2["octaves"], f2["desc"], grid4)
+    first = scan(*args, queries, qlev, qdesc, None, None, 257)
+    lists = []
+    for j in range(len(src)):
+        lst = [(int(first[j][0]), int(first[j][1])), (int(first[j][2]), int(first[j][3]))]
+        if lst[1][1] >= 0 and k > 2:
+            skip = np.zeros(n2, np.uint8)
+            skip[[lst[0][1], lst[1][1]]] = 1
+            nxt = scan(*args, queries[j:j + 1], qlev[j:j + 1], qdesc[j:j + 1], skip, None, 257)[0]
+            lst += [(int(nxt[0]), int(nxt[1])), (int(nxt[2]), int(nxt[3]))]
+        lists.append([c for c in lst if c[1] >= 0])
+    INF = 2 ** 31 - 1
+    matched_dist = np.full(n2, INF, np.int64)
+    m12, m21 = np.full(n1, -1, np.int32), np.full(n2, -1, np.int32)
+    nm, fallbacks, votes = 0, 0, []
+    gx = np.floor((f2["kps_xy"][:, 0] - grid4[0]) * grid4[2] + f32(0.5)).astype(np.int64)       # round(): the coordinates are >= 0 here
+    gy = np.floor((f2["kps_xy"][:, 1] - grid4[1]) * grid4[3] + f32(0.5)).astype(np.int64)
+    in_grid = (gx >= 0) & (gx < 64) & (gy >= 0) & (gy < 48) & (f2["octaves"] == 0)
+    for j, i1 in enumerate(src):
+        live = [(d, i) for d, i in lists[j] if matched_dist[i] > d]
+        if len(live) < 2 and len(lists[j]) == k:                                # the reference's loop for this one (ORBmatcher.cc:668-700)
+            x, y = f32(prev[i1][0]), f32(prev[i1][1])
+            cand = np.flatnonzero(in_grid & (np.abs(f2["kps_xy"][:, 0] - x) < window) & (np.abs(f2["kps_xy"][:, 1] - y) < window))
+            cand = sorted(cand, key=lambda i: (gx[i], gy[i], i))                 # cells column by column, index order inside a cell
+            best, best2, bidx = INF, INF, -1
+            for i2 in cand:
+                d = port.hamming(f1["desc"][i1], f2["desc"][i2])
+                if matched_dist[i2] <= d:
+                    continue
+                if d < best:
+                    best2, best, bidx = best, d, i2
+                elif d < best2:
+                    best2 = d
+            fallbacks += 1
+        else:
+            best, bidx = live[0] if live else (INF, -1)
+            best2 = live[1][0] if len(live) > 1 else INF
+        if best <= 50 and f32(best) < f32(f32(best2) * f32(nnratio)):
+            if m21[bidx] >= 0:
+                m12[m21[bidx]] = -1
+                nm -= 1
+            m12[i1], m21[bidx], matched_dist[bidx] = bidx, i1, best
+            nm += 1
+            if check_orientation:
+                rot = f32(f1["angles"][i1] - f2["angles"][bidx])
+                if rot < 0:
+                    rot = f32(rot + f32(360))
+                b = int(np.floor(float(f32(rot * f32(1.0 / 30))) + 0.5))
+                votes.append((0 if b == 30 else b, i1))
+    if check_orientation:
+        hist = np.bincount([b for b, _ in votes], minlength=30)
+        keep3 = set(int(v) for v in port.three_maxima(hist) if v >= 0)
+        for b, i1 in votes:
+            if b not in keep3 and m12[i1] >= 0:
+                m12[i1] = -1
+                nm -= 1
+    prev = np.array(prev, np.float32, copy=True)
+    for i1 in range(n1):
+        if m12[i1] >= 0:
+            prev[i1] = f2["kps_xy"][m12[i1]]
+    return nm, m12, prev, fallbacks
+
+
+@pytest.mark.parametrize("crowd,jitter,window,k", [(False, 0.0, 100, 4), (True, 0.0, 100, 4), (False, 6.0, 40, 4), (True, 0.0, 100, 2)])
+def test_batched_search_for_initialization_equals_reference(crowd, jitter, window, k):
+    """the reference's own ORBmatcher::SearchForInitialization (Tracking::MonocularInitialization; its definition cut out of
+    ORBmatcher.cc:648-766) against the batched formulation that the GPU host adapter implements, with the oracle's scan in the place of
+    the device scan.  k = 2 forces the fallback path (a list of two is exhausted by one take-over)."""
+    from scenes import init_scene
+    f1, f2, prev = init_scene(crowd=crowd, jitter=jitter)
+    nm_ref, m_ref, prev_ref = ref.search_for_initialization(f1, f2, prev, window, 0.9, True)
+    nm, m12, prev_out, fallbacks = _batched_search_for_initialization(f1, f2, prev, window, 0.9, True, port.search_area_best2, k)
+    assert nm == nm_ref and np.array_equal(m12, m_ref) and np.array_equal(prev_out, prev_ref)
+    assert nm_ref > 20
+    if k == 2:
+        assert fallbacks > 0
+    nm_ref2, m_ref2, _ = ref.search_for_initialization(f1, f2, prev, window, 0.9, False)
+    nm2, m122, _, _ = _batched_search_for_initialization(f1, f2, prev, window, 0.9, False, port.search_area_best2, k)
+    assert nm2 == nm_ref2 and np.array_equal(m122, m_ref2) and nm_ref2 >= nm_ref

@@ -1,4 +1,7 @@
-python -m pytest tests/test_gpu_extract.py -m gpu -x -q > gpurun_out/r2p_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2p_pytest.log
-echo kpw2; python tools/latency_probe.py 2>&1 | tail -3
-echo kpw1; ORBB_LIB=orb_slam3_ros_b200/liborbb200_kpw1.so python tools/latency_probe.py 2>&1 | tail -3
-echo kpw4; ORBB_LIB=orb_slam3_ros_b200/liborbb200_kpw4.so python tools/latency_probe.py 2>&1 | tail -3
+python -m pytest tests/test_gpu_matcher_host.py -m gpu -x -q > gpurun_out/r2r_pytest.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/r2r_pytest.log
+python bench.py --no-cpu-baseline --no-config3 --no-shapes --no-stereo --no-knn --no-matcher-rows --sustain-s 0 --steps 3 > gpurun_out/r2r_bench.json 2> gpurun_out/r2r_bench.err; tail -3 gpurun_out/r2r_bench.err
+python - <<'P'
+import json
+d=json.load(open('gpurun_out/r2r_bench.json'))
+print({k:v for k,v in d.items() if 'single' in k}, d['value'])
+P
