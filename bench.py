@@ -334,6 +334,26 @@ def measure_matcher_rows(local, with_cpu):
             row["cpu_ms"] = cpu_time(lambda: port.search_area_best2(kxy, octs, d, grid4, queries, qlev, qdesc, skip, None, 256))
             row["cpu_kind"] = "port"
     rows.append(row)
+    # (1b) Tracking::MonocularInitialization: every level-0 key point of the initial frame searches a 100-px window of the current frame
+    l0 = np.flatnonzero(octs == 0)
+    q_init = np.stack([kxy[l0, 0], kxy[l0, 1], np.full(len(l0), 100.0), np.full(len(l0), -1.0)], 1).astype(np.float32)
+    qlev_init = np.zeros((len(l0), 2), np.int32)
+    qdesc_init = np.ascontiguousarray(d[l0])
+    out_init = np.zeros((len(l0), 4, 2), np.int32)
+
+    def scan_init(view):
+        capi.check(lib.orbb_search_area_topk(m._m, C.byref(view), _p(grid4), _p(q_init), _p(qlev_init), _p(qdesc_init), len(l0), None, 257, 4, _p(out_init)),
+                   m._m, matcher=True)
+    row = {"row": f"SearchForInitialization scan (ORBmatcher.cc:661-700), {len(l0)} level-0 key points x 100-px windows", "api": "orbb_search_area_topk k=4",
+           "ms_host_frame": timeit(lambda: scan_init(hv)), "ms_device_resident_frame": timeit(lambda: scan_init(ev))}
+    if with_cpu:
+        from oracle import ref
+        if ref.available():
+            f1 = dict(octaves=octs, angles=np.ascontiguousarray(k["angle"], np.float32), desc=d)
+            f2 = dict(kps_xy=kxy, octaves=octs, angles=f1["angles"], desc=d, fp=np.float32([0, W_, 0, H_, 64 / W_, 48 / H_]))
+            row["cpu_ms"] = cpu_time(lambda: ref.search_for_initialization(f1, f2, kxy, 100, 0.9, True))
+            row["cpu_kind"] = "reference (ORBmatcher::SearchForInitialization cut out of ORBmatcher.cc, one thread, incl. AssignFeaturesToGrid)"
+    rows.append(row)
     print("matcher_rows: scan done", file=sys.stderr, flush=True)
     # (2) best / second-best over candidate lists (SearchByBoW-shaped: 1000 queries x 30 candidates)
     nq = 1000
