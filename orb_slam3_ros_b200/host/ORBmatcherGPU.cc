@@ -5,6 +5,9 @@
 //   SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono)                           reference ORBmatcher.cc:1676-1887
 //       (Tracking::TrackWithMotionModel, Tracking.cc:2925 / :2933)
 //
+//   SearchByBoW(KeyFrame* pKF, Frame& F, vpMapPointMatches)                                              reference ORBmatcher.cc:223-421
+//       (Tracking::TrackReferenceKeyFrame, Tracking.cc:2769; Tracking::Relocalization, :3687)
+//
 // and for the matcher of the monocular initialisation, which Tracking calls on every frame until the map exists:
 //
 //   SearchForInitialization(Frame& F1, Frame& F2, vbPrevMatched, vnMatches12, windowSize)                reference ORBmatcher.cc:648-766
@@ -31,6 +34,7 @@
 #include <cstring>
 
 #include "Frame.h"
+#include "KeyFrame.h"
 #include "MapPoint.h"
 
 namespace ORB_SLAM3 {
@@ -55,6 +59,7 @@ struct ORBmatcherGPU::Impl {
     std::vector<int32_t> oct, qlev, out;
     std::vector<unsigned char> qdesc, skip;
     std::vector<int> src;
+    std::vector<int32_t> cand, rowptr;
 };
 
 ORBmatcherGPU::Impl& ORBmatcherGPU::Scratch() {
@@ -346,6 +351,99 @@ int ORBmatcherGPU::SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv:
     }
     for (int i1 = 0; i1 < n1; i1++)                                               // :757-760
         if (vnMatches12[i1] >= 0) vbPrevMatched[i1] = F2.mvKeysUn[vnMatches12[i1]].pt;
+    return nmatches;
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (ORBmatcher.cc:223-421; Tracking::TrackReferenceKeyFrame, Tracking.cc:2769, and
+// Tracking::Relocalization): every key-frame feature that holds a good map point is compared with the frame's features of the SAME vocabulary
+// node.  The merge loop over the two feature vectors only collects (key-frame feature, candidate list) pairs here, in the reference's order;
+// the DescriptorDistance scans of all of them are one launch (orbb_best2_csr_dev against the frame's descriptors, uploaded once per frame
+// id).  The reference skips frame features that were matched earlier in the call (:278): when the best or the second candidate of a
+// feature has been taken meanwhile, its (short) list is walked again on the host with the live vpMapPointMatches.
+int ORBmatcherGPU::SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches, const float nnratio, const bool checkOrientation) {
+    if (F.Nleft != -1 || pKF->mpCamera2)
+        throw std::logic_error("ORBmatcherGPU::SearchByBoW: fisheye-stereo frames / key frames keep the reference's host path");
+    Impl& s = Scratch();
+    const std::vector<MapPoint*> vpMapPointsKF = pKF->GetMapPointMatches();
+    vpMapPointMatches = std::vector<MapPoint*>(F.N, static_cast<MapPoint*>(NULL));
+    const DBoW2::FeatureVector& vFeatVecKF = pKF->mFeatVec;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    for (int i = 0; i < HISTO_LENGTH; i++) rotHist[i].reserve(500);
+    const float factor = 1.0f / HISTO_LENGTH;
+    s.qdesc.clear(); s.src.clear(); s.cand.clear(); s.rowptr.assign(1, 0);
+    DBoW2::FeatureVector::const_iterator KFit = vFeatVecKF.begin(), Fit = F.mFeatVec.begin();
+    const DBoW2::FeatureVector::const_iterator KFend = vFeatVecKF.end(), Fend = F.mFeatVec.end();
+    while (KFit != KFend && Fit != Fend) {                                        // :244-394
+        if (KFit->first == Fit->first) {
+            const std::vector<unsigned int>& vIndicesKF = KFit->second;
+            const std::vector<unsigned int>& vIndicesF = Fit->second;
+            for (size_t iKF = 0; iKF < vIndicesKF.size(); iKF++) {
+                const unsigned int realIdxKF = vIndicesKF[iKF];
+                MapPoint* pMP = vpMapPointsKF[realIdxKF];
+                if (!pMP || pMP->isBad()) continue;
+                const uchar* d = pKF->mDescriptors.ptr<uchar>((int)realIdxKF);
+                s.qdesc.insert(s.qdesc.end(), d, d + 32);
+                s.src.push_back((int)realIdxKF);
+                s.cand.insert(s.cand.end(), vIndicesF.begin(), vIndicesF.end());
+                s.rowptr.push_back((int32_t)s.cand.size());
+            }
+            KFit++;
+            Fit++;
+        } else if (KFit->first < Fit->first) {
+            KFit = vFeatVecKF.lower_bound(Fit->first);
+        } else {
+            Fit = F.mFeatVec.lower_bound(KFit->first);
+        }
+    }
+    const int nq = (int)s.src.size();
+    s.out.assign((size_t)nq * 4, -1);
+    if (nq > 0) {
+        const orbb_frame_view* fv = FrameView(mpMatcher, s, F, 0);
+        if (orbb_best2_csr_dev(mpMatcher, s.qdesc.data(), nq, fv->desc, F.N, s.cand.data(), s.rowptr.data(), 256, s.out.data()) != ORBB_OK)
+            throw std::runtime_error(std::string("orbb_best2_csr_dev failed: ") + orbb_matcher_last_error(mpMatcher));
+    }
+    int nmatches = 0;
+    for (int j = 0; j < nq; j++) {                                                // :265-356 per key-frame feature, in the order of the merge loop
+        const int realIdxKF = s.src[j];
+        int bestDist1 = s.out[4 * (size_t)j], bestIdxF = s.out[4 * (size_t)j + 1], bestDist2 = s.out[4 * (size_t)j + 2];
+        const int secondIdx = s.out[4 * (size_t)j + 3];
+        if ((bestIdxF >= 0 && vpMapPointMatches[bestIdxF]) || (secondIdx >= 0 && vpMapPointMatches[secondIdx])) {
+            bestDist1 = 256; bestIdxF = -1; bestDist2 = 256;                      // :273-294 on the live matches
+            const uchar* dKF = s.qdesc.data() + (size_t)32 * j;
+            for (int c = s.rowptr[j]; c < s.rowptr[j + 1]; c++) {
+                const int realIdxF = s.cand[c];
+                if (vpMapPointMatches[realIdxF]) continue;
+                const int dist = orbb_hamming_distance(dKF, F.mDescriptors.ptr<uchar>(realIdxF));
+                if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = realIdxF; }
+                else if (dist < bestDist2) bestDist2 = dist;
+            }
+            mnRescans++;
+        }
+        if (bestDist1 <= TH_LOW) {                                                // :327-356
+            if (static_cast<float>(bestDist1) < nnratio * static_cast<float>(bestDist2)) {
+                vpMapPointMatches[bestIdxF] = vpMapPointsKF[realIdxKF];
+                if (checkOrientation) {
+                    float rot = pKF->mvKeysUn[realIdxKF].angle - F.mvKeys[bestIdxF].angle;
+                    if (rot < 0.0) rot += 360.0f;
+                    int bin = round(rot * factor);
+                    if (bin == HISTO_LENGTH) bin = 0;
+                    rotHist[bin].push_back(bestIdxF);
+                }
+                nmatches++;
+            }
+        }
+    }
+    if (checkOrientation) {                                                       // :396-415
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0, jend = rotHist[i].size(); j < jend; j++) {
+                vpMapPointMatches[rotHist[i][j]] = static_cast<MapPoint*>(NULL);
+                nmatches--;
+            }
+        }
+    }
     return nmatches;
 }
 

@@ -17,6 +17,7 @@
 namespace ORB_SLAM3 {
 
 class Frame;
+class KeyFrame;
 class MapPoint;
 
 class ORBmatcherGPU {
@@ -47,6 +48,8 @@ public:
     // ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vbPrevMatched, vnMatches12, windowSize)  ORBmatcher.cc:648-766; nnratio = mfNNratio
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize,
                                 const float nnratio, const bool checkOrientation);
+    // ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches)             ORBmatcher.cc:223-421
+    int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches, const float nnratio, const bool checkOrientation);
     static void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);      // ORBmatcher.cc:2012-2053
     long Rescans() const { return mnRescans; }      // points that had to be scanned a second time (their 4 candidates did not survive the in-order decisions)
     ORBmatcherGPU(const ORBmatcherGPU&) = delete;

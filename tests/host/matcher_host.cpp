@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "Frame.h"
+#include "KeyFrame.h"
 #include "MapPoint.h"
 #include "ORBmatcherGPU.h"
 
@@ -149,6 +150,33 @@ int gpuhost_search_for_initialization(const int32_t* oct1, const float* angle1, 
     delete F1;
     delete F2;
     return nmatches;
+}
+
+// same arguments and result as refcut_search_by_bow (oracle/ref_cut_tu.cpp)
+int gpuhost_search_by_bow(const float* kfAngle, const uint8_t* kfDesc, const uint8_t* kfHasPoint, int nK, const int32_t* kfNode, const int32_t* kfStart,
+                          const int32_t* kfFeat, int kfNodes, int kfFeats, const float* fAngle, const uint8_t* fDesc, int nF, const int32_t* fNode,
+                          const int32_t* fStart, const int32_t* fFeat, int fNodes, int fFeats, float nnratio, int checkOri, int32_t* matchOf) {
+    KeyFrame kf;
+    Frame* F = new Frame();
+    F->mnId = g_frameId++;
+    std::vector<MapPoint> mps(nK);
+    kf.mvKeysUn.resize(nK); kf.mvpMapPoints.assign(nK, nullptr);
+    for (int i = 0; i < nK; i++) { kf.mvKeysUn[i].angle = kfAngle[i]; if (kfHasPoint[i]) kf.mvpMapPoints[i] = &mps[i]; }
+    kf.mDescriptors = to_descriptors(kfDesc, nK);
+    for (int g = 0; g < kfNodes; g++)
+        for (int f = kfStart[g]; f < (g + 1 < kfNodes ? kfStart[g + 1] : kfFeats); f++) kf.mFeatVec[(unsigned)kfNode[g]].push_back((unsigned)kfFeat[f]);
+    F->N = nF; F->Nleft = -1;
+    F->mvKeys.resize(nF);
+    for (int i = 0; i < nF; i++) F->mvKeys[i].angle = fAngle[i];
+    F->mvKeysUn = F->mvKeys;
+    F->mDescriptors = to_descriptors(fDesc, nF);
+    for (int g = 0; g < fNodes; g++)
+        for (int f = fStart[g]; f < (g + 1 < fNodes ? fStart[g + 1] : fFeats); f++) F->mFeatVec[(unsigned)fNode[g]].push_back((unsigned)fFeat[f]);
+    std::vector<MapPoint*> matches;
+    const int nm = ORBmatcherGPU::Instance().SearchByBoW(&kf, *F, matches, nnratio, checkOri != 0);
+    for (int i = 0; i < nF; i++) matchOf[i] = matches[i] ? (int)(matches[i] - mps.data()) : -1;
+    delete F;
+    return nm;
 }
 
 }  // extern "C"

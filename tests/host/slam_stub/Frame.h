@@ -5,6 +5,7 @@
 // are compiled; the two sides are compared on identical flat inputs by tests/test_gpu_matcher_host.py.
 #pragma once
 #include <cmath>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -14,6 +15,10 @@
 
 #define FRAME_GRID_ROWS 48
 #define FRAME_GRID_COLS 64
+
+namespace DBoW2 {
+class FeatureVector : public std::map<unsigned int, std::vector<unsigned int> > {};
+}
 
 namespace ORB_SLAM3 {
 
@@ -74,6 +79,7 @@ public:
     std::vector<bool> mvbOutlier;
     std::vector<float> mvuRight, mvDepth;
     cv::Mat mDescriptors, mDescriptorsRight;
+    DBoW2::FeatureVector mFeatVec;
     GeometricCamera *mpCamera = nullptr, *mpCamera2 = nullptr;
     static float mfGridElementWidthInv, mfGridElementHeightInv;
     std::vector<float> mvScaleFactors, mvInvScaleFactors;

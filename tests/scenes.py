@@ -105,3 +105,21 @@ def init_scene(seed=3, crowd=False, jitter=0.0):
     f2 = dict(kps_xy=np.stack([k2["x"], k2["y"]], 1).astype(np.float32), octaves=k2["octave"].astype(np.int32), angles=k2["angle"].copy(), desc=d2,
               fp=np.float32([0, w, 0, h, np.float32(64) / np.float32(w), np.float32(48) / np.float32(h)]))
     return f1, f2, prev
+
+
+def bow_scene(seed=17, levelsup=2):
+    """Tracking::TrackReferenceKeyFrame: a key frame and a frame of the same place (the two views of a stereo pair), their feature vectors
+    from the BoW transform; 85 % of the key-frame features hold a map point, a quarter of them with an inconsistent rotation."""
+    from orb_slam3_ros_b200.bow import synthetic_vocabulary
+    vocab = synthetic_vocabulary(8, 4, seed=5, stop_fraction=0.0)
+    left, right = synth.stereo_pair(376, 620, 4, dmax=25)
+    _, kk, dk, _ = port.PortExtractor(900, 1.2, 8).extract(left)
+    _, kf, df, _ = port.PortExtractor(900, 1.2, 8).extract(right)
+    rng = np.random.default_rng(seed)
+    ang_k = kk["angle"].copy()
+    turn = rng.random(len(kk)) < 0.25
+    ang_k[turn] = (ang_k[turn] + rng.uniform(40, 320, int(turn.sum())).astype(np.float32)) % np.float32(360)      # inconsistent rotations
+    has_point = (rng.random(len(kk)) < 0.85).astype(np.uint8)
+    fv_k = port.bow_transform(vocab, dk, levelsup, 1)[2:5]
+    fv_f = port.bow_transform(vocab, df, levelsup, 1)[2:5]
+    return dict(ang_k=ang_k, dk=dk, has_point=has_point, fv_k=fv_k, ang_f=kf["angle"].copy(), df=df, fv_f=fv_f, nk=len(kk), nf=len(kf))

@@ -14,7 +14,7 @@ from oracle import port, ref
 from orb_slam3_ros_b200 import capi, synth
 from orb_slam3_ros_b200.extractor import ORBextractor
 from orb_slam3_ros_b200.matcher import ORBmatcher
-from scenes import init_scene, local_points_scene, motion_scene
+from scenes import bow_scene, init_scene, local_points_scene, motion_scene
 
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
@@ -44,10 +44,35 @@ def host():
     lib.gpuhost_search_by_projection_motion.restype = C.c_int
     lib.gpuhost_search_by_projection_motion.argtypes = [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int] + \
         [C.c_void_p] * 7 + [C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    lib.gpuhost_search_by_bow.restype = C.c_int
+    lib.gpuhost_search_by_bow.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_int] + [C.c_void_p] * 2 + [C.c_int] + \
+        [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]
     lib.gpuhost_search_for_initialization.restype = C.c_int
     lib.gpuhost_search_for_initialization.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 2 + \
         [C.c_int, C.c_float, C.c_int, C.c_void_p]
     return lib
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref (the reference's own object code) is not built")
+@pytest.mark.parametrize("levelsup,nnratio,check", [(2, 0.7, True), (3, 0.75, True), (2, 0.9, False)])
+def test_search_by_bow_equals_reference(host, levelsup, nnratio, check):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (ORBmatcher.cc:223-421, Tracking::TrackReferenceKeyFrame / Relocalization):
+    the map points that the compiled GPU replacement leaves in vpMapPointMatches against the reference's own body over the vendored
+    DBoW2::FeatureVector, on the same key frame / frame pair"""
+    sc = bow_scene(levelsup=levelsup)
+    nm_ref, match_ref = ref.search_by_bow(sc["ang_k"], sc["dk"], sc["has_point"], sc["fv_k"], sc["ang_f"], sc["df"], sc["fv_f"], nnratio, check)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    ka, kd, hp, fa, fd = f32(sc["ang_k"]), u8(sc["dk"]), u8(sc["has_point"]), f32(sc["ang_f"]), u8(sc["df"])
+    kn, ks, kfe = (i32(a) for a in sc["fv_k"])
+    fn, fs, ffe = (i32(a) for a in sc["fv_f"])
+    match = np.full(len(fa), -1, np.int32)
+    r0 = host.gpuhost_rescans()
+    nm = host.gpuhost_search_by_bow(_p(ka), _p(kd), _p(hp), len(ka), _p(kn), _p(ks), _p(kfe), len(kn), len(kfe), _p(fa), _p(fd), len(fa), _p(fn), _p(fs),
+                                    _p(ffe), len(fn), len(ffe), nnratio, int(check), _p(match))
+    assert nm == nm_ref and np.array_equal(match, match_ref)
+    assert nm_ref > 100 and host.gpuhost_rescans() > r0      # matches and in-call collisions both occurred
 
 
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref (the reference's own object code) is not built")

@@ -336,19 +336,11 @@ def test_batched_search_by_bow_equals_reference_search_by_bow():
     against the batched formulation: feature vectors from the BoW transform, one best-two scan over the candidate lists of all
     key-frame features (init 256), the in-order decision (frame features matched earlier in the call are skipped, :276-277; TH_LOW
     and the strict float ratio test, :322-324) and the rotation-histogram filter (:329-341, :396-415)"""
-    from orb_slam3_ros_b200.bow import synthetic_vocabulary
-    vocab = synthetic_vocabulary(8, 4, seed=5, stop_fraction=0.0)
-    left, right = synth.stereo_pair(376, 620, 4, dmax=25)
-    _, kk, dk, _ = port.PortExtractor(900, 1.2, 8).extract(left)
-    _, kf, df, _ = port.PortExtractor(900, 1.2, 8).extract(right)
-    rng = np.random.default_rng(17)
-    ang_k = kk["angle"].copy()
-    turn = rng.random(len(kk)) < 0.25
-    ang_k[turn] = (ang_k[turn] + rng.uniform(40, 320, int(turn.sum())).astype(np.float32)) % np.float32(360)      # inconsistent rotations
-    has_point = (rng.random(len(kk)) < 0.85).astype(np.uint8)
-    levelsup = 2
-    fv_k = port.bow_transform(vocab, dk, levelsup, 1)[2:5]
-    fv_f = port.bow_transform(vocab, df, levelsup, 1)[2:5]
+    from scenes import bow_scene
+    sc = bow_scene()
+    ang_k, dk, has_point, fv_k, df, fv_f = sc["ang_k"], sc["dk"], sc["has_point"], sc["fv_k"], sc["df"], sc["fv_f"]
+    kk, kf = np.zeros(sc["nk"]), np.zeros(sc["nf"], dtype=[("angle", np.float32)])
+    kf["angle"] = sc["ang_f"]
     nnratio = 0.7
     nm_ref, match_ref = ref.search_by_bow(ang_k, dk, has_point, fv_k, kf["angle"], df, fv_f, nnratio, True)
 
