@@ -32,6 +32,11 @@ PIECES = [
      r"^\s*int ORBmatcher::SearchByProjection\(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono\)", "function"),
     ("ORBmatcher_SearchForInitialization", "src/ORBmatcher.cc",
      r"^\s*int ORBmatcher::SearchForInitialization\(Frame &F1, Frame &F2, vector<cv::Point2f> &vbPrevMatched, vector<int> &vnMatches12, int windowSize\)", "function"),
+    ("ORBmatcher_SearchByProjection_reloc", "src/ORBmatcher.cc",
+     r"^\s*int ORBmatcher::SearchByProjection\(Frame &CurrentFrame, KeyFrame \*pKF, const set<MapPoint\*> &sAlreadyFound, const float th , const int ORBdist\)", "function"),
+    ("MapPoint_PredictScale_Frame", "src/MapPoint.cc", r"^int MapPoint::PredictScale\(const float &currentDist, Frame\* pF\)", "function"),
+    ("MapPoint_GetMinDistanceInvariance", "src/MapPoint.cc", r"^float MapPoint::GetMinDistanceInvariance\(\)", "function"),
+    ("MapPoint_GetMaxDistanceInvariance", "src/MapPoint.cc", r"^float MapPoint::GetMaxDistanceInvariance\(\)", "function"),
     ("MapPoint_ComputeDistinctiveDescriptors", "src/MapPoint.cc", r"^void MapPoint::ComputeDistinctiveDescriptors\(\)", "function"),
 ]
 

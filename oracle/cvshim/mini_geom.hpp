@@ -1,10 +1,11 @@
 // ORACLE / TEST INFRASTRUCTURE (not product code): the handful of Eigen / Sophus declarations that the motion-model
-// ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) (reference orb_slam3/src/ORBmatcher.cc:1676-1887) touches --
-// Eigen::Vector2f / Vector3f with operator()(int), Sophus::SE3f with inverse(), translation() and operator*(Vector3f).  Neither
+// ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) and the relocalisation overload (reference orb_slam3/src/ORBmatcher.cc:1676-2010) touch --
+// Eigen::Vector2f / Vector3f with operator()(int), operator-, norm(), Sophus::SE3f with inverse(), translation() and operator*(Vector3f).  Neither
 // library exists in this image.  The geometry is host code on both sides of the comparison (the reference's cut-out body in
 // oracle/_ref and the GPU-backed replacement in tests/host/ are compiled against THIS header with the same flags), so the floats
 // they feed into the candidate scan are identical; what is compared is the scan and its decisions.
 #pragma once
+#include <cmath>
 
 namespace Eigen {
 struct Vector2f {
@@ -20,6 +21,8 @@ struct Vector3f {
     Vector3f(float a, float b, float c) { v[0] = a; v[1] = b; v[2] = c; }
     float& operator()(int i) { return v[i]; }
     float operator()(int i) const { return v[i]; }
+    Vector3f operator-(const Vector3f& o) const { return Vector3f(v[0] - o.v[0], v[1] - o.v[1], v[2] - o.v[2]); }
+    float norm() const { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
 };
 }  // namespace Eigen
 

@@ -328,6 +328,32 @@ def search_by_projection_motion(cur, last, th, mono, nnratio=0.9, check_orientat
     return nm, match_of
 
 
+def search_by_projection_reloc(cur, kf, th, orb_dist, nnratio=0.9, check_orientation=True):
+    """ORBmatcher(nnratio, checkOri).SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1889-2010, reference
+    text; the refinement calls of Tracking::Relocalization, Tracking.cc:3765 / :3779).
+      cur: dict(kps_xy, octaves, angles, desc, holds [n] (key point already holds a map point), fp = (mnMinX, mnMaxX, mnMinY, mnMaxY, gridWInv,
+           gridHInv, 0, 0, mnScaleLevels, mfLogScaleFactor), scale_factors, Tcw [12], cam4)
+      kf:  dict(angles, state [m] (0 no map point / 1 good / 2 bad / 3 already found), pos [m,3], desc [m,32], min_dist [m], max_dist [m])
+    -> (nmatches, match_of[n]: key-frame feature whose map point the key point received, -1 otherwise)"""
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    k, o, a, d = f32(cur["kps_xy"]).reshape(-1, 2), i32(cur["octaves"]), f32(cur["angles"]), u8(cur["desc"])
+    holds, fp, sf, tcw, cam = u8(cur["holds"]), f32(cur["fp"]), f32(cur["scale_factors"]), f32(cur["Tcw"]), f32(cur["cam4"])
+    ka, ks, kp, kd, kmin, kmax = f32(kf["angles"]), u8(kf["state"]), f32(kf["pos"]).reshape(-1, 3), u8(kf["desc"]), f32(kf["min_dist"]), f32(kf["max_dist"])
+    match_of = np.full(len(k), -1, np.int32)
+    fn = lib().refcut_search_by_projection_reloc
+    fn.restype = C.c_int
+    fn.argtypes = RELOC_ARGTYPES
+    nm = fn(_ptr(k), _ptr(o), _ptr(a), _ptr(d), len(k), _ptr(fp), _ptr(holds), _ptr(sf), len(sf), _ptr(tcw), _ptr(cam), len(ka), _ptr(ka), _ptr(ks),
+            _ptr(kp), _ptr(kd), _ptr(kmin), _ptr(kmax), th, int(orb_dist), nnratio, int(check_orientation), _ptr(match_of))
+    return nm, match_of
+
+
+RELOC_ARGTYPES = [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 6 + \
+    [C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p]
+
+
 def search_for_initialization(f1, f2, prev, window=100, nnratio=0.9, check_orientation=True):
     """ORBmatcher(nnratio, checkOri).SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (ORBmatcher.cc:648-766,
     reference text; the call of Tracking::MonocularInitialization, Tracking.cc:2527).

@@ -29,6 +29,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <set>
 #include <tuple>
 #include <vector>
 
@@ -57,6 +58,7 @@ public:
                            const float thFarPoints = 50.0f);
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
+    int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist);
     static const int TH_LOW;
     static const int TH_HIGH;
     static const int HISTO_LENGTH;
@@ -82,6 +84,11 @@ public:
 class MapPoint {                // MapPoint.h:114-207: the members the cut functions touch; the three accessors are plain stand-ins
 public:
     void ComputeDistinctiveDescriptors();
+    int PredictScale(const float& currentDist, Frame* pF);
+    float GetMinDistanceInvariance();
+    float GetMaxDistanceInvariance();
+    float mfMinDistance = 0, mfMaxDistance = 0;
+    std::mutex mMutexPos;
     int Observations() { return nObs; }
     bool isBad() { return mbBad; }
     cv::Mat GetDescriptor() { return mDescriptor.clone(); }
@@ -125,6 +132,8 @@ public:
     static float mfGridElementWidthInv, mfGridElementHeightInv;
     std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
     std::vector<float> mvScaleFactors, mvInvScaleFactors;
+    int mnScaleLevels = 0;
+    float mfLogScaleFactor = 0;
     static float mnMinX, mnMaxX, mnMinY, mnMaxY;
     int Nleft = -1, Nright = -1;
     std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;
@@ -142,6 +151,7 @@ float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX
 #include "cut/ORBmatcher_SearchByBoW_KF_F.inc"
 #include "cut/ORBmatcher_SearchByProjection_motion.inc"
 #include "cut/ORBmatcher_SearchForInitialization.inc"
+#include "cut/ORBmatcher_SearchByProjection_reloc.inc"
 #include "cut/ORBmatcher_ComputeThreeMaxima.inc"
 #include "cut/ORBmatcher_DescriptorDistance.inc"
 #include "cut/Frame_AssignFeaturesToGrid.inc"
@@ -150,6 +160,9 @@ float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX
 #include "cut/Frame_ComputeStereoMatches.inc"
 #include "cut/Frame_ComputeStereoFromRGBD.inc"
 #include "cut/MapPoint_ComputeDistinctiveDescriptors.inc"
+#include "cut/MapPoint_PredictScale_Frame.inc"
+#include "cut/MapPoint_GetMinDistanceInvariance.inc"
+#include "cut/MapPoint_GetMaxDistanceInvariance.inc"
 
 }  // namespace ORB_SLAM3
 
@@ -377,6 +390,60 @@ int refcut_search_by_projection_motion(const float* kps, const int32_t* oct, con
     }
     delete C;
     delete L;
+    return nmatches;
+}
+
+// Tracking::Relocalization's refinement call (Tracking.cc:3765, :3779): ORBmatcher(0.9, true).SearchByProjection(CurrentFrame, pKF, sFound, th, ORBdist)
+// (ORBmatcher.cc:1889-2010).  Current frame as in refcut_search_by_projection_motion, curHolds[i] != 0: key point i already holds a map point
+// (any: the scan skips non-null entries, :1952); fp additionally carries {.., mnScaleLevels, mfLogScaleFactor} at [8], [9].  Key frame: per
+// feature kfState (0 no map point / 1 good / 2 bad / 3 in sAlreadyFound), angle, world position, descriptor, mfMinDistance, mfMaxDistance.
+// -> matchOf[i] = key-frame feature whose map point key point i received in this call (-1 otherwise); returns nmatches.
+int refcut_search_by_projection_reloc(const float* kps, const int32_t* oct, const float* angle, const uint8_t* desc, int n, const float* fp,
+                                      const uint8_t* curHolds, const float* scaleFactors, int nlevels, const float* Tcw, const float* cam4, int nK,
+                                      const float* kfAngle, const uint8_t* kfState, const float* kfPos, const uint8_t* kfDesc, const float* kfMinDist,
+                                      const float* kfMaxDist, float th, int ORBdist, float nnratio, int checkOri, int32_t* matchOf) {
+    using namespace ORB_SLAM3;
+    Frame* Cf = new Frame();
+    Frame::mnMinX = fp[0]; Frame::mnMaxX = fp[1]; Frame::mnMinY = fp[2]; Frame::mnMaxY = fp[3];
+    Frame::mfGridElementWidthInv = fp[4]; Frame::mfGridElementHeightInv = fp[5];
+    GeometricCamera cam;
+    cam.fx = cam4[0]; cam.fy = cam4[1]; cam.cx = cam4[2]; cam.cy = cam4[3];
+    Cf->N = n; Cf->Nleft = -1; Cf->mpCamera = &cam;
+    Cf->mnScaleLevels = (int)fp[8]; Cf->mfLogScaleFactor = fp[9];
+    Cf->mTcw = Sophus::SE3f(Tcw, Tcw + 9);
+    Cf->mvKeysUn.resize(n);
+    for (int i = 0; i < n; i++) {
+        Cf->mvKeysUn[i].pt.x = kps[2 * i]; Cf->mvKeysUn[i].pt.y = kps[2 * i + 1]; Cf->mvKeysUn[i].octave = oct[i]; Cf->mvKeysUn[i].angle = angle[i];
+    }
+    Cf->mvKeys = Cf->mvKeysUn;
+    Cf->AssignFeaturesToGrid();
+    Cf->mDescriptors = to_descriptors(desc, n);
+    Cf->mvuRight.assign(n, -1.0f);
+    Cf->mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    MapPoint held;
+    Cf->mvpMapPoints.assign(n, nullptr);
+    for (int i = 0; i < n; i++) if (curHolds && curHolds[i]) Cf->mvpMapPoints[i] = &held;
+    KeyFrame kf;
+    std::vector<MapPoint> mps(nK);
+    std::set<MapPoint*> sFound;
+    kf.mvKeysUn.resize(nK); kf.mvpMapPoints.assign(nK, nullptr);
+    for (int j = 0; j < nK; j++) {
+        kf.mvKeysUn[j].angle = kfAngle[j];
+        if (!kfState[j]) continue;
+        mps[j].mbBad = kfState[j] == 2;
+        mps[j].mWorldPos = Eigen::Vector3f(kfPos[3 * j], kfPos[3 * j + 1], kfPos[3 * j + 2]);
+        mps[j].mDescriptor = to_descriptors(kfDesc + (size_t)32 * j, 1);
+        mps[j].mfMinDistance = kfMinDist[j]; mps[j].mfMaxDistance = kfMaxDist[j];
+        kf.mvpMapPoints[j] = &mps[j];
+        if (kfState[j] == 3) sFound.insert(&mps[j]);
+    }
+    ORBmatcher matcher(nnratio, checkOri != 0);
+    const int nmatches = matcher.SearchByProjection(*Cf, &kf, sFound, th, ORBdist);
+    for (int i = 0; i < n; i++) {
+        MapPoint* p = Cf->mvpMapPoints[i];
+        matchOf[i] = (p && p != &held) ? (int)(p - mps.data()) : -1;
+    }
+    delete Cf;
     return nmatches;
 }
 

@@ -5,6 +5,8 @@
 //   SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono)                           reference ORBmatcher.cc:1676-1887
 //       (Tracking::TrackWithMotionModel, Tracking.cc:2925 / :2933)
 //
+//   SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, sAlreadyFound, th, ORBdist)                   reference ORBmatcher.cc:1889-2010
+//       (Tracking::Relocalization, Tracking.cc:3765 / :3779)
 //   SearchByBoW(KeyFrame* pKF, Frame& F, vpMapPointMatches)                                              reference ORBmatcher.cc:223-421
 //       (Tracking::TrackReferenceKeyFrame, Tracking.cc:2769; Tracking::Relocalization, :3687)
 //
@@ -32,6 +34,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <set>
 
 #include "Frame.h"
 #include "KeyFrame.h"
@@ -93,32 +96,34 @@ static const orbb_frame_view* FrameView(orbb_matcher* m, ORBmatcherGPU::Impl& s,
     return &c.view;
 }
 
-static inline bool Taken(const Frame& F, int idx) {      // ORBmatcher.cc:88-90 / :1749-1751, evaluated on the live objects
+// which key points a scan leaves out, evaluated on the live objects: the two per-frame searches skip key points whose map point has
+// observations (ORBmatcher.cc:88-90 / :1749-1751), the relocalisation search every key point that holds a map point (:1952)
+static inline bool Taken(const Frame& F, int idx, bool any = false) {
     MapPoint* p = F.mvpMapPoints[idx];
-    return p && p->Observations() > 0;
+    return p && (any || p->Observations() > 0);
 }
 
 // first `want` candidates of query j that are still free; false when the list is exhausted although it was full (more candidates
 // may exist beyond the k returned: the caller scans that one query again)
-static bool LiveHead(const Frame& F, const int32_t* list, int k, int want, Cand* out, int& nout) {
+static bool LiveHead(const Frame& F, const int32_t* list, int k, int want, Cand* out, int& nout, bool any = false) {
     nout = 0;
     int valid = 0;
     for (int t = 0; t < k; t++) {
         const int idx = list[2 * t + 1];
         if (idx < 0) break;
         valid++;
-        if (Taken(F, idx)) continue;
+        if (Taken(F, idx, any)) continue;
         if (nout < want) { out[nout].dist = list[2 * t]; out[nout].idx = idx; nout++; }
     }
     return nout >= want || valid < k;
 }
 
-void ORBmatcherGPU::RunScan(const Frame& F, int nq, int k, std::vector<int32_t>& out, bool maskTaken, bool rightCheck, int init) {
+void ORBmatcherGPU::RunScan(const Frame& F, int nq, int k, std::vector<int32_t>& out, bool maskTaken, bool rightCheck, int init, bool takenAny) {
     Impl& s = Scratch();
     orbb_frame_view fv = *FrameView(mpMatcher, s, F, 0);
     if (!rightCheck) fv.u_right = nullptr;                 // (a scan without the mvuRight test of ORBmatcher.cc:94-100 / :1755-1761)
     s.skip.assign(F.N, 0);
-    if (maskTaken) for (int i = 0; i < F.N; i++) s.skip[i] = Taken(F, i);
+    if (maskTaken) for (int i = 0; i < F.N; i++) s.skip[i] = Taken(F, i, takenAny);
     const float grid4[4] = {Frame::mnMinX, Frame::mnMinY, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv};
     out.assign((size_t)nq * k * 2, -1);
     if (nq == 0) return;
@@ -127,10 +132,12 @@ void ORBmatcherGPU::RunScan(const Frame& F, int nq, int k, std::vector<int32_t>&
 }
 
 // one query again, with the frame as it is now
-void ORBmatcherGPU::Rescan(const Frame& F, int j, int want, void* candOut, int& nout) {
+void ORBmatcherGPU::Rescan(const Frame& F, int j, int want, void* candOut, int& nout, bool rightCheck, bool takenAny) {
     Impl& s = Scratch();
-    const orbb_frame_view* fv = FrameView(mpMatcher, s, F, 0);
-    for (int i = 0; i < F.N; i++) s.skip[i] = Taken(F, i);
+    orbb_frame_view view = *FrameView(mpMatcher, s, F, 0);
+    if (!rightCheck) view.u_right = nullptr;
+    const orbb_frame_view* fv = &view;
+    for (int i = 0; i < F.N; i++) s.skip[i] = Taken(F, i, takenAny);
     const float grid4[4] = {Frame::mnMinX, Frame::mnMinY, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv};
     int32_t o[4] = {256, -1, 256, -1};
     if (orbb_search_area_topk(mpMatcher, fv, grid4, &s.q[4 * (size_t)j], &s.qlev[2 * (size_t)j], &s.qdesc[32 * (size_t)j], 1, s.skip.data(), 256, 2, o) != ORBB_OK)
@@ -351,6 +358,80 @@ int ORBmatcherGPU::SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv:
     }
     for (int i1 = 0; i1 < n1; i1++)                                               // :757-760
         if (vnMatches12[i1] >= 0) vbPrevMatched[i1] = F2.mvKeysUn[vnMatches12[i1]].pt;
+    return nmatches;
+}
+
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1889-2010;
+// Tracking::Relocalization, Tracking.cc:3765 / :3779): the key frame's map points that were not found yet are projected with the
+// frame's pose, the scale level predicted from the distance, and the best descriptor inside the window wins if it is within ORBdist.
+// Same shape as the motion-model search; the scan leaves out every key point that holds a map point (:1952) and has no mvuRight test.
+int ORBmatcherGPU::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist,
+                                      const bool checkOrientation) {
+    if (CurrentFrame.Nleft != -1)
+        throw std::logic_error("ORBmatcherGPU::SearchByProjection: fisheye-stereo frames (Nleft != -1) keep the reference's host path");
+    Impl& s = Scratch();
+    std::vector<int> rotHist[HISTO_LENGTH];
+    for (int i = 0; i < HISTO_LENGTH; i++) rotHist[i].reserve(500);
+    const float factor = 1.0f / HISTO_LENGTH;
+    const Sophus::SE3f Tcw = CurrentFrame.GetPose();                              // :1893-1894
+    Eigen::Vector3f Ow = Tcw.inverse().translation();
+    const std::vector<MapPoint*> vpMPs = pKF->GetMapPointMatches();
+    s.q.clear(); s.qlev.clear(); s.qdesc.clear(); s.src.clear();
+    for (size_t i = 0, iend = vpMPs.size(); i < iend; i++) {                      // :1904-1944: project, distance range, predicted level, window
+        MapPoint* pMP = vpMPs[i];
+        if (!pMP || pMP->isBad() || sAlreadyFound.count(pMP)) continue;
+        Eigen::Vector3f x3Dw = pMP->GetWorldPos();
+        Eigen::Vector3f x3Dc = Tcw * x3Dw;
+        const Eigen::Vector2f uv = CurrentFrame.mpCamera->project(x3Dc);
+        if (uv(0) < CurrentFrame.mnMinX || uv(0) > CurrentFrame.mnMaxX) continue;
+        if (uv(1) < CurrentFrame.mnMinY || uv(1) > CurrentFrame.mnMaxY) continue;
+        Eigen::Vector3f PO = x3Dw - Ow;
+        float dist3D = PO.norm();
+        const float maxDistance = pMP->GetMaxDistanceInvariance();
+        const float minDistance = pMP->GetMinDistanceInvariance();
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        int nPredictedLevel = pMP->PredictScale(dist3D, &CurrentFrame);
+        const float radius = th * CurrentFrame.mvScaleFactors[nPredictedLevel];
+        const float q4[4] = {uv(0), uv(1), radius, -1.0f};
+        s.q.insert(s.q.end(), q4, q4 + 4);
+        s.qlev.push_back(nPredictedLevel - 1); s.qlev.push_back(nPredictedLevel + 1);
+        const cv::Mat d = pMP->GetDescriptor();
+        s.qdesc.insert(s.qdesc.end(), d.ptr<uchar>(), d.ptr<uchar>() + 32);
+        s.src.push_back((int)i);
+    }
+    const int nq = (int)s.src.size();
+    RunScan(CurrentFrame, nq, kTopK, s.out, true, false, 256, true);
+    int nmatches = 0;
+    for (int j = 0; j < nq; j++) {                                                // :1946-1982
+        Cand c[1];
+        int nc = 0;
+        if (!LiveHead(CurrentFrame, &s.out[(size_t)j * kTopK * 2], kTopK, 1, c, nc, true)) Rescan(CurrentFrame, j, 1, c, nc, false, true);
+        if (nc == 0) continue;
+        const int bestDist = c[0].dist, bestIdx2 = c[0].idx, i = s.src[j];
+        if (bestDist <= ORBdist) {
+            CurrentFrame.mvpMapPoints[bestIdx2] = vpMPs[i];
+            nmatches++;
+            if (checkOrientation) {
+                float rot = pKF->mvKeysUn[i].angle - CurrentFrame.mvKeysUn[bestIdx2].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = round(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rotHist[bin].push_back(bestIdx2);
+            }
+        }
+    }
+    if (checkOrientation) {                                                       // :1988-2007
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i != ind1 && i != ind2 && i != ind3) {
+                for (size_t j = 0, jend = rotHist[i].size(); j < jend; j++) {
+                    CurrentFrame.mvpMapPoints[rotHist[i][j]] = NULL;
+                    nmatches--;
+                }
+            }
+        }
+    }
     return nmatches;
 }
 

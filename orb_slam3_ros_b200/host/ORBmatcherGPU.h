@@ -7,6 +7,7 @@
 #ifndef ORBMATCHER_GPU_H
 #define ORBMATCHER_GPU_H
 
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -48,6 +49,9 @@ public:
     // ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vbPrevMatched, vnMatches12, windowSize)  ORBmatcher.cc:648-766; nnratio = mfNNratio
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize,
                                 const float nnratio, const bool checkOrientation);
+    // ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist)   ORBmatcher.cc:1889-2010
+    int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist,
+                           const bool checkOrientation);
     // ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches)             ORBmatcher.cc:223-421
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches, const float nnratio, const bool checkOrientation);
     static void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);      // ORBmatcher.cc:2012-2053
@@ -140,8 +144,9 @@ public:
     }
 
 private:
-    void RunScan(const Frame& F, int nq, int k, std::vector<int32_t>& out, bool maskTaken = true, bool rightCheck = true, int init = 256);
-    void Rescan(const Frame& F, int j, int want, void* candOut, int& nout);
+    void RunScan(const Frame& F, int nq, int k, std::vector<int32_t>& out, bool maskTaken = true, bool rightCheck = true, int init = 256,
+                 bool takenAny = false);
+    void Rescan(const Frame& F, int j, int want, void* candOut, int& nout, bool rightCheck = true, bool takenAny = false);
     Impl& Scratch();
     orbb_matcher* mpMatcher;
     Impl* mpImpl;

@@ -4,6 +4,7 @@
 // library against tests/host/slam_stub + tests/cvstub (no Eigen / Sophus / OpenCV in this image).
 #include <cstdint>
 #include <cstring>
+#include <set>
 #include <vector>
 
 #include "Frame.h"
@@ -149,6 +150,55 @@ int gpuhost_search_for_initialization(const int32_t* oct1, const float* angle1, 
     for (int i = 0; i < n1; i++) { matches12[i] = vnMatches12[i]; prev[2 * i] = vbPrevMatched[i].x; prev[2 * i + 1] = vbPrevMatched[i].y; }
     delete F1;
     delete F2;
+    return nmatches;
+}
+
+// same arguments and result as refcut_search_by_projection_reloc (oracle/ref_cut_tu.cpp)
+int gpuhost_search_by_projection_reloc(const float* kps, const int32_t* oct, const float* angle, const uint8_t* desc, int n, const float* fp,
+                                       const uint8_t* curHolds, const float* scaleFactors, int nlevels, const float* Tcw, const float* cam4, int nK,
+                                       const float* kfAngle, const uint8_t* kfState, const float* kfPos, const uint8_t* kfDesc, const float* kfMinDist,
+                                       const float* kfMaxDist, float th, int ORBdist, float nnratio, int checkOri, int32_t* matchOf) {
+    (void)nnratio;
+    Frame* Cf = new Frame();
+    Cf->mnId = g_frameId++;
+    Frame::mnMinX = fp[0]; Frame::mnMaxX = fp[1]; Frame::mnMinY = fp[2]; Frame::mnMaxY = fp[3];
+    Frame::mfGridElementWidthInv = fp[4]; Frame::mfGridElementHeightInv = fp[5];
+    GeometricCamera cam;
+    cam.fx = cam4[0]; cam.fy = cam4[1]; cam.cx = cam4[2]; cam.cy = cam4[3];
+    Cf->N = n; Cf->Nleft = -1; Cf->mpCamera = &cam;
+    Cf->mnScaleLevels = (int)fp[8]; Cf->mfLogScaleFactor = fp[9];
+    Cf->mTcw = Sophus::SE3f(Tcw, Tcw + 9);
+    Cf->mvKeysUn.resize(n);
+    for (int i = 0; i < n; i++) {
+        Cf->mvKeysUn[i].pt.x = kps[2 * i]; Cf->mvKeysUn[i].pt.y = kps[2 * i + 1]; Cf->mvKeysUn[i].octave = oct[i]; Cf->mvKeysUn[i].angle = angle[i];
+    }
+    Cf->mvKeys = Cf->mvKeysUn;
+    Cf->mDescriptors = to_descriptors(desc, n);
+    Cf->mvuRight.assign(n, -1.0f);
+    Cf->mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    MapPoint held;
+    Cf->mvpMapPoints.assign(n, nullptr);
+    for (int i = 0; i < n; i++) if (curHolds && curHolds[i]) Cf->mvpMapPoints[i] = &held;
+    KeyFrame kf;
+    std::vector<MapPoint> mps(nK);
+    std::set<MapPoint*> sFound;
+    kf.mvKeysUn.resize(nK); kf.mvpMapPoints.assign(nK, nullptr);
+    for (int j = 0; j < nK; j++) {
+        kf.mvKeysUn[j].angle = kfAngle[j];
+        if (!kfState[j]) continue;
+        mps[j].mbBad = kfState[j] == 2;
+        mps[j].mWorldPos = Eigen::Vector3f(kfPos[3 * j], kfPos[3 * j + 1], kfPos[3 * j + 2]);
+        mps[j].mDescriptor = to_descriptors(kfDesc + (size_t)32 * j, 1);
+        mps[j].mfMinDistance = kfMinDist[j]; mps[j].mfMaxDistance = kfMaxDist[j];
+        kf.mvpMapPoints[j] = &mps[j];
+        if (kfState[j] == 3) sFound.insert(&mps[j]);
+    }
+    const int nmatches = ORBmatcherGPU::Instance().SearchByProjection(*Cf, &kf, sFound, th, ORBdist, checkOri != 0);
+    for (int i = 0; i < n; i++) {
+        MapPoint* p = Cf->mvpMapPoints[i];
+        matchOf[i] = (p && p != &held) ? (int)(p - mps.data()) : -1;
+    }
+    delete Cf;
     return nmatches;
 }
 

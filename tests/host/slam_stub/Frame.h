@@ -22,8 +22,15 @@ class FeatureVector : public std::map<unsigned int, std::vector<unsigned int> > 
 
 namespace ORB_SLAM3 {
 
+class Frame;
+
 class MapPoint {
 public:
+    // stand-ins for MapPoint::GetMin/MaxDistanceInvariance and PredictScale(const float&, Frame*) (MapPoint.cc:502-512, :531-546)
+    float GetMinDistanceInvariance() { return 0.8f * mfMinDistance; }
+    float GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; }
+    inline int PredictScale(const float& currentDist, Frame* pF);
+    float mfMinDistance = 0, mfMaxDistance = 0;
     int Observations() { return nObs; }
     bool isBad() { return mbBad; }
     cv::Mat GetDescriptor() { return mDescriptor.clone(); }
@@ -83,8 +90,18 @@ public:
     GeometricCamera *mpCamera = nullptr, *mpCamera2 = nullptr;
     static float mfGridElementWidthInv, mfGridElementHeightInv;
     std::vector<float> mvScaleFactors, mvInvScaleFactors;
+    int mnScaleLevels = 0;
+    float mfLogScaleFactor = 0;
     static float mnMinX, mnMaxX, mnMinY, mnMaxY;
     int Nleft = -1, Nright = -1;
 };
+
+inline int MapPoint::PredictScale(const float& currentDist, Frame* pF) {
+    const float ratio = mfMaxDistance / currentDist;
+    int nScale = std::ceil(std::log(ratio) / pF->mfLogScaleFactor);
+    if (nScale < 0) nScale = 0;
+    else if (nScale >= pF->mnScaleLevels) nScale = pF->mnScaleLevels - 1;
+    return nScale;
+}
 
 }  // namespace ORB_SLAM3

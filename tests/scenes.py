@@ -123,3 +123,26 @@ def bow_scene(seed=17, levelsup=2):
     fv_k = port.bow_transform(vocab, dk, levelsup, 1)[2:5]
     fv_f = port.bow_transform(vocab, df, levelsup, 1)[2:5]
     return dict(ang_k=ang_k, dk=dk, has_point=has_point, fv_k=fv_k, ang_f=kf["angle"].copy(), df=df, fv_f=fv_f, nk=len(kk), nf=len(kf))
+
+
+def reloc_scene(seed=5, th=10.0):
+    """Tracking::Relocalization, refinement step: a candidate key frame's map points projected into the current frame with its (PnP) pose.
+    Built on motion_scene's geometry (the key frame takes the place of the last frame): some points are bad, some were found already, some
+    lie outside their scale-invariance distance range, some current key points already hold a point, and a dense half of the map points
+    projects onto the same places (collisions)."""
+    cur, last = motion_scene(False, 0, seed=seed, dense=True)
+    rng = np.random.default_rng(100 + seed)
+    m, n = len(last["octaves"]), len(cur["octaves"])
+    sf = np.asarray(cur["scale_factors"], np.float32)
+    depth = last["pos"][:, 2].astype(np.float32)
+    # MapPoint::UpdateNormalAndDepth: mfMaxDistance = dist * scaleFactor[level], mfMinDistance = mfMaxDistance / scaleFactor[nLevels - 1]
+    max_dist = (depth * sf[last["octaves"]]).astype(np.float32)
+    min_dist = (max_dist / sf[-1]).astype(np.float32)
+    far = rng.random(m) < 0.1
+    max_dist[far] *= np.float32(0.5)                                 # out of range: skipped by the distance test
+    state = rng.choice([0, 1, 2, 3], m, p=[0.1, 0.7, 0.1, 0.1]).astype(np.uint8)
+    fp = np.concatenate([cur["fp"][:8], np.float32([len(sf), np.log(np.float32(1.2))])]).astype(np.float32)
+    c = dict(kps_xy=cur["kps_xy"], octaves=cur["octaves"], angles=cur["angles"], desc=cur["desc"], holds=(rng.random(n) < 0.2).astype(np.uint8), fp=fp,
+             scale_factors=sf, Tcw=cur["Tcw"], cam4=cur["cam4"])
+    kf = dict(angles=last["angles"], state=state, pos=last["pos"], desc=last["desc"], min_dist=min_dist, max_dist=max_dist)
+    return c, kf

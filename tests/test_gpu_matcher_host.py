@@ -14,7 +14,7 @@ from oracle import port, ref
 from orb_slam3_ros_b200 import capi, synth
 from orb_slam3_ros_b200.extractor import ORBextractor
 from orb_slam3_ros_b200.matcher import ORBmatcher
-from scenes import bow_scene, init_scene, local_points_scene, motion_scene
+from scenes import bow_scene, init_scene, local_points_scene, motion_scene, reloc_scene
 
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
@@ -44,6 +44,8 @@ def host():
     lib.gpuhost_search_by_projection_motion.restype = C.c_int
     lib.gpuhost_search_by_projection_motion.argtypes = [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int] + \
         [C.c_void_p] * 7 + [C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    lib.gpuhost_search_by_projection_reloc.restype = C.c_int
+    lib.gpuhost_search_by_projection_reloc.argtypes = ref.RELOC_ARGTYPES
     lib.gpuhost_search_by_bow.restype = C.c_int
     lib.gpuhost_search_by_bow.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_int] + [C.c_void_p] * 2 + [C.c_int] + \
         [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]
@@ -51,6 +53,26 @@ def host():
     lib.gpuhost_search_for_initialization.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 2 + \
         [C.c_int, C.c_float, C.c_int, C.c_void_p]
     return lib
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref (the reference's own object code) is not built")
+@pytest.mark.parametrize("th,orb_dist,check,seed", [(10.0, 100, True, 5), (3.0, 64, True, 5), (10.0, 100, False, 6)])
+def test_relocalization_search_equals_reference(host, th, orb_dist, check, seed):
+    """ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1889-2010, Tracking::Relocalization with
+    (10, 100) and (3, 64), Tracking.cc:3765 / :3779)"""
+    cur, kf = reloc_scene(seed)
+    nm_ref, match_ref = ref.search_by_projection_reloc(cur, kf, th, orb_dist, 0.9, check)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    k, o, a, d = f32(cur["kps_xy"]), i32(cur["octaves"]), f32(cur["angles"]), u8(cur["desc"])
+    holds, fp, sf, tcw, cam = u8(cur["holds"]), f32(cur["fp"]), f32(cur["scale_factors"]), f32(cur["Tcw"]), f32(cur["cam4"])
+    ka, ks, kp, kd, kmin, kmax = f32(kf["angles"]), u8(kf["state"]), f32(kf["pos"]), u8(kf["desc"]), f32(kf["min_dist"]), f32(kf["max_dist"])
+    match = np.full(len(k), -1, np.int32)
+    nm = host.gpuhost_search_by_projection_reloc(_p(k), _p(o), _p(a), _p(d), len(k), _p(fp), _p(holds), _p(sf), len(sf), _p(tcw), _p(cam), len(ka), _p(ka),
+                                                 _p(ks), _p(kp), _p(kd), _p(kmin), _p(kmax), th, orb_dist, 0.9, int(check), _p(match))
+    assert nm == nm_ref and np.array_equal(match, match_ref)
+    assert nm_ref > 30
 
 
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref (the reference's own object code) is not built")
