@@ -16,7 +16,7 @@ static double run(ORBextractor& ext, cv::Mat& im, int reps, size_t& n) {
     std::vector<cv::KeyPoint> keys;
     cv::Mat desc;
     std::vector<int> lapping = {0, 1000};
-    for (int i = 0; i < 10; i++) ext(im, cv::Mat(), keys, desc, lapping);
+    for (int i = 0; i < (reps < 10 ? reps : 10); i++) ext(im, cv::Mat(), keys, desc, lapping);
     const auto t0 = std::chrono::steady_clock::now();
     for (int i = 0; i < reps; i++) ext(im, cv::Mat(), keys, desc, lapping);
     const auto t1 = std::chrono::steady_clock::now();
