@@ -115,3 +115,20 @@ def test_reference_call_site_text_compiles_against_the_adapter_header(tmp_path):
     r = subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-w", f"-I{ROOT / 'oracle' / 'cvshim'}", f"-I{pkg / 'host'}", f"-I{ROOT / 'include'}", f"-I{tmp_path}",
                         str(ROOT / "tests" / "host" / "callsite_check.cpp")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_latency_tool_and_matcher_harness_compile():
+    """bench.py's `single_frame_cpp_adapter` leg (tests/host/adapter_latency.cpp) and the matcher harness of the GPU tests
+    (tests/host/matcher_host.cpp + host/ORBmatcherGPU.cc against tests/host/slam_stub) must compile where there is no GPU"""
+    from orb_slam3_ros_b200 import build
+    build.build_library()
+    pkg = ROOT / "orb_slam3_ros_b200"
+    out = EXE.parent
+    out.mkdir(exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++14", "-O1", f"-I{ROOT / 'tests' / 'cvstub'}", f"-I{ROOT / 'include'}", f"-I{pkg / 'host'}",
+                           str(ROOT / "tests" / "host" / "adapter_latency.cpp"), str(pkg / "host" / "ORBextractor.cc"), f"-L{pkg}", "-lorbb200",
+                           f"-Wl,-rpath,{pkg}", "-L/usr/local/cuda/lib64", "-lcudart", "-o", str(out / "adapter_latency_cpu_check")])
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-ffp-contract=off", "-fPIC", "-shared", f"-I{ROOT / 'tests' / 'cvstub'}",
+                           f"-I{ROOT / 'tests' / 'host' / 'slam_stub'}", f"-I{ROOT / 'oracle' / 'cvshim'}", f"-I{ROOT / 'include'}", f"-I{pkg / 'host'}",
+                           str(ROOT / "tests" / "host" / "matcher_host.cpp"), str(pkg / "host" / "ORBmatcherGPU.cc"), f"-L{pkg}", "-lorbb200",
+                           f"-Wl,-rpath,{pkg}", "-o", str(out / "libmatcher_host_cpu_check.so")])
