@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--no-matcher-rows", action="store_true")
     ap.add_argument("--no-config3", action="store_true")
     ap.add_argument("--config3-frames", type=int, default=4096)
+    ap.add_argument("--e2e-handles", type=int, default=2, help="extractor handles that alternate in the end-to-end leg (batches in flight)")
     ap.add_argument("--latency-reps", type=int, default=100, help="single-frame calls in the latency legs (the ncu launch-list pass uses 2)")
     ap.add_argument("--sustain-s", type=float, default=2.0, help="seconds of back-to-back resident extraction for the sustained figure")
     ap.add_argument("--no-bind", action="store_true", help="do not bind the rank to its GPU's local cores / NUMA node")
@@ -497,10 +498,11 @@ def run_ours(a):
     # Two handles alternate (submit batch i+1 on one while the other still computes batch i), the way a frame server
     # would drive the library; every step still uploads its own 92 MB of frames and downloads its own results.
     cap = ext.max_keypoints
-    ext2 = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=B)
-    exts = [ext, ext2]
+    NH = max(2, a.e2e_handles)
+    exts = [ext] + [ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=B) for _ in range(NH - 1)]
+    ext2 = exts[1]
     outs, outs_t = [], []
-    for _ in range(2):
+    for _ in range(NH):
         out_k = torch.empty((B, cap, 24), dtype=torch.uint8).pin_memory()
         out_d = torch.empty((B, cap, 32), dtype=torch.uint8).pin_memory()
         out_c = torch.empty((B, 2), dtype=torch.int32).pin_memory()
@@ -509,13 +511,14 @@ def run_ours(a):
     host_np = [h.numpy() for h in host_sets]
 
     def e2e_steps(n):
-        pending = None
+        pending = []
         for i in range(n):
-            exts[i % 2].submit_batch_host(host_np[i % NSETS], LAPPING, out=outs[i % 2])
-            if pending is not None:
-                pending.wait_batch_host()
-            pending = exts[i % 2]
-        pending.wait_batch_host()
+            exts[i % NH].submit_batch_host(host_np[i % NSETS], LAPPING, out=outs[i % NH])
+            pending.append(exts[i % NH])
+            if len(pending) == NH:
+                pending.pop(0).wait_batch_host()
+        for e in pending:
+            e.wait_batch_host()
 
     e2e_steps(max(a.warmup, 2))
     barrier()
@@ -533,6 +536,7 @@ def run_ours(a):
         ext.extract_batch_host(host_np[i % NSETS], LAPPING, out=outs[0])
     e2e_sync_s = max_over_ranks(time.perf_counter() - t0)
     del ext2
+    del exts[1:]
 
     # copy-only ceiling of the box: the SAME pinned buffers and byte counts per step, plain cudaMemcpyAsync (H2D in the pipeline's
     # two chunks on one stream, the result D2H on another), no kernels, all ranks at once.  What the end-to-end number can reach at
@@ -897,7 +901,7 @@ def run_ours(a):
                     "copy_ceiling_gbs_all_ranks": ceilings["copy_ceiling"] * (h2d + d2h) / B / 1e9,
                     "frac_of_copy_ceiling": e2e_value / ceilings["copy_ceiling"],
                     "copy_ceiling_note": "same pinned buffers and bytes per step as the e2e leg, plain cudaMemcpyAsync on two streams, no kernels, all ranks concurrently",
-                    "api": "orbb_extract_batch_host_submit/_wait on two alternating handles (pinned host frames -> keypoints+descriptors)",
+                    "api": f"orbb_extract_batch_host_submit/_wait on {NH} alternating handles (pinned host frames -> keypoints+descriptors)",
                     "single_sync_call_frames_per_s": world * B * a.steps / e2e_sync_s},
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "knn": knn, "stereo": stereo, "config3": config3, "matcher_rows": matcher_rows, "other_shapes": shapes, "clocks": clk,

@@ -2263,10 +2263,13 @@ int orbb_extract_batch_host_submit(orbb_extractor* h, const uint8_t* host_imgs, 
         h->pendingCapacity = (kps || desc) ? capacity : INT_MAX;
         return ORBB_OK;
     }
-    // Pipeline in chunks of frames (2 by default, up to 8 with ORBB_CHUNKS): H2D (copy engine 1) -> kernels (handle stream) -> D2H (copy engine 2), so the
-    // upload of chunk c+1 and the download of chunk c-1 overlap the kernels of chunk c.
+    // Pipeline in chunks of frames (about 64 frames each, at most 4; up to 8 with ORBB_CHUNKS): H2D (copy engine 1) -> kernels (handle stream) ->
+    // D2H (copy engine 2), so the upload of chunk c+1 and the download of chunk c-1 overlap the kernels of chunk c; the first upload and the
+    // last chunk's kernels are what cannot be hidden, so smaller chunks help until the per-launch tails of small batches cost more.
     static const int chunkOverride = getenv("ORBB_CHUNKS") ? atoi(getenv("ORBB_CHUNKS")) : 0;
-    const int nchunks = chunkOverride > 0 ? std::min(std::min(chunkOverride, 8), nframes) : (nframes >= 8 ? 2 : 1);      // measured: 2 chunks 127.7k frames/s end to end, 1: 122k, 3: 121k, 4: 118k
+    // measured end to end, 256 frames per call, two alternating handles: 2 chunks 141.5 k frames/s, 3: 144.3 k, 4: 145.1 k (0.969 of the copy
+    // ceiling), 5: 141.6 k, 6: 140.3 k, 8: 136.0 k
+    const int nchunks = chunkOverride > 0 ? std::min(std::min(chunkOverride, 8), nframes) : (nframes >= 192 ? 4 : nframes >= 96 ? 3 : nframes >= 8 ? 2 : 1);
     const int per = (nframes + nchunks - 1) / nchunks;
     const int ncopy = std::min(capacity, P.kpCap);
     ORBB_CUDA(h, cudaEventRecord(h->evDone[0], h->stream));                  // earlier work on the handle's stream ...
