@@ -145,6 +145,17 @@ __device__ __forceinline__ unsigned vresize4(const int (&h0)[4], const int (&h1)
     return out;
 }
 
+// The same with the two products of a pixel pair packed into one word: (b * h) >> 16 is the upper half of a 32-bit product (b <= 2048,
+// h < 2^15), so one PRMT packs two of them, the sums of the two rows and the rounding constant add as halves (<= 1022 each) and the
+// four result bytes are byte 0 of each half after the shift: 8 IMAD + 5 PRMT + 2 IADD3 + 2 SHF instead of 8 IMAD.HI + 15.  b0, b1 are
+// the plain coefficients here (not shifted by 16).
+__device__ __forceinline__ unsigned vresize4p(const int (&h0)[4], const int (&h1)[4], unsigned b0, unsigned b1) {
+    const unsigned p01 = __byte_perm(b0 * (unsigned)h0[0], b0 * (unsigned)h0[1], 0x7632), p23 = __byte_perm(b0 * (unsigned)h0[2], b0 * (unsigned)h0[3], 0x7632);
+    const unsigned q01 = __byte_perm(b1 * (unsigned)h1[0], b1 * (unsigned)h1[1], 0x7632), q23 = __byte_perm(b1 * (unsigned)h1[2], b1 * (unsigned)h1[3], 0x7632);
+    const unsigned s01 = (p01 + q01 + 0x00020002u) >> 2, s23 = (p23 + q23 + 0x00020002u) >> 2;
+    return __byte_perm(s01, s23, 0x6420);
+}
+
 // ROWS = destination rows per thread: PR_ROWS for batches; PR_ROWS_LATENCY for a call with a few frames, where a level is one
 // short dependent kernel on the critical path and more, shorter threads finish it sooner.
 template <int ROWS, bool PRMT>
@@ -175,7 +186,7 @@ __global__ void __launch_bounds__(PR_THREADS, 12) k_pyr_resize_t(const Plan* __r
     }
     if (tid < rowsPerCta && dyc + tid < Lh) {
         const int2 t = __ldg(tyc + dyc + tid);
-        sRow[tid] = make_int4(min(max(t.x, 0), Sh1) - rs0, min(max(t.x + 1, 0), Sh1) - rs0, (int)(t.y << 16), (int)(t.y & 0xffff0000));
+        sRow[tid] = make_int4(min(max(t.x, 0), Sh1) - rs0, min(max(t.x + 1, 0), Sh1) - rs0, (int)(t.y & 0xffff), (int)((unsigned)t.y >> 16));
     }
     __syncthreads();
     pdl_wait();                                                           // (everything above reads the plan's tables only)
@@ -219,7 +230,7 @@ __global__ void __launch_bounds__(PR_THREADS, 12) k_pyr_resize_t(const Plan* __r
     // emit every destination row whose lower source row is the newest one (`nw`; `pv` = the row before it)
 #define PR_EMIT(nw, pv)                                                                                         \
     while (cur.y == s) {                                                                                        \
-        *reinterpret_cast<unsigned*>(d) = cur.x == s ? vresize4(nw, nw, cur.z, cur.w) : vresize4(pv, nw, cur.z, cur.w); \
+        *reinterpret_cast<unsigned*>(d) = cur.x == s ? vresize4p(nw, nw, cur.z, cur.w) : vresize4p(pv, nw, cur.z, cur.w); \
         d += Lpitch;                                                                                            \
         if (++r == rows) return;                                                                                \
         cur = rowt[r];                                                                                          \
