@@ -14,7 +14,10 @@
 // The generic k_pyr_resize (orbb_extract.cu) stays as the fallback for larger scale steps.
 #pragma once
 
-constexpr int PR_ROWS = 8;            // destination rows per thread
+#ifndef ORBB_PR_ROWS
+#define ORBB_PR_ROWS 8
+#endif
+constexpr int PR_ROWS = ORBB_PR_ROWS;            // destination rows per thread (12 and 16 measured: see DESIGN.md)
 constexpr int PR_ROWS_LATENCY = 2;    // ... in calls with a few frames (k_pyr_resize_t only)
 constexpr int PR_THREADS = 128;       // 32 word-columns x 4 row strips
 
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(PR_THREADS, 16) k_pyr_resize_s(const Plan* __r
 // The same kernel with the source rows of the CTA (32 destination rows x 128 destination columns -> about 40 rows x 176 bytes)
 // staged in shared memory by one TMA bulk copy per source row: the three words per source row then come from shared
 // memory (short scoreboard) instead of L1/L2 (long scoreboard, which is what the kernel above waits on most).
-constexpr int PR_SROWS = 48, PR_SPITCH = 208;
+constexpr int PR_SROWS = PR_ROWS <= 8 ? 48 : PR_ROWS * 5 + 8, PR_SPITCH = 208;
 
 __device__ __forceinline__ unsigned vresize4(const int (&h0)[4], const int (&h1)[4], int b0, int b1) {
     unsigned out = 0;
@@ -161,7 +164,7 @@ __device__ __forceinline__ unsigned vresize4p(const int (&h0)[4], const int (&h1
 template <int ROWS, bool PRMT>
 __global__ void __launch_bounds__(PR_THREADS, 12) k_pyr_resize_t(const Plan* __restrict__ P, Bufs B, int level) {
     __shared__ __align__(128) uint8_t sSrc[PR_SROWS * PR_SPITCH];
-    __shared__ __align__(16) int4 sRow[(PR_THREADS / 32) * ROWS];      // per destination row of the CTA: {r0, r1, b0 << 16, b1 << 16}
+    __shared__ __align__(16) int4 sRow[(PR_THREADS / 32) * ROWS];      // per destination row of the CTA: {r0, r1, b0, b1}
     __shared__ __align__(8) unsigned long long sBar;
     const LevelPlan& L = P->lv[level];
     const LevelPlan& S = P->lv[level - 1];
