@@ -169,7 +169,10 @@ __global__ void __launch_bounds__(256) k_resize_image(const int2* __restrict__ t
 // the pyramid is handed out, ensure_full_apron): rows outside the image are read through reflected row pointers (first / last
 // strip only), the word left of the image and the bytes right of it are byte permutes of the two nearest image words (first /
 // last two word columns only).
-constexpr int BLUR_THREADS = 128, BLUR_STRIP = 32, BLUR_STRIP_EDGE = 8;
+#ifndef ORBB_BLUR_STRIP
+#define ORBB_BLUR_STRIP 32
+#endif
+constexpr int BLUR_THREADS = 128, BLUR_STRIP = ORBB_BLUR_STRIP, BLUR_STRIP_EDGE = 8;
 
 __device__ __forceinline__ unsigned hsum7(unsigned a, unsigned b) {
     // a = bytes x-3..x (taps 18,34,48,56), b = bytes x+1..x+4 (taps 48,34,18,0); result <= 255 * 256 fits 16 bits
@@ -1137,7 +1140,10 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 //   2. lanes 0..OD_KPW-1: fastAtan2 + cos/sin of their own keypoint.
 //   3. per keypoint, lane = descriptor byte: the 8 steered tests, pattern points held in registers.
 constexpr int OD_THREADS = 256;
-constexpr int OD_KPW = 8;
+#ifndef ORBB_OD_KPW
+#define ORBB_OD_KPW 8
+#endif
+constexpr int OD_KPW = ORBB_OD_KPW;
 constexpr int OD_ITEMS = 31 * 9;                              // words of the moment window
 
 __device__ int2 gMomW[4][9][32];                             // [column alignment][round][lane] -> (u weights, v weights)
@@ -1197,7 +1203,7 @@ __global__ void __launch_bounds__(OD_THREADS, 4) k_orient_desc32(const Plan* __r
     __shared__ int sRed[ASM ? OD_THREADS / 32 + 2 : 1];
     constexpr int KPW = ASM ? OD_KPW_LAT : OD_KPW;           // key points per warp
     constexpr int CTA_KPS = (OD_THREADS / 32) * KPW;          // key points per CTA
-    static_assert(CTA_KPS <= 64, "the assembly prologue holds one key point per thread of warps 0 and 1");
+    static_assert(!ASM || CTA_KPS <= 64, "the assembly prologue holds one key point per thread of warps 0 and 1");
     __shared__ WorkItem sWork[ASM ? CTA_KPS : 1];
     const int frame = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
