@@ -32,6 +32,8 @@ PIECES = [
      r"^\s*int ORBmatcher::SearchByProjection\(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono\)", "function"),
     ("ORBmatcher_SearchForInitialization", "src/ORBmatcher.cc",
      r"^\s*int ORBmatcher::SearchForInitialization\(Frame &F1, Frame &F2, vector<cv::Point2f> &vbPrevMatched, vector<int> &vnMatches12, int windowSize\)", "function"),
+    ("ORBmatcher_SearchByBoW_KF_KF", "src/ORBmatcher.cc",
+     r"^\s*int ORBmatcher::SearchByBoW\(KeyFrame \*pKF1, KeyFrame \*pKF2, vector<MapPoint \*> &vpMatches12\)", "function"),
     ("ORBmatcher_SearchByProjection_reloc", "src/ORBmatcher.cc",
      r"^\s*int ORBmatcher::SearchByProjection\(Frame &CurrentFrame, KeyFrame \*pKF, const set<MapPoint\*> &sAlreadyFound, const float th , const int ORBdist\)", "function"),
     ("MapPoint_PredictScale_Frame", "src/MapPoint.cc", r"^int MapPoint::PredictScale\(const float &currentDist, Frame\* pF\)", "function"),

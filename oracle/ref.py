@@ -354,6 +354,28 @@ RELOC_ARGTYPES = [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [
     [C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p]
 
 
+def search_by_bow_kf(angle1, desc1, state1, fv1, angle2, desc2, state2, fv2, nnratio=0.8, check_orientation=True):
+    """ORBmatcher(nnratio, checkOri).SearchByBoW(pKF1, pKF2, vpMatches12) (ORBmatcher.cc:765-905, reference text; LoopClosing.cc:1680) for two
+    monocular key frames; state: 0 no map point / 1 good / 2 bad; fv = (node, start, feat) arrays
+    -> (nmatches, match_of[n1]: feature of key frame 2 whose map point feature i of key frame 1 was matched to, -1 none)"""
+    a1, a2 = np.ascontiguousarray(angle1, np.float32), np.ascontiguousarray(angle2, np.float32)
+    d1, d2 = np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(desc2, np.uint8)
+    s1, s2 = np.ascontiguousarray(state1, np.uint8), np.ascontiguousarray(state2, np.uint8)
+    n1_, st1, f1_ = (np.ascontiguousarray(a, np.int32) for a in fv1)
+    n2_, st2, f2_ = (np.ascontiguousarray(a, np.int32) for a in fv2)
+    match_of = np.full(len(a1), -1, np.int32)
+    fn = lib().refcut_search_by_bow_kf
+    fn.restype = C.c_int
+    fn.argtypes = BOW_KF_ARGTYPES
+    nm = fn(_ptr(a1), _ptr(d1), _ptr(s1), len(a1), _ptr(n1_), _ptr(st1), _ptr(f1_), len(n1_), len(f1_), _ptr(a2), _ptr(d2), _ptr(s2), len(a2), _ptr(n2_),
+            _ptr(st2), _ptr(f2_), len(n2_), len(f2_), nnratio, int(check_orientation), _ptr(match_of))
+    return nm, match_of
+
+
+BOW_KF_ARGTYPES = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + \
+    [C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]
+
+
 def search_for_initialization(f1, f2, prev, window=100, nnratio=0.9, check_orientation=True):
     """ORBmatcher(nnratio, checkOri).SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (ORBmatcher.cc:648-766,
     reference text; the call of Tracking::MonocularInitialization, Tracking.cc:2527).

@@ -54,6 +54,7 @@ public:
     ORBmatcher(float nnratio = 0.6, bool checkOri = true);
     static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
+    int SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12);
     int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3, const bool bFarPoints = false,
                            const float thFarPoints = 50.0f);
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
@@ -149,6 +150,7 @@ float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX
 #include "cut/ORBmatcher_SearchByProjection_local.inc"
 #include "cut/ORBmatcher_RadiusByViewingCos.inc"
 #include "cut/ORBmatcher_SearchByBoW_KF_F.inc"
+#include "cut/ORBmatcher_SearchByBoW_KF_KF.inc"
 #include "cut/ORBmatcher_SearchByProjection_motion.inc"
 #include "cut/ORBmatcher_SearchForInitialization.inc"
 #include "cut/ORBmatcher_SearchByProjection_reloc.inc"
@@ -511,6 +513,33 @@ int refcut_search_by_bow(const float* kfAngle, const uint8_t* kfDesc, const uint
     const int nm = matcher.SearchByBoW(&kf, *F, matches);
     for (int i = 0; i < nF; i++) matchOf[i] = matches[i] ? (int)(matches[i] - mps.data()) : -1;
     delete F;
+    return nm;
+}
+
+// ORBmatcher(nnratio, checkOri).SearchByBoW(pKF1, pKF2, vpMatches12) (ORBmatcher.cc:765-905; LoopClosing's candidate check, LoopClosing.cc:1680)
+// on two monocular key frames.  state1 / state2 per feature: 0 no map point / 1 good / 2 bad.  -> matchOf[n1] = feature of key frame 2 whose
+// map point was matched to feature i of key frame 1 (-1 none); returns nmatches.
+int refcut_search_by_bow_kf(const float* angle1, const uint8_t* desc1, const uint8_t* state1, int n1, const int32_t* node1, const int32_t* start1,
+                            const int32_t* feat1, int nodes1, int feats1, const float* angle2, const uint8_t* desc2, const uint8_t* state2, int n2,
+                            const int32_t* node2, const int32_t* start2, const int32_t* feat2, int nodes2, int feats2, float nnratio, int checkOri,
+                            int32_t* matchOf) {
+    using namespace ORB_SLAM3;
+    KeyFrame k1, k2;
+    std::vector<MapPoint> mps1(n1), mps2(n2);
+    k1.mvKeysUn.resize(n1); k1.mvpMapPoints.assign(n1, nullptr);
+    for (int i = 0; i < n1; i++) { k1.mvKeysUn[i].angle = angle1[i]; if (state1[i]) { mps1[i].mbBad = state1[i] == 2; k1.mvpMapPoints[i] = &mps1[i]; } }
+    k1.mDescriptors = to_descriptors(desc1, n1);
+    for (int g = 0; g < nodes1; g++)
+        for (int f = start1[g]; f < (g + 1 < nodes1 ? start1[g + 1] : feats1); f++) k1.mFeatVec.addFeature(node1[g], feat1[f]);
+    k2.mvKeysUn.resize(n2); k2.mvpMapPoints.assign(n2, nullptr);
+    for (int i = 0; i < n2; i++) { k2.mvKeysUn[i].angle = angle2[i]; if (state2[i]) { mps2[i].mbBad = state2[i] == 2; k2.mvpMapPoints[i] = &mps2[i]; } }
+    k2.mDescriptors = to_descriptors(desc2, n2);
+    for (int g = 0; g < nodes2; g++)
+        for (int f = start2[g]; f < (g + 1 < nodes2 ? start2[g + 1] : feats2); f++) k2.mFeatVec.addFeature(node2[g], feat2[f]);
+    std::vector<MapPoint*> matches;
+    ORBmatcher matcher(nnratio, checkOri != 0);
+    const int nm = matcher.SearchByBoW(&k1, &k2, matches);
+    for (int i = 0; i < n1; i++) matchOf[i] = matches[i] ? (int)(matches[i] - mps2.data()) : -1;
     return nm;
 }
 

@@ -10,6 +10,9 @@
 //   SearchByBoW(KeyFrame* pKF, Frame& F, vpMapPointMatches)                                              reference ORBmatcher.cc:223-421
 //       (Tracking::TrackReferenceKeyFrame, Tracking.cc:2769; Tracking::Relocalization, :3687)
 //
+//   SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vpMatches12)                                             reference ORBmatcher.cc:765-905
+//       (LoopClosing::DetectCommonRegionsFromBoW, LoopClosing.cc:1680 -- the one call here that is not made by the Tracking thread)
+//
 // and for the matcher of the monocular initialisation, which Tracking calls on every frame until the map exists:
 //
 //   SearchForInitialization(Frame& F1, Frame& F2, vbPrevMatched, vnMatches12, windowSize)                reference ORBmatcher.cc:648-766
@@ -258,6 +261,109 @@ int ORBmatcherGPU::SearchByProjection(Frame& CurrentFrame, const Frame& LastFram
                     CurrentFrame.mvpMapPoints[rotHist[i][j]] = static_cast<MapPoint*>(NULL);
                     nmatches--;
                 }
+            }
+        }
+    }
+    return nmatches;
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vpMatches12) (ORBmatcher.cc:765-905; LoopClosing's candidate check,
+// LoopClosing.cc:1680): as above between two key frames -- a candidate must hold a good map point itself and must not have been matched
+// earlier in the call (vbMatched2, :826), the accept test is bestDist1 < TH_LOW (strict).  The candidate lists are collected with the
+// static part of that filter applied; one orbb_best2_csr launch against the second key frame's descriptors; lists whose head was matched
+// meanwhile are walked again on the host.
+int ORBmatcherGPU::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12, const float nnratio, const bool checkOrientation) {
+    if (pKF1->NLeft != -1 || pKF2->NLeft != -1)
+        throw std::logic_error("ORBmatcherGPU::SearchByBoW: fisheye-stereo key frames keep the reference's host path");
+    Impl& s = Scratch();
+    const std::vector<cv::KeyPoint>& vKeysUn1 = pKF1->mvKeysUn;
+    const std::vector<cv::KeyPoint>& vKeysUn2 = pKF2->mvKeysUn;
+    const DBoW2::FeatureVector& vFeatVec1 = pKF1->mFeatVec;
+    const DBoW2::FeatureVector& vFeatVec2 = pKF2->mFeatVec;
+    const std::vector<MapPoint*> vpMapPoints1 = pKF1->GetMapPointMatches();
+    const std::vector<MapPoint*> vpMapPoints2 = pKF2->GetMapPointMatches();
+    const cv::Mat& Descriptors1 = pKF1->mDescriptors;
+    const cv::Mat& Descriptors2 = pKF2->mDescriptors;
+    vpMatches12 = std::vector<MapPoint*>(vpMapPoints1.size(), static_cast<MapPoint*>(NULL));
+    std::vector<bool> vbMatched2(vpMapPoints2.size(), false);
+    std::vector<unsigned char> good2(vpMapPoints2.size(), 0);                     // :824-830, the part that does not change during the call
+    for (size_t i = 0; i < vpMapPoints2.size(); i++) good2[i] = vpMapPoints2[i] && !vpMapPoints2[i]->isBad();
+    std::vector<int> rotHist[HISTO_LENGTH];
+    for (int i = 0; i < HISTO_LENGTH; i++) rotHist[i].reserve(500);
+    const float factor = 1.0f / HISTO_LENGTH;
+    s.qdesc.clear(); s.src.clear(); s.cand.clear(); s.rowptr.assign(1, 0);
+    DBoW2::FeatureVector::const_iterator f1it = vFeatVec1.begin(), f2it = vFeatVec2.begin();
+    const DBoW2::FeatureVector::const_iterator f1end = vFeatVec1.end(), f2end = vFeatVec2.end();
+    while (f1it != f1end && f2it != f2end) {                                      // :793-882
+        if (f1it->first == f2it->first) {
+            for (size_t i1 = 0, iend1 = f1it->second.size(); i1 < iend1; i1++) {
+                const size_t idx1 = f1it->second[i1];
+                MapPoint* pMP1 = vpMapPoints1[idx1];
+                if (!pMP1 || pMP1->isBad()) continue;
+                const uchar* d = Descriptors1.ptr<uchar>((int)idx1);
+                s.qdesc.insert(s.qdesc.end(), d, d + 32);
+                s.src.push_back((int)idx1);
+                for (size_t i2 = 0, iend2 = f2it->second.size(); i2 < iend2; i2++)
+                    if (good2[f2it->second[i2]]) s.cand.push_back((int32_t)f2it->second[i2]);
+                s.rowptr.push_back((int32_t)s.cand.size());
+            }
+            f1it++;
+            f2it++;
+        } else if (f1it->first < f2it->first) {
+            f1it = vFeatVec1.lower_bound(f2it->first);
+        } else {
+            f2it = vFeatVec2.lower_bound(f1it->first);
+        }
+    }
+    const int nq = (int)s.src.size();
+    s.out.assign((size_t)nq * 4, -1);
+    if (nq > 0 && !s.cand.empty()) {
+        if (!Descriptors2.isContinuous()) throw std::runtime_error("KeyFrame::mDescriptors must be continuous");
+        if (orbb_best2_csr(mpMatcher, s.qdesc.data(), nq, Descriptors2.ptr<uchar>(), Descriptors2.rows, s.cand.data(), s.rowptr.data(), 256, s.out.data()) != ORBB_OK)
+            throw std::runtime_error(std::string("orbb_best2_csr failed: ") + orbb_matcher_last_error(mpMatcher));
+    } else {
+        for (int j = 0; j < nq; j++) { s.out[4 * (size_t)j] = 256; s.out[4 * (size_t)j + 2] = 256; }
+    }
+    int nmatches = 0;
+    for (int j = 0; j < nq; j++) {
+        const int idx1 = s.src[j];
+        int bestDist1 = s.out[4 * (size_t)j], bestIdx2 = s.out[4 * (size_t)j + 1], bestDist2 = s.out[4 * (size_t)j + 2];
+        const int secondIdx = s.out[4 * (size_t)j + 3];
+        if ((bestIdx2 >= 0 && vbMatched2[bestIdx2]) || (secondIdx >= 0 && vbMatched2[secondIdx])) {
+            bestDist1 = 256; bestIdx2 = -1; bestDist2 = 256;                      // :816-846 on the live vbMatched2
+            const uchar* d1 = s.qdesc.data() + (size_t)32 * j;
+            for (int c = s.rowptr[j]; c < s.rowptr[j + 1]; c++) {
+                const int idx2 = s.cand[c];
+                if (vbMatched2[idx2]) continue;
+                const int dist = orbb_hamming_distance(d1, Descriptors2.ptr<uchar>(idx2));
+                if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+                else if (dist < bestDist2) bestDist2 = dist;
+            }
+            mnRescans++;
+        }
+        if (bestDist1 < TH_LOW) {                                                 // :848-868
+            if (static_cast<float>(bestDist1) < nnratio * static_cast<float>(bestDist2)) {
+                vpMatches12[idx1] = vpMapPoints2[bestIdx2];
+                vbMatched2[bestIdx2] = true;
+                if (checkOrientation) {
+                    float rot = vKeysUn1[idx1].angle - vKeysUn2[bestIdx2].angle;
+                    if (rot < 0.0) rot += 360.0f;
+                    int bin = round(rot * factor);
+                    if (bin == HISTO_LENGTH) bin = 0;
+                    rotHist[bin].push_back(idx1);
+                }
+                nmatches++;
+            }
+        }
+    }
+    if (checkOrientation) {                                                       // :884-902
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0, jend = rotHist[i].size(); j < jend; j++) {
+                vpMatches12[rotHist[i][j]] = static_cast<MapPoint*>(NULL);
+                nmatches--;
             }
         }
     }

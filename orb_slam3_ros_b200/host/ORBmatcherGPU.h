@@ -54,6 +54,8 @@ public:
                            const bool checkOrientation);
     // ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches)             ORBmatcher.cc:223-421
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches, const float nnratio, const bool checkOrientation);
+    // ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12)              ORBmatcher.cc:765-905
+    int SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12, const float nnratio, const bool checkOrientation);
     static void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);      // ORBmatcher.cc:2012-2053
     long Rescans() const { return mnRescans; }      // points that had to be scanned a second time (their 4 candidates did not survive the in-order decisions)
     ORBmatcherGPU(const ORBmatcherGPU&) = delete;

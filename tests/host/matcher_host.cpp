@@ -229,4 +229,27 @@ int gpuhost_search_by_bow(const float* kfAngle, const uint8_t* kfDesc, const uin
     return nm;
 }
 
+// same arguments and result as refcut_search_by_bow_kf (oracle/ref_cut_tu.cpp)
+int gpuhost_search_by_bow_kf(const float* angle1, const uint8_t* desc1, const uint8_t* state1, int n1, const int32_t* node1, const int32_t* start1,
+                             const int32_t* feat1, int nodes1, int feats1, const float* angle2, const uint8_t* desc2, const uint8_t* state2, int n2,
+                             const int32_t* node2, const int32_t* start2, const int32_t* feat2, int nodes2, int feats2, float nnratio, int checkOri,
+                             int32_t* matchOf) {
+    KeyFrame k1, k2;
+    std::vector<MapPoint> mps1(n1), mps2(n2);
+    k1.mvKeysUn.resize(n1); k1.mvpMapPoints.assign(n1, nullptr);
+    for (int i = 0; i < n1; i++) { k1.mvKeysUn[i].angle = angle1[i]; if (state1[i]) { mps1[i].mbBad = state1[i] == 2; k1.mvpMapPoints[i] = &mps1[i]; } }
+    k1.mDescriptors = to_descriptors(desc1, n1);
+    for (int g = 0; g < nodes1; g++)
+        for (int f = start1[g]; f < (g + 1 < nodes1 ? start1[g + 1] : feats1); f++) k1.mFeatVec[(unsigned)node1[g]].push_back((unsigned)feat1[f]);
+    k2.mvKeysUn.resize(n2); k2.mvpMapPoints.assign(n2, nullptr);
+    for (int i = 0; i < n2; i++) { k2.mvKeysUn[i].angle = angle2[i]; if (state2[i]) { mps2[i].mbBad = state2[i] == 2; k2.mvpMapPoints[i] = &mps2[i]; } }
+    k2.mDescriptors = to_descriptors(desc2, n2);
+    for (int g = 0; g < nodes2; g++)
+        for (int f = start2[g]; f < (g + 1 < nodes2 ? start2[g + 1] : feats2); f++) k2.mFeatVec[(unsigned)node2[g]].push_back((unsigned)feat2[f]);
+    std::vector<MapPoint*> matches;
+    const int nm = ORBmatcherGPU::Instance().SearchByBoW(&k1, &k2, matches, nnratio, checkOri != 0);
+    for (int i = 0; i < n1; i++) matchOf[i] = matches[i] ? (int)(matches[i] - mps2.data()) : -1;
+    return nm;
+}
+
 }  // extern "C"

@@ -46,6 +46,8 @@ def host():
         [C.c_void_p] * 7 + [C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p]
     lib.gpuhost_search_by_projection_reloc.restype = C.c_int
     lib.gpuhost_search_by_projection_reloc.argtypes = ref.RELOC_ARGTYPES
+    lib.gpuhost_search_by_bow_kf.restype = C.c_int
+    lib.gpuhost_search_by_bow_kf.argtypes = ref.BOW_KF_ARGTYPES
     lib.gpuhost_search_by_bow.restype = C.c_int
     lib.gpuhost_search_by_bow.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_int] + [C.c_void_p] * 2 + [C.c_int] + \
         [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]
@@ -95,6 +97,30 @@ def test_search_by_bow_equals_reference(host, levelsup, nnratio, check):
                                     _p(ffe), len(fn), len(ffe), nnratio, int(check), _p(match))
     assert nm == nm_ref and np.array_equal(match, match_ref)
     assert nm_ref > 100 and host.gpuhost_rescans() > r0      # matches and in-call collisions both occurred
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref (the reference's own object code) is not built")
+@pytest.mark.parametrize("levelsup,nnratio,check,seed", [(2, 0.8, True, 17), (3, 0.75, True, 18), (2, 0.9, False, 19)])
+def test_search_by_bow_between_key_frames_equals_reference(host, levelsup, nnratio, check, seed):
+    """ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) (ORBmatcher.cc:765-905, LoopClosing.cc:1680): both sides need good map points, a key
+    point of the second key frame is matched at most once"""
+    sc = bow_scene(seed=seed, levelsup=levelsup)
+    rng = np.random.default_rng(seed)
+    st1 = np.where(sc["has_point"] > 0, rng.choice([1, 2], sc["nk"], p=[0.9, 0.1]), 0).astype(np.uint8)
+    st2 = rng.choice([0, 1, 2], sc["nf"], p=[0.2, 0.7, 0.1]).astype(np.uint8)
+    nm_ref, match_ref = ref.search_by_bow_kf(sc["ang_k"], sc["dk"], st1, sc["fv_k"], sc["ang_f"], sc["df"], st2, sc["fv_f"], nnratio, check)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    a1, d1, a2, d2 = f32(sc["ang_k"]), u8(sc["dk"]), f32(sc["ang_f"]), u8(sc["df"])
+    n1_, s1_, f1_ = (i32(a) for a in sc["fv_k"])
+    n2_, s2_, f2_ = (i32(a) for a in sc["fv_f"])
+    match = np.full(len(a1), -1, np.int32)
+    r0 = host.gpuhost_rescans()
+    nm = host.gpuhost_search_by_bow_kf(_p(a1), _p(d1), _p(st1), len(a1), _p(n1_), _p(s1_), _p(f1_), len(n1_), len(f1_), _p(a2), _p(d2), _p(st2), len(a2),
+                                       _p(n2_), _p(s2_), _p(f2_), len(n2_), len(f2_), nnratio, int(check), _p(match))
+    assert nm == nm_ref and np.array_equal(match, match_ref)
+    assert nm_ref > 60 and host.gpuhost_rescans() > r0
 
 
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref (the reference's own object code) is not built")
