@@ -22,6 +22,11 @@
 //   ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)   ORBmatcher.cc:223-421 (over the vendored DBoW2::FeatureVector)
 //   ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono)   ORBmatcher.cc:1676-1887 (the
 //       motion-model call of Tracking::TrackWithMotionModel, Tracking.cc:2925/:2933; Eigen / Sophus from cvshim/mini_geom.hpp)
+//   ORBmatcher::SearchForInitialization           ORBmatcher.cc:648-766 (Tracking::MonocularInitialization, Tracking.cc:2527)
+//   ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist)   ORBmatcher.cc:1889-2010
+//       (Tracking::Relocalization, Tracking.cc:3765/:3779) with MapPoint::PredictScale(float, Frame*) and GetMin/MaxDistanceInvariance,
+//       MapPoint.cc:502-546
+//   ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>&)   ORBmatcher.cc:765-905 (LoopClosing.cc:1680)
 #include <algorithm>
 #include <climits>
 #include <cmath>
