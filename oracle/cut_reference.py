@@ -36,6 +36,11 @@ PIECES = [
      r"^\s*int ORBmatcher::SearchByBoW\(KeyFrame \*pKF1, KeyFrame \*pKF2, vector<MapPoint \*> &vpMatches12\)", "function"),
     ("ORBmatcher_SearchByProjection_reloc", "src/ORBmatcher.cc",
      r"^\s*int ORBmatcher::SearchByProjection\(Frame &CurrentFrame, KeyFrame \*pKF, const set<MapPoint\*> &sAlreadyFound, const float th , const int ORBdist\)", "function"),
+    ("ORBmatcher_SearchByProjection_sim3", "src/ORBmatcher.cc",
+     r"^\s*int ORBmatcher::SearchByProjection\(KeyFrame\* pKF, Sophus::Sim3f &Scw, const vector<MapPoint\*> &vpPoints,\s*$", "function"),
+    ("KeyFrame_GetFeaturesInArea", "src/KeyFrame.cc", r"^vector<size_t> KeyFrame::GetFeaturesInArea\(", "function"),
+    ("KeyFrame_IsInImage", "src/KeyFrame.cc", r"^bool KeyFrame::IsInImage\(", "function"),
+    ("MapPoint_PredictScale_KeyFrame", "src/MapPoint.cc", r"^int MapPoint::PredictScale\(const float &currentDist, KeyFrame\* pKF\)", "function"),
     ("MapPoint_PredictScale_Frame", "src/MapPoint.cc", r"^int MapPoint::PredictScale\(const float &currentDist, Frame\* pF\)", "function"),
     ("MapPoint_GetMinDistanceInvariance", "src/MapPoint.cc", r"^float MapPoint::GetMinDistanceInvariance\(\)", "function"),
     ("MapPoint_GetMaxDistanceInvariance", "src/MapPoint.cc", r"^float MapPoint::GetMaxDistanceInvariance\(\)", "function"),

@@ -1,6 +1,6 @@
 // ORACLE / TEST INFRASTRUCTURE (not product code): the handful of Eigen / Sophus declarations that the motion-model
 // ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) and the relocalisation overload (reference orb_slam3/src/ORBmatcher.cc:1676-2010) touch --
-// Eigen::Vector2f / Vector3f with operator()(int), operator-, norm(), Sophus::SE3f with inverse(), translation() and operator*(Vector3f).  Neither
+// Eigen::Vector2f / Vector3f with operator()(int), operator-, operator/, norm(), dot(), Matrix3f, Sophus::Sim3f with rotationMatrix() / translation() / scale(), Sophus::SE3f with inverse(), translation() and operator*(Vector3f).  Neither
 // library exists in this image.  The geometry is host code on both sides of the comparison (the reference's cut-out body in
 // oracle/_ref and the GPU-backed replacement in tests/host/ are compiled against THIS header with the same flags), so the floats
 // they feed into the candidate scan are identical; what is compared is the scan and its decisions.
@@ -22,7 +22,14 @@ struct Vector3f {
     float& operator()(int i) { return v[i]; }
     float operator()(int i) const { return v[i]; }
     Vector3f operator-(const Vector3f& o) const { return Vector3f(v[0] - o.v[0], v[1] - o.v[1], v[2] - o.v[2]); }
+    Vector3f operator/(float d) const { return Vector3f(v[0] / d, v[1] / d, v[2] / d); }
     float norm() const { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+    float dot(const Vector3f& o) const { return v[0] * o.v[0] + v[1] * o.v[1] + v[2] * o.v[2]; }
+};
+struct Matrix3f {               // row major
+    float m[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    float& operator()(int r, int c) { return m[3 * r + c]; }
+    float operator()(int r, int c) const { return m[3 * r + c]; }
 };
 }  // namespace Eigen
 
@@ -34,6 +41,7 @@ public:
     T t[3] = {0, 0, 0};
     SE3() {}
     SE3(const T* r9, const T* t3) { for (int i = 0; i < 9; i++) R[i] = r9[i]; for (int i = 0; i < 3; i++) t[i] = t3[i]; }
+    SE3(const Eigen::Matrix3f& r, const Eigen::Vector3f& tv) { for (int i = 0; i < 9; i++) R[i] = r.m[i]; for (int i = 0; i < 3; i++) t[i] = tv(i); }
     SE3 inverse() const {       // (R^T, -R^T t)
         SE3 o;
         for (int i = 0; i < 3; i++)
@@ -48,6 +56,17 @@ public:
     }
 };
 typedef SE3<float> SE3f;
+template <class T>
+class Sim3 {                    // x -> s R x + t: the three accessors the Sim3 projection search uses (ORBmatcher.cc:435)
+public:
+    Eigen::Matrix3f R;
+    Eigen::Vector3f t;
+    T s = 1;
+    Eigen::Matrix3f rotationMatrix() const { return R; }
+    Eigen::Vector3f translation() const { return t; }
+    T scale() const { return s; }
+};
+typedef Sim3<float> Sim3f;
 }  // namespace Sophus
 
 namespace ORB_SLAM3 {

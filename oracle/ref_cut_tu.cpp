@@ -27,6 +27,9 @@
 //       (Tracking::Relocalization, Tracking.cc:3765/:3779) with MapPoint::PredictScale(float, Frame*) and GetMin/MaxDistanceInvariance,
 //       MapPoint.cc:502-546
 //   ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>&)   ORBmatcher.cc:765-905 (LoopClosing.cc:1680)
+//   ORBmatcher::SearchByProjection(KeyFrame* pKF, Sophus::Sim3f& Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched, th,
+//       ratioHamming)   ORBmatcher.cc:427-530 (LoopClosing.cc:1795/:1982) with KeyFrame::GetFeaturesInArea / IsInImage (KeyFrame.cc:707-756)
+//       and MapPoint::PredictScale(float, KeyFrame*) (MapPoint.cc:514-529)
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -65,6 +68,8 @@ public:
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
     int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist);
+    int SearchByProjection(KeyFrame* pKF, Sophus::Sim3f& Scw, const std::vector<MapPoint*>& vpPoints, std::vector<MapPoint*>& vpMatched, int th,
+                           float ratioHamming = 1.0);
     static const int TH_LOW;
     static const int TH_HIGH;
     static const int HISTO_LENGTH;
@@ -74,10 +79,21 @@ public:
     bool mbCheckOrientation;
 };
 
-class KeyFrame {                // KeyFrame.h:256, :380-522: the members the cut functions read
+class KeyFrame {                // KeyFrame.h:256, :324-334, :380-522: the members the cut functions read (the const members as plain ones)
 public:
     bool isBad() { return mbBad; }
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const bool bRight = false) const;
+    bool IsInImage(const float& x, const float& y) const;
+    int N = 0;
+    int mnGridCols = FRAME_GRID_COLS, mnGridRows = FRAME_GRID_ROWS;
+    float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+    int mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;
+    std::vector<std::vector<std::vector<size_t> > > mGrid, mGridRight;
+    float fx = 0, fy = 0, cx = 0, cy = 0;
+    std::vector<float> mvScaleFactors;
+    int mnScaleLevels = 0;
+    float mfLogScaleFactor = 0;
     std::vector<cv::KeyPoint> mvKeys, mvKeysUn, mvKeysRight;
     cv::Mat mDescriptors;
     DBoW2::FeatureVector mFeatVec;
@@ -91,6 +107,9 @@ class MapPoint {                // MapPoint.h:114-207: the members the cut funct
 public:
     void ComputeDistinctiveDescriptors();
     int PredictScale(const float& currentDist, Frame* pF);
+    int PredictScale(const float& currentDist, KeyFrame* pKF);
+    Eigen::Vector3f GetNormal() { return mNormalVector; }
+    Eigen::Vector3f mNormalVector;
     float GetMinDistanceInvariance();
     float GetMaxDistanceInvariance();
     float mfMinDistance = 0, mfMaxDistance = 0;
@@ -159,6 +178,10 @@ float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX
 #include "cut/ORBmatcher_SearchByProjection_motion.inc"
 #include "cut/ORBmatcher_SearchForInitialization.inc"
 #include "cut/ORBmatcher_SearchByProjection_reloc.inc"
+#include "cut/ORBmatcher_SearchByProjection_sim3.inc"
+#include "cut/KeyFrame_GetFeaturesInArea.inc"
+#include "cut/KeyFrame_IsInImage.inc"
+#include "cut/MapPoint_PredictScale_KeyFrame.inc"
 #include "cut/ORBmatcher_ComputeThreeMaxima.inc"
 #include "cut/ORBmatcher_DescriptorDistance.inc"
 #include "cut/Frame_AssignFeaturesToGrid.inc"
@@ -451,6 +474,66 @@ int refcut_search_by_projection_reloc(const float* kps, const int32_t* oct, cons
         matchOf[i] = (p && p != &held) ? (int)(p - mps.data()) : -1;
     }
     delete Cf;
+    return nmatches;
+}
+
+// LoopClosing's Sim3 projection search (LoopClosing.cc:1795 / :1982): ORBmatcher(0.9, true).SearchByProjection(pKF, Scw, vpPoints, vpMatched, th,
+// ratioHamming) (ORBmatcher.cc:427-530).  Key frame: undistorted key points (x, y), octaves, descriptors, bounds / grid fp = {mnMinX, mnMaxX,
+// mnMinY, mnMaxY (integers in KeyFrame.h), gridWInv, gridHInv, 0, 0, mnScaleLevels, mfLogScaleFactor}, scale factors, pinhole cam4; held[i] != 0:
+// key point i is matched already (vpMatched[i] non-null, a map point that is not among vpPoints).  Sim3 = {R (9), t (3), s}.  Map points: state
+// (1 good / 2 bad), world position, normal, descriptor, mfMinDistance, mfMaxDistance.  -> matchOf[i] = map point that key point i received in
+// this call (-1 otherwise); returns nmatches.
+int refcut_search_by_projection_sim3(const float* kps, const int32_t* oct, const uint8_t* desc, int n, const float* fp, const uint8_t* held,
+                                     const float* scaleFactors, int nlevels, const float* sim3, const float* cam4, int nP, const uint8_t* pState,
+                                     const float* pPos, const float* pNormal, const uint8_t* pDesc, const float* pMinDist, const float* pMaxDist, int th,
+                                     float ratioHamming, int32_t* matchOf) {
+    using namespace ORB_SLAM3;
+    KeyFrame kf;
+    GeometricCamera cam;
+    cam.fx = cam4[0]; cam.fy = cam4[1]; cam.cx = cam4[2]; cam.cy = cam4[3];
+    kf.fx = cam4[0]; kf.fy = cam4[1]; kf.cx = cam4[2]; kf.cy = cam4[3];
+    kf.mpCamera = &cam;
+    kf.N = n; kf.NLeft = -1;
+    kf.mnMinX = (int)fp[0]; kf.mnMaxX = (int)fp[1]; kf.mnMinY = (int)fp[2]; kf.mnMaxY = (int)fp[3];
+    kf.mfGridElementWidthInv = fp[4]; kf.mfGridElementHeightInv = fp[5];
+    kf.mnScaleLevels = (int)fp[8]; kf.mfLogScaleFactor = fp[9];
+    kf.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    kf.mvKeysUn.resize(n);
+    for (int i = 0; i < n; i++) { kf.mvKeysUn[i].pt.x = kps[2 * i]; kf.mvKeysUn[i].pt.y = kps[2 * i + 1]; kf.mvKeysUn[i].octave = oct[i]; }
+    kf.mDescriptors = to_descriptors(desc, n);
+    {   // the grid a KeyFrame copies from its Frame (KeyFrame.cc:60-71 <- Frame::AssignFeaturesToGrid): the reference's own assignment
+        Frame* F = new Frame();
+        Frame::mnMinX = fp[0]; Frame::mnMaxX = fp[1]; Frame::mnMinY = fp[2]; Frame::mnMaxY = fp[3];
+        Frame::mfGridElementWidthInv = fp[4]; Frame::mfGridElementHeightInv = fp[5];
+        F->N = n; F->Nleft = -1; F->mvKeysUn = kf.mvKeysUn;
+        F->AssignFeaturesToGrid();
+        kf.mGrid.resize(kf.mnGridCols);
+        for (int i = 0; i < kf.mnGridCols; i++) {
+            kf.mGrid[i].resize(kf.mnGridRows);
+            for (int j = 0; j < kf.mnGridRows; j++) kf.mGrid[i][j] = F->mGrid[i][j];
+        }
+        delete F;
+    }
+    MapPoint other;
+    std::vector<MapPoint*> vpMatched(n, nullptr);
+    for (int i = 0; i < n; i++) if (held && held[i]) vpMatched[i] = &other;
+    std::vector<MapPoint> mps(nP);
+    std::vector<MapPoint*> vpPoints(nP);
+    for (int j = 0; j < nP; j++) {
+        mps[j].mbBad = pState[j] == 2;
+        mps[j].mWorldPos = Eigen::Vector3f(pPos[3 * j], pPos[3 * j + 1], pPos[3 * j + 2]);
+        mps[j].mNormalVector = Eigen::Vector3f(pNormal[3 * j], pNormal[3 * j + 1], pNormal[3 * j + 2]);
+        mps[j].mDescriptor = to_descriptors(pDesc + (size_t)32 * j, 1);
+        mps[j].mfMinDistance = pMinDist[j]; mps[j].mfMaxDistance = pMaxDist[j];
+        vpPoints[j] = &mps[j];
+    }
+    Sophus::Sim3f Scw;
+    for (int i = 0; i < 9; i++) Scw.R.m[i] = sim3[i];
+    Scw.t = Eigen::Vector3f(sim3[9], sim3[10], sim3[11]);
+    Scw.s = sim3[12];
+    ORBmatcher matcher(0.9f, true);
+    const int nmatches = matcher.SearchByProjection(&kf, Scw, vpPoints, vpMatched, th, ratioHamming);
+    for (int i = 0; i < n; i++) matchOf[i] = (vpMatched[i] && vpMatched[i] != &other) ? (int)(vpMatched[i] - mps.data()) : -1;
     return nmatches;
 }
 

@@ -10,6 +10,8 @@
 //   SearchByBoW(KeyFrame* pKF, Frame& F, vpMapPointMatches)                                              reference ORBmatcher.cc:223-421
 //       (Tracking::TrackReferenceKeyFrame, Tracking.cc:2769; Tracking::Relocalization, :3687)
 //
+//   SearchByProjection(KeyFrame* pKF, Sophus::Sim3f& Scw, vpPoints, vpMatched, th, ratioHamming)         reference ORBmatcher.cc:427-530
+//       (LoopClosing.cc:1795 / :1982)
 //   SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vpMatches12)                                             reference ORBmatcher.cc:765-905
 //       (LoopClosing::DetectCommonRegionsFromBoW, LoopClosing.cc:1680 -- the one call here that is not made by the Tracking thread)
 //
@@ -536,6 +538,94 @@ int ORBmatcherGPU::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const 
                     nmatches--;
                 }
             }
+        }
+    }
+    return nmatches;
+}
+
+// ORBmatcher::SearchByProjection(KeyFrame* pKF, Sophus::Sim3f& Scw, vpPoints, vpMatched, th, ratioHamming) (ORBmatcher.cc:427-530;
+// LoopClosing.cc:1795 / :1982): map points of a loop / merge candidate projected into a key frame with a Sim3.  The scan side is a key
+// frame here: its undistorted key points, octaves and descriptors go up with the call (key frames are not cached: a loop candidate is
+// scanned once or twice); KeyFrame::GetFeaturesInArea (KeyFrame.cc:707-751) has the grid walk of Frame::GetFeaturesInArea without the level
+// test, which the matcher applies itself (:508-511) -- the same filter as a level window [n - 1, n] of orbb_search_area_topk.  Key points
+// that are matched already (vpMatched non-null, :505) are masked, on the live vector.
+int ORBmatcherGPU::SearchByProjectionSim3(KeyFrame* pKF, const float* R9, const float* t3, float scale, const std::vector<MapPoint*>& vpPoints,
+                                          std::vector<MapPoint*>& vpMatched, int th, float ratioHamming) {
+    if (pKF->NLeft != -1) throw std::logic_error("ORBmatcherGPU::SearchByProjection: fisheye-stereo key frames keep the reference's host path");
+    Impl& s = Scratch();
+    Eigen::Matrix3f Rm;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) Rm(i, j) = R9[3 * i + j];
+    Eigen::Vector3f tv(t3[0], t3[1], t3[2]);
+    Sophus::SE3f Tcw = Sophus::SE3f(Rm, tv / scale);                              // :435-436: SE3f(Scw.rotationMatrix(), Scw.translation() / Scw.scale())
+    Eigen::Vector3f Ow = Tcw.inverse().translation();
+    std::set<MapPoint*> spAlreadyFound(vpMatched.begin(), vpMatched.end());
+    spAlreadyFound.erase(static_cast<MapPoint*>(NULL));
+    s.q.clear(); s.qlev.clear(); s.qdesc.clear(); s.src.clear();
+    for (int iMP = 0, iendMP = (int)vpPoints.size(); iMP < iendMP; iMP++) {       // :445-490: project, range, viewing angle, predicted level, window
+        MapPoint* pMP = vpPoints[iMP];
+        if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;
+        Eigen::Vector3f p3Dw = pMP->GetWorldPos();
+        Eigen::Vector3f p3Dc = Tcw * p3Dw;
+        if (p3Dc(2) < 0.0) continue;
+        const Eigen::Vector2f uv = pKF->mpCamera->project(p3Dc);
+        if (!pKF->IsInImage(uv(0), uv(1))) continue;
+        const float maxDistance = pMP->GetMaxDistanceInvariance();
+        const float minDistance = pMP->GetMinDistanceInvariance();
+        Eigen::Vector3f PO = p3Dw - Ow;
+        const float dist = PO.norm();
+        if (dist < minDistance || dist > maxDistance) continue;
+        Eigen::Vector3f Pn = pMP->GetNormal();
+        if (PO.dot(Pn) < 0.5 * dist) continue;
+        int nPredictedLevel = pMP->PredictScale(dist, pKF);
+        const float radius = th * pKF->mvScaleFactors[nPredictedLevel];
+        const float q4[4] = {uv(0), uv(1), radius, -1.0f};
+        s.q.insert(s.q.end(), q4, q4 + 4);
+        s.qlev.push_back(nPredictedLevel - 1); s.qlev.push_back(nPredictedLevel);
+        const cv::Mat d = pMP->GetDescriptor();
+        s.qdesc.insert(s.qdesc.end(), d.ptr<uchar>(), d.ptr<uchar>() + 32);
+        s.src.push_back(iMP);
+    }
+    const int nq = (int)s.src.size(), n = (int)pKF->mvKeysUn.size();
+    if (nq == 0) return 0;
+    if (!pKF->mDescriptors.isContinuous()) throw std::runtime_error("KeyFrame::mDescriptors must be continuous");
+    s.xy.resize((size_t)n * 2);
+    s.oct.resize(n);
+    for (int i = 0; i < n; i++) { s.xy[2 * i] = pKF->mvKeysUn[i].pt.x; s.xy[2 * i + 1] = pKF->mvKeysUn[i].pt.y; s.oct[i] = pKF->mvKeysUn[i].octave; }
+    orbb_frame_view view;
+    view.kps_xy = s.xy.data(); view.kps_stride = 8; view.octaves = s.oct.data(); view.oct_stride = 4;
+    view.desc = pKF->mDescriptors.ptr<uchar>(); view.u_right = nullptr; view.n = n; view.on_device = 0;
+    const float grid4[4] = {(float)pKF->mnMinX, (float)pKF->mnMinY, pKF->mfGridElementWidthInv, pKF->mfGridElementHeightInv};
+    auto scan = [&](int first, int count, int k, int32_t* out) {
+        s.skip.assign(n, 0);
+        for (int i = 0; i < n; i++) s.skip[i] = vpMatched[i] != NULL;
+        if (orbb_search_area_topk(mpMatcher, &view, grid4, &s.q[4 * (size_t)first], &s.qlev[2 * (size_t)first], &s.qdesc[32 * (size_t)first], count,
+                                  s.skip.data(), 256, k, out) != ORBB_OK)
+            throw std::runtime_error(std::string("orbb_search_area_topk failed: ") + orbb_matcher_last_error(mpMatcher));
+    };
+    s.out.assign((size_t)nq * kTopK * 2, -1);
+    scan(0, nq, kTopK, s.out.data());
+    int nmatches = 0;
+    for (int j = 0; j < nq; j++) {                                                // :499-526, in the order of vpPoints
+        const int32_t* list = &s.out[(size_t)j * kTopK * 2];
+        int bestDist = 256, bestIdx = -1, valid = 0;
+        for (int t = 0; t < kTopK; t++) {
+            const int idx = list[2 * t + 1];
+            if (idx < 0) break;
+            valid++;
+            if (vpMatched[idx]) continue;
+            bestDist = list[2 * t]; bestIdx = idx;
+            break;
+        }
+        if (bestIdx < 0 && valid == kTopK) {                                      // all four were matched meanwhile: this point again, with the live mask
+            int32_t o[2] = {256, -1};
+            scan(j, 1, 1, o);
+            bestDist = o[0]; bestIdx = o[1];
+            mnRescans++;
+        }
+        if (bestIdx >= 0 && bestDist <= TH_LOW * ratioHamming) {
+            vpMatched[bestIdx] = vpPoints[s.src[j]];
+            nmatches++;
         }
     }
     return nmatches;

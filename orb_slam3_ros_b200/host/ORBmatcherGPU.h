@@ -52,6 +52,22 @@ public:
     // ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist)   ORBmatcher.cc:1889-2010
     int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist,
                            const bool checkOrientation);
+    // ORBmatcher::SearchByProjection(KeyFrame* pKF, Sophus::Sim3f& Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched, th, ratioHamming)
+    //                                                                                                      ORBmatcher.cc:427-530
+    // (a template on the Sim3 type so that this header needs no Sophus declaration: the transform crosses as nine + three + one floats)
+    template <class Sim3T>
+    int SearchByProjection(KeyFrame* pKF, Sim3T& Scw, const std::vector<MapPoint*>& vpPoints, std::vector<MapPoint*>& vpMatched, int th, float ratioHamming) {
+        float R[9], t[3];
+        const auto Rm = Scw.rotationMatrix();
+        const auto tv = Scw.translation();
+        for (int i = 0; i < 3; i++) {
+            t[i] = tv(i);
+            for (int j = 0; j < 3; j++) R[3 * i + j] = Rm(i, j);
+        }
+        return SearchByProjectionSim3(pKF, R, t, Scw.scale(), vpPoints, vpMatched, th, ratioHamming);
+    }
+    int SearchByProjectionSim3(KeyFrame* pKF, const float* R9, const float* t3, float scale, const std::vector<MapPoint*>& vpPoints,
+                               std::vector<MapPoint*>& vpMatched, int th, float ratioHamming);
     // ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches)             ORBmatcher.cc:223-421
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches, const float nnratio, const bool checkOrientation);
     // ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12)              ORBmatcher.cc:765-905

@@ -23,6 +23,7 @@ class FeatureVector : public std::map<unsigned int, std::vector<unsigned int> > 
 namespace ORB_SLAM3 {
 
 class Frame;
+class KeyFrame;
 
 class MapPoint {
 public:
@@ -30,6 +31,9 @@ public:
     float GetMinDistanceInvariance() { return 0.8f * mfMinDistance; }
     float GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; }
     inline int PredictScale(const float& currentDist, Frame* pF);
+    inline int PredictScale(const float& currentDist, KeyFrame* pKF);
+    Eigen::Vector3f GetNormal() { return mNormalVector; }
+    Eigen::Vector3f mNormalVector;
     float mfMinDistance = 0, mfMaxDistance = 0;
     int Observations() { return nObs; }
     bool isBad() { return mbBad; }

@@ -13,6 +13,13 @@ class KeyFrame {
 public:
     bool isBad() { return mbBad; }
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+    bool IsInImage(const float& x, const float& y) const { return x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY; }      // KeyFrame.cc:753-756
+    int mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;      // (integers in KeyFrame.h)
+    float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+    float fx = 0, fy = 0, cx = 0, cy = 0;
+    std::vector<float> mvScaleFactors;
+    int mnScaleLevels = 0;
+    float mfLogScaleFactor = 0;
     std::vector<cv::KeyPoint> mvKeys, mvKeysUn, mvKeysRight;
     cv::Mat mDescriptors;
     DBoW2::FeatureVector mFeatVec;
@@ -21,5 +28,13 @@ public:
     int NLeft = -1, NRight = -1;
     bool mbBad = false;
 };
+
+inline int MapPoint::PredictScale(const float& currentDist, KeyFrame* pKF) {      // MapPoint.cc:514-529
+    const float ratio = mfMaxDistance / currentDist;
+    int nScale = std::ceil(std::log(ratio) / pKF->mfLogScaleFactor);
+    if (nScale < 0) nScale = 0;
+    else if (nScale >= pKF->mnScaleLevels) nScale = pKF->mnScaleLevels - 1;
+    return nScale;
+}
 
 }  // namespace ORB_SLAM3

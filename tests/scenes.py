@@ -146,3 +146,26 @@ def reloc_scene(seed=5, th=10.0):
              scale_factors=sf, Tcw=cur["Tcw"], cam4=cur["cam4"])
     kf = dict(angles=last["angles"], state=state, pos=last["pos"], desc=last["desc"], min_dist=min_dist, max_dist=max_dist)
     return c, kf
+
+
+def sim3_scene(seed=5, scale=1.07):
+    """LoopClosing: the map points of a loop candidate's neighbourhood projected into the current key frame with a Sim3 (scale != 1).  Built on
+    reloc_scene: the key frame is its current frame, the map points are its key-frame points expressed in a frame that is `scale` times larger;
+    some normals point away (viewing-angle test), some points are bad, some key points are matched already."""
+    cur, kf = reloc_scene(seed)
+    rng = np.random.default_rng(200 + seed)
+    m = len(kf["state"])
+    pos = (kf["pos"] * np.float32(scale)).astype(np.float32)                      # world = scale * camera-frame coordinates of the old scene
+    R, t = cur["Tcw"][:9].astype(np.float32), cur["Tcw"][9:].astype(np.float32)
+    # Scw = (s, R, t_s): the reference uses Tcw = (R, t_s / s).  With world = scale * old world, s = 1 / scale and t_s = t the camera-frame points are
+    # scale * the old ones: the same pixels, depths and distances scaled
+    sim3 = np.concatenate([R, t, np.float32([1.0 / scale])]).astype(np.float32)
+    normal = pos / np.linalg.norm(pos, axis=1, keepdims=True)                   # mean viewing direction: from the (old) camera towards the point
+    away = rng.random(m) < 0.15
+    normal[away] *= -1
+    state = np.where(kf["state"] == 2, 2, 1).astype(np.uint8)
+    k = dict(kps_xy=cur["kps_xy"], octaves=cur["octaves"], desc=cur["desc"], held=(rng.random(len(cur["octaves"])) < 0.3).astype(np.uint8),
+             fp=cur["fp"], scale_factors=cur["scale_factors"], cam4=cur["cam4"])
+    pts = dict(state=state, pos=pos, normal=normal.astype(np.float32), desc=kf["desc"], min_dist=(kf["min_dist"] * np.float32(scale)).astype(np.float32),
+               max_dist=(kf["max_dist"] * np.float32(scale)).astype(np.float32))
+    return k, pts, sim3

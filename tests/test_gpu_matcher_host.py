@@ -14,7 +14,7 @@ from oracle import port, ref
 from orb_slam3_ros_b200 import capi, synth
 from orb_slam3_ros_b200.extractor import ORBextractor
 from orb_slam3_ros_b200.matcher import ORBmatcher
-from scenes import bow_scene, init_scene, local_points_scene, motion_scene, reloc_scene
+from scenes import bow_scene, init_scene, local_points_scene, motion_scene, reloc_scene, sim3_scene
 
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
@@ -46,6 +46,8 @@ def host():
         [C.c_void_p] * 7 + [C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p]
     lib.gpuhost_search_by_projection_reloc.restype = C.c_int
     lib.gpuhost_search_by_projection_reloc.argtypes = ref.RELOC_ARGTYPES
+    lib.gpuhost_search_by_projection_sim3.restype = C.c_int
+    lib.gpuhost_search_by_projection_sim3.argtypes = ref.SIM3_ARGTYPES
     lib.gpuhost_search_by_bow_kf.restype = C.c_int
     lib.gpuhost_search_by_bow_kf.argtypes = ref.BOW_KF_ARGTYPES
     lib.gpuhost_search_by_bow.restype = C.c_int
@@ -97,6 +99,26 @@ def test_search_by_bow_equals_reference(host, levelsup, nnratio, check):
                                     _p(ffe), len(fn), len(ffe), nnratio, int(check), _p(match))
     assert nm == nm_ref and np.array_equal(match, match_ref)
     assert nm_ref > 100 and host.gpuhost_rescans() > r0      # matches and in-call collisions both occurred
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref (the reference's own object code) is not built")
+@pytest.mark.parametrize("seed,th,ratio", [(5, 5, 1.0), (5, 3, 1.5), (6, 8, 1.5)])
+def test_sim3_projection_search_equals_reference(host, seed, th, ratio):
+    """ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (ORBmatcher.cc:427-530; LoopClosing.cc:1795 / :1982) with
+    the reference's own KeyFrame::GetFeaturesInArea on the oracle side"""
+    k, pts, sim3 = sim3_scene(seed)
+    nm_ref, match_ref = ref.search_by_projection_sim3(k, pts, sim3, th, ratio)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    kx, o, d, held, fp, sf, cam = f32(k["kps_xy"]), i32(k["octaves"]), u8(k["desc"]), u8(k["held"]), f32(k["fp"]), f32(k["scale_factors"]), f32(k["cam4"])
+    ps, pp, pn, pd, pmin, pmax = u8(pts["state"]), f32(pts["pos"]), f32(pts["normal"]), u8(pts["desc"]), f32(pts["min_dist"]), f32(pts["max_dist"])
+    s3 = f32(sim3)
+    match = np.full(len(kx), -1, np.int32)
+    nm = host.gpuhost_search_by_projection_sim3(_p(kx), _p(o), _p(d), len(kx), _p(fp), _p(held), _p(sf), len(sf), _p(s3), _p(cam), len(ps), _p(ps), _p(pp),
+                                                _p(pn), _p(pd), _p(pmin), _p(pmax), th, ratio, _p(match))
+    assert nm == nm_ref and np.array_equal(match, match_ref)
+    assert nm_ref > 100
 
 
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref (the reference's own object code) is not built")
