@@ -354,13 +354,14 @@ RELOC_ARGTYPES = [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [
     [C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p]
 
 
-def search_by_projection_sim3(kf, pts, sim3, th, ratio_hamming):
+def search_by_projection_sim3(kf, pts, sim3, th, ratio_hamming, with_kfs=False):
     """ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (ORBmatcher.cc:427-530, reference text; LoopClosing.cc:1795 /
     :1982) with the reference's KeyFrame::GetFeaturesInArea / IsInImage and MapPoint::PredictScale(float, KeyFrame*).
       kf:  dict(kps_xy, octaves, desc, held [n] (matched already), fp = (mnMinX, mnMaxX, mnMinY, mnMaxY, gridWInv, gridHInv, 0, 0, mnScaleLevels,
            mfLogScaleFactor), scale_factors, cam4)
       pts: dict(state [m] (1 good / 2 bad), pos [m,3], normal [m,3], desc [m,32], min_dist [m], max_dist [m]);  sim3 [13] = R row-major, t, s
-    -> (nmatches, match_of[n]: map point received by each key point in this call, -1 otherwise)"""
+    -> (nmatches, match_of[n]: map point received by each key point in this call, -1 otherwise); with_kfs: the overload with vpPointsKFs /
+    vpMatchedKF (ORBmatcher.cc:532-646, LoopClosing.cc:1773; point j comes from key frame j % 7) -> (nmatches, match_of, match_kf)"""
     f32 = lambda a: np.ascontiguousarray(a, np.float32)
     u8 = lambda a: np.ascontiguousarray(a, np.uint8)
     i32 = lambda a: np.ascontiguousarray(a, np.int32)
@@ -368,12 +369,18 @@ def search_by_projection_sim3(kf, pts, sim3, th, ratio_hamming):
     ps, pp, pn, pd, pmin, pmax = u8(pts["state"]), f32(pts["pos"]).reshape(-1, 3), f32(pts["normal"]).reshape(-1, 3), u8(pts["desc"]), f32(pts["min_dist"]), f32(pts["max_dist"])
     s3 = f32(sim3)
     match_of = np.full(len(k), -1, np.int32)
+    args = (_ptr(k), _ptr(o), _ptr(d), len(k), _ptr(fp), _ptr(held), _ptr(sf), len(sf), _ptr(s3), _ptr(cam), len(ps), _ptr(ps), _ptr(pp), _ptr(pn), _ptr(pd),
+            _ptr(pmin), _ptr(pmax), int(th), float(ratio_hamming), _ptr(match_of))
+    if with_kfs:
+        match_kf = np.full(len(k), -1, np.int32)
+        fn = lib().refcut_search_by_projection_sim3_kfs
+        fn.restype = C.c_int
+        fn.argtypes = SIM3_ARGTYPES + [C.c_void_p]
+        return fn(*args, _ptr(match_kf)), match_of, match_kf
     fn = lib().refcut_search_by_projection_sim3
     fn.restype = C.c_int
     fn.argtypes = SIM3_ARGTYPES
-    nm = fn(_ptr(k), _ptr(o), _ptr(d), len(k), _ptr(fp), _ptr(held), _ptr(sf), len(sf), _ptr(s3), _ptr(cam), len(ps), _ptr(ps), _ptr(pp), _ptr(pn), _ptr(pd),
-            _ptr(pmin), _ptr(pmax), int(th), float(ratio_hamming), _ptr(match_of))
-    return nm, match_of
+    return fn(*args), match_of
 
 
 SIM3_ARGTYPES = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_float, C.c_void_p]

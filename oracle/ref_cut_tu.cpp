@@ -28,7 +28,7 @@
 //       MapPoint.cc:502-546
 //   ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>&)   ORBmatcher.cc:765-905 (LoopClosing.cc:1680)
 //   ORBmatcher::SearchByProjection(KeyFrame* pKF, Sophus::Sim3f& Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched, th,
-//       ratioHamming)   ORBmatcher.cc:427-530 (LoopClosing.cc:1795/:1982) with KeyFrame::GetFeaturesInArea / IsInImage (KeyFrame.cc:707-756)
+//       ratioHamming) and the overload with vpPointsKFs / vpMatchedKF   ORBmatcher.cc:427-646 (LoopClosing.cc:1773/:1795/:1982) with KeyFrame::GetFeaturesInArea / IsInImage (KeyFrame.cc:707-756)
 //       and MapPoint::PredictScale(float, KeyFrame*) (MapPoint.cc:514-529)
 #include <algorithm>
 #include <climits>
@@ -70,6 +70,8 @@ public:
     int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist);
     int SearchByProjection(KeyFrame* pKF, Sophus::Sim3f& Scw, const std::vector<MapPoint*>& vpPoints, std::vector<MapPoint*>& vpMatched, int th,
                            float ratioHamming = 1.0);
+    int SearchByProjection(KeyFrame* pKF, Sophus::Sim3<float>& Scw, const std::vector<MapPoint*>& vpPoints, const std::vector<KeyFrame*>& vpPointsKFs,
+                           std::vector<MapPoint*>& vpMatched, std::vector<KeyFrame*>& vpMatchedKF, int th, float ratioHamming = 1.0);
     static const int TH_LOW;
     static const int TH_HIGH;
     static const int HISTO_LENGTH;
@@ -179,6 +181,7 @@ float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX
 #include "cut/ORBmatcher_SearchForInitialization.inc"
 #include "cut/ORBmatcher_SearchByProjection_reloc.inc"
 #include "cut/ORBmatcher_SearchByProjection_sim3.inc"
+#include "cut/ORBmatcher_SearchByProjection_sim3_kfs.inc"
 #include "cut/KeyFrame_GetFeaturesInArea.inc"
 #include "cut/KeyFrame_IsInImage.inc"
 #include "cut/MapPoint_PredictScale_KeyFrame.inc"
@@ -483,10 +486,30 @@ int refcut_search_by_projection_reloc(const float* kps, const int32_t* oct, cons
 // key point i is matched already (vpMatched[i] non-null, a map point that is not among vpPoints).  Sim3 = {R (9), t (3), s}.  Map points: state
 // (1 good / 2 bad), world position, normal, descriptor, mfMinDistance, mfMaxDistance.  -> matchOf[i] = map point that key point i received in
 // this call (-1 otherwise); returns nmatches.
+static int sim3_search(int withKFs, const float* kps, const int32_t* oct, const uint8_t* desc, int n, const float* fp, const uint8_t* held,
+                       const float* scaleFactors, int nlevels, const float* sim3, const float* cam4, int nP, const uint8_t* pState, const float* pPos,
+                       const float* pNormal, const uint8_t* pDesc, const float* pMinDist, const float* pMaxDist, int th, float ratioHamming,
+                       int32_t* matchOf, int32_t* matchKF);
 int refcut_search_by_projection_sim3(const float* kps, const int32_t* oct, const uint8_t* desc, int n, const float* fp, const uint8_t* held,
                                      const float* scaleFactors, int nlevels, const float* sim3, const float* cam4, int nP, const uint8_t* pState,
                                      const float* pPos, const float* pNormal, const uint8_t* pDesc, const float* pMinDist, const float* pMaxDist, int th,
                                      float ratioHamming, int32_t* matchOf) {
+    return sim3_search(0, kps, oct, desc, n, fp, held, scaleFactors, nlevels, sim3, cam4, nP, pState, pPos, pNormal, pDesc, pMinDist, pMaxDist, th,
+                       ratioHamming, matchOf, nullptr);
+}
+// the overload that also reports the key frame each matched point came from (ORBmatcher.cc:532-646, LoopClosing.cc:1773): point j comes from
+// "key frame" j % 7 of a small pool; matchKF[i] = that index for the key points matched in this call (-1 otherwise)
+int refcut_search_by_projection_sim3_kfs(const float* kps, const int32_t* oct, const uint8_t* desc, int n, const float* fp, const uint8_t* held,
+                                         const float* scaleFactors, int nlevels, const float* sim3, const float* cam4, int nP, const uint8_t* pState,
+                                         const float* pPos, const float* pNormal, const uint8_t* pDesc, const float* pMinDist, const float* pMaxDist,
+                                         int th, float ratioHamming, int32_t* matchOf, int32_t* matchKF) {
+    return sim3_search(1, kps, oct, desc, n, fp, held, scaleFactors, nlevels, sim3, cam4, nP, pState, pPos, pNormal, pDesc, pMinDist, pMaxDist, th,
+                       ratioHamming, matchOf, matchKF);
+}
+static int sim3_search(int withKFs, const float* kps, const int32_t* oct, const uint8_t* desc, int n, const float* fp, const uint8_t* held,
+                       const float* scaleFactors, int nlevels, const float* sim3, const float* cam4, int nP, const uint8_t* pState, const float* pPos,
+                       const float* pNormal, const uint8_t* pDesc, const float* pMinDist, const float* pMaxDist, int th, float ratioHamming,
+                       int32_t* matchOf, int32_t* matchKF) {
     using namespace ORB_SLAM3;
     KeyFrame kf;
     GeometricCamera cam;
@@ -532,7 +555,16 @@ int refcut_search_by_projection_sim3(const float* kps, const int32_t* oct, const
     Scw.t = Eigen::Vector3f(sim3[9], sim3[10], sim3[11]);
     Scw.s = sim3[12];
     ORBmatcher matcher(0.9f, true);
-    const int nmatches = matcher.SearchByProjection(&kf, Scw, vpPoints, vpMatched, th, ratioHamming);
+    int nmatches;
+    if (withKFs) {
+        KeyFrame pool[7];
+        std::vector<KeyFrame*> vpPointsKFs(nP), vpMatchedKF(n, nullptr);
+        for (int j = 0; j < nP; j++) vpPointsKFs[j] = &pool[j % 7];
+        nmatches = matcher.SearchByProjection(&kf, Scw, vpPoints, vpPointsKFs, vpMatched, vpMatchedKF, th, ratioHamming);
+        for (int i = 0; i < n; i++) matchKF[i] = vpMatchedKF[i] ? (int)(vpMatchedKF[i] - pool) : -1;
+    } else {
+        nmatches = matcher.SearchByProjection(&kf, Scw, vpPoints, vpMatched, th, ratioHamming);
+    }
     for (int i = 0; i < n; i++) matchOf[i] = (vpMatched[i] && vpMatched[i] != &other) ? (int)(vpMatched[i] - mps.data()) : -1;
     return nmatches;
 }

@@ -544,13 +544,14 @@ int ORBmatcherGPU::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const 
 }
 
 // ORBmatcher::SearchByProjection(KeyFrame* pKF, Sophus::Sim3f& Scw, vpPoints, vpMatched, th, ratioHamming) (ORBmatcher.cc:427-530;
-// LoopClosing.cc:1795 / :1982): map points of a loop / merge candidate projected into a key frame with a Sim3.  The scan side is a key
+// LoopClosing.cc:1795 / :1982) and its sibling with vpPointsKFs / vpMatchedKF (:532-646, LoopClosing.cc:1773): map points of a loop / merge candidate projected into a key frame with a Sim3.  The scan side is a key
 // frame here: its undistorted key points, octaves and descriptors go up with the call (key frames are not cached: a loop candidate is
 // scanned once or twice); KeyFrame::GetFeaturesInArea (KeyFrame.cc:707-751) has the grid walk of Frame::GetFeaturesInArea without the level
 // test, which the matcher applies itself (:508-511) -- the same filter as a level window [n - 1, n] of orbb_search_area_topk.  Key points
 // that are matched already (vpMatched non-null, :505) are masked, on the live vector.
 int ORBmatcherGPU::SearchByProjectionSim3(KeyFrame* pKF, const float* R9, const float* t3, float scale, const std::vector<MapPoint*>& vpPoints,
-                                          std::vector<MapPoint*>& vpMatched, int th, float ratioHamming) {
+                                          std::vector<MapPoint*>& vpMatched, int th, float ratioHamming, const std::vector<KeyFrame*>* vpPointsKFs,
+                                          std::vector<KeyFrame*>* vpMatchedKF) {
     if (pKF->NLeft != -1) throw std::logic_error("ORBmatcherGPU::SearchByProjection: fisheye-stereo key frames keep the reference's host path");
     Impl& s = Scratch();
     Eigen::Matrix3f Rm;
@@ -568,8 +569,18 @@ int ORBmatcherGPU::SearchByProjectionSim3(KeyFrame* pKF, const float* R9, const 
         Eigen::Vector3f p3Dw = pMP->GetWorldPos();
         Eigen::Vector3f p3Dc = Tcw * p3Dw;
         if (p3Dc(2) < 0.0) continue;
-        const Eigen::Vector2f uv = pKF->mpCamera->project(p3Dc);
-        if (!pKF->IsInImage(uv(0), uv(1))) continue;
+        float u, v;
+        if (!vpPointsKFs) {                                                       // :463 the camera model's projection
+            const Eigen::Vector2f uv = pKF->mpCamera->project(p3Dc);
+            u = uv(0); v = uv(1);
+        } else {                                                                  // :573-578 the second overload projects by hand
+            const float invz = 1 / p3Dc(2);
+            const float x = p3Dc(0) * invz;
+            const float y = p3Dc(1) * invz;
+            u = pKF->fx * x + pKF->cx;
+            v = pKF->fy * y + pKF->cy;
+        }
+        if (!pKF->IsInImage(u, v)) continue;
         const float maxDistance = pMP->GetMaxDistanceInvariance();
         const float minDistance = pMP->GetMinDistanceInvariance();
         Eigen::Vector3f PO = p3Dw - Ow;
@@ -579,7 +590,7 @@ int ORBmatcherGPU::SearchByProjectionSim3(KeyFrame* pKF, const float* R9, const 
         if (PO.dot(Pn) < 0.5 * dist) continue;
         int nPredictedLevel = pMP->PredictScale(dist, pKF);
         const float radius = th * pKF->mvScaleFactors[nPredictedLevel];
-        const float q4[4] = {uv(0), uv(1), radius, -1.0f};
+        const float q4[4] = {u, v, radius, -1.0f};
         s.q.insert(s.q.end(), q4, q4 + 4);
         s.qlev.push_back(nPredictedLevel - 1); s.qlev.push_back(nPredictedLevel);
         const cv::Mat d = pMP->GetDescriptor();
@@ -625,6 +636,7 @@ int ORBmatcherGPU::SearchByProjectionSim3(KeyFrame* pKF, const float* R9, const 
         }
         if (bestIdx >= 0 && bestDist <= TH_LOW * ratioHamming) {
             vpMatched[bestIdx] = vpPoints[s.src[j]];
+            if (vpMatchedKF) (*vpMatchedKF)[bestIdx] = (*vpPointsKFs)[s.src[j]];
             nmatches++;
         }
     }

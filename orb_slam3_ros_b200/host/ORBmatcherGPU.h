@@ -64,10 +64,24 @@ public:
             t[i] = tv(i);
             for (int j = 0; j < 3; j++) R[3 * i + j] = Rm(i, j);
         }
-        return SearchByProjectionSim3(pKF, R, t, Scw.scale(), vpPoints, vpMatched, th, ratioHamming);
+        return SearchByProjectionSim3(pKF, R, t, Scw.scale(), vpPoints, vpMatched, th, ratioHamming, nullptr, nullptr);
+    }
+    // ... and the overload that also reports the key frame every matched point comes from              ORBmatcher.cc:532-646
+    template <class Sim3T>
+    int SearchByProjection(KeyFrame* pKF, Sim3T& Scw, const std::vector<MapPoint*>& vpPoints, const std::vector<KeyFrame*>& vpPointsKFs,
+                           std::vector<MapPoint*>& vpMatched, std::vector<KeyFrame*>& vpMatchedKF, int th, float ratioHamming) {
+        float R[9], t[3];
+        const auto Rm = Scw.rotationMatrix();
+        const auto tv = Scw.translation();
+        for (int i = 0; i < 3; i++) {
+            t[i] = tv(i);
+            for (int j = 0; j < 3; j++) R[3 * i + j] = Rm(i, j);
+        }
+        return SearchByProjectionSim3(pKF, R, t, Scw.scale(), vpPoints, vpMatched, th, ratioHamming, &vpPointsKFs, &vpMatchedKF);
     }
     int SearchByProjectionSim3(KeyFrame* pKF, const float* R9, const float* t3, float scale, const std::vector<MapPoint*>& vpPoints,
-                               std::vector<MapPoint*>& vpMatched, int th, float ratioHamming);
+                               std::vector<MapPoint*>& vpMatched, int th, float ratioHamming, const std::vector<KeyFrame*>* vpPointsKFs,
+                               std::vector<KeyFrame*>* vpMatchedKF);
     // ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches)             ORBmatcher.cc:223-421
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches, const float nnratio, const bool checkOrientation);
     // ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12)              ORBmatcher.cc:765-905

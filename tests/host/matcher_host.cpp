@@ -230,10 +230,29 @@ int gpuhost_search_by_bow(const float* kfAngle, const uint8_t* kfDesc, const uin
 }
 
 // same arguments and result as refcut_search_by_projection_sim3 (oracle/ref_cut_tu.cpp)
+static int gpuhost_sim3(int withKFs, const float* kps, const int32_t* oct, const uint8_t* desc, int n, const float* fp, const uint8_t* held,
+                        const float* scaleFactors, int nlevels, const float* sim3, const float* cam4, int nP, const uint8_t* pState, const float* pPos,
+                        const float* pNormal, const uint8_t* pDesc, const float* pMinDist, const float* pMaxDist, int th, float ratioHamming,
+                        int32_t* matchOf, int32_t* matchKF);
 int gpuhost_search_by_projection_sim3(const float* kps, const int32_t* oct, const uint8_t* desc, int n, const float* fp, const uint8_t* held,
                                       const float* scaleFactors, int nlevels, const float* sim3, const float* cam4, int nP, const uint8_t* pState,
                                       const float* pPos, const float* pNormal, const uint8_t* pDesc, const float* pMinDist, const float* pMaxDist, int th,
                                       float ratioHamming, int32_t* matchOf) {
+    return gpuhost_sim3(0, kps, oct, desc, n, fp, held, scaleFactors, nlevels, sim3, cam4, nP, pState, pPos, pNormal, pDesc, pMinDist, pMaxDist, th,
+                        ratioHamming, matchOf, nullptr);
+}
+// same arguments and result as refcut_search_by_projection_sim3_kfs
+int gpuhost_search_by_projection_sim3_kfs(const float* kps, const int32_t* oct, const uint8_t* desc, int n, const float* fp, const uint8_t* held,
+                                          const float* scaleFactors, int nlevels, const float* sim3, const float* cam4, int nP, const uint8_t* pState,
+                                          const float* pPos, const float* pNormal, const uint8_t* pDesc, const float* pMinDist, const float* pMaxDist,
+                                          int th, float ratioHamming, int32_t* matchOf, int32_t* matchKF) {
+    return gpuhost_sim3(1, kps, oct, desc, n, fp, held, scaleFactors, nlevels, sim3, cam4, nP, pState, pPos, pNormal, pDesc, pMinDist, pMaxDist, th,
+                        ratioHamming, matchOf, matchKF);
+}
+static int gpuhost_sim3(int withKFs, const float* kps, const int32_t* oct, const uint8_t* desc, int n, const float* fp, const uint8_t* held,
+                        const float* scaleFactors, int nlevels, const float* sim3, const float* cam4, int nP, const uint8_t* pState, const float* pPos,
+                        const float* pNormal, const uint8_t* pDesc, const float* pMinDist, const float* pMaxDist, int th, float ratioHamming,
+                        int32_t* matchOf, int32_t* matchKF) {
     KeyFrame kf;
     GeometricCamera cam;
     cam.fx = cam4[0]; cam.fy = cam4[1]; cam.cx = cam4[2]; cam.cy = cam4[3];
@@ -264,7 +283,16 @@ int gpuhost_search_by_projection_sim3(const float* kps, const int32_t* oct, cons
     for (int i = 0; i < 9; i++) Scw.R.m[i] = sim3[i];
     Scw.t = Eigen::Vector3f(sim3[9], sim3[10], sim3[11]);
     Scw.s = sim3[12];
-    const int nmatches = ORBmatcherGPU::Instance().SearchByProjection(&kf, Scw, vpPoints, vpMatched, th, ratioHamming);
+    int nmatches;
+    if (withKFs) {
+        KeyFrame pool[7];
+        std::vector<KeyFrame*> vpPointsKFs(nP), vpMatchedKF(n, nullptr);
+        for (int j = 0; j < nP; j++) vpPointsKFs[j] = &pool[j % 7];
+        nmatches = ORBmatcherGPU::Instance().SearchByProjection(&kf, Scw, vpPoints, vpPointsKFs, vpMatched, vpMatchedKF, th, ratioHamming);
+        for (int i = 0; i < n; i++) matchKF[i] = vpMatchedKF[i] ? (int)(vpMatchedKF[i] - pool) : -1;
+    } else {
+        nmatches = ORBmatcherGPU::Instance().SearchByProjection(&kf, Scw, vpPoints, vpMatched, th, ratioHamming);
+    }
     for (int i = 0; i < n; i++) matchOf[i] = (vpMatched[i] && vpMatched[i] != &other) ? (int)(vpMatched[i] - mps.data()) : -1;
     return nmatches;
 }

@@ -48,6 +48,8 @@ def host():
     lib.gpuhost_search_by_projection_reloc.argtypes = ref.RELOC_ARGTYPES
     lib.gpuhost_search_by_projection_sim3.restype = C.c_int
     lib.gpuhost_search_by_projection_sim3.argtypes = ref.SIM3_ARGTYPES
+    lib.gpuhost_search_by_projection_sim3_kfs.restype = C.c_int
+    lib.gpuhost_search_by_projection_sim3_kfs.argtypes = ref.SIM3_ARGTYPES + [C.c_void_p]
     lib.gpuhost_search_by_bow_kf.restype = C.c_int
     lib.gpuhost_search_by_bow_kf.argtypes = ref.BOW_KF_ARGTYPES
     lib.gpuhost_search_by_bow.restype = C.c_int
@@ -119,6 +121,13 @@ def test_sim3_projection_search_equals_reference(host, seed, th, ratio):
                                                 _p(pn), _p(pd), _p(pmin), _p(pmax), th, ratio, _p(match))
     assert nm == nm_ref and np.array_equal(match, match_ref)
     assert nm_ref > 100
+    # the overload that also returns the source key frames (ORBmatcher.cc:532-646, LoopClosing.cc:1773: th 8, ratio 1.5); it projects by hand
+    nm_ref2, match_ref2, kf_ref2 = ref.search_by_projection_sim3(k, pts, sim3, th, ratio, with_kfs=True)
+    match2, kf2 = np.full(len(kx), -1, np.int32), np.full(len(kx), -1, np.int32)
+    nm2 = host.gpuhost_search_by_projection_sim3_kfs(_p(kx), _p(o), _p(d), len(kx), _p(fp), _p(held), _p(sf), len(sf), _p(s3), _p(cam), len(ps), _p(ps), _p(pp),
+                                                     _p(pn), _p(pd), _p(pmin), _p(pmax), th, ratio, _p(match2), _p(kf2))
+    assert nm2 == nm_ref2 and np.array_equal(match2, match_ref2) and np.array_equal(kf2, kf_ref2)
+    assert np.array_equal(kf_ref2 >= 0, match_ref2 >= 0) and np.array_equal(kf_ref2[match_ref2 >= 0], match_ref2[match_ref2 >= 0] % 7)
 
 
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref (the reference's own object code) is not built")
