@@ -383,6 +383,26 @@ def search_by_projection_sim3(kf, pts, sim3, th, ratio_hamming, with_kfs=False):
     return fn(*args), match_of
 
 
+def fuse_sim3(kf, pts, sim3, th):
+    """ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (ORBmatcher.cc:1340-1455, reference text; LoopClosing::SearchAndFuse).  Arguments as
+    search_by_projection_sim3, kf["held"]: 0 none / 1 a good map point / 2 a bad one
+    -> (nFused, replace_of[m]: key point whose map point replaces point j, added_at[m]: key point that received point j as an observation)"""
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    k, o, d, held, fp, sf, cam = f32(kf["kps_xy"]).reshape(-1, 2), i32(kf["octaves"]), u8(kf["desc"]), u8(kf["held"]), f32(kf["fp"]), f32(kf["scale_factors"]), f32(kf["cam4"])
+    ps, pp, pn, pd, pmin, pmax = u8(pts["state"]), f32(pts["pos"]).reshape(-1, 3), f32(pts["normal"]).reshape(-1, 3), u8(pts["desc"]), f32(pts["min_dist"]), f32(pts["max_dist"])
+    s3 = f32(sim3)
+    rep, add = np.full(len(ps), -1, np.int32), np.full(len(ps), -1, np.int32)
+    fn = lib().refcut_fuse_sim3
+    fn.restype = C.c_int
+    fn.argtypes = FUSE_SIM3_ARGTYPES
+    nf = fn(_ptr(k), _ptr(o), _ptr(d), len(k), _ptr(fp), _ptr(held), _ptr(sf), len(sf), _ptr(s3), _ptr(cam), len(ps), _ptr(ps), _ptr(pp), _ptr(pn), _ptr(pd),
+            _ptr(pmin), _ptr(pmax), float(th), _ptr(rep), _ptr(add))
+    return nf, rep, add
+
+
+FUSE_SIM3_ARGTYPES = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_void_p, C.c_void_p]
 SIM3_ARGTYPES = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_float, C.c_void_p]
 
 

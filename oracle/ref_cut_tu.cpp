@@ -27,6 +27,9 @@
 //       (Tracking::Relocalization, Tracking.cc:3765/:3779) with MapPoint::PredictScale(float, Frame*) and GetMin/MaxDistanceInvariance,
 //       MapPoint.cc:502-546
 //   ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>&)   ORBmatcher.cc:765-905 (LoopClosing.cc:1680)
+//   ORBmatcher::Fuse(KeyFrame* pKF, Sophus::Sim3f& Scw, const vector<MapPoint*>& vpPoints, th, vpReplacePoint)   ORBmatcher.cc:1340-1455
+//       (LoopClosing::SearchAndFuse, LoopClosing.cc:3464/:3509; KeyFrame::GetMapPoints / GetMapPoint / AddMapPoint and MapPoint::AddObservation
+//       are plain stand-ins: map bookkeeping, not matching)
 //   ORBmatcher::SearchByProjection(KeyFrame* pKF, Sophus::Sim3f& Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched, th,
 //       ratioHamming) and the overload with vpPointsKFs / vpMatchedKF   ORBmatcher.cc:427-646 (LoopClosing.cc:1773/:1795/:1982) with KeyFrame::GetFeaturesInArea / IsInImage (KeyFrame.cc:707-756)
 //       and MapPoint::PredictScale(float, KeyFrame*) (MapPoint.cc:514-529)
@@ -67,6 +70,7 @@ public:
                            const float thFarPoints = 50.0f);
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
+    int Fuse(KeyFrame* pKF, Sophus::Sim3f& Scw, const std::vector<MapPoint*>& vpPoints, float th, std::vector<MapPoint*>& vpReplacePoint);
     int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist);
     int SearchByProjection(KeyFrame* pKF, Sophus::Sim3f& Scw, const std::vector<MapPoint*>& vpPoints, std::vector<MapPoint*>& vpMatched, int th,
                            float ratioHamming = 1.0);
@@ -85,6 +89,14 @@ class KeyFrame {                // KeyFrame.h:256, :324-334, :380-522: the membe
 public:
     bool isBad() { return mbBad; }
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+    std::set<MapPoint*> GetMapPoints() {                    // KeyFrame.cc:404-418 (the good ones)
+        std::set<MapPoint*> s;
+        for (size_t i = 0; i < mvpMapPoints.size(); i++) if (mvpMapPoints[i] && !mapPointIsBad(mvpMapPoints[i])) s.insert(mvpMapPoints[i]);
+        return s;
+    }
+    MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }                       // KeyFrame.cc:471-475
+    void AddMapPoint(MapPoint* pMP, const size_t& idx) { mvpMapPoints[idx] = pMP; }              // KeyFrame.cc:350-354
+    static bool mapPointIsBad(MapPoint* p);
     std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const bool bRight = false) const;
     bool IsInImage(const float& x, const float& y) const;
     int N = 0;
@@ -110,6 +122,7 @@ public:
     void ComputeDistinctiveDescriptors();
     int PredictScale(const float& currentDist, Frame* pF);
     int PredictScale(const float& currentDist, KeyFrame* pKF);
+    void AddObservation(KeyFrame* pKF, int idx) { mObservations[pKF] = std::tuple<int, int>(idx, -1); nObs++; }      // (stand-in for MapPoint.cc:137-166)
     Eigen::Vector3f GetNormal() { return mNormalVector; }
     Eigen::Vector3f mNormalVector;
     float GetMinDistanceInvariance();
@@ -167,6 +180,7 @@ public:
     std::vector<std::size_t> mGridRight[FRAME_GRID_COLS][FRAME_GRID_ROWS];
 };
 float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
+bool KeyFrame::mapPointIsBad(MapPoint* p) { return p->isBad(); }
 
 // ---- the reference's own definitions (build-time cuts) ----
 #include "cut/ORBmatcher_TH_HIGH.inc"
@@ -182,6 +196,7 @@ float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX
 #include "cut/ORBmatcher_SearchByProjection_reloc.inc"
 #include "cut/ORBmatcher_SearchByProjection_sim3.inc"
 #include "cut/ORBmatcher_SearchByProjection_sim3_kfs.inc"
+#include "cut/ORBmatcher_Fuse_sim3.inc"
 #include "cut/KeyFrame_GetFeaturesInArea.inc"
 #include "cut/KeyFrame_IsInImage.inc"
 #include "cut/MapPoint_PredictScale_KeyFrame.inc"
@@ -567,6 +582,68 @@ static int sim3_search(int withKFs, const float* kps, const int32_t* oct, const 
     }
     for (int i = 0; i < n; i++) matchOf[i] = (vpMatched[i] && vpMatched[i] != &other) ? (int)(vpMatched[i] - mps.data()) : -1;
     return nmatches;
+}
+
+// LoopClosing::SearchAndFuse's call (LoopClosing.cc:3464 / :3509): ORBmatcher(0.8).Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (ORBmatcher.cc:1340-1455).
+// Key frame and map points as in refcut_search_by_projection_sim3; held[i]: 0 key point i holds no map point / 1 a good one / 2 a bad one (those are
+// points that are NOT among vpPoints).  -> replaceOf[j] = key point whose map point replaces point j (-1 none), addedAt[j] = key point that
+// received point j as a new observation (-1 none); returns nFused.
+int refcut_fuse_sim3(const float* kps, const int32_t* oct, const uint8_t* desc, int n, const float* fp, const uint8_t* held, const float* scaleFactors,
+                     int nlevels, const float* sim3, const float* cam4, int nP, const uint8_t* pState, const float* pPos, const float* pNormal,
+                     const uint8_t* pDesc, const float* pMinDist, const float* pMaxDist, float th, int32_t* replaceOf, int32_t* addedAt) {
+    using namespace ORB_SLAM3;
+    KeyFrame kf;
+    GeometricCamera cam;
+    cam.fx = cam4[0]; cam.fy = cam4[1]; cam.cx = cam4[2]; cam.cy = cam4[3];
+    kf.fx = cam4[0]; kf.fy = cam4[1]; kf.cx = cam4[2]; kf.cy = cam4[3];
+    kf.mpCamera = &cam;
+    kf.N = n; kf.NLeft = -1;
+    kf.mnMinX = (int)fp[0]; kf.mnMaxX = (int)fp[1]; kf.mnMinY = (int)fp[2]; kf.mnMaxY = (int)fp[3];
+    kf.mfGridElementWidthInv = fp[4]; kf.mfGridElementHeightInv = fp[5];
+    kf.mnScaleLevels = (int)fp[8]; kf.mfLogScaleFactor = fp[9];
+    kf.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    kf.mvKeysUn.resize(n);
+    for (int i = 0; i < n; i++) { kf.mvKeysUn[i].pt.x = kps[2 * i]; kf.mvKeysUn[i].pt.y = kps[2 * i + 1]; kf.mvKeysUn[i].octave = oct[i]; }
+    kf.mDescriptors = to_descriptors(desc, n);
+    {
+        Frame* F = new Frame();
+        Frame::mnMinX = fp[0]; Frame::mnMaxX = fp[1]; Frame::mnMinY = fp[2]; Frame::mnMaxY = fp[3];
+        Frame::mfGridElementWidthInv = fp[4]; Frame::mfGridElementHeightInv = fp[5];
+        F->N = n; F->Nleft = -1; F->mvKeysUn = kf.mvKeysUn;
+        F->AssignFeaturesToGrid();
+        kf.mGrid.resize(kf.mnGridCols);
+        for (int i = 0; i < kf.mnGridCols; i++) {
+            kf.mGrid[i].resize(kf.mnGridRows);
+            for (int j = 0; j < kf.mnGridRows; j++) kf.mGrid[i][j] = F->mGrid[i][j];
+        }
+        delete F;
+    }
+    std::vector<MapPoint> own(n);                                      // what the key points hold before the call
+    kf.mvpMapPoints.assign(n, nullptr);
+    for (int i = 0; i < n; i++) if (held && held[i]) { own[i].mbBad = held[i] == 2; kf.mvpMapPoints[i] = &own[i]; }
+    std::vector<MapPoint> mps(nP);
+    std::vector<MapPoint*> vpPoints(nP), vpReplace(nP, nullptr);
+    for (int j = 0; j < nP; j++) {
+        mps[j].mbBad = pState[j] == 2;
+        mps[j].mWorldPos = Eigen::Vector3f(pPos[3 * j], pPos[3 * j + 1], pPos[3 * j + 2]);
+        mps[j].mNormalVector = Eigen::Vector3f(pNormal[3 * j], pNormal[3 * j + 1], pNormal[3 * j + 2]);
+        mps[j].mDescriptor = to_descriptors(pDesc + (size_t)32 * j, 1);
+        mps[j].mfMinDistance = pMinDist[j]; mps[j].mfMaxDistance = pMaxDist[j];
+        vpPoints[j] = &mps[j];
+    }
+    Sophus::Sim3f Scw;
+    for (int i = 0; i < 9; i++) Scw.R.m[i] = sim3[i];
+    Scw.t = Eigen::Vector3f(sim3[9], sim3[10], sim3[11]);
+    Scw.s = sim3[12];
+    ORBmatcher matcher(0.8f, true);
+    const int nFused = matcher.Fuse(&kf, Scw, vpPoints, th, vpReplace);
+    for (int j = 0; j < nP; j++) {
+        // (a point can be replaced by one that an earlier iteration of this call added to the key frame: reported as 1000000 + its index)
+        replaceOf[j] = !vpReplace[j] ? -1 : (vpReplace[j] >= own.data() && vpReplace[j] < own.data() + n) ? (int)(vpReplace[j] - own.data())
+                                                                                                    : 1000000 + (int)(vpReplace[j] - mps.data());
+        addedAt[j] = mps[j].mObservations.count(&kf) ? std::get<0>(mps[j].mObservations[&kf]) : -1;
+    }
+    return nFused;
 }
 
 // Tracking::MonocularInitialization's call (Tracking.cc:2396 ff.): ORBmatcher(0.9, true).SearchForInitialization(mInitialFrame, mCurrentFrame,

@@ -12,6 +12,8 @@
 //
 //   SearchByProjection(KeyFrame* pKF, Sophus::Sim3f& Scw, vpPoints, vpMatched, th, ratioHamming)         reference ORBmatcher.cc:427-530
 //       (LoopClosing.cc:1795 / :1982)
+//   Fuse(KeyFrame* pKF, Sophus::Sim3f& Scw, vpPoints, th, vpReplacePoint)                                reference ORBmatcher.cc:1340-1455
+//       (LoopClosing::SearchAndFuse, LoopClosing.cc:3464 / :3509)
 //   SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vpMatches12)                                             reference ORBmatcher.cc:765-905
 //       (LoopClosing::DetectCommonRegionsFromBoW, LoopClosing.cc:1680 -- the one call here that is not made by the Tracking thread)
 //
@@ -641,6 +643,78 @@ int ORBmatcherGPU::SearchByProjectionSim3(KeyFrame* pKF, const float* R9, const 
         }
     }
     return nmatches;
+}
+
+// ORBmatcher::Fuse(KeyFrame* pKF, Sophus::Sim3f& Scw, vpPoints, th, vpReplacePoint) (ORBmatcher.cc:1340-1455; LoopClosing::SearchAndFuse,
+// LoopClosing.cc:3464 / :3509): the projection of the Sim3 search above, but the scan is unmasked (every key point inside the window and
+// the level band competes, bestDist starts at INT_MAX) -- so the scans of all points are independent of what the loop decides, and one
+// launch serves the whole call.  What the loop then does with the best key point -- replace the point it holds, or add the observation
+// -- is map bookkeeping on the reference's own objects, in the reference's order.
+int ORBmatcherGPU::FuseSim3(KeyFrame* pKF, const float* R9, const float* t3, float scale, const std::vector<MapPoint*>& vpPoints, float th,
+                            std::vector<MapPoint*>& vpReplacePoint) {
+    if (pKF->NLeft != -1) throw std::logic_error("ORBmatcherGPU::Fuse: fisheye-stereo key frames keep the reference's host path");
+    Impl& s = Scratch();
+    Eigen::Matrix3f Rm;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) Rm(i, j) = R9[3 * i + j];
+    Eigen::Vector3f tv(t3[0], t3[1], t3[2]);
+    Sophus::SE3f Tcw = Sophus::SE3f(Rm, tv / scale);                              // :1349
+    Eigen::Vector3f Ow = Tcw.inverse().translation();
+    const std::set<MapPoint*> spAlreadyFound = pKF->GetMapPoints();
+    const int nPoints = (int)vpPoints.size();
+    s.q.clear(); s.qlev.clear(); s.qdesc.clear(); s.src.clear();
+    for (int iMP = 0; iMP < nPoints; iMP++) {                                     // :1360-1406
+        MapPoint* pMP = vpPoints[iMP];
+        if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;
+        Eigen::Vector3f p3Dw = pMP->GetWorldPos();
+        Eigen::Vector3f p3Dc = Tcw * p3Dw;
+        if (p3Dc(2) < 0.0f) continue;
+        const Eigen::Vector2f uv = pKF->mpCamera->project(p3Dc);
+        if (!pKF->IsInImage(uv(0), uv(1))) continue;
+        const float maxDistance = pMP->GetMaxDistanceInvariance();
+        const float minDistance = pMP->GetMinDistanceInvariance();
+        Eigen::Vector3f PO = p3Dw - Ow;
+        const float dist3D = PO.norm();
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        Eigen::Vector3f Pn = pMP->GetNormal();
+        if (PO.dot(Pn) < 0.5 * dist3D) continue;
+        const int nPredictedLevel = pMP->PredictScale(dist3D, pKF);
+        const float radius = th * pKF->mvScaleFactors[nPredictedLevel];
+        const float q4[4] = {uv(0), uv(1), radius, -1.0f};
+        s.q.insert(s.q.end(), q4, q4 + 4);
+        s.qlev.push_back(nPredictedLevel - 1); s.qlev.push_back(nPredictedLevel);
+        const cv::Mat d = pMP->GetDescriptor();
+        s.qdesc.insert(s.qdesc.end(), d.ptr<uchar>(), d.ptr<uchar>() + 32);
+        s.src.push_back(iMP);
+    }
+    const int nq = (int)s.src.size(), n = (int)pKF->mvKeysUn.size();
+    if (nq == 0) return 0;
+    if (!pKF->mDescriptors.isContinuous()) throw std::runtime_error("KeyFrame::mDescriptors must be continuous");
+    s.xy.resize((size_t)n * 2);
+    s.oct.resize(n);
+    for (int i = 0; i < n; i++) { s.xy[2 * i] = pKF->mvKeysUn[i].pt.x; s.xy[2 * i + 1] = pKF->mvKeysUn[i].pt.y; s.oct[i] = pKF->mvKeysUn[i].octave; }
+    orbb_frame_view view;
+    view.kps_xy = s.xy.data(); view.kps_stride = 8; view.octaves = s.oct.data(); view.oct_stride = 4;
+    view.desc = pKF->mDescriptors.ptr<uchar>(); view.u_right = nullptr; view.n = n; view.on_device = 0;
+    const float grid4[4] = {(float)pKF->mnMinX, (float)pKF->mnMinY, pKF->mfGridElementWidthInv, pKF->mfGridElementHeightInv};
+    s.out.assign((size_t)nq * 2, -1);
+    if (orbb_search_area_topk(mpMatcher, &view, grid4, s.q.data(), s.qlev.data(), s.qdesc.data(), nq, nullptr, 257, 1, s.out.data()) != ORBB_OK)
+        throw std::runtime_error(std::string("orbb_search_area_topk failed: ") + orbb_matcher_last_error(mpMatcher));
+    int nFused = 0;
+    for (int j = 0; j < nq; j++) {                                                // :1436-1451
+        const int bestDist = s.out[2 * (size_t)j], bestIdx = s.out[2 * (size_t)j + 1], iMP = s.src[j];
+        if (bestIdx < 0 || bestDist > TH_LOW) continue;
+        MapPoint* pMP = vpPoints[iMP];
+        MapPoint* pMPinKF = pKF->GetMapPoint(bestIdx);
+        if (pMPinKF) {
+            if (!pMPinKF->isBad()) vpReplacePoint[iMP] = pMPinKF;
+        } else {
+            pMP->AddObservation(pKF, bestIdx);
+            pKF->AddMapPoint(pMP, bestIdx);
+        }
+        nFused++;
+    }
+    return nFused;
 }
 
 // ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (ORBmatcher.cc:223-421; Tracking::TrackReferenceKeyFrame, Tracking.cc:2769, and

@@ -82,6 +82,20 @@ public:
     int SearchByProjectionSim3(KeyFrame* pKF, const float* R9, const float* t3, float scale, const std::vector<MapPoint*>& vpPoints,
                                std::vector<MapPoint*>& vpMatched, int th, float ratioHamming, const std::vector<KeyFrame*>* vpPointsKFs,
                                std::vector<KeyFrame*>* vpMatchedKF);
+    // ORBmatcher::Fuse(KeyFrame* pKF, Sophus::Sim3f& Scw, const vector<MapPoint*>& vpPoints, th, vector<MapPoint*>& vpReplacePoint)   ORBmatcher.cc:1340-1455
+    template <class Sim3T>
+    int Fuse(KeyFrame* pKF, Sim3T& Scw, const std::vector<MapPoint*>& vpPoints, float th, std::vector<MapPoint*>& vpReplacePoint) {
+        float R[9], t[3];
+        const auto Rm = Scw.rotationMatrix();
+        const auto tv = Scw.translation();
+        for (int i = 0; i < 3; i++) {
+            t[i] = tv(i);
+            for (int j = 0; j < 3; j++) R[3 * i + j] = Rm(i, j);
+        }
+        return FuseSim3(pKF, R, t, Scw.scale(), vpPoints, th, vpReplacePoint);
+    }
+    int FuseSim3(KeyFrame* pKF, const float* R9, const float* t3, float scale, const std::vector<MapPoint*>& vpPoints, float th,
+                 std::vector<MapPoint*>& vpReplacePoint);
     // ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches)             ORBmatcher.cc:223-421
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches, const float nnratio, const bool checkOrientation);
     // ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12)              ORBmatcher.cc:765-905

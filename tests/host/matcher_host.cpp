@@ -297,6 +297,50 @@ static int gpuhost_sim3(int withKFs, const float* kps, const int32_t* oct, const
     return nmatches;
 }
 
+// same arguments and result as refcut_fuse_sim3 (oracle/ref_cut_tu.cpp)
+int gpuhost_fuse_sim3(const float* kps, const int32_t* oct, const uint8_t* desc, int n, const float* fp, const uint8_t* held, const float* scaleFactors,
+                      int nlevels, const float* sim3, const float* cam4, int nP, const uint8_t* pState, const float* pPos, const float* pNormal,
+                      const uint8_t* pDesc, const float* pMinDist, const float* pMaxDist, float th, int32_t* replaceOf, int32_t* addedAt) {
+    KeyFrame kf;
+    GeometricCamera cam;
+    cam.fx = cam4[0]; cam.fy = cam4[1]; cam.cx = cam4[2]; cam.cy = cam4[3];
+    kf.fx = cam4[0]; kf.fy = cam4[1]; kf.cx = cam4[2]; kf.cy = cam4[3];
+    kf.mpCamera = &cam;
+    kf.NLeft = -1;
+    kf.mnMinX = (int)fp[0]; kf.mnMaxX = (int)fp[1]; kf.mnMinY = (int)fp[2]; kf.mnMaxY = (int)fp[3];
+    kf.mfGridElementWidthInv = fp[4]; kf.mfGridElementHeightInv = fp[5];
+    kf.mnScaleLevels = (int)fp[8]; kf.mfLogScaleFactor = fp[9];
+    kf.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    kf.mvKeysUn.resize(n);
+    for (int i = 0; i < n; i++) { kf.mvKeysUn[i].pt.x = kps[2 * i]; kf.mvKeysUn[i].pt.y = kps[2 * i + 1]; kf.mvKeysUn[i].octave = oct[i]; }
+    kf.mDescriptors = to_descriptors(desc, n);
+    std::vector<MapPoint> own(n);
+    kf.mvpMapPoints.assign(n, nullptr);
+    for (int i = 0; i < n; i++) if (held && held[i]) { own[i].mbBad = held[i] == 2; kf.mvpMapPoints[i] = &own[i]; }
+    std::vector<MapPoint> mps(nP);
+    std::vector<MapPoint*> vpPoints(nP), vpReplace(nP, nullptr);
+    for (int j = 0; j < nP; j++) {
+        mps[j].mbBad = pState[j] == 2;
+        mps[j].mWorldPos = Eigen::Vector3f(pPos[3 * j], pPos[3 * j + 1], pPos[3 * j + 2]);
+        mps[j].mNormalVector = Eigen::Vector3f(pNormal[3 * j], pNormal[3 * j + 1], pNormal[3 * j + 2]);
+        mps[j].mDescriptor = to_descriptors(pDesc + (size_t)32 * j, 1);
+        mps[j].mfMinDistance = pMinDist[j]; mps[j].mfMaxDistance = pMaxDist[j];
+        vpPoints[j] = &mps[j];
+    }
+    Sophus::Sim3f Scw;
+    for (int i = 0; i < 9; i++) Scw.R.m[i] = sim3[i];
+    Scw.t = Eigen::Vector3f(sim3[9], sim3[10], sim3[11]);
+    Scw.s = sim3[12];
+    const int nFused = ORBmatcherGPU::Instance().Fuse(&kf, Scw, vpPoints, th, vpReplace);
+    for (int j = 0; j < nP; j++) {
+        // (a point can be replaced by one that an earlier iteration of this call added to the key frame: reported as 1000000 + its index)
+        replaceOf[j] = !vpReplace[j] ? -1 : (vpReplace[j] >= own.data() && vpReplace[j] < own.data() + n) ? (int)(vpReplace[j] - own.data())
+                                                                                                    : 1000000 + (int)(vpReplace[j] - mps.data());
+        addedAt[j] = mps[j].mObservations.count(&kf) ? mps[j].mObservations[&kf] : -1;
+    }
+    return nFused;
+}
+
 // same arguments and result as refcut_search_by_bow_kf (oracle/ref_cut_tu.cpp)
 int gpuhost_search_by_bow_kf(const float* angle1, const uint8_t* desc1, const uint8_t* state1, int n1, const int32_t* node1, const int32_t* start1,
                              const int32_t* feat1, int nodes1, int feats1, const float* angle2, const uint8_t* desc2, const uint8_t* state2, int n2,

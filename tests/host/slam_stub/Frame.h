@@ -33,6 +33,8 @@ public:
     inline int PredictScale(const float& currentDist, Frame* pF);
     inline int PredictScale(const float& currentDist, KeyFrame* pKF);
     Eigen::Vector3f GetNormal() { return mNormalVector; }
+    void AddObservation(KeyFrame* pKF, int idx) { mObservations[pKF] = idx; nObs++; }      // (stand-in for MapPoint.cc:137-166)
+    std::map<KeyFrame*, int> mObservations;
     Eigen::Vector3f mNormalVector;
     float mfMinDistance = 0, mfMaxDistance = 0;
     int Observations() { return nObs; }

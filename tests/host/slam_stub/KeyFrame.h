@@ -3,6 +3,7 @@
 // orb_slam3_ros_b200/host/ORBmatcherGPU.cc touches.  See Frame.h.
 #pragma once
 #include <map>
+#include <set>
 #include <vector>
 
 #include "Frame.h"
@@ -13,6 +14,13 @@ class KeyFrame {
 public:
     bool isBad() { return mbBad; }
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+    std::set<MapPoint*> GetMapPoints() {                    // KeyFrame.cc:404-418 (the good ones)
+        std::set<MapPoint*> s;
+        for (size_t i = 0; i < mvpMapPoints.size(); i++) if (mvpMapPoints[i] && !mvpMapPoints[i]->isBad()) s.insert(mvpMapPoints[i]);
+        return s;
+    }
+    MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
+    void AddMapPoint(MapPoint* pMP, const size_t& idx) { mvpMapPoints[idx] = pMP; }
     bool IsInImage(const float& x, const float& y) const { return x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY; }      // KeyFrame.cc:753-756
     int mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;      // (integers in KeyFrame.h)
     float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;

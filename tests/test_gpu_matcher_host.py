@@ -50,6 +50,8 @@ def host():
     lib.gpuhost_search_by_projection_sim3.argtypes = ref.SIM3_ARGTYPES
     lib.gpuhost_search_by_projection_sim3_kfs.restype = C.c_int
     lib.gpuhost_search_by_projection_sim3_kfs.argtypes = ref.SIM3_ARGTYPES + [C.c_void_p]
+    lib.gpuhost_fuse_sim3.restype = C.c_int
+    lib.gpuhost_fuse_sim3.argtypes = ref.FUSE_SIM3_ARGTYPES
     lib.gpuhost_search_by_bow_kf.restype = C.c_int
     lib.gpuhost_search_by_bow_kf.argtypes = ref.BOW_KF_ARGTYPES
     lib.gpuhost_search_by_bow.restype = C.c_int
@@ -128,6 +130,28 @@ def test_sim3_projection_search_equals_reference(host, seed, th, ratio):
                                                      _p(pn), _p(pd), _p(pmin), _p(pmax), th, ratio, _p(match2), _p(kf2))
     assert nm2 == nm_ref2 and np.array_equal(match2, match_ref2) and np.array_equal(kf2, kf_ref2)
     assert np.array_equal(kf_ref2 >= 0, match_ref2 >= 0) and np.array_equal(kf_ref2[match_ref2 >= 0], match_ref2[match_ref2 >= 0] % 7)
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref (the reference's own object code) is not built")
+@pytest.mark.parametrize("seed,th", [(5, 4.0), (6, 4.0), (7, 8.0)])
+def test_sim3_fuse_equals_reference(host, seed, th):
+    """ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (ORBmatcher.cc:1340-1455; LoopClosing::SearchAndFuse with th = 4): which points
+    replace an existing map point, which become new observations of which key point, and the count"""
+    k, pts, sim3 = sim3_scene(seed)
+    rng = np.random.default_rng(300 + seed)
+    k = dict(k, held=rng.choice([0, 1, 2], len(k["octaves"]), p=[0.5, 0.4, 0.1]).astype(np.uint8))
+    nf_ref, rep_ref, add_ref = ref.fuse_sim3(k, pts, sim3, th)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    kx, o, d, held, fp, sf, cam = f32(k["kps_xy"]), i32(k["octaves"]), u8(k["desc"]), u8(k["held"]), f32(k["fp"]), f32(k["scale_factors"]), f32(k["cam4"])
+    ps, pp, pn, pd, pmin, pmax = u8(pts["state"]), f32(pts["pos"]), f32(pts["normal"]), u8(pts["desc"]), f32(pts["min_dist"]), f32(pts["max_dist"])
+    s3 = f32(sim3)
+    rep, add = np.full(len(ps), -1, np.int32), np.full(len(ps), -1, np.int32)
+    nf = host.gpuhost_fuse_sim3(_p(kx), _p(o), _p(d), len(kx), _p(fp), _p(held), _p(sf), len(sf), _p(s3), _p(cam), len(ps), _p(ps), _p(pp), _p(pn), _p(pd),
+                                _p(pmin), _p(pmax), th, _p(rep), _p(add))
+    assert nf == nf_ref and np.array_equal(rep, rep_ref) and np.array_equal(add, add_ref)
+    assert nf_ref > 100 and (rep_ref >= 0).sum() > 20 and (add_ref >= 0).sum() > 20
 
 
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref (the reference's own object code) is not built")
