@@ -25,18 +25,8 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-@pytest.fixture(scope="module")
-def host():
-    """the adapter + harness compiled as C++14 against the stand-in headers (tests/host/slam_stub, tests/cvstub, oracle/cvshim/mini_geom.hpp)"""
-    from orb_slam3_ros_b200 import build
-    build.build_library()
-    SO.parent.mkdir(exist_ok=True)
-    pkg = ROOT / "orb_slam3_ros_b200"
-    subprocess.check_call(["g++", "-std=c++14", "-O2", "-ffp-contract=off", "-fPIC", "-shared", f"-I{ROOT / 'tests' / 'cvstub'}",
-                           f"-I{ROOT / 'tests' / 'host' / 'slam_stub'}", f"-I{ROOT / 'oracle' / 'cvshim'}", f"-I{ROOT / 'include'}", f"-I{pkg / 'host'}",
-                           str(ROOT / "tests" / "host" / "matcher_host.cpp"), str(pkg / "host" / "ORBmatcherGPU.cc"), f"-L{pkg}", "-lorbb200",
-                           f"-Wl,-rpath,{pkg}", "-o", str(SO)])
-    lib = C.CDLL(str(SO))
+def declare(lib):
+    """argument types of the harness entry points (tests/host/matcher_host.cpp), shared with tests/test_matcher_host_cpu.py"""
     lib.gpuhost_rescans.restype = C.c_long
     lib.gpuhost_search_by_projection.restype = C.c_int
     lib.gpuhost_search_by_projection.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
@@ -60,6 +50,21 @@ def host():
     lib.gpuhost_search_for_initialization.restype = C.c_int
     lib.gpuhost_search_for_initialization.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 2 + \
         [C.c_int, C.c_float, C.c_int, C.c_void_p]
+
+
+@pytest.fixture(scope="module")
+def host():
+    """the adapter + harness compiled as C++14 against the stand-in headers (tests/host/slam_stub, tests/cvstub, oracle/cvshim/mini_geom.hpp)"""
+    from orb_slam3_ros_b200 import build
+    build.build_library()
+    SO.parent.mkdir(exist_ok=True)
+    pkg = ROOT / "orb_slam3_ros_b200"
+    subprocess.check_call(["g++", "-std=c++14", "-O2", "-ffp-contract=off", "-fPIC", "-shared", f"-I{ROOT / 'tests' / 'cvstub'}",
+                           f"-I{ROOT / 'tests' / 'host' / 'slam_stub'}", f"-I{ROOT / 'oracle' / 'cvshim'}", f"-I{ROOT / 'include'}", f"-I{pkg / 'host'}",
+                           str(ROOT / "tests" / "host" / "matcher_host.cpp"), str(pkg / "host" / "ORBmatcherGPU.cc"), f"-L{pkg}", "-lorbb200",
+                           f"-Wl,-rpath,{pkg}", "-o", str(SO)])
+    lib = C.CDLL(str(SO))
+    declare(lib)
     return lib
 
 
