@@ -42,6 +42,8 @@ PIECES = [
      r"^\s*int ORBmatcher::SearchByProjection\(KeyFrame\* pKF, Sophus::Sim3<float> &Scw, const std::vector<MapPoint\*> &vpPoints, const std::vector<KeyFrame\*> &vpPointsKFs,\s*$", "function"),
     ("ORBmatcher_Fuse_sim3", "src/ORBmatcher.cc",
      r"^\s*int ORBmatcher::Fuse\(KeyFrame \*pKF, Sophus::Sim3f &Scw, const vector<MapPoint \*> &vpPoints, float th, vector<MapPoint \*> &vpReplacePoint\)", "function"),
+    ("ORBmatcher_Fuse_kf", "src/ORBmatcher.cc",
+     r"^\s*int ORBmatcher::Fuse\(KeyFrame \*pKF, const vector<MapPoint \*> &vpMapPoints, const float th, const bool bRight\)", "function"),
     ("KeyFrame_GetFeaturesInArea", "src/KeyFrame.cc", r"^vector<size_t> KeyFrame::GetFeaturesInArea\(", "function"),
     ("KeyFrame_IsInImage", "src/KeyFrame.cc", r"^bool KeyFrame::IsInImage\(", "function"),
     ("MapPoint_PredictScale_KeyFrame", "src/MapPoint.cc", r"^int MapPoint::PredictScale\(const float &currentDist, KeyFrame\* pKF\)", "function"),

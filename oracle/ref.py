@@ -402,6 +402,29 @@ def fuse_sim3(kf, pts, sim3, th):
     return nf, rep, add
 
 
+def fuse_kf(kf, pts, th):
+    """ORBmatcher::Fuse(pKF, vpMapPoints, th) (ORBmatcher.cc:1148-1338, reference text; LocalMapping::SearchInNeighbors) on a key frame with
+    NLeft == -1.  kf: dict(kps_xy, octaves, desc, held [n] (0 none / 1 good / 2 bad), held_obs [n], u_right (or None), inv_sigma2, fp (.., mbf at
+    [6], mnScaleLevels, mfLogScaleFactor), scale_factors, Tcw [12], cam4); pts: dict(state [m] (0 null entry / 1 good / 2 bad), obs [m], pos, normal,
+    desc, min_dist, max_dist)  -> (nFused, kp_holds[n], own_bad[n], pt_bad[m])"""
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    k, o, d, held, hobs = f32(kf["kps_xy"]).reshape(-1, 2), i32(kf["octaves"]), u8(kf["desc"]), u8(kf["held"]), i32(kf["held_obs"])
+    ur = None if kf.get("u_right") is None else f32(kf["u_right"])
+    isg, fp, sf, tcw, cam = f32(kf["inv_sigma2"]), f32(kf["fp"]), f32(kf["scale_factors"]), f32(kf["Tcw"]), f32(kf["cam4"])
+    ps, pobs, pp, pn, pd, pmin, pmax = u8(pts["state"]), i32(pts["obs"]), f32(pts["pos"]).reshape(-1, 3), f32(pts["normal"]).reshape(-1, 3), u8(pts["desc"]), \
+        f32(pts["min_dist"]), f32(pts["max_dist"])
+    holds, own_bad, pt_bad = np.full(len(k), -1, np.int32), np.zeros(len(k), np.uint8), np.zeros(len(ps), np.uint8)
+    fn = lib().refcut_fuse_kf
+    fn.restype = C.c_int
+    fn.argtypes = FUSE_KF_ARGTYPES
+    nf = fn(_ptr(k), _ptr(o), _ptr(d), len(k), _ptr(fp), _ptr(held), _ptr(hobs), None if ur is None else _ptr(ur), _ptr(isg), _ptr(sf), len(sf), _ptr(tcw),
+            _ptr(cam), len(ps), _ptr(ps), _ptr(pobs), _ptr(pp), _ptr(pn), _ptr(pd), _ptr(pmin), _ptr(pmax), float(th), _ptr(holds), _ptr(own_bad), _ptr(pt_bad))
+    return nf, holds, own_bad, pt_bad
+
+
+FUSE_KF_ARGTYPES = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 7 + [C.c_float] + [C.c_void_p] * 3
 FUSE_SIM3_ARGTYPES = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_void_p, C.c_void_p]
 SIM3_ARGTYPES = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_float, C.c_void_p]
 

@@ -27,6 +27,9 @@
 //       (Tracking::Relocalization, Tracking.cc:3765/:3779) with MapPoint::PredictScale(float, Frame*) and GetMin/MaxDistanceInvariance,
 //       MapPoint.cc:502-546
 //   ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>&)   ORBmatcher.cc:765-905 (LoopClosing.cc:1680)
+//   ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, th, bRight)   ORBmatcher.cc:1148-1338 (LocalMapping::SearchInNeighbors,
+//       LocalMapping.cc:772/:802; MapPoint::Replace / IsInKeyFrame and KeyFrame::ReplaceMapPointMatch / EraseMapPointMatch / GetPose /
+//       GetCameraCenter are stand-ins with the reference's effect on the one key frame of a test)
 //   ORBmatcher::Fuse(KeyFrame* pKF, Sophus::Sim3f& Scw, const vector<MapPoint*>& vpPoints, th, vpReplacePoint)   ORBmatcher.cc:1340-1455
 //       (LoopClosing::SearchAndFuse, LoopClosing.cc:3464/:3509; KeyFrame::GetMapPoints / GetMapPoint / AddMapPoint and MapPoint::AddObservation
 //       are plain stand-ins: map bookkeeping, not matching)
@@ -71,6 +74,7 @@ public:
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
     int Fuse(KeyFrame* pKF, Sophus::Sim3f& Scw, const std::vector<MapPoint*>& vpPoints, float th, std::vector<MapPoint*>& vpReplacePoint);
+    int Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, const float th = 3.0, const bool bRight = false);
     int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist);
     int SearchByProjection(KeyFrame* pKF, Sophus::Sim3f& Scw, const std::vector<MapPoint*>& vpPoints, std::vector<MapPoint*>& vpMatched, int th,
                            float ratioHamming = 1.0);
@@ -96,6 +100,15 @@ public:
     }
     MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }                       // KeyFrame.cc:471-475
     void AddMapPoint(MapPoint* pMP, const size_t& idx) { mvpMapPoints[idx] = pMP; }              // KeyFrame.cc:350-354
+    void ReplaceMapPointMatch(const int& idx, MapPoint* pMP) { mvpMapPoints[idx] = pMP; }        // KeyFrame.cc:386-389
+    void EraseMapPointMatch(const int& idx) { mvpMapPoints[idx] = static_cast<MapPoint*>(NULL); }   // KeyFrame.cc:356-360
+    Sophus::SE3f GetPose() { return mTcw; }
+    Eigen::Vector3f GetCameraCenter() { return mTcw.inverse().translation(); }                  // KeyFrame.cc:143-146 (mTwc.translation())
+    Sophus::SE3f GetRightPose() { return mTcw; }                  // (declared for the body's bRight branch; the tests run NLeft == -1, bRight == false)
+    Eigen::Vector3f GetRightCameraCenter() { return GetCameraCenter(); }
+    Sophus::SE3f mTcw;
+    float mbf = 0;
+    std::vector<float> mvuRight, mvInvLevelSigma2;
     static bool mapPointIsBad(MapPoint* p);
     std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const bool bRight = false) const;
     bool IsInImage(const float& x, const float& y) const;
@@ -123,6 +136,9 @@ public:
     int PredictScale(const float& currentDist, Frame* pF);
     int PredictScale(const float& currentDist, KeyFrame* pKF);
     void AddObservation(KeyFrame* pKF, int idx) { mObservations[pKF] = std::tuple<int, int>(idx, -1); nObs++; }      // (stand-in for MapPoint.cc:137-166)
+    bool IsInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF); }                                            // MapPoint.cc:420-424
+    void Replace(MapPoint* pMP);                                    // stand-in for MapPoint.cc:248-300 (below, once KeyFrame is complete)
+    MapPoint* mpReplaced = nullptr;
     Eigen::Vector3f GetNormal() { return mNormalVector; }
     Eigen::Vector3f mNormalVector;
     float GetMinDistanceInvariance();
@@ -181,6 +197,22 @@ public:
 };
 float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
 bool KeyFrame::mapPointIsBad(MapPoint* p) { return p->isBad(); }
+// MapPoint::Replace (MapPoint.cc:248-300) without the found / visible counters and the descriptor update: this point goes bad, its observations
+// move to pMP (or are erased where pMP is observed already)
+void MapPoint::Replace(MapPoint* pMP) {
+    if (pMP == this) return;
+    std::map<KeyFrame*, std::tuple<int, int>> obs = mObservations;
+    mObservations.clear();
+    mbBad = true;
+    mpReplaced = pMP;
+    for (std::map<KeyFrame*, std::tuple<int, int>>::iterator mit = obs.begin(); mit != obs.end(); mit++) {
+        KeyFrame* pKF = mit->first;
+        const int leftIndex = std::get<0>(mit->second);
+        if (!pMP->IsInKeyFrame(pKF)) {
+            if (leftIndex != -1) { pKF->ReplaceMapPointMatch(leftIndex, pMP); pMP->AddObservation(pKF, leftIndex); }
+        } else if (leftIndex != -1) pKF->EraseMapPointMatch(leftIndex);
+    }
+}
 
 // ---- the reference's own definitions (build-time cuts) ----
 #include "cut/ORBmatcher_TH_HIGH.inc"
@@ -197,6 +229,7 @@ bool KeyFrame::mapPointIsBad(MapPoint* p) { return p->isBad(); }
 #include "cut/ORBmatcher_SearchByProjection_sim3.inc"
 #include "cut/ORBmatcher_SearchByProjection_sim3_kfs.inc"
 #include "cut/ORBmatcher_Fuse_sim3.inc"
+#include "cut/ORBmatcher_Fuse_kf.inc"
 #include "cut/KeyFrame_GetFeaturesInArea.inc"
 #include "cut/KeyFrame_IsInImage.inc"
 #include "cut/MapPoint_PredictScale_KeyFrame.inc"
@@ -643,6 +676,79 @@ int refcut_fuse_sim3(const float* kps, const int32_t* oct, const uint8_t* desc, 
                                                                                                     : 1000000 + (int)(vpReplace[j] - mps.data());
         addedAt[j] = mps[j].mObservations.count(&kf) ? std::get<0>(mps[j].mObservations[&kf]) : -1;
     }
+    return nFused;
+}
+
+// LocalMapping::SearchInNeighbors' calls (LocalMapping.cc:772 / :802): ORBmatcher().Fuse(pKF, vpMapPoints, th) (ORBmatcher.cc:1148-1338) on a monocular
+// / rectified-stereo key frame (NLeft == -1, bRight == false).  Key frame as in refcut_fuse_sim3 plus its pose Tcw (12), mbf at fp[6], mvuRight (or null)
+// and mvInvLevelSigma2; held[i]: 0 none / 1 a good map point / 2 a bad one, heldObs[i] = Observations() of that point.  Map points: state 0 = null
+// entry of the list / 1 good / 2 bad, their Observations() in pObs.  -> kpHolds[i] = what key point i holds after the call (-1 nothing, i' < 1000000: its
+// own point i', 1000000 + j: list point j), ownBad[i] / ptBad[j] = bad flags after the call; returns nFused.
+int refcut_fuse_kf(const float* kps, const int32_t* oct, const uint8_t* desc, int n, const float* fp, const uint8_t* held, const int32_t* heldObs,
+                   const float* uRight, const float* invSigma2, const float* scaleFactors, int nlevels, const float* Tcw, const float* cam4, int nP,
+                   const uint8_t* pState, const int32_t* pObs, const float* pPos, const float* pNormal, const uint8_t* pDesc, const float* pMinDist,
+                   const float* pMaxDist, float th, int32_t* kpHolds, uint8_t* ownBad, uint8_t* ptBad) {
+    using namespace ORB_SLAM3;
+    KeyFrame kf;
+    GeometricCamera cam;
+    cam.fx = cam4[0]; cam.fy = cam4[1]; cam.cx = cam4[2]; cam.cy = cam4[3];
+    kf.fx = cam4[0]; kf.fy = cam4[1]; kf.cx = cam4[2]; kf.cy = cam4[3];
+    kf.mpCamera = &cam;
+    kf.N = n; kf.NLeft = -1;
+    kf.mnMinX = (int)fp[0]; kf.mnMaxX = (int)fp[1]; kf.mnMinY = (int)fp[2]; kf.mnMaxY = (int)fp[3];
+    kf.mfGridElementWidthInv = fp[4]; kf.mfGridElementHeightInv = fp[5];
+    kf.mbf = fp[6];
+    kf.mnScaleLevels = (int)fp[8]; kf.mfLogScaleFactor = fp[9];
+    kf.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    kf.mvInvLevelSigma2.assign(invSigma2, invSigma2 + nlevels);
+    kf.mTcw = Sophus::SE3f(Tcw, Tcw + 9);
+    kf.mvKeysUn.resize(n);
+    for (int i = 0; i < n; i++) { kf.mvKeysUn[i].pt.x = kps[2 * i]; kf.mvKeysUn[i].pt.y = kps[2 * i + 1]; kf.mvKeysUn[i].octave = oct[i]; }
+    kf.mvuRight.assign(n, -1.0f);
+    if (uRight) kf.mvuRight.assign(uRight, uRight + n);
+    kf.mDescriptors = to_descriptors(desc, n);
+    {
+        Frame* F = new Frame();
+        Frame::mnMinX = fp[0]; Frame::mnMaxX = fp[1]; Frame::mnMinY = fp[2]; Frame::mnMaxY = fp[3];
+        Frame::mfGridElementWidthInv = fp[4]; Frame::mfGridElementHeightInv = fp[5];
+        F->N = n; F->Nleft = -1; F->mvKeysUn = kf.mvKeysUn;
+        F->AssignFeaturesToGrid();
+        kf.mGrid.resize(kf.mnGridCols);
+        for (int i = 0; i < kf.mnGridCols; i++) {
+            kf.mGrid[i].resize(kf.mnGridRows);
+            for (int j = 0; j < kf.mnGridRows; j++) kf.mGrid[i][j] = F->mGrid[i][j];
+        }
+        delete F;
+    }
+    std::vector<MapPoint> own(n);
+    kf.mvpMapPoints.assign(n, nullptr);
+    for (int i = 0; i < n; i++)
+        if (held && held[i]) {
+            own[i].mbBad = held[i] == 2;
+            own[i].nObs = heldObs[i];
+            own[i].mObservations[&kf] = std::tuple<int, int>(i, -1);
+            kf.mvpMapPoints[i] = &own[i];
+        }
+    std::vector<MapPoint> mps(nP);
+    std::vector<MapPoint*> vpPoints(nP, nullptr);
+    for (int j = 0; j < nP; j++) {
+        if (!pState[j]) continue;
+        mps[j].mbBad = pState[j] == 2;
+        mps[j].nObs = pObs[j];
+        mps[j].mWorldPos = Eigen::Vector3f(pPos[3 * j], pPos[3 * j + 1], pPos[3 * j + 2]);
+        mps[j].mNormalVector = Eigen::Vector3f(pNormal[3 * j], pNormal[3 * j + 1], pNormal[3 * j + 2]);
+        mps[j].mDescriptor = to_descriptors(pDesc + (size_t)32 * j, 1);
+        mps[j].mfMinDistance = pMinDist[j]; mps[j].mfMaxDistance = pMaxDist[j];
+        vpPoints[j] = &mps[j];
+    }
+    ORBmatcher matcher(0.6f, true);
+    const int nFused = matcher.Fuse(&kf, vpPoints, th);
+    for (int i = 0; i < n; i++) {
+        MapPoint* p = kf.mvpMapPoints[i];
+        kpHolds[i] = !p ? -1 : (p >= own.data() && p < own.data() + n) ? (int)(p - own.data()) : 1000000 + (int)(p - mps.data());
+        ownBad[i] = own[i].mbBad;
+    }
+    for (int j = 0; j < nP; j++) ptBad[j] = mps[j].mbBad;
     return nFused;
 }
 

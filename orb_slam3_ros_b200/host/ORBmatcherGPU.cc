@@ -12,6 +12,8 @@
 //
 //   SearchByProjection(KeyFrame* pKF, Sophus::Sim3f& Scw, vpPoints, vpMatched, th, ratioHamming)         reference ORBmatcher.cc:427-530
 //       (LoopClosing.cc:1795 / :1982)
+//   Fuse(KeyFrame* pKF, vpMapPoints, th, bRight = false)                                                 reference ORBmatcher.cc:1148-1338
+//       (LocalMapping::SearchInNeighbors, LocalMapping.cc:772 / :802)
 //   Fuse(KeyFrame* pKF, Sophus::Sim3f& Scw, vpPoints, th, vpReplacePoint)                                reference ORBmatcher.cc:1340-1455
 //       (LoopClosing::SearchAndFuse, LoopClosing.cc:3464 / :3509)
 //   SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vpMatches12)                                             reference ORBmatcher.cc:765-905
@@ -643,6 +645,131 @@ int ORBmatcherGPU::SearchByProjectionSim3(KeyFrame* pKF, const float* R9, const 
         }
     }
     return nmatches;
+}
+
+// ORBmatcher::Fuse(KeyFrame* pKF, vpMapPoints, th, bRight = false) (ORBmatcher.cc:1148-1338; LocalMapping::SearchInNeighbors, LocalMapping.cc:772 /
+// :802) for monocular / rectified-stereo key frames.  Every candidate inside the window and the level band must also pass a chi-square test
+// of its reprojection error (:1272-1296: 5.99 on (ex, ey), 7.8 with the right coordinate where the key point has one) -- a test on the key
+// point's position, not on its descriptor.  The scan is unmasked, so ONE launch returns the eight nearest candidates of every point and
+// the loop below takes the first of them that passes the test: what the reference's scan keeps.  A point whose eight all fail walks its
+// window on the host.  Which points are bad or already observed by the key frame changes while the loop replaces and adds (:1187-1196 are
+// evaluated per iteration in the reference): the same tests run again at decision time on the live objects.
+int ORBmatcherGPU::Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, const float th) {
+    if (pKF->NLeft != -1) throw std::logic_error("ORBmatcherGPU::Fuse: fisheye-stereo key frames keep the reference's host path");
+    Impl& s = Scratch();
+    const int kFuseK = 8;
+    GeometricCamera* pCamera = pKF->mpCamera;
+    Sophus::SE3f Tcw = pKF->GetPose();
+    Eigen::Vector3f Ow = pKF->GetCameraCenter();
+    const float& bf = pKF->mbf;
+    const int nMPs = (int)vpMapPoints.size();
+    std::vector<float> urs;                                                       // per query: the projected right coordinate (:1219)
+    s.q.clear(); s.qlev.clear(); s.qdesc.clear(); s.src.clear();
+    for (int i = 0; i < nMPs; i++) {                                              // :1177-1252
+        MapPoint* pMP = vpMapPoints[i];
+        if (!pMP) continue;
+        if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;                     // (both can only stay true or turn true during the call)
+        Eigen::Vector3f p3Dw = pMP->GetWorldPos();
+        Eigen::Vector3f p3Dc = Tcw * p3Dw;
+        if (p3Dc(2) < 0.0f) continue;
+        const float invz = 1 / p3Dc(2);
+        const Eigen::Vector2f uv = pCamera->project(p3Dc);
+        if (!pKF->IsInImage(uv(0), uv(1))) continue;
+        const float ur = uv(0) - bf * invz;
+        const float maxDistance = pMP->GetMaxDistanceInvariance();
+        const float minDistance = pMP->GetMinDistanceInvariance();
+        Eigen::Vector3f PO = p3Dw - Ow;
+        const float dist3D = PO.norm();
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        Eigen::Vector3f Pn = pMP->GetNormal();
+        if (PO.dot(Pn) < 0.5 * dist3D) continue;
+        int nPredictedLevel = pMP->PredictScale(dist3D, pKF);
+        const float radius = th * pKF->mvScaleFactors[nPredictedLevel];
+        const float q4[4] = {uv(0), uv(1), radius, -1.0f};
+        s.q.insert(s.q.end(), q4, q4 + 4);
+        s.qlev.push_back(nPredictedLevel - 1); s.qlev.push_back(nPredictedLevel);
+        const cv::Mat d = pMP->GetDescriptor();
+        s.qdesc.insert(s.qdesc.end(), d.ptr<uchar>(), d.ptr<uchar>() + 32);
+        s.src.push_back(i);
+        urs.push_back(ur);
+    }
+    const int nq = (int)s.src.size(), n = (int)pKF->mvKeysUn.size();
+    if (nq == 0) return 0;
+    if (!pKF->mDescriptors.isContinuous()) throw std::runtime_error("KeyFrame::mDescriptors must be continuous");
+    s.xy.resize((size_t)n * 2);
+    s.oct.resize(n);
+    for (int i = 0; i < n; i++) { s.xy[2 * i] = pKF->mvKeysUn[i].pt.x; s.xy[2 * i + 1] = pKF->mvKeysUn[i].pt.y; s.oct[i] = pKF->mvKeysUn[i].octave; }
+    orbb_frame_view view;
+    view.kps_xy = s.xy.data(); view.kps_stride = 8; view.octaves = s.oct.data(); view.oct_stride = 4;
+    view.desc = pKF->mDescriptors.ptr<uchar>(); view.u_right = nullptr; view.n = n; view.on_device = 0;
+    const float grid4[4] = {(float)pKF->mnMinX, (float)pKF->mnMinY, pKF->mfGridElementWidthInv, pKF->mfGridElementHeightInv};
+    s.out.assign((size_t)nq * kFuseK * 2, -1);
+    if (orbb_search_area_topk(mpMatcher, &view, grid4, s.q.data(), s.qlev.data(), s.qdesc.data(), nq, nullptr, 256, kFuseK, s.out.data()) != ORBB_OK)
+        throw std::runtime_error(std::string("orbb_search_area_topk failed: ") + orbb_matcher_last_error(mpMatcher));
+    auto passes = [&](int idx, float u, float v, float ur) {                     // :1272-1296
+        const cv::KeyPoint& kp = pKF->mvKeysUn[idx];
+        const int& kpLevel = kp.octave;
+        if (pKF->mvuRight[idx] >= 0) {
+            const float& kpx = kp.pt.x;
+            const float& kpy = kp.pt.y;
+            const float& kpr = pKF->mvuRight[idx];
+            const float ex = u - kpx;
+            const float ey = v - kpy;
+            const float er = ur - kpr;
+            const float e2 = ex * ex + ey * ey + er * er;
+            return !(e2 * pKF->mvInvLevelSigma2[kpLevel] > 7.8);
+        }
+        const float& kpx = kp.pt.x;
+        const float& kpy = kp.pt.y;
+        const float ex = u - kpx;
+        const float ey = v - kpy;
+        const float e2 = ex * ex + ey * ey;
+        return !(e2 * pKF->mvInvLevelSigma2[kpLevel] > 5.99);
+    };
+    int nFused = 0;
+    for (int j = 0; j < nq; j++) {
+        MapPoint* pMP = vpMapPoints[s.src[j]];
+        if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;                     // :1187-1196 on the live objects
+        const float u = s.q[4 * (size_t)j], v = s.q[4 * (size_t)j + 1], radius = s.q[4 * (size_t)j + 2], ur = urs[j];
+        const int32_t* list = &s.out[(size_t)j * kFuseK * 2];
+        int bestDist = 256, bestIdx = -1, valid = 0;
+        for (int t = 0; t < kFuseK; t++) {
+            const int idx = list[2 * t + 1];
+            if (idx < 0) break;
+            valid++;
+            if (!passes(idx, u, v, ur)) continue;
+            bestDist = list[2 * t]; bestIdx = idx;
+            break;
+        }
+        if (bestIdx < 0 && valid == kFuseK) {                                     // the reference's own scan for this point (:1246-1309)
+            const int nPredictedLevel = s.qlev[2 * (size_t)j + 1];
+            const std::vector<size_t> vIndices = pKF->GetFeaturesInArea(u, v, radius, false);
+            const uchar* dMP = s.qdesc.data() + (size_t)32 * j;
+            for (std::vector<size_t>::const_iterator vit = vIndices.begin(), vend = vIndices.end(); vit != vend; vit++) {
+                const size_t idx = *vit;
+                const int& kpLevel = pKF->mvKeysUn[idx].octave;
+                if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+                if (!passes((int)idx, u, v, ur)) continue;
+                const int dist = orbb_hamming_distance(dMP, pKF->mDescriptors.ptr<uchar>((int)idx));
+                if (dist < bestDist) { bestDist = dist; bestIdx = (int)idx; }
+            }
+            mnRescans++;
+        }
+        if (bestIdx >= 0 && bestDist <= TH_LOW) {                                 // :1312-1331
+            MapPoint* pMPinKF = pKF->GetMapPoint(bestIdx);
+            if (pMPinKF) {
+                if (!pMPinKF->isBad()) {
+                    if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
+                    else pMPinKF->Replace(pMP);
+                }
+            } else {
+                pMP->AddObservation(pKF, bestIdx);
+                pKF->AddMapPoint(pMP, bestIdx);
+            }
+            nFused++;
+        }
+    }
+    return nFused;
 }
 
 // ORBmatcher::Fuse(KeyFrame* pKF, Sophus::Sim3f& Scw, vpPoints, th, vpReplacePoint) (ORBmatcher.cc:1340-1455; LoopClosing::SearchAndFuse,

@@ -82,6 +82,8 @@ public:
     int SearchByProjectionSim3(KeyFrame* pKF, const float* R9, const float* t3, float scale, const std::vector<MapPoint*>& vpPoints,
                                std::vector<MapPoint*>& vpMatched, int th, float ratioHamming, const std::vector<KeyFrame*>* vpPointsKFs,
                                std::vector<KeyFrame*>* vpMatchedKF);
+    // ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, th, bRight)                   ORBmatcher.cc:1148-1338 (bRight == false)
+    int Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, const float th);
     // ORBmatcher::Fuse(KeyFrame* pKF, Sophus::Sim3f& Scw, const vector<MapPoint*>& vpPoints, th, vector<MapPoint*>& vpReplacePoint)   ORBmatcher.cc:1340-1455
     template <class Sim3T>
     int Fuse(KeyFrame* pKF, Sim3T& Scw, const std::vector<MapPoint*>& vpPoints, float th, std::vector<MapPoint*>& vpReplacePoint) {

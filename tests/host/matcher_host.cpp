@@ -297,6 +297,61 @@ static int gpuhost_sim3(int withKFs, const float* kps, const int32_t* oct, const
     return nmatches;
 }
 
+// same arguments and result as refcut_fuse_kf (oracle/ref_cut_tu.cpp)
+int gpuhost_fuse_kf(const float* kps, const int32_t* oct, const uint8_t* desc, int n, const float* fp, const uint8_t* held, const int32_t* heldObs,
+                    const float* uRight, const float* invSigma2, const float* scaleFactors, int nlevels, const float* Tcw, const float* cam4, int nP,
+                    const uint8_t* pState, const int32_t* pObs, const float* pPos, const float* pNormal, const uint8_t* pDesc, const float* pMinDist,
+                    const float* pMaxDist, float th, int32_t* kpHolds, uint8_t* ownBad, uint8_t* ptBad) {
+    KeyFrame kf;
+    GeometricCamera cam;
+    cam.fx = cam4[0]; cam.fy = cam4[1]; cam.cx = cam4[2]; cam.cy = cam4[3];
+    kf.fx = cam4[0]; kf.fy = cam4[1]; kf.cx = cam4[2]; kf.cy = cam4[3];
+    kf.mpCamera = &cam;
+    kf.NLeft = -1;
+    kf.mnMinX = (int)fp[0]; kf.mnMaxX = (int)fp[1]; kf.mnMinY = (int)fp[2]; kf.mnMaxY = (int)fp[3];
+    kf.mfGridElementWidthInv = fp[4]; kf.mfGridElementHeightInv = fp[5];
+    kf.mbf = fp[6];
+    kf.mnScaleLevels = (int)fp[8]; kf.mfLogScaleFactor = fp[9];
+    kf.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    kf.mvInvLevelSigma2.assign(invSigma2, invSigma2 + nlevels);
+    kf.mTcw = Sophus::SE3f(Tcw, Tcw + 9);
+    kf.mvKeysUn.resize(n);
+    for (int i = 0; i < n; i++) { kf.mvKeysUn[i].pt.x = kps[2 * i]; kf.mvKeysUn[i].pt.y = kps[2 * i + 1]; kf.mvKeysUn[i].octave = oct[i]; }
+    kf.mvuRight.assign(n, -1.0f);
+    if (uRight) kf.mvuRight.assign(uRight, uRight + n);
+    kf.mDescriptors = to_descriptors(desc, n);
+    kf.AssignFeaturesToGrid();
+    std::vector<MapPoint> own(n);
+    kf.mvpMapPoints.assign(n, nullptr);
+    for (int i = 0; i < n; i++)
+        if (held && held[i]) {
+            own[i].mbBad = held[i] == 2;
+            own[i].nObs = heldObs[i];
+            own[i].mObservations[&kf] = i;
+            kf.mvpMapPoints[i] = &own[i];
+        }
+    std::vector<MapPoint> mps(nP);
+    std::vector<MapPoint*> vpPoints(nP, nullptr);
+    for (int j = 0; j < nP; j++) {
+        if (!pState[j]) continue;
+        mps[j].mbBad = pState[j] == 2;
+        mps[j].nObs = pObs[j];
+        mps[j].mWorldPos = Eigen::Vector3f(pPos[3 * j], pPos[3 * j + 1], pPos[3 * j + 2]);
+        mps[j].mNormalVector = Eigen::Vector3f(pNormal[3 * j], pNormal[3 * j + 1], pNormal[3 * j + 2]);
+        mps[j].mDescriptor = to_descriptors(pDesc + (size_t)32 * j, 1);
+        mps[j].mfMinDistance = pMinDist[j]; mps[j].mfMaxDistance = pMaxDist[j];
+        vpPoints[j] = &mps[j];
+    }
+    const int nFused = ORBmatcherGPU::Instance().Fuse(&kf, vpPoints, th);
+    for (int i = 0; i < n; i++) {
+        MapPoint* p = kf.mvpMapPoints[i];
+        kpHolds[i] = !p ? -1 : (p >= own.data() && p < own.data() + n) ? (int)(p - own.data()) : 1000000 + (int)(p - mps.data());
+        ownBad[i] = own[i].mbBad;
+    }
+    for (int j = 0; j < nP; j++) ptBad[j] = mps[j].mbBad;
+    return nFused;
+}
+
 // same arguments and result as refcut_fuse_sim3 (oracle/ref_cut_tu.cpp)
 int gpuhost_fuse_sim3(const float* kps, const int32_t* oct, const uint8_t* desc, int n, const float* fp, const uint8_t* held, const float* scaleFactors,
                       int nlevels, const float* sim3, const float* cam4, int nP, const uint8_t* pState, const float* pPos, const float* pNormal,

@@ -34,6 +34,9 @@ public:
     inline int PredictScale(const float& currentDist, KeyFrame* pKF);
     Eigen::Vector3f GetNormal() { return mNormalVector; }
     void AddObservation(KeyFrame* pKF, int idx) { mObservations[pKF] = idx; nObs++; }      // (stand-in for MapPoint.cc:137-166)
+    bool IsInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF); }                  // MapPoint.cc:420-424
+    inline void Replace(MapPoint* pMP);                                                    // stand-in for MapPoint.cc:248-300 (KeyFrame.h)
+    MapPoint* mpReplaced = nullptr;
     std::map<KeyFrame*, int> mObservations;
     Eigen::Vector3f mNormalVector;
     float mfMinDistance = 0, mfMaxDistance = 0;

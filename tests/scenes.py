@@ -169,3 +169,35 @@ def sim3_scene(seed=5, scale=1.07):
     pts = dict(state=state, pos=pos, normal=normal.astype(np.float32), desc=kf["desc"], min_dist=(kf["min_dist"] * np.float32(scale)).astype(np.float32),
                max_dist=(kf["max_dist"] * np.float32(scale)).astype(np.float32))
     return k, pts, sim3
+
+
+def fuse_scene(seed=5, stereo=False):
+    """LocalMapping::SearchInNeighbors: a neighbour's map points fused into a key frame.  Built on reloc_scene (key frame = its current frame with
+    its pose); the key points hold good / bad / no map points with different observation counts, so that both replacement directions and new
+    observations occur; the list contains null entries, bad points and duplicates; with `stereo` most key points have a right coordinate (the 7.8
+    chi-square branch), a few of them inconsistent with the projection."""
+    cur, kfp = reloc_scene(seed)
+    rng = np.random.default_rng(400 + seed)
+    n, m = len(cur["octaves"]), len(kfp["state"])
+    sf = np.asarray(cur["scale_factors"], np.float32)
+    pos = kfp["pos"]
+    normal = (pos / np.linalg.norm(pos, axis=1, keepdims=True)).astype(np.float32)
+    fp = cur["fp"].copy()
+    fp[6] = np.float32(40.0)                                                     # mbf
+    R, t = cur["Tcw"][:9].reshape(3, 3).astype(np.float32), cur["Tcw"][9:].astype(np.float32)
+    u_right = None
+    if stereo:
+        # right coordinates consistent with a plausible depth for most key points (so that the 3-dof test can pass), noise on some
+        z = rng.uniform(4.0, 9.0, n).astype(np.float32)
+        u_right = (cur["kps_xy"][:, 0] - np.float32(40.0) / z).astype(np.float32)
+        u_right[rng.random(n) < 0.3] = -1
+    state = rng.choice([0, 1, 2], m, p=[0.05, 0.85, 0.10]).astype(np.uint8)
+    dup = rng.integers(0, m, 30)                                                   # (the harness cannot alias entries: duplicates are separate but identical points)
+    k = dict(kps_xy=cur["kps_xy"], octaves=cur["octaves"], desc=cur["desc"], held=rng.choice([0, 1, 2], n, p=[0.5, 0.42, 0.08]).astype(np.uint8),
+             held_obs=rng.integers(1, 9, n).astype(np.int32), u_right=u_right, inv_sigma2=(1.0 / (sf * sf)).astype(np.float32), fp=fp, scale_factors=sf,
+             Tcw=cur["Tcw"], cam4=cur["cam4"])
+    pts = dict(state=state, obs=rng.integers(1, 9, m).astype(np.int32), pos=pos, normal=normal, desc=kfp["desc"], min_dist=kfp["min_dist"], max_dist=kfp["max_dist"])
+    for a, b in zip(dup[:15], dup[15:]):
+        for key in ("pos", "normal", "desc", "min_dist", "max_dist"):
+            pts[key][b] = pts[key][a]
+    return k, pts

@@ -14,7 +14,7 @@ from oracle import port, ref
 from orb_slam3_ros_b200 import capi, synth
 from orb_slam3_ros_b200.extractor import ORBextractor
 from orb_slam3_ros_b200.matcher import ORBmatcher
-from scenes import bow_scene, init_scene, local_points_scene, motion_scene, reloc_scene, sim3_scene
+from scenes import bow_scene, fuse_scene, init_scene, local_points_scene, motion_scene, reloc_scene, sim3_scene
 
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
@@ -40,6 +40,8 @@ def declare(lib):
     lib.gpuhost_search_by_projection_sim3.argtypes = ref.SIM3_ARGTYPES
     lib.gpuhost_search_by_projection_sim3_kfs.restype = C.c_int
     lib.gpuhost_search_by_projection_sim3_kfs.argtypes = ref.SIM3_ARGTYPES + [C.c_void_p]
+    lib.gpuhost_fuse_kf.restype = C.c_int
+    lib.gpuhost_fuse_kf.argtypes = ref.FUSE_KF_ARGTYPES
     lib.gpuhost_fuse_sim3.restype = C.c_int
     lib.gpuhost_fuse_sim3.argtypes = ref.FUSE_SIM3_ARGTYPES
     lib.gpuhost_search_by_bow_kf.restype = C.c_int
@@ -135,6 +137,32 @@ def test_sim3_projection_search_equals_reference(host, seed, th, ratio):
                                                      _p(pn), _p(pd), _p(pmin), _p(pmax), th, ratio, _p(match2), _p(kf2))
     assert nm2 == nm_ref2 and np.array_equal(match2, match_ref2) and np.array_equal(kf2, kf_ref2)
     assert np.array_equal(kf_ref2 >= 0, match_ref2 >= 0) and np.array_equal(kf_ref2[match_ref2 >= 0], match_ref2[match_ref2 >= 0] % 7)
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref (the reference's own object code) is not built")
+@pytest.mark.parametrize("seed,th,stereo", [(5, 3.0, False), (6, 3.0, True), (7, 6.0, True), (8, 12.0, True)])
+def test_fuse_equals_reference(host, seed, th, stereo):
+    """ORBmatcher::Fuse(pKF, vpMapPoints, th) (ORBmatcher.cc:1148-1338; LocalMapping::SearchInNeighbors): what every key point holds after the
+    call, which key-frame points and which list points went bad (replaced), and the count"""
+    k, pts = fuse_scene(seed, stereo)
+    nf_ref, holds_ref, ob_ref, pb_ref = ref.fuse_kf(k, pts, th)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    kx, o, d, held, hobs = f32(k["kps_xy"]), i32(k["octaves"]), u8(k["desc"]), u8(k["held"]), i32(k["held_obs"])
+    ur = None if k["u_right"] is None else f32(k["u_right"])
+    isg, fp, sf, tcw, cam = f32(k["inv_sigma2"]), f32(k["fp"]), f32(k["scale_factors"]), f32(k["Tcw"]), f32(k["cam4"])
+    ps, pobs, pp, pn, pd, pmin, pmax = u8(pts["state"]), i32(pts["obs"]), f32(pts["pos"]), f32(pts["normal"]), u8(pts["desc"]), f32(pts["min_dist"]), f32(pts["max_dist"])
+    holds, ob, pb = np.full(len(kx), -1, np.int32), np.zeros(len(kx), np.uint8), np.zeros(len(ps), np.uint8)
+    r0 = host.gpuhost_rescans()
+    nf = host.gpuhost_fuse_kf(_p(kx), _p(o), _p(d), len(kx), _p(fp), _p(held), _p(hobs), _p(ur), _p(isg), _p(sf), len(sf), _p(tcw), _p(cam), len(ps), _p(ps),
+                              _p(pobs), _p(pp), _p(pn), _p(pd), _p(pmin), _p(pmax), th, _p(holds), _p(ob), _p(pb))
+    assert nf == nf_ref and np.array_equal(holds, holds_ref) and np.array_equal(ob, ob_ref) and np.array_equal(pb, pb_ref)
+    went_bad_own = int((ob_ref > 0).sum() - (held == 2).sum())
+    went_bad_pts = int((pb_ref > 0).sum() - (ps == 2).sum())
+    assert nf_ref > 60 and went_bad_own > 5 and went_bad_pts > 5 and (holds_ref >= 1000000).sum() > 20      # both replacement directions, new observations
+    if th >= 12:
+        assert host.gpuhost_rescans() > r0      # wide windows: some points lose all eight candidates to the chi-square test and walk the window on the host
 
 
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref (the reference's own object code) is not built")

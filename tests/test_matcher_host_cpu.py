@@ -69,3 +69,8 @@ def test_sim3_projection(host_cpu, seed, th, ratio):
 @pytest.mark.parametrize("seed,th", [(5, 4.0), (6, 4.0), (7, 8.0)])
 def test_sim3_fuse(host_cpu, seed, th):
     gpu_cases.test_sim3_fuse_equals_reference(host_cpu, seed, th)
+
+
+@pytest.mark.parametrize("seed,th,stereo", [(5, 3.0, False), (6, 3.0, True), (7, 6.0, True), (8, 12.0, True)])
+def test_fuse(host_cpu, seed, th, stereo):
+    gpu_cases.test_fuse_equals_reference(host_cpu, seed, th, stereo)
