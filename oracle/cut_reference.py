@@ -44,6 +44,7 @@ PIECES = [
      r"^\s*int ORBmatcher::Fuse\(KeyFrame \*pKF, Sophus::Sim3f &Scw, const vector<MapPoint \*> &vpPoints, float th, vector<MapPoint \*> &vpReplacePoint\)", "function"),
     ("ORBmatcher_Fuse_kf", "src/ORBmatcher.cc",
      r"^\s*int ORBmatcher::Fuse\(KeyFrame \*pKF, const vector<MapPoint \*> &vpMapPoints, const float th, const bool bRight\)", "function"),
+    ("ORBmatcher_SearchForTriangulation", "src/ORBmatcher.cc", r"^\s*int ORBmatcher::SearchForTriangulation\(KeyFrame \*pKF1, KeyFrame \*pKF2,\s*$", "function"),
     ("KeyFrame_GetFeaturesInArea", "src/KeyFrame.cc", r"^vector<size_t> KeyFrame::GetFeaturesInArea\(", "function"),
     ("KeyFrame_IsInImage", "src/KeyFrame.cc", r"^bool KeyFrame::IsInImage\(", "function"),
     ("MapPoint_PredictScale_KeyFrame", "src/MapPoint.cc", r"^int MapPoint::PredictScale\(const float &currentDist, KeyFrame\* pKF\)", "function"),

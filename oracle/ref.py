@@ -402,6 +402,34 @@ def fuse_sim3(kf, pts, sim3, th):
     return nf, rep, add
 
 
+def search_for_triangulation(k1, k2, common, only_stereo=False, coarse=False, check_orientation=False):
+    """ORBmatcher(0.6, checkOri).SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse) (ORBmatcher.cc:906-1146, reference text;
+    LocalMapping::CreateNewMapPoints).  k1 / k2: dict(kps_xy, octaves, angles, desc, has_point, u_right (or None), fv, Tcw [12]); common:
+    dict(sigma2, scale_factors, cam4)  -> (nmatches, pairs [nmatches, 2])"""
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    keep, args = [], []
+    for k in (k1, k2):
+        arrs = [f32(k["kps_xy"]).reshape(-1, 2), i32(k["octaves"]), f32(k["angles"]), u8(k["desc"]), u8(k["has_point"]),
+                None if k.get("u_right") is None else f32(k["u_right"])]
+        fv = [i32(a) for a in k["fv"]]
+        t = f32(k["Tcw"])
+        keep += arrs + fv + [t]
+        args += [None if a is None else _ptr(a) for a in arrs] + [len(arrs[0])] + [_ptr(a) for a in fv] + [len(fv[0]), len(fv[2]), _ptr(t)]
+    sg, sf, cam = f32(common["sigma2"]), f32(common["scale_factors"]), f32(common["cam4"])
+    pairs = np.full((len(keep[0]), 2), -1, np.int32)
+    fn = lib().refcut_search_for_triangulation
+    fn.restype = C.c_int
+    fn.argtypes = TRI_ARGTYPES
+    nm = fn(*args, _ptr(sg), _ptr(sf), len(sf), _ptr(cam), int(only_stereo), int(coarse), int(check_orientation), _ptr(pairs))
+    return nm, pairs[:max(nm, 0)]
+
+
+_TRI_KF = [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_void_p]
+TRI_ARGTYPES = _TRI_KF + _TRI_KF + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+
+
 def fuse_kf(kf, pts, th):
     """ORBmatcher::Fuse(pKF, vpMapPoints, th) (ORBmatcher.cc:1148-1338, reference text; LocalMapping::SearchInNeighbors) on a key frame with
     NLeft == -1.  kf: dict(kps_xy, octaves, desc, held [n] (0 none / 1 good / 2 bad), held_obs [n], u_right (or None), inv_sigma2, fp (.., mbf at

@@ -12,6 +12,8 @@
 //
 //   SearchByProjection(KeyFrame* pKF, Sophus::Sim3f& Scw, vpPoints, vpMatched, th, ratioHamming)         reference ORBmatcher.cc:427-530
 //       (LoopClosing.cc:1795 / :1982)
+//   SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse)                              reference ORBmatcher.cc:906-1146
+//       (LocalMapping::CreateNewMapPoints, LocalMapping.cc:466)
 //   Fuse(KeyFrame* pKF, vpMapPoints, th, bRight = false)                                                 reference ORBmatcher.cc:1148-1338
 //       (LocalMapping::SearchInNeighbors, LocalMapping.cc:772 / :802)
 //   Fuse(KeyFrame* pKF, Sophus::Sim3f& Scw, vpPoints, th, vpReplacePoint)                                reference ORBmatcher.cc:1340-1455
@@ -643,6 +645,117 @@ int ORBmatcherGPU::SearchByProjectionSim3(KeyFrame* pKF, const float* R9, const 
             if (vpMatchedKF) (*vpMatchedKF)[bestIdx] = (*vpPointsKFs)[s.src[j]];
             nmatches++;
         }
+    }
+    return nmatches;
+}
+
+// ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse) (ORBmatcher.cc:906-1146; LocalMapping::CreateNewMapPoints,
+// LocalMapping.cc:466) for two monocular / rectified-stereo key frames.  Key points without map points that share a vocabulary node are
+// compared; a candidate counts only if it is not too close to the epipole (:1019-1027) and satisfies the epipolar constraint of the
+// camera model (:1067), and the reference's update rule `dist > bestDist -> continue` (:1010) lets a LATER candidate with the same distance
+// replace the current best.  vbMatched2 is never written in the reference, so the scans of all key points are independent: the geometric
+// tests -- pure functions of the two key points -- run on the host while the candidate lists are collected, in REVERSED order, and one
+// orbb_best2_csr launch with the bound TH_LOW + 1 returns the first minimum of every reversed list = the last minimum of the original one.
+int ORBmatcherGPU::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<std::pair<size_t, size_t> >& vMatchedPairs, const bool bOnlyStereo,
+                                          const bool bCoarse, const bool checkOrientation) {
+    if (pKF1->NLeft != -1 || pKF2->NLeft != -1 || pKF1->mpCamera2 || pKF2->mpCamera2)
+        throw std::logic_error("ORBmatcherGPU::SearchForTriangulation: fisheye-stereo key frames keep the reference's host path");
+    Impl& s = Scratch();
+    const DBoW2::FeatureVector& vFeatVec1 = pKF1->mFeatVec;
+    const DBoW2::FeatureVector& vFeatVec2 = pKF2->mFeatVec;
+    Sophus::SE3f T1w = pKF1->GetPose();                                           // :913-930
+    Sophus::SE3f T2w = pKF2->GetPose();
+    Sophus::SE3f Tw2 = pKF2->GetPoseInverse();
+    Eigen::Vector3f Cw = pKF1->GetCameraCenter();
+    Eigen::Vector3f C2 = T2w * Cw;
+    Eigen::Vector2f ep = pKF2->mpCamera->project(C2);
+    Sophus::SE3f T12 = T1w * Tw2;
+    Eigen::Matrix3f R12 = T12.rotationMatrix();
+    Eigen::Vector3f t12 = T12.translation();
+    GeometricCamera* pCamera1 = pKF1->mpCamera, *pCamera2 = pKF2->mpCamera;
+    int nmatches = 0;
+    std::vector<int> vMatches12(pKF1->N, -1);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    for (int i = 0; i < HISTO_LENGTH; i++) rotHist[i].reserve(500);
+    const float factor = 1.0f / HISTO_LENGTH;
+    std::vector<unsigned char> free2(pKF2->N, 0);                                 // :1000-1008, the part that does not depend on the first key point
+    for (int i = 0; i < pKF2->N; i++) free2[i] = !pKF2->GetMapPoint(i) && (!bOnlyStereo || pKF2->mvuRight[i] >= 0);
+    s.qdesc.clear(); s.src.clear(); s.cand.clear(); s.rowptr.assign(1, 0);
+    DBoW2::FeatureVector::const_iterator f1it = vFeatVec1.begin(), f2it = vFeatVec2.begin();
+    const DBoW2::FeatureVector::const_iterator f1end = vFeatVec1.end(), f2end = vFeatVec2.end();
+    while (f1it != f1end && f2it != f2end) {
+        if (f1it->first == f2it->first) {
+            for (size_t i1 = 0, iend1 = f1it->second.size(); i1 < iend1; i1++) {
+                const size_t idx1 = f1it->second[i1];
+                if (pKF1->GetMapPoint(idx1)) continue;
+                const bool bStereo1 = pKF1->mvuRight[idx1] >= 0;
+                if (bOnlyStereo && !bStereo1) continue;
+                const cv::KeyPoint& kp1 = pKF1->mvKeysUn[idx1];
+                const size_t first = s.cand.size();
+                for (size_t i2 = f2it->second.size(); i2-- > 0;) {                 // reversed (see above)
+                    const size_t idx2 = f2it->second[i2];
+                    if (!free2[idx2]) continue;
+                    const bool bStereo2 = pKF2->mvuRight[idx2] >= 0;
+                    const cv::KeyPoint& kp2 = pKF2->mvKeysUn[idx2];
+                    if (!bStereo1 && !bStereo2) {                                 // :1019-1027
+                        const float distex = ep(0) - kp2.pt.x;
+                        const float distey = ep(1) - kp2.pt.y;
+                        if (distex * distex + distey * distey < 100 * pKF2->mvScaleFactors[kp2.octave]) continue;
+                    }
+                    if (bCoarse || pCamera1->epipolarConstrain(pCamera2, kp1, kp2, R12, t12, pKF1->mvLevelSigma2[kp1.octave], pKF2->mvLevelSigma2[kp2.octave]))
+                        s.cand.push_back((int32_t)idx2);
+                }
+                if (s.cand.size() == first) continue;                             // (no candidate can match: no query)
+                const uchar* d = pKF1->mDescriptors.ptr<uchar>((int)idx1);
+                s.qdesc.insert(s.qdesc.end(), d, d + 32);
+                s.src.push_back((int)idx1);
+                s.rowptr.push_back((int32_t)s.cand.size());
+            }
+            f1it++;
+            f2it++;
+        } else if (f1it->first < f2it->first) {
+            f1it = vFeatVec1.lower_bound(f2it->first);
+        } else {
+            f2it = vFeatVec2.lower_bound(f1it->first);
+        }
+    }
+    const int nq = (int)s.src.size();
+    s.out.assign((size_t)nq * 4, -1);
+    if (nq > 0) {
+        if (!pKF2->mDescriptors.isContinuous()) throw std::runtime_error("KeyFrame::mDescriptors must be continuous");
+        if (orbb_best2_csr(mpMatcher, s.qdesc.data(), nq, pKF2->mDescriptors.ptr<uchar>(), pKF2->mDescriptors.rows, s.cand.data(), s.rowptr.data(), TH_LOW + 1,
+                           s.out.data()) != ORBB_OK)
+            throw std::runtime_error(std::string("orbb_best2_csr failed: ") + orbb_matcher_last_error(mpMatcher));
+    }
+    for (int j = 0; j < nq; j++) {                                                // :1077-1096
+        const int bestIdx2 = s.out[4 * (size_t)j + 1], idx1 = s.src[j];
+        if (bestIdx2 < 0) continue;
+        vMatches12[idx1] = bestIdx2;
+        nmatches++;
+        if (checkOrientation) {
+            float rot = pKF1->mvKeysUn[idx1].angle - pKF2->mvKeysUn[bestIdx2].angle;
+            if (rot < 0.0) rot += 360.0f;
+            int bin = round(rot * factor);
+            if (bin == HISTO_LENGTH) bin = 0;
+            rotHist[bin].push_back(idx1);
+        }
+    }
+    if (checkOrientation) {                                                       // :1111-1130
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0, jend = rotHist[i].size(); j < jend; j++) {
+                vMatches12[rotHist[i][j]] = -1;
+                nmatches--;
+            }
+        }
+    }
+    vMatchedPairs.clear();
+    vMatchedPairs.reserve(nmatches);
+    for (size_t i = 0, iend = vMatches12.size(); i < iend; i++) {
+        if (vMatches12[i] < 0) continue;
+        vMatchedPairs.push_back(std::make_pair(i, (size_t)vMatches12[i]));
     }
     return nmatches;
 }

@@ -10,6 +10,7 @@
 #include <set>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 #include <opencv2/opencv.hpp>
 
@@ -82,6 +83,9 @@ public:
     int SearchByProjectionSim3(KeyFrame* pKF, const float* R9, const float* t3, float scale, const std::vector<MapPoint*>& vpPoints,
                                std::vector<MapPoint*>& vpMatched, int th, float ratioHamming, const std::vector<KeyFrame*>* vpPointsKFs,
                                std::vector<KeyFrame*>* vpMatchedKF);
+    // ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse)                   ORBmatcher.cc:906-1146
+    int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<std::pair<size_t, size_t> >& vMatchedPairs, const bool bOnlyStereo,
+                               const bool bCoarse, const bool checkOrientation);
     // ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, th, bRight)                   ORBmatcher.cc:1148-1338 (bRight == false)
     int Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, const float th);
     // ORBmatcher::Fuse(KeyFrame* pKF, Sophus::Sim3f& Scw, const vector<MapPoint*>& vpPoints, th, vector<MapPoint*>& vpReplacePoint)   ORBmatcher.cc:1340-1455

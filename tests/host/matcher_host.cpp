@@ -297,6 +297,42 @@ static int gpuhost_sim3(int withKFs, const float* kps, const int32_t* oct, const
     return nmatches;
 }
 
+// same arguments and result as refcut_search_for_triangulation (oracle/ref_cut_tu.cpp)
+int gpuhost_search_for_triangulation(const float* kps1, const int32_t* oct1, const float* angle1, const uint8_t* desc1, const uint8_t* has1, const float* ur1,
+                                     int n1, const int32_t* node1, const int32_t* start1, const int32_t* feat1, int nodes1, int feats1, const float* T1,
+                                     const float* kps2, const int32_t* oct2, const float* angle2, const uint8_t* desc2, const uint8_t* has2, const float* ur2,
+                                     int n2, const int32_t* node2, const int32_t* start2, const int32_t* feat2, int nodes2, int feats2, const float* T2,
+                                     const float* sigma2, const float* scaleFactors, int nlevels, const float* cam4, int onlyStereo, int coarse, int checkOri,
+                                     int32_t* pairs) {
+    GeometricCamera cam;
+    cam.fx = cam4[0]; cam.fy = cam4[1]; cam.cx = cam4[2]; cam.cy = cam4[3];
+    KeyFrame k1, k2;
+    MapPoint some;
+    auto fill = [&](KeyFrame& k, const float* kps, const int32_t* oct, const float* angle, const uint8_t* desc, const uint8_t* has, const float* ur, int n,
+                    const int32_t* node, const int32_t* start, const int32_t* feat, int nodes, int feats, const float* T) {
+        k.mpCamera = &cam; k.N = n; k.NLeft = -1;
+        k.mTcw = Sophus::SE3f(T, T + 9);
+        k.mvKeysUn.resize(n); k.mvpMapPoints.assign(n, nullptr);
+        for (int i = 0; i < n; i++) {
+            k.mvKeysUn[i].pt.x = kps[2 * i]; k.mvKeysUn[i].pt.y = kps[2 * i + 1]; k.mvKeysUn[i].octave = oct[i]; k.mvKeysUn[i].angle = angle[i];
+            if (has[i]) k.mvpMapPoints[i] = &some;
+        }
+        k.mvuRight.assign(n, -1.0f);
+        if (ur) k.mvuRight.assign(ur, ur + n);
+        k.mDescriptors = to_descriptors(desc, n);
+        k.mvLevelSigma2.assign(sigma2, sigma2 + nlevels);
+        k.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+        for (int g = 0; g < nodes; g++)
+            for (int f = start[g]; f < (g + 1 < nodes ? start[g + 1] : feats); f++) k.mFeatVec[(unsigned)node[g]].push_back((unsigned)feat[f]);
+    };
+    fill(k1, kps1, oct1, angle1, desc1, has1, ur1, n1, node1, start1, feat1, nodes1, feats1, T1);
+    fill(k2, kps2, oct2, angle2, desc2, has2, ur2, n2, node2, start2, feat2, nodes2, feats2, T2);
+    std::vector<std::pair<size_t, size_t> > vMatchedPairs;
+    const int nm = ORBmatcherGPU::Instance().SearchForTriangulation(&k1, &k2, vMatchedPairs, onlyStereo != 0, coarse != 0, checkOri != 0);
+    for (size_t k = 0; k < vMatchedPairs.size(); k++) { pairs[2 * k] = (int)vMatchedPairs[k].first; pairs[2 * k + 1] = (int)vMatchedPairs[k].second; }
+    return nm;
+}
+
 // same arguments and result as refcut_fuse_kf (oracle/ref_cut_tu.cpp)
 int gpuhost_fuse_kf(const float* kps, const int32_t* oct, const uint8_t* desc, int n, const float* fp, const uint8_t* held, const int32_t* heldObs,
                     const float* uRight, const float* invSigma2, const float* scaleFactors, int nlevels, const float* Tcw, const float* cam4, int nP,

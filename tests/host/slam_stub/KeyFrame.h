@@ -26,6 +26,9 @@ public:
     void ReplaceMapPointMatch(const int& idx, MapPoint* pMP) { mvpMapPoints[idx] = pMP; }
     void EraseMapPointMatch(const int& idx) { mvpMapPoints[idx] = static_cast<MapPoint*>(NULL); }
     Sophus::SE3f GetPose() { return mTcw; }
+    Sophus::SE3f GetPoseInverse() { return mTcw.inverse(); }
+    std::vector<float> mvLevelSigma2;
+    int N = 0;
     Eigen::Vector3f GetCameraCenter() { return mTcw.inverse().translation(); }
     Sophus::SE3f mTcw;
     float mbf = 0;

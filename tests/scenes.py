@@ -201,3 +201,36 @@ def fuse_scene(seed=5, stereo=False):
         for key in ("pos", "normal", "desc", "min_dist", "max_dist"):
             pts[key][b] = pts[key][a]
     return k, pts
+
+
+def triangulation_scene(seed=17, levelsup=2, stereo=False, ties=False):
+    """LocalMapping::CreateNewMapPoints: two neighbouring key frames (the two views of a stereo pair: a pure sideways translation, so that the
+    epipolar lines are the image rows and true matches satisfy the constraint), feature vectors from the BoW transform, most key points
+    without map points; with `stereo` some key points have right coordinates (no epipole test for those, and bOnlyStereo has something to keep)."""
+    sc = bow_scene(seed=seed, levelsup=levelsup)
+    from orb_slam3_ros_b200 import synth as _s
+    left, right = _s.stereo_pair(376, 620, 4, dmax=25)
+    pe = port.PortExtractor(900, 1.2, 8)
+    _, ka, da, _ = pe.extract(left)
+    _, kb, db, _ = pe.extract(right)
+    rng = np.random.default_rng(500 + seed)
+    sf = np.asarray(pe.scale_factors, np.float32)
+    eye = np.eye(3, dtype=np.float32).ravel()
+    T1 = np.concatenate([eye, np.float32([0, 0, 0])]).astype(np.float32)
+    T2 = np.concatenate([eye, np.float32([-0.25, 0.0, 0.02])]).astype(np.float32)      # camera 2 to the right (and slightly forward: a finite epipole)
+
+    def kf(k, d, fv, T):
+        n = len(k)
+        return dict(kps_xy=np.stack([k["x"], k["y"]], 1).astype(np.float32), octaves=k["octave"].astype(np.int32), angles=k["angle"].copy(), desc=d,
+                    has_point=(rng.random(n) < 0.25).astype(np.uint8),
+                    u_right=(np.where(rng.random(n) < 0.4, k["x"] - rng.uniform(2, 40, n), -1).astype(np.float32) if stereo else None), fv=fv, Tcw=T)
+    if ties:                                                                     # equal distances inside a node: the LAST minimum wins in the reference (:1010)
+        db = db.copy()
+        node, start, feat = (np.asarray(a) for a in sc["fv_f"])
+        ends = list(start[1:]) + [len(feat)]
+        for s0, e0 in zip(start, ends):
+            for a in range(s0 + 1, e0, 2):
+                db[feat[a]] = db[feat[a - 1]]
+    k1, k2 = kf(ka, da, sc["fv_k"], T1), kf(kb, db, sc["fv_f"], T2)
+    common = dict(sigma2=(sf * sf).astype(np.float32), scale_factors=sf, cam4=np.float32([458.0, 458.0, 310.0, 188.0]))
+    return k1, k2, common

@@ -14,7 +14,7 @@ from oracle import port, ref
 from orb_slam3_ros_b200 import capi, synth
 from orb_slam3_ros_b200.extractor import ORBextractor
 from orb_slam3_ros_b200.matcher import ORBmatcher
-from scenes import bow_scene, fuse_scene, init_scene, local_points_scene, motion_scene, reloc_scene, sim3_scene
+from scenes import bow_scene, fuse_scene, init_scene, local_points_scene, motion_scene, reloc_scene, sim3_scene, triangulation_scene
 
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
@@ -40,6 +40,8 @@ def declare(lib):
     lib.gpuhost_search_by_projection_sim3.argtypes = ref.SIM3_ARGTYPES
     lib.gpuhost_search_by_projection_sim3_kfs.restype = C.c_int
     lib.gpuhost_search_by_projection_sim3_kfs.argtypes = ref.SIM3_ARGTYPES + [C.c_void_p]
+    lib.gpuhost_search_for_triangulation.restype = C.c_int
+    lib.gpuhost_search_for_triangulation.argtypes = ref.TRI_ARGTYPES
     lib.gpuhost_fuse_kf.restype = C.c_int
     lib.gpuhost_fuse_kf.argtypes = ref.FUSE_KF_ARGTYPES
     lib.gpuhost_fuse_sim3.restype = C.c_int
@@ -137,6 +139,31 @@ def test_sim3_projection_search_equals_reference(host, seed, th, ratio):
                                                      _p(pn), _p(pd), _p(pmin), _p(pmax), th, ratio, _p(match2), _p(kf2))
     assert nm2 == nm_ref2 and np.array_equal(match2, match_ref2) and np.array_equal(kf2, kf_ref2)
     assert np.array_equal(kf_ref2 >= 0, match_ref2 >= 0) and np.array_equal(kf_ref2[match_ref2 >= 0], match_ref2[match_ref2 >= 0] % 7)
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref (the reference's own object code) is not built")
+@pytest.mark.parametrize("stereo,only_stereo,coarse,check,levelsup,ties", [(False, False, False, False, 2, False), (True, False, False, True, 2, False),
+                                                                           (True, True, False, False, 3, False), (False, False, True, True, 2, False),
+                                                                           (False, False, True, False, 2, True), (False, False, False, False, 3, True)])
+def test_search_for_triangulation_equals_reference(host, stereo, only_stereo, coarse, check, levelsup, ties):
+    """ORBmatcher::SearchForTriangulation (ORBmatcher.cc:906-1146; LocalMapping::CreateNewMapPoints): the matched pairs"""
+    k1, k2, common = triangulation_scene(levelsup=levelsup, stereo=stereo, ties=ties)
+    nm_ref, pairs_ref = ref.search_for_triangulation(k1, k2, common, only_stereo, coarse, check)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    keep, args = [], []
+    for k in (k1, k2):
+        arrs = [f32(k["kps_xy"]), i32(k["octaves"]), f32(k["angles"]), u8(k["desc"]), u8(k["has_point"]), None if k["u_right"] is None else f32(k["u_right"])]
+        fv = [i32(a) for a in k["fv"]]
+        t = f32(k["Tcw"])
+        keep += arrs + fv + [t]
+        args += [_p(a) for a in arrs] + [len(arrs[0])] + [_p(a) for a in fv] + [len(fv[0]), len(fv[2]), _p(t)]
+    sg, sf, cam = f32(common["sigma2"]), f32(common["scale_factors"]), f32(common["cam4"])
+    pairs = np.full((len(keep[0]), 2), -1, np.int32)
+    nm = host.gpuhost_search_for_triangulation(*args, _p(sg), _p(sf), len(sf), _p(cam), int(only_stereo), int(coarse), int(check), _p(pairs))
+    assert nm == nm_ref and np.array_equal(pairs[:max(nm, 0)], pairs_ref)
+    assert nm_ref > (15 if only_stereo else 60)
 
 
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref (the reference's own object code) is not built")

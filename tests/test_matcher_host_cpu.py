@@ -74,3 +74,10 @@ def test_sim3_fuse(host_cpu, seed, th):
 @pytest.mark.parametrize("seed,th,stereo", [(5, 3.0, False), (6, 3.0, True), (7, 6.0, True), (8, 12.0, True)])
 def test_fuse(host_cpu, seed, th, stereo):
     gpu_cases.test_fuse_equals_reference(host_cpu, seed, th, stereo)
+
+
+@pytest.mark.parametrize("stereo,only_stereo,coarse,check,levelsup,ties", [(False, False, False, False, 2, False), (True, False, False, True, 2, False),
+                                                                           (True, True, False, False, 3, False), (False, False, True, True, 2, False),
+                                                                           (False, False, True, False, 2, True), (False, False, False, False, 3, True)])
+def test_search_for_triangulation(host_cpu, stereo, only_stereo, coarse, check, levelsup, ties):
+    gpu_cases.test_search_for_triangulation_equals_reference(host_cpu, stereo, only_stereo, coarse, check, levelsup, ties)
