@@ -300,6 +300,31 @@ def search_by_projection(kps_xy, octaves, train, grid4, scale_factors, proj, lev
     return nm, match_of
 
 
+def search_by_projection_fisheye(f, mp, nnratio=0.8, th=1.0):
+    """ORBmatcher(nnratio).SearchByProjection(F, vpMapPoints, th) (ORBmatcher.cc:43-213, reference text) on a fisheye-stereo frame (Nleft != -1).
+      f:  dict(kps_l [nL,2], oct_l, kps_r [nR,2], oct_r, desc [nL+nR,32], fp (mnMinX, mnMaxX, mnMinY, mnMaxY, gridWInv, gridHInv), l2r [nL], r2l [nR],
+          has_point [nL+nR], scale_factors)
+      mp: dict(proj_l [m,3] (x, y, viewCos), level_l, in_view_l, proj_r [m,3], level_r (-1 none), in_view_r, desc [m,32])
+    -> (nmatches, match_of[nL+nR])"""
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    kl, ol, kr, orr, d, fp = f32(f["kps_l"]).reshape(-1, 2), i32(f["oct_l"]), f32(f["kps_r"]).reshape(-1, 2), i32(f["oct_r"]), u8(f["desc"]), f32(f["fp"])
+    l2r, r2l, hp, sf = i32(f["l2r"]), i32(f["r2l"]), u8(f["has_point"]), f32(f["scale_factors"])
+    pl, ll, il, pr, lr, ir, md = f32(mp["proj_l"]).reshape(-1, 3), i32(mp["level_l"]), u8(mp["in_view_l"]), f32(mp["proj_r"]).reshape(-1, 3), \
+        i32(mp["level_r"]), u8(mp["in_view_r"]), u8(mp["desc"])
+    match_of = np.full(len(kl) + len(kr), -1, np.int32)
+    fn = lib().refcut_search_by_projection_fisheye
+    fn.restype = C.c_int
+    fn.argtypes = FISHEYE_ARGTYPES
+    nm = fn(_ptr(kl), _ptr(ol), len(kl), _ptr(kr), _ptr(orr), len(kr), _ptr(d), _ptr(fp), _ptr(l2r), _ptr(r2l), _ptr(hp), _ptr(sf), len(sf), _ptr(pl), _ptr(ll),
+            _ptr(il), _ptr(pr), _ptr(lr), _ptr(ir), _ptr(md), len(pl), nnratio, th, _ptr(match_of))
+    return nm, match_of
+
+
+FISHEYE_ARGTYPES = [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_float, C.c_float, C.c_void_p]
+
+
 def search_by_projection_motion(cur, last, th, mono, nnratio=0.9, check_orientation=True):
     """ORBmatcher(nnratio, checkOri).SearchByProjection(CurrentFrame, LastFrame, th, bMono) (ORBmatcher.cc:1676-1887, reference text;
     the call of Tracking::TrackWithMotionModel) for frames with Nleft == -1.

@@ -418,6 +418,56 @@ int refcut_search_by_projection(const float* kps, const int32_t* oct, const uint
     return nmatches;
 }
 
+// The same call on a fisheye-stereo frame (Nleft != -1, the KannalaBrandt8 rigs of config/Stereo/TUM-VI.yaml): left key points mvKeys[0 .. nL) and
+// right key points mvKeysRight[0 .. nR) with their own grids, descriptors stacked left then right, mvLeftToRightMatch / mvRightToLeftMatch of the
+// stereo pairs; hasPoint over all nL + nR entries.  Map points: projL = {x, y, viewCos}, levelL, inViewL, projR = {xR, yR, viewCosR}, levelR (-1: none),
+// inViewR.  -> matchOf[nL + nR]; returns nmatches.
+int refcut_search_by_projection_fisheye(const float* kpsL, const int32_t* octL, int nL, const float* kpsR, const int32_t* octR, int nR, const uint8_t* desc,
+                                        const float* fp, const int32_t* l2r, const int32_t* r2l, const uint8_t* hasPoint, const float* scaleFactors,
+                                        int nlevels, const float* projL, const int32_t* levelL, const uint8_t* inViewL, const float* projR,
+                                        const int32_t* levelR, const uint8_t* inViewR, const uint8_t* mpDesc, int nmp, float nnratio, float th,
+                                        int32_t* matchOf) {
+    using namespace ORB_SLAM3;
+    Frame* F = new Frame();
+    Frame::mnMinX = fp[0]; Frame::mnMaxX = fp[1]; Frame::mnMinY = fp[2]; Frame::mnMaxY = fp[3];
+    Frame::mfGridElementWidthInv = fp[4]; Frame::mfGridElementHeightInv = fp[5];
+    const int n = nL + nR;
+    F->N = n; F->Nleft = nL; F->Nright = nR;
+    F->mvKeys.resize(nL); F->mvKeysRight.resize(nR);
+    for (int i = 0; i < nL; i++) { F->mvKeys[i].pt.x = kpsL[2 * i]; F->mvKeys[i].pt.y = kpsL[2 * i + 1]; F->mvKeys[i].octave = octL[i]; }
+    for (int i = 0; i < nR; i++) { F->mvKeysRight[i].pt.x = kpsR[2 * i]; F->mvKeysRight[i].pt.y = kpsR[2 * i + 1]; F->mvKeysRight[i].octave = octR[i]; }
+    F->AssignFeaturesToGrid();
+    F->mDescriptors = to_descriptors(desc, n);
+    F->mvuRight.assign(n, -1.0f);
+    F->mvLeftToRightMatch.assign(l2r, l2r + nL);
+    F->mvRightToLeftMatch.assign(r2l, r2l + nR);
+    F->mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    MapPoint old;
+    old.nObs = 1;
+    F->mvpMapPoints.assign(n, nullptr);
+    for (int i = 0; i < n; i++) if (hasPoint && hasPoint[i]) F->mvpMapPoints[i] = &old;
+    std::vector<MapPoint> mps(nmp);
+    std::vector<MapPoint*> vp(nmp);
+    for (int j = 0; j < nmp; j++) {
+        MapPoint& m = mps[j];
+        m.mTrackProjX = projL[3 * j]; m.mTrackProjY = projL[3 * j + 1]; m.mTrackViewCos = projL[3 * j + 2];
+        m.mnTrackScaleLevel = levelL[j]; m.mbTrackInView = inViewL[j] != 0;
+        m.mTrackProjXR = projR[3 * j]; m.mTrackProjYR = projR[3 * j + 1]; m.mTrackViewCosR = projR[3 * j + 2];
+        m.mnTrackScaleLevelR = levelR[j]; m.mbTrackInViewR = inViewR[j] != 0;
+        m.mDescriptor = to_descriptors(mpDesc + (size_t)32 * j, 1);
+        m.nObs = 1;
+        vp[j] = &m;
+    }
+    ORBmatcher matcher(nnratio);
+    const int nmatches = matcher.SearchByProjection(*F, vp, th);
+    for (int i = 0; i < n; i++) {
+        MapPoint* p = F->mvpMapPoints[i];
+        matchOf[i] = (p && p != &old) ? (int)(p - mps.data()) : -1;
+    }
+    delete F;
+    return nmatches;
+}
+
 // Tracking::TrackWithMotionModel's call: ORBmatcher(nnratio, checkOri).SearchByProjection(CurrentFrame, LastFrame, th, bMono) on
 // monocular / rectified-stereo / RGB-D frames (Nleft == -1).
 //   current frame: undistorted key points (x, y), octaves, angles, descriptors, mvuRight (or null), curState[i] = 0 no map point /

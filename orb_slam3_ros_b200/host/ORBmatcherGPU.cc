@@ -162,9 +162,145 @@ void ORBmatcherGPU::Rescan(const Frame& F, int j, int want, void* candOut, int& 
 
 static inline float RadiusByViewingCos(float viewCos) { return viewCos > 0.998f ? 2.5f : 4.0f; }      // ORBmatcher.cc:215-221
 
+// The same search on a fisheye-stereo frame (Nleft != -1; KannalaBrandt8 rigs): two key point sets with their own grids -- mvKeys[0 .. Nleft) and
+// mvKeysRight, descriptors stacked left then right -- and a map point can be visible in either eye (mbTrackInView / mbTrackInViewR) with its own
+// projection, level and window.  Two batched scans (left queries against the left set, right queries against the right set, no mvuRight test:
+// :94), then the reference's loop in order: the left decision, which also claims the stereo partner in the right set (:127-131), then the right
+// decision, which also claims the partner in the left set (:196-200); a map point whose left ratio test fails skips its right half too (the
+// `continue` at :122 leaves the outer loop body).
+int ORBmatcherGPU::SearchByProjectionFisheye(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th, const bool bFarPoints,
+                                             const float thFarPoints, const float nnratio) {
+    Impl& s = Scratch();
+    const bool bFactor = th != 1.0;
+    const int nL = F.Nleft, nR = (int)F.mvKeysRight.size();
+    if (!F.mDescriptors.isContinuous()) throw std::runtime_error("Frame::mDescriptors must be continuous");
+    const float grid4[4] = {Frame::mnMinX, Frame::mnMinY, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv};
+    // queries of the two eyes; qOf*[iMP] = query index or -1
+    std::vector<float> qL, qR;
+    std::vector<int32_t> levL, levR, outL, outR;
+    std::vector<unsigned char> dL, dR, skipL, skipR;
+    std::vector<int> qOfL(vpMapPoints.size(), -1), qOfR(vpMapPoints.size(), -1);
+    for (size_t iMP = 0; iMP < vpMapPoints.size(); iMP++) {
+        MapPoint* pMP = vpMapPoints[iMP];
+        if (!pMP->mbTrackInView && !pMP->mbTrackInViewR) continue;
+        if (bFarPoints && pMP->mTrackDepth > thFarPoints) continue;
+        if (pMP->isBad()) continue;
+        const cv::Mat d = pMP->GetDescriptor();
+        if (pMP->mbTrackInView) {
+            const int nPredictedLevel = pMP->mnTrackScaleLevel;
+            float r = RadiusByViewingCos(pMP->mTrackViewCos);
+            if (bFactor) r *= th;
+            const float q4[4] = {pMP->mTrackProjX, pMP->mTrackProjY, r * F.mvScaleFactors[nPredictedLevel], -1.0f};
+            qOfL[iMP] = (int)levL.size() / 2;
+            qL.insert(qL.end(), q4, q4 + 4);
+            levL.push_back(nPredictedLevel - 1); levL.push_back(nPredictedLevel);
+            dL.insert(dL.end(), d.ptr<uchar>(), d.ptr<uchar>() + 32);
+        }
+        if (pMP->mbTrackInViewR && pMP->mnTrackScaleLevelR != -1) {
+            const int nPredictedLevel = pMP->mnTrackScaleLevelR;
+            float r = RadiusByViewingCos(pMP->mTrackViewCosR);                    // (:144: no th factor on the right window)
+            const float q4[4] = {pMP->mTrackProjXR, pMP->mTrackProjYR, r * F.mvScaleFactors[nPredictedLevel], -1.0f};
+            qOfR[iMP] = (int)levR.size() / 2;
+            qR.insert(qR.end(), q4, q4 + 4);
+            levR.push_back(nPredictedLevel - 1); levR.push_back(nPredictedLevel);
+            dR.insert(dR.end(), d.ptr<uchar>(), d.ptr<uchar>() + 32);
+        }
+    }
+    std::vector<float> xyL((size_t)nL * 2), xyR((size_t)nR * 2);
+    std::vector<int32_t> octL(nL), octR(nR);
+    for (int i = 0; i < nL; i++) { xyL[2 * i] = F.mvKeys[i].pt.x; xyL[2 * i + 1] = F.mvKeys[i].pt.y; octL[i] = F.mvKeys[i].octave; }
+    for (int i = 0; i < nR; i++) { xyR[2 * i] = F.mvKeysRight[i].pt.x; xyR[2 * i + 1] = F.mvKeysRight[i].pt.y; octR[i] = F.mvKeysRight[i].octave; }
+    orbb_frame_view vL, vR;
+    vL.kps_xy = xyL.data(); vL.kps_stride = 8; vL.octaves = octL.data(); vL.oct_stride = 4; vL.desc = F.mDescriptors.ptr<uchar>(); vL.u_right = nullptr;
+    vL.n = nL; vL.on_device = 0;
+    vR = vL;
+    vR.kps_xy = xyR.data(); vR.octaves = octR.data(); vR.desc = F.mDescriptors.ptr<uchar>() + (size_t)32 * nL; vR.n = nR;
+    auto scan = [&](bool right, int first, int count, int k, int32_t* out) {
+        const int n = right ? nR : nL, base = right ? nL : 0;
+        std::vector<unsigned char>& skip = right ? skipR : skipL;
+        skip.assign(n, 0);
+        for (int i = 0; i < n; i++) skip[i] = Taken(F, i + base);
+        const std::vector<float>& q = right ? qR : qL;
+        const std::vector<int32_t>& lev = right ? levR : levL;
+        const std::vector<unsigned char>& d = right ? dR : dL;
+        if (orbb_search_area_topk(mpMatcher, right ? &vR : &vL, grid4, &q[4 * (size_t)first], &lev[2 * (size_t)first], &d[32 * (size_t)first], count,
+                                  skip.data(), 256, k, out) != ORBB_OK)
+            throw std::runtime_error(std::string("orbb_search_area_topk failed: ") + orbb_matcher_last_error(mpMatcher));
+    };
+    const int nqL = (int)levL.size() / 2, nqR = (int)levR.size() / 2;
+    outL.assign((size_t)nqL * kTopK * 2, -1);
+    outR.assign((size_t)nqR * kTopK * 2, -1);
+    if (nqL) scan(false, 0, nqL, kTopK, outL.data());
+    if (nqR) scan(true, 0, nqR, kTopK, outR.data());
+    // the first two candidates of a list that are still free (base = offset of the eye's key points in mvpMapPoints); one query again when the
+    // list is used up
+    auto head = [&](bool right, int j, Cand* c, int& nc) {
+        const int base = right ? nL : 0;
+        const int32_t* list = right ? &outR[(size_t)j * kTopK * 2] : &outL[(size_t)j * kTopK * 2];
+        nc = 0;
+        int valid = 0;
+        for (int t = 0; t < kTopK; t++) {
+            const int idx = list[2 * t + 1];
+            if (idx < 0) break;
+            valid++;
+            if (Taken(F, idx + base)) continue;
+            if (nc < 2) { c[nc].dist = list[2 * t]; c[nc].idx = idx; nc++; }
+        }
+        if (nc < 2 && valid == kTopK) {
+            int32_t o[4] = {256, -1, 256, -1};
+            scan(right, j, 1, 2, o);
+            nc = 0;
+            for (int t = 0; t < 2; t++) if (o[2 * t + 1] >= 0) { c[nc].dist = o[2 * t]; c[nc].idx = o[2 * t + 1]; nc++; }
+            mnRescans++;
+        }
+    };
+    int nmatches = 0;
+    for (size_t iMP = 0; iMP < vpMapPoints.size(); iMP++) {
+        MapPoint* pMP = vpMapPoints[iMP];
+        if (qOfL[iMP] >= 0) {                                                     // :60-137
+            Cand c[2];
+            int nc = 0;
+            head(false, qOfL[iMP], c, nc);
+            if (nc > 0) {
+                const int bestDist = c[0].dist, bestIdx = c[0].idx, bestDist2 = nc > 1 ? c[1].dist : 256;
+                const int bestLevel = F.mvKeys[bestIdx].octave, bestLevel2 = nc > 1 ? F.mvKeys[c[1].idx].octave : -1;
+                if (bestDist <= TH_HIGH) {
+                    if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;      // (skips the right half of this point too)
+                    if (bestLevel != bestLevel2 || bestDist <= nnratio * bestDist2) {
+                        F.mvpMapPoints[bestIdx] = pMP;
+                        if (F.mvLeftToRightMatch[bestIdx] != -1) {
+                            F.mvpMapPoints[F.mvLeftToRightMatch[bestIdx] + nL] = pMP;
+                            nmatches++;
+                        }
+                        nmatches++;
+                    }
+                }
+            }
+        }
+        if (qOfR[iMP] >= 0) {                                                     // :139-208
+            Cand c[2];
+            int nc = 0;
+            head(true, qOfR[iMP], c, nc);
+            if (nc == 0) continue;
+            const int bestDist = c[0].dist, bestIdx = c[0].idx, bestDist2 = nc > 1 ? c[1].dist : 256;
+            const int bestLevel = F.mvKeysRight[bestIdx].octave, bestLevel2 = nc > 1 ? F.mvKeysRight[c[1].idx].octave : -1;
+            if (bestDist <= TH_HIGH) {
+                if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+                if (F.mvRightToLeftMatch[bestIdx] != -1) {
+                    F.mvpMapPoints[F.mvRightToLeftMatch[bestIdx]] = pMP;
+                    nmatches++;
+                }
+                F.mvpMapPoints[bestIdx + nL] = pMP;
+                nmatches++;
+            }
+        }
+    }
+    return nmatches;
+}
+
 int ORBmatcherGPU::SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th, const bool bFarPoints,
                                       const float thFarPoints, const float nnratio) {
-    if (F.Nleft != -1) throw std::logic_error("ORBmatcherGPU::SearchByProjection: fisheye-stereo frames (Nleft != -1) keep the reference's host path");
+    if (F.Nleft != -1) return SearchByProjectionFisheye(F, vpMapPoints, th, bFarPoints, thFarPoints, nnratio);
     Impl& s = Scratch();
     const bool bFactor = th != 1.0;
     s.q.clear(); s.qlev.clear(); s.qdesc.clear(); s.src.clear();

@@ -67,6 +67,51 @@ int gpuhost_search_by_projection(const float* kps, const int32_t* oct, const uin
     return nmatches;
 }
 
+// same arguments and result as refcut_search_by_projection_fisheye (oracle/ref_cut_tu.cpp)
+int gpuhost_search_by_projection_fisheye(const float* kpsL, const int32_t* octL, int nL, const float* kpsR, const int32_t* octR, int nR, const uint8_t* desc,
+                                         const float* fp, const int32_t* l2r, const int32_t* r2l, const uint8_t* hasPoint, const float* scaleFactors,
+                                         int nlevels, const float* projL, const int32_t* levelL, const uint8_t* inViewL, const float* projR,
+                                         const int32_t* levelR, const uint8_t* inViewR, const uint8_t* mpDesc, int nmp, float nnratio, float th,
+                                         int32_t* matchOf) {
+    Frame* F = new Frame();
+    F->mnId = g_frameId++;
+    Frame::mnMinX = fp[0]; Frame::mnMaxX = fp[1]; Frame::mnMinY = fp[2]; Frame::mnMaxY = fp[3];
+    Frame::mfGridElementWidthInv = fp[4]; Frame::mfGridElementHeightInv = fp[5];
+    const int n = nL + nR;
+    F->N = n; F->Nleft = nL; F->Nright = nR;
+    F->mvKeys.resize(nL); F->mvKeysRight.resize(nR);
+    for (int i = 0; i < nL; i++) { F->mvKeys[i].pt.x = kpsL[2 * i]; F->mvKeys[i].pt.y = kpsL[2 * i + 1]; F->mvKeys[i].octave = octL[i]; }
+    for (int i = 0; i < nR; i++) { F->mvKeysRight[i].pt.x = kpsR[2 * i]; F->mvKeysRight[i].pt.y = kpsR[2 * i + 1]; F->mvKeysRight[i].octave = octR[i]; }
+    F->mDescriptors = to_descriptors(desc, n);
+    F->mvuRight.assign(n, -1.0f);
+    F->mvLeftToRightMatch.assign(l2r, l2r + nL);
+    F->mvRightToLeftMatch.assign(r2l, r2l + nR);
+    F->mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    MapPoint old;
+    old.nObs = 1;
+    F->mvpMapPoints.assign(n, nullptr);
+    for (int i = 0; i < n; i++) if (hasPoint && hasPoint[i]) F->mvpMapPoints[i] = &old;
+    std::vector<MapPoint> mps(nmp);
+    std::vector<MapPoint*> vp(nmp);
+    for (int j = 0; j < nmp; j++) {
+        MapPoint& m = mps[j];
+        m.mTrackProjX = projL[3 * j]; m.mTrackProjY = projL[3 * j + 1]; m.mTrackViewCos = projL[3 * j + 2];
+        m.mnTrackScaleLevel = levelL[j]; m.mbTrackInView = inViewL[j] != 0;
+        m.mTrackProjXR = projR[3 * j]; m.mTrackProjYR = projR[3 * j + 1]; m.mTrackViewCosR = projR[3 * j + 2];
+        m.mnTrackScaleLevelR = levelR[j]; m.mbTrackInViewR = inViewR[j] != 0;
+        m.mDescriptor = to_descriptors(mpDesc + (size_t)32 * j, 1);
+        m.nObs = 1;
+        vp[j] = &m;
+    }
+    const int nmatches = ORBmatcherGPU::Instance().SearchByProjection(*F, vp, th, false, 50.0f, nnratio);
+    for (int i = 0; i < n; i++) {
+        MapPoint* p = F->mvpMapPoints[i];
+        matchOf[i] = (p && p != &old) ? (int)(p - mps.data()) : -1;
+    }
+    delete F;
+    return nmatches;
+}
+
 // same arguments and result as refcut_search_by_projection_motion (oracle/ref_cut_tu.cpp)
 int gpuhost_search_by_projection_motion(const float* kps, const int32_t* oct, const float* angle, const uint8_t* desc, int n, const float* fp,
                                         const float* uRight, const uint8_t* curState, const float* scaleFactors, int nlevels, const float* Tcw,

@@ -103,6 +103,7 @@ public:
     float mfLogScaleFactor = 0;
     static float mnMinX, mnMaxX, mnMinY, mnMaxY;
     int Nleft = -1, Nright = -1;
+    std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;
 };
 
 inline int MapPoint::PredictScale(const float& currentDist, Frame* pF) {

@@ -234,3 +234,38 @@ def triangulation_scene(seed=17, levelsup=2, stereo=False, ties=False):
     k1, k2 = kf(ka, da, sc["fv_k"], T1), kf(kb, db, sc["fv_f"], T2)
     common = dict(sigma2=(sf * sf).astype(np.float32), scale_factors=sf, cam4=np.float32([458.0, 458.0, 310.0, 188.0]))
     return k1, k2, common
+
+
+def fisheye_local_points_scene(seed=41, nmp=1500):
+    """Tracking::SearchLocalPoints on a fisheye-stereo frame (Nleft != -1): the two views of a stereo pair as the two eyes, stereo partners between
+    them for a third of the key points (mvLeftToRightMatch / mvRightToLeftMatch), map points visible in the left eye, the right eye or both."""
+    left, right = synth.stereo_pair(376, 620, 4, dmax=25)
+    pe = port.PortExtractor(900, 1.2, 8)
+    _, kl, dl, _ = pe.extract(left)
+    _, kr, dr, _ = pe.extract(right)
+    nL, nR = len(kl), len(kr)
+    rng = np.random.default_rng(seed)
+    l2r, r2l = np.full(nL, -1, np.int32), np.full(nR, -1, np.int32)
+    perm = rng.permutation(min(nL, nR))[: min(nL, nR) // 3]
+    partner = rng.permutation(nR)[: len(perm)]
+    for a, b in zip(perm, partner):
+        l2r[a] = b
+        r2l[b] = a
+    w, h = 620, 376
+    fp = np.float32([0, w, 0, h, np.float32(64) / np.float32(w), np.float32(48) / np.float32(h)])
+    srcL, srcR = rng.integers(0, nL, nmp), rng.integers(0, nR, nmp)
+    proj_l = np.stack([kl["x"][srcL] + rng.normal(0, 2.5, nmp), kl["y"][srcL] + rng.normal(0, 2.5, nmp), rng.choice([0.9, 0.999, 0.9985], nmp)], 1).astype(np.float32)
+    proj_r = np.stack([kr["x"][srcR] + rng.normal(0, 2.5, nmp), kr["y"][srcR] + rng.normal(0, 2.5, nmp), rng.choice([0.9, 0.999, 0.9985], nmp)], 1).astype(np.float32)
+    level_l = np.clip(kl["octave"][srcL] + rng.integers(-1, 2, nmp), 0, 7).astype(np.int32)
+    level_r = np.clip(kr["octave"][srcR] + rng.integers(-1, 2, nmp), 0, 7).astype(np.int32)
+    level_r[rng.random(nmp) < 0.1] = -1
+    in_l = (rng.random(nmp) < 0.7).astype(np.uint8)
+    in_r = (rng.random(nmp) < 0.6).astype(np.uint8)
+    use_r = rng.random(nmp) < 0.4                                                  # descriptor close to the right-eye key point for some
+    desc = np.where(use_r[:, None], dr[srcR], dl[srcL]).astype(np.uint8)
+    desc[:, :4] ^= rng.integers(0, 256, (nmp, 4), dtype=np.uint8) & rng.integers(0, 256, (nmp, 4), dtype=np.uint8)
+    f = dict(kps_l=np.stack([kl["x"], kl["y"]], 1).astype(np.float32), oct_l=kl["octave"].astype(np.int32),
+             kps_r=np.stack([kr["x"], kr["y"]], 1).astype(np.float32), oct_r=kr["octave"].astype(np.int32), desc=np.concatenate([dl, dr]), fp=fp, l2r=l2r, r2l=r2l,
+             has_point=(rng.random(nL + nR) < 0.2).astype(np.uint8), scale_factors=pe.scale_factors)
+    mp = dict(proj_l=proj_l, level_l=level_l, in_view_l=in_l, proj_r=proj_r, level_r=level_r, in_view_r=in_r, desc=desc)
+    return f, mp

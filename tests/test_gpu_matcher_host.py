@@ -14,7 +14,7 @@ from oracle import port, ref
 from orb_slam3_ros_b200 import capi, synth
 from orb_slam3_ros_b200.extractor import ORBextractor
 from orb_slam3_ros_b200.matcher import ORBmatcher
-from scenes import bow_scene, fuse_scene, init_scene, local_points_scene, motion_scene, reloc_scene, sim3_scene, triangulation_scene
+from scenes import bow_scene, fisheye_local_points_scene, fuse_scene, init_scene, local_points_scene, motion_scene, reloc_scene, sim3_scene, triangulation_scene
 
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
@@ -31,6 +31,8 @@ def declare(lib):
     lib.gpuhost_search_by_projection.restype = C.c_int
     lib.gpuhost_search_by_projection.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]
+    lib.gpuhost_search_by_projection_fisheye.restype = C.c_int
+    lib.gpuhost_search_by_projection_fisheye.argtypes = ref.FISHEYE_ARGTYPES
     lib.gpuhost_search_by_projection_motion.restype = C.c_int
     lib.gpuhost_search_by_projection_motion.argtypes = [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int] + \
         [C.c_void_p] * 7 + [C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p]
@@ -376,3 +378,27 @@ def test_best2_csr_with_device_resident_train_descriptors():
     out = np.zeros((nq, 4), np.int32)
     capi.check(lib.orbb_best2_csr_dev(m._m, _p(q), nq, desc_dev, n, _p(cand), _p(rowptr), 256, _p(out)), m._m, matcher=True)
     assert np.array_equal(out, want)
+
+
+def fisheye_local_points_case(host, seed, th):
+    """ORBmatcher::SearchByProjection(F, vpMapPoints, th) on a fisheye-stereo frame (Nleft != -1, ORBmatcher.cc:43-213 with its right-eye half
+    :139-208).  Shared with tests/test_matcher_host_cpu.py, which is where it runs for now: the branch was written after this round's GPU budget
+    was spent, so it is pinned to the reference over the CPU test double of the scans only (the scans themselves are the GPU-verified entry
+    point of every other case in this file)."""
+    f, mp = fisheye_local_points_scene(seed)
+    nm_ref, match_ref = ref.search_by_projection_fisheye(f, mp, 0.8, th)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    kl, ol, kr, orr, d, fp = f32(f["kps_l"]), i32(f["oct_l"]), f32(f["kps_r"]), i32(f["oct_r"]), u8(f["desc"]), f32(f["fp"])
+    l2r, r2l, hp, sf = i32(f["l2r"]), i32(f["r2l"]), u8(f["has_point"]), f32(f["scale_factors"])
+    pl, ll, il, pr, lr, ir, md = f32(mp["proj_l"]), i32(mp["level_l"]), u8(mp["in_view_l"]), f32(mp["proj_r"]), i32(mp["level_r"]), u8(mp["in_view_r"]), u8(mp["desc"])
+    match = np.full(len(kl) + len(kr), -1, np.int32)
+    r0 = host.gpuhost_rescans()
+    nm = host.gpuhost_search_by_projection_fisheye(_p(kl), _p(ol), len(kl), _p(kr), _p(orr), len(kr), _p(d), _p(fp), _p(l2r), _p(r2l), _p(hp), _p(sf), len(sf),
+                                                   _p(pl), _p(ll), _p(il), _p(pr), _p(lr), _p(ir), _p(md), len(pl), 0.8, th, _p(match))
+    assert nm == nm_ref and np.array_equal(match, match_ref)
+    nL = len(kl)
+    assert (match_ref[:nL] >= 0).sum() > 100 and (match_ref[nL:] >= 0).sum() > 100
+    if th >= 3:
+        assert host.gpuhost_rescans() > r0      # wide windows: some four-candidate lists are used up by earlier matches
