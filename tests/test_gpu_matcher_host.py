@@ -380,11 +380,11 @@ def test_best2_csr_with_device_resident_train_descriptors():
     assert np.array_equal(out, want)
 
 
-def fisheye_local_points_case(host, seed, th):
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref (the reference's own object code) is not built")
+@pytest.mark.parametrize("seed,th", [(41, 1.0), (42, 3.0), (43, 1.0)])
+def test_search_local_points_fisheye_stereo_equals_reference(host, seed, th):
     """ORBmatcher::SearchByProjection(F, vpMapPoints, th) on a fisheye-stereo frame (Nleft != -1, ORBmatcher.cc:43-213 with its right-eye half
-    :139-208).  Shared with tests/test_matcher_host_cpu.py, which is where it runs for now: the branch was written after this round's GPU budget
-    was spent, so it is pinned to the reference over the CPU test double of the scans only (the scans themselves are the GPU-verified entry
-    point of every other case in this file)."""
+    :139-208): two key point sets with their own grids, stereo partners claimed across the eyes"""
     f, mp = fisheye_local_points_scene(seed)
     nm_ref, match_ref = ref.search_by_projection_fisheye(f, mp, 0.8, th)
     f32 = lambda a: np.ascontiguousarray(a, np.float32)

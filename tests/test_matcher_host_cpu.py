@@ -85,4 +85,4 @@ def test_search_for_triangulation(host_cpu, stereo, only_stereo, coarse, check, 
 
 @pytest.mark.parametrize("seed,th", [(41, 1.0), (42, 3.0), (43, 1.0)])
 def test_search_local_points_fisheye_stereo(host_cpu, seed, th):
-    gpu_cases.fisheye_local_points_case(host_cpu, seed, th)
+    gpu_cases.test_search_local_points_fisheye_stereo_equals_reference(host_cpu, seed, th)
