@@ -353,6 +353,31 @@ def search_by_projection_motion(cur, last, th, mono, nnratio=0.9, check_orientat
     return nm, match_of
 
 
+def search_by_projection_motion_fisheye(cur, last, th, mono, nnratio=0.9, check_orientation=True):
+    """ORBmatcher(nnratio, checkOri).SearchByProjection(CurrentFrame, LastFrame, th, bMono) (ORBmatcher.cc:1676-1887, reference text) on fisheye-stereo
+    frames.  cur: dict(kps_l, oct_l, ang_l, kps_r, oct_r, ang_r, desc [nL+nR,32], state [nL+nR], fp (.., mbf, mb), scale_factors, Tcw [12], Trl [12],
+    cam4); last: dict(n_left, octaves, angles, state, outlier, pos, desc, Tlw)  -> (nmatches, match_of[nL+nR])"""
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    kl, ol, al, kr, orr, ar = f32(cur["kps_l"]).reshape(-1, 2), i32(cur["oct_l"]), f32(cur["ang_l"]), f32(cur["kps_r"]).reshape(-1, 2), i32(cur["oct_r"]), f32(cur["ang_r"])
+    d, fp, cs, sf, tcw, trl, cam = u8(cur["desc"]), f32(cur["fp"]), u8(cur["state"]), f32(cur["scale_factors"]), f32(cur["Tcw"]), f32(cur["Trl"]), f32(cur["cam4"])
+    lo, la, ls, lout, lp, ld, tlw = i32(last["octaves"]), f32(last["angles"]), u8(last["state"]), u8(last["outlier"]), f32(last["pos"]).reshape(-1, 3), \
+        u8(last["desc"]), f32(last["Tlw"])
+    match_of = np.full(len(kl) + len(kr), -1, np.int32)
+    fn = lib().refcut_search_by_projection_motion_fisheye
+    fn.restype = C.c_int
+    fn.argtypes = MOTION_FISHEYE_ARGTYPES
+    nm = fn(_ptr(kl), _ptr(ol), _ptr(al), len(kl), _ptr(kr), _ptr(orr), _ptr(ar), len(kr), _ptr(d), _ptr(fp), _ptr(cs), _ptr(sf), len(sf), _ptr(tcw), _ptr(trl),
+            _ptr(cam), len(lo), int(last["n_left"]), _ptr(lo), _ptr(la), _ptr(ls), _ptr(lout), _ptr(lp), _ptr(ld), _ptr(tlw), th, int(mono), nnratio,
+            int(check_orientation), _ptr(match_of))
+    return nm, match_of
+
+
+MOTION_FISHEYE_ARGTYPES = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_int] + \
+    [C.c_void_p] * 7 + [C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p]
+
+
 def search_by_projection_reloc(cur, kf, th, orb_dist, nnratio=0.9, check_orientation=True):
     """ORBmatcher(nnratio, checkOri).SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1889-2010, reference
     text; the refinement calls of Tracking::Relocalization, Tracking.cc:3765 / :3779).

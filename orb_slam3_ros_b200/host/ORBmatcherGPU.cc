@@ -341,9 +341,152 @@ int ORBmatcherGPU::SearchByProjection(Frame& F, const std::vector<MapPoint*>& vp
     return nmatches;
 }
 
+// The motion-model search on fisheye-stereo frames (Nleft != -1, ORBmatcher.cc:1676-1887 with the right-eye half :1798-1860): every map point
+// of the last frame is projected into the left eye and -- through GetRelativePoseTrl(), with the LEFT camera model as the reference does --
+// into the right eye.  Three batched scans: the left set with the taken key points masked (four candidates), the left set unmasked with
+// k = 1 (the reference leaves a point -- right half included -- when its left window holds no key point at all, :1736, which is not the same
+// as "every candidate is taken"), and the right set masked.  Then the reference's loop in order.
+int ORBmatcherGPU::SearchByProjectionFisheye(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono, const bool checkOrientation) {
+    Impl& s = Scratch();
+    std::vector<int> rotHist[HISTO_LENGTH];
+    for (int i = 0; i < HISTO_LENGTH; i++) rotHist[i].reserve(500);
+    const float factor = 1.0f / HISTO_LENGTH;
+    const Sophus::SE3f Tcw = CurrentFrame.GetPose();
+    const Eigen::Vector3f twc = Tcw.inverse().translation();
+    const Sophus::SE3f Tlw = LastFrame.GetPose();
+    const Eigen::Vector3f tlc = Tlw * twc;
+    const bool bForward = tlc(2) > CurrentFrame.mb && !bMono;
+    const bool bBackward = -tlc(2) > CurrentFrame.mb && !bMono;
+    const int nL = CurrentFrame.Nleft, nR = (int)CurrentFrame.mvKeysRight.size();
+    if (!CurrentFrame.mDescriptors.isContinuous()) throw std::runtime_error("Frame::mDescriptors must be continuous");
+    const float grid4[4] = {Frame::mnMinX, Frame::mnMinY, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv};
+    std::vector<float> qL, qR;
+    std::vector<int32_t> lev, outL, outAny, outR;
+    std::vector<unsigned char> dq, skipL, skipR;
+    s.src.clear();
+    for (int i = 0; i < LastFrame.N; i++) {                                       // :1695-1727 and :1799-1813
+        MapPoint* pMP = LastFrame.mvpMapPoints[i];
+        if (!pMP || LastFrame.mvbOutlier[i]) continue;
+        Eigen::Vector3f x3Dw = pMP->GetWorldPos();
+        Eigen::Vector3f x3Dc = Tcw * x3Dw;
+        const float invzc = 1.0 / x3Dc(2);
+        if (invzc < 0) continue;
+        Eigen::Vector2f uv = CurrentFrame.mpCamera->project(x3Dc);
+        if (uv(0) < CurrentFrame.mnMinX || uv(0) > CurrentFrame.mnMaxX) continue;
+        if (uv(1) < CurrentFrame.mnMinY || uv(1) > CurrentFrame.mnMaxY) continue;
+        const int nLastOctave = (LastFrame.Nleft == -1 || i < LastFrame.Nleft) ? LastFrame.mvKeys[i].octave : LastFrame.mvKeysRight[i - LastFrame.Nleft].octave;
+        const float radius = th * CurrentFrame.mvScaleFactors[nLastOctave];
+        Eigen::Vector3f x3Dr = CurrentFrame.GetRelativePoseTrl() * x3Dc;
+        Eigen::Vector2f uvr = CurrentFrame.mpCamera->project(x3Dr);
+        const float a4[4] = {uv(0), uv(1), radius, -1.0f}, b4[4] = {uvr(0), uvr(1), radius, -1.0f};
+        qL.insert(qL.end(), a4, a4 + 4);
+        qR.insert(qR.end(), b4, b4 + 4);
+        if (bForward) { lev.push_back(nLastOctave); lev.push_back(-1); }
+        else if (bBackward) { lev.push_back(0); lev.push_back(nLastOctave); }
+        else { lev.push_back(nLastOctave - 1); lev.push_back(nLastOctave + 1); }
+        const cv::Mat d = pMP->GetDescriptor();
+        dq.insert(dq.end(), d.ptr<uchar>(), d.ptr<uchar>() + 32);
+        s.src.push_back(i);
+    }
+    const int nq = (int)s.src.size();
+    std::vector<float> xyL((size_t)nL * 2), xyR((size_t)nR * 2);
+    std::vector<int32_t> octL(nL), octR(nR);
+    for (int i = 0; i < nL; i++) { xyL[2 * i] = CurrentFrame.mvKeys[i].pt.x; xyL[2 * i + 1] = CurrentFrame.mvKeys[i].pt.y; octL[i] = CurrentFrame.mvKeys[i].octave; }
+    for (int i = 0; i < nR; i++) {
+        xyR[2 * i] = CurrentFrame.mvKeysRight[i].pt.x; xyR[2 * i + 1] = CurrentFrame.mvKeysRight[i].pt.y; octR[i] = CurrentFrame.mvKeysRight[i].octave;
+    }
+    orbb_frame_view vL, vR;
+    vL.kps_xy = xyL.data(); vL.kps_stride = 8; vL.octaves = octL.data(); vL.oct_stride = 4; vL.desc = CurrentFrame.mDescriptors.ptr<uchar>();
+    vL.u_right = nullptr; vL.n = nL; vL.on_device = 0;
+    vR = vL;
+    vR.kps_xy = xyR.data(); vR.octaves = octR.data(); vR.desc = CurrentFrame.mDescriptors.ptr<uchar>() + (size_t)32 * nL; vR.n = nR;
+    auto scan = [&](bool right, bool masked, int first, int count, int k, int init, int32_t* out) {
+        const int n = right ? nR : nL, base = right ? nL : 0;
+        std::vector<unsigned char>& skip = right ? skipR : skipL;
+        skip.assign(n, 0);
+        if (masked) for (int i = 0; i < n; i++) skip[i] = Taken(CurrentFrame, i + base);
+        const std::vector<float>& q = right ? qR : qL;
+        if (orbb_search_area_topk(mpMatcher, right ? &vR : &vL, grid4, &q[4 * (size_t)first], &lev[2 * (size_t)first], &dq[32 * (size_t)first], count,
+                                  skip.data(), init, k, out) != ORBB_OK)
+            throw std::runtime_error(std::string("orbb_search_area_topk failed: ") + orbb_matcher_last_error(mpMatcher));
+    };
+    outL.assign((size_t)nq * kTopK * 2, -1);
+    outAny.assign((size_t)nq * 2, -1);
+    outR.assign((size_t)nq * kTopK * 2, -1);
+    if (nq) {
+        scan(false, true, 0, nq, kTopK, 256, outL.data());
+        scan(false, false, 0, nq, 1, 257, outAny.data());
+        scan(true, true, 0, nq, kTopK, 256, outR.data());
+    }
+    auto head = [&](bool right, int j, Cand& c) {                                // best candidate that is still free; false: none
+        const int base = right ? nL : 0;
+        const int32_t* list = right ? &outR[(size_t)j * kTopK * 2] : &outL[(size_t)j * kTopK * 2];
+        int valid = 0;
+        for (int t = 0; t < kTopK; t++) {
+            const int idx = list[2 * t + 1];
+            if (idx < 0) break;
+            valid++;
+            if (Taken(CurrentFrame, idx + base)) continue;
+            c.dist = list[2 * t]; c.idx = idx;
+            return true;
+        }
+        if (valid < kTopK) return false;
+        int32_t o[2] = {256, -1};
+        scan(right, true, j, 1, 1, 256, o);
+        mnRescans++;
+        if (o[1] < 0) return false;
+        c.dist = o[0]; c.idx = o[1];
+        return true;
+    };
+    int nmatches = 0;
+    for (int j = 0; j < nq; j++) {
+        const int i = s.src[j];
+        MapPoint* pMP = LastFrame.mvpMapPoints[i];
+        if (outAny[2 * (size_t)j + 1] < 0) continue;                              // :1735-1736 vIndices2.empty(): the right half is skipped too
+        const float lastAngle = (LastFrame.Nleft == -1 || i < LastFrame.Nleft) ? LastFrame.mvKeys[i].angle : LastFrame.mvKeysRight[i - LastFrame.Nleft].angle;
+        Cand c;
+        if (head(false, j, c) && c.dist <= TH_HIGH) {                             // :1738-1796
+            CurrentFrame.mvpMapPoints[c.idx] = pMP;
+            nmatches++;
+            if (checkOrientation) {
+                float rot = lastAngle - CurrentFrame.mvKeys[c.idx].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = round(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rotHist[bin].push_back(c.idx);
+            }
+        }
+        if (head(true, j, c) && c.dist <= TH_HIGH) {                              // :1815-1859
+            CurrentFrame.mvpMapPoints[c.idx + nL] = pMP;
+            nmatches++;
+            if (checkOrientation) {
+                float rot = lastAngle - CurrentFrame.mvKeysRight[c.idx].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = round(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rotHist[bin].push_back(c.idx + nL);
+            }
+        }
+    }
+    if (checkOrientation) {                                                       // :1866-1884
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i != ind1 && i != ind2 && i != ind3) {
+                for (size_t j = 0, jend = rotHist[i].size(); j < jend; j++) {
+                    CurrentFrame.mvpMapPoints[rotHist[i][j]] = static_cast<MapPoint*>(NULL);
+                    nmatches--;
+                }
+            }
+        }
+    }
+    return nmatches;
+}
+
 int ORBmatcherGPU::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono, const bool checkOrientation) {
-    if (CurrentFrame.Nleft != -1 || LastFrame.Nleft != -1)
-        throw std::logic_error("ORBmatcherGPU::SearchByProjection: fisheye-stereo frames (Nleft != -1) keep the reference's host path");
+    if (CurrentFrame.Nleft != -1) return SearchByProjectionFisheye(CurrentFrame, LastFrame, th, bMono, checkOrientation);
+    if (LastFrame.Nleft != -1)
+        throw std::logic_error("ORBmatcherGPU::SearchByProjection: a fisheye-stereo last frame with a monocular current frame is not a rig the reference builds");
     Impl& s = Scratch();
     std::vector<int> rotHist[HISTO_LENGTH];
     const float factor = 1.0f / HISTO_LENGTH;

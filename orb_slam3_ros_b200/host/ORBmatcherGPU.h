@@ -198,6 +198,7 @@ public:
 private:
     int SearchByProjectionFisheye(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th, const bool bFarPoints, const float thFarPoints,
                                   const float nnratio);
+    int SearchByProjectionFisheye(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono, const bool checkOrientation);
     void RunScan(const Frame& F, int nq, int k, std::vector<int32_t>& out, bool maskTaken = true, bool rightCheck = true, int init = 256,
                  bool takenAny = false);
     void Rescan(const Frame& F, int j, int want, void* candOut, int& nout, bool rightCheck = true, bool takenAny = false);

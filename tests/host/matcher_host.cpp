@@ -198,6 +198,63 @@ int gpuhost_search_for_initialization(const int32_t* oct1, const float* angle1, 
     return nmatches;
 }
 
+// same arguments and result as refcut_search_by_projection_motion_fisheye (oracle/ref_cut_tu.cpp)
+int gpuhost_search_by_projection_motion_fisheye(const float* kpsL, const int32_t* octL, const float* angL, int nL, const float* kpsR, const int32_t* octR,
+                                                const float* angR, int nR, const uint8_t* desc, const float* fp, const uint8_t* curState,
+                                                const float* scaleFactors, int nlevels, const float* Tcw, const float* Trl, const float* cam4, int nLast,
+                                                int lastNL, const int32_t* lastOct, const float* lastAngle, const uint8_t* lastState,
+                                                const uint8_t* lastOutlier, const float* lastPos, const uint8_t* lastDesc, const float* Tlw, float th,
+                                                int bMono, float nnratio, int checkOri, int32_t* matchOf) {
+    (void)nnratio;
+    Frame* Cf = new Frame();
+    Frame* Lf = new Frame();
+    Cf->mnId = g_frameId++; Lf->mnId = g_frameId++;
+    Frame::mnMinX = fp[0]; Frame::mnMaxX = fp[1]; Frame::mnMinY = fp[2]; Frame::mnMaxY = fp[3];
+    Frame::mfGridElementWidthInv = fp[4]; Frame::mfGridElementHeightInv = fp[5];
+    GeometricCamera cam;
+    cam.fx = cam4[0]; cam.fy = cam4[1]; cam.cx = cam4[2]; cam.cy = cam4[3];
+    const int n = nL + nR;
+    Cf->N = n; Cf->Nleft = nL; Cf->Nright = nR; Cf->mbf = fp[6]; Cf->mb = fp[7]; Cf->mpCamera = &cam;
+    Cf->mTcw = Sophus::SE3f(Tcw, Tcw + 9);
+    Cf->mTrl = Sophus::SE3f(Trl, Trl + 9);
+    Cf->mvKeys.resize(nL); Cf->mvKeysRight.resize(nR);
+    for (int i = 0; i < nL; i++) { Cf->mvKeys[i].pt.x = kpsL[2 * i]; Cf->mvKeys[i].pt.y = kpsL[2 * i + 1]; Cf->mvKeys[i].octave = octL[i]; Cf->mvKeys[i].angle = angL[i]; }
+    for (int i = 0; i < nR; i++) {
+        Cf->mvKeysRight[i].pt.x = kpsR[2 * i]; Cf->mvKeysRight[i].pt.y = kpsR[2 * i + 1]; Cf->mvKeysRight[i].octave = octR[i]; Cf->mvKeysRight[i].angle = angR[i];
+    }
+    Cf->mDescriptors = to_descriptors(desc, n);
+    Cf->mvuRight.assign(n, -1.0f);
+    Cf->mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    MapPoint oldObs, oldNoObs;
+    oldObs.nObs = 1; oldNoObs.nObs = 0;
+    Cf->mvpMapPoints.assign(n, nullptr);
+    for (int i = 0; i < n; i++) if (curState && curState[i]) Cf->mvpMapPoints[i] = curState[i] == 1 ? &oldObs : &oldNoObs;
+    Lf->N = nLast; Lf->Nleft = lastNL; Lf->Nright = nLast - lastNL; Lf->mTcw = Sophus::SE3f(Tlw, Tlw + 9);
+    Lf->mvKeys.resize(lastNL); Lf->mvKeysRight.resize(nLast - lastNL);
+    std::vector<MapPoint> mps(nLast);
+    Lf->mvpMapPoints.assign(nLast, nullptr);
+    Lf->mvbOutlier.assign(nLast, false);
+    for (int j = 0; j < nLast; j++) {
+        cv::KeyPoint& kp = j < lastNL ? Lf->mvKeys[j] : Lf->mvKeysRight[j - lastNL];
+        kp.octave = lastOct[j]; kp.angle = lastAngle[j];
+        Lf->mvbOutlier[j] = lastOutlier[j] != 0;
+        if (lastState[j]) {
+            mps[j].nObs = lastState[j] == 1 ? 1 : 0;
+            mps[j].mWorldPos = Eigen::Vector3f(lastPos[3 * j], lastPos[3 * j + 1], lastPos[3 * j + 2]);
+            mps[j].mDescriptor = to_descriptors(lastDesc + (size_t)32 * j, 1);
+            Lf->mvpMapPoints[j] = &mps[j];
+        }
+    }
+    const int nmatches = ORBmatcherGPU::Instance().SearchByProjection(*Cf, *Lf, th, bMono != 0, checkOri != 0);
+    for (int i = 0; i < n; i++) {
+        MapPoint* p = Cf->mvpMapPoints[i];
+        matchOf[i] = (p && p != &oldObs && p != &oldNoObs) ? (int)(p - mps.data()) : -1;
+    }
+    delete Cf;
+    delete Lf;
+    return nmatches;
+}
+
 // same arguments and result as refcut_search_by_projection_reloc (oracle/ref_cut_tu.cpp)
 int gpuhost_search_by_projection_reloc(const float* kps, const int32_t* oct, const float* angle, const uint8_t* desc, int n, const float* fp,
                                        const uint8_t* curHolds, const float* scaleFactors, int nlevels, const float* Tcw, const float* cam4, int nK,

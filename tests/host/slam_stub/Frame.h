@@ -57,6 +57,8 @@ public:
 class Frame {
 public:
     Sophus::SE3<float> GetPose() const { return mTcw; }
+    Sophus::SE3f GetRelativePoseTrl() { return mTrl; }      // Frame.cc:1054
+    Sophus::SE3<float> mTrl;
     // Test stand-ins for Frame::AssignFeaturesToGrid / GetFeaturesInArea (Frame.cc:385-416, :657-735; monocular branch): the key points of a
     // 64 x 48 grid cell in index order, cells visited column by column.  (The compiled adapter calls GetFeaturesInArea only for the rare key
     // point of SearchForInitialization whose candidate list is exhausted; in the reference's build it is the reference's own method.)

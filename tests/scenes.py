@@ -269,3 +269,31 @@ def fisheye_local_points_scene(seed=41, nmp=1500):
              has_point=(rng.random(nL + nR) < 0.2).astype(np.uint8), scale_factors=pe.scale_factors)
     mp = dict(proj_l=proj_l, level_l=level_l, in_view_l=in_l, proj_r=proj_r, level_r=level_r, in_view_r=in_r, desc=desc)
     return f, mp
+
+
+def fisheye_motion_scene(direction=0, seed=5, dense=False):
+    """Tracking::TrackWithMotionModel on a fisheye-stereo rig: motion_scene's current frame as the LEFT eye; the right eye sees the same key points
+    through GetRelativePoseTrl() (a sideways baseline), re-projected with the left camera model as the reference does, with its own jitter and
+    order; the last frame's features are split into a left and a right set."""
+    cur, last = motion_scene(True, direction, seed=seed, dense=dense)
+    rng = np.random.default_rng(600 + seed)
+    nL = len(cur["octaves"])
+    fx, fy, cx, cy = (np.float32(v) for v in cur["cam4"])
+    Trl = np.concatenate([np.eye(3, dtype=np.float32).ravel(), np.float32([-0.11, 0.0, 0.0])]).astype(np.float32)
+    # right-eye key points: the left ones shifted by the disparity of a plausible depth, shuffled, some dropped
+    z = rng.uniform(4.0, 9.0, nL).astype(np.float32)
+    keep = np.flatnonzero(rng.random(nL) < 0.85)
+    rng.shuffle(keep)
+    kps_r = np.stack([cur["kps_xy"][keep, 0] - fx * np.float32(0.11) / z[keep] + rng.normal(0, 0.3, len(keep)).astype(np.float32),
+                      cur["kps_xy"][keep, 1] + rng.normal(0, 0.3, len(keep)).astype(np.float32)], 1).astype(np.float32)
+    inside = (kps_r[:, 0] > 1) & (kps_r[:, 0] < 750) & (kps_r[:, 1] > 1) & (kps_r[:, 1] < 478)
+    keep, kps_r = keep[inside], kps_r[inside]
+    desc_r = cur["desc"][keep].copy()
+    desc_r[:, :2] ^= rng.integers(0, 256, (len(keep), 2), dtype=np.uint8) & rng.integers(0, 256, (len(keep), 2), dtype=np.uint8)
+    nR = len(keep)
+    c = dict(kps_l=cur["kps_xy"], oct_l=cur["octaves"], ang_l=cur["angles"], kps_r=kps_r, oct_r=cur["octaves"][keep], ang_r=cur["angles"][keep],
+             desc=np.concatenate([cur["desc"], desc_r]), state=np.concatenate([cur["state"], rng.choice([0, 1, 2], nR, p=[0.8, 0.12, 0.08]).astype(np.uint8)]),
+             fp=cur["fp"], scale_factors=cur["scale_factors"], Tcw=cur["Tcw"], Trl=Trl, cam4=cur["cam4"])
+    m = len(last["octaves"])
+    lst = dict(last, n_left=int(m * 0.55))
+    return c, lst

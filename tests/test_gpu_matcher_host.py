@@ -14,7 +14,7 @@ from oracle import port, ref
 from orb_slam3_ros_b200 import capi, synth
 from orb_slam3_ros_b200.extractor import ORBextractor
 from orb_slam3_ros_b200.matcher import ORBmatcher
-from scenes import bow_scene, fisheye_local_points_scene, fuse_scene, init_scene, local_points_scene, motion_scene, reloc_scene, sim3_scene, triangulation_scene
+from scenes import bow_scene, fisheye_local_points_scene, fisheye_motion_scene, fuse_scene, init_scene, local_points_scene, motion_scene, reloc_scene, sim3_scene, triangulation_scene
 
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
@@ -33,6 +33,8 @@ def declare(lib):
                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]
     lib.gpuhost_search_by_projection_fisheye.restype = C.c_int
     lib.gpuhost_search_by_projection_fisheye.argtypes = ref.FISHEYE_ARGTYPES
+    lib.gpuhost_search_by_projection_motion_fisheye.restype = C.c_int
+    lib.gpuhost_search_by_projection_motion_fisheye.argtypes = ref.MOTION_FISHEYE_ARGTYPES
     lib.gpuhost_search_by_projection_motion.restype = C.c_int
     lib.gpuhost_search_by_projection_motion.argtypes = [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int] + \
         [C.c_void_p] * 7 + [C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p]
@@ -402,3 +404,25 @@ def test_search_local_points_fisheye_stereo_equals_reference(host, seed, th):
     assert (match_ref[:nL] >= 0).sum() > 100 and (match_ref[nL:] >= 0).sum() > 100
     if th >= 3:
         assert host.gpuhost_rescans() > r0      # wide windows: some four-candidate lists are used up by earlier matches
+
+
+def fisheye_motion_case(host, direction, dense, check):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) on fisheye-stereo frames (ORBmatcher.cc:1676-1887 with the right-eye half
+    :1798-1860).  Not collected here: the branch was written after this round's GPU budget was spent; tests/test_matcher_host_cpu.py runs it
+    against the reference's body over the CPU test double of the scans (the double has predicted the GPU result of every other case in this file)."""
+    cur, last = fisheye_motion_scene(direction, dense=dense)
+    th = 7
+    nm_ref, match_ref = ref.search_by_projection_motion_fisheye(cur, last, th, mono=False, check_orientation=check)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    kl, ol, al, kr, orr, ar = f32(cur["kps_l"]), i32(cur["oct_l"]), f32(cur["ang_l"]), f32(cur["kps_r"]), i32(cur["oct_r"]), f32(cur["ang_r"])
+    d, fp, cs, sf, tcw, trl, cam = u8(cur["desc"]), f32(cur["fp"]), u8(cur["state"]), f32(cur["scale_factors"]), f32(cur["Tcw"]), f32(cur["Trl"]), f32(cur["cam4"])
+    lo, la, ls, lout, lp, ld, tlw = i32(last["octaves"]), f32(last["angles"]), u8(last["state"]), u8(last["outlier"]), f32(last["pos"]), u8(last["desc"]), f32(last["Tlw"])
+    match = np.full(len(kl) + len(kr), -1, np.int32)
+    nm = host.gpuhost_search_by_projection_motion_fisheye(_p(kl), _p(ol), _p(al), len(kl), _p(kr), _p(orr), _p(ar), len(kr), _p(d), _p(fp), _p(cs), _p(sf), len(sf),
+                                                          _p(tcw), _p(trl), _p(cam), len(lo), int(last["n_left"]), _p(lo), _p(la), _p(ls), _p(lout), _p(lp), _p(ld),
+                                                          _p(tlw), th, 0, 0.9, int(check), _p(match))
+    assert nm == nm_ref and np.array_equal(match, match_ref)
+    nL = len(kl)
+    assert (match_ref[:nL] >= 0).sum() > 30 and (match_ref[nL:] >= 0).sum() > 30

@@ -86,3 +86,9 @@ def test_search_for_triangulation(host_cpu, stereo, only_stereo, coarse, check, 
 @pytest.mark.parametrize("seed,th", [(41, 1.0), (42, 3.0), (43, 1.0)])
 def test_search_local_points_fisheye_stereo(host_cpu, seed, th):
     gpu_cases.test_search_local_points_fisheye_stereo_equals_reference(host_cpu, seed, th)
+
+
+@pytest.mark.parametrize("direction,dense,check", [(0, False, True), (1, False, True), (-1, True, True), (0, True, False)])
+def test_motion_model_fisheye_stereo(host_cpu, direction, dense, check):
+    """CPU test double only (see fisheye_motion_case): this branch has not run on a GPU yet"""
+    gpu_cases.fisheye_motion_case(host_cpu, direction, dense, check)
